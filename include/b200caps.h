@@ -1,0 +1,229 @@
+/* b200caps C ABI -- the drop-in boundary of the B200-native training step.
+ *
+ * The reference (AKASH2907/pi-consistency-activity-detection) has no FFI: its seam is the
+ * Python module surface.  The Python mirrors of those modules
+ * (pi-consistency-activity-detection_b200/{models,utils}) call ONLY the entry points below,
+ * through ctypes.  Each entry point names the reference call site it replaces.
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 invalid argument (message via b2c_last_error()),
+ *     >0 a cudaError_t.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.  The library never
+ *     allocates or frees tensor memory; the caller owns every buffer.
+ *   - all work is enqueued on the given stream; no internal synchronisation, no host
+ *     callbacks (CUDA-graph capturable).
+ *   - activations are channels-last (N,T,H,W,C) bf16 "views": base pointer, row stride in
+ *     elements (>= C), channel offset -- so concatenations are written in place.
+ */
+#ifndef B200CAPS_H
+#define B200CAPS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b2c_stream_t; /* cudaStream_t */
+
+const char* b2c_last_error(void);
+int b2c_version(void);
+/* number of kernels launched by this library since process start (bench.py "gpu_launches") */
+long long b2c_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Generalised implicit-GEMM convolution on tcgen05 tensor cores (TMEM accumulators).
+ *   out[n, q*so + po, co] = epilogue( sum_{tap, ci} in[n, q*si + d_tap, ci] * w[co][tap][ci] )
+ * One descriptor covers: Conv3d/Conv2d fprop (pytorch_i3d.py:115, capsules_ucf101.py:44-45,
+ * :490,:497,:501), stride-1 dgrad (flipped taps), ConvTranspose fprop by output-parity class
+ * (capsules_ucf101.py:486,495,499,504,509), strided-conv dgrad and ConvTranspose dgrad.
+ * taps: int32 per tap, signed bytes (dt | dh<<8 | dw<<16).
+ * weights: bf16 [Cout][ntaps*Cin] (K-major), produced by b2c_pack_weights.
+ * Requirements: Cin % 8 == 0, Cout % 8 == 0, channel offsets % 8 == 0, row strides % 8 == 0.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  const int32_t* taps; /* [ntaps] */
+  const void* w;       /* bf16 [Cout][ntaps*Cin] */
+  int32_t ntaps;
+  int32_t Qt, Qh, Qw;       /* GEMM-M grid of this class */
+  int32_t po_t, po_h, po_w; /* output offset of this class */
+  int32_t pad_;
+} b2c_conv_class;
+
+typedef struct {
+  const void* in;        /* bf16 */
+  void* out;             /* bf16 or fp32 */
+  const float* bias;     /* [Cout] or NULL */
+  const float* scale_nc; /* [N][Cout] per-sample channel scale (Dropout3d mask) or NULL */
+  int64_t in_row_stride, out_row_stride;
+  int32_t in_c_off, out_c_off, Cin, Cout;
+  int32_t N, Ti, Hi, Wi, To, Ho, Wo;
+  int32_t si_t, si_h, si_w, so_t, so_h, so_w;
+  int32_t out_fp32;     /* 0: bf16 output, 1: fp32 output */
+  int32_t relu;         /* apply ReLU */
+  int32_t sigmoid_from; /* apply sigmoid to output channels >= this (PrimaryCaps 'a'), <0: none */
+  int32_t accumulate;   /* out += result (gradient accumulation) */
+  int32_t bn_tile;      /* output-channel tile per CTA; 0 = auto */
+  int32_t nclass;
+  b2c_conv_class cls[8];
+} b2c_conv_desc;
+
+int b2c_conv_fprop(const b2c_conv_desc* desc_host, b2c_stream_t stream);
+
+/* wgrad: dw[pc*s_p + gc*s_g + wtap[tap]] (+)= sum_q g[n, q*sg + d_tap, gc] * p[n, q*sp + pp, pc]
+ * (g: tensor that is gathered through the taps, p: tensor read at plain positions).
+ * Replaces cuDNN wgrad for every conv / transposed conv of the step (loss.backward(),
+ * main_ucf101.py:183).  dw must be zeroed by the caller when nsplit > 1 or accumulate. */
+typedef struct {
+  const void* g;
+  const void* p;
+  float* dw;
+  const int32_t* taps; /* [ntaps] */
+  const int32_t* wtap; /* [ntaps] element offset of the tap inside dw */
+  int64_t g_row_stride, p_row_stride, s_p, s_g;
+  int32_t g_c_off, p_c_off, Cg, Cp, Cg_real;
+  int32_t N, Tg, Hg, Wg, Tp, Hp, Wp;
+  int32_t Qt, Qh, Qw;
+  int32_t sg_t, sg_h, sg_w, sp_t, sp_h, sp_w, pp_t, pp_h, pp_w;
+  int32_t ntaps;
+  int32_t bn_tile; /* 0 = auto */
+  int32_t nsplit;  /* 0 = auto */
+  int32_t atomic;  /* 1: atomicAdd into dw, 0: plain store (only legal when nsplit==1) */
+} b2c_wgrad_desc;
+
+int b2c_conv_wgrad(const b2c_wgrad_desc* desc_host, b2c_stream_t stream);
+
+/* packed[r][t*C + c] = (c < C_real) ? bf16(w[r*s_r + c*s_c + wtap[t]]) : 0     r<R, t<ntaps, c<C */
+int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, int32_t R, int32_t ntaps, int32_t C,
+                     int32_t C_real, int64_t s_r, int64_t s_c, b2c_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Bandwidth kernels (channels-last bf16 views: ptr, rows, C, row_stride, c_off)
+ * ---------------------------------------------------------------------------------- */
+/* (N,C,T,H,W) fp32 -> (N,T,H,W,Cpad) bf16, zero padded channels.  main_ucf101.py:52-55 cast + layout. */
+int b2c_ncdhw_to_ndhwc(const float* in, void* out, int32_t N, int32_t C, int64_t THW, int32_t Cpad, b2c_stream_t s);
+/* (rows,C) bf16 view -> (N,C,THW) fp32 and back (module-boundary conversions) */
+int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_t in_c_off, float* out, int32_t N, int32_t C,
+                           int64_t THW, b2c_stream_t s);
+
+/* BatchNorm3d training statistics (pytorch_i3d.py:80,117).  groups: rows are split evenly into
+ * `groups` contiguous segments with independent statistics (two forward passes batched).
+ * ws: fp32 [groups][2][C] zeroed by the caller.  stats out: mean[g][C], rstd[g][C].
+ * running_mean/var updated with momentum (unbiased var) when non-NULL (groups applied in order). */
+int b2c_bn_stats(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
+                 float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
+                 b2c_stream_t s);
+/* y = relu((x-mean)*rstd*gamma+beta) written into a concat slot */
+int b2c_bn_relu_apply(const void* x, int64_t rows, int32_t C, int64_t x_row_stride, int32_t x_c_off, int32_t groups,
+                      const float* mean, const float* rstd, const float* gamma, const float* beta, void* y,
+                      int64_t y_row_stride, int32_t y_c_off, int32_t relu, b2c_stream_t s);
+/* backward: pass 1 reduces sum(dyr) and sum(dyr*xhat) (dyr = dy * (y>0)); ws fp32 [groups][2][C] zeroed */
+int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_row_stride, int32_t dy_c_off, const void* y, int64_t y_row_stride,
+                           int32_t y_c_off, const void* x, int64_t x_row_stride, int32_t x_c_off, int64_t rows,
+                           int32_t C, int32_t groups, const float* mean, const float* rstd, float* ws, int32_t relu,
+                           b2c_stream_t s);
+/* pass 2: dx = gamma*rstd*(dyr - s1/M - xhat*s2/M); also dgamma += sum_g s2, dbeta += sum_g s1 */
+int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_row_stride, int32_t dy_c_off, const void* y, int64_t y_row_stride,
+                          int32_t y_c_off, const void* x, int64_t x_row_stride, int32_t x_c_off, int64_t rows,
+                          int32_t C, int32_t groups, const float* mean, const float* rstd, const float* gamma,
+                          const float* ws, void* dx, int64_t dx_row_stride, int32_t dx_c_off, float* dgamma,
+                          float* dbeta, int32_t relu, b2c_stream_t s);
+
+/* MaxPool3dSamePadding (pytorch_i3d.py:13-45): zero 'same' padding then max; idx = uint8 argmax tap
+ * (255 = a padding zero won).  */
+int b2c_maxpool_fwd(const void* x, int64_t x_row_stride, int32_t x_c_off, void* y, int64_t y_row_stride, int32_t y_c_off,
+                    uint8_t* idx, int32_t N, int32_t C, int32_t Ti, int32_t Hi, int32_t Wi, int32_t To, int32_t Ho,
+                    int32_t Wo, int32_t kt, int32_t kh, int32_t kw, int32_t st, int32_t sh, int32_t sw, int32_t pt,
+                    int32_t ph, int32_t pw, b2c_stream_t s);
+int b2c_maxpool_bwd(const void* dy, int64_t dy_row_stride, int32_t dy_c_off, const uint8_t* idx, void* dx,
+                    int64_t dx_row_stride, int32_t dx_c_off, int32_t N, int32_t C, int32_t Ti, int32_t Hi, int32_t Wi,
+                    int32_t To, int32_t Ho, int32_t Wo, int32_t kt, int32_t kh, int32_t kw, int32_t st, int32_t sh,
+                    int32_t sw, int32_t pt, int32_t ph, int32_t pw, int32_t accumulate, b2c_stream_t s);
+
+/* y[n,pos,c] = x[n,pos,c] * scale[n,c]   (Dropout3d, capsules_ucf101.py:428) ; rows_per_n = T*H*W */
+int b2c_channel_scale(const void* x, int64_t x_row_stride, int32_t x_c_off, const float* scale_nc, void* y,
+                      int64_t y_row_stride, int32_t y_c_off, int32_t N, int64_t rows_per_n, int32_t C, b2c_stream_t s);
+/* dz = dy * (y > 0) (ReLU backward, optional) * scale[n,c] (optional); dbias[c] += sum dz */
+int b2c_act_bwd(const void* dy, int64_t dy_row_stride, int32_t dy_c_off, const void* y, int64_t y_row_stride,
+                int32_t y_c_off, const float* scale_nc, void* dz, int64_t dz_row_stride, int32_t dz_c_off, float* dbias,
+                int32_t N, int64_t rows_per_n, int32_t C, int32_t relu, b2c_stream_t s);
+/* out = a + b (bf16 views, gradient fan-in) */
+int b2c_add(const void* a, int64_t a_row_stride, int32_t a_c_off, const void* b, int64_t b_row_stride, int32_t b_c_off,
+            void* out, int64_t o_row_stride, int32_t o_c_off, int64_t rows, int32_t C, b2c_stream_t s);
+
+/* 'smooth' ConvTranspose3d(128->1,k3,p1) (capsules_ucf101.py:509) second half: 27-tap stencil over the
+ * per-tap projections P (rows,32) fp32 -> logits fp32 (N,T,H,W); and its adjoint dP (bf16). */
+int b2c_stencil27_fwd(const float* P, float* out, float bias, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s);
+int b2c_stencil27_bwd(const float* dout, void* dP, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Capsule head
+ * ---------------------------------------------------------------------------------- */
+/* EM routing, ConvCaps.forward with K=(1,1) (capsules_ucf101.py:290-309; m_step :108-156,
+ * e_step :158-182, 3 iterations).  caps: fp32 (b, 32*16 + 32) [poses | activations] as produced by the
+ * fused PrimaryCaps GEMM; W fp32 (32, C, 4, 4); out fp32 (b, C*16 + C) [mu | a_out]. C <= 32. */
+int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out,
+                       int64_t b, int32_t C, b2c_stream_t s);
+/* backward through the 3 unrolled iterations (recomputes the forward per location).
+ * dW/dbeta_u/dbeta_a are accumulated (atomicAdd) -- zero them first. */
+int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
+                       float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s);
+/* class activation = mean over the 400 locations (capsules_ucf101.py:450-451); feat is a view of out */
+int b2c_class_mean_fwd(const float* rout, float* act, int32_t N, int32_t L, int32_t C, b2c_stream_t s);
+/* pose masking (capsules_ucf101.py:455-483): x[n,l,j*16+h] = mu[n,l,j,h] * mask[n,j]  -> bf16 (N,L,C*16) */
+int b2c_pose_mask_fwd(const float* rout, const float* mask, void* x, int32_t N, int32_t L, int32_t C, b2c_stream_t s);
+/* drout[n,l,:] = [dx * mask | dact[n,j]/L + dfeat[n,l,j]] */
+int b2c_caps_head_bwd(const void* dx, const float* mask, const float* dact, const float* dfeat, float* drout, int32_t N,
+                      int32_t L, int32_t C, b2c_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Losses (utils/losses.py, utils/helpers.py, main_ucf101.py:89-148)
+ * ---------------------------------------------------------------------------------- */
+/* BCEWithLogits(mean) + Dice over the labeled subset (main_ucf101.py:89-92, losses.py:44-57).
+ * logits fp32 (P, V); targets fp32; lab_idx int32 [n_lab] rows of logits; sums: fp32[4] zeroed
+ * (bce_sum, sum p*t, sum p, sum t).  loss out: fp32[2] = (bce, dice). */
+int b2c_seg_loss_fwd(const float* logits, const float* targets, const int32_t* lab_idx, int32_t n_lab, int64_t V,
+                     float* sums, float* loss, b2c_stream_t s);
+/* dlogits[lab rows] += w_bce * dBCE + w_dice * dDice  (other rows untouched) */
+int b2c_seg_loss_bwd(const float* logits, const float* targets, const int32_t* lab_idx, int32_t n_lab, int64_t V,
+                     const float* sums, float w_bce, float w_dice, float* dlogits, b2c_stream_t s);
+/* SpreadLoss (losses.py:14-37) on rows lab_idx of act (P,C); loss fp32[2] (loss, absloss);
+ * dact rows (+)= w * dloss */
+int b2c_spread_loss(const float* act, const float* target, const int32_t* lab_idx, int32_t n_lab, int32_t C, float m_min,
+                    float* loss, float w, float* dact, b2c_stream_t s);
+/* Temporal-variance attentive mask (helpers.py:8-67), both directions fused:
+ *   out, flp: logits of the clip and of the flipped clip ALREADY flipped back in W is NOT required --
+ *   `flp` is the raw second-pass output; the kernel mirrors W itself (main_ucf101.py:100).
+ * raw masks (unnormalised, shifted by nothing) are written to m_clk, m_anti (fp32 (P,8,H,W)) and
+ * per-clip min/max to mm fp32 (P,4) = (min_clk, max_clk, min_anti, max_anti). */
+int b2c_bv_masks(const float* out, const float* flp, float* m_clk, float* m_anti, float* mm, int32_t P, int32_t H,
+                 int32_t W, int32_t frames_cnt, int32_t use_sigmoid, b2c_stream_t s);
+/* gradient-smoothness mask (helpers.py:70-95): raw second temporal derivative of sigmoid + per-clip min/max */
+int b2c_gv_mask(const float* out, float* m, float* mm, int32_t P, int32_t H, int32_t W, float lower, float upper,
+                int32_t use_lower, int32_t use_upper, b2c_stream_t s);
+/* consistency loss + gradients.  mode bit0: bv, bit1: gv.
+ *   d = flipW(flp) - out ; l2 = mean(d^2) ; lv = mean(w_clk*d^2) + mean(flipT(w_anti)*d^2) ;
+ *   lg = mean_thw( mean_j w_j * mean_i d_i^2 )   (the (B,B,...) broadcast of main_ucf101.py:130-132)
+ * acc: fp32[4+2*T*H*W] scratch zeroed by caller; loss out fp32[4] = (cons, l2, lv, lg).
+ * Two launches: _reduce then _grad (dout (+)= , dflp (+)= , scaled by wt). */
+int b2c_cons_reduce(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
+                    const float* mm_bv, const float* mm_gv, float* acc, int32_t P, int32_t H, int32_t W, int32_t mode,
+                    b2c_stream_t s);
+int b2c_cons_finish(const float* acc, float* loss, int32_t P, int32_t H, int32_t W, int32_t mode, float wt_ramp,
+                    float bv_wt, float gv_wt, b2c_stream_t s);
+int b2c_cons_grad(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
+                  const float* mm_bv, const float* mm_gv, const float* acc, float* dout, float* dflp, int32_t P,
+                  int32_t H, int32_t W, int32_t mode, float wt_ramp, float bv_wt, float gv_wt, float wt, b2c_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Optimiser: Adam(lr, betas, eps=1e-6, wd=0) over one flat fp32 buffer (main_ucf101.py:416,184)
+ * ---------------------------------------------------------------------------------- */
+int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  int32_t step, float grad_scale, b2c_stream_t s);
+
+/* generic helpers */
+int b2c_fill_f32(float* p, int64_t n, float v, b2c_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

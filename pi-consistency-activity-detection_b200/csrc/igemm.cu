@@ -1,0 +1,601 @@
+// Generalised implicit-GEMM convolution for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM),
+// im2col gather by cp.async into 128B-swizzled UMMA tiles, mbarrier producer/consumer pipeline.
+//
+//   fprop-like kernel : D[M = output positions (128/CTA), N = Cout tile] = A_im2col[M,K] * W[N,K]^T
+//                       A and W are K-major.  Covers conv fprop, dgrad, transposed-conv fprop
+//                       (by output-parity class) and transposed-conv dgrad.
+//   wgrad kernel      : D[M = (tap,ci) tile of 128, N = Cp tile] = sum_positions Gcol[pos,M] * P[pos,N]
+//                       both operands MN-major (positions are the GEMM-K dimension), split over
+//                       position ranges, fp32 red.add into the weight gradient.
+//
+// Warp roles (160 threads): warps 0-3 = producers (one GEMM row / position per thread) and, after the
+// main loop, the TMEM->global epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4 = TMEM allocator +
+// single-thread UMMA issuer.
+#include "common.cuh"
+#include "../../include/b200caps.h"
+
+static long long g_launches = 0;
+long long b2c_launches_add(long long n) {
+  g_launches += n;
+  return g_launches;
+}
+
+namespace {
+
+constexpr int kTileM = 128;      // UMMA M
+constexpr int kBlockK = 64;      // bf16 elements per 128-byte swizzle row
+constexpr int kATileBytes = kTileM * 128;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 160;
+
+struct PipeSmem {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t accum;
+  uint32_t tmem_base;
+  uint32_t pad_;
+};
+
+__device__ __forceinline__ int tap_dt(int32_t t) { return (int)(int8_t)(t & 0xff); }
+__device__ __forceinline__ int tap_dh(int32_t t) { return (int)(int8_t)((t >> 8) & 0xff); }
+__device__ __forceinline__ int tap_dw(int32_t t) { return (int)(int8_t)((t >> 16) & 0xff); }
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int n) {
+  uint32_t c = 32;
+  while ((int)c < n) c <<= 1;
+  return c;
+}
+
+// =====================================================================================
+// fprop-like kernel
+// =====================================================================================
+__global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d, int stages,
+                                                               int lag) {
+  const b2c_conv_class& cc = d.cls[blockIdx.z];
+  const long long Mtot = (long long)d.N * cc.Qt * cc.Qh * cc.Qw;
+  const long long m0 = (long long)blockIdx.x * kTileM;
+  if (m0 >= Mtot) return;  // uniform for the CTA; nothing allocated yet
+  const int n0 = blockIdx.y * d.bn_tile;
+  int bn = d.Cout - n0;
+  if (bn > d.bn_tile) bn = d.bn_tile;
+  const int bn16 = (bn + 15) & ~15;  // UMMA N (multiple of 16 for M=128)
+  const int K = cc.ntaps * d.Cin;
+  const int nkb = (K + kBlockK - 1) / kBlockK;
+  const int b_tile_bytes = ((bn16 * 128) + 1023) & ~1023;
+  const int stage_bytes = kATileBytes + b_tile_bytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem_al + (size_t)stages * stage_bytes);
+  int32_t* s_taps = reinterpret_cast<int32_t*>(ps + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  for (int i = tid; i < cc.ntaps; i += kThreads) s_taps[i] = cc.taps[i];
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&ps->full[s], 128);
+      mbar_init(&ps->empty[s], 1);
+    }
+    mbar_init(&ps->accum, 1);
+    fence_barrier_init();
+  }
+  const uint32_t tmem_cols = tmem_cols_for(bn16);
+  if (warp == 4) tmem_alloc(&ps->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = ps->tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------ producers --------------------------------------
+    const int r = tid;  // A row == TMEM lane
+    const long long m = m0 + r;
+    const bool mvalid = m < Mtot;
+    int n_i = 0, qt = 0, qh = 0, qw = 0;
+    if (mvalid) {
+      long long t = m;
+      qw = (int)(t % cc.Qw); t /= cc.Qw;
+      qh = (int)(t % cc.Qh); t /= cc.Qh;
+      qt = (int)(t % cc.Qt); t /= cc.Qt;
+      n_i = (int)t;
+    }
+    const int it0 = qt * d.si_t, ih0 = qh * d.si_h, iw0 = qw * d.si_w;
+    const bf16* in_n = reinterpret_cast<const bf16*>(d.in) + d.in_c_off;
+    const bf16* wbase = reinterpret_cast<const bf16*>(cc.w);
+    const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const uint32_t swz = (uint32_t)(r & 7);
+
+    // running (tap, channel) cursor for this thread's next chunk; identical across threads
+    int tap = 0, c = 0;
+    const bf16* tap_ptr = nullptr;  // pointer to channel 0 of the current tap's input pixel (or null if OOB)
+    auto load_tap = [&](int tp) {
+      tap_ptr = nullptr;
+      if (mvalid && tp < cc.ntaps) {
+        const int32_t tv = s_taps[tp];
+        const int it = it0 + tap_dt(tv), ih = ih0 + tap_dh(tv), iw = iw0 + tap_dw(tv);
+        if ((unsigned)it < (unsigned)d.Ti && (unsigned)ih < (unsigned)d.Hi && (unsigned)iw < (unsigned)d.Wi)
+          tap_ptr = in_n + ((((long long)n_i * d.Ti + it) * d.Hi + ih) * d.Wi + iw) * d.in_row_stride;
+      }
+    };
+    load_tap(0);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&ps->empty[stage], phase ^ 1, 1);
+      const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
+      const uint32_t b_st = a_st + kATileBytes;
+      // A: 8 chunks of 8 channels
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = a_st + a_row_off + (((uint32_t)j ^ swz) << 4);
+        const void* src = tap_ptr ? (const void*)(tap_ptr + c) : (const void*)d.in;
+        cp_async16(dst, src, tap_ptr ? 16u : 0u);
+        c += 8;
+        if (c >= d.Cin) {
+          c = 0;
+          ++tap;
+          load_tap(tap);
+        }
+      }
+      // B: rows rr = r, r+128 of the weight tile
+      const int k0 = kb * kBlockK;
+      for (int rr = r; rr < bn16; rr += 128) {
+        const bool rvalid = (n0 + rr) < d.Cout;
+        const bf16* wrow = wbase + (long long)(n0 + rr) * K + k0;
+        const uint32_t brow = b_st + (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128);
+        const uint32_t sw = (uint32_t)(rr & 7);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = rvalid && (k0 + j * 8) < K;
+          cp_async16(brow + (((uint32_t)j ^ sw) << 4), ok ? (const void*)(wrow + j * 8) : (const void*)cc.w, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      // signal the stage issued `lag` iterations ago
+      if (kb >= lag) {
+        cp_async_wait_dyn(lag);
+        fence_proxy_async_smem();
+        int s2 = stage - lag;
+        if (s2 < 0) s2 += stages;
+        mbar_arrive(&ps->full[s2]);
+      }
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // drain
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    {
+      int first = nkb - lag;
+      if (first < 0) first = 0;
+      for (int kb = first; kb < nkb; ++kb) mbar_arrive(&ps->full[kb % stages]);
+    }
+
+    // ------------------------------ epilogue ---------------------------------------
+    mbar_wait(&ps->accum, 0, 3);
+    tc_fence_after();
+    long long opos = 0;
+    if (mvalid)
+      opos = (((long long)n_i * d.To + (qt * d.so_t + cc.po_t)) * d.Ho + (qh * d.so_h + cc.po_h)) * d.Wo +
+             (qw * d.so_w + cc.po_w);
+    const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
+    const float* scale_row = d.scale_nc ? d.scale_nc + (long long)n_i * d.Cout : nullptr;
+    for (int c0 = 0; c0 < bn16; c0 += 16) {
+      float v[16];
+      tmem_ld16(t_lane + (uint32_t)c0, v);
+      if (!mvalid) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = n0 + c0 + h * 8;
+        if (col >= d.Cout) break;
+        float* vv = v + h * 8;
+        if (d.bias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] += __ldg(d.bias + col + i);
+        }
+        if (scale_row) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] *= __ldg(scale_row + col + i);
+        }
+        if (d.relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+        }
+        if (d.sigmoid_from >= 0 && col >= d.sigmoid_from) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
+        }
+        if (d.out_fp32) {
+          float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+          float4* o4 = reinterpret_cast<float4*>(o);
+          if (d.accumulate) {
+            float4 a = o4[0], b = o4[1];
+            vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
+            vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
+          }
+          o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+          uint4* o4 = reinterpret_cast<uint4*>(o);
+          if (d.accumulate) {
+            float e[8];
+            unpack8(*o4, e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] += e[i];
+          }
+          *o4 = pack8(vv);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ------------------------------ MMA issuer (warp 4) ----------------------------
+    const uint32_t idesc = umma_idesc_bf16(bn16, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&ps->full[stage], phase, 2);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
+        const uint32_t b_st = a_st + kATileBytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(a_st + k * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(b_st + k * 32, 16, 1024);
+          umma_bf16(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&ps->empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (lane == 0) umma_commit(&ps->accum);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+// =====================================================================================
+// wgrad kernel
+// =====================================================================================
+__global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_constant__ b2c_wgrad_desc d, int stages,
+                                                               int lag, int nsplit) {
+  const int K = d.ntaps * d.Cg;            // GEMM-M extent ((tap, gc) columns of the im2col matrix)
+  const int mk0 = blockIdx.x * kTileM;     // first (tap,gc) column of this CTA
+  const int n0 = blockIdx.y * d.bn_tile;   // first p-channel
+  int bn = d.Cp - n0;
+  if (bn > d.bn_tile) bn = d.bn_tile;
+  const int bn16 = (bn + 15) & ~15;
+  const long long Mtot = (long long)d.N * d.Qt * d.Qh * d.Qw;  // positions = GEMM-K extent
+  const long long nkb_all = (Mtot + kBlockK - 1) / kBlockK;
+  const long long kb_lo = nkb_all * blockIdx.z / nsplit;
+  const long long kb_hi = nkb_all * (blockIdx.z + 1) / nsplit;
+  const int nkb = (int)(kb_hi - kb_lo);
+  if (nkb <= 0) return;
+  const int b_atoms = (bn16 + 63) / 64;
+  const int b_tile_bytes = b_atoms * 8 * 1024;
+  const int stage_bytes = kATileBytes + b_tile_bytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem_al + (size_t)stages * stage_bytes);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&ps->full[s], 128);
+      mbar_init(&ps->empty[s], 1);
+    }
+    mbar_init(&ps->accum, 1);
+    fence_barrier_init();
+  }
+  const uint32_t tmem_cols = tmem_cols_for(bn16);
+  if (warp == 4) tmem_alloc(&ps->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = ps->tmem_base;
+
+  if (warp < 4) {
+    // producers: thread -> position row r (0..63) and half (0/1) of the chunk columns
+    const int r = tid & 63;
+    const int half = tid >> 6;
+    // fixed (tap, channel) of this thread's 8 A chunks
+    int a_dt[8], a_dh[8], a_dw[8], a_c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kcol = mk0 + (half * 8 + j) * 8;
+      if (kcol < K) {
+        const int tp = kcol / d.Cg;
+        const int32_t tv = __ldg(d.taps + tp);
+        a_dt[j] = tap_dt(tv); a_dh[j] = tap_dh(tv); a_dw[j] = tap_dw(tv);
+        a_c[j] = kcol - tp * d.Cg;
+      } else {
+        a_c[j] = -1; a_dt[j] = a_dh[j] = a_dw[j] = 0;
+      }
+    }
+    const bf16* gbase = reinterpret_cast<const bf16*>(d.g) + d.g_c_off;
+    const bf16* pbase = reinterpret_cast<const bf16*>(d.p) + d.p_c_off + n0;
+    const int nbch = bn16 / 8;          // B chunks per row (even)
+    const int bch_per = nbch / 2;       // per half
+    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const uint32_t swz = (uint32_t)(r & 7);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&ps->empty[stage], phase ^ 1, 11);
+      const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
+      const uint32_t b_st = a_st + kATileBytes;
+      const long long pos = (kb_lo + i) * kBlockK + r;
+      const bool pvalid = pos < Mtot;
+      int n_i = 0, qt = 0, qh = 0, qw = 0;
+      if (pvalid) {
+        long long t = pos;
+        qw = (int)(t % d.Qw); t /= d.Qw;
+        qh = (int)(t % d.Qh); t /= d.Qh;
+        qt = (int)(t % d.Qt); t /= d.Qt;
+        n_i = (int)t;
+      }
+      const int gt0 = qt * d.sg_t, gh0 = qh * d.sg_h, gw0 = qw * d.sg_w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = a_st + (uint32_t)(half * 8 * 1024) + row_off + (((uint32_t)j ^ swz) << 4);
+        const void* src = d.g;
+        uint32_t nb = 0;
+        if (pvalid && a_c[j] >= 0) {
+          const int it = gt0 + a_dt[j], ih = gh0 + a_dh[j], iw = gw0 + a_dw[j];
+          if ((unsigned)it < (unsigned)d.Tg && (unsigned)ih < (unsigned)d.Hg && (unsigned)iw < (unsigned)d.Wg) {
+            src = gbase + ((((long long)n_i * d.Tg + it) * d.Hg + ih) * d.Wg + iw) * d.g_row_stride + a_c[j];
+            nb = 16;
+          }
+        }
+        cp_async16(dst, src, nb);
+      }
+      const bf16* prow = nullptr;
+      if (pvalid)
+        prow = pbase + ((((long long)n_i * d.Tp + (qt * d.sp_t + d.pp_t)) * d.Hp + (qh * d.sp_h + d.pp_h)) * d.Wp +
+                        (qw * d.sp_w + d.pp_w)) * d.p_row_stride;
+      for (int j = 0; j < bch_per; ++j) {
+        const int ch = half * bch_per + j;
+        const uint32_t dst = b_st + (uint32_t)((ch >> 3) * 8 * 1024) + row_off + (((uint32_t)(ch & 7) ^ swz) << 4);
+        const bool ok = pvalid && (n0 + ch * 8) < d.Cp;
+        cp_async16(dst, ok ? (const void*)(prow + ch * 8) : d.p, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (i >= lag) {
+        cp_async_wait_dyn(lag);
+        fence_proxy_async_smem();
+        int s2 = stage - lag;
+        if (s2 < 0) s2 += stages;
+        mbar_arrive(&ps->full[s2]);
+      }
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    {
+      int first = nkb - lag;
+      if (first < 0) first = 0;
+      for (int i = first; i < nkb; ++i) mbar_arrive(&ps->full[i % stages]);
+    }
+
+    // epilogue: TMEM lane = (tap,gc) column mk0 + tid ; columns = p channels
+    mbar_wait(&ps->accum, 0, 13);
+    tc_fence_after();
+    const int kcol = mk0 + tid;
+    bool rvalid = kcol < K;
+    long long base = 0;
+    if (rvalid) {
+      const int tp = kcol / d.Cg;
+      const int gc = kcol - tp * d.Cg;
+      rvalid = gc < d.Cg_real;
+      base = (long long)gc * d.s_g + __ldg(d.wtap + tp);
+    }
+    const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < bn16; c0 += 16) {
+      float v[16];
+      tmem_ld16(t_lane + (uint32_t)c0, v);
+      if (!rvalid) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int pc = n0 + c0 + i;
+        if (pc < d.Cp) {
+          float* dst = d.dw + base + (long long)pc * d.s_p;
+          if (d.atomic) atomicAdd(dst, v[i]);
+          else *dst = v[i];
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    const uint32_t idesc = umma_idesc_bf16(bn16, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&ps->full[stage], phase, 12);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
+        const uint32_t b_st = a_st + kATileBytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // MN-major SW128: LBO = stride between 64-element MN atoms (8 KB), SBO = stride between 8-position groups
+          const uint64_t ad = umma_desc_sw128(a_st + k * 2048, 8192, 1024);
+          const uint64_t bd = umma_desc_sw128(b_st + k * 2048, 8192, 1024);
+          umma_bf16(tmem_d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&ps->empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (lane == 0) umma_commit(&ps->accum);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ packed, const int32_t* __restrict__ wtap,
+                                    int R, int ntaps, int C, int C_real, long long s_r, long long s_c) {
+  const long long total = (long long)R * ntaps * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t2 = i / C;
+    const int t = (int)(t2 % ntaps);
+    const int r = (int)(t2 / ntaps);
+    float v = 0.f;
+    if (c < C_real) v = w[(long long)r * s_r + (long long)c * s_c + wtap[t]];
+    packed[i] = __float2bfloat16(v);
+  }
+}
+
+int pick_bn_tile(int Cout) {
+  if (Cout <= 256) return (Cout + 15) & ~15;
+  const int nt = (Cout + 255) / 256;
+  int t = (Cout + nt - 1) / nt;
+  return (t + 15) & ~15;
+}
+
+constexpr int kSmemBudget = 200 * 1024;
+
+}  // namespace
+
+B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
+  B2C_REQUIRE(dh != nullptr, "conv_fprop: null descriptor");
+  b2c_conv_desc d = *dh;
+  B2C_REQUIRE(d.in && d.out, "conv_fprop: null tensor");
+  B2C_REQUIRE(d.Cin > 0 && d.Cin % 8 == 0, "conv_fprop: Cin=%d must be a positive multiple of 8", d.Cin);
+  B2C_REQUIRE(d.Cout > 0 && d.Cout % 8 == 0, "conv_fprop: Cout=%d must be a positive multiple of 8", d.Cout);
+  B2C_REQUIRE(d.in_c_off % 8 == 0 && d.out_c_off % 8 == 0, "conv_fprop: channel offsets must be multiples of 8");
+  B2C_REQUIRE(d.in_row_stride % 8 == 0 && d.out_row_stride % (d.out_fp32 ? 4 : 8) == 0, "conv_fprop: row strides unaligned");
+  B2C_REQUIRE(d.nclass >= 1 && d.nclass <= 8, "conv_fprop: nclass=%d out of range", d.nclass);
+  B2C_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.out & 15) == 0, "conv_fprop: tensors must be 16B aligned");
+  if (d.bn_tile <= 0) d.bn_tile = pick_bn_tile(d.Cout);
+  B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_fprop: bn_tile=%d invalid", d.bn_tile);
+  long long max_m = 0;
+  int max_taps = 0;
+  for (int i = 0; i < d.nclass; ++i) {
+    const b2c_conv_class& c = d.cls[i];
+    B2C_REQUIRE(c.taps && c.w && c.ntaps > 0, "conv_fprop: class %d incomplete", i);
+    B2C_REQUIRE(((uintptr_t)c.w & 15) == 0, "conv_fprop: weights must be 16B aligned");
+    long long m = (long long)d.N * c.Qt * c.Qh * c.Qw;
+    if (m > max_m) max_m = m;
+    if (c.ntaps > max_taps) max_taps = c.ntaps;
+  }
+  if (max_m == 0) return 0;
+  const int bn16 = (d.bn_tile + 15) & ~15;
+  const int stage_bytes = kATileBytes + (((bn16 * 128) + 1023) & ~1023);
+  int stages = kSmemBudget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  B2C_REQUIRE(stages >= 3, "conv_fprop: tile too large for shared memory");
+  int lag = stages - 2;
+  if (lag > 4) lag = 4;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeSmem) + (size_t)max_taps * 4 + 1024 + 64;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    if (e != cudaSuccess) return b2c_cuda_check(e, "conv_fprop: cudaFuncSetAttribute");
+    configured = 220 * 1024;
+  }
+  dim3 grid((unsigned)((max_m + kTileM - 1) / kTileM), (unsigned)((d.Cout + d.bn_tile - 1) / d.bn_tile), (unsigned)d.nclass);
+  igemm_fprop_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, stages, lag);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("conv_fprop launch");
+  return 0;
+}
+
+B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
+  B2C_REQUIRE(dh != nullptr, "conv_wgrad: null descriptor");
+  b2c_wgrad_desc d = *dh;
+  B2C_REQUIRE(d.g && d.p && d.dw && d.taps && d.wtap, "conv_wgrad: null pointer");
+  B2C_REQUIRE(d.Cg > 0 && d.Cg % 8 == 0 && d.Cp > 0 && d.Cp % 8 == 0, "conv_wgrad: channels must be multiples of 8");
+  B2C_REQUIRE(d.g_c_off % 8 == 0 && d.p_c_off % 8 == 0 && d.g_row_stride % 8 == 0 && d.p_row_stride % 8 == 0,
+              "conv_wgrad: unaligned view");
+  B2C_REQUIRE(((uintptr_t)d.g & 15) == 0 && ((uintptr_t)d.p & 15) == 0, "conv_wgrad: tensors must be 16B aligned");
+  if (d.Cg_real <= 0) d.Cg_real = d.Cg;
+  if (d.bn_tile <= 0) d.bn_tile = pick_bn_tile(d.Cp);
+  B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_wgrad: bn_tile=%d invalid", d.bn_tile);
+  const long long Mtot = (long long)d.N * d.Qt * d.Qh * d.Qw;
+  if (Mtot == 0) return 0;
+  const int K = d.ntaps * d.Cg;
+  const int mt = (K + kTileM - 1) / kTileM;
+  const int nt = (d.Cp + d.bn_tile - 1) / d.bn_tile;
+  const long long nkb = (Mtot + kBlockK - 1) / kBlockK;
+  int nsplit = d.nsplit;
+  if (nsplit <= 0) {
+    // fill ~2 waves of SMs, keep >= 8 position blocks per CTA
+    long long want = (2LL * b2c_num_sms() + (long long)mt * nt - 1) / ((long long)mt * nt);
+    long long cap = nkb / 8;
+    if (cap < 1) cap = 1;
+    nsplit = (int)(want < cap ? want : cap);
+    if (nsplit < 1) nsplit = 1;
+  }
+  if (nsplit > nkb) nsplit = (int)nkb;
+  B2C_REQUIRE(nsplit == 1 || d.atomic, "conv_wgrad: nsplit>1 requires atomic accumulation");
+  const int bn16 = (d.bn_tile + 15) & ~15;
+  const int stage_bytes = kATileBytes + ((bn16 + 63) / 64) * 8 * 1024;
+  int stages = kSmemBudget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  B2C_REQUIRE(stages >= 3, "conv_wgrad: tile too large for shared memory");
+  int lag = stages - 2;
+  if (lag > 4) lag = 4;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeSmem) + 1024 + 64;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    if (e != cudaSuccess) return b2c_cuda_check(e, "conv_wgrad: cudaFuncSetAttribute");
+    configured = true;
+  }
+  dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)nsplit);
+  igemm_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, stages, lag, nsplit);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("conv_wgrad launch");
+  return 0;
+}
+
+B2C_API int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, int32_t R, int32_t ntaps, int32_t C,
+                             int32_t C_real, int64_t s_r, int64_t s_c, b2c_stream_t stream) {
+  B2C_REQUIRE(w && packed && wtap, "pack_weights: null pointer");
+  B2C_REQUIRE(R > 0 && ntaps > 0 && C > 0 && C_real > 0 && C_real <= C, "pack_weights: bad dims");
+  const long long total = (long long)R * ntaps * C;
+  int blocks = (int)((total + 255) / 256);
+  const int cap = b2c_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<bf16*>(packed), wtap, R, ntaps, C, C_real,
+                                                               s_r, s_c);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("pack_weights launch");
+  return 0;
+}
