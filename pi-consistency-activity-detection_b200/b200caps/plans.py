@@ -1,0 +1,277 @@
+"""Host-side planning for the generalised implicit-GEMM convolution (csrc/igemm.cu).
+
+A ``ConvPlan`` turns one torch-style convolution / transposed convolution into the
+tap tables, output-parity classes and packed bf16 weight tiles the tcgen05 kernels consume:
+
+  * conv fprop                         -> 1 class, taps d = k - pad_front, input stride = conv stride
+  * conv dgrad / convT fprop           -> prod(stride) output-parity classes, only the taps that hit
+                                          real inputs (no MACs on inserted zeros)
+  * convT dgrad                        -> 1 class (a strided conv over the output gradient)
+  * wgrad (conv and convT)             -> 1 launch, positions are the GEMM-K dimension
+
+Pure host logic (unit-tested on CPU); device work happens only in ``ops``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _abi
+
+
+def _tap_word(dt: int, dh: int, dw: int) -> int:
+    for v in (dt, dh, dw):
+        assert -128 <= v <= 127
+    w = (dt & 0xFF) | ((dh & 0xFF) << 8) | ((dw & 0xFF) << 16)
+    return w
+
+
+@dataclass
+class TapClass:
+    taps: List[Tuple[int, int, int]]   # input offsets (dt, dh, dw)
+    wtap: List[int]                    # linear tap offset inside the torch weight's kernel dims
+    Q: Tuple[int, int, int]            # GEMM-M grid (per sample)
+    po: Tuple[int, int, int]           # output offset
+    taps_dev: Optional[torch.Tensor] = None
+    wtap_dev: Optional[torch.Tensor] = None
+    packed: Optional[torch.Tensor] = None
+
+
+def conv_out_size(i: int, k: int, s: int, pf: int, pb: int) -> int:
+    return (i + pf + pb - k) // s + 1
+
+
+def convT_out_size(i: int, k: int, s: int, p: int, op: int) -> int:
+    return (i - 1) * s - 2 * p + k + op
+
+
+def same_pad(size: int, k: int, s: int) -> Tuple[int, int]:
+    """TF 'same' padding of the reference (pytorch_i3d.py:15-19, :82-86): front = pad // 2."""
+    pad = max(k - s, 0) if size % s == 0 else max(k - (size % s), 0)
+    return pad // 2, pad - pad // 2
+
+
+def _dim_conv_like(k: int, p: int):
+    """taps of a gather 'in[q*s + (kk - p)]' for one dimension: list of (kk, d)."""
+    return [(kk, kk - p) for kk in range(k)]
+
+
+def _dim_transposed_like(k: int, s: int, p: int, out_size: int):
+    """Per output parity r (o = s*q + r): taps kk with (r + p - kk) % s == 0 reading in[q + d],
+    d = (r + p - kk) // s.  Returns list over r of (taps [(kk, d)], Q_r)."""
+    out = []
+    for r in range(s):
+        taps = [(kk, (r + p - kk) // s) for kk in range(k) if (r + p - kk) % s == 0]
+        q = max(0, -(-(out_size - r) // s))
+        out.append((taps, q))
+    return out
+
+
+def _product_classes(per_dim, kdims):
+    """per_dim: for each of 3 dims a list over parity of (taps, Q).  Build the class list."""
+    classes = []
+    kt, kh, kw = kdims
+    for rt, (tt, qt) in enumerate(per_dim[0]):
+        for rh, (th, qh) in enumerate(per_dim[1]):
+            for rw, (tw, qw) in enumerate(per_dim[2]):
+                taps, wtap = [], []
+                for (a, da) in tt:
+                    for (b, db) in th:
+                        for (c, dc) in tw:
+                            taps.append((da, db, dc))
+                            wtap.append((a * kh + b) * kw + c)
+                if qt * qh * qw == 0:
+                    continue
+                classes.append(TapClass(taps, wtap, (qt, qh, qw), (rt, rh, rw)))
+    return classes
+
+
+@dataclass
+class ConvSpec:
+    """A torch convolution (transposed=False: weight (Cout,Cin,k..)) or transposed convolution
+    (transposed=True: weight (Cin,Cout,k..)).  2-D layers use kt=1."""
+    Cin: int
+    Cout: int
+    k: Tuple[int, int, int]
+    stride: Tuple[int, int, int] = (1, 1, 1)
+    pad_front: Tuple[int, int, int] = (0, 0, 0)   # conv: explicit front pad ; convT: `padding`
+    pad_back: Tuple[int, int, int] = (0, 0, 0)    # conv only
+    out_pad: Tuple[int, int, int] = (0, 0, 0)     # convT only
+    transposed: bool = False
+    Cin_pad: int = 0                              # channels of the stored input tensor (>= Cin, % 8 == 0)
+    Cout_pad: int = 0                             # channels of the stored output tensor
+
+    def __post_init__(self):
+        if not self.Cin_pad:
+            self.Cin_pad = (self.Cin + 7) // 8 * 8
+        if not self.Cout_pad:
+            self.Cout_pad = (self.Cout + 7) // 8 * 8
+
+    def out_dims(self, in_dims):
+        if self.transposed:
+            return tuple(convT_out_size(i, k, s, p, op) for i, k, s, p, op in
+                         zip(in_dims, self.k, self.stride, self.pad_front, self.out_pad))
+        return tuple(conv_out_size(i, k, s, pf, pb) for i, k, s, pf, pb in
+                     zip(in_dims, self.k, self.stride, self.pad_front, self.pad_back))
+
+
+class ConvPlan:
+    """Geometry of one layer at one input size.  ``in_dims`` = (T, H, W) of the layer input."""
+
+    def __init__(self, spec: ConvSpec, in_dims: Sequence[int]):
+        self.spec = spec
+        self.in_dims = tuple(int(v) for v in in_dims)
+        self.out_dims = spec.out_dims(self.in_dims)
+        k, s, p = spec.k, spec.stride, spec.pad_front
+        T = k[0] * k[1] * k[2]
+        self.ntaps_full = T
+        if not spec.transposed:
+            # weight (Cout, Cin, T)
+            per = [[(_dim_conv_like(k[i], p[i]), self.out_dims[i])] for i in range(3)]
+            self.fprop = _product_classes(per, k)
+            self.fprop_si, self.fprop_so = s, (1, 1, 1)
+            self.fprop_pack = dict(R=spec.Cout, R_pad=spec.Cout_pad, C=spec.Cin_pad, C_real=spec.Cin, s_r=spec.Cin * T, s_c=T)
+            perd = [_dim_transposed_like(k[i], s[i], p[i], self.in_dims[i]) for i in range(3)]
+            self.dgrad = _product_classes(perd, k)
+            self.dgrad_si, self.dgrad_so = (1, 1, 1), s
+            self.dgrad_pack = dict(R=spec.Cin, R_pad=spec.Cin_pad, C=spec.Cout_pad, C_real=spec.Cout, s_r=T, s_c=spec.Cin * T)
+            # wgrad: g = x gathered with the fprop taps, p = dy at plain positions
+            self.wgrad_cls = self.fprop[0]
+            self.wgrad_geom = dict(g_is_input=True, sg=s, sp=(1, 1, 1), s_p=spec.Cin * T, s_g=T,
+                                   Cg=spec.Cin_pad, Cg_real=spec.Cin, Cp=spec.Cout_pad, Q=self.out_dims)
+        else:
+            # weight (Cin, Cout, T)
+            perf = [_dim_transposed_like(k[i], s[i], p[i], self.out_dims[i]) for i in range(3)]
+            self.fprop = _product_classes(perf, k)
+            self.fprop_si, self.fprop_so = (1, 1, 1), s
+            self.fprop_pack = dict(R=spec.Cout, R_pad=spec.Cout_pad, C=spec.Cin_pad, C_real=spec.Cin, s_r=T, s_c=spec.Cout * T)
+            perd = [[(_dim_conv_like(k[i], p[i]), self.in_dims[i])] for i in range(3)]
+            self.dgrad = _product_classes(perd, k)
+            self.dgrad_si, self.dgrad_so = s, (1, 1, 1)
+            self.dgrad_pack = dict(R=spec.Cin, R_pad=spec.Cin_pad, C=spec.Cout_pad, C_real=spec.Cout, s_r=spec.Cout * T, s_c=T)
+            # wgrad: g = dOut gathered with the dgrad taps, p = x at plain positions
+            self.wgrad_cls = self.dgrad[0]
+            self.wgrad_geom = dict(g_is_input=False, sg=s, sp=(1, 1, 1), s_p=spec.Cout * T, s_g=T,
+                                   Cg=spec.Cout_pad, Cg_real=spec.Cout, Cp=spec.Cin_pad, Q=self.in_dims)
+        self._device = None
+
+    # ---- algorithmic work (for roofline accounting) ------------------------------------
+    def macs_fprop(self, n: int) -> int:
+        return n * sum(c.Q[0] * c.Q[1] * c.Q[2] * len(c.taps) for c in self.fprop) * self.spec.Cin * self.spec.Cout
+
+    # ---- device state -------------------------------------------------------------------
+    def to(self, device):
+        if self._device == device:
+            return self
+        for cl in self.fprop + self.dgrad:
+            cl.taps_dev = torch.tensor([_tap_word(*t) for t in cl.taps], dtype=torch.int32, device=device)
+            cl.wtap_dev = torch.tensor(cl.wtap, dtype=torch.int32, device=device)
+        self._device = device
+        return self
+
+    def pack(self, weight: torch.Tensor, which: str, stream_ptr: int):
+        """(Re)build the packed bf16 weights of the fprop or dgrad classes from the fp32 master."""
+        assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.is_cuda
+        classes = self.fprop if which == "fprop" else self.dgrad
+        pk = self.fprop_pack if which == "fprop" else self.dgrad_pack
+        for cl in classes:
+            nt = len(cl.taps)
+            if cl.packed is None:
+                cl.packed = torch.zeros((pk["R_pad"], nt * pk["C"]), dtype=torch.bfloat16, device=weight.device)
+            _abi.call("b2c_pack_weights", weight.data_ptr(), cl.packed.data_ptr(), cl.wtap_dev.data_ptr(), pk["R"], nt,
+                      pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], stream_ptr)
+
+
+@dataclass
+class View:
+    """Channels-last bf16/fp32 activation view: tensor (N,T,H,W,Ctot), channel window [c_off, c_off+C)."""
+    t: torch.Tensor
+    c_off: int = 0
+    C: int = -1
+
+    def __post_init__(self):
+        assert self.t.dim() == 5 and self.t.is_contiguous(), (self.t.shape, self.t.stride())
+        if self.C < 0:
+            self.C = self.t.shape[-1] - self.c_off
+
+    @property
+    def N(self):
+        return self.t.shape[0]
+
+    @property
+    def dims(self):
+        return tuple(self.t.shape[1:4])
+
+    @property
+    def rows(self):
+        return self.t.shape[0] * self.t.shape[1] * self.t.shape[2] * self.t.shape[3]
+
+    @property
+    def row_stride(self):
+        return self.t.shape[-1]
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, scale_nc=None, relu=False,
+                   sigmoid_from=-1, accumulate=False, bn_tile=0) -> _abi.ConvDesc:
+    """which = 'fprop' (x = layer input, out = layer output) or 'dgrad' (x = dY, out = dX)."""
+    classes = plan.fprop if which == "fprop" else plan.dgrad
+    si, so = (plan.fprop_si, plan.fprop_so) if which == "fprop" else (plan.dgrad_si, plan.dgrad_so)
+    pk = plan.fprop_pack if which == "fprop" else plan.dgrad_pack
+    exp_in, exp_out = (plan.in_dims, plan.out_dims) if which == "fprop" else (plan.out_dims, plan.in_dims)
+    assert x.dims == tuple(exp_in) and out.dims == tuple(exp_out), (which, x.dims, exp_in, out.dims, exp_out)
+    assert x.C == pk["C"] and out.C == pk["R_pad"], (which, x.C, pk["C"], out.C, pk["R_pad"])
+    assert x.t.dtype == torch.bfloat16 and out.t.dtype in (torch.bfloat16, torch.float32)
+    d = _abi.ConvDesc()
+    d.inp, d.out = x.ptr, out.ptr
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.scale_nc = scale_nc.data_ptr() if scale_nc is not None else None
+    d.in_row_stride, d.out_row_stride = x.row_stride, out.row_stride
+    d.in_c_off, d.out_c_off, d.Cin, d.Cout = x.c_off, out.c_off, pk["C"], pk["R_pad"]
+    d.N = x.N
+    d.Ti, d.Hi, d.Wi = x.dims
+    d.To, d.Ho, d.Wo = out.dims
+    d.si_t, d.si_h, d.si_w = si
+    d.so_t, d.so_h, d.so_w = so
+    d.out_fp32 = 1 if out.t.dtype == torch.float32 else 0
+    d.relu, d.sigmoid_from, d.accumulate, d.bn_tile = int(relu), int(sigmoid_from), int(accumulate), int(bn_tile)
+    d.nclass = len(classes)
+    assert 1 <= d.nclass <= 8
+    for i, cl in enumerate(classes):
+        assert cl.packed is not None, "weights not packed"
+        c = d.cls[i]
+        c.taps, c.w, c.ntaps = cl.taps_dev.data_ptr(), cl.packed.data_ptr(), len(cl.taps)
+        c.Qt, c.Qh, c.Qw = cl.Q
+        c.po_t, c.po_h, c.po_w = cl.po
+    return d
+
+
+def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0) -> _abi.WgradDesc:
+    """x = layer input, dy = gradient of the layer output, dw = fp32 gradient in torch weight layout."""
+    geo = plan.wgrad_geom
+    cl = plan.wgrad_cls
+    g, p = (x, dy) if geo["g_is_input"] else (dy, x)
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    assert g.C == geo["Cg"] and p.C == geo["Cp"], (g.C, geo["Cg"], p.C, geo["Cp"])
+    # only the gathered side may carry zero-padded channels (Cg_real); the plain side indexes dw directly
+    assert geo["Cp"] == (plan.spec.Cout if geo["g_is_input"] else plan.spec.Cin), "padded channels on the plain side"
+    d = _abi.WgradDesc()
+    d.g, d.p, d.dw = g.ptr, p.ptr, dw.data_ptr()
+    d.taps, d.wtap = cl.taps_dev.data_ptr(), cl.wtap_dev.data_ptr()
+    d.g_row_stride, d.p_row_stride, d.s_p, d.s_g = g.row_stride, p.row_stride, geo["s_p"], geo["s_g"]
+    d.g_c_off, d.p_c_off, d.Cg, d.Cp, d.Cg_real = g.c_off, p.c_off, geo["Cg"], geo["Cp"], geo["Cg_real"]
+    d.N = x.N
+    d.Tg, d.Hg, d.Wg = g.dims
+    d.Tp, d.Hp, d.Wp = p.dims
+    d.Qt, d.Qh, d.Qw = geo["Q"]
+    d.sg_t, d.sg_h, d.sg_w = geo["sg"]
+    d.sp_t, d.sp_h, d.sp_w = geo["sp"]
+    d.pp_t = d.pp_h = d.pp_w = 0
+    d.ntaps, d.bn_tile, d.nsplit, d.atomic = len(cl.taps), int(bn_tile), int(nsplit), int(atomic)
+    return d
