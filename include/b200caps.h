@@ -58,7 +58,7 @@ typedef struct {
   int32_t in_c_off, out_c_off, Cin, Cout;
   int32_t N, Ti, Hi, Wi, To, Ho, Wo;
   int32_t si_t, si_h, si_w, so_t, so_h, so_w;
-  int32_t out_fp32;     /* 0: bf16 output, 1: fp32 output */
+  int32_t out_fp32;     /* 0: bf16 rows, 1: fp32 rows, 2: fp32 planar out[c][pos] (out_row_stride = plane stride) */
   int32_t relu;         /* apply ReLU */
   int32_t sigmoid_from; /* apply sigmoid to output channels >= this (PrimaryCaps 'a'), <0: none */
   int32_t accumulate;   /* out += result (gradient accumulation) */
@@ -179,13 +179,13 @@ int b2c_caps_head_bwd(const void* dx, const float* mask, const float* dact, cons
  * Losses (utils/losses.py, utils/helpers.py, main_ucf101.py:89-148)
  * ---------------------------------------------------------------------------------- */
 /* BCEWithLogits(mean) + Dice over the labeled subset (main_ucf101.py:89-92, losses.py:44-57).
- * logits fp32 (P, V); targets fp32; lab_idx int32 [n_lab] rows of logits; sums: fp32[4] zeroed
- * (bce_sum, sum p*t, sum p, sum t).  loss out: fp32[2] = (bce, dice). */
+ * logits fp32 (P, V); targets fp32; lab_idx int32 [n_lab] rows of logits; sums: fp64[4] scratch
+ * (bce_sum, sum p*t, sum p, sum t; zeroed by the call).  loss out: fp32[2] = (bce, dice). */
 int b2c_seg_loss_fwd(const float* logits, const float* targets, const int32_t* lab_idx, int32_t n_lab, int64_t V,
-                     float* sums, float* loss, b2c_stream_t s);
+                     double* sums, float* loss, b2c_stream_t s);
 /* dlogits[lab rows] += w_bce * dBCE + w_dice * dDice  (other rows untouched) */
 int b2c_seg_loss_bwd(const float* logits, const float* targets, const int32_t* lab_idx, int32_t n_lab, int64_t V,
-                     const float* sums, float w_bce, float w_dice, float* dlogits, b2c_stream_t s);
+                     const double* sums, float w_bce, float w_dice, float* dlogits, b2c_stream_t s);
 /* SpreadLoss (losses.py:14-37) on rows lab_idx of act (P,C); loss fp32[2] (loss, absloss);
  * dact rows (+)= w * dloss */
 int b2c_spread_loss(const float* act, const float* target, const int32_t* lab_idx, int32_t n_lab, int32_t C, float m_min,
@@ -203,15 +203,15 @@ int b2c_gv_mask(const float* out, float* m, float* mm, int32_t P, int32_t H, int
 /* consistency loss + gradients.  mode bit0: bv, bit1: gv.
  *   d = flipW(flp) - out ; l2 = mean(d^2) ; lv = mean(w_clk*d^2) + mean(flipT(w_anti)*d^2) ;
  *   lg = mean_thw( mean_j w_j * mean_i d_i^2 )   (the (B,B,...) broadcast of main_ucf101.py:130-132)
- * acc: fp32[4+2*T*H*W] scratch zeroed by caller; loss out fp32[4] = (cons, l2, lv, lg).
- * Two launches: _reduce then _grad (dout (+)= , dflp (+)= , scaled by wt). */
+ * acc: fp64[4] scratch (zeroed by _reduce); loss out fp32[4] = (cons, l2, lv, lg).
+ * _reduce + _finish give the loss; _grad adds wt * dcons/d{out,flp} into dout / dflp. */
 int b2c_cons_reduce(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
-                    const float* mm_bv, const float* mm_gv, float* acc, int32_t P, int32_t H, int32_t W, int32_t mode,
+                    const float* mm_bv, const float* mm_gv, double* acc, int32_t P, int32_t H, int32_t W, int32_t mode,
                     b2c_stream_t s);
-int b2c_cons_finish(const float* acc, float* loss, int32_t P, int32_t H, int32_t W, int32_t mode, float wt_ramp,
+int b2c_cons_finish(const double* acc, float* loss, int32_t P, int32_t H, int32_t W, int32_t mode, float wt_ramp,
                     float bv_wt, float gv_wt, b2c_stream_t s);
 int b2c_cons_grad(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
-                  const float* mm_bv, const float* mm_gv, const float* acc, float* dout, float* dflp, int32_t P,
+                  const float* mm_bv, const float* mm_gv, float* dout, float* dflp, int32_t P,
                   int32_t H, int32_t W, int32_t mode, float wt_ramp, float bv_wt, float gv_wt, float wt, b2c_stream_t s);
 
 /* ------------------------------------------------------------------------------------

@@ -1,0 +1,715 @@
+// Bandwidth-bound kernels of the step: layout conversion, train-mode BatchNorm (+ReLU, + concat slot),
+// same-padding max-pool, Dropout3d channel scale, activation backward + bias gradient, the 27-tap
+// 'smooth' stencil.  Activations are channels-last bf16 views (ptr, row_stride, c_off); every thread
+// moves 16-byte (8-channel) vectors; reductions go warp/registers -> shared -> one fp32 atomic per
+// block and channel.
+#include "common.cuh"
+#include "../../include/b200caps.h"
+
+long long b2c_launches_add(long long n);
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct RowMap {
+  int cv;        // this thread's channel-vector index
+  int rlane;     // this thread's row lane inside the block
+  int rpb;       // rows per block iteration
+  bool active;
+};
+// block threads are arranged as [rpb][CV]; threads beyond rpb*CV idle
+__device__ __forceinline__ RowMap row_map(int CV) {
+  RowMap m;
+  m.rpb = kBlock / CV;
+  if (m.rpb < 1) m.rpb = 1;
+  m.cv = threadIdx.x % CV;
+  m.rlane = threadIdx.x / CV;
+  m.active = m.rlane < m.rpb;
+  return m;
+}
+
+__device__ __forceinline__ uint4 ld16(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st16(bf16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int N, int C, long long THW,
+                                      int Cpad) {
+  const long long total = (long long)N * THW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / THW, pos = i - n * THW;
+    const float* src = in + n * C * THW + pos;
+    bf16* dst = out + i * Cpad;
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? src[(long long)(c0 + j) * THW] : 0.f;
+      st16(dst + c0, pack8(v));
+    }
+  }
+}
+
+__global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ in, long long in_row_stride, int in_c_off, float* __restrict__ out,
+                                      int N, int C, long long THW) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < THW && c < C) v = __bfloat162float(in[(n * THW + p) * in_row_stride + in_c_off + c]);
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    if (p < THW && c < C) out[(n * C + c) * THW + p] = tile[threadIdx.x][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm statistics: grid (blocks, groups)
+__global__ void __launch_bounds__(kBlock) bn_stats_kernel(const bf16* __restrict__ x, long long rows_per_group, int C,
+                                                          long long row_stride, int c_off, float* __restrict__ ws) {
+  const int CV = C / 8;
+  const RowMap m = row_map(CV);
+  const int g = blockIdx.y;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (m.active) {
+    const bf16* base = x + (long long)g * rows_per_group * row_stride + c_off + m.cv * 8;
+    for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
+      float v[8];
+      unpack8(ld16(base + r * row_stride), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += v[j];
+        s2[j] += v[j] * v[j];
+      }
+    }
+  }
+  // block reduce over row lanes through shared memory
+  extern __shared__ float sh[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[m.cv * 8 + j], s1[j]);
+      atomicAdd(&sh[C + m.cv * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  float* w = ws + (long long)g * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&w[i], sh[i]);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ ws, long long rows_per_group, int C, int groups,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* running_mean, float* running_var,
+                                   float momentum, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double M = (double)rows_per_group;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+  for (int g = 0; g < groups; ++g) {
+    const double s1 = ws[(long long)g * 2 * C + c], s2 = ws[(long long)g * 2 * C + C + c];
+    const double mu = s1 / M;
+    double var = s2 / M - mu * mu;
+    if (var < 0) var = 0;
+    mean[g * C + c] = (float)mu;
+    rstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    const double unb = rows_per_group > 1 ? var * M / (M - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * (float)mu;
+    rv = (1.f - momentum) * rv + momentum * (float)unb;
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
+}
+
+__global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const bf16* __restrict__ x, long long rows_per_group, int C,
+                                                               long long x_rs, int x_co, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, bf16* __restrict__ y, long long y_rs,
+                                                               int y_co, int relu) {
+  const int CV = C / 8;
+  const RowMap m = row_map(CV);
+  if (!m.active) return;
+  const int g = blockIdx.y;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = m.cv * 8 + j;
+    sc[j] = rstd[g * C + c] * gamma[c];
+    sf[j] = beta[c] - mean[g * C + c] * sc[j];
+  }
+  const long long row0 = (long long)g * rows_per_group;
+  for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
+    float v[8];
+    unpack8(ld16(x + (row0 + r) * x_rs + x_co + m.cv * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = v[j] * sc[j] + sf[j];
+      if (relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    st16(y + (row0 + r) * y_rs + y_co + m.cv * 8, pack8(v));
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
+                                                               const bf16* __restrict__ y, long long y_rs, int y_co,
+                                                               const bf16* __restrict__ x, long long x_rs, int x_co,
+                                                               long long rows_per_group, int C, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, float* __restrict__ ws, int relu) {
+  const int CV = C / 8;
+  const RowMap m = row_map(CV);
+  const int g = blockIdx.y;
+  float s1[8], s2[8], mu[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean[g * C + m.cv * 8 + j];
+      rs[j] = rstd[g * C + m.cv * 8 + j];
+    }
+    const long long row0 = (long long)g * rows_per_group;
+    for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
+      float d[8], yy[8], xx[8];
+      unpack8(ld16(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8), d);
+      unpack8(ld16(x + (row0 + r) * x_rs + x_co + m.cv * 8), xx);
+      if (relu) unpack8(ld16(y + (row0 + r) * y_rs + y_co + m.cv * 8), yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
+        s1[j] += dr;
+        s2[j] += dr * (xx[j] - mu[j]) * rs[j];
+      }
+    }
+  }
+  extern __shared__ float sh[];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[m.cv * 8 + j], s1[j]);
+      atomicAdd(&sh[C + m.cv * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  float* w = ws + (long long)g * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&w[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
+                                                              const bf16* __restrict__ y, long long y_rs, int y_co,
+                                                              const bf16* __restrict__ x, long long x_rs, int x_co,
+                                                              long long rows_per_group, int C, int groups,
+                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ ws,
+                                                              bf16* __restrict__ dx, long long dx_rs, int dx_co, float* dgamma,
+                                                              float* dbeta, int relu) {
+  const int CV = C / 8;
+  const RowMap m = row_map(CV);
+  const int g = blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f, b = 0.f;
+      for (int gg = 0; gg < groups; ++gg) {
+        b += ws[(long long)gg * 2 * C + c];
+        a += ws[(long long)gg * 2 * C + C + c];
+      }
+      dgamma[c] += a;
+      dbeta[c] += b;
+    }
+  }
+  if (!m.active) return;
+  const float invM = 1.f / (float)rows_per_group;
+  float mu[8], rs[8], k0[8], a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = m.cv * 8 + j;
+    mu[j] = mean[g * C + c];
+    rs[j] = rstd[g * C + c];
+    k0[j] = gamma[c] * rs[j];
+    a1[j] = ws[(long long)g * 2 * C + c] * invM;
+    a2[j] = ws[(long long)g * 2 * C + C + c] * invM;
+  }
+  const long long row0 = (long long)g * rows_per_group;
+  for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
+    float d[8], yy[8], xx[8], o[8];
+    unpack8(ld16(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8), d);
+    unpack8(ld16(x + (row0 + r) * x_rs + x_co + m.cv * 8), xx);
+    if (relu) unpack8(ld16(y + (row0 + r) * y_rs + y_co + m.cv * 8), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
+      o[j] = k0[j] * (dr - a1[j] - (xx[j] - mu[j]) * rs[j] * a2[j]);
+    }
+    st16(dx + (row0 + r) * dx_rs + dx_co + m.cv * 8, pack8(o));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PoolGeom {
+  int N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw;
+};
+
+__global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restrict__ x, long long x_rs, int x_co,
+                                                             bf16* __restrict__ y, long long y_rs, int y_co,
+                                                             uint8_t* __restrict__ idx, PoolGeom G) {
+  const int CV = G.C / 8;
+  const long long total = (long long)G.N * G.To * G.Ho * G.Wo * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long o = i / CV;
+    const long long orow = o;
+    const int ow = (int)(o % G.Wo); o /= G.Wo;
+    const int oh = (int)(o % G.Ho); o /= G.Ho;
+    const int ot = (int)(o % G.To); o /= G.To;
+    const int n = (int)o;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 255;
+    }
+    int tap = 0;
+    for (int a = 0; a < G.kt; ++a) {
+      const int it = ot * G.st - G.pt + a;
+      for (int b = 0; b < G.kh; ++b) {
+        const int ih = oh * G.sh - G.ph + b;
+        for (int c = 0; c < G.kw; ++c, ++tap) {
+          const int iw = ow * G.sw - G.pw + c;
+          float v[8];
+          const bool inb = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi && (unsigned)iw < (unsigned)G.Wi;
+          if (inb) {
+            unpack8(ld16(x + ((((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi + iw) * x_rs + x_co + cv * 8), v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;  // F.pad zeros are real candidates (pytorch_i3d.py:44)
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (v[j] > best[j]) {   // strict: first occurrence wins, like ATen
+              best[j] = v[j];
+              bi[j] = inb ? tap : 255;
+            }
+          }
+        }
+      }
+    }
+    st16(y + orow * y_rs + y_co + cv * 8, pack8(best));
+    uint2 pk;
+    pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + orow * G.C + cv * 8) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
+                                                             const uint8_t* __restrict__ idx, bf16* __restrict__ dx,
+                                                             long long dx_rs, int dx_co, PoolGeom G, int accumulate) {
+  const int CV = G.C / 8;
+  const long long total = (long long)G.N * G.Ti * G.Hi * G.Wi * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const long long irow = p;
+    const int iw = (int)(p % G.Wi); p /= G.Wi;
+    const int ih = (int)(p % G.Hi); p /= G.Hi;
+    const int it = (int)(p % G.Ti); p /= G.Ti;
+    const int n = (int)p;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a = 0; a < G.kt; ++a) {
+      const int nt = it + G.pt - a;
+      if (nt < 0 || nt % G.st) continue;
+      const int ot = nt / G.st;
+      if (ot >= G.To) continue;
+      for (int b = 0; b < G.kh; ++b) {
+        const int nh = ih + G.ph - b;
+        if (nh < 0 || nh % G.sh) continue;
+        const int oh = nh / G.sh;
+        if (oh >= G.Ho) continue;
+        for (int c = 0; c < G.kw; ++c) {
+          const int nw = iw + G.pw - c;
+          if (nw < 0 || nw % G.sw) continue;
+          const int ow = nw / G.sw;
+          if (ow >= G.Wo) continue;
+          const int tap = (a * G.kh + b) * G.kw + c;
+          const long long orow = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo + ow;
+          const uint2 pk = *reinterpret_cast<const uint2*>(idx + orow * G.C + cv * 8);
+          float d[8];
+          unpack8(ld16(dy + orow * dy_rs + dy_co + cv * 8), d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t w = j < 4 ? pk.x : pk.y;
+            const int bi = (w >> ((j & 3) * 8)) & 0xff;
+            if (bi == tap) acc[j] += d[j];
+          }
+        }
+      }
+    }
+    bf16* dst = dx + irow * dx_rs + dx_co + cv * 8;
+    if (accumulate) {
+      float e[8];
+      unpack8(ld16(dst), e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += e[j];
+    }
+    st16(dst, pack8(acc));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) channel_scale_kernel(const bf16* __restrict__ x, long long x_rs, int x_co,
+                                                               const float* __restrict__ scale, bf16* __restrict__ y, long long y_rs,
+                                                               int y_co, int N, long long rows_per_n, int C) {
+  const int CV = C / 8;
+  const long long total = (long long)N * rows_per_n * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const long long row = i / CV;
+    const long long n = row / rows_per_n;
+    float v[8];
+    unpack8(ld16(x + row * x_rs + x_co + cv * 8), v);
+    const float* s = scale + n * C + cv * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= s[j];
+    st16(y + row * y_rs + y_co + cv * 8, pack8(v));
+  }
+}
+
+// grid (blocks, N): per-sample so the scale row is fixed per block
+__global__ void __launch_bounds__(kBlock) act_bwd_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
+                                                         const bf16* __restrict__ y, long long y_rs, int y_co,
+                                                         const float* __restrict__ scale, bf16* __restrict__ dz, long long dz_rs,
+                                                         int dz_co, float* __restrict__ dbias, long long rows_per_n, int C, int relu) {
+  const int CV = C / 8;
+  const RowMap m = row_map(CV);
+  const int n = blockIdx.y;
+  float s1[8], sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = 0.f;
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = scale ? scale[(long long)n * C + m.cv * 8 + j] : 1.f;
+    const long long row0 = (long long)n * rows_per_n;
+    for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_n; r += (long long)gridDim.x * m.rpb) {
+      float d[8], yy[8];
+      unpack8(ld16(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8), d);
+      if (relu) unpack8(ld16(y + (row0 + r) * y_rs + y_co + m.cv * 8), yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = d[j] * sc[j];
+        if (relu && !(yy[j] > 0.f)) v = 0.f;
+        d[j] = v;
+        s1[j] += v;
+      }
+      if (dz) st16(dz + (row0 + r) * dz_rs + dz_co + m.cv * 8, pack8(d));
+    }
+  }
+  if (!dbias) return;
+  extern __shared__ float sh[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[m.cv * 8 + j], s1[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(kBlock) add_kernel(const bf16* __restrict__ a, long long a_rs, int a_co, const bf16* __restrict__ b,
+                                                     long long b_rs, int b_co, bf16* __restrict__ o, long long o_rs, int o_co,
+                                                     long long rows, int C) {
+  const int CV = C / 8;
+  const long long total = rows * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const long long row = i / CV;
+    float x[8], y[8];
+    unpack8(ld16(a + row * a_rs + a_co + cv * 8), x);
+    unpack8(ld16(b + row * b_rs + b_co + cv * 8), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    st16(o + row * o_rs + o_co + cv * 8, pack8(x));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// smooth = ConvTranspose3d(128->1, k3, p1): out[o] = bias + sum_k P_k[o + 1 - k], P planar fp32 [32][rows]
+__global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __restrict__ P, float* __restrict__ out, float bias,
+                                                               int N, int T, int H, int W) {
+  const long long rows = (long long)N * T * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    long long p = i;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H); p /= H;
+    const int t = (int)(p % T);
+    float acc = bias;
+    int tap = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int tt = t + 1 - a;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int hh = h + 1 - b;
+#pragma unroll
+        for (int c = 0; c < 3; ++c, ++tap) {
+          const int ww = w + 1 - c;
+          if ((unsigned)tt < (unsigned)T && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
+            acc += __ldg(P + (long long)tap * rows + i + ((long long)(1 - a) * H + (1 - b)) * W + (1 - c));
+        }
+      }
+    }
+    out[i] = acc;
+  }
+}
+// adjoint: dP[i][k] = dout[i - 1 + k] (bf16 rows of 32, taps 27..31 zero)
+__global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dP, int N, int T,
+                                                               int H, int W) {
+  const long long rows = (long long)N * T * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    long long p = i;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H); p /= H;
+    const int t = (int)(p % T);
+    float v[32];
+    int tap = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int tt = t - 1 + a;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int hh = h - 1 + b;
+#pragma unroll
+        for (int c = 0; c < 3; ++c, ++tap) {
+          const int ww = w - 1 + c;
+          float g = 0.f;
+          if ((unsigned)tt < (unsigned)T && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
+            g = __ldg(dout + i + ((long long)(a - 1) * H + (b - 1)) * W + (c - 1));
+          v[tap] = g;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+    bf16* dst = dP + i * 32;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st16(dst + q * 8, pack8(v + q * 8));
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+inline int grid_for(long long work_items, int per_block = kBlock, int waves = 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)b2c_num_sms() * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+inline int row_grid(long long rows, int C, int waves = 4) {
+  int rpb = kBlock / (C / 8);
+  if (rpb < 1) rpb = 1;
+  return grid_for(rows, rpb, waves);
+}
+
+#define CHECK_VIEW(name, C, rs, co)                                                                         \
+  B2C_REQUIRE((C) > 0 && (C) % 8 == 0 && (rs) % 8 == 0 && (co) % 8 == 0 && (C) / 8 <= kBlock, name ": bad view C=%d rs=%lld co=%d", \
+              (int)(C), (long long)(rs), (int)(co))
+
+}  // namespace
+
+B2C_API int b2c_ncdhw_to_ndhwc(const float* in, void* out, int32_t N, int32_t C, int64_t THW, int32_t Cpad, b2c_stream_t s) {
+  B2C_REQUIRE(in && out && N > 0 && C > 0 && Cpad % 8 == 0 && Cpad >= C, "ncdhw_to_ndhwc: bad args");
+  ncdhw_to_ndhwc_kernel<<<grid_for((long long)N * THW), kBlock, 0, (cudaStream_t)s>>>(in, (bf16*)out, N, C, THW, Cpad);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("ncdhw_to_ndhwc");
+  return 0;
+}
+
+B2C_API int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_t in_c_off, float* out, int32_t N, int32_t C,
+                                   int64_t THW, b2c_stream_t s) {
+  B2C_REQUIRE(in && out && N > 0 && C > 0, "ndhwc_to_ncdhw: bad args");
+  dim3 grid((unsigned)((THW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), block(32, 8);
+  ndhwc_to_ncdhw_kernel<<<grid, block, 0, (cudaStream_t)s>>>((const bf16*)in, in_row_stride, in_c_off, out, N, C, THW);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("ndhwc_to_ncdhw");
+  return 0;
+}
+
+B2C_API int b2c_bn_stats(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
+                         float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
+                         b2c_stream_t s) {
+  B2C_REQUIRE(x && ws && mean && rstd, "bn_stats: null pointer");
+  CHECK_VIEW("bn_stats", C, row_stride, c_off);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_stats: rows=%lld not divisible by groups=%d", (long long)rows, groups);
+  const long long rpg = rows / groups;
+  dim3 grid((unsigned)row_grid(rpg, C, 2), (unsigned)groups);
+  bn_stats_kernel<<<grid, kBlock, 2 * C * sizeof(float), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(ws, rpg, C, groups, mean, rstd, running_mean, running_var,
+                                                                  momentum, eps);
+  b2c_launches_add(2);
+  B2C_LAUNCH_CHECK("bn_stats");
+  return 0;
+}
+
+B2C_API int b2c_bn_relu_apply(const void* x, int64_t rows, int32_t C, int64_t x_rs, int32_t x_co, int32_t groups, const float* mean,
+                              const float* rstd, const float* gamma, const float* beta, void* y, int64_t y_rs, int32_t y_co,
+                              int32_t relu, b2c_stream_t s) {
+  B2C_REQUIRE(x && y && mean && rstd && gamma && beta, "bn_relu_apply: null pointer");
+  CHECK_VIEW("bn_relu_apply", C, x_rs, x_co);
+  CHECK_VIEW("bn_relu_apply(y)", C, y_rs, y_co);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_relu_apply: rows not divisible by groups");
+  const long long rpg = rows / groups;
+  dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
+  bn_relu_apply_kernel<<<grid, kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, rpg, C, x_rs, x_co, mean, rstd, gamma, beta, (bf16*)y,
+                                                             y_rs, y_co, relu);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("bn_relu_apply");
+  return 0;
+}
+
+B2C_API int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_rs, int32_t dy_co, const void* y, int64_t y_rs, int32_t y_co,
+                                   const void* x, int64_t x_rs, int32_t x_co, int64_t rows, int32_t C, int32_t groups,
+                                   const float* mean, const float* rstd, float* ws, int32_t relu, b2c_stream_t s) {
+  B2C_REQUIRE(dy && x && mean && rstd && ws && (y || !relu), "bn_bwd_reduce: null pointer");
+  CHECK_VIEW("bn_bwd_reduce(dy)", C, dy_rs, dy_co);
+  CHECK_VIEW("bn_bwd_reduce(x)", C, x_rs, x_co);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_reduce: rows not divisible by groups");
+  const long long rpg = rows / groups;
+  dim3 grid((unsigned)row_grid(rpg, C, 2), (unsigned)groups);
+  bn_bwd_reduce_kernel<<<grid, kBlock, 2 * C * sizeof(float), (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs,
+                                                                                 y_co, (const bf16*)x, x_rs, x_co, rpg, C, mean, rstd,
+                                                                                 ws, relu);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("bn_bwd_reduce");
+  return 0;
+}
+
+B2C_API int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_rs, int32_t dy_co, const void* y, int64_t y_rs, int32_t y_co,
+                                  const void* x, int64_t x_rs, int32_t x_co, int64_t rows, int32_t C, int32_t groups,
+                                  const float* mean, const float* rstd, const float* gamma, const float* ws, void* dx,
+                                  int64_t dx_rs, int32_t dx_co, float* dgamma, float* dbeta, int32_t relu, b2c_stream_t s) {
+  B2C_REQUIRE(dy && x && dx && mean && rstd && gamma && ws && (y || !relu), "bn_bwd_apply: null pointer");
+  CHECK_VIEW("bn_bwd_apply(dy)", C, dy_rs, dy_co);
+  CHECK_VIEW("bn_bwd_apply(dx)", C, dx_rs, dx_co);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_apply: rows not divisible by groups");
+  const long long rpg = rows / groups;
+  dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
+  bn_bwd_apply_kernel<<<grid, kBlock, 0, (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs, y_co, (const bf16*)x,
+                                                            x_rs, x_co, rpg, C, groups, mean, rstd, gamma, ws, (bf16*)dx, dx_rs, dx_co,
+                                                            dgamma, dbeta, relu);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("bn_bwd_apply");
+  return 0;
+}
+
+B2C_API int b2c_maxpool_fwd(const void* x, int64_t x_rs, int32_t x_co, void* y, int64_t y_rs, int32_t y_co, uint8_t* idx, int32_t N,
+                            int32_t C, int32_t Ti, int32_t Hi, int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, int32_t kt, int32_t kh,
+                            int32_t kw, int32_t st, int32_t sh, int32_t sw, int32_t pt, int32_t ph, int32_t pw, b2c_stream_t s) {
+  B2C_REQUIRE(x && y && idx, "maxpool_fwd: null pointer");
+  CHECK_VIEW("maxpool_fwd(x)", C, x_rs, x_co);
+  CHECK_VIEW("maxpool_fwd(y)", C, y_rs, y_co);
+  B2C_REQUIRE(kt * kh * kw < 255, "maxpool_fwd: window too large");
+  PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
+  const long long total = (long long)N * To * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, x_rs, x_co, (bf16*)y, y_rs, y_co, idx, G);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("maxpool_fwd");
+  return 0;
+}
+
+B2C_API int b2c_maxpool_bwd(const void* dy, int64_t dy_rs, int32_t dy_co, const uint8_t* idx, void* dx, int64_t dx_rs, int32_t dx_co,
+                            int32_t N, int32_t C, int32_t Ti, int32_t Hi, int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, int32_t kt,
+                            int32_t kh, int32_t kw, int32_t st, int32_t sh, int32_t sw, int32_t pt, int32_t ph, int32_t pw,
+                            int32_t accumulate, b2c_stream_t s) {
+  B2C_REQUIRE(dy && dx && idx, "maxpool_bwd: null pointer");
+  CHECK_VIEW("maxpool_bwd(dy)", C, dy_rs, dy_co);
+  CHECK_VIEW("maxpool_bwd(dx)", C, dx_rs, dx_co);
+  PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
+  const long long total = (long long)N * Ti * Hi * Wi * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, idx, (bf16*)dx, dx_rs, dx_co, G,
+                                                                      accumulate);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("maxpool_bwd");
+  return 0;
+}
+
+B2C_API int b2c_channel_scale(const void* x, int64_t x_rs, int32_t x_co, const float* scale_nc, void* y, int64_t y_rs, int32_t y_co,
+                              int32_t N, int64_t rows_per_n, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(x && y && scale_nc, "channel_scale: null pointer");
+  CHECK_VIEW("channel_scale(x)", C, x_rs, x_co);
+  CHECK_VIEW("channel_scale(y)", C, y_rs, y_co);
+  channel_scale_kernel<<<grid_for((long long)N * rows_per_n * (C / 8)), kBlock, 0, (cudaStream_t)s>>>(
+      (const bf16*)x, x_rs, x_co, scale_nc, (bf16*)y, y_rs, y_co, N, rows_per_n, C);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("channel_scale");
+  return 0;
+}
+
+B2C_API int b2c_act_bwd(const void* dy, int64_t dy_rs, int32_t dy_co, const void* y, int64_t y_rs, int32_t y_co, const float* scale_nc,
+                        void* dz, int64_t dz_rs, int32_t dz_co, float* dbias, int32_t N, int64_t rows_per_n, int32_t C, int32_t relu,
+                        b2c_stream_t s) {
+  B2C_REQUIRE(dy && (y || !relu) && (dz || dbias), "act_bwd: null pointer");
+  CHECK_VIEW("act_bwd(dy)", C, dy_rs, dy_co);
+  if (dz) CHECK_VIEW("act_bwd(dz)", C, dz_rs, dz_co);
+  int gx = row_grid(rows_per_n, C, 2);
+  if (gx * N > b2c_num_sms() * 8) gx = (b2c_num_sms() * 8 + N - 1) / N;
+  dim3 grid((unsigned)gx, (unsigned)N);
+  act_bwd_kernel<<<grid, kBlock, C * sizeof(float), (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs, y_co,
+                                                                       scale_nc, (bf16*)dz, dz_rs, dz_co, dbias, rows_per_n, C, relu);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("act_bwd");
+  return 0;
+}
+
+B2C_API int b2c_add(const void* a, int64_t a_rs, int32_t a_co, const void* b, int64_t b_rs, int32_t b_co, void* out, int64_t o_rs,
+                    int32_t o_co, int64_t rows, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(a && b && out, "add: null pointer");
+  CHECK_VIEW("add(a)", C, a_rs, a_co);
+  CHECK_VIEW("add(b)", C, b_rs, b_co);
+  CHECK_VIEW("add(out)", C, o_rs, o_co);
+  add_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, (cudaStream_t)s>>>((const bf16*)a, a_rs, a_co, (const bf16*)b, b_rs, b_co,
+                                                                      (bf16*)out, o_rs, o_co, rows, C);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("add");
+  return 0;
+}
+
+B2C_API int b2c_stencil27_fwd(const float* P, float* out, float bias, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s) {
+  B2C_REQUIRE(P && out && N > 0, "stencil27_fwd: bad args");
+  stencil27_fwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(P, out, bias, N, T, H, W);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("stencil27_fwd");
+  return 0;
+}
+
+B2C_API int b2c_stencil27_bwd(const float* dout, void* dP, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s) {
+  B2C_REQUIRE(dout && dP && N > 0, "stencil27_bwd: bad args");
+  stencil27_bwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, N, T, H, W);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("stencil27_bwd");
+  return 0;
+}
+
+B2C_API int b2c_fill_f32(float* p, int64_t n, float v, b2c_stream_t s) {
+  B2C_REQUIRE(p || n == 0, "fill_f32: null pointer");
+  if (n == 0) return 0;
+  fill_f32_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)s>>>(p, n, v);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("fill_f32");
+  return 0;
+}

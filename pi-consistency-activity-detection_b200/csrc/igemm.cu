@@ -212,7 +212,15 @@ __global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
         }
-        if (d.out_fp32) {
+        if (d.out_fp32 == 2) {
+          // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
+          float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (d.accumulate) vv[i] += o[(long long)i * d.out_row_stride];
+            o[(long long)i * d.out_row_stride] = vv[i];
+          }
+        } else if (d.out_fp32) {
           float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
           float4* o4 = reinterpret_cast<float4*>(o);
           if (d.accumulate) {
@@ -499,7 +507,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(d.Cin > 0 && d.Cin % 8 == 0, "conv_fprop: Cin=%d must be a positive multiple of 8", d.Cin);
   B2C_REQUIRE(d.Cout > 0 && d.Cout % 8 == 0, "conv_fprop: Cout=%d must be a positive multiple of 8", d.Cout);
   B2C_REQUIRE(d.in_c_off % 8 == 0 && d.out_c_off % 8 == 0, "conv_fprop: channel offsets must be multiples of 8");
-  B2C_REQUIRE(d.in_row_stride % 8 == 0 && d.out_row_stride % (d.out_fp32 ? 4 : 8) == 0, "conv_fprop: row strides unaligned");
+  B2C_REQUIRE(d.in_row_stride % 8 == 0 && (d.out_fp32 == 2 || d.out_row_stride % (d.out_fp32 ? 4 : 8) == 0),
+              "conv_fprop: row strides unaligned");
   B2C_REQUIRE(d.nclass >= 1 && d.nclass <= 8, "conv_fprop: nclass=%d out of range", d.nclass);
   B2C_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.out & 15) == 0, "conv_fprop: tensors must be 16B aligned");
   if (d.bn_tile <= 0) d.bn_tile = pick_bn_tile(d.Cout);

@@ -1,0 +1,550 @@
+// Capsule head: fused EM routing (ConvCaps with K=(1,1), capsules_ucf101.py:290-309; m_step :108-156,
+// e_step :158-182; 3 iterations) forward and hand-derived backward, plus the small glue kernels around
+// it (class-activation mean, pose masking, their adjoints).
+//
+// Parallelisation: one CTA (8 warps) per spatial location, persistent over locations.
+//   lane  = output capsule type j (C <= 32 active lanes)
+//   warp w owns input capsule types i = w, w+8, w+16, w+24   (B = 32)
+// so every (i,j) vote V_ij (4x4) lives in the registers of exactly one thread for the whole routing:
+// the 32x24x16 votes are never written to memory (the reference materialises them 60 times).
+// Sums over j are warp shuffles; sums over i are 8-way cross-warp reductions through shared memory.
+// The transformation matrices W (32,C,4,4) sit in shared memory as [i][h][lane] (conflict-free).
+//
+// cost_h_stdv (capsules_ucf101.py:144) squares a SUM of deviations that is analytically zero; the
+// reference's fp32 value is rounding noise.  We evaluate that 24-term sum in fp64 so the result sits
+// on the fp64 reference (the parity yardstick); its gradient is analytically zero.
+#include "common.cuh"
+#include "../../include/b200caps.h"
+
+long long b2c_launches_add(long long n);
+
+namespace {
+
+constexpr int kB = 32;        // input capsule types
+constexpr int kNW = 8;        // warps per CTA
+constexpr int kIPT = kB / kNW;  // i's per thread
+constexpr int kRT = kNW * 32;
+constexpr float kEps = 1e-8f;
+constexpr float kLambda = 1e-6f;
+constexpr float kHalfLn2Pi16 = 14.703016531274763f;  // 16 * 0.5 * ln(2*pi)
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// cross-warp sum of n per-lane values; ping-pong buffers make one __syncthreads per call sufficient
+template <int N>
+__device__ __forceinline__ void block_sum(float* vals, float* red, int& pp, int w, int lane) {
+  float* buf = red + pp * (kNW * 17 * 32);
+  pp ^= 1;
+#pragma unroll
+  for (int q = 0; q < N; ++q) buf[(w * 17 + q) * 32 + lane] = vals[q];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kNW; ++ww) s += buf[(ww * 17 + q) * 32 + lane];
+    vals[q] = s;
+  }
+}
+
+__device__ __forceinline__ void load_W_smem(const float* __restrict__ W, float* sW, int C) {
+  for (int idx = threadIdx.x; idx < kB * 16 * 32; idx += kRT) sW[idx] = 0.f;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kB * C * 16; idx += kRT) {
+    const int h = idx & 15;
+    const int j = (idx >> 4) % C;
+    const int i = (idx >> 4) / C;
+    sW[(i * 16 + h) * 32 + j] = W[idx];
+  }
+}
+
+__device__ __forceinline__ void compute_votes(const float* s_caps, const float* sW, int w, int lane, float (*V)[16]) {
+#pragma unroll
+  for (int k = 0; k < kIPT; ++k) {
+    const int i = w + kNW * k;
+    float M[16], Wr[16];
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+      M[h] = s_caps[i * 16 + h];
+      Wr[h] = sW[(i * 16 + h) * 32 + lane];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) acc = fmaf(M[r * 4 + kk], Wr[kk * 4 + c], acc);
+        V[k][r * 4 + c] = acc;
+      }
+  }
+}
+
+struct MStepOut {
+  float R, T, a, inv_s;
+};
+
+// one M step: in r_prev[k]; out rn[k], Z[k], mu[16], S[16] and scalars.  All warps end with identical
+// per-j values.
+__device__ __forceinline__ MStepOut m_step(const float (*V)[16], const float* r_prev, const float* s_ain, const float* bu,
+                                           float ba, int C, bool active, int w, int lane, float* red, int& pp, float* rn,
+                                           float* Z, float* mu, float* S) {
+  float acc[17];
+#pragma unroll
+  for (int q = 0; q < 17; ++q) acc[q] = 0.f;
+#pragma unroll
+  for (int k = 0; k < kIPT; ++k) {
+    const int i = w + kNW * k;
+    const float rp = active ? r_prev[k] * s_ain[i] : 0.f;
+    Z[k] = warp_sum(rp) + kEps;
+    rn[k] = rp / Z[k];
+    acc[16] += rn[k];
+#pragma unroll
+    for (int h = 0; h < 16; ++h) acc[h] = fmaf(rn[k], V[k][h], acc[h]);
+  }
+  block_sum<17>(acc, red, pp, w, lane);
+  MStepOut o;
+  o.R = acc[16];
+  const float invR = 1.f / (o.R + kEps);
+#pragma unroll
+  for (int h = 0; h < 16; ++h) mu[h] = acc[h] * invR;
+  float sacc[16];
+#pragma unroll
+  for (int h = 0; h < 16; ++h) sacc[h] = 0.f;
+#pragma unroll
+  for (int k = 0; k < kIPT; ++k) {
+    const float c = rn[k] * invR;
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+      const float dv = V[k][h] - mu[h];
+      sacc[h] = fmaf(c, dv * dv, sacc[h]);
+    }
+  }
+  block_sum<16>(sacc, red, pp, w, lane);
+  float T = 0.f;
+#pragma unroll
+  for (int h = 0; h < 16; ++h) {
+    S[h] = sacc[h] + kEps;
+    T += bu[h] + 0.5f * logf(S[h]);
+  }
+  o.T = T;
+  const float cost = T * o.R;
+  // mean and the (analytically zero) sum of deviations, in fp64 over the C active lanes
+  const double cd = active ? (double)cost : 0.0;
+  const double md = warp_sum_d(cd) / (double)C;
+  const double dev = active ? (cd - md) : 0.0;
+  const double sdev = warp_sum_d(dev);
+  const double stdv = sqrt(sdev * sdev / (double)C + (double)kEps);
+  o.inv_s = (float)(1.0 / (stdv + (double)kEps));
+  const float u = kLambda * (ba - ((float)md - cost) * o.inv_s);
+  o.a = 1.f / (1.f + expf(-u));
+  return o;
+}
+
+__device__ __forceinline__ void e_step(const float (*V)[16], const float* mu, const float* S, float a, bool active, float* r_out) {
+  float inv2S[16], lnS = 0.f;
+#pragma unroll
+  for (int h = 0; h < 16; ++h) {
+    inv2S[h] = 0.5f / S[h];
+    lnS += logf(S[h]);
+  }
+  const float base = -0.5f * lnS - kHalfLn2Pi16 + logf(kEps + a);
+#pragma unroll
+  for (int k = 0; k < kIPT; ++k) {
+    float q = 0.f;
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+      const float dv = V[k][h] - mu[h];
+      q = fmaf(dv * dv, inv2S[h], q);
+    }
+    const float z = active ? (base - q) : -INFINITY;
+    const float mx = warp_max(z);
+    const float e = active ? expf(z - mx) : 0.f;
+    r_out[k] = e / warp_sum(e);
+  }
+}
+
+// =====================================================================================
+__global__ void __launch_bounds__(kRT, 2) em_routing_fwd_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+                                                                const float* __restrict__ beta_u, const float* __restrict__ beta_a,
+                                                                float* __restrict__ out, long long b, int C) {
+  extern __shared__ float sm[];
+  float* sW = sm;                          // [32][16][32]
+  float* red = sW + kB * 16 * 32;          // [2][8][17][32]
+  float* s_caps = red + 2 * kNW * 17 * 32; // [544]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool active = lane < C;
+  load_W_smem(W, sW, C);
+  float bu[16], ba = active ? beta_a[lane] : 0.f;
+#pragma unroll
+  for (int h = 0; h < 16; ++h) bu[h] = active ? beta_u[lane * 16 + h] : 0.f;
+  const int ocols = C * 17;
+  int pp = 0;
+  for (long long loc = blockIdx.x; loc < b; loc += gridDim.x) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 544; idx += kRT) s_caps[idx] = caps[loc * 544 + idx];
+    __syncthreads();
+    float V[kIPT][16];
+    compute_votes(s_caps, sW, w, lane, V);
+    float r[kIPT], rn[kIPT], Z[kIPT], mu[16], S[16];
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) r[k] = 1.f / (float)C;
+    MStepOut o;
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+      o = m_step(V, r, s_caps + 512, bu, ba, C, active, w, lane, red, pp, rn, Z, mu, S);
+      if (t < 2) e_step(V, mu, S, o.a, active, r);
+    }
+    if (w == 0 && active) {
+      float* dst = out + loc * ocols;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) dst[lane * 16 + h] = mu[h];   // rows are C*17 floats: not 16B aligned for odd C
+      dst[C * 16 + lane] = o.a;
+    }
+  }
+}
+
+// =====================================================================================
+__global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+                                                                const float* __restrict__ beta_u, const float* __restrict__ beta_a,
+                                                                const float* __restrict__ dout, float* __restrict__ dcaps,
+                                                                float* __restrict__ dW, float* __restrict__ dbeta_u,
+                                                                float* __restrict__ dbeta_a, long long b, int C) {
+  extern __shared__ float sm[];
+  float* sW = sm;                            // [32][16][32]
+  float* sgW = sW + kB * 16 * 32;            // [32][16][32] per-CTA dW accumulator (owner-thread RMW, no atomics)
+  float* red = sgW + kB * 16 * 32;           // [2][8][17][32]
+  float* s_mu = red + 2 * kNW * 17 * 32;     // [3][16][32]
+  float* s_S = s_mu + 3 * 16 * 32;           // [3][16][32]
+  float* s_gbu = s_S + 3 * 16 * 32;          // [17][32]  dbeta_u (16) + dbeta_a (1) accumulators (warp 0)
+  float* s_caps = s_gbu + 17 * 32;           // [544]
+  float* s_dout = s_caps + 544;              // [32*17]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool active = lane < C;
+  load_W_smem(W, sW, C);
+  for (int idx = threadIdx.x; idx < kB * 16 * 32; idx += kRT) sgW[idx] = 0.f;
+  for (int idx = threadIdx.x; idx < 17 * 32; idx += kRT) s_gbu[idx] = 0.f;
+  float bu[16], ba = active ? beta_a[lane] : 0.f;
+#pragma unroll
+  for (int h = 0; h < 16; ++h) bu[h] = active ? beta_u[lane * 16 + h] : 0.f;
+  const int ocols = C * 17;
+  int pp = 0;
+  for (long long loc = blockIdx.x; loc < b; loc += gridDim.x) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 544; idx += kRT) s_caps[idx] = caps[loc * 544 + idx];
+    for (int idx = threadIdx.x; idx < ocols; idx += kRT) s_dout[idx] = dout[loc * ocols + idx];
+    __syncthreads();
+    const float* s_ain = s_caps + 512;
+    float V[kIPT][16];
+    compute_votes(s_caps, sW, w, lane, V);
+
+    // ---- forward with the per-iteration state kept: scalars in registers, mu/S in shared memory ----
+    float rp_s[3][kIPT], rn_s[3][kIPT], Z_s[3][kIPT];
+    float R_s[3], T_s[3], a_s[3], is_s[3];
+    {
+      float r[kIPT], mu[16], S[16];
+#pragma unroll
+      for (int k = 0; k < kIPT; ++k) r[k] = 1.f / (float)C;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) rp_s[t][k] = r[k];
+        const MStepOut o = m_step(V, r, s_ain, bu, ba, C, active, w, lane, red, pp, rn_s[t], Z_s[t], mu, S);
+        R_s[t] = o.R; T_s[t] = o.T; a_s[t] = o.a; is_s[t] = o.inv_s;
+        if (w == 0) {
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            s_mu[(t * 16 + h) * 32 + lane] = mu[h];
+            s_S[(t * 16 + h) * 32 + lane] = S[h];
+          }
+        }
+        if (t < 2) e_step(V, mu, S, o.a, active, r);
+      }
+    }
+    __syncthreads();  // s_mu / s_S visible to all warps
+
+    // ---- backward sweep ----
+    float gV[kIPT][16];
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k)
+#pragma unroll
+      for (int h = 0; h < 16; ++h) gV[k][h] = 0.f;
+    float gmu[16], gS[16], ga, gr[kIPT], gain[kIPT];
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+      gmu[h] = active ? s_dout[lane * 16 + h] : 0.f;
+      gS[h] = 0.f;
+    }
+    ga = active ? s_dout[C * 16 + lane] : 0.f;
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) gr[k] = gain[k] = 0.f;
+
+#pragma unroll
+    for (int t = 2; t >= 0; --t) {
+      const float* mu_t = s_mu + t * 16 * 32 + lane;   // stride 32 per h
+      const float* S_t = s_S + t * 16 * 32 + lane;
+      if (t < 2) {
+        // E-step backward: r^t = softmax_j(ln p_ij + ln(eps + a_j)) feeds iteration t+1
+        float gz[kIPT];
+        float acc[17];
+#pragma unroll
+        for (int q = 0; q < 17; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          const float r = rp_s[t + 1][k];
+          const float dot = warp_sum(gr[k] * r);
+          gz[k] = r * (gr[k] - dot);
+          acc[16] += gz[k];
+        }
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          const float m = mu_t[h * 32], invS = 1.f / S_t[h * 32];
+          float gm = 0.f;
+#pragma unroll
+          for (int k = 0; k < kIPT; ++k) {
+            const float dv = (V[k][h] - m) * invS;
+            gm = fmaf(gz[k], dv, gm);
+            gV[k][h] = fmaf(-gz[k], dv, gV[k][h]);
+          }
+          acc[h] = gm;
+        }
+        block_sum<17>(acc, red, pp, w, lane);
+#pragma unroll
+        for (int h = 0; h < 16; ++h) gmu[h] = acc[h];
+        ga = acc[16] / (kEps + a_s[t]);
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          const float m = mu_t[h * 32], invS = 1.f / S_t[h * 32];
+          float g = 0.f;
+#pragma unroll
+          for (int k = 0; k < kIPT; ++k) {
+            const float dv = V[k][h] - m;
+            g = fmaf(gz[k], 0.5f * invS * (dv * dv * invS - 1.f), g);
+          }
+          acc[h] = g;
+        }
+        block_sum<16>(acc, red, pp, w, lane);
+#pragma unroll
+        for (int h = 0; h < 16; ++h) gS[h] = acc[h];
+      }
+      // M-step backward
+      const float R = R_s[t], invR = 1.f / (R + kEps);
+      const float a = a_s[t];
+      const float gu = active ? ga * a * (1.f - a) : 0.f;
+      const float gcost = kLambda * is_s[t] * (gu - warp_sum(gu) / (float)C);
+      if (w == 0 && active) {
+        s_gbu[16 * 32 + lane] += kLambda * gu;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) s_gbu[h * 32 + lane] += gcost * R;
+      }
+      const float gR = gcost * T_s[t];
+      const float one_m_csum = 1.f - R * invR;
+      float gc[kIPT];
+#pragma unroll
+      for (int k = 0; k < kIPT; ++k) gc[k] = 0.f;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) {
+        const float m = mu_t[h * 32], Sv = S_t[h * 32];
+        const float gSh = gS[h] + gcost * R * 0.5f / Sv;
+        const float gmh = gmu[h] - 2.f * gSh * m * one_m_csum;
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          const float dv = V[k][h] - m;
+          gc[k] = fmaf(gSh, dv * dv, gc[k]);
+          gc[k] = fmaf(gmh, V[k][h], gc[k]);
+          const float c = rn_s[t][k] * invR;
+          gV[k][h] = fmaf(c, gmh + 2.f * gSh * dv, gV[k][h]);
+        }
+      }
+      float D[1] = {0.f};
+#pragma unroll
+      for (int k = 0; k < kIPT; ++k) D[0] = fmaf(gc[k], rn_s[t][k] * invR, D[0]);
+      block_sum<1>(D, red, pp, w, lane);
+      const float gR_tot = gR - D[0] * invR;
+#pragma unroll
+      for (int k = 0; k < kIPT; ++k) {
+        const int i = w + kNW * k;
+        const float grn = active ? (gc[k] * invR + gR_tot) : 0.f;
+        const float dot2 = warp_sum(grn * rn_s[t][k]);
+        const float grp = active ? (grn - dot2) / Z_s[t][k] : 0.f;
+        gain[k] += warp_sum(grp * rp_s[t][k]);
+        gr[k] = grp * s_ain[i];
+      }
+    }
+
+    // ---- votes -> poses / W ----
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+      const int i = w + kNW * k;
+      float M[16], Wr[16];
+#pragma unroll
+      for (int h = 0; h < 16; ++h) {
+        M[h] = s_caps[i * 16 + h];
+        Wr[h] = sW[(i * 16 + h) * 32 + lane];
+      }
+      float mine = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float g = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) g = fmaf(gV[k][r * 4 + c], Wr[kk * 4 + c], g);
+          g = warp_sum(active ? g : 0.f);
+          if (lane == r * 4 + kk) mine = g;
+        }
+      if (lane < 16) dcaps[loc * 544 + i * 16 + lane] = mine;
+      if (lane == 0) dcaps[loc * 544 + 512 + i] = gain[k];
+      if (active) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float g = 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) g = fmaf(M[r * 4 + kk], gV[k][r * 4 + c], g);
+            sgW[(i * 16 + kk * 4 + c) * 32 + lane] += g;
+          }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kB * C * 16; idx += kRT) {
+    const int h = idx & 15;
+    const int j = (idx >> 4) % C;
+    const int i = (idx >> 4) / C;
+    atomicAdd(dW + idx, sgW[(i * 16 + h) * 32 + j]);
+  }
+  if (w == 0 && active) {
+#pragma unroll
+    for (int h = 0; h < 16; ++h) atomicAdd(dbeta_u + lane * 16 + h, s_gbu[h * 32 + lane]);
+    atomicAdd(dbeta_a + lane, s_gbu[16 * 32 + lane]);
+  }
+}
+
+// =====================================================================================
+// glue: rout (N, L, C*16 + C) fp32
+__global__ void class_mean_kernel(const float* __restrict__ rout, float* __restrict__ act, int L, int C) {
+  const int n = blockIdx.x;
+  const int ocols = C * 17;
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    // reference: mean over h then mean over w (capsules_ucf101.py:450-451) == mean over L for a full grid
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += rout[((long long)n * L + l) * ocols + C * 16 + j];
+    act[n * C + j] = s / (float)L;
+  }
+}
+
+__global__ void pose_mask_kernel(const float* __restrict__ rout, const float* __restrict__ mask, bf16* __restrict__ x, int L, int C,
+                                 long long total) {
+  const int ocols = C * 17, pc = C * 16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % (pc / 8));
+    const long long row = i / (pc / 8);
+    const int n = (int)(row / L);
+    const float* src = rout + row * ocols + e * 8;
+    const float m = mask[n * C + (e * 8) / 16];
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = src[q] * m;
+    *reinterpret_cast<uint4*>(x + row * pc + e * 8) = pack8(v);
+  }
+}
+
+__global__ void caps_head_bwd_kernel(const bf16* __restrict__ dx, const float* __restrict__ mask, const float* __restrict__ dact,
+                                     const float* __restrict__ dfeat, float* __restrict__ drout, int L, int C, long long rows) {
+  const int ocols = C * 17, pc = C * 16;
+  const long long total = rows * ocols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % ocols);
+    const long long row = i / ocols;
+    const int n = (int)(row / L);
+    float v;
+    if (col < pc) {
+      v = dx ? __bfloat162float(dx[row * pc + col]) * mask[n * C + col / 16] : 0.f;
+    } else {
+      const int j = col - pc;
+      v = (dact ? dact[n * C + j] / (float)L : 0.f) + (dfeat ? dfeat[row * C + j] : 0.f);
+    }
+    drout[i] = v;
+  }
+}
+
+}  // namespace
+
+B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, int64_t b,
+                               int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(caps && W && beta_u && beta_a && out, "em_routing_fwd: null pointer");
+  B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_fwd: C=%d must be in [1,32]", C);
+  if (b <= 0) return 0;
+  const size_t smem = (size_t)(kB * 16 * 32 + 2 * kNW * 17 * 32 + 544) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd attr");
+    cfg = true;
+  }
+  long long grid = 2LL * b2c_num_sms();
+  if (grid > b) grid = b;
+  em_routing_fwd_kernel<<<(unsigned)grid, kRT, smem, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, b, C);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("em_routing_fwd");
+  return 0;
+}
+
+B2C_API int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
+                               float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(caps && W && beta_u && beta_a && dout && dcaps && dW && dbeta_u && dbeta_a, "em_routing_bwd: null pointer");
+  B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_bwd: C=%d must be in [1,32]", C);
+  if (b <= 0) return 0;
+  const size_t smem = (size_t)(2 * kB * 16 * 32 + 2 * kNW * 17 * 32 + 2 * 3 * 16 * 32 + 17 * 32 + 544 + 32 * 17) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_bwd attr");
+    cfg = true;
+  }
+  long long grid = b2c_num_sms();
+  if (grid > b) grid = b;
+  em_routing_bwd_kernel<<<(unsigned)grid, kRT, smem, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, dout, dcaps, dW, dbeta_u, dbeta_a,
+                                                                       b, C);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("em_routing_bwd");
+  return 0;
+}
+
+B2C_API int b2c_class_mean_fwd(const float* rout, float* act, int32_t N, int32_t L, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(rout && act && N > 0 && L > 0 && C > 0, "class_mean_fwd: bad args");
+  class_mean_kernel<<<N, 32, 0, (cudaStream_t)s>>>(rout, act, L, C);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("class_mean_fwd");
+  return 0;
+}
+
+B2C_API int b2c_pose_mask_fwd(const float* rout, const float* mask, void* x, int32_t N, int32_t L, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(rout && mask && x && N > 0 && C > 0, "pose_mask_fwd: bad args");
+  const long long total = (long long)N * L * (C * 16 / 8);
+  int blocks = (int)((total + 255) / 256);
+  pose_mask_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(rout, mask, (bf16*)x, L, C, total);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("pose_mask_fwd");
+  return 0;
+}
+
+B2C_API int b2c_caps_head_bwd(const void* dx, const float* mask, const float* dact, const float* dfeat, float* drout, int32_t N,
+                              int32_t L, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(drout && mask && N > 0, "caps_head_bwd: bad args");
+  const long long rows = (long long)N * L;
+  const long long total = rows * C * 17;
+  int blocks = (int)((total + 255) / 256);
+  const int cap = b2c_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  caps_head_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>((const bf16*)dx, mask, dact, dfeat, drout, L, C, rows);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("caps_head_bwd");
+  return 0;
+}
