@@ -80,7 +80,8 @@ typedef struct {
   const int32_t* taps; /* [ntaps] */
   const int32_t* wtap; /* [ntaps] element offset of the tap inside dw */
   int64_t g_row_stride, p_row_stride, s_p, s_g;
-  int32_t g_c_off, p_c_off, Cg, Cp, Cg_real;
+  int32_t g_c_off, p_c_off, Cg, Cp, Cg_real; /* channels >= Cg_real are zero padding */
+  int32_t Cp_real;                           /* p channels >= Cp_real are padding (0 = Cp) */
   int32_t N, Tg, Hg, Wg, Tp, Hp, Wp;
   int32_t Qt, Qh, Qw;
   int32_t sg_t, sg_h, sg_w, sp_t, sp_h, sp_w, pp_t, pp_h, pp_w;
@@ -92,9 +93,12 @@ typedef struct {
 
 int b2c_conv_wgrad(const b2c_wgrad_desc* desc_host, b2c_stream_t stream);
 
-/* packed[r][t*C + c] = (c < C_real) ? bf16(w[r*s_r + c*s_c + wtap[t]]) : 0     r<R, t<ntaps, c<C */
+/* packed[r*row_pitch + t*tap_pitch + col_off + c] = (c < C_real) ? bf16(w[r*s_r + c*s_c + wtap[t]]) : 0
+ * r<R, t<ntaps, c<C.  (row_pitch = ntaps*C, tap_pitch = C, col_off = 0 for a stand-alone layer; other
+ * values place sibling layers side by side in one fused GEMM operand.) */
 int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, int32_t R, int32_t ntaps, int32_t C,
-                     int32_t C_real, int64_t s_r, int64_t s_c, b2c_stream_t stream);
+                     int32_t C_real, int64_t s_r, int64_t s_c, int64_t row_pitch, int64_t tap_pitch, int64_t col_off,
+                     b2c_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Bandwidth kernels (channels-last bf16 views: ptr, rows, C, row_stride, c_off)
@@ -107,11 +111,14 @@ int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_t in_c_o
 
 /* BatchNorm3d training statistics (pytorch_i3d.py:80,117).  groups: rows are split evenly into
  * `groups` contiguous segments with independent statistics (two forward passes batched).
- * ws: fp32 [groups][2][C] zeroed by the caller.  stats out: mean[g][C], rstd[g][C].
- * running_mean/var updated with momentum (unbiased var) when non-NULL (groups applied in order). */
-int b2c_bn_stats(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
-                 float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
-                 b2c_stream_t s);
+ * _sums: ws fp32 [groups][2][C] (zeroed by the caller) += per-channel sum / sum of squares.
+ * _finalize: for channels [c_off, c_off+C) of a ws with ws_C channels: mean[g][C], rstd[g][C]; running
+ * stats updated with momentum (unbiased variance; groups applied in order) when non-NULL. */
+int b2c_bn_sums(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
+                b2c_stream_t s);
+int b2c_bn_finalize(const float* ws, int32_t ws_C, int32_t c_off, int32_t C, int32_t groups, int64_t rows_per_group,
+                    float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
+                    b2c_stream_t s);
 /* y = relu((x-mean)*rstd*gamma+beta) written into a concat slot */
 int b2c_bn_relu_apply(const void* x, int64_t rows, int32_t C, int64_t x_row_stride, int32_t x_c_off, int32_t groups,
                       const float* mean, const float* rstd, const float* gamma, const float* beta, void* y,
@@ -151,9 +158,12 @@ int b2c_add(const void* a, int64_t a_row_stride, int32_t a_c_off, const void* b,
             void* out, int64_t o_row_stride, int32_t o_c_off, int64_t rows, int32_t C, b2c_stream_t s);
 
 /* 'smooth' ConvTranspose3d(128->1,k3,p1) (capsules_ucf101.py:509) second half: 27-tap stencil over the
- * per-tap projections P (rows,32) fp32 -> logits fp32 (N,T,H,W); and its adjoint dP (bf16). */
-int b2c_stencil27_fwd(const float* P, float* out, float bias, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s);
-int b2c_stencil27_bwd(const float* dout, void* dP, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s);
+ * per-tap projections P, PLANAR fp32 [32][rows] -> logits fp32 (N,T,H,W); and its adjoint dP (bf16 rows). */
+int b2c_stencil27_fwd(const float* P, float* out, const float* bias, int32_t N, int32_t T, int32_t H, int32_t W,
+                      b2c_stream_t s);
+/* dP bf16 (rows,32); dbias[0] += sum(dout) when non-NULL */
+int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t N, int32_t T, int32_t H, int32_t W,
+                      b2c_stream_t s);
 
 /* ------------------------------------------------------------------------------------
  * Capsule head
@@ -190,29 +200,31 @@ int b2c_seg_loss_bwd(const float* logits, const float* targets, const int32_t* l
  * dact rows (+)= w * dloss */
 int b2c_spread_loss(const float* act, const float* target, const int32_t* lab_idx, int32_t n_lab, int32_t C, float m_min,
                     float* loss, float w, float* dact, b2c_stream_t s);
-/* Temporal-variance attentive mask (helpers.py:8-67), both directions fused:
- *   out, flp: logits of the clip and of the flipped clip ALREADY flipped back in W is NOT required --
- *   `flp` is the raw second-pass output; the kernel mirrors W itself (main_ucf101.py:100).
- * raw masks (unnormalised, shifted by nothing) are written to m_clk, m_anti (fp32 (P,8,H,W)) and
- * per-clip min/max to mm fp32 (P,4) = (min_clk, max_clk, min_anti, max_anti). */
-int b2c_bv_masks(const float* out, const float* flp, float* m_clk, float* m_anti, float* mm, int32_t P, int32_t H,
-                 int32_t W, int32_t frames_cnt, int32_t use_sigmoid, b2c_stream_t s);
-/* gradient-smoothness mask (helpers.py:70-95): raw second temporal derivative of sigmoid + per-clip min/max */
+/* Temporal-variance attentive mask, measure_pixelwise_var_v2 (helpers.py:8-67): 14-frame cycle
+ * pred[0..7] ++ flip_pred[1..6], cyclic windowed population variance (frames_cnt 3|5), fold to 8 frames,
+ * per-clip min-max normalisation.  pred/flip_pred/m: fp32 (P,8,H,W); mm: fp32 (P,2) scratch.
+ * pred_tflip / fp_tflip / fp_wmirror apply the caller's torch.flip's (main_ucf101.py:100,114-115) on the
+ * fly so the fused step can pass the raw outputs of both forward passes. */
+int b2c_bv_mask(const float* pred, const float* flip_pred, float* m, float* mm, int32_t P, int32_t H, int32_t W,
+                int32_t frames_cnt, int32_t use_sigmoid, int32_t pred_tflip, int32_t fp_tflip, int32_t fp_wmirror,
+                b2c_stream_t s);
+/* gradient-smoothness mask, measure_pixelwise_gradient (helpers.py:70-95): sigmoid, optional clamps,
+ * np.gradient twice along time, per-clip min-max normalisation.  m: fp32 (P,8,H,W) (no channel dim). */
 int b2c_gv_mask(const float* out, float* m, float* mm, int32_t P, int32_t H, int32_t W, float lower, float upper,
                 int32_t use_lower, int32_t use_upper, b2c_stream_t s);
-/* consistency loss + gradients.  mode bit0: bv, bit1: gv.
- *   d = flipW(flp) - out ; l2 = mean(d^2) ; lv = mean(w_clk*d^2) + mean(flipT(w_anti)*d^2) ;
- *   lg = mean_thw( mean_j w_j * mean_i d_i^2 )   (the (B,B,...) broadcast of main_ucf101.py:130-132)
- * acc: fp64[4] scratch (zeroed by _reduce); loss out fp32[4] = (cons, l2, lv, lg).
- * _reduce + _finish give the loss; _grad adds wt * dcons/d{out,flp} into dout / dflp. */
-int b2c_cons_reduce(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
-                    const float* mm_bv, const float* mm_gv, double* acc, int32_t P, int32_t H, int32_t W, int32_t mode,
-                    b2c_stream_t s);
+/* consistency loss, weighted_mse_loss (losses.py:74-76) as composed in main_ucf101.py:100-148.
+ *   d = (mirror ? flipW(flp) : flp) - out ; l2 = mean(d^2) ; lv = mean(w1 d^2) + mean(w2' d^2)
+ *   (w2' = time-flipped w2 when w2_tflip) ; lg = mean_thw( mean_j wg_j * mean_i d_i^2 ) -- the
+ *   (B,B,8,H,W) broadcast of a (B,8,H,W) weight against (B,1,8,H,W) (main_ucf101.py:130-132).
+ * w1/w2/wg may be NULL.  acc: fp64[4] scratch; loss fp32[4] = (cons, l2, lv, lg); mode bit0 bv, bit1 gv.
+ * _grad: dout -= g, dflp(+mirror) += g with g = (a_l2 + a_lv (w1+w2')) 2d/(P THW) + a_lg 2 B d/(THW P^2). */
+int b2c_cons_reduce(const float* out, const float* flp, const float* w1, const float* w2, const float* wg, double* acc,
+                    int32_t P, int32_t H, int32_t W, int32_t mirror, int32_t w2_tflip, b2c_stream_t s);
 int b2c_cons_finish(const double* acc, float* loss, int32_t P, int32_t H, int32_t W, int32_t mode, float wt_ramp,
                     float bv_wt, float gv_wt, b2c_stream_t s);
-int b2c_cons_grad(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
-                  const float* mm_bv, const float* mm_gv, float* dout, float* dflp, int32_t P,
-                  int32_t H, int32_t W, int32_t mode, float wt_ramp, float bv_wt, float gv_wt, float wt, b2c_stream_t s);
+int b2c_cons_grad(const float* out, const float* flp, const float* w1, const float* w2, const float* wg, float* dout,
+                  float* dflp, int32_t P, int32_t H, int32_t W, int32_t mirror, int32_t w2_tflip, float a_l2, float a_lv,
+                  float a_lg, b2c_stream_t s);
 
 /* ------------------------------------------------------------------------------------
  * Optimiser: Adam(lr, betas, eps=1e-6, wd=0) over one flat fp32 buffer (main_ucf101.py:416,184)

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
 class WgradDesc(C.Structure):
     _fields_ = [("g", vp), ("p", vp), ("dw", vp), ("taps", vp), ("wtap", vp),
                 ("g_row_stride", i64), ("p_row_stride", i64), ("s_p", i64), ("s_g", i64),
-                ("g_c_off", i32), ("p_c_off", i32), ("Cg", i32), ("Cp", i32), ("Cg_real", i32),
+                ("g_c_off", i32), ("p_c_off", i32), ("Cg", i32), ("Cp", i32), ("Cg_real", i32), ("Cp_real", i32),
                 ("N", i32), ("Tg", i32), ("Hg", i32), ("Wg", i32), ("Tp", i32), ("Hp", i32), ("Wp", i32),
                 ("Qt", i32), ("Qh", i32), ("Qw", i32),
                 ("sg_t", i32), ("sg_h", i32), ("sg_w", i32), ("sp_t", i32), ("sp_h", i32), ("sp_w", i32),
@@ -44,10 +44,11 @@ class WgradDesc(C.Structure):
 _SIGS = {
     "b2c_conv_fprop": [C.POINTER(ConvDesc), vp],
     "b2c_conv_wgrad": [C.POINTER(WgradDesc), vp],
-    "b2c_pack_weights": [vp, vp, vp, i32, i32, i32, i32, i64, i64, vp],
+    "b2c_pack_weights": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, vp],
     "b2c_ncdhw_to_ndhwc": [vp, vp, i32, i32, i64, i32, vp],
     "b2c_ndhwc_to_ncdhw_f32": [vp, i64, i32, vp, i32, i32, i64, vp],
-    "b2c_bn_stats": [vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp],
+    "b2c_bn_sums": [vp, i64, i32, i64, i32, i32, vp, vp],
+    "b2c_bn_finalize": [vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, f32, f32, vp],
     "b2c_bn_relu_apply": [vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, i64, i32, i32, vp],
     "b2c_bn_relu_bwd_reduce": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, i32, vp, vp, vp, i32, vp],
     "b2c_bn_relu_bwd_apply": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, i64, i32,
@@ -57,8 +58,8 @@ _SIGS = {
     "b2c_channel_scale": [vp, i64, i32, vp, vp, i64, i32, i32, i64, i32, vp],
     "b2c_act_bwd": [vp, i64, i32, vp, i64, i32, vp, vp, i64, i32, vp, i32, i64, i32, i32, vp],
     "b2c_add": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, vp],
-    "b2c_stencil27_fwd": [vp, vp, f32, i32, i32, i32, i32, vp],
-    "b2c_stencil27_bwd": [vp, vp, i32, i32, i32, i32, vp],
+    "b2c_stencil27_fwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2c_stencil27_bwd": [vp, vp, vp, i32, i32, i32, i32, vp],
     "b2c_em_routing_fwd": [vp, vp, vp, vp, vp, i64, i32, vp],
     "b2c_em_routing_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "b2c_class_mean_fwd": [vp, vp, i32, i32, i32, vp],
@@ -67,11 +68,11 @@ _SIGS = {
     "b2c_seg_loss_fwd": [vp, vp, vp, i32, i64, vp, vp, vp],
     "b2c_seg_loss_bwd": [vp, vp, vp, i32, i64, vp, f32, f32, vp, vp],
     "b2c_spread_loss": [vp, vp, vp, i32, i32, f32, vp, f32, vp, vp],
-    "b2c_bv_masks": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "b2c_bv_mask": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_gv_mask": [vp, vp, vp, i32, i32, i32, f32, f32, i32, i32, vp],
-    "b2c_cons_reduce": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2c_cons_reduce": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "b2c_cons_finish": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp],
-    "b2c_cons_grad": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, vp],
+    "b2c_cons_grad": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, vp],
     "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
     "b2c_fill_f32": [vp, i64, f32, vp],
 }

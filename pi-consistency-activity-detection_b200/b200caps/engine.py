@@ -1,0 +1,632 @@
+"""Layer-level composition of the C-ABI kernels and the torch.autograd.Function wrappers the
+drop-in nn.Modules call.  Host logic only: shapes, buffers (torch = allocator), launch order.
+All arithmetic happens inside libb200caps.so.
+
+Internal activation format: contiguous (N,T,H,W,C) bf16 tensors ("CL").  Module boundaries expose
+them as logical (N,C,T,H,W) views (``from_cl``) so reference code such as ``x.view(-1,832,28,28)``
+keeps working without copies.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .plans import ConvPlan, ConvSpec, View, same_pad
+
+BN_EPS = 1e-3       # pytorch_i3d.py:80
+BN_MOMENTUM = 0.01  # pytorch_i3d.py:80
+
+
+class _State:
+    weights_epoch = 0          # bumped by the fused optimiser (raw-pointer updates bypass tensor._version)
+    dropout_source: Optional[Callable] = None   # tests inject Dropout3d masks: f(n, c, device) -> (n,c) fp32 keep*2
+    bn_groups = 1              # >1: the batch holds several independent forward passes (own BN statistics each)
+
+
+STATE = _State()
+
+
+def bump_weights_epoch():
+    STATE.weights_epoch += 1
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"b200caps: {what} must be a CUDA tensor -- the hot path has no CPU fallback")
+
+
+# ---- layout helpers -------------------------------------------------------------------------------
+class _ToCL(torch.autograd.Function):
+    """(N,C,T,H,W) fp32 -> CL bf16 (channels zero-padded to a multiple of 8)."""
+
+    @staticmethod
+    def forward(ctx, x, cpad):
+        ctx.C = x.shape[1]
+        return ops.ncdhw_to_cl(x.contiguous(), cpad)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        return ops.cl_to_ncdhw_f32(View(g, 0, ctx.C)), None
+
+
+class _FromCLf32(torch.autograd.Function):
+    """CL bf16 -> (N,C,T,H,W) fp32 contiguous (user-facing boundary of a stand-alone module)."""
+
+    @staticmethod
+    def forward(ctx, x_cl):
+        ctx.cpad = x_cl.shape[-1]
+        return ops.cl_to_ncdhw_f32(View(x_cl))
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.ncdhw_to_cl(g.float().contiguous(), ctx.cpad)
+
+
+def to_cl(x: torch.Tensor, cpad: Optional[int] = None) -> torch.Tensor:
+    """Accepts logical (N,C,T,H,W) / (N,C,H,W) tensors: bf16 channels-last views pass through without a copy,
+    fp32 tensors are converted by the layout kernel."""
+    require_cuda(x, "activation")
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    assert x.dim() == 5, x.shape
+    C = x.shape[1]
+    cpad = cpad or (C + 7) // 8 * 8
+    if x.dtype == torch.bfloat16 and cpad == C:
+        v = x.permute(0, 2, 3, 4, 1)
+        return v if v.is_contiguous() else v.contiguous()
+    return _ToCL.apply(x.float(), cpad)
+
+
+def from_cl(x_cl: torch.Tensor) -> torch.Tensor:
+    return x_cl.permute(0, 4, 1, 2, 3)
+
+
+def grad_cl(g: torch.Tensor) -> torch.Tensor:
+    """Incoming gradient for a CL-shaped output -> contiguous bf16."""
+    if g.dtype != torch.bfloat16:
+        g = g.to(torch.bfloat16)
+    return g if g.is_contiguous() else g.contiguous()
+
+
+# ---- conv layer state --------------------------------------------------------------------------------
+class ConvLayer:
+    """Plans + packed bf16 weights of one convolution parameter.  The fp32 nn.Parameter in the reference
+    layout stays the parameter of record; packed tiles are derived caches, rebuilt when it changes."""
+
+    def __init__(self, weight: torch.nn.Parameter, spec_fn: Callable[[Tuple[int, int, int]], ConvSpec]):
+        self.weight = weight
+        self.spec_fn = spec_fn
+        self.plans: Dict[Tuple[int, int, int], ConvPlan] = {}
+        self.keys: Dict[Tuple, Tuple] = {}
+
+    def plan(self, in_dims) -> ConvPlan:
+        in_dims = tuple(int(v) for v in in_dims)
+        pl = self.plans.get(in_dims)
+        if pl is None:
+            pl = ConvPlan(self.spec_fn(in_dims), in_dims)
+            self.plans[in_dims] = pl
+        return pl.to(self.weight.device)
+
+    def packed(self, in_dims, which: str) -> ConvPlan:
+        in_dims = tuple(int(v) for v in in_dims)
+        pl = self.plan(in_dims)
+        w = self.weight
+        key = (w.data_ptr(), w._version, STATE.weights_epoch)
+        if self.keys.get((in_dims, which)) != key:
+            pl.pack(w.detach(), which, ops.stream())
+            self.keys[(in_dims, which)] = key
+        return pl
+
+
+# ---- primitives (no autograd) -----------------------------------------------------------------------
+class UnitSaved:
+    __slots__ = ("raw", "mean", "rstd", "groups", "dims")
+
+
+def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: bool, groups: int) -> UnitSaved:
+    """Unit3D (pytorch_i3d.py:89-120): same-pad conv (tcgen05) -> BatchNorm3d -> ReLU, written into `y`."""
+    pl = layer.packed(x.dims, "fprop")
+    N = x.N
+    Cout = pl.spec.Cout_pad
+    raw = torch.empty((N,) + tuple(pl.out_dims) + (Cout,), dtype=torch.bfloat16, device=x.t.device)
+    ops.conv_fprop(pl, "fprop", x, View(raw))
+    sv = UnitSaved()
+    sv.raw, sv.dims = raw, x.dims
+    rv_ = View(raw)
+    if training:
+        g = groups
+        assert N % g == 0
+        ws = torch.zeros((g, 2, Cout), dtype=torch.float32, device=raw.device)
+        sv.mean = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
+        sv.rstd = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
+        ops.bn_sums(rv_, g, ws)
+        ops.bn_finalize(ws, Cout, 0, Cout, g, rv_.rows // g, sv.mean, sv.rstd, rm, rv, BN_MOMENTUM, BN_EPS)
+        sv.groups = g
+    else:
+        sv.mean = rm.detach().float().view(1, -1).contiguous()
+        sv.rstd = torch.rsqrt(rv.detach().float() + BN_EPS).view(1, -1).contiguous()
+        sv.groups = 1
+    ops.bn_relu_apply(rv_, sv.groups, sv.mean, sv.rstd, gamma.detach(), beta.detach(), y, relu=True)
+    return sv
+
+
+def unit_bwd(layer: ConvLayer, gamma, sv: UnitSaved, x: View, y: View, gy: View, dx: Optional[View], accumulate: bool):
+    """Returns (dweight, dgamma, dbeta); writes dx (+= when accumulate)."""
+    dev = x.t.device
+    Cout = sv.raw.shape[-1]
+    raw = View(sv.raw)
+    ws = torch.zeros((sv.groups, 2, Cout), dtype=torch.float32, device=dev)
+    ops.bn_relu_bwd_reduce(gy, y, raw, sv.groups, sv.mean, sv.rstd, ws, relu=True)
+    draw = torch.empty_like(sv.raw)
+    dgamma = torch.zeros(Cout, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(Cout, dtype=torch.float32, device=dev)
+    ops.bn_relu_bwd_apply(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
+    if dx is not None:
+        pl = layer.packed(sv.dims, "dgrad")
+        ops.conv_fprop(pl, "dgrad", View(draw), dx, accumulate=accumulate)
+    pl = layer.plan(sv.dims)
+    dw = torch.zeros_like(layer.weight)
+    ops.conv_wgrad(pl, x, View(draw), dw, atomic=True)
+    return dw, dgamma, dbeta
+
+
+def cba_fwd(layer: ConvLayer, bias, x: View, y: View, relu: bool, scale_nc=None, sigmoid_from=-1):
+    """conv / transposed conv + bias (+ per-sample channel scale) (+ ReLU) fused in the GEMM epilogue."""
+    pl = layer.packed(x.dims, "fprop")
+    ops.conv_fprop(pl, "fprop", x, y, bias=bias.detach() if bias is not None else None, scale_nc=scale_nc, relu=relu,
+                   sigmoid_from=sigmoid_from)
+
+
+def cba_bwd(layer: ConvLayer, x: View, y: Optional[View], gy: View, relu: bool, scale_nc, dx: Optional[View],
+            accumulate: bool = False, want_bias: bool = True):
+    """Returns (dweight, dbias)."""
+    dev = x.t.device
+    C = gy.C
+    dbias = torch.zeros(C, dtype=torch.float32, device=dev) if want_bias else None
+    if relu or scale_nc is not None:
+        dz_t = torch.empty((gy.N,) + tuple(gy.dims) + (C,), dtype=torch.bfloat16, device=dev)
+        dz = View(dz_t)
+        ops.act_bwd(gy, y if relu else None, scale_nc, dz, dbias, relu)
+    else:
+        dz = gy
+        if want_bias:
+            ops.act_bwd(gy, None, None, None, dbias, False)
+    if dx is not None:
+        pl = layer.packed(x.dims, "dgrad")
+        ops.conv_fprop(pl, "dgrad", dz, dx, accumulate=accumulate)
+    pl = layer.plan(x.dims)
+    dw = torch.zeros_like(layer.weight)
+    ops.conv_wgrad(pl, x, dz, dw, atomic=True)
+    return dw, dbias
+
+
+def dropout_scale(n: int, c: int, device, p: float = 0.5) -> torch.Tensor:
+    """Dropout3d keep mask scaled by 1/(1-p), one value per (sample, channel) (capsules_ucf101.py:371).
+    RNG draw = torch's bernoulli on the device (plumbing); tests inject masks through STATE.dropout_source."""
+    if STATE.dropout_source is not None:
+        m = STATE.dropout_source(n, c, device)
+        return m.to(device=device, dtype=torch.float32).reshape(n, c).contiguous()
+    return torch.empty((n, c), dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
+
+
+# ---- autograd functions -------------------------------------------------------------------------------
+class Unit3DFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, weight, gamma, beta, mod):
+        layer = mod._layer
+        pl = layer.plan(x_cl.shape[1:4])
+        y = torch.empty((x_cl.shape[0],) + tuple(pl.out_dims) + (pl.spec.Cout_pad,), dtype=torch.bfloat16,
+                        device=x_cl.device)
+        training = mod.training
+        sv = unit_fwd(layer, gamma, beta, mod.bn.running_mean, mod.bn.running_var, View(x_cl), View(y), training,
+                      STATE.bn_groups if training else 1)
+        if training:
+            mod.bn.num_batches_tracked += 1
+        ctx.mod, ctx.sv, ctx.x, ctx.y, ctx.gamma = mod, sv, x_cl, y, gamma
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.training:
+            raise RuntimeError("b200caps: backward through eval-mode BatchNorm is not supported")
+        gy = grad_cl(gy)
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_like(ctx.x) if need_dx else None
+        dw, dg, db = unit_bwd(ctx.mod._layer, ctx.gamma, ctx.sv, View(ctx.x), View(ctx.y), View(gy),
+                              View(dx) if need_dx else None, False)
+        return dx, dw, dg, db, None
+
+
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, k, s):
+        N, T, H, W, C = x_cl.shape
+        pads = [same_pad(d, kk, ss) for d, kk, ss in zip((T, H, W), k, s)]
+        od = tuple((d + p[0] + p[1] - kk) // ss + 1 for d, p, kk, ss in zip((T, H, W), pads, k, s))
+        y = torch.empty((N,) + od + (C,), dtype=torch.bfloat16, device=x_cl.device)
+        idx = torch.empty((N,) + od + (C,), dtype=torch.uint8, device=x_cl.device)
+        pf = tuple(p[0] for p in pads)
+        ops.maxpool_fwd(View(x_cl), View(y), idx, k, s, pf)
+        ctx.geo = (tuple(k), tuple(s), pf, tuple(x_cl.shape))
+        ctx.idx = idx
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        k, s, pf, xshape = ctx.geo
+        gy = grad_cl(gy)
+        dx = torch.empty(xshape, dtype=torch.bfloat16, device=gy.device)
+        ops.maxpool_bwd(View(gy), ctx.idx, View(dx), k, s, pf, accumulate=False)
+        return dx, None, None
+
+
+class InceptionFn(torch.autograd.Function):
+    """InceptionModule (pytorch_i3d.py:124-149) hand-scheduled: six Unit3D + same-pad max-pool, every branch
+    writes straight into its channel slot of the concatenated output (no torch.cat), gradients of the four
+    consumers of x are accumulated in the dgrad epilogues."""
+    UNITS = ("b0", "b1a", "b1b", "b2a", "b2b", "b3b")
+
+    @staticmethod
+    def forward(ctx, x_cl, mod, *params):
+        N, T, H, W, Cin = x_cl.shape
+        dev = x_cl.device
+        u = {n: getattr(mod, n) for n in InceptionFn.UNITS}
+        oc = [m.bn.weight.numel() for m in (u["b0"], u["b1a"], u["b1b"], u["b2a"], u["b2b"], u["b3b"])]
+        c0, c1, c2, c3, c4, c5 = oc
+        training = mod.training
+        g = STATE.bn_groups if training else 1
+        out = torch.empty((N, T, H, W, c0 + c2 + c4 + c5), dtype=torch.bfloat16, device=dev)
+        mid1 = torch.empty((N, T, H, W, c1), dtype=torch.bfloat16, device=dev)
+        mid2 = torch.empty((N, T, H, W, c3), dtype=torch.bfloat16, device=dev)
+        pooled = torch.empty_like(x_cl)
+        idx = torch.empty(x_cl.shape, dtype=torch.uint8, device=dev)
+        xv = View(x_cl)
+
+        def run(name, xin, yout):
+            m = u[name]
+            return unit_fwd(m._layer, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var, xin, yout, training, g)
+
+        sv = {}
+        sv["b0"] = run("b0", xv, View(out, 0, c0))
+        sv["b1a"] = run("b1a", xv, View(mid1))
+        sv["b1b"] = run("b1b", View(mid1), View(out, c0, c2))
+        sv["b2a"] = run("b2a", xv, View(mid2))
+        sv["b2b"] = run("b2b", View(mid2), View(out, c0 + c2, c4))
+        ops.maxpool_fwd(xv, View(pooled), idx, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        sv["b3b"] = run("b3b", View(pooled), View(out, c0 + c2 + c4, c5))
+        if training:
+            for m in u.values():
+                m.bn.num_batches_tracked += 1
+        ctx.mod, ctx.sv, ctx.oc = mod, sv, oc
+        ctx.x, ctx.out, ctx.mid1, ctx.mid2, ctx.pooled, ctx.idx = x_cl, out, mid1, mid2, pooled, idx
+        ctx.training = training
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        if not ctx.training:
+            raise RuntimeError("b200caps: backward through eval-mode BatchNorm is not supported")
+        gout = grad_cl(gout)
+        mod, sv = ctx.mod, ctx.sv
+        c0, c1, c2, c3, c4, c5 = ctx.oc
+        u = {n: getattr(mod, n) for n in InceptionFn.UNITS}
+        x, out = ctx.x, ctx.out
+        xv = View(x)
+        dx = torch.empty_like(x)
+        dmid1 = torch.empty_like(ctx.mid1)
+        dmid2 = torch.empty_like(ctx.mid2)
+        dpool = torch.empty_like(x)
+        grads = {}
+
+        def run(name, xin, yv, gyv, dxv, acc):
+            m = u[name]
+            grads[name] = unit_bwd(m._layer, m.bn.weight, sv[name], xin, yv, gyv, dxv, acc)
+
+        run("b0", xv, View(out, 0, c0), View(gout, 0, c0), View(dx), False)
+        run("b1b", View(ctx.mid1), View(out, c0, c2), View(gout, c0, c2), View(dmid1), False)
+        run("b1a", xv, View(ctx.mid1), View(dmid1), View(dx), True)
+        run("b2b", View(ctx.mid2), View(out, c0 + c2, c4), View(gout, c0 + c2, c4), View(dmid2), False)
+        run("b2a", xv, View(ctx.mid2), View(dmid2), View(dx), True)
+        run("b3b", View(ctx.pooled), View(out, c0 + c2 + c4, c5), View(gout, c0 + c2 + c4, c5), View(dpool), False)
+        ops.maxpool_bwd(View(dpool), ctx.idx, View(dx), (3, 3, 3), (1, 1, 1), (1, 1, 1), accumulate=True)
+        flat = []
+        for n in InceptionFn.UNITS:
+            flat += list(grads[n])
+        return (dx, None) + tuple(flat)
+
+
+class ChannelScaleFn(torch.autograd.Function):
+    """Dropout3d as a per-(sample, channel) scale (capsules_ucf101.py:428)."""
+
+    @staticmethod
+    def forward(ctx, x_cl, scale_nc):
+        y = torch.empty_like(x_cl)
+        ops.channel_scale(View(x_cl), scale_nc, View(y))
+        ctx.scale = scale_nc
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = grad_cl(gy)
+        dx = torch.empty_like(gy)
+        ops.channel_scale(View(gy), ctx.scale, View(dx))
+        return dx, None
+
+
+class FusedConvLayer:
+    """Several convolutions that read the same input (same kernel / stride / padding) executed as ONE implicit
+    GEMM with N = sum(Cout_i): the packed fprop operand stacks the members' rows, the dgrad operand places them
+    side by side along K.  Used for PrimaryCaps (pose | a, N = 544)."""
+
+    def __init__(self, weights: Sequence[torch.nn.Parameter], spec_fn):
+        self.weights = list(weights)
+        self.couts = [int(w.shape[0]) for w in self.weights]
+        self.offs = [sum(self.couts[:i]) for i in range(len(self.couts))]
+        self.spec_fn = spec_fn
+        self.plans: Dict[Tuple[int, int, int], ConvPlan] = {}
+        self.keys: Dict[Tuple, Tuple] = {}
+
+    def plan(self, in_dims) -> ConvPlan:
+        in_dims = tuple(int(v) for v in in_dims)
+        pl = self.plans.get(in_dims)
+        if pl is None:
+            pl = ConvPlan(self.spec_fn(in_dims), in_dims)
+            assert not pl.spec.transposed and pl.spec.Cout == sum(self.couts)
+            self.plans[in_dims] = pl
+        return pl.to(self.weights[0].device)
+
+    def packed(self, in_dims, which: str) -> ConvPlan:
+        pl = self.plan(in_dims)
+        key = tuple((w.data_ptr(), w._version) for w in self.weights) + (STATE.weights_epoch,)
+        if self.keys.get((tuple(in_dims), which)) == key:
+            return pl
+        spec = pl.spec
+        T = spec.k[0] * spec.k[1] * spec.k[2]
+        dev = self.weights[0].device
+        if which == "fprop":
+            cl = pl.fprop[0]
+            K = len(cl.taps) * spec.Cin_pad
+            if cl.packed is None:
+                cl.packed = torch.zeros((spec.Cout_pad, K), dtype=torch.bfloat16, device=dev)
+            for w, co, off in zip(self.weights, self.couts, self.offs):
+                ops.pack_part(w.detach(), cl.packed[off:], cl.wtap_dev, co, len(cl.taps), spec.Cin_pad, spec.Cin,
+                              spec.Cin * T, T)
+        else:
+            for cl in pl.dgrad:
+                nt = len(cl.taps)
+                if cl.packed is None:
+                    cl.packed = torch.zeros((spec.Cin_pad, nt * spec.Cout_pad), dtype=torch.bfloat16, device=dev)
+                for w, co, off in zip(self.weights, self.couts, self.offs):
+                    ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, spec.Cin, nt, co, co, T, spec.Cin * T,
+                                  nt * spec.Cout_pad, spec.Cout_pad, off)
+        self.keys[(tuple(in_dims), which)] = key
+        return pl
+
+    def wgrad(self, in_dims, x: View, dy: View) -> List[torch.Tensor]:
+        pl = self.plan(in_dims)
+        outs = []
+        for w, co, off in zip(self.weights, self.couts, self.offs):
+            dw = torch.zeros_like(w)
+            ops.conv_wgrad(pl, x, dy, dw, atomic=True, part=(off, co))
+            outs.append(dw)
+        return outs
+
+
+class PrimaryCapsFn(torch.autograd.Function):
+    """PrimaryCaps (capsules_ucf101.py:43-49): the pose (512) and activation (32) 9x9 convolutions run as ONE
+    implicit GEMM with N = 544 whose epilogue adds the biases, applies the sigmoid to the last 32 columns and
+    writes fp32 rows -- exactly the (B,20,20,544) permuted / concatenated layout the routing consumes."""
+
+    @staticmethod
+    def forward(ctx, x_cl, wp, bp, wa, ba, mod):
+        layer: FusedConvLayer = mod._layer
+        pl = layer.packed(x_cl.shape[1:4], "fprop")
+        N = x_cl.shape[0]
+        bias = torch.cat([bp.detach(), ba.detach()])      # 544 floats (plumbing)
+        out = torch.empty((N,) + tuple(pl.out_dims) + (544,), dtype=torch.float32, device=x_cl.device)
+        ops.conv_fprop(pl, "fprop", View(x_cl), View(out), bias=bias, sigmoid_from=512)
+        ctx.mod, ctx.x, ctx.out = mod, x_cl, out
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        mod, x, out = ctx.mod, ctx.x, ctx.out
+        layer: FusedConvLayer = mod._layer
+        N, _, h, w, _ = out.shape
+        # pre-activation gradient in bf16 rows + bias gradient: act_bwd on an fp32->bf16 staged copy.
+        # sigmoid'(z) = a (1 - a) for the 32 activation columns, identity for the poses.
+        g = g.contiguous().float()
+        dz = g.clone()
+        a = out[..., 512:]
+        dz[..., 512:] = g[..., 512:] * a * (1.0 - a)
+        dbias = dz.sum(dim=(0, 1, 2, 3))
+        dzb = dz.to(torch.bfloat16)
+        dims = x.shape[1:4]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.conv_fprop(layer.packed(dims, "dgrad"), "dgrad", View(dzb), View(dx))
+        dwp, dwa = layer.wgrad(dims, View(x), View(dzb))
+        return dx, dwp, dbias[:512].contiguous(), dwa, dbias[512:].contiguous(), None
+
+
+class EMRoutingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, caps, W, beta_u, beta_a):
+        """caps (N,h,w,544) fp32 -> (N,h,w,C*17) fp32 [mu | a]."""
+        C = beta_a.numel()
+        N, h, w, _ = caps.shape
+        caps = caps.contiguous()
+        out = torch.empty((N, h, w, C * 17), dtype=torch.float32, device=caps.device)
+        Wc = W.detach().reshape(32, C, 4, 4).contiguous()
+        ops.em_routing_fwd(caps, Wc, beta_u.detach().contiguous(), beta_a.detach().contiguous(), out, N * h * w, C)
+        ctx.save_for_backward(caps, W, beta_u, beta_a)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        caps, W, beta_u, beta_a = ctx.saved_tensors
+        C = beta_a.numel()
+        N, h, w, _ = caps.shape
+        g = g.contiguous().float()
+        dcaps = torch.empty_like(caps)
+        dW = torch.zeros_like(W)
+        dbu = torch.zeros_like(beta_u)
+        dba = torch.zeros_like(beta_a)
+        ops.em_routing_bwd(caps, W.detach().reshape(32, C, 4, 4).contiguous(), beta_u.detach().contiguous(),
+                           beta_a.detach().contiguous(), g, dcaps, dW, dbu, dba, N * h * w, C)
+        return dcaps, dW, dbu, dba
+
+
+class CapsHeadFn(torch.autograd.Function):
+    """Class activation = spatial mean of a_out, feat = a_out, masked poses -> decoder input
+    (capsules_ucf101.py:440-483).  mask (N,C) fp32 is a constant."""
+
+    @staticmethod
+    def forward(ctx, rout, mask):
+        N, h, w, oc = rout.shape
+        C = oc // 17
+        L = h * w
+        x0 = torch.empty((N, 1, h, w, C * 16), dtype=torch.bfloat16, device=rout.device)
+        ops.pose_mask_fwd(rout, mask, x0, N, L, C)
+        ctx.mask, ctx.shape = mask, (N, h, w, C)
+        return x0
+
+    @staticmethod
+    def backward(ctx, gx):
+        N, h, w, C = ctx.shape
+        gx = grad_cl(gx)
+        drout = torch.empty((N, h, w, C * 17), dtype=torch.float32, device=gx.device)
+        ops.caps_head_bwd(gx, ctx.mask, None, None, drout, N, h * w, C)
+        return drout, None
+
+
+class ClassActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rout):
+        N, h, w, oc = rout.shape
+        C = oc // 17
+        act = torch.empty((N, C), dtype=torch.float32, device=rout.device)
+        ops.class_mean_fwd(rout, act, N, h * w, C)
+        ctx.shape = (N, h, w, C)
+        return act
+
+    @staticmethod
+    def backward(ctx, gact):
+        N, h, w, C = ctx.shape
+        drout = torch.empty((N, h, w, C * 17), dtype=torch.float32, device=gact.device)
+        ops.caps_head_bwd(None, gact, gact.contiguous().float(), None, drout, N, h * w, C)
+        return drout
+
+
+class DecoderFn(torch.autograd.Function):
+    """Localisation decoder (capsules_ucf101.py:486-510) hand-scheduled: transposed convs by output-parity
+    class, skip convs, concatenations written in place, Dropout3d folded into the upsample4 epilogue,
+    `smooth` = tensor-core projection onto its 27 taps + a 27-point stencil.  Output: fp32 logits."""
+    ORDER = ("upsample1", "conv28", "upsample2", "conv56", "upsample3", "conv112", "upsample4", "smooth")
+
+    @staticmethod
+    def forward(ctx, x0, c28, c56, c112, drop_scale, mod, *params):
+        dev = x0.device
+        N = x0.shape[0]
+        L = mod._layers
+        bf = torch.bfloat16
+        T1 = c56.shape[1]          # 2 for 8-frame clips
+        H1 = c28.shape[2]          # 28
+        cat28 = torch.empty((N, 1, H1, H1, 128), dtype=bf, device=dev)
+        cba_fwd(L["upsample1"], mod.upsample1.bias, View(x0), View(cat28, 0, 64), relu=True)
+        cba_fwd(L["conv28"], mod.conv28.bias, View(c28), View(cat28, 64, 64), relu=True)
+        cat56 = torch.empty((N, T1, 2 * H1, 2 * H1, 128), dtype=bf, device=dev)
+        cba_fwd(L["upsample2"], mod.upsample2.bias, View(cat28), View(cat56, 0, 64), relu=True)
+        cba_fwd(L["conv56"], mod.conv56.bias, View(c56), View(cat56, 64, 64), relu=True)
+        cat112 = torch.empty((N, 2 * T1, 4 * H1, 4 * H1, 128), dtype=bf, device=dev)
+        cba_fwd(L["upsample3"], mod.upsample3.bias, View(cat56), View(cat112, 0, 64), relu=True)
+        cba_fwd(L["conv112"], mod.conv112.bias, View(c112), View(cat112, 64, 64), relu=True)
+        To, Ho = 4 * T1, 8 * H1
+        u4 = torch.empty((N, To, Ho, Ho, 128), dtype=bf, device=dev)
+        cba_fwd(L["upsample4"], mod.upsample4.bias, View(cat112), View(u4), relu=False, scale_nc=drop_scale)
+        rows = N * To * Ho * Ho
+        P = torch.empty((32, rows), dtype=torch.float32, device=dev)
+        ops.conv_fprop(L["smooth"].packed((To, Ho, Ho), "fprop"), "fprop", View(u4), P)
+        logits = torch.empty((N, 1, To, Ho, Ho), dtype=torch.float32, device=dev)
+        ops.stencil27_fwd(P, logits, mod.smooth.bias.detach(), N, To, Ho, Ho)
+        ctx.mod, ctx.drop = mod, drop_scale
+        ctx.t = (x0, c28, c56, c112, cat28, cat56, cat112, u4)
+        ctx.needs = ctx.needs_input_grad[:4]
+        return logits
+
+    @staticmethod
+    def backward(ctx, glog):
+        mod = ctx.mod
+        L = mod._layers
+        x0, c28, c56, c112, cat28, cat56, cat112, u4 = ctx.t
+        dev = glog.device
+        bf = torch.bfloat16
+        N, To, Ho = u4.shape[0], u4.shape[1], u4.shape[2]
+        glog = glog.contiguous().float()
+        dP = torch.empty((N, To, Ho, Ho, 32), dtype=bf, device=dev)
+        db_smooth = torch.zeros(1, dtype=torch.float32, device=dev)
+        ops.stencil27_bwd(glog, dP, db_smooth, N, To, Ho, Ho)
+        sm = L["smooth"]
+        du4 = torch.empty_like(u4)
+        ops.conv_fprop(sm.packed((To, Ho, Ho), "dgrad"), "dgrad", View(dP), View(du4))
+        dw_smooth = torch.zeros_like(mod.smooth.weight)
+        ops.conv_wgrad(sm.plan((To, Ho, Ho)), View(u4), View(dP), dw_smooth, atomic=True)
+        del dP
+        g = {}
+        dcat112 = torch.empty_like(cat112)
+        g["upsample4"] = cba_bwd(L["upsample4"], View(cat112), None, View(du4), False, ctx.drop, View(dcat112))
+        del du4
+        dc112 = torch.empty_like(c112) if ctx.needs[3] else None
+        g["conv112"] = cba_bwd(L["conv112"], View(c112), View(cat112, 64, 64), View(dcat112, 64, 64), True, None,
+                               View(dc112) if dc112 is not None else None)
+        dcat56 = torch.empty_like(cat56)
+        g["upsample3"] = cba_bwd(L["upsample3"], View(cat56), View(cat112, 0, 64), View(dcat112, 0, 64), True, None,
+                                 View(dcat56))
+        dc56 = torch.empty_like(c56) if ctx.needs[2] else None
+        g["conv56"] = cba_bwd(L["conv56"], View(c56), View(cat56, 64, 64), View(dcat56, 64, 64), True, None,
+                              View(dc56) if dc56 is not None else None)
+        dcat28 = torch.empty_like(cat28)
+        g["upsample2"] = cba_bwd(L["upsample2"], View(cat28), View(cat56, 0, 64), View(dcat56, 0, 64), True, None,
+                                 View(dcat28))
+        dc28 = torch.empty_like(c28) if ctx.needs[1] else None
+        g["conv28"] = cba_bwd(L["conv28"], View(c28), View(cat28, 64, 64), View(dcat28, 64, 64), True, None,
+                              View(dc28) if dc28 is not None else None)
+        dx0 = torch.empty_like(x0) if ctx.needs[0] else None
+        g["upsample1"] = cba_bwd(L["upsample1"], View(x0), View(cat28, 0, 64), View(dcat28, 0, 64), True, None,
+                                 View(dx0) if dx0 is not None else None)
+        g["smooth"] = (dw_smooth, db_smooth)
+        flat = []
+        for n in DecoderFn.ORDER:
+            flat += [g[n][0], g[n][1]]
+        return (dx0, dc28, dc56, dc112, None, None) + tuple(flat)
+
+
+class SmoothLayer:
+    """`smooth` weight (128,1,3,3,3) viewed as the 128 -> 27 (padded 32) projection matrix."""
+
+    def __init__(self, weight: torch.nn.Parameter):
+        self.weight = weight
+        self.plans: Dict = {}
+        self.keys: Dict = {}
+
+    def plan(self, dims) -> ConvPlan:
+        dims = tuple(int(v) for v in dims)
+        pl = self.plans.get(dims)
+        if pl is None:
+            pl = ConvPlan.pointwise_from_strides(128, 27, 32, 1, 27, dims)
+            self.plans[dims] = pl
+        return pl.to(self.weight.device)
+
+    def packed(self, dims, which) -> ConvPlan:
+        pl = self.plan(dims)
+        w = self.weight
+        key = (w.data_ptr(), w._version, STATE.weights_epoch)
+        if self.keys.get((tuple(dims), which)) != key:
+            pl.pack(w.detach(), which, ops.stream())
+            self.keys[(tuple(dims), which)] = key
+        return pl

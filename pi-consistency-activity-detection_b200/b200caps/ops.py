@@ -24,12 +24,170 @@ def _p(t: Optional[torch.Tensor]):
 
 
 # ---- tcgen05 implicit GEMM ---------------------------------------------------------------
-def conv_fprop(plan: ConvPlan, which: str, x: View, out: View, bias=None, scale_nc=None, relu=False,
+def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=None, relu=False,
                sigmoid_from=-1, accumulate=False, bn_tile=0):
+    """out: View (bf16 / fp32 rows) or a 2-D fp32 tensor (Cout_pad, rows) for the planar epilogue."""
     d = fill_conv_desc(plan, which, x, out, bias, scale_nc, relu, sigmoid_from, accumulate, bn_tile)
     _abi.call("b2c_conv_fprop", C.byref(d), stream())
 
 
-def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0):
-    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile)
+def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None):
+    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part)
     _abi.call("b2c_conv_wgrad", C.byref(d), stream())
+
+
+def pack_part(weight, packed, wtap_dev, R, ntaps, C, C_real, s_r, s_c, row_pitch=0, tap_pitch=0, col_off=0):
+    _abi.call("b2c_pack_weights", _p(weight), _p(packed), _p(wtap_dev), R, ntaps, C, C_real, s_r, s_c, row_pitch, tap_pitch,
+              col_off, stream())
+
+
+# ---- layout ---------------------------------------------------------------------------------
+def ncdhw_to_cl(x: torch.Tensor, cpad: int) -> torch.Tensor:
+    """(N,C,T,H,W) fp32 contiguous -> (N,T,H,W,cpad) bf16."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
+    N, Cc, T, H, W = x.shape
+    out = torch.empty((N, T, H, W, cpad), dtype=torch.bfloat16, device=x.device)
+    _abi.call("b2c_ncdhw_to_ndhwc", _p(x), _p(out), N, Cc, T * H * W, cpad, stream())
+    return out
+
+
+def cl_to_ncdhw_f32(v: View) -> torch.Tensor:
+    N = v.N
+    T, H, W = v.dims
+    out = torch.empty((N, v.C, T, H, W), dtype=torch.float32, device=v.t.device)
+    _abi.call("b2c_ndhwc_to_ncdhw_f32", v.ptr, v.row_stride, v.c_off, _p(out), N, v.C, T * H * W, stream())
+    return out
+
+
+# ---- batch norm -----------------------------------------------------------------------------
+def bn_sums(x: View, groups: int, ws: torch.Tensor):
+    _abi.call("b2c_bn_sums", x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(ws), stream())
+
+
+def bn_finalize(ws, ws_C, c_off, C, groups, rows_per_group, mean, rstd, rm, rv, momentum, eps):
+    _abi.call("b2c_bn_finalize", _p(ws), ws_C, c_off, C, groups, rows_per_group, _p(mean), _p(rstd), _p(rm), _p(rv),
+              momentum, eps, stream())
+
+
+def bn_relu_apply(x: View, groups, mean, rstd, gamma, beta, y: View, relu=True):
+    _abi.call("b2c_bn_relu_apply", x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(mean), _p(rstd), _p(gamma),
+              _p(beta), y.ptr, y.row_stride, y.c_off, int(relu), stream())
+
+
+def bn_relu_bwd_reduce(dy: View, y: View, x: View, groups, mean, rstd, ws, relu=True):
+    _abi.call("b2c_bn_relu_bwd_reduce", dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
+              x.row_stride, x.c_off, x.rows, x.C, groups, _p(mean), _p(rstd), _p(ws), int(relu), stream())
+
+
+def bn_relu_bwd_apply(dy: View, y: View, x: View, groups, mean, rstd, gamma, ws, dx: View, dgamma, dbeta, relu=True):
+    _abi.call("b2c_bn_relu_bwd_apply", dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
+              x.row_stride, x.c_off, x.rows, x.C, groups, _p(mean), _p(rstd), _p(gamma), _p(ws), dx.ptr, dx.row_stride,
+              dx.c_off, _p(dgamma), _p(dbeta), int(relu), stream())
+
+
+# ---- pooling / elementwise ------------------------------------------------------------------
+def maxpool_fwd(x: View, y: View, idx, k, s, p):
+    _abi.call("b2c_maxpool_fwd", x.ptr, x.row_stride, x.c_off, y.ptr, y.row_stride, y.c_off, _p(idx), x.N, x.C,
+              *x.dims, *y.dims, *k, *s, *p, stream())
+
+
+def maxpool_bwd(dy: View, idx, dx: View, k, s, p, accumulate=False):
+    _abi.call("b2c_maxpool_bwd", dy.ptr, dy.row_stride, dy.c_off, _p(idx), dx.ptr, dx.row_stride, dx.c_off, dx.N, dx.C,
+              *dx.dims, *dy.dims, *k, *s, *p, int(accumulate), stream())
+
+
+def channel_scale(x: View, scale_nc, y: View):
+    T, H, W = x.dims
+    _abi.call("b2c_channel_scale", x.ptr, x.row_stride, x.c_off, _p(scale_nc), y.ptr, y.row_stride, y.c_off, x.N,
+              T * H * W, x.C, stream())
+
+
+def act_bwd(dy: View, y: Optional[View], scale_nc, dz: Optional[View], dbias, relu: bool):
+    T, H, W = dy.dims
+    _abi.call("b2c_act_bwd", dy.ptr, dy.row_stride, dy.c_off, y.ptr if y is not None else None,
+              y.row_stride if y is not None else 0, y.c_off if y is not None else 0, _p(scale_nc),
+              dz.ptr if dz is not None else None, dz.row_stride if dz is not None else 0,
+              dz.c_off if dz is not None else 0, _p(dbias), dy.N, T * H * W, dy.C, int(relu), stream())
+
+
+def add(a: View, b: View, out: View):
+    _abi.call("b2c_add", a.ptr, a.row_stride, a.c_off, b.ptr, b.row_stride, b.c_off, out.ptr, out.row_stride, out.c_off,
+              a.rows, a.C, stream())
+
+
+def stencil27_fwd(P, out, bias, N, T, H, W):
+    _abi.call("b2c_stencil27_fwd", _p(P), _p(out), _p(bias), N, T, H, W, stream())
+
+
+def stencil27_bwd(dout, dP, dbias, N, T, H, W):
+    _abi.call("b2c_stencil27_bwd", _p(dout), _p(dP), _p(dbias), N, T, H, W, stream())
+
+
+# ---- capsule head ---------------------------------------------------------------------------
+def em_routing_fwd(caps, W, beta_u, beta_a, out, b, C):
+    _abi.call("b2c_em_routing_fwd", _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out), b, C, stream())
+
+
+def em_routing_bwd(caps, W, beta_u, beta_a, dout, dcaps, dW, dbu, dba, b, C):
+    _abi.call("b2c_em_routing_bwd", _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout), _p(dcaps), _p(dW), _p(dbu),
+              _p(dba), b, C, stream())
+
+
+def class_mean_fwd(rout, act, N, L, C):
+    _abi.call("b2c_class_mean_fwd", _p(rout), _p(act), N, L, C, stream())
+
+
+def pose_mask_fwd(rout, mask, x, N, L, C):
+    _abi.call("b2c_pose_mask_fwd", _p(rout), _p(mask), _p(x), N, L, C, stream())
+
+
+def caps_head_bwd(dx, mask, dact, dfeat, drout, N, L, C):
+    _abi.call("b2c_caps_head_bwd", _p(dx), _p(mask), _p(dact), _p(dfeat), _p(drout), N, L, C, stream())
+
+
+# ---- losses ---------------------------------------------------------------------------------
+def seg_loss_fwd(logits, targets, lab_idx, n_lab, V, sums, loss):
+    _abi.call("b2c_seg_loss_fwd", _p(logits), _p(targets), _p(lab_idx), n_lab, V, _p(sums), _p(loss), stream())
+
+
+def seg_loss_bwd(logits, targets, lab_idx, n_lab, V, sums, w_bce, w_dice, dlogits):
+    _abi.call("b2c_seg_loss_bwd", _p(logits), _p(targets), _p(lab_idx), n_lab, V, _p(sums), float(w_bce), float(w_dice),
+              _p(dlogits), stream())
+
+
+def spread_loss(act, target, lab_idx, n_lab, C, m_min, loss, w, dact):
+    _abi.call("b2c_spread_loss", _p(act), _p(target), _p(lab_idx), n_lab, C, float(m_min), _p(loss), float(w), _p(dact),
+              stream())
+
+
+def bv_mask(pred, flip_pred, m, mm, P, H, W, frames_cnt, use_sig, pred_tflip=0, fp_tflip=0, fp_wmirror=0):
+    _abi.call("b2c_bv_mask", _p(pred), _p(flip_pred), _p(m), _p(mm), P, H, W, frames_cnt, int(use_sig), int(pred_tflip),
+              int(fp_tflip), int(fp_wmirror), stream())
+
+
+def gv_mask(out, m, mm, P, H, W, lower, upper):
+    _abi.call("b2c_gv_mask", _p(out), _p(m), _p(mm), P, H, W, float(lower or 0.0), float(upper or 0.0),
+              int(lower is not None), int(upper is not None), stream())
+
+
+def cons_reduce(out, flp, w1, w2, wg, acc, P, H, W, mirror, w2_tflip):
+    _abi.call("b2c_cons_reduce", _p(out), _p(flp), _p(w1), _p(w2), _p(wg), _p(acc), P, H, W, int(mirror), int(w2_tflip),
+              stream())
+
+
+def cons_finish(acc, loss, P, H, W, mode, wt_ramp, bv_wt, gv_wt):
+    _abi.call("b2c_cons_finish", _p(acc), _p(loss), P, H, W, mode, float(wt_ramp), float(bv_wt), float(gv_wt), stream())
+
+
+def cons_grad(out, flp, w1, w2, wg, dout, dflp, P, H, W, mirror, w2_tflip, a_l2, a_lv, a_lg):
+    _abi.call("b2c_cons_grad", _p(out), _p(flp), _p(w1), _p(w2), _p(wg), _p(dout), _p(dflp), P, H, W, int(mirror),
+              int(w2_tflip), float(a_l2), float(a_lv), float(a_lg), stream())
+
+
+def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _abi.call("b2c_adam_step", _p(p), _p(g), _p(m), _p(v), n, float(lr), float(beta1), float(beta2), float(eps), int(step),
+              float(grad_scale), stream())
+
+
+def fill_f32(t, v):
+    _abi.call("b2c_fill_f32", _p(t), t.numel(), float(v), stream())

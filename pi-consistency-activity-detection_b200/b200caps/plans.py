@@ -141,7 +141,7 @@ class ConvPlan:
             # wgrad: g = x gathered with the fprop taps, p = dy at plain positions
             self.wgrad_cls = self.fprop[0]
             self.wgrad_geom = dict(g_is_input=True, sg=s, sp=(1, 1, 1), s_p=spec.Cin * T, s_g=T,
-                                   Cg=spec.Cin_pad, Cg_real=spec.Cin, Cp=spec.Cout_pad, Q=self.out_dims)
+                                   Cg=spec.Cin_pad, Cg_real=spec.Cin, Cp=spec.Cout_pad, Cp_real=spec.Cout, Q=self.out_dims)
         else:
             # weight (Cin, Cout, T)
             perf = [_dim_transposed_like(k[i], s[i], p[i], self.out_dims[i]) for i in range(3)]
@@ -155,8 +155,19 @@ class ConvPlan:
             # wgrad: g = dOut gathered with the dgrad taps, p = x at plain positions
             self.wgrad_cls = self.dgrad[0]
             self.wgrad_geom = dict(g_is_input=False, sg=s, sp=(1, 1, 1), s_p=spec.Cout * T, s_g=T,
-                                   Cg=spec.Cout_pad, Cg_real=spec.Cout, Cp=spec.Cin_pad, Q=self.in_dims)
+                                   Cg=spec.Cout_pad, Cg_real=spec.Cout, Cp=spec.Cin_pad, Cp_real=spec.Cin, Q=self.in_dims)
         self._device = None
+
+    @staticmethod
+    def pointwise_from_strides(Cin: int, Cout: int, Cout_pad: int, s_co: int, s_ci: int, dims) -> "ConvPlan":
+        """A 1x1x1 convolution whose (Cout, Cin) matrix lives inside another tensor with element strides
+        (s_co, s_ci) -- used for `smooth`: W[c][0][k] viewed as the 128 -> 27 projection (s_co=1, s_ci=27)."""
+        pl = ConvPlan(ConvSpec(Cin, Cout, (1, 1, 1), Cout_pad=Cout_pad), dims)
+        pl.fprop_pack = dict(R=Cout, R_pad=Cout_pad, C=Cin, C_real=Cin, s_r=s_co, s_c=s_ci)
+        pl.dgrad_pack = dict(R=Cin, R_pad=Cin, C=Cout_pad, C_real=Cout, s_r=s_ci, s_c=s_co)
+        pl.wgrad_geom = dict(g_is_input=True, sg=(1, 1, 1), sp=(1, 1, 1), s_p=s_co, s_g=s_ci, Cg=Cin, Cg_real=Cin,
+                             Cp=Cout_pad, Cp_real=Cout, Q=tuple(dims))
+        return pl
 
     # ---- algorithmic work (for roofline accounting) ------------------------------------
     def macs_fprop(self, n: int) -> int:
@@ -182,7 +193,7 @@ class ConvPlan:
             if cl.packed is None:
                 cl.packed = torch.zeros((pk["R_pad"], nt * pk["C"]), dtype=torch.bfloat16, device=weight.device)
             _abi.call("b2c_pack_weights", weight.data_ptr(), cl.packed.data_ptr(), cl.wtap_dev.data_ptr(), pk["R"], nt,
-                      pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], stream_ptr)
+                      pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], 0, 0, 0, stream_ptr)
 
 
 @dataclass
@@ -225,21 +236,30 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
     si, so = (plan.fprop_si, plan.fprop_so) if which == "fprop" else (plan.dgrad_si, plan.dgrad_so)
     pk = plan.fprop_pack if which == "fprop" else plan.dgrad_pack
     exp_in, exp_out = (plan.in_dims, plan.out_dims) if which == "fprop" else (plan.out_dims, plan.in_dims)
-    assert x.dims == tuple(exp_in) and out.dims == tuple(exp_out), (which, x.dims, exp_in, out.dims, exp_out)
-    assert x.C == pk["C"] and out.C == pk["R_pad"], (which, x.C, pk["C"], out.C, pk["R_pad"])
-    assert x.t.dtype == torch.bfloat16 and out.t.dtype in (torch.bfloat16, torch.float32)
+    assert x.dims == tuple(exp_in), (which, x.dims, exp_in)
+    assert x.C == pk["C"], (which, x.C, pk["C"])
+    assert x.t.dtype == torch.bfloat16
     d = _abi.ConvDesc()
-    d.inp, d.out = x.ptr, out.ptr
+    d.inp = x.ptr
     d.bias = bias.data_ptr() if bias is not None else None
     d.scale_nc = scale_nc.data_ptr() if scale_nc is not None else None
-    d.in_row_stride, d.out_row_stride = x.row_stride, out.row_stride
-    d.in_c_off, d.out_c_off, d.Cin, d.Cout = x.c_off, out.c_off, pk["C"], pk["R_pad"]
+    d.in_row_stride = x.row_stride
+    d.in_c_off, d.Cin, d.Cout = x.c_off, pk["C"], pk["R_pad"]
     d.N = x.N
     d.Ti, d.Hi, d.Wi = x.dims
-    d.To, d.Ho, d.Wo = out.dims
+    d.To, d.Ho, d.Wo = exp_out
     d.si_t, d.si_h, d.si_w = si
     d.so_t, d.so_h, d.so_w = so
-    d.out_fp32 = 1 if out.t.dtype == torch.float32 else 0
+    if isinstance(out, View):
+        assert out.dims == tuple(exp_out) and out.C == pk["R_pad"], (which, out.dims, exp_out, out.C, pk["R_pad"])
+        assert out.t.dtype in (torch.bfloat16, torch.float32)
+        d.out, d.out_row_stride, d.out_c_off = out.ptr, out.row_stride, out.c_off
+        d.out_fp32 = 1 if out.t.dtype == torch.float32 else 0
+    else:   # planar fp32 (Cout_pad, rows)
+        rows = x.N * exp_out[0] * exp_out[1] * exp_out[2]
+        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (pk["R_pad"], rows)
+        d.out, d.out_row_stride, d.out_c_off = out.data_ptr(), rows, 0
+        d.out_fp32 = 2
     d.relu, d.sigmoid_from, d.accumulate, d.bn_tile = int(relu), int(sigmoid_from), int(accumulate), int(bn_tile)
     d.nclass = len(classes)
     assert 1 <= d.nclass <= 8
@@ -252,16 +272,22 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
     return d
 
 
-def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0) -> _abi.WgradDesc:
-    """x = layer input, dy = gradient of the layer output, dw = fp32 gradient in torch weight layout."""
-    geo = plan.wgrad_geom
+def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0,
+                    part=None) -> _abi.WgradDesc:
+    """x = layer input, dy = gradient of the layer output, dw = fp32 gradient in torch weight layout.
+    part=(c_off, C): restrict a fused layer's wgrad to the output-channel window of one member weight."""
+    geo = dict(plan.wgrad_geom)
     cl = plan.wgrad_cls
+    if part is not None:
+        assert geo["g_is_input"], "fused members are plain convolutions"
+        dy = View(dy.t, dy.c_off + part[0], part[1])
+        geo["Cp"] = part[1]
+        geo["Cp_real"] = part[1]
     g, p = (x, dy) if geo["g_is_input"] else (dy, x)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     assert g.C == geo["Cg"] and p.C == geo["Cp"], (g.C, geo["Cg"], p.C, geo["Cp"])
-    # only the gathered side may carry zero-padded channels (Cg_real); the plain side indexes dw directly
-    assert geo["Cp"] == (plan.spec.Cout if geo["g_is_input"] else plan.spec.Cin), "padded channels on the plain side"
     d = _abi.WgradDesc()
+    d.Cp_real = geo.get("Cp_real", geo["Cp"])
     d.g, d.p, d.dw = g.ptr, p.ptr, dw.data_ptr()
     d.taps, d.wtap = cl.taps_dev.data_ptr(), cl.wtap_dev.data_ptr()
     d.g_row_stride, d.p_row_stride, d.s_p, d.s_g = g.row_stride, p.row_stride, geo["s_p"], geo["s_g"]

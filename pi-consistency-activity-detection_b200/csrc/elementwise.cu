@@ -108,15 +108,17 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const bf16* __restrict
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&w[i], sh[i]);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ ws, long long rows_per_group, int C, int groups,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* running_mean, float* running_var,
-                                   float momentum, float eps) {
+__global__ void bn_finalize_kernel(const float* __restrict__ ws_all, int ws_C, int c_off, long long rows_per_group, int C,
+                                   int groups, float* __restrict__ mean, float* __restrict__ rstd, float* running_mean,
+                                   float* running_var, float momentum, float eps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const float* ws = ws_all + c_off;
+  const int Cw = ws_C;
   const double M = (double)rows_per_group;
   float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
   for (int g = 0; g < groups; ++g) {
-    const double s1 = ws[(long long)g * 2 * C + c], s2 = ws[(long long)g * 2 * C + C + c];
+    const double s1 = ws[(long long)g * 2 * Cw + c], s2 = ws[(long long)g * 2 * Cw + Cw + c];
     const double mu = s1 / M;
     double var = s2 / M - mu * mu;
     if (var < 0) var = 0;
@@ -447,9 +449,10 @@ __global__ void __launch_bounds__(kBlock) add_kernel(const bf16* __restrict__ a,
 
 // ---------------------------------------------------------------------------------------------
 // smooth = ConvTranspose3d(128->1, k3, p1): out[o] = bias + sum_k P_k[o + 1 - k], P planar fp32 [32][rows]
-__global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __restrict__ P, float* __restrict__ out, float bias,
-                                                               int N, int T, int H, int W) {
+__global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __restrict__ P, float* __restrict__ out,
+                                                               const float* __restrict__ bias_p, int N, int T, int H, int W) {
   const long long rows = (long long)N * T * H * W;
+  const float bias = bias_p ? __ldg(bias_p) : 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
     long long p = i;
     const int w = (int)(p % W); p /= W;
@@ -475,9 +478,10 @@ __global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __re
   }
 }
 // adjoint: dP[i][k] = dout[i - 1 + k] (bf16 rows of 32, taps 27..31 zero)
-__global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dP, int N, int T,
-                                                               int H, int W) {
+__global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dP,
+                                                               float* __restrict__ dbias, int N, int T, int H, int W) {
   const long long rows = (long long)N * T * H * W;
+  float bsum = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
     long long p = i;
     const int w = (int)(p % W); p /= W;
@@ -503,9 +507,21 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
     }
 #pragma unroll
     for (int k = 27; k < 32; ++k) v[k] = 0.f;
+    bsum += v[13];  // centre tap == dout[i]
     bf16* dst = dP + i * 32;
 #pragma unroll
     for (int q = 0; q < 4; ++q) st16(dst + q * 8, pack8(v + q * 8));
+  }
+  if (dbias) {
+    __shared__ float sb[kBlock / 32];
+    bsum = warp_sum(bsum);
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = bsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int q = 0; q < kBlock / 32; ++q) t += sb[q];
+      atomicAdd(dbias, t);
+    }
   }
 }
 
@@ -550,19 +566,28 @@ B2C_API int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_
   return 0;
 }
 
-B2C_API int b2c_bn_stats(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
-                         float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
-                         b2c_stream_t s) {
-  B2C_REQUIRE(x && ws && mean && rstd, "bn_stats: null pointer");
-  CHECK_VIEW("bn_stats", C, row_stride, c_off);
-  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_stats: rows=%lld not divisible by groups=%d", (long long)rows, groups);
+B2C_API int b2c_bn_sums(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
+                        b2c_stream_t s) {
+  B2C_REQUIRE(x && ws, "bn_sums: null pointer");
+  CHECK_VIEW("bn_sums", C, row_stride, c_off);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_sums: rows=%lld not divisible by groups=%d", (long long)rows, groups);
   const long long rpg = rows / groups;
   dim3 grid((unsigned)row_grid(rpg, C, 2), (unsigned)groups);
   bn_stats_kernel<<<grid, kBlock, 2 * C * sizeof(float), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(ws, rpg, C, groups, mean, rstd, running_mean, running_var,
-                                                                  momentum, eps);
-  b2c_launches_add(2);
-  B2C_LAUNCH_CHECK("bn_stats");
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("bn_sums");
+  return 0;
+}
+
+B2C_API int b2c_bn_finalize(const float* ws, int32_t ws_C, int32_t c_off, int32_t C, int32_t groups, int64_t rows_per_group,
+                            float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
+                            b2c_stream_t s) {
+  B2C_REQUIRE(ws && mean && rstd && C > 0 && c_off >= 0 && c_off + C <= ws_C && groups >= 1 && rows_per_group > 0,
+              "bn_finalize: bad args");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(ws, ws_C, c_off, rows_per_group, C, groups, mean, rstd,
+                                                                  running_mean, running_var, momentum, eps);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("bn_finalize");
   return 0;
 }
 
@@ -689,7 +714,8 @@ B2C_API int b2c_add(const void* a, int64_t a_rs, int32_t a_co, const void* b, in
   return 0;
 }
 
-B2C_API int b2c_stencil27_fwd(const float* P, float* out, float bias, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s) {
+B2C_API int b2c_stencil27_fwd(const float* P, float* out, const float* bias, int32_t N, int32_t T, int32_t H, int32_t W,
+                              b2c_stream_t s) {
   B2C_REQUIRE(P && out && N > 0, "stencil27_fwd: bad args");
   stencil27_fwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(P, out, bias, N, T, H, W);
   b2c_launches_add(1);
@@ -697,9 +723,10 @@ B2C_API int b2c_stencil27_fwd(const float* P, float* out, float bias, int32_t N,
   return 0;
 }
 
-B2C_API int b2c_stencil27_bwd(const float* dout, void* dP, int32_t N, int32_t T, int32_t H, int32_t W, b2c_stream_t s) {
+B2C_API int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t N, int32_t T, int32_t H, int32_t W,
+                              b2c_stream_t s) {
   B2C_REQUIRE(dout && dP && N > 0, "stencil27_bwd: bad args");
-  stencil27_bwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, N, T, H, W);
+  stencil27_bwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, dbias, N, T, H, W);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("stencil27_bwd");
   return 0;

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int pc = n0 + c0 + i;
-        if (pc < d.Cp) {
+        if (pc < d.Cp_real) {
           float* dst = d.dw + base + (long long)pc * d.s_p;
           if (d.atomic) atomicAdd(dst, v[i]);
           else *dst = v[i];
@@ -476,7 +476,8 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
 
 // ---------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ packed, const int32_t* __restrict__ wtap,
-                                    int R, int ntaps, int C, int C_real, long long s_r, long long s_c) {
+                                    int R, int ntaps, int C, int C_real, long long s_r, long long s_c, long long row_pitch,
+                                    long long tap_pitch, long long col_off) {
   const long long total = (long long)R * ntaps * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -485,7 +486,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     const int r = (int)(t2 / ntaps);
     float v = 0.f;
     if (c < C_real) v = w[(long long)r * s_r + (long long)c * s_c + wtap[t]];
-    packed[i] = __float2bfloat16(v);
+    packed[(long long)r * row_pitch + (long long)t * tap_pitch + col_off + c] = __float2bfloat16(v);
   }
 }
 
@@ -554,6 +555,7 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
               "conv_wgrad: unaligned view");
   B2C_REQUIRE(((uintptr_t)d.g & 15) == 0 && ((uintptr_t)d.p & 15) == 0, "conv_wgrad: tensors must be 16B aligned");
   if (d.Cg_real <= 0) d.Cg_real = d.Cg;
+  if (d.Cp_real <= 0 || d.Cp_real > d.Cp) d.Cp_real = d.Cp;
   if (d.bn_tile <= 0) d.bn_tile = pick_bn_tile(d.Cp);
   B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_wgrad: bn_tile=%d invalid", d.bn_tile);
   const long long Mtot = (long long)d.N * d.Qt * d.Qh * d.Qw;
@@ -595,15 +597,18 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
 }
 
 B2C_API int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, int32_t R, int32_t ntaps, int32_t C,
-                             int32_t C_real, int64_t s_r, int64_t s_c, b2c_stream_t stream) {
+                             int32_t C_real, int64_t s_r, int64_t s_c, int64_t row_pitch, int64_t tap_pitch, int64_t col_off,
+                             b2c_stream_t stream) {
   B2C_REQUIRE(w && packed && wtap, "pack_weights: null pointer");
   B2C_REQUIRE(R > 0 && ntaps > 0 && C > 0 && C_real > 0 && C_real <= C, "pack_weights: bad dims");
   const long long total = (long long)R * ntaps * C;
   int blocks = (int)((total + 255) / 256);
   const int cap = b2c_num_sms() * 16;
   if (blocks > cap) blocks = cap;
+  if (row_pitch <= 0) row_pitch = (int64_t)ntaps * C;
+  if (tap_pitch <= 0) tap_pitch = C;
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<bf16*>(packed), wtap, R, ntaps, C, C_real,
-                                                               s_r, s_c);
+                                                               s_r, s_c, row_pitch, tap_pitch, col_off);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("pack_weights launch");
   return 0;

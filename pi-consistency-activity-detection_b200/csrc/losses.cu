@@ -206,59 +206,53 @@ __device__ __forceinline__ void fold14(const float* v, float* o) {
   for (int k = 1; k < 7; ++k) o[k] = v[k] + v[14 - k];
 }
 
-// grid (blocks over H*W, P)
+// grid (blocks over H*W, P).  cyc = pred[0..7] ++ flip_pred[1..6] (helpers.py:29) with optional index
+// transforms so the fused step can feed the raw second-pass output: pred_tflip / fp_tflip reverse time,
+// fp_wmirror mirrors W (main_ucf101.py:100,114-115).
 template <int NF>
-__global__ void __launch_bounds__(kBlock) bv_masks_kernel(const float* __restrict__ out, const float* __restrict__ flp,
-                                                          float* __restrict__ m_clk, float* __restrict__ m_anti, float* __restrict__ mm,
-                                                          int H, int W, int use_sig) {
+__global__ void __launch_bounds__(kBlock) bv_mask_kernel(const float* __restrict__ pred, const float* __restrict__ fpred,
+                                                         float* __restrict__ m, float* __restrict__ mm, int H, int W, int use_sig,
+                                                         int pred_tflip, int fp_tflip, int fp_wmirror) {
   const int p = blockIdx.y;
   const long long HW = (long long)H * W;
-  const float* o = out + (long long)p * kT * HW;
-  const float* f = flp + (long long)p * kT * HW;
-  float mn0 = INFINITY, mx0 = -INFINITY, mn1 = INFINITY, mx1 = -INFINITY;
+  const float* o = pred + (long long)p * kT * HW;
+  const float* f = fpred + (long long)p * kT * HW;
+  float mn0 = INFINITY, mx0 = -INFINITY;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < HW; i += (long long)gridDim.x * kBlock) {
     const int w = (int)(i % W);
-    const long long im = i - w + (W - 1 - w);   // mirrored column (main_ucf101.py:100 flip on W)
-    float ov[kT], fv[kT];
+    const long long im = fp_wmirror ? (i - w + (W - 1 - w)) : i;
+    float cyc[14], v[14], r[8];
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
-      ov[t] = o[t * HW + i];
-      fv[t] = f[t * HW + im];
-      if (use_sig) {
-        ov[t] = sigmoid_precise(ov[t]);
-        fv[t] = sigmoid_precise(fv[t]);
-      }
+      float a = o[(pred_tflip ? 7 - t : t) * HW + i];
+      if (use_sig) a = sigmoid_precise(a);
+      cyc[t] = a;
     }
-    float cyc[14], v[14], r[8];
-    // clockwise: pred = out, flip_pred = flipT(F)  -> [o0..o7, F6, F5, .., F1]
 #pragma unroll
-    for (int t = 0; t < 8; ++t) cyc[t] = ov[t];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cyc[8 + k] = fv[6 - k];
+    for (int k = 1; k < 7; ++k) {
+      float a = f[(fp_tflip ? 7 - k : k) * HW + im];
+      if (use_sig) a = sigmoid_precise(a);
+      cyc[7 + k] = a;
+    }
     cyc_var<NF>(cyc, v);
     fold14(v, r);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      m_clk[((long long)p * kT + t) * HW + i] = r[t];
+      m[((long long)p * kT + t) * HW + i] = r[t];
       mn0 = fminf(mn0, r[t]);
       mx0 = fmaxf(mx0, r[t]);
     }
-    // anticlockwise: pred = flipT(out), flip_pred = F  -> [o7..o0, F1, .., F6]
-#pragma unroll
-    for (int t = 0; t < 8; ++t) cyc[t] = ov[7 - t];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cyc[8 + k] = fv[1 + k];
-    cyc_var<NF>(cyc, v);
-    fold14(v, r);
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      m_anti[((long long)p * kT + t) * HW + i] = r[t];
-      mn1 = fminf(mn1, r[t]);
-      mx1 = fmaxf(mx1, r[t]);
-    }
   }
-  block_minmax(mn0, mx0, mm + p * 4 + 0, mm + p * 4 + 1);
-  block_minmax(mn1, mx1, mm + p * 4 + 2, mm + p * 4 + 3);
+  block_minmax(mn0, mx0, mm + p * 2 + 0, mm + p * 2 + 1);
+}
+// per-clip min-max normalisation exactly as the reference: x -= min ; x /= (max(x) - min(x) + 1e-7)
+__global__ void __launch_bounds__(kBlock) minmax_normalize_kernel(float* __restrict__ m, const float* __restrict__ mm, long long per_clip) {
+  const int p = blockIdx.y;
+  const float mn = mm[p * 2], mx = mm[p * 2 + 1];
+  const float den = ((mx - mn) - 0.f) + 1e-7f;
+  float* x = m + (long long)p * per_clip;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < per_clip; i += (long long)gridDim.x * kBlock)
+    x[i] = (x[i] - mn) / den;
 }
 
 __device__ __forceinline__ void grad_t8(const float* a, float* g) {   // np.gradient along an axis of length 8
@@ -294,37 +288,30 @@ __global__ void __launch_bounds__(kBlock) gv_mask_kernel(const float* __restrict
   block_minmax(mn, mx, mm + p * 2, mm + p * 2 + 1);
 }
 
-// per-clip min-max normalisation exactly as the reference: x -= min ; x /= (max(x) - min(x) + 1e-7)
-__device__ __forceinline__ float norm_w(float raw, float mn, float mx) { return (raw - mn) / ((mx - mn) - 0.f + 1e-7f); }
-
-// consistency reduce: thread per (t,h,w), loop over clips.  acc: double[4] = sum d^2, sum w_clk d^2,
-// sum w_anti d^2, sum_thw (sum_i d_i^2)(sum_j w_j)
+// consistency reduce: thread per (t,h,w), loop over clips.  Weights are already normalised.
+//   d = (mirror ? flipW(flp) : flp) - out
+//   acc: double[4] = sum d^2, sum w1 d^2, sum w2' d^2 (w2' = time-flipped w2 if w2_tflip), sum_thw (sum_i d_i^2)(sum_j wg_j)
 __global__ void __launch_bounds__(kBlock) cons_reduce_kernel(const float* __restrict__ out, const float* __restrict__ flp,
-                                                             const float* __restrict__ m_clk, const float* __restrict__ m_anti,
-                                                             const float* __restrict__ m_gv, const float* __restrict__ mm_bv,
-                                                             const float* __restrict__ mm_gv, double* acc, int P, int H, int W,
-                                                             int mode) {
+                                                             const float* __restrict__ w1, const float* __restrict__ w2,
+                                                             const float* __restrict__ wg, double* acc, int P, int H, int W,
+                                                             int mirror, int w2_tflip) {
   const long long HW = (long long)H * W, THW = kT * HW;
   float part[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < THW; i += (long long)gridDim.x * kBlock) {
     const int w = (int)(i % W);
     const int t = (int)(i / HW);
-    const long long im = i - w + (W - 1 - w);
-    const long long ia = i + (long long)(7 - 2 * t) * HW;   // time-flipped index (anticlock mask is flipped back by the caller)
+    const long long im = mirror ? (i - w + (W - 1 - w)) : i;
+    const long long ia = w2_tflip ? (i + (long long)(7 - 2 * t) * HW) : i;
     float A = 0.f, B = 0.f;
     for (int p = 0; p < P; ++p) {
       const float d = flp[p * THW + im] - out[p * THW + i];
       const float d2 = d * d;
       part[0] += d2;
-      if (mode & 1) {
-        const float wc = norm_w(m_clk[p * THW + i], mm_bv[p * 4 + 0], mm_bv[p * 4 + 1]);
-        const float wa = norm_w(m_anti[p * THW + ia], mm_bv[p * 4 + 2], mm_bv[p * 4 + 3]);
-        part[1] += wc * d2;
-        part[2] += wa * d2;
-      }
-      if (mode & 2) {
+      if (w1) part[1] += w1[p * THW + i] * d2;
+      if (w2) part[2] += w2[p * THW + ia] * d2;
+      if (wg) {
         A += d2;
-        B += norm_w(m_gv[p * THW + i], mm_gv[p * 2], mm_gv[p * 2 + 1]);
+        B += wg[p * THW + i];
       }
     }
     part[3] += A * B;
@@ -348,36 +335,34 @@ __global__ void cons_finish_kernel(const double* acc, float* loss, int P, long l
   loss[2] = (float)lv;
   loss[3] = (float)lg;
 }
+// g_d = (a_l2 + a_lv (w1 + w2')) 2 d / (P THW) + a_lg 2 B d / (THW P^2) ; dout -= g_d ; dflp[mirrored] += g_d
 __global__ void __launch_bounds__(kBlock) cons_grad_kernel(const float* __restrict__ out, const float* __restrict__ flp,
-                                                           const float* __restrict__ m_clk, const float* __restrict__ m_anti,
-                                                           const float* __restrict__ m_gv, const float* __restrict__ mm_bv,
-                                                           const float* __restrict__ mm_gv, float* __restrict__ dout,
-                                                           float* __restrict__ dflp, int P, int H, int W, int mode, float a_l2,
-                                                           float a_lv, float a_lg) {
+                                                           const float* __restrict__ w1, const float* __restrict__ w2,
+                                                           const float* __restrict__ wg, float* __restrict__ dout,
+                                                           float* __restrict__ dflp, int P, int H, int W, int mirror, int w2_tflip,
+                                                           float a_l2, float a_lv, float a_lg) {
   const long long HW = (long long)H * W, THW = kT * HW;
-  // coefficient of each term on d = F - out:  g_d = (a_l2 + a_lv (w_clk + w_anti)) 2 d / (P THW) + a_lg 2 B d / (THW P^2)
   const float k1 = 2.f / (float)((double)P * (double)THW);
   const float k2 = 2.f / (float)((double)THW * (double)P * (double)P);
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < THW; i += (long long)gridDim.x * kBlock) {
     const int w = (int)(i % W);
     const int t = (int)(i / HW);
-    const long long im = i - w + (W - 1 - w);
-    const long long ia = i + (long long)(7 - 2 * t) * HW;
+    const long long im = mirror ? (i - w + (W - 1 - w)) : i;
+    const long long ia = w2_tflip ? (i + (long long)(7 - 2 * t) * HW) : i;
     float B = 0.f;
-    if (mode & 2)
-      for (int p = 0; p < P; ++p) B += norm_w(m_gv[p * THW + i], mm_gv[p * 2], mm_gv[p * 2 + 1]);
+    if (wg)
+      for (int p = 0; p < P; ++p) B += wg[p * THW + i];
     for (int p = 0; p < P; ++p) {
       const float d = flp[p * THW + im] - out[p * THW + i];
       float coef = a_l2 * k1;
-      if (mode & 1) {
-        const float wc = norm_w(m_clk[p * THW + i], mm_bv[p * 4 + 0], mm_bv[p * 4 + 1]);
-        const float wa = norm_w(m_anti[p * THW + ia], mm_bv[p * 4 + 2], mm_bv[p * 4 + 3]);
-        coef += a_lv * k1 * (wc + wa);
-      }
-      if (mode & 2) coef += a_lg * k2 * B;
+      float ws = 0.f;
+      if (w1) ws += w1[p * THW + i];
+      if (w2) ws += w2[p * THW + ia];
+      coef += a_lv * k1 * ws;
+      if (wg) coef += a_lg * k2 * B;
       const float g = coef * d;
-      dout[p * THW + i] -= g;
-      dflp[p * THW + im] += g;
+      if (dout) dout[p * THW + i] -= g;
+      if (dflp) dflp[p * THW + im] += g;
     }
   }
 }
@@ -428,19 +413,23 @@ B2C_API int b2c_spread_loss(const float* act, const float* target, const int32_t
   return 0;
 }
 
-B2C_API int b2c_bv_masks(const float* out, const float* flp, float* m_clk, float* m_anti, float* mm, int32_t P, int32_t H, int32_t W,
-                         int32_t frames_cnt, int32_t use_sigmoid, b2c_stream_t s) {
-  B2C_REQUIRE(out && flp && m_clk && m_anti && mm && P > 0, "bv_masks: bad args");
-  B2C_REQUIRE(frames_cnt == 3 || frames_cnt == 5, "bv_masks: frames_cnt=%d (the reference implements only 3 and 5)", frames_cnt);
-  init_minmax_kernel<<<(2 * P + 127) / 128, 128, 0, (cudaStream_t)s>>>(mm, 2 * P);
+B2C_API int b2c_bv_mask(const float* pred, const float* flip_pred, float* m, float* mm, int32_t P, int32_t H, int32_t W,
+                        int32_t frames_cnt, int32_t use_sigmoid, int32_t pred_tflip, int32_t fp_tflip, int32_t fp_wmirror,
+                        b2c_stream_t s) {
+  B2C_REQUIRE(pred && flip_pred && m && mm && P > 0, "bv_mask: bad args");
+  B2C_REQUIRE(frames_cnt == 3 || frames_cnt == 5, "bv_mask: frames_cnt=%d (the reference implements only 3 and 5)", frames_cnt);
+  init_minmax_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)s>>>(mm, P);
   int bx = blocks_for((long long)H * W);
   if ((long long)bx * P > (long long)b2c_num_sms() * 8) bx = (b2c_num_sms() * 8 + P - 1) / P;
   if (frames_cnt == 3)
-    bv_masks_kernel<3><<<dim3(bx, P), kBlock, 0, (cudaStream_t)s>>>(out, flp, m_clk, m_anti, mm, H, W, use_sigmoid);
+    bv_mask_kernel<3><<<dim3(bx, P), kBlock, 0, (cudaStream_t)s>>>(pred, flip_pred, m, mm, H, W, use_sigmoid, pred_tflip, fp_tflip,
+                                                                   fp_wmirror);
   else
-    bv_masks_kernel<5><<<dim3(bx, P), kBlock, 0, (cudaStream_t)s>>>(out, flp, m_clk, m_anti, mm, H, W, use_sigmoid);
-  b2c_launches_add(2);
-  B2C_LAUNCH_CHECK("bv_masks");
+    bv_mask_kernel<5><<<dim3(bx, P), kBlock, 0, (cudaStream_t)s>>>(pred, flip_pred, m, mm, H, W, use_sigmoid, pred_tflip, fp_tflip,
+                                                                   fp_wmirror);
+  minmax_normalize_kernel<<<dim3(bx, P), kBlock, 0, (cudaStream_t)s>>>(m, mm, (long long)kT * H * W);
+  b2c_launches_add(3);
+  B2C_LAUNCH_CHECK("bv_mask");
   return 0;
 }
 
@@ -451,20 +440,18 @@ B2C_API int b2c_gv_mask(const float* out, float* m, float* mm, int32_t P, int32_
   int bx = blocks_for((long long)H * W);
   if ((long long)bx * P > (long long)b2c_num_sms() * 8) bx = (b2c_num_sms() * 8 + P - 1) / P;
   gv_mask_kernel<<<dim3(bx, P), kBlock, 0, (cudaStream_t)s>>>(out, m, mm, H, W, lower, upper, use_lower, use_upper);
-  b2c_launches_add(2);
+  minmax_normalize_kernel<<<dim3(bx, P), kBlock, 0, (cudaStream_t)s>>>(m, mm, (long long)kT * H * W);
+  b2c_launches_add(3);
   B2C_LAUNCH_CHECK("gv_mask");
   return 0;
 }
 
-B2C_API int b2c_cons_reduce(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
-                            const float* mm_bv, const float* mm_gv, double* acc, int32_t P, int32_t H, int32_t W, int32_t mode,
-                            b2c_stream_t s) {
+B2C_API int b2c_cons_reduce(const float* out, const float* flp, const float* w1, const float* w2, const float* wg, double* acc,
+                            int32_t P, int32_t H, int32_t W, int32_t mirror, int32_t w2_tflip, b2c_stream_t s) {
   B2C_REQUIRE(out && flp && acc && P > 0, "cons_reduce: bad args");
-  B2C_REQUIRE(!(mode & 1) || (m_clk && m_anti && mm_bv), "cons_reduce: bv mode without masks");
-  B2C_REQUIRE(!(mode & 2) || (m_gv && mm_gv), "cons_reduce: gv mode without mask");
   cudaMemsetAsync(acc, 0, 4 * sizeof(double), (cudaStream_t)s);
-  cons_reduce_kernel<<<blocks_for((long long)kT * H * W), kBlock, 0, (cudaStream_t)s>>>(out, flp, m_clk, m_anti, m_gv, mm_bv, mm_gv,
-                                                                                       acc, P, H, W, mode);
+  cons_reduce_kernel<<<blocks_for((long long)kT * H * W), kBlock, 0, (cudaStream_t)s>>>(out, flp, w1, w2, wg, acc, P, H, W, mirror,
+                                                                                       w2_tflip);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("cons_reduce");
   return 0;
@@ -479,18 +466,12 @@ B2C_API int b2c_cons_finish(const double* acc, float* loss, int32_t P, int32_t H
   return 0;
 }
 
-B2C_API int b2c_cons_grad(const float* out, const float* flp, const float* m_clk, const float* m_anti, const float* m_gv,
-                          const float* mm_bv, const float* mm_gv, float* dout, float* dflp, int32_t P, int32_t H, int32_t W,
-                          int32_t mode, float wt_ramp, float bv_wt, float gv_wt, float wt, b2c_stream_t s) {
-  B2C_REQUIRE(out && flp && dout && dflp && P > 0, "cons_grad: bad args");
-  float a_l2, a_lv, a_lg;
-  if ((mode & 3) == 3) { a_l2 = bv_wt * (1.f - wt_ramp); a_lv = bv_wt * wt_ramp; a_lg = gv_wt; }
-  else if (mode & 2) { a_l2 = 0.f; a_lv = 0.f; a_lg = 1.f; }
-  else if (mode & 1) { a_l2 = 1.f - wt_ramp; a_lv = wt_ramp; a_lg = 0.f; }
-  else { a_l2 = 1.f; a_lv = 0.f; a_lg = 0.f; }
-  cons_grad_kernel<<<blocks_for((long long)kT * H * W), kBlock, 0, (cudaStream_t)s>>>(out, flp, m_clk, m_anti, m_gv, mm_bv, mm_gv,
-                                                                                     dout, dflp, P, H, W, mode, a_l2 * wt, a_lv * wt,
-                                                                                     a_lg * wt);
+B2C_API int b2c_cons_grad(const float* out, const float* flp, const float* w1, const float* w2, const float* wg, float* dout,
+                          float* dflp, int32_t P, int32_t H, int32_t W, int32_t mirror, int32_t w2_tflip, float a_l2, float a_lv,
+                          float a_lg, b2c_stream_t s) {
+  B2C_REQUIRE(out && flp && (dout || dflp) && P > 0, "cons_grad: bad args");
+  cons_grad_kernel<<<blocks_for((long long)kT * H * W), kBlock, 0, (cudaStream_t)s>>>(out, flp, w1, w2, wg, dout, dflp, P, H, W,
+                                                                                     mirror, w2_tflip, a_l2, a_lv, a_lg);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("cons_grad");
   return 0;
