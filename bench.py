@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- train clips/s of the semi-supervised step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode bv|gv|bvgv]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1)
+
+ours      : the fused step of b200caps (pi-consistency-activity-detection_b200/b200caps/step.py) on config 2 of
+            BASELINE.json (UCF101-24, 8 labeled + 8 unlabeled clips per GPU, --bv, wt_cons 0.1, synthetic data,
+            random-init weights).  Prints ONE JSON line (rank 0).
+reference : the reference's own algorithm on the box's host cores (the oracle port of its training step; the
+            reference is CPU-runnable Python, SURVEY config 1) on a bounded sample (1 + 1 clips per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pi-consistency-activity-detection_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "train clips/sec (labeled+unlabeled fwd+bwd)"
+UNIT = "clips/s"
+WORKLOAD = "UCF101-24 semi-supervised step bs 8 labeled + 8 unlabeled, --bv temporal-variance mask, wt_cons 0.1, l2, 1xB200"
+# algorithmic conv / transposed-conv FLOPs per clip (both passes, fwd + dgrad + wgrad)
+FLOP_PER_CLIP = 713.8e9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bv", choices=["bv", "gv", "bvgv", "none"])
+    ap.add_argument("--clips", type=int, default=8, help="labeled (= unlabeled) clips per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def synthetic_host_batch(n_lab, n_unl, seed, num_classes=24):
+    """U[0,1) clips, flipped copies, random class, random box mask; pinned host memory."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    n = n_lab + n_unl
+    data = torch.rand((n, 3, 8, 224, 224), generator=g)
+    action = torch.randint(0, num_classes, (n, 1), generator=g).float()
+    seg = torch.zeros((n, 1, 8, 224, 224))
+    for i in range(n):
+        y0, x0 = [int(v) for v in torch.randint(0, 150, (2,), generator=g)]
+        hh, ww = [int(v) for v in torch.randint(30, 74, (2,), generator=g)]
+        seg[i, 0, :, y0:y0 + hh, x0:x0 + ww] = 1.0
+    labels = torch.cat([torch.ones(n_lab), torch.zeros(n_unl)])
+    fl = torch.flip(data, [4]).contiguous()
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+    return dict(data=pin(data), fl_data=pin(fl), action=pin(action), seg=pin(seg), labels=labels)
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(steps: int, warmup: int):
+    """The reference's training step (oracle port, fp32, torch CPU autograd) on 1 labeled + 1 unlabeled clip,
+    all host threads.  Returns (seconds per step, threads)."""
+    import torch
+    from oracle import restate
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = restate.make_state_dict(24, seed=0)
+    sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
+    b = restate.synthetic_batch(1, 1, seed=47)
+    masks = restate.make_drop_masks(2, seed=3, count=4)
+    names = [k for k, v in sdg.items() if v.requires_grad]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = restate.train_step_losses(sdg, b["data"], b["fl_data"], b["action"], b["seg"], b["labels"], epoch=1,
+                                        bv=True, gv=False, n_frames=5, wt_cons=0.1, drop_masks=masks)
+        torch.autograd.grad(res["total"], [sdg[k] for k in names], allow_unused=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    sec, threads = cpu_reference_step_time(max(1, args.steps), max(0, args.warmup))
+    value = 2.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic (U[0,1) clips, random-init weights)",
+        "config": {"workload": WORKLOAD, "sample": "1 labeled + 1 unlabeled clip per step (bounded sample of the 8+8 workload)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "oracle port of train_model_interface + backward, 1+1 clips, fp32, torch CPU"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a GPU: the b200caps hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from b200caps import _abi, ops
+    from b200caps.step import StepArgs, TrainStep
+    from models.capsules_ucf101 import CapsNet
+
+    torch.manual_seed(47 + rank)
+    model = CapsNet(pt_path=None).to(dev)
+    sa = StepArgs(bv=args.mode in ("bv", "bvgv"), gv=args.mode in ("gv", "bvgv"), n_frames=5, wt_cons=0.1, lr=1e-4)
+    step = TrainStep(model, sa)
+    P = 2 * args.clips
+    hb = synthetic_host_batch(args.clips, args.clips, seed=47 + rank)
+    db = {k: (v.to(dev) if k != "labels" else v) for k, v in hb.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------------
+    for _ in range(args.warmup):
+        step(db["data"], db["fl_data"], db["action"], db["seg"], db["labels"], epoch=1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _abi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step(db["data"], db["fl_data"], db["action"], db["seg"], db["labels"], epoch=1)
+    e1.record()
+    barrier()
+    launches = _abi.launch_count() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    value = P * world / (ms / 1e3)
+    loss_val = float(res["total"])
+
+    # ---- end-to-end through the public call with HOST buffers ------------------------------------------
+    h2d = sum(hb[k].numel() * hb[k].element_size() for k in ("data", "fl_data", "action", "seg"))
+    out_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        d = {k: hb[k].to(dev, non_blocking=True) for k in ("data", "fl_data", "action", "seg")}
+        r = step(d["data"], d["fl_data"], d["action"], d["seg"], hb["labels"], epoch=1)
+        out_host.copy_(r["total"].detach().reshape(1), non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = P * world / (ms_e2e / 1e3)
+
+    # ---- kernel-level timing of the dominant kernel family (tcgen05 implicit GEMM) -------------------------
+    roofline = None
+    if rank == 0 and not args.no_kernel_timing:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ops.TIMING = []
+        step(db["data"], db["fl_data"], db["action"], db["seg"], db["labels"], epoch=1)
+        torch.cuda.synchronize()
+        recs, ops.TIMING = ops.TIMING, None
+        t_ms = sum(a.elapsed_time(b) for _, a, b in recs)
+        achieved = FLOP_PER_CLIP * P / (t_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (all conv / transposed-conv launches)",
+                    "kernel_ms_per_step": t_ms, "kernel_launches_per_step": len(recs),
+                    "share_of_step": t_ms / ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+                    if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
+                    "algorithmic_flop_per_step": FLOP_PER_CLIP * P}
+        if world == 1:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            agg = {}
+            for tag, a, b in recs:
+                d = agg.setdefault(tag, [0, 0.0])
+                d[0] += 1
+                d[1] += a.elapsed_time(b)
+            with open(os.path.join(ROOT, "gpurun_out", "igemm_kernel_times.json"), "w") as f:
+                json.dump({"ms_per_step_total": t_ms, "by_kind": agg}, f, indent=1)
+    if world > 1:
+        dist.barrier()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, threads = cpu_reference_step_time(1, 1)
+        cpu_baseline = {"value": 2.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "oracle port of the full --bv step + backward, 1 labeled + 1 unlabeled clip, fp32, 1 warm-up + 1 timed"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (U[0,1) 8x224x224 clips, random box masks, random-init weights)",
+            "config": {"workload": WORKLOAD if world == 1 else WORKLOAD.replace("1xB200", f"{world}xB200 data-parallel, NCCL all-reduce"),
+                       "clips_per_gpu": P, "mode": args.mode, "n_frames": 5,
+                       "l2": "working set per step (>20 GB of activations) >> 126 MB L2; no explicit flush",
+                       "parallelism": f"dp{world}", "loss_last_step": loss_val},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

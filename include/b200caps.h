@@ -177,6 +177,9 @@ int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, c
  * dW/dbeta_u/dbeta_a are accumulated (atomicAdd) -- zero them first. */
 int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
                        float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s);
+/* PrimaryCaps backward prologue (capsules_ucf101.py:43-49 adjoint): g, out fp32 (rows,544); dz bf16 (rows,544) =
+ * g * (col >= 512 ? a(1-a) : 1); dbias[544] += column sums (first 512: pose bias, last 32: a bias). */
+int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, b2c_stream_t s);
 /* class activation = mean over the 400 locations (capsules_ucf101.py:450-451); feat is a view of out */
 int b2c_class_mean_fwd(const float* rout, float* act, int32_t N, int32_t L, int32_t C, b2c_stream_t s);
 /* pose masking (capsules_ucf101.py:455-483): x[n,l,j*16+h] = mu[n,l,j,h] * mask[n,j]  -> bf16 (N,L,C*16) */

@@ -31,6 +31,32 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 
 # --------------------------------------------------------------------------------------
+# optional emulation of the CUDA path's bf16 rounding points (operands of every tensor-core
+# GEMM, stored activations) on top of the otherwise exact restatement.  The routing of this
+# model is chaotically sensitive at random init: bf16 rounding anywhere upstream
+# moves the mask logits by O(1).  Comparing the CUDA path with the *same roundings applied to
+# the oracle* separates implementation fidelity from that conditioning.  Straight-through in
+# autograd (rounding has identity gradient), like the CUDA backward.
+# --------------------------------------------------------------------------------------
+_EMULATE_BF16 = False
+
+
+class emulate_bf16:
+    def __enter__(self):
+        global _EMULATE_BF16
+        self.prev, _EMULATE_BF16 = _EMULATE_BF16, True
+
+    def __exit__(self, *a):
+        global _EMULATE_BF16
+        _EMULATE_BF16 = self.prev
+
+
+def _q(x: Tensor) -> Tensor:
+    if not _EMULATE_BF16:
+        return x
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+# --------------------------------------------------------------------------------------
 # architecture tables (models/pytorch_i3d.py:221-281, truncated at Mixed_4f by
 # models/capsules_ucf101.py:343)
 # --------------------------------------------------------------------------------------
@@ -178,7 +204,7 @@ class BNState:
 
 def unit3d(x: Tensor, sd, prefix: str, k, s, bn: BNState) -> Tensor:
     """Unit3D.forward (pytorch_i3d.py:89-120): same-pad -> conv3d(no bias) -> BN -> ReLU."""
-    x = F.conv3d(_pad_same(x, k, s), sd[prefix + ".conv3d.weight"], None, stride=tuple(s))
+    x = _q(F.conv3d(_pad_same(_q(x), k, s), _q(sd[prefix + ".conv3d.weight"]), None, stride=tuple(s)))
     w, b = sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"]
     rm, rv = sd[prefix + ".bn.running_mean"].to(x.dtype), sd[prefix + ".bn.running_var"].to(x.dtype)
     if bn.train:
@@ -192,7 +218,7 @@ def unit3d(x: Tensor, sd, prefix: str, k, s, bn: BNState) -> Tensor:
         mean, var = rm, rv
     sh = (1, -1, 1, 1, 1)
     x = (x - mean.view(sh)) / torch.sqrt(var.view(sh) + 1e-3) * w.view(sh) + b.view(sh)
-    return F.relu(x)
+    return _q(F.relu(x))
 
 
 def inception(x: Tensor, sd, p: str, bn: BNState) -> Tensor:
@@ -225,8 +251,8 @@ def i3d_trunk(x: Tensor, sd, bn: BNState, prefix: str = "conv1.") -> Tuple[Tenso
 # --------------------------------------------------------------------------------------
 def primary_caps(x: Tensor, sd) -> Tensor:
     """PrimaryCaps.forward (capsules_ucf101.py:43-49) -> (B, 20, 20, 544)."""
-    p = F.conv2d(x, sd["primary_caps.pose.weight"], sd["primary_caps.pose.bias"])
-    a = torch.sigmoid(F.conv2d(x, sd["primary_caps.a.weight"], sd["primary_caps.a.bias"]))
+    p = F.conv2d(_q(x), _q(sd["primary_caps.pose.weight"]), sd["primary_caps.pose.bias"])
+    a = torch.sigmoid(F.conv2d(_q(x), _q(sd["primary_caps.a.weight"]), sd["primary_caps.a.bias"]))
     return torch.cat([p, a], dim=1).permute(0, 2, 3, 1)
 
 
@@ -264,29 +290,32 @@ def em_routing(poses: Tensor, a_in: Tensor, W: Tensor, beta_u: Tensor, beta_a: T
     return mu.view(b, C, 16), a_out
 
 
-def capsnet_forward(sd, img: Tensor, classification: Tensor, concat_labels: Tensor, epoch: int,
-                    thresh_ep: int, train: bool, drop_masks: Optional[Sequence[Tensor]] = None,
-                    bn: Optional[BNState] = None, num_classes: int = 24):
-    """CapsNet.forward (capsules_ucf101.py:413-512).
-
-    drop_masks: the two Dropout3d keep-masks already scaled by 1/(1-p) -- shapes
-    (B,832,1,1,1) and (B,128,1,1,1) -- or None for no dropout (eval / p=0).
-    Returns (logits (B,1,8,224,224), class_act (B,C), feat (B,400,C))."""
-    bn = bn or BNState(train)
-    C = num_classes
+def encode(sd, img: Tensor, drop_mask1: Optional[Tensor], bn: BNState):
+    """Segment 1 of CapsNet.forward (capsules_ucf101.py:425-431): trunk + Dropout3d."""
     x, cross56, cross112 = i3d_trunk(img, sd, bn)
-    if drop_masks is not None:
-        x = x * drop_masks[0].to(x.dtype)
-    x = x.view(-1, 832, 28, 28)
-    cross28 = x
-    caps = primary_caps(x, sd)                                  # (B,20,20,544)
+    if drop_mask1 is not None:
+        x = _q(x * drop_mask1.to(x.dtype))
+    return x.view(-1, 832, 28, 28), cross56, cross112
+
+
+def capsules(sd, x: Tensor):
+    """Segment 2 (:432-436): PrimaryCaps + EM routing.  Returns caps (B,20,20,544) and rout (B,20,20,C*17)."""
+    caps = primary_caps(x, sd)
     B_ = caps.shape[0]
-    poses_in = caps[..., :512].reshape(B_ * 400, 32, 16)
-    acts_in = caps[..., 512:].reshape(B_ * 400, 32)
-    mu, a_out = em_routing(poses_in, acts_in, sd["conv_caps.weights"][0], sd["conv_caps.beta_u"],
-                           sd["conv_caps.beta_a"])
-    poses = mu.view(B_, 20, 20, C, 16)
-    activations = a_out.view(B_, 20, 20, C)
+    mu, a_out = em_routing(caps[..., :512].reshape(B_ * 400, 32, 16), caps[..., 512:].reshape(B_ * 400, 32),
+                           sd["conv_caps.weights"][0], sd["conv_caps.beta_u"], sd["conv_caps.beta_a"])
+    C = a_out.shape[-1]
+    rout = torch.cat([mu.reshape(B_, 20, 20, C * 16), a_out.reshape(B_, 20, 20, C)], dim=-1)
+    return caps, rout
+
+
+def decode(sd, rout: Tensor, cross28: Tensor, cross56: Tensor, cross112: Tensor, classification: Tensor,
+           concat_labels: Tensor, epoch: int, thresh_ep: int, train: bool, drop_mask2: Optional[Tensor]):
+    """Segment 3 (:438-512): class activations, pose masking, localisation decoder."""
+    B_ = rout.shape[0]
+    C = rout.shape[-1] // 17
+    poses = rout[..., :C * 16].reshape(B_, 20, 20, C, 16)
+    activations = rout[..., C * 16:]
     feat = activations.reshape(B_, 400, C)
     class_act = activations.mean(dim=1).mean(dim=1)
     eye = torch.eye(C, dtype=poses.dtype)
@@ -301,24 +330,40 @@ def capsnet_forward(sd, img: Tensor, classification: Tensor, concat_labels: Tens
     else:
         mask = eye[torch.argmax(class_act, dim=1)]
     poses = poses * mask.view(B_, 1, 1, C, 1)
-    x = poses.reshape(B_, 20, 20, C * 16).permute(0, 3, 1, 2)
-    x = F.relu(F.conv_transpose2d(x, sd["upsample1.weight"], sd["upsample1.bias"]))
+    x = _q(poses.reshape(B_, 20, 20, C * 16).permute(0, 3, 1, 2))
+    W = {k: _q(sd[k + ".weight"]) for k in ("upsample1", "conv28", "upsample2", "conv56", "upsample3", "conv112",
+                                             "upsample4", "smooth")}
+    x = _q(F.relu(F.conv_transpose2d(x, W["upsample1"], sd["upsample1.bias"])))
     x = x.view(-1, 64, 1, 28, 28)
-    c28 = F.relu(F.conv2d(cross28, sd["conv28.weight"], sd["conv28.bias"], padding=1)).view(-1, 64, 1, 28, 28)
+    c28 = _q(F.relu(F.conv2d(cross28, W["conv28"], sd["conv28.bias"], padding=1))).view(-1, 64, 1, 28, 28)
     x = torch.cat((x, c28), dim=1)
-    x = F.relu(F.conv_transpose3d(x, sd["upsample2.weight"], sd["upsample2.bias"], stride=2, padding=1,
-                                  output_padding=1))
-    c56 = F.relu(F.conv3d(cross56, sd["conv56.weight"], sd["conv56.bias"], padding=1))
+    x = _q(F.relu(F.conv_transpose3d(x, W["upsample2"], sd["upsample2.bias"], stride=2, padding=1, output_padding=1)))
+    c56 = _q(F.relu(F.conv3d(cross56, W["conv56"], sd["conv56.bias"], padding=1)))
     x = torch.cat((x, c56), dim=1)
-    x = F.relu(F.conv_transpose3d(x, sd["upsample3.weight"], sd["upsample3.bias"], stride=2, padding=1,
-                                  output_padding=1))
-    c112 = F.relu(F.conv3d(cross112, sd["conv112.weight"], sd["conv112.bias"], padding=1))
+    x = _q(F.relu(F.conv_transpose3d(x, W["upsample3"], sd["upsample3.bias"], stride=2, padding=1, output_padding=1)))
+    c112 = _q(F.relu(F.conv3d(cross112, W["conv112"], sd["conv112.bias"], padding=1)))
     x = torch.cat((x, c112), dim=1)
-    x = F.conv_transpose3d(x, sd["upsample4.weight"], sd["upsample4.bias"], stride=2, padding=1, output_padding=1)
-    if drop_masks is not None:
-        x = x * drop_masks[1].to(x.dtype)
-    x = F.conv_transpose3d(x, sd["smooth.weight"], sd["smooth.bias"], padding=1)
+    x = F.conv_transpose3d(x, W["upsample4"], sd["upsample4.bias"], stride=2, padding=1, output_padding=1)
+    if drop_mask2 is not None:
+        x = x * drop_mask2.to(x.dtype)
+    x = _q(x)
+    x = F.conv_transpose3d(x, W["smooth"], sd["smooth.bias"], padding=1)
     return x.view(-1, 1, 8, 224, 224), class_act, feat
+
+
+def capsnet_forward(sd, img: Tensor, classification: Tensor, concat_labels: Tensor, epoch: int,
+                    thresh_ep: int, train: bool, drop_masks: Optional[Sequence[Tensor]] = None,
+                    bn: Optional[BNState] = None, num_classes: int = 24):
+    """CapsNet.forward (capsules_ucf101.py:413-512) = encode -> capsules -> decode.
+
+    drop_masks: the two Dropout3d keep-masks already scaled by 1/(1-p) -- shapes
+    (B,832,1,1,1) and (B,128,1,1,1) -- or None for no dropout (eval / p=0).
+    Returns (logits (B,1,8,224,224), class_act (B,C), feat (B,400,C))."""
+    bn = bn or BNState(train)
+    x, cross56, cross112 = encode(sd, img, None if drop_masks is None else drop_masks[0], bn)
+    _, rout = capsules(sd, x)
+    return decode(sd, rout, x, cross56, cross112, classification, concat_labels, epoch, thresh_ep, train,
+                  None if drop_masks is None else drop_masks[1])
 
 
 # --------------------------------------------------------------------------------------

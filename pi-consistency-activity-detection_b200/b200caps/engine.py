@@ -23,6 +23,7 @@ class _State:
     weights_epoch = 0          # bumped by the fused optimiser (raw-pointer updates bypass tensor._version)
     dropout_source: Optional[Callable] = None   # tests inject Dropout3d masks: f(n, c, device) -> (n,c) fp32 keep*2
     bn_groups = 1              # >1: the batch holds several independent forward passes (own BN statistics each)
+    direct_grads = False       # fused step: kernels accumulate straight into param.grad (flat buffer views)
 
 
 STATE = _State()
@@ -30,6 +31,14 @@ STATE = _State()
 
 def bump_weights_epoch():
     STATE.weights_epoch += 1
+
+
+def grad_buf(p: torch.Tensor):
+    """Where a parameter gradient is accumulated: the existing .grad (fused step, zeroed once per step) or a
+    fresh zero tensor that is handed back to autograd."""
+    if STATE.direct_grads and p.grad is not None:
+        return p.grad, True
+    return torch.zeros_like(p), False
 
 
 def require_cuda(t: torch.Tensor, what: str):
@@ -153,24 +162,25 @@ def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: 
     return sv
 
 
-def unit_bwd(layer: ConvLayer, gamma, sv: UnitSaved, x: View, y: View, gy: View, dx: Optional[View], accumulate: bool):
-    """Returns (dweight, dgamma, dbeta); writes dx (+= when accumulate)."""
+def unit_bwd(layer: ConvLayer, gamma, beta, sv: UnitSaved, x: View, y: View, gy: View, dx: Optional[View],
+             accumulate: bool):
+    """Returns (dweight, dgamma, dbeta) (None where accumulated directly into .grad); writes dx (+= when accumulate)."""
     dev = x.t.device
     Cout = sv.raw.shape[-1]
     raw = View(sv.raw)
     ws = torch.zeros((sv.groups, 2, Cout), dtype=torch.float32, device=dev)
     ops.bn_relu_bwd_reduce(gy, y, raw, sv.groups, sv.mean, sv.rstd, ws, relu=True)
     draw = torch.empty_like(sv.raw)
-    dgamma = torch.zeros(Cout, dtype=torch.float32, device=dev)
-    dbeta = torch.zeros(Cout, dtype=torch.float32, device=dev)
+    dgamma, d1 = grad_buf(gamma)
+    dbeta, d2 = grad_buf(beta)
     ops.bn_relu_bwd_apply(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
     if dx is not None:
         pl = layer.packed(sv.dims, "dgrad")
         ops.conv_fprop(pl, "dgrad", View(draw), dx, accumulate=accumulate)
     pl = layer.plan(sv.dims)
-    dw = torch.zeros_like(layer.weight)
+    dw, d0 = grad_buf(layer.weight)
     ops.conv_wgrad(pl, x, View(draw), dw, atomic=True)
-    return dw, dgamma, dbeta
+    return (None if d0 else dw), (None if d1 else dgamma), (None if d2 else dbeta)
 
 
 def cba_fwd(layer: ConvLayer, bias, x: View, y: View, relu: bool, scale_nc=None, sigmoid_from=-1):
@@ -180,27 +190,26 @@ def cba_fwd(layer: ConvLayer, bias, x: View, y: View, relu: bool, scale_nc=None,
                    sigmoid_from=sigmoid_from)
 
 
-def cba_bwd(layer: ConvLayer, x: View, y: Optional[View], gy: View, relu: bool, scale_nc, dx: Optional[View],
-            accumulate: bool = False, want_bias: bool = True):
-    """Returns (dweight, dbias)."""
+def cba_bwd(layer: ConvLayer, bias, x: View, y: Optional[View], gy: View, relu: bool, scale_nc, dx: Optional[View],
+            accumulate: bool = False):
+    """Returns (dweight, dbias) (None where accumulated directly into .grad)."""
     dev = x.t.device
     C = gy.C
-    dbias = torch.zeros(C, dtype=torch.float32, device=dev) if want_bias else None
+    dbias, d1 = grad_buf(bias)
     if relu or scale_nc is not None:
         dz_t = torch.empty((gy.N,) + tuple(gy.dims) + (C,), dtype=torch.bfloat16, device=dev)
         dz = View(dz_t)
         ops.act_bwd(gy, y if relu else None, scale_nc, dz, dbias, relu)
     else:
         dz = gy
-        if want_bias:
-            ops.act_bwd(gy, None, None, None, dbias, False)
+        ops.act_bwd(gy, None, None, None, dbias, False)
     if dx is not None:
         pl = layer.packed(x.dims, "dgrad")
         ops.conv_fprop(pl, "dgrad", dz, dx, accumulate=accumulate)
     pl = layer.plan(x.dims)
-    dw = torch.zeros_like(layer.weight)
+    dw, d0 = grad_buf(layer.weight)
     ops.conv_wgrad(pl, x, dz, dw, atomic=True)
-    return dw, dbias
+    return (None if d0 else dw), (None if d1 else dbias)
 
 
 def dropout_scale(n: int, c: int, device, p: float = 0.5) -> torch.Tensor:
@@ -236,7 +245,7 @@ class Unit3DFn(torch.autograd.Function):
         gy = grad_cl(gy)
         need_dx = ctx.needs_input_grad[0]
         dx = torch.empty_like(ctx.x) if need_dx else None
-        dw, dg, db = unit_bwd(ctx.mod._layer, ctx.gamma, ctx.sv, View(ctx.x), View(ctx.y), View(gy),
+        dw, dg, db = unit_bwd(ctx.mod._layer, ctx.gamma, ctx.mod.bn.bias, ctx.sv, View(ctx.x), View(ctx.y), View(gy),
                               View(dx) if need_dx else None, False)
         return dx, dw, dg, db, None
 
@@ -324,7 +333,7 @@ class InceptionFn(torch.autograd.Function):
 
         def run(name, xin, yv, gyv, dxv, acc):
             m = u[name]
-            grads[name] = unit_bwd(m._layer, m.bn.weight, sv[name], xin, yv, gyv, dxv, acc)
+            grads[name] = unit_bwd(m._layer, m.bn.weight, m.bn.bias, sv[name], xin, yv, gyv, dxv, acc)
 
         run("b0", xv, View(out, 0, c0), View(gout, 0, c0), View(dx), False)
         run("b1b", View(ctx.mid1), View(out, c0, c2), View(gout, c0, c2), View(dmid1), False)
@@ -410,9 +419,9 @@ class FusedConvLayer:
         pl = self.plan(in_dims)
         outs = []
         for w, co, off in zip(self.weights, self.couts, self.offs):
-            dw = torch.zeros_like(w)
+            dw, direct = grad_buf(w)
             ops.conv_wgrad(pl, x, dy, dw, atomic=True, part=(off, co))
-            outs.append(dw)
+            outs.append(None if direct else dw)
         return outs
 
 
@@ -436,22 +445,23 @@ class PrimaryCapsFn(torch.autograd.Function):
     def backward(ctx, g):
         mod, x, out = ctx.mod, ctx.x, ctx.out
         layer: FusedConvLayer = mod._layer
-        N, _, h, w, _ = out.shape
-        # pre-activation gradient in bf16 rows + bias gradient: act_bwd on an fp32->bf16 staged copy.
-        # sigmoid'(z) = a (1 - a) for the 32 activation columns, identity for the poses.
         g = g.contiguous().float()
-        dz = g.clone()
-        a = out[..., 512:]
-        dz[..., 512:] = g[..., 512:] * a * (1.0 - a)
-        dbias = dz.sum(dim=(0, 1, 2, 3))
-        dzb = dz.to(torch.bfloat16)
+        rows = out.numel() // 544
+        dzb = torch.empty(out.shape, dtype=torch.bfloat16, device=out.device)
+        dbias = torch.zeros(544, dtype=torch.float32, device=out.device)
+        ops.primarycaps_bwd_prep(g, out, dzb, dbias, rows)
         dims = x.shape[1:4]
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             ops.conv_fprop(layer.packed(dims, "dgrad"), "dgrad", View(dzb), View(dx))
         dwp, dwa = layer.wgrad(dims, View(x), View(dzb))
-        return dx, dwp, dbias[:512].contiguous(), dwa, dbias[512:].contiguous(), None
+        dbp, dba = dbias[:512], dbias[512:]
+        if STATE.direct_grads and mod.pose.bias.grad is not None:
+            mod.pose.bias.grad.add_(dbp)
+            mod.a.bias.grad.add_(dba)
+            dbp = dba = None
+        return dx, dwp, dbp, dwa, dba, None
 
 
 class EMRoutingFn(torch.autograd.Function):
@@ -474,12 +484,12 @@ class EMRoutingFn(torch.autograd.Function):
         N, h, w, _ = caps.shape
         g = g.contiguous().float()
         dcaps = torch.empty_like(caps)
-        dW = torch.zeros_like(W)
-        dbu = torch.zeros_like(beta_u)
-        dba = torch.zeros_like(beta_a)
+        dW, d0 = grad_buf(W)
+        dbu, d1 = grad_buf(beta_u)
+        dba, d2 = grad_buf(beta_a)
         ops.em_routing_bwd(caps, W.detach().reshape(32, C, 4, 4).contiguous(), beta_u.detach().contiguous(),
                            beta_a.detach().contiguous(), g, dcaps, dW, dbu, dba, N * h * w, C)
-        return dcaps, dW, dbu, dba
+        return dcaps, (None if d0 else dW), (None if d1 else dbu), (None if d2 else dba)
 
 
 class CapsHeadFn(torch.autograd.Function):
@@ -569,37 +579,37 @@ class DecoderFn(torch.autograd.Function):
         N, To, Ho = u4.shape[0], u4.shape[1], u4.shape[2]
         glog = glog.contiguous().float()
         dP = torch.empty((N, To, Ho, Ho, 32), dtype=bf, device=dev)
-        db_smooth = torch.zeros(1, dtype=torch.float32, device=dev)
+        db_smooth, ds1 = grad_buf(mod.smooth.bias)
         ops.stencil27_bwd(glog, dP, db_smooth, N, To, Ho, Ho)
         sm = L["smooth"]
         du4 = torch.empty_like(u4)
         ops.conv_fprop(sm.packed((To, Ho, Ho), "dgrad"), "dgrad", View(dP), View(du4))
-        dw_smooth = torch.zeros_like(mod.smooth.weight)
+        dw_smooth, ds0 = grad_buf(mod.smooth.weight)
         ops.conv_wgrad(sm.plan((To, Ho, Ho)), View(u4), View(dP), dw_smooth, atomic=True)
         del dP
         g = {}
         dcat112 = torch.empty_like(cat112)
-        g["upsample4"] = cba_bwd(L["upsample4"], View(cat112), None, View(du4), False, ctx.drop, View(dcat112))
+        g["upsample4"] = cba_bwd(L["upsample4"], mod.upsample4.bias, View(cat112), None, View(du4), False, ctx.drop, View(dcat112))
         del du4
         dc112 = torch.empty_like(c112) if ctx.needs[3] else None
-        g["conv112"] = cba_bwd(L["conv112"], View(c112), View(cat112, 64, 64), View(dcat112, 64, 64), True, None,
+        g["conv112"] = cba_bwd(L["conv112"], mod.conv112.bias, View(c112), View(cat112, 64, 64), View(dcat112, 64, 64), True, None,
                                View(dc112) if dc112 is not None else None)
         dcat56 = torch.empty_like(cat56)
-        g["upsample3"] = cba_bwd(L["upsample3"], View(cat56), View(cat112, 0, 64), View(dcat112, 0, 64), True, None,
+        g["upsample3"] = cba_bwd(L["upsample3"], mod.upsample3.bias, View(cat56), View(cat112, 0, 64), View(dcat112, 0, 64), True, None,
                                  View(dcat56))
         dc56 = torch.empty_like(c56) if ctx.needs[2] else None
-        g["conv56"] = cba_bwd(L["conv56"], View(c56), View(cat56, 64, 64), View(dcat56, 64, 64), True, None,
+        g["conv56"] = cba_bwd(L["conv56"], mod.conv56.bias, View(c56), View(cat56, 64, 64), View(dcat56, 64, 64), True, None,
                               View(dc56) if dc56 is not None else None)
         dcat28 = torch.empty_like(cat28)
-        g["upsample2"] = cba_bwd(L["upsample2"], View(cat28), View(cat56, 0, 64), View(dcat56, 0, 64), True, None,
+        g["upsample2"] = cba_bwd(L["upsample2"], mod.upsample2.bias, View(cat28), View(cat56, 0, 64), View(dcat56, 0, 64), True, None,
                                  View(dcat28))
         dc28 = torch.empty_like(c28) if ctx.needs[1] else None
-        g["conv28"] = cba_bwd(L["conv28"], View(c28), View(cat28, 64, 64), View(dcat28, 64, 64), True, None,
+        g["conv28"] = cba_bwd(L["conv28"], mod.conv28.bias, View(c28), View(cat28, 64, 64), View(dcat28, 64, 64), True, None,
                               View(dc28) if dc28 is not None else None)
         dx0 = torch.empty_like(x0) if ctx.needs[0] else None
-        g["upsample1"] = cba_bwd(L["upsample1"], View(x0), View(cat28, 0, 64), View(dcat28, 0, 64), True, None,
+        g["upsample1"] = cba_bwd(L["upsample1"], mod.upsample1.bias, View(x0), View(cat28, 0, 64), View(dcat28, 0, 64), True, None,
                                  View(dx0) if dx0 is not None else None)
-        g["smooth"] = (dw_smooth, db_smooth)
+        g["smooth"] = (None if ds0 else dw_smooth, None if ds1 else db_smooth)
         flat = []
         for n in DecoderFn.ORDER:
             flat += [g[n][0], g[n][1]]

@@ -24,16 +24,30 @@ def _p(t: Optional[torch.Tensor]):
 
 
 # ---- tcgen05 implicit GEMM ---------------------------------------------------------------
+TIMING = None   # bench.py: list collecting (kind, start_event, end_event) of every implicit-GEMM launch
+
+
+def _launch(kind: str, name: str, desc):
+    if TIMING is None:
+        _abi.call(name, C.byref(desc), stream())
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _abi.call(name, C.byref(desc), stream())
+    b.record()
+    TIMING.append((kind, a, b))
+
+
 def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=None, relu=False,
                sigmoid_from=-1, accumulate=False, bn_tile=0):
     """out: View (bf16 / fp32 rows) or a 2-D fp32 tensor (Cout_pad, rows) for the planar epilogue."""
     d = fill_conv_desc(plan, which, x, out, bias, scale_nc, relu, sigmoid_from, accumulate, bn_tile)
-    _abi.call("b2c_conv_fprop", C.byref(d), stream())
+    _launch(which, "b2c_conv_fprop", d)
 
 
 def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None):
     d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part)
-    _abi.call("b2c_conv_wgrad", C.byref(d), stream())
+    _launch("wgrad", "b2c_conv_wgrad", d)
 
 
 def pack_part(weight, packed, wtap_dev, R, ntaps, C, C_real, s_r, s_c, row_pitch=0, tap_pitch=0, col_off=0):
@@ -42,11 +56,13 @@ def pack_part(weight, packed, wtap_dev, R, ntaps, C, C_real, s_r, s_c, row_pitch
 
 
 # ---- layout ---------------------------------------------------------------------------------
-def ncdhw_to_cl(x: torch.Tensor, cpad: int) -> torch.Tensor:
-    """(N,C,T,H,W) fp32 contiguous -> (N,T,H,W,cpad) bf16."""
+def ncdhw_to_cl(x: torch.Tensor, cpad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,C,T,H,W) fp32 contiguous -> (N,T,H,W,cpad) bf16 (optionally into a preallocated slice)."""
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
     N, Cc, T, H, W = x.shape
-    out = torch.empty((N, T, H, W, cpad), dtype=torch.bfloat16, device=x.device)
+    if out is None:
+        out = torch.empty((N, T, H, W, cpad), dtype=torch.bfloat16, device=x.device)
+    assert tuple(out.shape) == (N, T, H, W, cpad) and out.is_contiguous() and out.dtype == torch.bfloat16
     _abi.call("b2c_ncdhw_to_ndhwc", _p(x), _p(out), N, Cc, T * H * W, cpad, stream())
     return out
 
@@ -131,6 +147,10 @@ def em_routing_fwd(caps, W, beta_u, beta_a, out, b, C):
 def em_routing_bwd(caps, W, beta_u, beta_a, dout, dcaps, dW, dbu, dba, b, C):
     _abi.call("b2c_em_routing_bwd", _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout), _p(dcaps), _p(dW), _p(dbu),
               _p(dba), b, C, stream())
+
+
+def primarycaps_bwd_prep(g, out, dz, dbias, rows):
+    _abi.call("b2c_primarycaps_bwd_prep", _p(g), _p(out), _p(dz), _p(dbias), rows, stream())
 
 
 def class_mean_fwd(rout, act, N, L, C):

@@ -1,0 +1,210 @@
+"""The fused semi-supervised training step -- what the reference's ``train()`` loop body does
+(main_ucf101.py:169-184: zero_grad, train_model_interface :50-150, loss.backward(), Adam step) -- scheduled
+for B200:
+
+  * both forward passes (clips and their horizontal flips) run as ONE batch of 2P clips; BatchNorm keeps the
+    reference's per-pass statistics through the kernels' `groups` argument (STATE.bn_groups = 2);
+  * losses, consistency masks and their gradients stay on the device (no numpy / host round trip);
+  * parameters, gradients and Adam moments live in flat fp32 buffers: one fused Adam launch, one (bucketed)
+    NCCL all-reduce, gradients accumulated by the kernels straight into the flat buffer;
+  * no host synchronisation inside the step (losses are returned as device tensors).
+
+Host logic only; every number is produced by libb200caps.so kernels (torch is the allocator / autograd tape).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import engine, ops
+
+
+@dataclass
+class StepArgs:
+    """The flags of main_ucf101.py:283-318 that enter the step."""
+    bv: bool = True
+    gv: bool = False
+    n_frames: int = 5
+    predict_maps: bool = False
+    bv_wt: float = 0.5
+    gv_wt: float = 0.5
+    lower_thresh: Optional[float] = None
+    upper_thresh: Optional[float] = None
+    wt_loc: float = 1.0
+    wt_cls: float = 1.0
+    wt_cons: float = 0.1
+    thresh_epoch: int = 11
+    lr: float = 1e-4
+    rampup_epochs: int = 100      # exp_rampup(N_EPOCHS), main_ucf101.py:419
+
+
+def exp_rampup(rampup_length: int, epoch: float) -> float:
+    if epoch < rampup_length:
+        e = float(np.clip(epoch, 0.0, rampup_length))
+        phase = 1.0 - e / rampup_length
+        return float(np.exp(-5.0 * phase * phase))
+    return 1.0
+
+
+class FlatParams:
+    """Re-homes every parameter of `model` (and its gradient) as a view into one flat fp32 buffer, in
+    registration order.  state_dict keys / shapes are unchanged."""
+
+    def __init__(self, model: torch.nn.Module):
+        params = [p for p in model.parameters()]
+        dev = params[0].device
+        offs, n = [], 0
+        for p in params:
+            n = (n + 3) // 4 * 4          # 16-byte alignment of every tensor
+            offs.append(n)
+            n += p.numel()
+        n = (n + 3) // 4 * 4
+        self.n = n
+        self.data = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets: Dict[str, int] = {}
+        names = {id(p): k for k, p in model.named_parameters()}
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.data[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                self.offsets[names[id(p)]] = o
+        engine.bump_weights_epoch()
+
+    def zero_grad(self):
+        ops.fill_f32(self.grad, 0.0)
+
+
+class TrainStep:
+    def __init__(self, model: torch.nn.Module, args: StepArgs = StepArgs(), process_group=None):
+        self.model = model
+        self.args = args
+        self.flat = FlatParams(model)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        # bucket boundary: encoder (conv1.*) parameters come first in registration order; everything after the
+        # encoder is complete once the capsule head has back-propagated, i.e. before the encoder backward starts.
+        enc_end = 0
+        for k, o in self.flat.offsets.items():
+            if k.startswith("conv1."):
+                enc_end = max(enc_end, o + dict(model.named_parameters())[k].numel())
+        self.enc_end = (enc_end + 3) // 4 * 4
+        self._bucket_event = None
+
+    # ---- multi-GPU: gradient all-reduce overlapped with the encoder backward --------------------------
+    def _allreduce_async(self, lo: int, hi: int):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def __call__(self, data, fl_data, action, seg, labels_host, epoch: int = 1):
+        """data / fl_data (P,3,8,H,W) fp32 CUDA, action (P,1) CUDA, seg (P,1,8,H,W) fp32 CUDA, labels_host: CPU tensor /
+        list with 1 = labeled.  Returns dict of device scalars (total, loc, cls, cons) and the step's outputs."""
+        a, model, flat = self.args, self.model, self.flat
+        engine.require_cuda(data, "data")
+        P = data.shape[0]
+        H, W = data.shape[-2], data.shape[-1]
+        dev = data.device
+        labels_host = torch.as_tensor(labels_host).float().cpu()
+        lab_idx_host = torch.nonzero(labels_host == 1).view(-1).to(torch.int32)
+        n_lab = int(lab_idx_host.numel())
+        lab_idx = lab_idx_host.to(dev, non_blocking=True)
+        labels_dev = labels_host.to(dev, non_blocking=True)
+        wt_ramp = exp_rampup(a.rampup_epochs, epoch)
+
+        model.train()
+        flat.zero_grad()
+        engine.STATE.direct_grads = True
+        engine.STATE.bn_groups = 2
+        try:
+            # both passes as one batch: [clips ; flipped clips]
+            x_cl = torch.empty((2 * P, data.shape[2], H, W, 8), dtype=torch.bfloat16, device=dev)
+            ops.ncdhw_to_cl(data.contiguous(), 8, out=x_cl[:P])
+            ops.ncdhw_to_cl(fl_data.contiguous(), 8, out=x_cl[P:])
+            img = engine.from_cl(x_cl)
+            cls2 = torch.cat([action, action]).to(dev)
+            lab2 = torch.cat([labels_dev, labels_dev])
+            xe, c56, c112, drop2 = model._encode(img)
+            hook = None
+            if self.world > 1:
+                # everything after the encoder (84 % of the parameters, incl. the 138 MB PrimaryCaps weight) is final
+                # when the gradient w.r.t. the encoder output has been formed -> all-reduce it under the encoder bwd
+                hook = xe.register_hook(lambda g: (self._allreduce_async(self.enc_end, flat.n), None)[1])
+            caps, rout = model._capsules(xe)
+            logits, act, feat = model._decode(rout, xe, c56, c112, drop2, cls2, lab2, epoch, a.thresh_epoch)
+        finally:
+            engine.STATE.bn_groups = 1
+
+        # ---- losses + their gradients (device only) -------------------------------------------------
+        out, flp = logits[:P], logits[P:]
+        V = out.numel() // P
+        dlogits = torch.zeros_like(logits)
+        dact = torch.zeros_like(act)
+        seg = seg.contiguous().float()
+        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        l_seg = torch.zeros(2, dtype=torch.float32, device=dev)
+        l_cls = torch.zeros(2, dtype=torch.float32, device=dev)
+        if n_lab > 0:
+            ops.seg_loss_fwd(out, seg, lab_idx, n_lab, V, sums, l_seg)
+            ops.seg_loss_bwd(out, seg, lab_idx, n_lab, V, sums, a.wt_loc, a.wt_loc, dlogits)
+            ops.spread_loss(act, action.to(dev).float().contiguous().view(-1), lab_idx, n_lab, act.shape[1], 0.2, l_cls,
+                            a.wt_cls, dact)
+        m_clk = m_anti = m_gv = None
+        if a.bv:
+            m_clk = torch.empty((P, 8, H, W), dtype=torch.float32, device=dev)
+            m_anti = torch.empty((P, 8, H, W), dtype=torch.float32, device=dev)
+            mm = torch.empty((P, 2), dtype=torch.float32, device=dev)
+            # clock: pred = output, flip_pred = flipT(flipW(flip_op)) ; anticlock: pred = flipT(output), flip_pred = flipW(flip_op)
+            ops.bv_mask(out, flp, m_clk, mm, P, H, W, a.n_frames, a.predict_maps, 0, 1, 1)
+            ops.bv_mask(out, flp, m_anti, mm, P, H, W, a.n_frames, a.predict_maps, 1, 0, 1)
+        if a.gv:
+            m_gv = torch.empty((P, 8, H, W), dtype=torch.float32, device=dev)
+            mm2 = torch.empty((P, 2), dtype=torch.float32, device=dev)
+            ops.gv_mask(out, m_gv, mm2, P, H, W, a.lower_thresh, a.upper_thresh)
+        acc = torch.empty(4, dtype=torch.float64, device=dev)
+        l_cons = torch.empty(4, dtype=torch.float32, device=dev)
+        mode = (1 if a.bv else 0) | (2 if a.gv else 0)
+        ops.cons_reduce(out, flp, m_clk, m_anti, m_gv, acc, P, H, W, 1, 1)
+        ops.cons_finish(acc, l_cons, P, H, W, mode, wt_ramp, a.bv_wt, a.gv_wt)
+        if mode == 3:
+            a_l2, a_lv, a_lg = a.bv_wt * (1 - wt_ramp), a.bv_wt * wt_ramp, a.gv_wt
+        elif mode == 2:
+            a_l2, a_lv, a_lg = 0.0, 0.0, 1.0
+        elif mode == 1:
+            a_l2, a_lv, a_lg = 1 - wt_ramp, wt_ramp, 0.0
+        else:
+            a_l2, a_lv, a_lg = 1.0, 0.0, 0.0
+        ops.cons_grad(out, flp, m_clk, m_anti, m_gv, dlogits[:P], dlogits[P:], P, H, W, 1, 1, a_l2 * a.wt_cons,
+                      a_lv * a.wt_cons, a_lg * a.wt_cons)
+
+        # ---- backward + optimiser ----------------------------------------------------------------------
+        try:
+            torch.autograd.backward([logits, act], [dlogits, dact])
+        finally:
+            engine.STATE.direct_grads = False
+            if hook is not None:
+                hook.remove()
+        if self.world > 1:
+            self._allreduce_async(0, self.enc_end)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.step_count += 1
+        ops.adam_step(flat.data, flat.grad, flat.m, flat.v, flat.n, a.lr, 0.9, 0.999, 1e-6, self.step_count,
+                      1.0 / self.world)
+        engine.bump_weights_epoch()
+        loc = l_seg[0] + l_seg[1]
+        total = a.wt_loc * loc + a.wt_cls * l_cls[0] + a.wt_cons * l_cons[0]
+        return dict(total=total, loc=loc, bce=l_seg[0], dice=l_seg[1], cls=l_cls[0], cons=l_cons[0], l2=l_cons[1],
+                    output=out, flip_op=flp, pred_action=act[:P], feat=feat[:P])

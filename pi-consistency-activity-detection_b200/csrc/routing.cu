@@ -474,6 +474,46 @@ __global__ void caps_head_bwd_kernel(const bf16* __restrict__ dx, const float* _
   }
 }
 
+// PrimaryCaps backward prologue: g fp32 (rows, 544) is the gradient w.r.t. [poses | sigmoid(act)];
+// dz = g * (col >= 512 ? a (1 - a) : 1) as bf16 rows for the dgrad / wgrad GEMMs, dbias[col] += sum_rows dz.
+__global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* __restrict__ g, const float* __restrict__ out,
+                                                                   bf16* __restrict__ dz, float* __restrict__ dbias, long long rows) {
+  // block = 256 threads: 4 row lanes x 68 column groups of 8 (544 = 68 * 8); threads >= 272 idle
+  const int cg = threadIdx.x % 68, rl = threadIdx.x / 68;
+  const bool act = rl < 3;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (act) {
+    for (long long r = (long long)blockIdx.x * 3 + rl; r < rows; r += (long long)gridDim.x * 3) {
+      const float* gp = g + r * 544 + cg * 8;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gp[j];
+      if (cg >= 64) {
+        const float* op = out + r * 544 + cg * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = op[j];
+          v[j] *= a * (1.f - a);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      *reinterpret_cast<uint4*>(dz + r * 544 + cg * 8) = pack8(v);
+    }
+  }
+  __shared__ float sh[544];
+  for (int i = threadIdx.x; i < 544; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cg * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 544; i += blockDim.x) atomicAdd(&dbias[i], sh[i]);
+}
+
 }  // namespace
 
 B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, int64_t b,
@@ -546,5 +586,16 @@ B2C_API int b2c_caps_head_bwd(const void* dx, const float* mask, const float* da
   caps_head_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>((const bf16*)dx, mask, dact, dfeat, drout, L, C, rows);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("caps_head_bwd");
+  return 0;
+}
+
+B2C_API int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, b2c_stream_t s) {
+  B2C_REQUIRE(g && out && dz && dbias && rows > 0, "primarycaps_bwd_prep: bad args");
+  long long blocks = (rows + 2) / 3;
+  const long long cap = (long long)b2c_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  primarycaps_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("primarycaps_bwd_prep");
   return 0;
 }

@@ -166,30 +166,33 @@ class CapsNet(nn.Module):
         pose_range = num_imgcaps * self.P * self.P
         return torch.cat((imgcaps[:, :, :, :pose_range], imgcaps[:, :, :, pose_range:pose_range + num_imgcaps]), dim=-1)
 
-    def forward(self, img, classification, concat_labels, epoch, thresh_ep):
-        '''
-        img (B,3,T,H,W); classification (B,1) ground-truth class (pose masking of labeled clips);
-        concat_labels (B,) 1 = labeled, 0 = unlabeled.
-        Returns (mask logits (B,1,8,224,224) fp32, class activations (B,C) fp32, per-location activations (B,400,C) fp32).
-        '''
-        engine.require_cuda(img, "img")
-        C = self.NUM_CLASSES
+    # The forward pass in three segments (tests drive them separately: the EM routing in the middle is
+    # chaotically sensitive at random init, so parity is established per segment).
+    def _encode(self, img):
+        """I3D trunk + Dropout3d -> (x (N,1,28,28,832) bf16 CL, cross56 CL, cross112 CL, decoder dropout scale)."""
         x, cross56, cross112 = self.conv1(img)
         x_cl = engine.to_cl(x)
-        N = x_cl.shape[0]
-        dev = x_cl.device
+        N, dev = x_cl.shape[0], x_cl.device
         drop2 = None
         if self.training:
             # nn.Dropout3d(0.5): one Bernoulli per (sample, channel) (reference :428, :507)
             x_cl = engine.ChannelScaleFn.apply(x_cl, engine.dropout_scale(N, 832, dev))
             drop2 = engine.dropout_scale(N, 128, dev)
-        caps = engine.PrimaryCapsFn.apply(x_cl, self.primary_caps.pose.weight, self.primary_caps.pose.bias,
-                                          self.primary_caps.a.weight, self.primary_caps.a.bias, self.primary_caps)[:, 0]
+        return x_cl, engine.to_cl(cross56), engine.to_cl(cross112), drop2
+
+    def _capsules(self, x_cl):
+        """PrimaryCaps GEMM -> (N,20,20,544) fp32 ; EM routing -> (N,20,20,C*17) fp32 [mu | a]."""
+        pc = self.primary_caps
+        caps = engine.PrimaryCapsFn.apply(x_cl, pc.pose.weight, pc.pose.bias, pc.a.weight, pc.a.bias, pc)[:, 0]
         rout = engine.EMRoutingFn.apply(caps, self.conv_caps.weights, self.conv_caps.beta_u, self.conv_caps.beta_a)
-        h, w = rout.shape[1], rout.shape[2]
+        return caps, rout
+
+    def _decode(self, rout, x_cl, c56, c112, drop2, classification, concat_labels, epoch, thresh_ep):
+        C = self.NUM_CLASSES
+        N, h, w = rout.shape[0], rout.shape[1], rout.shape[2]
+        dev = rout.device
         actor_prediction = engine.ClassActFn.apply(rout)
         feat_shape = rout[..., C * 16:].reshape(N, h * w, C)
-
         # pose mask (reference :455-479), built on the device without host round trips
         with torch.no_grad():
             if self.training:
@@ -203,10 +206,20 @@ class CapsNet(nn.Module):
             else:
                 mask = F.one_hot(torch.argmax(actor_prediction, dim=1), C).float().contiguous()
         x0 = engine.CapsHeadFn.apply(rout, mask)
-
         params = []
         for n in engine.DecoderFn.ORDER:
             m = getattr(self, n)
             params += [m.weight, m.bias]
-        out_1 = engine.DecoderFn.apply(x0, x_cl, engine.to_cl(cross56), engine.to_cl(cross112), drop2, self, *params)
+        out_1 = engine.DecoderFn.apply(x0, x_cl, c56, c112, drop2, self, *params)
         return out_1, actor_prediction, feat_shape
+
+    def forward(self, img, classification, concat_labels, epoch, thresh_ep):
+        '''
+        img (B,3,T,H,W); classification (B,1) ground-truth class (pose masking of labeled clips);
+        concat_labels (B,) 1 = labeled, 0 = unlabeled.
+        Returns (mask logits (B,1,8,224,224) fp32, class activations (B,C) fp32, per-location activations (B,400,C) fp32).
+        '''
+        engine.require_cuda(img, "img")
+        x_cl, c56, c112, drop2 = self._encode(img)
+        caps, rout = self._capsules(x_cl)
+        return self._decode(rout, x_cl, c56, c112, drop2, classification, concat_labels, epoch, thresh_ep)

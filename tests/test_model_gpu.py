@@ -51,58 +51,130 @@ def test_eval_forward_matches_reference_golden(setup):
     assert float((vals - ref).abs().max()) / gold["logits"]["maxabs"] < 2e-2
 
 
-def test_train_forward_and_grads_match_oracle(setup):
-    """bf16 mode: logits / activations / per-tensor gradients within 2e-2 (max-abs, normalised) of the fp64 oracle;
-    thresholded masks and argmax identical outside the stated margin."""
+def _cl2ncdhw(t):
+    return t.detach().float().permute(0, 4, 1, 2, 3).double().cpu()
+
+
+def test_train_mode_segment_parity(setup):
+    """Train mode (batch-stat BN, injected Dropout3d masks), bf16 mode, against the fp64 oracle.
+
+    The EM routing is chaotically sensitive at random init: bf16 rounding upstream moves the logits by O(1) in the
+    REFERENCE ITSELF (oracle with emulated bf16 roundings vs exact: logits 0.59, feat 0.36).  Parity
+    is therefore asserted per segment with the routing teacher-forced, within the bf16 tolerance of north_star
+    (2e-2 max-abs normalised); the end-to-end deviation is measured and printed next to the oracle's own."""
     s = setup
     model, sd, b, masks, engine, restate = s["model"], s["sd"], s["batch"], s["masks"], s["engine"], s["restate"]
     model.train()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     for p in model.parameters():
         p.grad = None
-    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-    _inject(engine, masks[:2])
-    try:
-        out, act, feat = model(b["data"].cuda(), b["action"].cuda(), b["labels"].cuda(), 1, 11)
-    finally:
-        engine.STATE.dropout_source = None
-    # oracle fp64 with autograd
     sd64 = {k: (v.double().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v)
             for k, v in sd.items()}
+    m64 = [m.double() for m in masks]
+    img = b["data"].cuda()
+
+    # ---- segment 1: encoder ------------------------------------------------------------------------
+    _inject(engine, masks[:2])
+    try:
+        x_cl, c56, c112, drop2 = model._encode(img)
+    finally:
+        engine.STATE.dropout_source = None
     bn = restate.BNState(True)
-    o_ref, a_ref, f_ref = restate.capsnet_forward(sd64, b["data"].double(), b["action"], b["labels"], 1, 11, True,
-                                                  [m.double() for m in masks[:2]], bn)
-    e_logits, e_act, e_feat = rel(out, o_ref.detach()), rel(act, a_ref.detach()), rel(feat, f_ref.detach())
-    print(f"train fwd: logits {e_logits:.2e} act {e_act:.2e} feat {e_feat:.2e}")
-    assert e_logits < 2e-2 and e_act < 2e-2 and e_feat < 5e-2
-    # thresholded masks: bit-exact where the oracle margin exceeds the tolerance
+    x_ref, c56_ref, c112_ref = restate.encode(sd64, b["data"].double(), m64[0], bn)
+    e = dict(x=rel(_cl2ncdhw(x_cl)[:, :, 0], x_ref.detach()), c56=rel(_cl2ncdhw(c56), c56_ref.detach()),
+             c112=rel(_cl2ncdhw(c112), c112_ref.detach()))
+    print("encoder:", e)
+    assert max(e.values()) < 2e-2, e
+    new_sd = model.state_dict()
+    worst = max(max(rel(new_sd[p + ".bn.running_mean"], rm), rel(new_sd[p + ".bn.running_var"], rv))
+                for p, (rm, rv) in bn.updates.items())
+    assert worst < 1e-2, worst
+    # encoder gradients through a linear probe of the three taps
+    g = torch.Generator().manual_seed(9)
+    w1 = torch.randn(x_ref.shape, generator=g, dtype=torch.float64)
+    w2 = torch.randn(c56_ref.shape, generator=g, dtype=torch.float64) * 0.2
+    w3 = torch.randn(c112_ref.shape, generator=g, dtype=torch.float64) * 0.05
+    enc_names = [k for k in sd64 if k.startswith("conv1.") and sd64[k].requires_grad]
+    gref = torch.autograd.grad((x_ref * w1).sum() + (c56_ref * w2).sum() + (c112_ref * w3).sum(), [sd64[k] for k in enc_names])
+    to_cl_w = lambda w: w.permute(0, 2, 3, 4, 1).float().cuda()
+    probe = (x_cl.float() * to_cl_w(w1.unsqueeze(2))).sum() + (c56.float() * to_cl_w(w2)).sum() + (c112.float() * to_cl_w(w3)).sum()
+    probe.backward()
+    gp = dict(model.named_parameters())
+    errs = {k: rel(gp[k].grad, gr) for k, gr in zip(enc_names, gref)}
+    worst_k = max(errs, key=errs.get)
+    print(f"encoder grads: worst {worst_k} {errs[worst_k]:.2e}; median {sorted(errs.values())[len(errs) // 2]:.2e}")
+    assert errs[worst_k] < 5e-2, (worst_k, errs[worst_k])
+    for p in model.parameters():
+        p.grad = None
+
+    # ---- segment 2: PrimaryCaps (linear) + routing (teacher-forced on OUR capsules) ---------------------
+    x_leaf = x_cl.detach().requires_grad_(True)
+    caps, rout = model._capsules(x_leaf)
+    x_in = _cl2ncdhw(x_cl)[:, :, 0].requires_grad_(True)
+    caps_ref = restate.primary_caps(x_in, sd64)
+    e_caps = rel(caps, caps_ref.detach())
+    print(f"primary caps (same input): {e_caps:.2e}")
+    assert e_caps < 1e-2
+    wc = torch.randn(caps_ref.shape, generator=g, dtype=torch.float64)
+    pc_names = [k for k in sd64 if k.startswith("primary_caps.")]
+    gref = torch.autograd.grad((caps_ref * wc).sum(), [sd64[k] for k in pc_names] + [x_in])
+    (caps * wc.float().cuda()).sum().backward(retain_graph=True)
+    for k, gr in zip(pc_names, gref[:-1]):
+        assert rel(gp[k].grad, gr) < 2e-2, (k, rel(gp[k].grad, gr))
+    assert rel(_cl2ncdhw(x_leaf.grad)[:, :, 0], gref[-1]) < 2e-2
+    for p in model.parameters():
+        p.grad = None
+    caps_d = caps.detach().double().cpu()
+    mu_tf, a_tf = restate.em_routing(caps_d[..., :512].reshape(800, 32, 16), caps_d[..., 512:].reshape(800, 32),
+                                     sd64["conv_caps.weights"][0].detach(), sd64["conv_caps.beta_u"].detach(),
+                                     sd64["conv_caps.beta_a"].detach())
+    e_mu = rel(rout[..., :384].reshape(800, 24, 16), mu_tf)
+    e_a = rel(rout[..., 384:].reshape(800, 24), a_tf)
+    print(f"routing (teacher-forced): mu {e_mu:.2e} a {e_a:.2e}")
+    assert e_mu < 1e-3 and e_a < 1e-3
+
+    # ---- segment 3: class activations, pose mask, decoder (teacher-forced on OUR routing output) -------
+    rout_leaf = rout.detach().requires_grad_(True)
+    out, act, feat = model._decode(rout_leaf, x_cl.detach(), c56.detach(), c112.detach(), drop2, b["action"].cuda(),
+                                   b["labels"].cuda(), 1, 11)
+    rout_in = rout.detach().double().cpu().requires_grad_(True)
+    o_ref, a_ref, f_ref = restate.decode(sd64, rout_in, _cl2ncdhw(x_cl)[:, :, 0], _cl2ncdhw(c56), _cl2ncdhw(c112),
+                                         b["action"], b["labels"], 1, 11, True, m64[1])
+    e = dict(logits=rel(out, o_ref.detach()), act=rel(act, a_ref.detach()), feat=rel(feat, f_ref.detach()))
+    print("decoder:", e)
+    assert e["logits"] < 2e-2 and e["act"] < 1e-5 and e["feat"] < 1e-6, e
     tol = 2e-2 * float(o_ref.abs().max())
     safe = o_ref.detach().abs() > tol
     agree = ((out.cpu() > 0) == (o_ref.detach() > 0)) | ~safe
-    assert bool(agree.all()), f"{int((~agree).sum())} mask flips outside the margin; excluded {int((~safe).sum())}"
-    # BN running statistics
-    new_sd = model.state_dict()
-    worst = 0.0
-    for p, (rm, rv) in bn.updates.items():
-        worst = max(worst, rel(new_sd[p + ".bn.running_mean"], rm), rel(new_sd[p + ".bn.running_var"], rv))
-    assert worst < 2e-2, worst
-    # gradients of a scalar that touches all three outputs
-    g = torch.Generator().manual_seed(9)
-    w_o = torch.randn(out.shape, generator=g) / out.numel() ** 0.5
-    w_a = torch.randn(act.shape, generator=g)
-    w_f = torch.randn(feat.shape, generator=g) / 400
-    loss = (out * w_o.cuda()).sum() + (act * w_a.cuda()).sum() + (feat * w_f.cuda()).sum()
-    loss.backward()
-    loss_ref = (o_ref * w_o.double()).sum() + (a_ref * w_a.double()).sum() + (f_ref * w_f.double()).sum()
-    names = [k for k, v in sd64.items() if v.requires_grad]
-    grads_ref = torch.autograd.grad(loss_ref, [sd64[k] for k in names])
-    gp = dict(model.named_parameters())
-    bad = []
-    worst = 0.0
-    for k, gr in zip(names, grads_ref):
-        e = rel(gp[k].grad, gr)
-        worst = max(worst, e)
-        if e > 5e-2:
-            bad.append((k, e))
-    print(f"worst per-tensor gradient error {worst:.2e}")
-    assert not bad, bad[:10]
+    print(f"thresholded masks: {int((~safe).sum())} of {safe.numel()} pixels inside the margin (excluded)")
+    assert bool(agree.all()), f"{int((~agree).sum())} mask flips outside the margin"
+    assert act.argmax(1).tolist() == a_ref.argmax(1).tolist()
+    w_o = torch.randn(out.shape, generator=g, dtype=torch.float64) / out.numel() ** 0.5
+    w_a = torch.randn(act.shape, generator=g, dtype=torch.float64)
+    w_f = torch.randn(feat.shape, generator=g, dtype=torch.float64) / 400
+    dec_names = [k for k in sd64 if sd64[k].requires_grad and not k.startswith(("conv1.", "primary_caps.", "conv_caps."))]
+    gref = torch.autograd.grad((o_ref * w_o).sum() + (a_ref * w_a).sum() + (f_ref * w_f).sum(),
+                               [sd64[k] for k in dec_names] + [rout_in])
+    ((out * w_o.float().cuda()).sum() + (act * w_a.float().cuda()).sum() + (feat * w_f.float().cuda()).sum()).backward()
+    errs = {k: rel(gp[k].grad, gr) for k, gr in zip(dec_names, gref[:-1])}
+    errs["rout"] = rel(rout_leaf.grad, gref[-1])
+    print("decoder grads:", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < 3e-2, errs
+
+    # ---- end to end, reported (not asserted at 2e-2: see docstring) -----------------------------------
+    model.load_state_dict(sd0)
+    _inject(engine, masks[:2])
+    try:
+        with torch.no_grad():
+            out, act, feat = model(img, b["action"].cuda(), b["labels"].cuda(), 1, 11)
+    finally:
+        engine.STATE.dropout_source = None
+    with torch.no_grad():
+        sdd = {k: v.detach() for k, v in sd64.items()}
+        o_ex, a_ex, f_ex = restate.capsnet_forward(sdd, b["data"].double(), b["action"], b["labels"], 1, 11, True, m64[:2])
+        with restate.emulate_bf16():
+            o_em, a_em, f_em = restate.capsnet_forward(sdd, b["data"].double(), b["action"], b["labels"], 1, 11, True, m64[:2])
+    print("END-TO-END vs exact fp64 oracle : logits %.2e act %.2e feat %.2e" % (rel(out, o_ex), rel(act, a_ex), rel(feat, f_ex)))
+    print("oracle(bf16 roundings) vs exact : logits %.2e act %.2e feat %.2e" % (rel(o_em, o_ex), rel(a_em, a_ex), rel(f_em, f_ex)))
+    assert rel(act, a_ex) < 5e-2 and torch.isfinite(out).all()
     model.load_state_dict(sd0)
