@@ -243,13 +243,17 @@ def run_ours(args):
                     "algorithmic_flop_per_step": FLOP_PER_CLIP * P}
         if world == 1:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            agg = {}
+            agg, kinds = {}, {}
             for tag, a, b in recs:
                 d = agg.setdefault(tag, [0, 0.0])
                 d[0] += 1
                 d[1] += a.elapsed_time(b)
+                k = kinds.setdefault(tag.split(" ")[0], [0, 0.0])
+                k[0] += 1
+                k[1] += a.elapsed_time(b)
+            top = sorted(agg.items(), key=lambda kv: -kv[1][1])
             with open(os.path.join(ROOT, "gpurun_out", "igemm_kernel_times.json"), "w") as f:
-                json.dump({"ms_per_step_total": t_ms, "by_kind": agg}, f, indent=1)
+                json.dump({"ms_per_step_total": t_ms, "by_kind": kinds, "by_layer_sorted": top}, f, indent=1)
     if world > 1:
         dist.barrier()
 

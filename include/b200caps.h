@@ -37,12 +37,12 @@ long long b2c_launch_count(void);
  * :490,:497,:501), stride-1 dgrad (flipped taps), ConvTranspose fprop by output-parity class
  * (capsules_ucf101.py:486,495,499,504,509), strided-conv dgrad and ConvTranspose dgrad.
  * taps: int32 per tap, signed bytes (dt | dh<<8 | dw<<16).
- * weights: bf16 [Cout][ntaps*Cin] (K-major), produced by b2c_pack_weights.
+ * weights: bf16 tiles produced by b2c_pack_weights with the same bn_tile (pre-swizzled smem image).
  * Requirements: Cin % 8 == 0, Cout % 8 == 0, channel offsets % 8 == 0, row strides % 8 == 0.
  * ---------------------------------------------------------------------------------- */
 typedef struct {
   const int32_t* taps; /* [ntaps] */
-  const void* w;       /* bf16 [Cout][ntaps*Cin] */
+  const void* w;       /* packed bf16 tiles (b2c_pack_weights) */
   int32_t ntaps;
   int32_t Qt, Qh, Qw;       /* GEMM-M grid of this class */
   int32_t po_t, po_h, po_w; /* output offset of this class */
@@ -62,7 +62,7 @@ typedef struct {
   int32_t relu;         /* apply ReLU */
   int32_t sigmoid_from; /* apply sigmoid to output channels >= this (PrimaryCaps 'a'), <0: none */
   int32_t accumulate;   /* out += result (gradient accumulation) */
-  int32_t bn_tile;      /* output-channel tile per CTA; 0 = auto */
+  int32_t bn_tile;      /* output-channel tile per CTA: must equal the bn_tile the weights were packed with */
   int32_t nclass;
   b2c_conv_class cls[8];
 } b2c_conv_desc;
@@ -93,12 +93,15 @@ typedef struct {
 
 int b2c_conv_wgrad(const b2c_wgrad_desc* desc_host, b2c_stream_t stream);
 
-/* packed[r*row_pitch + t*tap_pitch + col_off + c] = (c < C_real) ? bf16(w[r*s_r + c*s_c + wtap[t]]) : 0
- * r<R, t<ntaps, c<C.  (row_pitch = ntaps*C, tap_pitch = C, col_off = 0 for a stand-alone layer; other
- * values place sibling layers side by side in one fused GEMM operand.) */
+/* fp32 master weights -> bf16 GEMM operand in the fprop kernel's shared-memory image:
+ *   tiles [n-tile][k-block][bn_tile rows][64 K-elements], 128-byte swizzle pre-applied, so each pipeline stage
+ *   fetches its weight tile with ONE bulk copy.  Element (r, t, c), r<R, t<ntaps, c<C:
+ *     value = (c < C_real) ? bf16(w[r*s_r + c*s_c + wtap[t]]) : 0 ; GEMM row = r + r_off ; k = t*tap_pitch + col_off + c.
+ *   (tap_pitch = C, col_off = r_off = 0 for a stand-alone layer; other values place sibling layers side by side in
+ *   one fused GEMM operand.)  `packed` must be zero-initialised, size ceil(rows/bn_tile)*nkb*bn_tile*64 elements. */
 int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, int32_t R, int32_t ntaps, int32_t C,
-                     int32_t C_real, int64_t s_r, int64_t s_c, int64_t row_pitch, int64_t tap_pitch, int64_t col_off,
-                     b2c_stream_t stream);
+                     int32_t C_real, int64_t s_r, int64_t s_c, int64_t tap_pitch, int64_t col_off, int32_t r_off,
+                     int32_t bn_tile, int32_t nkb, b2c_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Bandwidth kernels (channels-last bf16 views: ptr, rows, C, row_stride, c_off)

@@ -44,7 +44,7 @@ class WgradDesc(C.Structure):
 _SIGS = {
     "b2c_conv_fprop": [C.POINTER(ConvDesc), vp],
     "b2c_conv_wgrad": [C.POINTER(WgradDesc), vp],
-    "b2c_pack_weights": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, vp],
+    "b2c_pack_weights": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, i32, i32, vp],
     "b2c_ncdhw_to_ndhwc": [vp, vp, i32, i32, i64, i32, vp],
     "b2c_ndhwc_to_ncdhw_f32": [vp, i64, i32, vp, i32, i32, i64, vp],
     "b2c_bn_sums": [vp, i64, i32, i64, i32, i32, vp, vp],

@@ -396,22 +396,25 @@ class FusedConvLayer:
         spec = pl.spec
         T = spec.k[0] * spec.k[1] * spec.k[2]
         dev = self.weights[0].device
+        from .plans import packed_geometry
         if which == "fprop":
             cl = pl.fprop[0]
-            K = len(cl.taps) * spec.Cin_pad
+            nt = len(cl.taps)
+            bn, _, nkb, elems = packed_geometry(spec.Cout_pad, nt * spec.Cin_pad)
             if cl.packed is None:
-                cl.packed = torch.zeros((spec.Cout_pad, K), dtype=torch.bfloat16, device=dev)
+                cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=dev)
             for w, co, off in zip(self.weights, self.couts, self.offs):
-                ops.pack_part(w.detach(), cl.packed[off:], cl.wtap_dev, co, len(cl.taps), spec.Cin_pad, spec.Cin,
-                              spec.Cin * T, T)
+                ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, co, nt, spec.Cin_pad, spec.Cin, spec.Cin * T, T,
+                              spec.Cin_pad, 0, off, bn, nkb)
         else:
             for cl in pl.dgrad:
                 nt = len(cl.taps)
+                bn, _, nkb, elems = packed_geometry(spec.Cin_pad, nt * spec.Cout_pad)
                 if cl.packed is None:
-                    cl.packed = torch.zeros((spec.Cin_pad, nt * spec.Cout_pad), dtype=torch.bfloat16, device=dev)
+                    cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=dev)
                 for w, co, off in zip(self.weights, self.couts, self.offs):
                     ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, spec.Cin, nt, co, co, T, spec.Cin * T,
-                                  nt * spec.Cout_pad, spec.Cout_pad, off)
+                                  spec.Cout_pad, off, 0, bn, nkb)
         self.keys[(tuple(in_dims), which)] = key
         return pl
 

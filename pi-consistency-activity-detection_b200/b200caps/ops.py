@@ -42,17 +42,19 @@ def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=Non
                sigmoid_from=-1, accumulate=False, bn_tile=0):
     """out: View (bf16 / fp32 rows) or a 2-D fp32 tensor (Cout_pad, rows) for the planar epilogue."""
     d = fill_conv_desc(plan, which, x, out, bias, scale_nc, relu, sigmoid_from, accumulate, bn_tile)
-    _launch(which, "b2c_conv_fprop", d)
+    _launch(f"{which} {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
+            f"{' T' if plan.spec.transposed else ''}", "b2c_conv_fprop", d)
 
 
 def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None):
     d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part)
-    _launch("wgrad", "b2c_conv_wgrad", d)
+    _launch(f"wgrad {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
+            f"{' T' if plan.spec.transposed else ''}", "b2c_conv_wgrad", d)
 
 
-def pack_part(weight, packed, wtap_dev, R, ntaps, C, C_real, s_r, s_c, row_pitch=0, tap_pitch=0, col_off=0):
-    _abi.call("b2c_pack_weights", _p(weight), _p(packed), _p(wtap_dev), R, ntaps, C, C_real, s_r, s_c, row_pitch, tap_pitch,
-              col_off, stream())
+def pack_part(weight, packed, wtap_dev, R, ntaps, C, C_real, s_r, s_c, tap_pitch, col_off, r_off, bn_tile, nkb):
+    _abi.call("b2c_pack_weights", _p(weight), _p(packed), _p(wtap_dev), R, ntaps, C, C_real, s_r, s_c, tap_pitch, col_off,
+              r_off, bn_tile, nkb, stream())
 
 
 # ---- layout ---------------------------------------------------------------------------------

@@ -22,6 +22,22 @@ import torch
 from . import _abi
 
 
+def pick_bn_tile(cout: int) -> int:
+    """Output-channel tile per CTA (UMMA N): the whole Cout when <= 256, else an even split (multiple of 16)."""
+    if cout <= 256:
+        return (cout + 15) // 16 * 16
+    nt = (cout + 255) // 256
+    return ((cout + nt - 1) // nt + 15) // 16 * 16
+
+
+def packed_geometry(rows_pad: int, K: int):
+    """(bn_tile, n_tiles, nkb, elements) of the pre-swizzled weight operand."""
+    bn = pick_bn_tile(rows_pad)
+    nt = (rows_pad + bn - 1) // bn
+    nkb = (K + 63) // 64
+    return bn, nt, nkb, nt * nkb * bn * 64
+
+
 def _tap_word(dt: int, dh: int, dw: int) -> int:
     for v in (dt, dh, dw):
         assert -128 <= v <= 127
@@ -184,16 +200,17 @@ class ConvPlan:
         return self
 
     def pack(self, weight: torch.Tensor, which: str, stream_ptr: int):
-        """(Re)build the packed bf16 weights of the fprop or dgrad classes from the fp32 master."""
+        """(Re)build the packed bf16 weight tiles of the fprop or dgrad classes from the fp32 master."""
         assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.is_cuda
         classes = self.fprop if which == "fprop" else self.dgrad
         pk = self.fprop_pack if which == "fprop" else self.dgrad_pack
         for cl in classes:
             nt = len(cl.taps)
+            bn, ntile, nkb, elems = packed_geometry(pk["R_pad"], nt * pk["C"])
             if cl.packed is None:
-                cl.packed = torch.zeros((pk["R_pad"], nt * pk["C"]), dtype=torch.bfloat16, device=weight.device)
+                cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=weight.device)
             _abi.call("b2c_pack_weights", weight.data_ptr(), cl.packed.data_ptr(), cl.wtap_dev.data_ptr(), pk["R"], nt,
-                      pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], 0, 0, 0, stream_ptr)
+                      pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], pk["C"], 0, 0, bn, nkb, stream_ptr)
 
 
 @dataclass
@@ -260,7 +277,8 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
         assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (pk["R_pad"], rows)
         d.out, d.out_row_stride, d.out_c_off = out.data_ptr(), rows, 0
         d.out_fp32 = 2
-    d.relu, d.sigmoid_from, d.accumulate, d.bn_tile = int(relu), int(sigmoid_from), int(accumulate), int(bn_tile)
+    assert bn_tile in (0, pick_bn_tile(pk["R_pad"])), "bn_tile is fixed by the packed weight layout"
+    d.relu, d.sigmoid_from, d.accumulate, d.bn_tile = int(relu), int(sigmoid_from), int(accumulate), pick_bn_tile(pk["R_pad"])
     d.nclass = len(classes)
     assert 1 <= d.nclass <= 8
     for i, cl in enumerate(classes):

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_cons
   for (int i = tid; i < cc.ntaps; i += kThreads) s_taps[i] = cc.taps[i];
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&ps->full[s], 128);
+      mbar_init(&ps->full[s], 128 + 1);   // 128 gather threads + the thread that arms the weight bulk copy
       mbar_init(&ps->empty[s], 1);
     }
     mbar_init(&ps->accum, 1);
@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_cons
     }
     const int it0 = qt * d.si_t, ih0 = qh * d.si_h, iw0 = qw * d.si_w;
     const bf16* in_n = reinterpret_cast<const bf16*>(d.in) + d.in_c_off;
-    const bf16* wbase = reinterpret_cast<const bf16*>(cc.w);
     const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     const uint32_t swz = (uint32_t)(r & 7);
 
@@ -142,18 +141,11 @@ __global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_cons
           load_tap(tap);
         }
       }
-      // B: rows rr = r, r+128 of the weight tile
-      const int k0 = kb * kBlockK;
-      for (int rr = r; rr < bn16; rr += 128) {
-        const bool rvalid = (n0 + rr) < d.Cout;
-        const bf16* wrow = wbase + (long long)(n0 + rr) * K + k0;
-        const uint32_t brow = b_st + (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128);
-        const uint32_t sw = (uint32_t)(rr & 7);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool ok = rvalid && (k0 + j * 8) < K;
-          cp_async16(brow + (((uint32_t)j ^ sw) << 4), ok ? (const void*)(wrow + j * 8) : (const void*)cc.w, ok ? 16u : 0u);
-        }
+      // B: the weight tile of this (n-tile, k-block) is stored pre-swizzled and contiguous -> one bulk copy
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)b_tile_bytes);
+        bulk_g2s(b_st, reinterpret_cast<const uint8_t*>(cc.w) + ((size_t)blockIdx.y * nkb + kb) * (size_t)b_tile_bytes,
+                 (uint32_t)b_tile_bytes, &ps->full[stage]);
       }
       cp_async_commit();
       // signal the stage issued `lag` iterations ago
@@ -187,12 +179,15 @@ __global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_cons
              (qw * d.so_w + cc.po_w);
     const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
     const float* scale_row = d.scale_nc ? d.scale_nc + (long long)n_i * d.Cout : nullptr;
-    for (int c0 = 0; c0 < bn16; c0 += 16) {
-      float v[16];
-      tmem_ld16(t_lane + (uint32_t)c0, v);
+    for (int c0 = 0; c0 < bn16; c0 += 32) {
+      float v[32];
+      const int nh = (bn16 - c0 >= 32) ? 4 : 2;
+      if (nh == 4) tmem_ld32(t_lane + (uint32_t)c0, v);
+      else tmem_ld16(t_lane + (uint32_t)c0, v);
       if (!mvalid) continue;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 4; ++h) {
+        if (h >= nh) break;
         const int col = n0 + c0 + h * 8;
         if (col >= d.Cout) break;
         float* vv = v + h * 8;
@@ -349,22 +344,23 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
     const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     const uint32_t swz = (uint32_t)(r & 7);
 
+    // position cursor of this thread's row; advanced by 64 positions per stage without divisions
+    const long long pos0 = kb_lo * kBlockK + r;
+    int n_i, qt, qh, qw;
+    {
+      long long t = pos0;
+      qw = (int)(t % d.Qw); t /= d.Qw;
+      qh = (int)(t % d.Qh); t /= d.Qh;
+      qt = (int)(t % d.Qt); t /= d.Qt;
+      n_i = (int)t;
+    }
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < nkb; ++i) {
       mbar_wait(&ps->empty[stage], phase ^ 1, 11);
       const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
       const uint32_t b_st = a_st + kATileBytes;
-      const long long pos = (kb_lo + i) * kBlockK + r;
-      const bool pvalid = pos < Mtot;
-      int n_i = 0, qt = 0, qh = 0, qw = 0;
-      if (pvalid) {
-        long long t = pos;
-        qw = (int)(t % d.Qw); t /= d.Qw;
-        qh = (int)(t % d.Qh); t /= d.Qh;
-        qt = (int)(t % d.Qt); t /= d.Qt;
-        n_i = (int)t;
-      }
+      const bool pvalid = (pos0 + (long long)i * kBlockK) < Mtot;
       const int gt0 = qt * d.sg_t, gh0 = qh * d.sg_h, gw0 = qw * d.sg_w;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -391,6 +387,17 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
         cp_async16(dst, ok ? (const void*)(prow + ch * 8) : d.p, ok ? 16u : 0u);
       }
       cp_async_commit();
+      qw += kBlockK;
+      while (qw >= d.Qw) {
+        qw -= d.Qw;
+        if (++qh == d.Qh) {
+          qh = 0;
+          if (++qt == d.Qt) {
+            qt = 0;
+            ++n_i;
+          }
+        }
+      }
       if (i >= lag) {
         cp_async_wait_dyn(lag);
         fence_proxy_async_smem();
@@ -424,12 +431,15 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
       base = (long long)gc * d.s_g + __ldg(d.wtap + tp);
     }
     const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < bn16; c0 += 16) {
-      float v[16];
-      tmem_ld16(t_lane + (uint32_t)c0, v);
+    for (int c0 = 0; c0 < bn16; c0 += 32) {
+      float v[32];
+      const int nc = (bn16 - c0 >= 32) ? 32 : 16;
+      if (nc == 32) tmem_ld32(t_lane + (uint32_t)c0, v);
+      else tmem_ld16(t_lane + (uint32_t)c0, v);
       if (!rvalid) continue;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 32; ++i) {
+        if (i >= nc) break;
         const int pc = n0 + c0 + i;
         if (pc < d.Cp_real) {
           float* dst = d.dw + base + (long long)pc * d.s_p;
@@ -475,10 +485,14 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------
+// fp32 master weights -> bf16 GEMM operand tiles in exactly the shared-memory image the fprop kernel wants:
+// [n-tile][k-block][row (bn_tile)][64 K-elements] with the 128-byte swizzle already applied, so a stage's
+// weight tile is ONE contiguous bulk copy.  k = t*tap_pitch + col_off + c ; global row = r + r_off.
 __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ packed, const int32_t* __restrict__ wtap,
-                                    int R, int ntaps, int C, int C_real, long long s_r, long long s_c, long long row_pitch,
-                                    long long tap_pitch, long long col_off) {
+                                    int R, int ntaps, int C, int C_real, long long s_r, long long s_c, long long tap_pitch,
+                                    long long col_off, int r_off, int bn_tile, int nkb) {
   const long long total = (long long)R * ntaps * C;
+  const long long tile_elems = (long long)bn_tile * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long t2 = i / C;
@@ -486,7 +500,13 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     const int r = (int)(t2 / ntaps);
     float v = 0.f;
     if (c < C_real) v = w[(long long)r * s_r + (long long)c * s_c + wtap[t]];
-    packed[(long long)r * row_pitch + (long long)t * tap_pitch + col_off + c] = __float2bfloat16(v);
+    const int rg = r + r_off;
+    const int tile = rg / bn_tile, rr = rg - tile * bn_tile;
+    const long long k = (long long)t * tap_pitch + col_off + c;
+    const int kb = (int)(k >> 6), kk = (int)(k & 63);
+    const long long off = ((long long)tile * nkb + kb) * tile_elems + (rr >> 3) * 512 + (rr & 7) * 64 +
+                          (((kk >> 3) ^ (rr & 7)) << 3) + (kk & 7);
+    packed[off] = __float2bfloat16(v);
   }
 }
 
@@ -497,7 +517,7 @@ int pick_bn_tile(int Cout) {
   return (t + 15) & ~15;
 }
 
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kCtaSmemTarget = 72 * 1024;    // ~3 CTAs per SM (2 for 256-wide tiles)
 
 }  // namespace
 
@@ -527,11 +547,11 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   if (max_m == 0) return 0;
   const int bn16 = (d.bn_tile + 15) & ~15;
   const int stage_bytes = kATileBytes + (((bn16 * 128) + 1023) & ~1023);
-  int stages = kSmemBudget / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  B2C_REQUIRE(stages >= 3, "conv_fprop: tile too large for shared memory");
-  int lag = stages - 2;
-  if (lag > 4) lag = 4;
+  // several CTAs per SM (each with a short pipeline) so one CTA's prologue / epilogue overlaps the others' main loops
+  int stages = kCtaSmemTarget / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  const int lag = stages - 1;
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeSmem) + (size_t)max_taps * 4 + 1024 + 64;
   static size_t configured = 0;
   if (smem > configured) {
@@ -577,11 +597,10 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(nsplit == 1 || d.atomic, "conv_wgrad: nsplit>1 requires atomic accumulation");
   const int bn16 = (d.bn_tile + 15) & ~15;
   const int stage_bytes = kATileBytes + ((bn16 + 63) / 64) * 8 * 1024;
-  int stages = kSmemBudget / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  B2C_REQUIRE(stages >= 3, "conv_wgrad: tile too large for shared memory");
-  int lag = stages - 2;
-  if (lag > 4) lag = 4;
+  int stages = kCtaSmemTarget / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  const int lag = stages - 1;
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeSmem) + 1024 + 64;
   static bool configured = false;
   if (!configured) {
@@ -597,18 +616,19 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
 }
 
 B2C_API int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, int32_t R, int32_t ntaps, int32_t C,
-                             int32_t C_real, int64_t s_r, int64_t s_c, int64_t row_pitch, int64_t tap_pitch, int64_t col_off,
-                             b2c_stream_t stream) {
+                             int32_t C_real, int64_t s_r, int64_t s_c, int64_t tap_pitch, int64_t col_off, int32_t r_off,
+                             int32_t bn_tile, int32_t nkb, b2c_stream_t stream) {
   B2C_REQUIRE(w && packed && wtap, "pack_weights: null pointer");
   B2C_REQUIRE(R > 0 && ntaps > 0 && C > 0 && C_real > 0 && C_real <= C, "pack_weights: bad dims");
+  B2C_REQUIRE(bn_tile > 0 && bn_tile % 16 == 0 && bn_tile <= 256 && nkb > 0, "pack_weights: bad tiling bn_tile=%d nkb=%d", bn_tile, nkb);
+  if (tap_pitch <= 0) tap_pitch = C;
+  B2C_REQUIRE(((int64_t)(ntaps - 1) * tap_pitch + col_off + C + 63) / 64 <= nkb, "pack_weights: K exceeds nkb");
   const long long total = (long long)R * ntaps * C;
   int blocks = (int)((total + 255) / 256);
   const int cap = b2c_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  if (row_pitch <= 0) row_pitch = (int64_t)ntaps * C;
-  if (tap_pitch <= 0) tap_pitch = C;
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<bf16*>(packed), wtap, R, ntaps, C, C_real,
-                                                               s_r, s_c, row_pitch, tap_pitch, col_off);
+                                                               s_r, s_c, tap_pitch, col_off, r_off, bn_tile, nkb);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("pack_weights launch");
   return 0;
