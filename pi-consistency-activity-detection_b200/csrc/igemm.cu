@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_cons
   const int bn16 = (bn + 15) & ~15;  // UMMA N (multiple of 16 for M=128)
   const int K = cc.ntaps * d.Cin;
   const int nkb = (K + kBlockK - 1) / kBlockK;
-  const int b_tile_bytes = ((bn16 * 128) + 1023) & ~1023;
+  // weight tiles are packed with the layer-wide bn_tile (the last n-tile is zero padded to the same size)
+  const int b_tile_bytes = (((((d.bn_tile + 15) & ~15)) * 128) + 1023) & ~1023;
   const int stage_bytes = kATileBytes + b_tile_bytes;
 
   extern __shared__ uint8_t smem_raw[];
