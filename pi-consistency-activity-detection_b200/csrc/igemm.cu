@@ -47,231 +47,322 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
 }
 
 // =====================================================================================
-// fprop-like kernel
+// fprop-like kernel: persistent, warp specialised
+//   warps 0-3 : im2col gather producers (one GEMM row per thread, 16-byte cp.async with zero fill);
+//               thread 0 also arms the bulk copy of the pre-swizzled weight tile of each K-block
+//   warp  4   : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 5-8 : epilogue (TMEM -> registers -> bias / scale / ReLU / sigmoid -> global), overlapped with the
+//               next tile's main loop through two TMEM accumulators
+// Each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and its mbarrier phases run
+// continuously across tiles, so there is no pipeline drain / fill between tiles.
 // =====================================================================================
-__global__ void __launch_bounds__(kThreads) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d, int stages,
-                                                               int lag) {
-  const b2c_conv_class& cc = d.cls[blockIdx.z];
-  const long long Mtot = (long long)d.N * cc.Qt * cc.Qh * cc.Qw;
-  const long long m0 = (long long)blockIdx.x * kTileM;
-  if (m0 >= Mtot) return;  // uniform for the CTA; nothing allocated yet
-  const int n0 = blockIdx.y * d.bn_tile;
-  int bn = d.Cout - n0;
-  if (bn > d.bn_tile) bn = d.bn_tile;
-  const int bn16 = (bn + 15) & ~15;  // UMMA N (multiple of 16 for M=128)
-  const int K = cc.ntaps * d.Cin;
-  const int nkb = (K + kBlockK - 1) / kBlockK;
-  // weight tiles are packed with the layer-wide bn_tile (the last n-tile is zero padded to the same size)
-  const int b_tile_bytes = (((((d.bn_tile + 15) & ~15)) * 128) + 1023) & ~1023;
+constexpr int kFpropThreads = 288;
+
+struct FpropSmem {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad_;
+};
+
+struct TileInfo {
+  int cls, n_idx;
+  long long m0;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const b2c_conv_desc& d, long long t, int n_tiles) {
+  TileInfo ti;
+  ti.cls = 0;
+  for (int c = 0; c < d.nclass; ++c) {
+    const b2c_conv_class& cc = d.cls[c];
+    const long long mt = ((long long)d.N * cc.Qt * cc.Qh * cc.Qw + kTileM - 1) / kTileM;
+    const long long tc = mt * n_tiles;
+    if (t < tc) {
+      ti.cls = c;
+      break;
+    }
+    t -= tc;
+  }
+  ti.n_idx = (int)(t % n_tiles);
+  ti.m0 = (t / n_tiles) * kTileM;
+  return ti;
+}
+
+__global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d, int stages,
+                                                                       int lag, long long total_tiles, int n_tiles) {
+  const int acc_cols = (d.bn_tile + 15) & ~15;                     // TMEM columns per accumulator
+  const int b_tile_bytes = ((acc_cols * 128) + 1023) & ~1023;      // packed weight tile (layer-wide bn_tile)
   const int stage_bytes = kATileBytes + b_tile_bytes;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem_al + (size_t)stages * stage_bytes);
-  int32_t* s_taps = reinterpret_cast<int32_t*>(ps + 1);
+  FpropSmem* ps = reinterpret_cast<FpropSmem*>(smem_al + (size_t)stages * stage_bytes);
+  int32_t* s_taps = reinterpret_cast<int32_t*>(ps + 1);            // all classes back to back
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
-  for (int i = tid; i < cc.ntaps; i += kThreads) s_taps[i] = cc.taps[i];
+  int tap_off[8];
+  {
+    int o = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      tap_off[c] = o;
+      if (c < d.nclass) o += d.cls[c].ntaps;
+    }
+    for (int c = 0; c < d.nclass; ++c)
+      for (int i = tid; i < d.cls[c].ntaps; i += kFpropThreads) s_taps[tap_off[c] + i] = d.cls[c].taps[i];
+  }
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&ps->full[s], 128 + 1);   // 128 gather threads + the thread that arms the weight bulk copy
       mbar_init(&ps->empty[s], 1);
     }
-    mbar_init(&ps->accum, 1);
+    mbar_init(&ps->tfull[0], 1);
+    mbar_init(&ps->tfull[1], 1);
+    mbar_init(&ps->tempty[0], 128);
+    mbar_init(&ps->tempty[1], 128);
     fence_barrier_init();
   }
-  const uint32_t tmem_cols = tmem_cols_for(bn16);
+  const uint32_t tmem_cols = tmem_cols_for(2 * acc_cols);
   if (warp == 4) tmem_alloc(&ps->tmem_base, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = ps->tmem_base;
+  const uint32_t tmem_base = ps->tmem_base;
 
   if (warp < 4) {
     // ------------------------------ producers --------------------------------------
-    const int r = tid;  // A row == TMEM lane
-    const long long m = m0 + r;
-    const bool mvalid = m < Mtot;
-    int n_i = 0, qt = 0, qh = 0, qw = 0;
-    if (mvalid) {
-      long long t = m;
-      qw = (int)(t % cc.Qw); t /= cc.Qw;
-      qh = (int)(t % cc.Qh); t /= cc.Qh;
-      qt = (int)(t % cc.Qt); t /= cc.Qt;
-      n_i = (int)t;
-    }
-    const int it0 = qt * d.si_t, ih0 = qh * d.si_h, iw0 = qw * d.si_w;
+    const int r = tid;
     const bf16* in_n = reinterpret_cast<const bf16*>(d.in) + d.in_c_off;
     const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     const uint32_t swz = (uint32_t)(r & 7);
-
-    // running (tap, channel) cursor for this thread's next chunk; identical across threads
-    int tap = 0, c = 0;
-    const bf16* tap_ptr = nullptr;  // pointer to channel 0 of the current tap's input pixel (or null if OOB)
-    auto load_tap = [&](int tp) {
-      tap_ptr = nullptr;
-      if (mvalid && tp < cc.ntaps) {
-        const int32_t tv = s_taps[tp];
-        const int it = it0 + tap_dt(tv), ih = ih0 + tap_dh(tv), iw = iw0 + tap_dw(tv);
-        if ((unsigned)it < (unsigned)d.Ti && (unsigned)ih < (unsigned)d.Hi && (unsigned)iw < (unsigned)d.Wi)
-          tap_ptr = in_n + ((((long long)n_i * d.Ti + it) * d.Hi + ih) * d.Wi + iw) * d.in_row_stride;
-      }
-    };
-    load_tap(0);
-
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(&ps->empty[stage], phase ^ 1, 1);
-      const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
-      const uint32_t b_st = a_st + kATileBytes;
-      // A: 8 chunks of 8 channels
+    long long issued = 0;   // K-blocks issued so far by this CTA (all tiles)
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = decode_tile(d, t, n_tiles);
+      const b2c_conv_class& cc = d.cls[ti.cls];
+      const int32_t* taps = s_taps + tap_off[ti.cls];
+      const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
+      const unsigned m = (unsigned)ti.m0 + (unsigned)r;
+      const bool mvalid = m < Mtot;
+      int n_i = 0, qt = 0, qh = 0, qw = 0;
+      if (mvalid) {
+        unsigned q = m;
+        qw = (int)(q % (unsigned)cc.Qw); q /= (unsigned)cc.Qw;
+        qh = (int)(q % (unsigned)cc.Qh); q /= (unsigned)cc.Qh;
+        qt = (int)(q % (unsigned)cc.Qt); q /= (unsigned)cc.Qt;
+        n_i = (int)q;
+      }
+      const int it0 = qt * d.si_t, ih0 = qh * d.si_h, iw0 = qw * d.si_w;
+      const int K = cc.ntaps * d.Cin;
+      const int nkb = (K + kBlockK - 1) / kBlockK;
+      const uint8_t* wtile = reinterpret_cast<const uint8_t*>(cc.w) + (size_t)ti.n_idx * nkb * (size_t)b_tile_bytes;
+      int tap = 0, c = 0;
+      const bf16* tap_ptr = nullptr;
+      auto load_tap = [&](int tp) {
+        tap_ptr = nullptr;
+        if (mvalid && tp < cc.ntaps) {
+          const int32_t tv = taps[tp];
+          const int it = it0 + tap_dt(tv), ih = ih0 + tap_dh(tv), iw = iw0 + tap_dw(tv);
+          if ((unsigned)it < (unsigned)d.Ti && (unsigned)ih < (unsigned)d.Hi && (unsigned)iw < (unsigned)d.Wi)
+            tap_ptr = in_n + ((((long long)n_i * d.Ti + it) * d.Hi + ih) * d.Wi + iw) * d.in_row_stride;
+        }
+      };
+      load_tap(0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&ps->empty[stage], phase ^ 1, 1);
+        const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t dst = a_st + a_row_off + (((uint32_t)j ^ swz) << 4);
-        const void* src = tap_ptr ? (const void*)(tap_ptr + c) : (const void*)d.in;
-        cp_async16(dst, src, tap_ptr ? 16u : 0u);
-        c += 8;
-        if (c >= d.Cin) {
-          c = 0;
-          ++tap;
-          load_tap(tap);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = a_st + a_row_off + (((uint32_t)j ^ swz) << 4);
+          const void* src = tap_ptr ? (const void*)(tap_ptr + c) : (const void*)d.in;
+          cp_async16(dst, src, tap_ptr ? 16u : 0u);
+          c += 8;
+          if (c >= d.Cin) {
+            c = 0;
+            ++tap;
+            load_tap(tap);
+          }
+        }
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)b_tile_bytes);
+          bulk_g2s(a_st + kATileBytes, wtile + (size_t)kb * b_tile_bytes, (uint32_t)b_tile_bytes, &ps->full[stage]);
+        }
+        cp_async_commit();
+        ++issued;
+        if (issued > lag) {   // the K-block issued `lag` iterations ago has landed
+          cp_async_wait_dyn(lag);
+          fence_proxy_async_smem();
+          int s2 = stage - lag;
+          if (s2 < 0) s2 += stages;
+          mbar_arrive(&ps->full[s2]);
+        }
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
-      // B: the weight tile of this (n-tile, k-block) is stored pre-swizzled and contiguous -> one bulk copy
-      if (tid == 0) {
-        mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)b_tile_bytes);
-        bulk_g2s(b_st, reinterpret_cast<const uint8_t*>(cc.w) + ((size_t)blockIdx.y * nkb + kb) * (size_t)b_tile_bytes,
-                 (uint32_t)b_tile_bytes, &ps->full[stage]);
-      }
-      cp_async_commit();
-      // signal the stage issued `lag` iterations ago
-      if (kb >= lag) {
-        cp_async_wait_dyn(lag);
-        fence_proxy_async_smem();
-        int s2 = stage - lag;
-        if (s2 < 0) s2 += stages;
-        mbar_arrive(&ps->full[s2]);
-      }
-      if (++stage == stages) {
-        stage = 0;
-        phase ^= 1;
-      }
     }
-    // drain
+    // drain the last `lag` K-blocks
     cp_async_wait<0>();
     fence_proxy_async_smem();
     {
-      int first = nkb - lag;
-      if (first < 0) first = 0;
-      for (int kb = first; kb < nkb; ++kb) mbar_arrive(&ps->full[kb % stages]);
-    }
-
-    // ------------------------------ epilogue ---------------------------------------
-    mbar_wait(&ps->accum, 0, 3);
-    tc_fence_after();
-    long long opos = 0;
-    if (mvalid)
-      opos = (((long long)n_i * d.To + (qt * d.so_t + cc.po_t)) * d.Ho + (qh * d.so_h + cc.po_h)) * d.Wo +
-             (qw * d.so_w + cc.po_w);
-    const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
-    const float* scale_row = d.scale_nc ? d.scale_nc + (long long)n_i * d.Cout : nullptr;
-    for (int c0 = 0; c0 < bn16; c0 += 32) {
-      float v[32];
-      const int nh = (bn16 - c0 >= 32) ? 4 : 2;
-      if (nh == 4) tmem_ld32(t_lane + (uint32_t)c0, v);
-      else tmem_ld16(t_lane + (uint32_t)c0, v);
-      if (!mvalid) continue;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        if (h >= nh) break;
-        const int col = n0 + c0 + h * 8;
-        if (col >= d.Cout) break;
-        float* vv = v + h * 8;
-        if (d.bias) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] += __ldg(d.bias + col + i);
-        }
-        if (scale_row) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] *= __ldg(scale_row + col + i);
-        }
-        if (d.relu) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
-        }
-        if (d.sigmoid_from >= 0 && col >= d.sigmoid_from) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
-        }
-        if (d.out_fp32 == 2) {
-          // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
-          float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (d.accumulate) vv[i] += o[(long long)i * d.out_row_stride];
-            o[(long long)i * d.out_row_stride] = vv[i];
-          }
-        } else if (d.out_fp32) {
-          float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
-          float4* o4 = reinterpret_cast<float4*>(o);
-          if (d.accumulate) {
-            float4 a = o4[0], b = o4[1];
-            vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
-            vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
-          }
-          o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-          o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
-        } else {
-          bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
-          uint4* o4 = reinterpret_cast<uint4*>(o);
-          if (d.accumulate) {
-            float e[8];
-            unpack8(*o4, e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] += e[i];
-          }
-          *o4 = pack8(vv);
-        }
+      long long pending = issued < lag ? issued : lag;
+      int s2 = stage - (int)pending;
+      if (s2 < 0) s2 += stages;
+      for (long long i = 0; i < pending; ++i) {
+        mbar_arrive(&ps->full[s2]);
+        if (++s2 == stages) s2 = 0;
       }
     }
-    tc_fence_before();
-  } else {
-    // ------------------------------ MMA issuer (warp 4) ----------------------------
-    const uint32_t idesc = umma_idesc_bf16(bn16, 0, 0);
+  } else if (warp == 4) {
+    // ------------------------------ MMA issuer -------------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(&ps->full[stage], phase, 2);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = decode_tile(d, t, n_tiles);
+      const b2c_conv_class& cc = d.cls[ti.cls];
+      const int n0 = ti.n_idx * d.bn_tile;
+      int bn = d.Cout - n0;
+      if (bn > d.bn_tile) bn = d.bn_tile;
+      const int bn16 = (bn + 15) & ~15;
+      const int nkb = (cc.ntaps * d.Cin + kBlockK - 1) / kBlockK;
+      const uint32_t idesc = umma_idesc_bf16(bn16, 0, 0);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+      mbar_wait(&ps->tempty[acc], acc_phase ^ 1, 4);   // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
-        const uint32_t b_st = a_st + kATileBytes;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&ps->full[stage], phase, 2);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t b_st = a_st + kATileBytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(a_st + k * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(b_st + k * 32, 16, 1024);
-          umma_bf16(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(a_st + k * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(b_st + k * 32, 16, 1024);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&ps->empty[stage]);
         }
-        umma_commit(&ps->empty[stage]);
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (lane == 0) umma_commit(&ps->tfull[acc]);
       __syncwarp();
-      if (++stage == stages) {
-        stage = 0;
-        phase ^= 1;
-      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) umma_commit(&ps->accum);
-    __syncwarp();
+  } else {
+    // ------------------------------ epilogue (warps 5..8) ---------------------------
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = decode_tile(d, t, n_tiles);
+      const b2c_conv_class& cc = d.cls[ti.cls];
+      const int n0 = ti.n_idx * d.bn_tile;
+      int bn = d.Cout - n0;
+      if (bn > d.bn_tile) bn = d.bn_tile;
+      const int bn16 = (bn + 15) & ~15;
+      const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
+      const unsigned m = (unsigned)ti.m0 + (unsigned)(quarter * 32 + lane);
+      const bool mvalid = m < Mtot;
+      long long opos = 0;
+      int n_i = 0;
+      if (mvalid) {
+        unsigned q = m;
+        const int qw = (int)(q % (unsigned)cc.Qw); q /= (unsigned)cc.Qw;
+        const int qh = (int)(q % (unsigned)cc.Qh); q /= (unsigned)cc.Qh;
+        const int qt = (int)(q % (unsigned)cc.Qt); q /= (unsigned)cc.Qt;
+        n_i = (int)q;
+        opos = (((long long)n_i * d.To + (qt * d.so_t + cc.po_t)) * d.Ho + (qh * d.so_h + cc.po_h)) * d.Wo +
+               (qw * d.so_w + cc.po_w);
+      }
+      const float* scale_row = d.scale_nc ? d.scale_nc + (long long)n_i * d.Cout : nullptr;
+      mbar_wait(&ps->tfull[acc], acc_phase, 3);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = 0; c0 < bn16; c0 += 32) {
+        float v[32];
+        const int nh = (bn16 - c0 >= 32) ? 4 : 2;
+        if (nh == 4) tmem_ld32(t_lane + (uint32_t)c0, v);
+        else tmem_ld16(t_lane + (uint32_t)c0, v);
+        if (!mvalid) continue;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (h >= nh) break;
+          const int col = n0 + c0 + h * 8;
+          if (col >= d.Cout) break;
+          float* vv = v + h * 8;
+          if (d.bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] += __ldg(d.bias + col + i);
+          }
+          if (scale_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] *= __ldg(scale_row + col + i);
+          }
+          if (d.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+          }
+          if (d.sigmoid_from >= 0 && col >= d.sigmoid_from) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
+          }
+          if (d.out_fp32 == 2) {
+            // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
+            float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (d.accumulate) vv[i] += o[(long long)i * d.out_row_stride];
+              o[(long long)i * d.out_row_stride] = vv[i];
+            }
+          } else if (d.out_fp32) {
+            float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+            float4* o4 = reinterpret_cast<float4*>(o);
+            if (d.accumulate) {
+              float4 a = o4[0], b = o4[1];
+              vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
+              vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
+            }
+            o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+          } else {
+            bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+            if (d.accumulate) {
+              float e[8];
+              unpack8(*o4, e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] += e[i];
+            }
+            *o4 = pack8(vv);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ps->tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
   }
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, tmem_cols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -535,33 +626,36 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.out & 15) == 0, "conv_fprop: tensors must be 16B aligned");
   if (d.bn_tile <= 0) d.bn_tile = pick_bn_tile(d.Cout);
   B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_fprop: bn_tile=%d invalid", d.bn_tile);
-  long long max_m = 0;
-  int max_taps = 0;
+  long long total_tiles = 0;
+  int sum_taps = 0;
+  const int n_tiles = (d.Cout + d.bn_tile - 1) / d.bn_tile;
   for (int i = 0; i < d.nclass; ++i) {
     const b2c_conv_class& c = d.cls[i];
     B2C_REQUIRE(c.taps && c.w && c.ntaps > 0, "conv_fprop: class %d incomplete", i);
     B2C_REQUIRE(((uintptr_t)c.w & 15) == 0, "conv_fprop: weights must be 16B aligned");
-    long long m = (long long)d.N * c.Qt * c.Qh * c.Qw;
-    if (m > max_m) max_m = m;
-    if (c.ntaps > max_taps) max_taps = c.ntaps;
+    const long long m = (long long)d.N * c.Qt * c.Qh * c.Qw;
+    B2C_REQUIRE(m < (1LL << 31), "conv_fprop: GEMM-M too large");
+    total_tiles += ((m + kTileM - 1) / kTileM) * n_tiles;
+    sum_taps += c.ntaps;
   }
-  if (max_m == 0) return 0;
-  const int bn16 = (d.bn_tile + 15) & ~15;
-  const int stage_bytes = kATileBytes + (((bn16 * 128) + 1023) & ~1023);
-  // several CTAs per SM (each with a short pipeline) so one CTA's prologue / epilogue overlaps the others' main loops
-  int stages = kCtaSmemTarget / stage_bytes;
-  if (stages > 4) stages = 4;
-  if (stages < 2) stages = 2;
-  const int lag = stages - 1;
-  const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeSmem) + (size_t)max_taps * 4 + 1024 + 64;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+  if (total_tiles == 0) return 0;
+  const int acc_cols = (d.bn_tile + 15) & ~15;
+  const int stage_bytes = kATileBytes + (((acc_cols * 128) + 1023) & ~1023);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  B2C_REQUIRE(stages >= 3, "conv_fprop: tile too large for shared memory");
+  int lag = stages - 2;
+  if (lag > 6) lag = 6;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(FpropSmem) + (size_t)sum_taps * 4 + 1024 + 64;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
     if (e != cudaSuccess) return b2c_cuda_check(e, "conv_fprop: cudaFuncSetAttribute");
-    configured = 220 * 1024;
+    configured = true;
   }
-  dim3 grid((unsigned)((max_m + kTileM - 1) / kTileM), (unsigned)((d.Cout + d.bn_tile - 1) / d.bn_tile), (unsigned)d.nclass);
-  igemm_fprop_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, stages, lag);
+  long long grid = b2c_num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, stages, lag, total_tiles, n_tiles);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_fprop launch");
   return 0;
@@ -587,8 +681,11 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   const long long nkb = (Mtot + kBlockK - 1) / kBlockK;
   int nsplit = d.nsplit;
   if (nsplit <= 0) {
-    // fill ~2 waves of SMs, keep >= 8 position blocks per CTA
-    long long want = (2LL * b2c_num_sms() + (long long)mt * nt - 1) / ((long long)mt * nt);
+    // long position loops with a deep pipeline, one CTA per SM: pick the split so the grid is ~1-2 full waves
+    const long long tiles = (long long)mt * nt;
+    const long long sms = b2c_num_sms();
+    long long want = (2 * sms + tiles - 1) / tiles;
+    if (tiles * want > 2 * sms && want > 1) --want;
     long long cap = nkb / 8;
     if (cap < 1) cap = 1;
     nsplit = (int)(want < cap ? want : cap);
@@ -598,10 +695,13 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(nsplit == 1 || d.atomic, "conv_wgrad: nsplit>1 requires atomic accumulation");
   const int bn16 = (d.bn_tile + 15) & ~15;
   const int stage_bytes = kATileBytes + ((bn16 + 63) / 64) * 8 * 1024;
-  int stages = kCtaSmemTarget / stage_bytes;
-  if (stages > 4) stages = 4;
+  // latency-bound gather: keep as many K-blocks in flight as shared memory allows (ncu r01: 2 stages -> L2 45 %, tensor 11 %)
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  const int lag = stages - 1;
+  int lag = stages - 2;
+  if (lag < 1) lag = 1;
+  if (lag > 6) lag = 6;
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeSmem) + 1024 + 64;
   static bool configured = false;
   if (!configured) {
