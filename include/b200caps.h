@@ -46,7 +46,7 @@ typedef struct {
   int32_t ntaps;
   int32_t Qt, Qh, Qw;       /* GEMM-M grid of this class */
   int32_t po_t, po_h, po_w; /* output offset of this class */
-  int32_t pad_;
+  int32_t lo_t, lo_h, lo_w; /* per-dimension minimum tap offset (lower corner of the im2col TMA box) */
 } b2c_conv_class;
 
 typedef struct {

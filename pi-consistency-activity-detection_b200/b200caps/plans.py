@@ -287,6 +287,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
         c.taps, c.w, c.ntaps = cl.taps_dev.data_ptr(), cl.packed.data_ptr(), len(cl.taps)
         c.Qt, c.Qh, c.Qw = cl.Q
         c.po_t, c.po_h, c.po_w = cl.po
+        c.lo_t, c.lo_h, c.lo_w = (min(t[i] for t in cl.taps) for i in range(3))
     return d
 
 

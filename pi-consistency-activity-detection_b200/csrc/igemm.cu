@@ -13,6 +13,8 @@
 // single-thread UMMA issuer.
 #include "common.cuh"
 #include "../../include/b200caps.h"
+#include <string.h>
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
 
 static long long g_launches = 0;
 long long b2c_launches_add(long long n) {
@@ -58,6 +60,20 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
 // =====================================================================================
 constexpr int kFpropThreads = 288;
 
+struct alignas(64) TmaMaps {
+  CUtensorMap a[8];   // per class: im2col map of the gathered activation view
+};
+
+// im2col TMA: 128 pixels x 64 channels of one filter tap, 128B-swizzled, zero fill outside the tensor
+__device__ __forceinline__ void tma_im2col_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int t,
+                                              int n, uint16_t ow, uint16_t oh, uint16_t ot) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(t), "r"(n), "h"(ow), "h"(oh), "h"(ot)
+      : "memory");
+}
+
 struct FpropSmem {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -90,8 +106,9 @@ __device__ __forceinline__ TileInfo decode_tile(const b2c_conv_desc& d, long lon
   return ti;
 }
 
-__global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d, int stages,
-                                                                       int lag, long long total_tiles, int n_tiles) {
+__global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d,
+                                                                       const __grid_constant__ TmaMaps maps, int use_tma,
+                                                                       int stages, int lag, long long total_tiles, int n_tiles) {
   const int acc_cols = (d.bn_tile + 15) & ~15;                     // TMEM columns per accumulator
   const int b_tile_bytes = ((acc_cols * 128) + 1023) & ~1023;      // packed weight tile (layer-wide bn_tile)
   const int stage_bytes = kATileBytes + b_tile_bytes;
@@ -119,7 +136,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   }
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&ps->full[s], 128 + 1);   // 128 gather threads + the thread that arms the weight bulk copy
+      // gather path: 128 gather threads + the thread that arms the weight bulk copy; TMA path: one producer thread
+      mbar_init(&ps->full[s], use_tma ? 1 : 128 + 1);
       mbar_init(&ps->empty[s], 1);
     }
     mbar_init(&ps->tfull[0], 1);
@@ -135,8 +153,47 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = ps->tmem_base;
 
-  if (warp < 4) {
-    // ------------------------------ producers --------------------------------------
+  if (warp < 4 && use_tma) {
+    // ------------------------------ TMA producer (one elected thread) ----------------
+    // A: im2col tensor map, one instruction per (tap, 64-channel block); B: bulk copy of the packed weight tile
+    if (tid == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cblocks = d.Cin / kBlockK;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(d, t, n_tiles);
+        const b2c_conv_class& cc = d.cls[ti.cls];
+        const int32_t* taps = s_taps + tap_off[ti.cls];
+        unsigned q = (unsigned)ti.m0;
+        const int qw = (int)(q % (unsigned)cc.Qw); q /= (unsigned)cc.Qw;
+        const int qh = (int)(q % (unsigned)cc.Qh); q /= (unsigned)cc.Qh;
+        const int qt = (int)(q % (unsigned)cc.Qt); q /= (unsigned)cc.Qt;
+        const int n_i = (int)q;
+        const int bw = qw * d.si_w + cc.lo_w, bh = qh * d.si_h + cc.lo_h, bt = qt * d.si_t + cc.lo_t;
+        const int nkb = cc.ntaps * cblocks;
+        const uint8_t* wtile = reinterpret_cast<const uint8_t*>(cc.w) + (size_t)ti.n_idx * nkb * (size_t)b_tile_bytes;
+        const CUtensorMap* map = &maps.a[ti.cls];
+        int kb = 0;
+        for (int tp = 0; tp < cc.ntaps; ++tp) {
+          const int32_t tv = taps[tp];
+          const uint16_t ow = (uint16_t)(tap_dw(tv) - cc.lo_w), oh = (uint16_t)(tap_dh(tv) - cc.lo_h),
+                         ot = (uint16_t)(tap_dt(tv) - cc.lo_t);
+          for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+            mbar_wait(&ps->empty[stage], phase ^ 1, 1);
+            const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
+            mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)(kATileBytes + b_tile_bytes));
+            tma_im2col_5d(a_st, map, &ps->full[stage], cb * kBlockK, bw, bh, bt, n_i, ow, oh, ot);
+            bulk_g2s(a_st + kATileBytes, wtile + (size_t)kb * b_tile_bytes, (uint32_t)b_tile_bytes, &ps->full[stage]);
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------ gather producers (Cin not a multiple of 64) --------
     const int r = tid;
     const bf16* in_n = reinterpret_cast<const bf16*>(d.in) + d.in_c_off;
     const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
@@ -602,6 +659,49 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
   }
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  return fn;
+}
+
+// im2col tensor map over a channels-last bf16 view (C, W, H, T, N).  The bounding box of BASE pixels is
+// [lo, lo + (Q-1)*stride] per spatial dim (corner arrays in W,H,D order, like CUTLASS); filter taps are passed as
+// non-negative offsets (d_tap - lo) in the instruction.  Out-of-tensor reads are zero filled (= padding).
+int encode_im2col_map(CUtensorMap* map, const bf16* base, int C, long long row_stride, int N, int T, int H, int W, int lo_t,
+                      int lo_h, int lo_w, int Qt, int Qh, int Qw, int st, int sh, int sw, int channels, int pixels) {
+  EncodeIm2colFn fn = get_encode_im2col();
+  if (!fn) return b2c_fail(-2, "cuTensorMapEncodeIm2col entry point not available in this driver");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)row_stride * 2, (cuuint64_t)row_stride * 2 * W, (cuuint64_t)row_stride * 2 * W * H,
+                           (cuuint64_t)row_stride * 2 * W * H * T};
+  int lower[3] = {lo_w, lo_h, lo_t};
+  int upper[3] = {lo_w + (Qw - 1) * sw - (W - 1), lo_h + (Qh - 1) * sh - (H - 1), lo_t + (Qt - 1) * st - (T - 1)};
+  for (int i = 0; i < 3; ++i)
+    if (lower[i] < -16 || lower[i] > 15 || upper[i] < -16 || upper[i] > 15)
+      return b2c_fail(-1, "im2col corner out of range: lower %d upper %d (dim %d)", lower[i], upper[i], i);
+  cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)st, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, lower, upper,
+                  (cuuint32_t)channels, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return b2c_fail(-3, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
+  // CUTLASS (copy_traits_sm90_im2col.hpp) clears this descriptor bit for tensors < 128 KiB on drivers <= 13.1
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  const unsigned long long bytes = (unsigned long long)row_stride * 2ull * W * H * T * N;
+  if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  return 0;
+}
+
 int pick_bn_tile(int Cout) {
   if (Cout <= 256) return (Cout + 15) & ~15;
   const int nt = (Cout + 255) / 256;
@@ -653,9 +753,21 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
     if (e != cudaSuccess) return b2c_cuda_check(e, "conv_fprop: cudaFuncSetAttribute");
     configured = true;
   }
+  TmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int use_tma = (d.Cin % kBlockK == 0) ? 1 : 0;
+  if (use_tma) {
+    for (int i = 0; i < d.nclass; ++i) {
+      const b2c_conv_class& c = d.cls[i];
+      int rc = encode_im2col_map(&maps.a[i], reinterpret_cast<const bf16*>(d.in) + d.in_c_off, d.Cin, d.in_row_stride, d.N, d.Ti,
+                                 d.Hi, d.Wi, c.lo_t, c.lo_h, c.lo_w, c.Qt, c.Qh, c.Qw, d.si_t, d.si_h, d.si_w, kBlockK, kTileM);
+      if (rc) return rc;
+    }
+  }
   long long grid = b2c_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, stages, lag, total_tiles, n_tiles);
+  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, stages, lag, total_tiles,
+                                                                                    n_tiles);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_fprop launch");
   return 0;
