@@ -77,8 +77,9 @@ typedef struct {
   const void* g;
   const void* p;
   float* dw;
-  const int32_t* taps; /* [ntaps] */
-  const int32_t* wtap; /* [ntaps] element offset of the tap inside dw */
+  const int32_t* taps;      /* [ntaps] device */
+  const int32_t* wtap;      /* [ntaps] device: element offset of the tap inside dw */
+  const int32_t* taps_host; /* [ntaps] host copy of taps (needed to build the TMA im2col box); NULL = gather path */
   int64_t g_row_stride, p_row_stride, s_p, s_g;
   int32_t g_c_off, p_c_off, Cg, Cp, Cg_real; /* channels >= Cg_real are zero padding */
   int32_t Cp_real;                           /* p channels >= Cp_real are padding (0 = Cp) */

@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
 
 
 class WgradDesc(C.Structure):
-    _fields_ = [("g", vp), ("p", vp), ("dw", vp), ("taps", vp), ("wtap", vp),
+    _fields_ = [("g", vp), ("p", vp), ("dw", vp), ("taps", vp), ("wtap", vp), ("taps_host", vp),
                 ("g_row_stride", i64), ("p_row_stride", i64), ("s_p", i64), ("s_g", i64),
                 ("g_c_off", i32), ("p_c_off", i32), ("Cg", i32), ("Cp", i32), ("Cg_real", i32), ("Cp_real", i32),
                 ("N", i32), ("Tg", i32), ("Hg", i32), ("Wg", i32), ("Tp", i32), ("Hp", i32), ("Wp", i32),

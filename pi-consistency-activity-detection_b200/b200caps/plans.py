@@ -53,6 +53,7 @@ class TapClass:
     po: Tuple[int, int, int]           # output offset
     taps_dev: Optional[torch.Tensor] = None
     wtap_dev: Optional[torch.Tensor] = None
+    taps_host: Optional[object] = None       # ctypes int32 array (kept alive with the plan)
     packed: Optional[torch.Tensor] = None
 
 
@@ -194,7 +195,9 @@ class ConvPlan:
         if self._device == device:
             return self
         for cl in self.fprop + self.dgrad:
-            cl.taps_dev = torch.tensor([_tap_word(*t) for t in cl.taps], dtype=torch.int32, device=device)
+            words = [_tap_word(*t) for t in cl.taps]
+            cl.taps_dev = torch.tensor(words, dtype=torch.int32, device=device)
+            cl.taps_host = (C.c_int32 * len(words))(*words)
             cl.wtap_dev = torch.tensor(cl.wtap, dtype=torch.int32, device=device)
         self._device = device
         return self
@@ -309,6 +312,7 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
     d.Cp_real = geo.get("Cp_real", geo["Cp"])
     d.g, d.p, d.dw = g.ptr, p.ptr, dw.data_ptr()
     d.taps, d.wtap = cl.taps_dev.data_ptr(), cl.wtap_dev.data_ptr()
+    d.taps_host = C.cast(cl.taps_host, C.c_void_p)
     d.g_row_stride, d.p_row_stride, d.s_p, d.s_g = g.row_stride, p.row_stride, geo["s_p"], geo["s_g"]
     d.g_c_off, d.p_c_off, d.Cg, d.Cp, d.Cg_real = g.c_off, p.c_off, geo["Cg"], geo["Cp"], geo["Cg_real"]
     d.N = x.N

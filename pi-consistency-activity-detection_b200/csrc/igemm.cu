@@ -87,27 +87,31 @@ struct TileInfo {
   int cls, n_idx;
   long long m0;
 };
+struct TileSched {
+  unsigned start[9];   // first tile index of each class (prefix sums), start[nclass] = total
+};
 
-__device__ __forceinline__ TileInfo decode_tile(const b2c_conv_desc& d, long long t, int n_tiles) {
+__device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass, long long t, int n_tiles) {
   TileInfo ti;
-  ti.cls = 0;
-  for (int c = 0; c < d.nclass; ++c) {
-    const b2c_conv_class& cc = d.cls[c];
-    const long long mt = ((long long)d.N * cc.Qt * cc.Qh * cc.Qw + kTileM - 1) / kTileM;
-    const long long tc = mt * n_tiles;
-    if (t < tc) {
-      ti.cls = c;
-      break;
-    }
-    t -= tc;
+  int c = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < nclass && (unsigned)t >= ts.start[i]) c = i;
+  const unsigned local = (unsigned)t - ts.start[c];
+  ti.cls = c;
+  if (n_tiles == 1) {
+    ti.n_idx = 0;
+    ti.m0 = (long long)local * kTileM;
+  } else {
+    ti.n_idx = (int)(local % (unsigned)n_tiles);
+    ti.m0 = (long long)(local / (unsigned)n_tiles) * kTileM;
   }
-  ti.n_idx = (int)(t % n_tiles);
-  ti.m0 = (t / n_tiles) * kTileM;
   return ti;
 }
 
 __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d,
-                                                                       const __grid_constant__ TmaMaps maps, int use_tma,
+                                                                       const __grid_constant__ TmaMaps maps,
+                                                                       const __grid_constant__ TileSched ts, int use_tma,
                                                                        int stages, int lag, long long total_tiles, int n_tiles) {
   const int acc_cols = (d.bn_tile + 15) & ~15;                     // TMEM columns per accumulator
   const int b_tile_bytes = ((acc_cols * 128) + 1023) & ~1023;      // packed weight tile (layer-wide bn_tile)
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       uint32_t phase = 0;
       const int cblocks = d.Cin / kBlockK;
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = decode_tile(d, t, n_tiles);
+        const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
         const b2c_conv_class& cc = d.cls[ti.cls];
         const int32_t* taps = s_taps + tap_off[ti.cls];
         unsigned q = (unsigned)ti.m0;
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     uint32_t phase = 0;
     long long issued = 0;   // K-blocks issued so far by this CTA (all tiles)
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(d, t, n_tiles);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int32_t* taps = s_taps + tap_off[ti.cls];
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(d, t, n_tiles);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int n0 = ti.n_idx * d.bn_tile;
       int bn = d.Cout - n0;
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(d, t, n_tiles);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int n0 = ti.n_idx * d.bn_tile;
       int bn = d.Cout - n0;
@@ -426,8 +430,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
 // =====================================================================================
 // wgrad kernel
 // =====================================================================================
-__global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_constant__ b2c_wgrad_desc d, int stages,
-                                                               int lag, int nsplit) {
+struct alignas(64) WgradMaps {
+  CUtensorMap g;   // gathered operand (im2col over the taps), 64 positions x 64 channels per load
+  CUtensorMap p;   // plain operand (same traversal, no taps)
+};
+
+__global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_constant__ b2c_wgrad_desc d,
+                                                               const __grid_constant__ WgradMaps maps, int use_tma, int lo_t,
+                                                               int lo_h, int lo_w, int stages, int lag, int nsplit) {
   const int K = d.ntaps * d.Cg;            // GEMM-M extent ((tap, gc) columns of the im2col matrix)
   const int mk0 = blockIdx.x * kTileM;     // first (tap,gc) column of this CTA
   const int n0 = blockIdx.y * d.bn_tile;   // first p-channel
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&ps->full[s], 128);
+      mbar_init(&ps->full[s], use_tma ? 1 : 128);
       mbar_init(&ps->empty[s], 1);
     }
     mbar_init(&ps->accum, 1);
@@ -468,8 +478,70 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_d = ps->tmem_base;
 
-  if (warp < 4) {
-    // producers: thread -> position row r (0..63) and half (0/1) of the chunk columns
+  if (warp < 4 && use_tma) {
+    // ---- TMA producer: one thread; per stage 2 im2col boxes (64 positions x 64 channels) of the gathered operand for the
+    // two 64-column halves of this CTA's 128 (tap, channel) columns, and bn/64 boxes of the plain operand
+    if (tid == 0) {
+      const int cblocks = d.Cg / kBlockK;
+      int sub_c[2];
+      uint16_t sub_ow[2], sub_oh[2], sub_ot[2];
+      bool sub_ok[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int blk = blockIdx.x * 2 + h;          // 64-column block index over (tap, channel block)
+        sub_ok[h] = blk < d.ntaps * cblocks;
+        const int tp = sub_ok[h] ? blk / cblocks : 0;
+        sub_c[h] = (blk - tp * cblocks) * kBlockK;
+        const int32_t tv = __ldg(d.taps + tp);
+        sub_ow[h] = (uint16_t)(tap_dw(tv) - lo_w);
+        sub_oh[h] = (uint16_t)(tap_dh(tv) - lo_h);
+        sub_ot[h] = (uint16_t)(tap_dt(tv) - lo_t);
+      }
+      const int nb = (bn16 + 63) / 64;
+      const uint32_t tx = (uint32_t)(((sub_ok[0] ? 1 : 0) + (sub_ok[1] ? 1 : 0) + nb) * 8192);
+      long long pos = kb_lo * kBlockK;
+      int n_i, qt, qh, qw;
+      {
+        unsigned q = (unsigned)pos;
+        qw = (int)(q % (unsigned)d.Qw); q /= (unsigned)d.Qw;
+        qh = (int)(q % (unsigned)d.Qh); q /= (unsigned)d.Qh;
+        qt = (int)(q % (unsigned)d.Qt); q /= (unsigned)d.Qt;
+        n_i = (int)q;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&ps->empty[stage], phase ^ 1, 11);
+        const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
+        const uint32_t b_st = a_st + kATileBytes;
+        mbar_arrive_expect_tx(&ps->full[stage], tx);
+        const int gw = qw * d.sg_w + lo_w, gh = qh * d.sg_h + lo_h, gt = qt * d.sg_t + lo_t;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (sub_ok[h])
+            tma_im2col_5d(a_st + h * 8192, &maps.g, &ps->full[stage], sub_c[h], gw, gh, gt, n_i, sub_ow[h], sub_oh[h], sub_ot[h]);
+        for (int j = 0; j < nb; ++j)
+          tma_im2col_5d(b_st + j * 8192, &maps.p, &ps->full[stage], n0 + j * 64, qw * d.sp_w + d.pp_w, qh * d.sp_h + d.pp_h,
+                        qt * d.sp_t + d.pp_t, n_i, 0, 0, 0);
+        qw += kBlockK;
+        while (qw >= d.Qw) {
+          qw -= d.Qw;
+          if (++qh == d.Qh) {
+            qh = 0;
+            if (++qt == d.Qt) {
+              qt = 0;
+              ++n_i;
+            }
+          }
+        }
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // gather producers: thread -> position row r (0..63) and half (0/1) of the chunk columns
     const int r = tid & 63;
     const int half = tid >> 6;
     // fixed (tap, channel) of this thread's 8 A chunks
@@ -566,7 +638,8 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
       if (first < 0) first = 0;
       for (int i = first; i < nkb; ++i) mbar_arrive(&ps->full[i % stages]);
     }
-
+  }
+  if (warp < 4) {
     // epilogue: TMEM lane = (tap,gc) column mk0 + tid ; columns = p channels
     mbar_wait(&ps->accum, 0, 13);
     tc_fence_after();
@@ -695,8 +768,8 @@ int encode_im2col_map(CUtensorMap* map, const bf16* base, int C, long long row_s
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return b2c_fail(-3, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
   // CUTLASS (copy_traits_sm90_im2col.hpp) clears this descriptor bit for tensors < 128 KiB on drivers <= 13.1
-  int drv = 0;
-  cudaDriverGetVersion(&drv);
+  static int drv = -1;
+  if (drv < 0) cudaDriverGetVersion(&drv);
   const unsigned long long bytes = (unsigned long long)row_stride * 2ull * W * H * T * N;
   if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
   return 0;
@@ -728,8 +801,11 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_fprop: bn_tile=%d invalid", d.bn_tile);
   long long total_tiles = 0;
   int sum_taps = 0;
+  TileSched ts;
+  memset(&ts, 0, sizeof(ts));
   const int n_tiles = (d.Cout + d.bn_tile - 1) / d.bn_tile;
   for (int i = 0; i < d.nclass; ++i) {
+    ts.start[i] = (unsigned)total_tiles;
     const b2c_conv_class& c = d.cls[i];
     B2C_REQUIRE(c.taps && c.w && c.ntaps > 0, "conv_fprop: class %d incomplete", i);
     B2C_REQUIRE(((uintptr_t)c.w & 15) == 0, "conv_fprop: weights must be 16B aligned");
@@ -738,6 +814,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
     total_tiles += ((m + kTileM - 1) / kTileM) * n_tiles;
     sum_taps += c.ntaps;
   }
+  for (int i = d.nclass; i < 9; ++i) ts.start[i] = (unsigned)total_tiles;
+  B2C_REQUIRE(total_tiles < (1LL << 31), "conv_fprop: too many tiles");
   if (total_tiles == 0) return 0;
   const int acc_cols = (d.bn_tile + 15) & ~15;
   const int stage_bytes = kATileBytes + (((acc_cols * 128) + 1023) & ~1023);
@@ -766,8 +844,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   }
   long long grid = b2c_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, stages, lag, total_tiles,
-                                                                                    n_tiles);
+  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, ts, use_tma, stages, lag,
+                                                                                    total_tiles, n_tiles);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_fprop launch");
   return 0;
@@ -821,8 +899,28 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
     if (e != cudaSuccess) return b2c_cuda_check(e, "conv_wgrad: cudaFuncSetAttribute");
     configured = true;
   }
+  // TMA path: both operands 64-channel aligned; min tap offsets = lower corner of the im2col box
+  WgradMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int lo[3] = {0, 0, 0};
+  const int use_tma = (d.Cg % kBlockK == 0 && d.Cp % kBlockK == 0 && d.taps_host != nullptr) ? 1 : 0;
+  if (use_tma) {
+    for (int k = 0; k < 3; ++k) lo[k] = 127;
+    for (int i = 0; i < d.ntaps; ++i) {
+      const int32_t tv = d.taps_host[i];
+      const int v[3] = {(int)(int8_t)(tv & 0xff), (int)(int8_t)((tv >> 8) & 0xff), (int)(int8_t)((tv >> 16) & 0xff)};
+      for (int k = 0; k < 3; ++k)
+        if (v[k] < lo[k]) lo[k] = v[k];
+    }
+    int rc = encode_im2col_map(&maps.g, reinterpret_cast<const bf16*>(d.g) + d.g_c_off, d.Cg, d.g_row_stride, d.N, d.Tg, d.Hg, d.Wg,
+                               lo[0], lo[1], lo[2], d.Qt, d.Qh, d.Qw, d.sg_t, d.sg_h, d.sg_w, kBlockK, kBlockK);
+    if (rc) return rc;
+    rc = encode_im2col_map(&maps.p, reinterpret_cast<const bf16*>(d.p) + d.p_c_off, d.Cp, d.p_row_stride, d.N, d.Tp, d.Hp, d.Wp,
+                           d.pp_t, d.pp_h, d.pp_w, d.Qt, d.Qh, d.Qw, d.sp_t, d.sp_h, d.sp_w, kBlockK, kBlockK);
+    if (rc) return rc;
+  }
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)nsplit);
-  igemm_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, stages, lag, nsplit);
+  igemm_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_wgrad launch");
   return 0;
