@@ -113,6 +113,12 @@ int b2c_ncdhw_to_ndhwc(const float* in, void* out, int32_t N, int32_t C, int64_t
 int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_t in_c_off, float* out, int32_t N, int32_t C,
                            int64_t THW, b2c_stream_t s);
 
+/* Explicit im2col for the few-channel stem (Conv3d_1a_7x7, pytorch_i3d.py:224): x channels-last bf16 (N,T,H,W,Cs) with C
+ * real channels -> out (N*To*Ho*Wo, Kpad) bf16, column = tap*C + c, zero padded to Kpad (multiple of 64). */
+int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, int32_t C, int32_t T, int32_t H, int32_t W, int32_t To,
+                     int32_t Ho, int32_t Wo, int32_t kt, int32_t kh, int32_t kw, int32_t st, int32_t sh, int32_t sw, int32_t pt,
+                     int32_t ph, int32_t pw, int32_t Kpad, b2c_stream_t s);
+
 /* BatchNorm3d training statistics (pytorch_i3d.py:80,117).  groups: rows are split evenly into
  * `groups` contiguous segments with independent statistics (two forward passes batched).
  * _sums: ws fp32 [groups][2][C] (zeroed by the caller) += per-channel sum / sum of squares.

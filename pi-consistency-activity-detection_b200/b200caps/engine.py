@@ -130,20 +130,81 @@ class ConvLayer:
         return pl
 
 
+class StemLayer(ConvLayer):
+    """Few-input-channel convolution (the RGB 7x7x7 stem) = explicit im2col (bandwidth kernel) + the TMA GEMM path as
+    a 1x1x1 convolution over K = taps*Cin columns (zero padded to a multiple of 64)."""
+
+    def __init__(self, weight, cin, cout, k, stride):
+        self.weight, self.cin, self.cout, self.k, self.stride = weight, cin, cout, tuple(k), tuple(stride)
+        self.taps = k[0] * k[1] * k[2]
+        self.K = self.taps * cin
+        self.Kpad = (self.K + 63) // 64 * 64
+        self.plans, self.keys = {}, {}
+        self._wtap = None
+
+    def geometry(self, in_dims):
+        pads = [same_pad(d, kk, ss) for d, kk, ss in zip(in_dims, self.k, self.stride)]
+        od = tuple((d + p[0] + p[1] - kk) // ss + 1 for d, p, kk, ss in zip(in_dims, pads, self.k, self.stride))
+        return od, tuple(p[0] for p in pads)
+
+    def im2col(self, x: View) -> torch.Tensor:
+        od, pf = self.geometry(x.dims)
+        col = torch.empty((x.N,) + od + (self.Kpad,), dtype=torch.bfloat16, device=x.t.device)
+        ops.im2col_small(x, col, self.cin, od, self.k, self.stride, pf, self.Kpad)
+        return col
+
+    def plan(self, col_dims) -> ConvPlan:
+        col_dims = tuple(int(v) for v in col_dims)
+        pl = self.plans.get(col_dims)
+        if pl is None:
+            pl = ConvPlan(ConvSpec(self.Kpad, self.cout, (1, 1, 1)), col_dims)
+            pl.wgrad_geom.update(s_p=self.Kpad, s_g=1, Cg_real=self.K)    # wgrad lands in a (Cout, Kpad) scratch
+            self.plans[col_dims] = pl
+        return pl.to(self.weight.device)
+
+    def packed(self, col_dims, which: str) -> ConvPlan:
+        assert which == "fprop", "the stem input needs no gradient"
+        col_dims = tuple(int(v) for v in col_dims)
+        pl = self.plan(col_dims)
+        w = self.weight
+        key = (w.data_ptr(), w._version, STATE.weights_epoch)
+        if self.keys.get(col_dims) != key:
+            from .plans import packed_geometry
+            cl = pl.fprop[0]
+            bn, _, nkb, elems = packed_geometry(self.cout, self.Kpad)
+            if cl.packed is None:
+                cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=w.device)
+                self._wtap = torch.arange(self.taps, dtype=torch.int32, device=w.device)
+            # k = tap*cin + c  <-  w[co][c][tap]
+            ops.pack_part(w.detach(), cl.packed, self._wtap, self.cout, self.taps, self.cin, self.cin, self.cin * self.taps,
+                          self.taps, self.cin, 0, 0, bn, nkb)
+            self.keys[col_dims] = key
+        return pl
+
+    def scatter_wgrad(self, scratch: torch.Tensor, dw: torch.Tensor):
+        """(Cout, Kpad) scratch with column tap*cin + c  ->  += into dw (Cout, cin, kt, kh, kw)."""
+        g = scratch[:, :self.K].view(self.cout, self.taps, self.cin).permute(0, 2, 1).reshape(dw.shape)
+        dw.add_(g)
+
+
 # ---- primitives (no autograd) -----------------------------------------------------------------------
 class UnitSaved:
-    __slots__ = ("raw", "mean", "rstd", "groups", "dims")
+    __slots__ = ("raw", "mean", "rstd", "groups", "dims", "col")
 
 
 def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: bool, groups: int) -> UnitSaved:
     """Unit3D (pytorch_i3d.py:89-120): same-pad conv (tcgen05) -> BatchNorm3d -> ReLU, written into `y`."""
+    col = None
+    if isinstance(layer, StemLayer):
+        col = layer.im2col(x)
+        x = View(col)
     pl = layer.packed(x.dims, "fprop")
     N = x.N
     Cout = pl.spec.Cout_pad
     raw = torch.empty((N,) + tuple(pl.out_dims) + (Cout,), dtype=torch.bfloat16, device=x.t.device)
     ops.conv_fprop(pl, "fprop", x, View(raw))
     sv = UnitSaved()
-    sv.raw, sv.dims = raw, x.dims
+    sv.raw, sv.dims, sv.col = raw, x.dims, col
     rv_ = View(raw)
     if training:
         g = groups
@@ -174,11 +235,17 @@ def unit_bwd(layer: ConvLayer, gamma, beta, sv: UnitSaved, x: View, y: View, gy:
     dgamma, d1 = grad_buf(gamma)
     dbeta, d2 = grad_buf(beta)
     ops.bn_relu_bwd_apply(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
+    dw, d0 = grad_buf(layer.weight)
+    if isinstance(layer, StemLayer):
+        assert dx is None, "the few-channel stem does not propagate a gradient to its input"
+        scratch = torch.zeros((layer.cout, layer.Kpad), dtype=torch.float32, device=dev)
+        ops.conv_wgrad(layer.plan(sv.dims), View(sv.col), View(draw), scratch, atomic=True)
+        layer.scatter_wgrad(scratch, dw)
+        return (None if d0 else dw), (None if d1 else dgamma), (None if d2 else dbeta)
     if dx is not None:
         pl = layer.packed(sv.dims, "dgrad")
         ops.conv_fprop(pl, "dgrad", View(draw), dx, accumulate=accumulate)
     pl = layer.plan(sv.dims)
-    dw, d0 = grad_buf(layer.weight)
     ops.conv_wgrad(pl, x, View(draw), dw, atomic=True)
     return (None if d0 else dw), (None if d1 else dgamma), (None if d2 else dbeta)
 
@@ -226,9 +293,12 @@ class Unit3DFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_cl, weight, gamma, beta, mod):
         layer = mod._layer
-        pl = layer.plan(x_cl.shape[1:4])
-        y = torch.empty((x_cl.shape[0],) + tuple(pl.out_dims) + (pl.spec.Cout_pad,), dtype=torch.bfloat16,
-                        device=x_cl.device)
+        if isinstance(layer, StemLayer):
+            od, cpad = layer.geometry(tuple(x_cl.shape[1:4]))[0], layer.cout
+        else:
+            pl = layer.plan(x_cl.shape[1:4])
+            od, cpad = tuple(pl.out_dims), pl.spec.Cout_pad
+        y = torch.empty((x_cl.shape[0],) + od + (cpad,), dtype=torch.bfloat16, device=x_cl.device)
         training = mod.training
         sv = unit_fwd(layer, gamma, beta, mod.bn.running_mean, mod.bn.running_var, View(x_cl), View(y), training,
                       STATE.bn_groups if training else 1)
@@ -243,7 +313,7 @@ class Unit3DFn(torch.autograd.Function):
         if not ctx.training:
             raise RuntimeError("b200caps: backward through eval-mode BatchNorm is not supported")
         gy = grad_cl(gy)
-        need_dx = ctx.needs_input_grad[0]
+        need_dx = ctx.needs_input_grad[0] and not isinstance(ctx.mod._layer, StemLayer)
         dx = torch.empty_like(ctx.x) if need_dx else None
         dw, dg, db = unit_bwd(ctx.mod._layer, ctx.gamma, ctx.mod.bn.bias, ctx.sv, View(ctx.x), View(ctx.y), View(gy),
                               View(dx) if need_dx else None, False)

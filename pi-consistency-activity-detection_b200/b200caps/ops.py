@@ -77,6 +77,10 @@ def cl_to_ncdhw_f32(v: View) -> torch.Tensor:
     return out
 
 
+def im2col_small(x: View, out: torch.Tensor, C, out_dims, k, s, pf, Kpad):
+    _abi.call("b2c_im2col_small", x.ptr, _p(out), x.N, x.row_stride, C, *x.dims, *out_dims, *k, *s, *pf, Kpad, stream())
+
+
 # ---- batch norm -----------------------------------------------------------------------------
 def bn_sums(x: View, groups: int, ws: torch.Tensor):
     _abi.call("b2c_bn_sums", x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(ws), stream())

@@ -525,6 +525,52 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
   }
 }
 
+// Explicit im2col for convolutions with very few input channels (the 7x7x7 stride-2 RGB stem): the implicit-GEMM
+// gather would issue one 16-byte load per (row, tap) for 6 useful bytes.  out[(n,to,ho,wo)][tap*C + c] (bf16, zero
+// padded to Kpad, a multiple of 64) is then consumed by the TMA GEMM path as a 1x1x1 convolution with Cin = Kpad.
+struct Im2colGeom {
+  int N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad;
+};
+__global__ void __launch_bounds__(kBlock) im2col_small_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Im2colGeom G) {
+  extern __shared__ int s_lut[];   // per k: dt | dh<<8 | dw<<16 | c<<24 ; -1 = padding column
+  for (int k = threadIdx.x; k < G.Kpad; k += blockDim.x) {
+    int v = -1;
+    if (k < G.K) {
+      const int tap = k / G.C, c = k - tap * G.C;
+      const int a = tap / (G.kh * G.kw), r = tap - a * G.kh * G.kw;
+      const int b = r / G.kw, cc = r - b * G.kw;
+      v = a | (b << 8) | (cc << 16) | (c << 24);
+    }
+    s_lut[k] = v;
+  }
+  __syncthreads();
+  const int chunks = G.Kpad / 8;
+  const long long total = (long long)G.N * G.To * G.Ho * G.Wo * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    long long row = i / chunks;
+    const long long orow = row;
+    const int wo = (int)(row % G.Wo); row /= G.Wo;
+    const int ho = (int)(row % G.Ho); row /= G.Ho;
+    const int to = (int)(row % G.To); row /= G.To;
+    const int n = (int)row;
+    const int t0 = to * G.st - G.pt, h0 = ho * G.sh - G.ph, w0 = wo * G.sw - G.pw;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int l = s_lut[ch * 8 + e];
+      float val = 0.f;
+      if (l >= 0) {
+        const int t = t0 + (l & 0xff), h = h0 + ((l >> 8) & 0xff), w = w0 + ((l >> 16) & 0xff), c = (l >> 24) & 0xff;
+        if ((unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H && (unsigned)w < (unsigned)G.W)
+          val = __bfloat162float(x[((((long long)n * G.T + t) * G.H + h) * G.W + w) * G.Cs + c]);
+      }
+      v[e] = val;
+    }
+    st16(out + orow * G.Kpad + ch * 8, pack8(v));
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -738,5 +784,19 @@ B2C_API int b2c_fill_f32(float* p, int64_t n, float v, b2c_stream_t s) {
   fill_f32_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)s>>>(p, n, v);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("fill_f32");
+  return 0;
+}
+
+B2C_API int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, int32_t C, int32_t T, int32_t H, int32_t W, int32_t To,
+                             int32_t Ho, int32_t Wo, int32_t kt, int32_t kh, int32_t kw, int32_t st, int32_t sh, int32_t sw,
+                             int32_t pt, int32_t ph, int32_t pw, int32_t Kpad, b2c_stream_t s) {
+  B2C_REQUIRE(x && out && N > 0 && C > 0 && C <= Cs && C < 256, "im2col_small: bad args");
+  const int K = kt * kh * kw * C;
+  B2C_REQUIRE(Kpad % 64 == 0 && Kpad >= K && kt < 256 && kh < 256 && kw < 256 && Kpad * 4 <= 48 * 1024, "im2col_small: bad K");
+  Im2colGeom G{N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad};
+  const long long total = (long long)N * To * Ho * Wo * (Kpad / 8);
+  im2col_small_kernel<<<grid_for(total, kBlock, 16), kBlock, Kpad * sizeof(int), (cudaStream_t)s>>>((const bf16*)x, (bf16*)out, G);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("im2col_small");
   return 0;
 }

@@ -368,12 +368,16 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
           if (col >= d.Cout) break;
           float* vv = v + h * 8;
           if (d.bias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] += __ldg(d.bias + col + i);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(d.bias + col + 4));
+            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
           }
           if (scale_row) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] *= __ldg(scale_row + col + i);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_row + col));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale_row + col + 4));
+            vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
+            vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
           }
           if (d.relu) {
 #pragma unroll

@@ -66,7 +66,10 @@ class Unit3D(nn.Module):
                 pads = [same_pad(d, kk, ss) for d, kk, ss in zip(dims, k, s)]
                 return ConvSpec(cin, cout, k, s, tuple(p[0] for p in pads), tuple(p[1] for p in pads))
 
-            lc = engine.ConvLayer(self.conv3d.weight, spec_fn)
+            if cin < 8 and k[0] * k[1] * k[2] > 1:
+                lc = engine.StemLayer(self.conv3d.weight, cin, cout, k, s)   # RGB stem: explicit im2col + TMA GEMM
+            else:
+                lc = engine.ConvLayer(self.conv3d.weight, spec_fn)
             self.__dict__["_layer_cache"] = lc
         return lc
 
