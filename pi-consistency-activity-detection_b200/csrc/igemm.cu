@@ -112,7 +112,8 @@ __device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass,
 __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d,
                                                                        const __grid_constant__ TmaMaps maps,
                                                                        const __grid_constant__ TileSched ts, int use_tma,
-                                                                       int stages, int lag, long long total_tiles, int n_tiles) {
+                                                                       int stages, int lag, long long total_tiles, int n_tiles,
+                                                                       int sum_taps) {
   const int acc_cols = (d.bn_tile + 15) & ~15;                     // TMEM columns per accumulator
   const int b_tile_bytes = ((acc_cols * 128) + 1023) & ~1023;      // packed weight tile (layer-wide bn_tile)
   const int stage_bytes = kATileBytes + b_tile_bytes;
@@ -122,6 +123,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   FpropSmem* ps = reinterpret_cast<FpropSmem*>(smem_al + (size_t)stages * stage_bytes);
   int32_t* s_taps = reinterpret_cast<int32_t*>(ps + 1);            // all classes back to back
+  // epilogue staging (bf16 rows, pitch acc_cols*2 + 16 bytes: conflict-free 16-byte shared stores), after the tap tables
+  const uint32_t stg_pitch = (uint32_t)(acc_cols * 2 + 16);
+  const uint32_t stg_base = (smem_base + (uint32_t)stages * stage_bytes + (uint32_t)sizeof(FpropSmem) + (uint32_t)sum_taps * 4 + 15u) & ~15u;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   } else {
     // ------------------------------ epilogue (warps 5..8) ---------------------------
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const bool staged = (d.out_fp32 == 0 && !d.accumulate);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -355,6 +360,59 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       mbar_wait(&ps->tfull[acc], acc_phase, 3);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
+      if (staged) {
+        // bf16 row output: registers -> padded smem row -> ONE bulk async store per row (full 128-byte lines instead of
+        // 32 partial sectors per store instruction; ncu r01: 32 sectors/request, epilogue-bound short-K tiles)
+        const uint32_t srow = stg_base + (uint32_t)(quarter * 32 + lane) * stg_pitch;
+        bulk_wait_read0();   // this thread's previous row has left shared memory
+        for (int c0 = 0; c0 < bn16; c0 += 32) {
+          float v[32];
+          const int nh = (bn16 - c0 >= 32) ? 4 : 2;
+          if (nh == 4) tmem_ld32(t_lane + (uint32_t)c0, v);
+          else tmem_ld16(t_lane + (uint32_t)c0, v);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h >= nh) break;
+            const int col = n0 + c0 + h * 8;
+            if (col >= d.Cout) break;
+            float* vv = v + h * 8;
+            if (d.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(d.bias + col + 4));
+              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+            }
+            if (scale_row) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_row + col));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale_row + col + 4));
+              vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
+              vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
+            }
+            if (d.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+            }
+            if (d.sigmoid_from >= 0 && col >= d.sigmoid_from) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
+            }
+            st_shared16(srow + (uint32_t)(c0 + h * 8) * 2, pack8(vv));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&ps->tempty[acc]);       // accumulator drained: the MMA warp may start the tile after next
+        fence_proxy_async_smem();
+        if (mvalid) {
+          bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + n0;
+          int ncols = d.Cout - n0;
+          if (ncols > bn) ncols = bn;
+          bulk_s2g(o, srow, (uint32_t)ncols * 2);
+        }
+        bulk_commit();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       for (int c0 = 0; c0 < bn16; c0 += 32) {
         float v[32];
         const int nh = (bn16 - c0 >= 32) ? 4 : 2;
@@ -423,6 +481,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    bulk_wait0();   // all bulk stores of this thread have completed before the CTA retires
   }
   __syncthreads();
   if (warp == 4) {
@@ -823,12 +882,14 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   if (total_tiles == 0) return 0;
   const int acc_cols = (d.bn_tile + 15) & ~15;
   const int stage_bytes = kATileBytes + (((acc_cols * 128) + 1023) & ~1023);
-  int stages = (200 * 1024) / stage_bytes;
+  const int staging = kTileM * (acc_cols * 2 + 16) + 16;
+  const int fixed = (int)sizeof(FpropSmem) + sum_taps * 4 + staging + 1024 + 64;
+  int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B2C_REQUIRE(stages >= 3, "conv_fprop: tile too large for shared memory");
   int lag = stages - 2;
   if (lag > 6) lag = 6;
-  const size_t smem = (size_t)stages * stage_bytes + sizeof(FpropSmem) + (size_t)sum_taps * 4 + 1024 + 64;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
@@ -849,7 +910,7 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   long long grid = b2c_num_sms();
   if (grid > total_tiles) grid = total_tiles;
   igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, ts, use_tma, stages, lag,
-                                                                                    total_tiles, n_tiles);
+                                                                                    total_tiles, n_tiles, sum_taps);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_fprop launch");
   return 0;
