@@ -242,8 +242,9 @@ int b2c_cons_grad(const float* out, const float* flp, const float* w1, const flo
 /* ------------------------------------------------------------------------------------
  * Optimiser: Adam(lr, betas, eps=1e-6, wd=0) over one flat fp32 buffer (main_ucf101.py:416,184)
  * ---------------------------------------------------------------------------------- */
+/* step_dev: device int32 step counter, incremented by the call (graph replayable bias correction) */
 int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                  int32_t step, float grad_scale, b2c_stream_t s);
+                  int32_t* step_dev, float grad_scale, b2c_stream_t s);
 
 /* generic helpers */
 int b2c_fill_f32(float* p, int64_t n, float v, b2c_stream_t s);

@@ -75,7 +75,7 @@ _SIGS = {
     "b2c_cons_reduce": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "b2c_cons_finish": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp],
     "b2c_cons_grad": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, vp],
-    "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
+    "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp],
     "b2c_fill_f32": [vp, i64, f32, vp],
 }
 

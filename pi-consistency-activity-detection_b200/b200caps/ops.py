@@ -210,8 +210,9 @@ def cons_grad(out, flp, w1, w2, wg, dout, dflp, P, H, W, mirror, w2_tflip, a_l2,
               int(w2_tflip), float(a_l2), float(a_lv), float(a_lg), stream())
 
 
-def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale=1.0):
-    _abi.call("b2c_adam_step", _p(p), _p(g), _p(m), _p(v), n, float(lr), float(beta1), float(beta2), float(eps), int(step),
+def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
+    """step_dev: int32 device tensor holding the number of steps taken so far (incremented by the call)."""
+    _abi.call("b2c_adam_step", _p(p), _p(g), _p(m), _p(v), n, float(lr), float(beta1), float(beta2), float(eps), _p(step_dev),
               float(grad_scale), stream())
 
 

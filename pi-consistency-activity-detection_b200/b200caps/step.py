@@ -85,22 +85,29 @@ class FlatParams:
 
 
 class TrainStep:
+    """Eager:   step = TrainStep(model, args); out = step(data, fl_data, action, seg, labels_host)
+    Graphed: step.capture(P, labels_host); out = step.replay(data, fl_data, action, seg)  (one cudaGraphLaunch per step)"""
+
     def __init__(self, model: torch.nn.Module, args: StepArgs = StepArgs(), process_group=None):
         self.model = model
         self.args = args
         self.flat = FlatParams(model)
-        self.step_count = 0
+        dev = self.flat.data.device
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # Adam step counter (device: graph replayable)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
         self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
         # bucket boundary: encoder (conv1.*) parameters come first in registration order; everything after the
         # encoder is complete once the capsule head has back-propagated, i.e. before the encoder backward starts.
         enc_end = 0
+        named = dict(model.named_parameters())
         for k, o in self.flat.offsets.items():
             if k.startswith("conv1."):
-                enc_end = max(enc_end, o + dict(model.named_parameters())[k].numel())
+                enc_end = max(enc_end, o + named[k].numel())
         self.enc_end = (enc_end + 3) // 4 * 4
-        self._bucket_event = None
+        self.graph = None
+        self.static = None
+        self.launches_per_step = None
 
     # ---- multi-GPU: gradient all-reduce overlapped with the encoder backward --------------------------
     def _allreduce_async(self, lo: int, hi: int):
@@ -110,25 +117,71 @@ class TrainStep:
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
 
+    @staticmethod
+    def _label_tensors(labels_host, dev):
+        labels_host = torch.as_tensor(labels_host).float().cpu()
+        lab_idx = torch.nonzero(labels_host == 1).view(-1).to(torch.int32)
+        return lab_idx.to(dev), labels_host.to(dev), int(lab_idx.numel())
+
     def __call__(self, data, fl_data, action, seg, labels_host, epoch: int = 1):
         """data / fl_data (P,3,8,H,W) fp32 CUDA, action (P,1) CUDA, seg (P,1,8,H,W) fp32 CUDA, labels_host: CPU tensor /
         list with 1 = labeled.  Returns dict of device scalars (total, loc, cls, cons) and the step's outputs."""
-        a, model, flat = self.args, self.model, self.flat
         engine.require_cuda(data, "data")
+        lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, data.device)
+        return self._impl(data, fl_data, action, seg, lab_idx, labels_dev, n_lab, epoch)
+
+    # ---- CUDA graph ------------------------------------------------------------------------------------
+    def capture(self, P: int, labels_host, epoch: int = 1, T: int = 8, H: int = 224, W: int = 224, warmup: int = 3,
+                init_batch=None):
+        """Capture the whole step (both passes, losses, backward, all-reduce, Adam, weight re-packing) into one CUDA
+        graph with static input buffers.  The labeled/unlabeled pattern and the epoch are baked into the graph.
+        NOTE: `warmup` REAL optimisation steps are taken on `init_batch` (data, fl_data, action, seg) before the
+        capture (they size the allocator pools and build the kernel plans)."""
+        dev = self.flat.data.device
+        st = dict(data=torch.rand((P, 3, T, H, W), device=dev), fl_data=torch.rand((P, 3, T, H, W), device=dev),
+                  action=torch.zeros((P, 1), device=dev), seg=torch.zeros((P, 1, T, H, W), device=dev))
+        if init_batch is not None:
+            for k, v in zip(("data", "fl_data", "action", "seg"), init_batch):
+                st[k].copy_(v)
+        lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):      # plans, packed-weight buffers, kernel attributes, allocator pools
+                self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _abi
+        l0 = _abi.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+        self.launches_per_step = _abi.launch_count() - l0
+        self.graph, self.static, self.static_out = g, st, out
+        return self
+
+    def replay(self, data=None, fl_data=None, action=None, seg=None):
+        """Copy the (host or device) inputs into the static buffers on the current stream and launch the graph."""
+        st = self.static
+        for k, v in (("data", data), ("fl_data", fl_data), ("action", action), ("seg", seg)):
+            if v is not None:
+                st[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+    # ---- the step ------------------------------------------------------------------------------------------
+    def _impl(self, data, fl_data, action, seg, lab_idx, labels_dev, n_lab: int, epoch: int):
+        a, model, flat = self.args, self.model, self.flat
         P = data.shape[0]
         H, W = data.shape[-2], data.shape[-1]
         dev = data.device
-        labels_host = torch.as_tensor(labels_host).float().cpu()
-        lab_idx_host = torch.nonzero(labels_host == 1).view(-1).to(torch.int32)
-        n_lab = int(lab_idx_host.numel())
-        lab_idx = lab_idx_host.to(dev, non_blocking=True)
-        labels_dev = labels_host.to(dev, non_blocking=True)
         wt_ramp = exp_rampup(a.rampup_epochs, epoch)
 
         model.train()
         flat.zero_grad()
         engine.STATE.direct_grads = True
         engine.STATE.bn_groups = 2
+        hook = None
         try:
             # both passes as one batch: [clips ; flipped clips]
             x_cl = torch.empty((2 * P, data.shape[2], H, W, 8), dtype=torch.bfloat16, device=dev)
@@ -138,7 +191,6 @@ class TrainStep:
             cls2 = torch.cat([action, action]).to(dev)
             lab2 = torch.cat([labels_dev, labels_dev])
             xe, c56, c112, drop2 = model._encode(img)
-            hook = None
             if self.world > 1:
                 # everything after the encoder (84 % of the parameters, incl. the 138 MB PrimaryCaps weight) is final
                 # when the gradient w.r.t. the encoder output has been formed -> all-reduce it under the encoder bwd
@@ -200,9 +252,7 @@ class TrainStep:
         if self.world > 1:
             self._allreduce_async(0, self.enc_end)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
-        self.step_count += 1
-        ops.adam_step(flat.data, flat.grad, flat.m, flat.v, flat.n, a.lr, 0.9, 0.999, 1e-6, self.step_count,
-                      1.0 / self.world)
+        ops.adam_step(flat.data, flat.grad, flat.m, flat.v, flat.n, a.lr, 0.9, 0.999, 1e-6, self.step_dev, 1.0 / self.world)
         engine.bump_weights_epoch()
         loc = l_seg[0] + l_seg[1]
         total = a.wt_loc * loc + a.wt_cls * l_cls[0] + a.wt_cons * l_cons[0]

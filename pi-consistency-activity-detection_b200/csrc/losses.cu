@@ -478,11 +478,17 @@ B2C_API int b2c_cons_grad(const float* out, const float* flp, const float* w1, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Adam (torch.optim.Adam semantics, main_ucf101.py:416: betas (0.9, 0.999), eps 1e-6, no weight decay)
+// Adam (torch.optim.Adam semantics, main_ucf101.py:416: betas (0.9, 0.999), eps 1e-6, no weight decay).
+// The step counter lives in device memory so the launch is CUDA-graph replayable.
 namespace {
+__global__ void adam_tick_kernel(int* step) { step[0] += 1; }
 __global__ void __launch_bounds__(kBlock) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                       float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                                      float bc1, float bc2_sqrt, float gscale) {
+                                                      const int* __restrict__ step_ptr, float gscale) {
+  const int step = step_ptr[0];
+  const float bc1 = 1.f - powf(b1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
+  const float step_size = lr / bc1;
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n4; i += (long long)gridDim.x * kBlock) {
     float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
@@ -494,7 +500,7 @@ __global__ void __launch_bounds__(kBlock) adam_kernel(float* __restrict__ p, con
       ms[q] = b1 * ms[q] + (1.f - b1) * gs[q];
       vs[q] = b2 * vs[q] + (1.f - b2) * gs[q] * gs[q];
       const float denom = sqrtf(vs[q]) / bc2_sqrt + eps;
-      ps[q] -= (lr / bc1) * (ms[q] / denom);
+      ps[q] -= step_size * (ms[q] / denom);
     }
     reinterpret_cast<float4*>(p)[i] = make_float4(ps[0], ps[1], ps[2], ps[3]);
     reinterpret_cast<float4*>(m)[i] = make_float4(ms[0], ms[1], ms[2], ms[3]);
@@ -505,21 +511,20 @@ __global__ void __launch_bounds__(kBlock) adam_kernel(float* __restrict__ p, con
       const float gg = g[i] * gscale;
       m[i] = b1 * m[i] + (1.f - b1) * gg;
       v[i] = b2 * v[i] + (1.f - b2) * gg * gg;
-      p[i] -= (lr / bc1) * (m[i] / (sqrtf(v[i]) / bc2_sqrt + eps));
+      p[i] -= step_size * (m[i] / (sqrtf(v[i]) / bc2_sqrt + eps));
     }
   }
 }
 }  // namespace
 
 B2C_API int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                          int32_t step, float grad_scale, b2c_stream_t s) {
-  B2C_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adam_step: bad args");
+                          int32_t* step_dev, float grad_scale, b2c_stream_t s) {
+  B2C_REQUIRE(p && g && m && v && step_dev && n > 0, "adam_step: bad args");
   B2C_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0,
               "adam_step: buffers must be 16B aligned");
-  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-  const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
-  adam_kernel<<<blocks_for(n, 4), kBlock, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
-  b2c_launches_add(1);
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
+  adam_kernel<<<blocks_for(n, 4), kBlock, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale);
+  b2c_launches_add(2);
   B2C_LAUNCH_CHECK("adam_step");
   return 0;
 }

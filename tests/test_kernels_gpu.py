@@ -223,9 +223,11 @@ def test_adam_matches_torch():
     ref = p.clone().requires_grad_(True)
     opt = torch.optim.Adam([ref], lr=1e-3, eps=1e-6)
     m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step_dev = torch.zeros(1, dtype=torch.int32, device=dev())
     for step in range(1, 4):
         g = torch.randn(n, device=dev())
         ref.grad = g.clone()
         opt.step()
-        ops.adam_step(p, g, m, v, n, 1e-3, 0.9, 0.999, 1e-6, step)
-    assert rel(p, ref.detach()) < 1e-6
+        ops.adam_step(p, g, m, v, n, 1e-3, 0.9, 0.999, 1e-6, step_dev)
+    assert int(step_dev) == 3
+    assert rel(p, ref.detach()) < 1e-5
