@@ -174,12 +174,21 @@ def test_train_mode_segment_parity(setup):
     w_a = torch.randn(act.shape, generator=g, dtype=torch.float64)
     w_f = torch.randn(feat.shape, generator=g, dtype=torch.float64) / 400
     dec_names = [k for k in sd64 if sd64[k].requires_grad and not k.startswith(("conv1.", "primary_caps.", "conv_caps."))]
-    gref = torch.autograd.grad((o_ref * w_o).sum() + (a_ref * w_a).sum() + (f_ref * w_f).sum(),
+    gref_exact = torch.autograd.grad((o_ref * w_o).sum() + (a_ref * w_a).sum() + (f_ref * w_f).sum(),
+                                     [sd64[k] for k in dec_names] + [rout_in])
+    # gradient yardstick = oracle with the same bf16 rounding points: at random init the gradients are noise-like sums,
+    # and a fraction f of ReLU masks flipped by bf16 rounding perturbs them by ~sqrt(f) (5-15 %) in the reference itself
+    with restate.emulate_bf16():
+        o_em, a_em, f_em = restate.decode(sd64, rout_in, _cl2ncdhw(x_cl)[:, :, 0], _cl2ncdhw(c56), _cl2ncdhw(c112),
+                                          b["action"], b["labels"], 1, 11, True, m64[1])
+    gref = torch.autograd.grad((o_em * w_o).sum() + (a_em * w_a).sum() + (f_em * w_f).sum(),
                                [sd64[k] for k in dec_names] + [rout_in])
     ((out * w_o.float().cuda()).sum() + (act * w_a.float().cuda()).sum() + (feat * w_f.float().cuda()).sum()).backward()
     errs = {k: rel(gp[k].grad, gr) for k, gr in zip(dec_names, gref[:-1])}
     errs["rout"] = rel(rout_leaf.grad, gref[-1])
-    print("decoder grads:", {k: f"{v:.1e}" for k, v in errs.items()})
+    errs_exact = {k: rel(gp[k].grad, gr) for k, gr in zip(dec_names, gref_exact[:-1])}
+    print("decoder grads vs oracle(bf16 roundings):", {k: f"{v:.1e}" for k, v in errs.items()})
+    print("decoder grads vs exact fp64 oracle      :", {k: f"{v:.1e}" for k, v in errs_exact.items()})
     assert max(errs.values()) < 3e-2, errs
 
     # ---- end to end, reported (not asserted at 2e-2: see docstring) -----------------------------------
@@ -232,18 +241,28 @@ def test_encoder_modules_fwd_bwd(setup, which):
     sd64 = {k: (v.double().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v)
             for k, v in sd.items() if k.startswith(prefix)}
     xr = x.double().requires_grad_(which != "stem")
-    yr = ref_fn(xr, sd64, restate.BNState(True))
-    e_fwd = rel(y.float(), yr.detach())
+    # yardstick: the oracle with the same bf16 rounding points (GEMM operands, stored conv output / activation);
+    # the exact fp64 oracle is printed next to it (ReLU masks flipped by bf16 rounding make noise-like gradients
+    # differ by ~sqrt(flipped fraction) in the reference itself)
+    with restate.emulate_bf16():
+        yr = ref_fn(xr, sd64, restate.BNState(True))
     w = torch.randn(yr.shape, generator=g, dtype=torch.float64)
     names = [k for k, v in sd64.items() if v.requires_grad]
-    gref = torch.autograd.grad((yr * w).sum(), [sd64[k] for k in names] + ([xr] if which != "stem" else []))
+    leaves = [sd64[k] for k in names] + ([xr] if which != "stem" else [])
+    gref = torch.autograd.grad((yr * w).sum(), leaves)
+    y_ex = ref_fn(xr, sd64, restate.BNState(True))
+    gex = torch.autograd.grad((y_ex * w).sum(), leaves)
+    e_fwd, e_fwd_ex = rel(y.float(), yr.detach()), rel(y.float(), y_ex.detach())
     (y.float() * w.float().cuda()).sum().backward()
     gp = dict(model.named_parameters())
     errs = {k: rel(gp[k].grad, gr) for k, gr in zip(names, gref)}
+    errs_ex = {k: rel(gp[k].grad, gr) for k, gr in zip(names, gex)}
     if which != "stem":
         errs["input"] = rel(xg.grad.float(), gref[-1])
-    worst = max(errs, key=errs.get)
-    print(f"{which}: fwd {e_fwd:.2e}; grads worst {worst} {errs[worst]:.2e}")
+        errs_ex["input"] = rel(xg.grad.float(), gex[-1])
+    worst, worst_ex = max(errs, key=errs.get), max(errs_ex, key=errs_ex.get)
+    print(f"{which}: fwd {e_fwd:.2e} (exact oracle {e_fwd_ex:.2e}); grads worst {worst} {errs[worst]:.2e} "
+          f"(exact oracle: {worst_ex} {errs_ex[worst_ex]:.2e})")
     model.load_state_dict(sd0)
-    assert e_fwd < 2e-2, e_fwd
-    assert errs[worst] < 4e-2, (worst, errs[worst])
+    assert e_fwd < 2e-2 and e_fwd_ex < 3e-2, (e_fwd, e_fwd_ex)
+    assert errs[worst] < 3e-2, (worst, errs[worst])
