@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import engine, ops
+from .plans import View
 
 
 @dataclass
@@ -171,36 +172,97 @@ class TrainStep:
 
     # ---- the step ------------------------------------------------------------------------------------------
     def _impl(self, data, fl_data, action, seg, lab_idx, labels_dev, n_lab: int, epoch: int):
+        """Hand-scheduled forward + backward: the model topology is fixed, so the step walks it explicitly and calls
+        the forward / backward halves of the engine functions directly (no autograd engine, no tape threads) -- which
+        also makes the whole step capturable in one CUDA graph."""
+        with torch.no_grad():
+            return self._impl_nograd(data, fl_data, action, seg, lab_idx, labels_dev, n_lab, epoch)
+
+    def _impl_nograd(self, data, fl_data, action, seg, lab_idx, labels_dev, n_lab: int, epoch: int):
         a, model, flat = self.args, self.model, self.flat
+        E = engine
         P = data.shape[0]
         H, W = data.shape[-2], data.shape[-1]
         dev = data.device
+        C = model.NUM_CLASSES
         wt_ramp = exp_rampup(a.rampup_epochs, epoch)
-
         model.train()
         flat.zero_grad()
-        engine.STATE.direct_grads = True
-        engine.STATE.bn_groups = 2
-        hook = None
+        E.STATE.direct_grads = True
+        E.STATE.bn_groups = 2
+        tape = []   # (backward closure) in forward order
         try:
-            # both passes as one batch: [clips ; flipped clips]
+            # ---------------- forward: both passes as one batch [clips ; flipped clips] ----------------
             x_cl = torch.empty((2 * P, data.shape[2], H, W, 8), dtype=torch.bfloat16, device=dev)
             ops.ncdhw_to_cl(data.contiguous(), 8, out=x_cl[:P])
             ops.ncdhw_to_cl(fl_data.contiguous(), 8, out=x_cl[P:])
-            img = engine.from_cl(x_cl)
+            i3d = model.conv1
+
+            def unit(mod, x, need_dx=True):
+                ctx = _Ctx((need_dx, True, True, True, False))
+                y = E.Unit3DFn.forward(ctx, x, mod.conv3d.weight, mod.bn.weight, mod.bn.bias, mod)
+                return y, (lambda g, ctx=ctx: E.Unit3DFn.backward(ctx, g)[0])
+
+            def pool(mod, x):
+                ctx = _Ctx((True, False, False))
+                y = E.MaxPoolFn.forward(ctx, x, tuple(mod.kernel_size), tuple(mod.stride))
+                return y, (lambda g, ctx=ctx: E.MaxPoolFn.backward(ctx, g)[0])
+
+            def incep(mod, x):
+                ctx = _Ctx((True,) + (False,) * 19)
+                params = []
+                for n in E.InceptionFn.UNITS:
+                    u = getattr(mod, n)
+                    params += [u.conv3d.weight, u.bn.weight, u.bn.bias]
+                y = E.InceptionFn.forward(ctx, x, mod, *params)
+                return y, (lambda g, ctx=ctx: E.InceptionFn.backward(ctx, g)[0])
+
+            y1, b_stem = unit(i3d.Conv3d_1a_7x7, x_cl, need_dx=False)          # cross112
+            p1, b_p1 = pool(i3d.MaxPool3d_2a_3x3, y1)
+            y2, b_2b = unit(i3d.Conv3d_2b_1x1, p1)
+            y3, b_2c = unit(i3d.Conv3d_2c_3x3, y2)                            # cross56
+            x, b_p2 = pool(i3d.MaxPool3d_3a_3x3, y3)
+            chain = []
+            for name in ("Mixed_3b", "Mixed_3c", "MaxPool3d_4a_3x3", "Mixed_4b", "Mixed_4c", "Mixed_4d", "Mixed_4e", "Mixed_4f"):
+                mod = getattr(i3d, name)
+                x, bw = pool(mod, x) if name.startswith("MaxPool") else incep(mod, x)
+                chain.append(bw)
+            N2 = x.shape[0]
+            drop1 = E.dropout_scale(N2, 832, dev)
+            drop2 = E.dropout_scale(N2, 128, dev)
+            ctx_d = _Ctx((True, False))
+            xe = E.ChannelScaleFn.forward(ctx_d, x, drop1)
+            pc = model.primary_caps
+            ctx_pc = _Ctx((True, True, True, True, True, False))
+            caps5 = E.PrimaryCapsFn.forward(ctx_pc, xe, pc.pose.weight, pc.pose.bias, pc.a.weight, pc.a.bias, pc)
+            caps = caps5[:, 0]
+            cc = model.conv_caps
+            ctx_r = _Ctx((True, True, True, True))
+            rout = E.EMRoutingFn.forward(ctx_r, caps, cc.weights, cc.beta_u, cc.beta_a)
+            ctx_a = _Ctx((True,))
+            act = E.ClassActFn.forward(ctx_a, rout)
+            feat = rout[..., C * 16:].reshape(N2, -1, C)
             cls2 = torch.cat([action, action]).to(dev)
             lab2 = torch.cat([labels_dev, labels_dev])
-            xe, c56, c112, drop2 = model._encode(img)
-            if self.world > 1:
-                # everything after the encoder (84 % of the parameters, incl. the 138 MB PrimaryCaps weight) is final
-                # when the gradient w.r.t. the encoder output has been formed -> all-reduce it under the encoder bwd
-                hook = xe.register_hook(lambda g: (self._allreduce_async(self.enc_end, flat.n), None)[1])
-            caps, rout = model._capsules(xe)
-            logits, act, feat = model._decode(rout, xe, c56, c112, drop2, cls2, lab2, epoch, a.thresh_epoch)
+            lab = torch.nn.functional.one_hot(cls2.long().view(-1), C).float()
+            if epoch < a.thresh_epoch:
+                unl = torch.ones_like(lab)
+            else:
+                unl = torch.nn.functional.one_hot(torch.argmax(act, dim=1), C).float()
+            sel = (lab2.view(-1, 1) == 0).float()
+            mask = (sel * unl + (1.0 - sel) * lab).contiguous()
+            ctx_h = _Ctx((True, False))
+            x0 = E.CapsHeadFn.forward(ctx_h, rout, mask)
+            ctx_dec = _Ctx((True, True, True, True, False, False) + (True,) * 16)
+            dparams = []
+            for n in E.DecoderFn.ORDER:
+                m = getattr(model, n)
+                dparams += [m.weight, m.bias]
+            logits = E.DecoderFn.forward(ctx_dec, x0, xe, y3, y1, drop2, model, *dparams)
         finally:
-            engine.STATE.bn_groups = 1
+            E.STATE.bn_groups = 1
 
-        # ---- losses + their gradients (device only) -------------------------------------------------
+        # ---------------- losses + their gradients (device only) ----------------
         out, flp = logits[:P], logits[P:]
         V = out.numel() // P
         dlogits = torch.zeros_like(logits)
@@ -242,19 +304,49 @@ class TrainStep:
         ops.cons_grad(out, flp, m_clk, m_anti, m_gv, dlogits[:P], dlogits[P:], P, H, W, 1, 1, a_l2 * a.wt_cons,
                       a_lv * a.wt_cons, a_lg * a.wt_cons)
 
-        # ---- backward + optimiser ----------------------------------------------------------------------
+        # ---------------- backward (explicit reverse walk) ----------------
         try:
-            torch.autograd.backward([logits, act], [dlogits, dact])
+            gd = E.DecoderFn.backward(ctx_dec, dlogits)
+            dx0, dxe_dec, dy3_dec, dy1_dec = gd[0], gd[1], gd[2], gd[3]
+            drout = E.CapsHeadFn.backward(ctx_h, dx0)[0]
+            drout.add_(E.ClassActFn.backward(ctx_a, dact))                   # fp32 (2P,20,20,408): tiny
+            dcaps = E.EMRoutingFn.backward(ctx_r, drout)[0]
+            dxe = E.PrimaryCapsFn.backward(ctx_pc, dcaps.view(caps5.shape))[0]
+            ops.add(View(dxe), View(dxe_dec), View(dxe))                      # two consumers of the encoder output
+            if self.world > 1:
+                # everything after the encoder (84 % of the parameters, incl. the 138 MB PrimaryCaps weight) is final now:
+                # all-reduce it on the side stream underneath the encoder backward
+                self._allreduce_async(self.enc_end, flat.n)
+            g = E.ChannelScaleFn.backward(ctx_d, dxe)[0]
+            for bw in reversed(chain):
+                g = bw(g)
+            g = b_p2(g)
+            ops.add(View(g), View(dy3_dec), View(g))                          # cross56 skip
+            g = b_2c(g)
+            g = b_2b(g)
+            g = b_p1(g)
+            ops.add(View(g), View(dy1_dec), View(g))                          # cross112 skip
+            b_stem(g)
         finally:
-            engine.STATE.direct_grads = False
-            if hook is not None:
-                hook.remove()
+            E.STATE.direct_grads = False
         if self.world > 1:
             self._allreduce_async(0, self.enc_end)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         ops.adam_step(flat.data, flat.grad, flat.m, flat.v, flat.n, a.lr, 0.9, 0.999, 1e-6, self.step_dev, 1.0 / self.world)
-        engine.bump_weights_epoch()
+        E.bump_weights_epoch()
         loc = l_seg[0] + l_seg[1]
         total = a.wt_loc * loc + a.wt_cls * l_cls[0] + a.wt_cons * l_cons[0]
         return dict(total=total, loc=loc, bce=l_seg[0], dice=l_seg[1], cls=l_cls[0], cons=l_cons[0], l2=l_cons[1],
                     output=out, flip_op=flp, pred_action=act[:P], feat=feat[:P])
+
+
+class _Ctx:
+    """Minimal stand-in for the autograd context so the engine functions' forward / backward halves can be called
+    directly by the hand-scheduled step."""
+
+    def __init__(self, needs_input_grad):
+        self.needs_input_grad = tuple(needs_input_grad)
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
