@@ -171,8 +171,8 @@ int b2c_add(const void* a, int64_t a_row_stride, int32_t a_c_off, const void* b,
  * per-tap projections P, PLANAR fp32 [32][rows] -> logits fp32 (N,T,H,W); and its adjoint dP (bf16 rows). */
 int b2c_stencil27_fwd(const float* P, float* out, const float* bias, int32_t N, int32_t T, int32_t H, int32_t W,
                       b2c_stream_t s);
-/* dP bf16 (rows,32); dbias[0] += sum(dout) when non-NULL */
-int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t N, int32_t T, int32_t H, int32_t W,
+/* dP bf16 (rows,cpad), taps 27..cpad-1 zero; dbias[0] += sum(dout) when non-NULL */
+int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t N, int32_t T, int32_t H, int32_t W, int32_t cpad,
                       b2c_stream_t s);
 
 /* ------------------------------------------------------------------------------------
@@ -187,9 +187,10 @@ int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, c
  * dW/dbeta_u/dbeta_a are accumulated (atomicAdd) -- zero them first. */
 int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
                        float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s);
-/* PrimaryCaps backward prologue (capsules_ucf101.py:43-49 adjoint): g, out fp32 (rows,544); dz bf16 (rows,544) =
+/* PrimaryCaps backward prologue (capsules_ucf101.py:43-49 adjoint): g, out fp32 (rows,544); dz bf16 (rows,dz_pitch>=544) =
  * g * (col >= 512 ? a(1-a) : 1); dbias[544] += column sums (first 512: pose bias, last 32: a bias). */
-int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, b2c_stream_t s);
+int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, int32_t dz_pitch,
+                             b2c_stream_t s);
 /* class activation = mean over the 400 locations (capsules_ucf101.py:450-451); feat is a view of out */
 int b2c_class_mean_fwd(const float* rout, float* act, int32_t N, int32_t L, int32_t C, b2c_stream_t s);
 /* pose masking (capsules_ucf101.py:455-483): x[n,l,j*16+h] = mu[n,l,j,h] * mask[n,j]  -> bf16 (N,L,C*16) */

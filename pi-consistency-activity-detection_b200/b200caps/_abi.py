@@ -60,10 +60,10 @@ _SIGS = {
     "b2c_act_bwd": [vp, i64, i32, vp, i64, i32, vp, vp, i64, i32, vp, i32, i64, i32, i32, vp],
     "b2c_add": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, vp],
     "b2c_stencil27_fwd": [vp, vp, vp, i32, i32, i32, i32, vp],
-    "b2c_stencil27_bwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2c_stencil27_bwd": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "b2c_em_routing_fwd": [vp, vp, vp, vp, vp, i64, i32, vp],
     "b2c_em_routing_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
-    "b2c_primarycaps_bwd_prep": [vp, vp, vp, vp, i64, vp],
+    "b2c_primarycaps_bwd_prep": [vp, vp, vp, vp, i64, i32, vp],
     "b2c_class_mean_fwd": [vp, vp, i32, i32, i32, vp],
     "b2c_pose_mask_fwd": [vp, vp, vp, i32, i32, i32, vp],
     "b2c_caps_head_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp],

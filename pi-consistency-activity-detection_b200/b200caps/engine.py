@@ -441,8 +441,9 @@ class FusedConvLayer:
     GEMM with N = sum(Cout_i): the packed fprop operand stacks the members' rows, the dgrad operand places them
     side by side along K.  Used for PrimaryCaps (pose | a, N = 544)."""
 
-    def __init__(self, weights: Sequence[torch.nn.Parameter], spec_fn):
+    def __init__(self, weights: Sequence[torch.nn.Parameter], spec_fn, grad_cpad: int = 0):
         self.weights = list(weights)
+        self.grad_cpad = grad_cpad       # channel width of the output-gradient tensor (>= sum Cout, 64-aligned for TMA)
         self.couts = [int(w.shape[0]) for w in self.weights]
         self.offs = [sum(self.couts[:i]) for i in range(len(self.couts))]
         self.spec_fn = spec_fn
@@ -455,6 +456,11 @@ class FusedConvLayer:
         if pl is None:
             pl = ConvPlan(self.spec_fn(in_dims), in_dims)
             assert not pl.spec.transposed and pl.spec.Cout == sum(self.couts)
+            if self.grad_cpad:
+                # the gradient w.r.t. the fused output is stored grad_cpad channels wide (zero tail): dgrad's K and
+                # wgrad's plain operand become 64-channel aligned -> TMA path
+                pl.dgrad_pack = dict(pl.dgrad_pack, C=self.grad_cpad)
+                pl.wgrad_geom = dict(pl.wgrad_geom, Cp=self.grad_cpad)
             self.plans[in_dims] = pl
         return pl.to(self.weights[0].device)
 
@@ -477,14 +483,14 @@ class FusedConvLayer:
                 ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, co, nt, spec.Cin_pad, spec.Cin, spec.Cin * T, T,
                               spec.Cin_pad, 0, off, bn, nkb)
         else:
+            cg = self.grad_cpad or spec.Cout_pad
             for cl in pl.dgrad:
                 nt = len(cl.taps)
-                bn, _, nkb, elems = packed_geometry(spec.Cin_pad, nt * spec.Cout_pad)
+                bn, _, nkb, elems = packed_geometry(spec.Cin_pad, nt * cg)
                 if cl.packed is None:
                     cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=dev)
                 for w, co, off in zip(self.weights, self.couts, self.offs):
-                    ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, spec.Cin, nt, co, co, T, spec.Cin * T,
-                                  spec.Cout_pad, off, 0, bn, nkb)
+                    ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, spec.Cin, nt, co, co, T, spec.Cin * T, cg, off, 0, bn, nkb)
         self.keys[(tuple(in_dims), which)] = key
         return pl
 
@@ -520,9 +526,10 @@ class PrimaryCapsFn(torch.autograd.Function):
         layer: FusedConvLayer = mod._layer
         g = g.contiguous().float()
         rows = out.numel() // 544
-        dzb = torch.empty(out.shape, dtype=torch.bfloat16, device=out.device)
+        cg = layer.grad_cpad or 544
+        dzb = (torch.zeros if cg != 544 else torch.empty)(out.shape[:-1] + (cg,), dtype=torch.bfloat16, device=out.device)
         dbias = torch.zeros(544, dtype=torch.float32, device=out.device)
-        ops.primarycaps_bwd_prep(g, out, dzb, dbias, rows)
+        ops.primarycaps_bwd_prep(g, out, dzb, dbias, rows, cg)
         dims = x.shape[1:4]
         dx = None
         if ctx.needs_input_grad[0]:
@@ -651,14 +658,14 @@ class DecoderFn(torch.autograd.Function):
         bf = torch.bfloat16
         N, To, Ho = u4.shape[0], u4.shape[1], u4.shape[2]
         glog = glog.contiguous().float()
-        dP = torch.empty((N, To, Ho, Ho, 32), dtype=bf, device=dev)
+        dP = torch.empty((N, To, Ho, Ho, SmoothLayer.BWD_CPAD), dtype=bf, device=dev)
         db_smooth, ds1 = grad_buf(mod.smooth.bias)
-        ops.stencil27_bwd(glog, dP, db_smooth, N, To, Ho, Ho)
+        ops.stencil27_bwd(glog, dP, db_smooth, N, To, Ho, Ho, SmoothLayer.BWD_CPAD)
         sm = L["smooth"]
         du4 = torch.empty_like(u4)
         ops.conv_fprop(sm.packed((To, Ho, Ho), "dgrad"), "dgrad", View(dP), View(du4))
         dw_smooth, ds0 = grad_buf(mod.smooth.weight)
-        ops.conv_wgrad(sm.plan((To, Ho, Ho)), View(u4), View(dP), dw_smooth, atomic=True)
+        ops.conv_wgrad(sm.plan((To, Ho, Ho), "dgrad"), View(u4), View(dP), dw_smooth, atomic=True)
         del dP
         g = {}
         dcat112 = torch.empty_like(cat112)
@@ -690,26 +697,30 @@ class DecoderFn(torch.autograd.Function):
 
 
 class SmoothLayer:
-    """`smooth` weight (128,1,3,3,3) viewed as the 128 -> 27 (padded 32) projection matrix."""
+    """`smooth` weight (128,1,3,3,3) viewed as the 128 -> 27 projection matrix.  Forward writes 32 planar fp32 planes;
+    the backward GEMMs see the tap gradients dP 64 channels wide (zero tail) so both run on the TMA path."""
+    BWD_CPAD = 64
 
     def __init__(self, weight: torch.nn.Parameter):
         self.weight = weight
         self.plans: Dict = {}
         self.keys: Dict = {}
 
-    def plan(self, dims) -> ConvPlan:
+    def plan(self, dims, which="fprop") -> ConvPlan:
         dims = tuple(int(v) for v in dims)
-        pl = self.plans.get(dims)
+        bwd = which != "fprop"
+        pl = self.plans.get((dims, bwd))
         if pl is None:
-            pl = ConvPlan.pointwise_from_strides(128, 27, 32, 1, 27, dims)
-            self.plans[dims] = pl
+            pl = ConvPlan.pointwise_from_strides(128, 27, self.BWD_CPAD if bwd else 32, 1, 27, dims)
+            self.plans[(dims, bwd)] = pl
         return pl.to(self.weight.device)
 
     def packed(self, dims, which) -> ConvPlan:
-        pl = self.plan(dims)
+        dims = tuple(int(v) for v in dims)
+        pl = self.plan(dims, which)
         w = self.weight
         key = (w.data_ptr(), w._version, STATE.weights_epoch)
-        if self.keys.get((tuple(dims), which)) != key:
+        if self.keys.get((dims, which)) != key:
             pl.pack(w.detach(), which, ops.stream())
-            self.keys[(tuple(dims), which)] = key
+            self.keys[(dims, which)] = key
         return pl

@@ -141,8 +141,8 @@ def stencil27_fwd(P, out, bias, N, T, H, W):
     _abi.call("b2c_stencil27_fwd", _p(P), _p(out), _p(bias), N, T, H, W, stream())
 
 
-def stencil27_bwd(dout, dP, dbias, N, T, H, W):
-    _abi.call("b2c_stencil27_bwd", _p(dout), _p(dP), _p(dbias), N, T, H, W, stream())
+def stencil27_bwd(dout, dP, dbias, N, T, H, W, cpad=32):
+    _abi.call("b2c_stencil27_bwd", _p(dout), _p(dP), _p(dbias), N, T, H, W, cpad, stream())
 
 
 # ---- capsule head ---------------------------------------------------------------------------
@@ -155,8 +155,8 @@ def em_routing_bwd(caps, W, beta_u, beta_a, dout, dcaps, dW, dbu, dba, b, C):
               _p(dba), b, C, stream())
 
 
-def primarycaps_bwd_prep(g, out, dz, dbias, rows):
-    _abi.call("b2c_primarycaps_bwd_prep", _p(g), _p(out), _p(dz), _p(dbias), rows, stream())
+def primarycaps_bwd_prep(g, out, dz, dbias, rows, dz_pitch=544):
+    _abi.call("b2c_primarycaps_bwd_prep", _p(g), _p(out), _p(dz), _p(dbias), rows, dz_pitch, stream())
 
 
 def class_mean_fwd(rout, act, N, L, C):

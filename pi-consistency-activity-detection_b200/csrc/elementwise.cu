@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __re
 }
 // adjoint: dP[i][k] = dout[i - 1 + k] (bf16 rows of 32, taps 27..31 zero)
 __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dP,
-                                                               float* __restrict__ dbias, int N, int T, int H, int W) {
+                                                               float* __restrict__ dbias, int N, int T, int H, int W, int cpad) {
   const long long rows = (long long)N * T * H * W;
   float bsum = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
@@ -508,9 +508,10 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
 #pragma unroll
     for (int k = 27; k < 32; ++k) v[k] = 0.f;
     bsum += v[13];  // centre tap == dout[i]
-    bf16* dst = dP + i * 32;
+    bf16* dst = dP + i * cpad;
 #pragma unroll
     for (int q = 0; q < 4; ++q) st16(dst + q * 8, pack8(v + q * 8));
+    for (int q = 4; q < cpad / 8; ++q) st16(dst + q * 8, make_uint4(0, 0, 0, 0));
   }
   if (dbias) {
     __shared__ float sb[kBlock / 32];
@@ -531,43 +532,44 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
 struct Im2colGeom {
   int N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad;
 };
+// One warp per output row.  For a fixed (kt, kh) the kw x C block of the im2col row is kw consecutive input pixels
+// (16 bytes each, channels-last with Cs = 8), i.e. one contiguous run: each lane gathers whole (kt,kh) runs with
+// 16-byte loads into a shared row image, then the warp streams the Kpad-wide row out with coalesced 16-byte stores.
 __global__ void __launch_bounds__(kBlock) im2col_small_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Im2colGeom G) {
-  extern __shared__ int s_lut[];   // per k: dt | dh<<8 | dw<<16 | c<<24 ; -1 = padding column
-  for (int k = threadIdx.x; k < G.Kpad; k += blockDim.x) {
-    int v = -1;
-    if (k < G.K) {
-      const int tap = k / G.C, c = k - tap * G.C;
-      const int a = tap / (G.kh * G.kw), r = tap - a * G.kh * G.kw;
-      const int b = r / G.kw, cc = r - b * G.kw;
-      v = a | (b << 8) | (cc << 16) | (c << 24);
-    }
-    s_lut[k] = v;
-  }
-  __syncthreads();
-  const int chunks = G.Kpad / 8;
-  const long long total = (long long)G.N * G.To * G.Ho * G.Wo * chunks;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % chunks);
-    long long row = i / chunks;
-    const long long orow = row;
-    const int wo = (int)(row % G.Wo); row /= G.Wo;
-    const int ho = (int)(row % G.Ho); row /= G.Ho;
-    const int to = (int)(row % G.To); row /= G.To;
-    const int n = (int)row;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int warps = kBlock / 32;
+  const int w_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bf16* srow = reinterpret_cast<bf16*>(s_raw) + (size_t)w_id * G.Kpad;
+  const long long rows = (long long)G.N * G.To * G.Ho * G.Wo;
+  const int pairs = G.kt * G.kh;
+  const int run = G.kw * G.C;
+  // zero the padding tail once (columns K..Kpad never change)
+  for (int k = G.K + lane; k < G.Kpad; k += 32) srow[k] = __float2bfloat16(0.f);
+  for (long long row = (long long)blockIdx.x * warps + w_id; row < rows; row += (long long)gridDim.x * warps) {
+    long long r = row;
+    const int wo = (int)(r % G.Wo); r /= G.Wo;
+    const int ho = (int)(r % G.Ho); r /= G.Ho;
+    const int to = (int)(r % G.To); r /= G.To;
+    const int n = (int)r;
     const int t0 = to * G.st - G.pt, h0 = ho * G.sh - G.ph, w0 = wo * G.sw - G.pw;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int l = s_lut[ch * 8 + e];
-      float val = 0.f;
-      if (l >= 0) {
-        const int t = t0 + (l & 0xff), h = h0 + ((l >> 8) & 0xff), w = w0 + ((l >> 16) & 0xff), c = (l >> 24) & 0xff;
-        if ((unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H && (unsigned)w < (unsigned)G.W)
-          val = __bfloat162float(x[((((long long)n * G.T + t) * G.H + h) * G.W + w) * G.Cs + c]);
+    for (int p = lane; p < pairs; p += 32) {
+      const int a = p / G.kh, b = p - a * G.kh;
+      const int t = t0 + a, h = h0 + b;
+      const bool rowok = (unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H;
+      const bf16* src = x + (((long long)n * G.T + t) * G.H + h) * (long long)G.W * G.Cs;
+      bf16* dst = srow + p * run;
+      for (int c = 0; c < G.kw; ++c) {
+        const int w = w0 + c;
+        uint4 px = make_uint4(0, 0, 0, 0);
+        if (rowok && (unsigned)w < (unsigned)G.W) px = ld16(src + (long long)w * G.Cs);   // Cs == 8: one pixel = 16 bytes
+        const bf16* pv = reinterpret_cast<const bf16*>(&px);
+        for (int ch = 0; ch < G.C; ++ch) dst[c * G.C + ch] = pv[ch];
       }
-      v[e] = val;
     }
-    st16(out + orow * G.Kpad + ch * 8, pack8(v));
+    __syncwarp();
+    bf16* orow = out + row * G.Kpad;
+    for (int v = lane; v < G.Kpad / 8; v += 32) st16(orow + v * 8, *reinterpret_cast<const uint4*>(srow + v * 8));
+    __syncwarp();
   }
 }
 
@@ -769,10 +771,10 @@ B2C_API int b2c_stencil27_fwd(const float* P, float* out, const float* bias, int
   return 0;
 }
 
-B2C_API int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t N, int32_t T, int32_t H, int32_t W,
+B2C_API int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t N, int32_t T, int32_t H, int32_t W, int32_t cpad,
                               b2c_stream_t s) {
-  B2C_REQUIRE(dout && dP && N > 0, "stencil27_bwd: bad args");
-  stencil27_bwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, dbias, N, T, H, W);
+  B2C_REQUIRE(dout && dP && N > 0 && cpad >= 32 && cpad % 8 == 0, "stencil27_bwd: bad args");
+  stencil27_bwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, dbias, N, T, H, W, cpad);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("stencil27_bwd");
   return 0;
@@ -792,10 +794,11 @@ B2C_API int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, in
                              int32_t pt, int32_t ph, int32_t pw, int32_t Kpad, b2c_stream_t s) {
   B2C_REQUIRE(x && out && N > 0 && C > 0 && C <= Cs && C < 256, "im2col_small: bad args");
   const int K = kt * kh * kw * C;
-  B2C_REQUIRE(Kpad % 64 == 0 && Kpad >= K && kt < 256 && kh < 256 && kw < 256 && Kpad * 4 <= 48 * 1024, "im2col_small: bad K");
+  B2C_REQUIRE(Kpad % 64 == 0 && Kpad >= K && Cs == 8 && (kBlock / 32) * Kpad * 2 <= 48 * 1024, "im2col_small: bad K / Cs");
   Im2colGeom G{N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad};
-  const long long total = (long long)N * To * Ho * Wo * (Kpad / 8);
-  im2col_small_kernel<<<grid_for(total, kBlock, 16), kBlock, Kpad * sizeof(int), (cudaStream_t)s>>>((const bf16*)x, (bf16*)out, G);
+  const long long rows = (long long)N * To * Ho * Wo;
+  im2col_small_kernel<<<grid_for(rows, kBlock / 32, 16), kBlock, (kBlock / 32) * Kpad * 2, (cudaStream_t)s>>>((const bf16*)x,
+                                                                                                              (bf16*)out, G);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("im2col_small");
   return 0;

@@ -477,7 +477,7 @@ __global__ void caps_head_bwd_kernel(const bf16* __restrict__ dx, const float* _
 // PrimaryCaps backward prologue: g fp32 (rows, 544) is the gradient w.r.t. [poses | sigmoid(act)];
 // dz = g * (col >= 512 ? a (1 - a) : 1) as bf16 rows for the dgrad / wgrad GEMMs, dbias[col] += sum_rows dz.
 __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* __restrict__ g, const float* __restrict__ out,
-                                                                   bf16* __restrict__ dz, float* __restrict__ dbias, long long rows) {
+                                                                   bf16* __restrict__ dz, float* __restrict__ dbias, long long rows, int dz_pitch) {
   // block = 256 threads: 4 row lanes x 68 column groups of 8 (544 = 68 * 8); threads >= 272 idle
   const int cg = threadIdx.x % 68, rl = threadIdx.x / 68;
   const bool act = rl < 3;
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
-      *reinterpret_cast<uint4*>(dz + r * 544 + cg * 8) = pack8(v);
+      *reinterpret_cast<uint4*>(dz + r * dz_pitch + cg * 8) = pack8(v);
     }
   }
   __shared__ float sh[544];
@@ -589,12 +589,13 @@ B2C_API int b2c_caps_head_bwd(const void* dx, const float* mask, const float* da
   return 0;
 }
 
-B2C_API int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, b2c_stream_t s) {
-  B2C_REQUIRE(g && out && dz && dbias && rows > 0, "primarycaps_bwd_prep: bad args");
+B2C_API int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, int32_t dz_pitch,
+                                     b2c_stream_t s) {
+  B2C_REQUIRE(g && out && dz && dbias && rows > 0 && dz_pitch >= 544 && dz_pitch % 8 == 0, "primarycaps_bwd_prep: bad args");
   long long blocks = (rows + 2) / 3;
   const long long cap = (long long)b2c_num_sms() * 4;
   if (blocks > cap) blocks = cap;
-  primarycaps_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows);
+  primarycaps_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows, dz_pitch);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("primarycaps_bwd_prep");
   return 0;
