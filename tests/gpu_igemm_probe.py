@@ -28,6 +28,9 @@ CASES = [
     ("convT3d s2 128->64", True, 128, 64, (3, 3, 3), (2, 2, 2), (1, 14, 14), 1, 2),
     ("convT3d s2 128->128", True, 128, 128, (3, 3, 3), (2, 2, 2), (2, 12, 12), 1, 1),
     ("proj 1x1 128->32 fp32out", False, 128, 32, (1, 1, 1), (1, 1, 1), (2, 16, 16), "same", 1),
+    ("convT3d s2 128->64 (1,28,28) N=4", True, 128, 64, (3, 3, 3), (2, 2, 2), (1, 28, 28), 1, 4),
+    ("convT3d s2 128->64 (2,56,56) N=2", True, 128, 64, (3, 3, 3), (2, 2, 2), (2, 56, 56), 1, 2),
+    ("conv 3x3x3 192->64 p1 (2,56,56)", False, 192, 64, (3, 3, 3), (1, 1, 1), (2, 56, 56), 1, 2),
 ]
 
 
