@@ -95,28 +95,14 @@ class TrainStep:
         self.flat = FlatParams(model)
         dev = self.flat.data.device
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # Adam step counter (device: graph replayable)
-        self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
-        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
-        # bucket boundary: encoder (conv1.*) parameters come first in registration order; everything after the
-        # encoder is complete once the capsule head has back-propagated, i.e. before the encoder backward starts.
-        enc_end = 0
+        from .ddp import GradBuckets, bucket_ranges
         named = dict(model.named_parameters())
-        for k, o in self.flat.offsets.items():
-            if k.startswith("conv1."):
-                enc_end = max(enc_end, o + named[k].numel())
-        self.enc_end = (enc_end + 3) // 4 * 4
+        ranges = bucket_ranges(self.flat.offsets, {k: p.numel() for k, p in named.items()}, self.flat.n)
+        self.buckets = GradBuckets(self.flat.grad, ranges, process_group)
+        self.world = self.buckets.world
         self.graph = None
         self.static = None
         self.launches_per_step = None
-
-    # ---- multi-GPU: gradient all-reduce overlapped with the encoder backward --------------------------
-    def _allreduce_async(self, lo: int, hi: int):
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
 
     @staticmethod
     def _label_tensors(labels_host, dev):
@@ -316,7 +302,7 @@ class TrainStep:
             if self.world > 1:
                 # everything after the encoder (84 % of the parameters, incl. the 138 MB PrimaryCaps weight) is final now:
                 # all-reduce it on the side stream underneath the encoder backward
-                self._allreduce_async(self.enc_end, flat.n)
+                self.buckets.allreduce(1)
             g = E.ChannelScaleFn.backward(ctx_d, dxe)[0]
             for bw in reversed(chain):
                 g = bw(g)
@@ -330,8 +316,8 @@ class TrainStep:
         finally:
             E.STATE.direct_grads = False
         if self.world > 1:
-            self._allreduce_async(0, self.enc_end)
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self.buckets.allreduce(0)
+            self.buckets.join()
         ops.adam_step(flat.data, flat.grad, flat.m, flat.v, flat.n, a.lr, 0.9, 0.999, 1e-6, self.step_dev, 1.0 / self.world)
         E.bump_weights_epoch()
         loc = l_seg[0] + l_seg[1]

@@ -1,0 +1,92 @@
+"""-m gpu: the fused, hand-scheduled training step (b200caps.step.TrainStep: batched passes, device losses, explicit
+backward walk, direct gradient accumulation) against the SAME step composed the way the reference's
+train_model_interface does it (main_ucf101.py:50-150) from the drop-in modules + torch autograd."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("mode", ["bv", "gv"])
+def test_fused_step_equals_dropin_composition(mode):
+    from b200caps import engine
+    from b200caps.step import StepArgs, TrainStep
+    from models.capsules_ucf101 import CapsNet
+    from oracle import restate
+    from utils.helpers import measure_pixelwise_gradient, measure_pixelwise_var_v2
+    from utils.losses import BCEWithLogitsLoss, DiceLoss, SpreadLoss, weighted_mse_loss
+    from utils.ramp_ups import exp_rampup
+
+    sd = restate.make_state_dict(24, seed=0)
+    m1 = CapsNet(pt_path=None)
+    m1.load_state_dict(sd)
+    m1 = m1.cuda().train()
+    m2 = copy.deepcopy(m1)
+    b = restate.synthetic_batch(1, 1, seed=47)
+    masks = restate.make_drop_masks(2, seed=3, count=4)       # draw order: enc#1, dec#1, enc#2, dec#2
+    data, fl, action, seg, labels = [b[k].cuda() for k in ("data", "fl_data", "action", "seg", "labels")]
+    bv, gv = mode == "bv", mode == "gv"
+
+    # ---- drop-in composition (reference's train_model_interface with our modules) ----
+    it = iter(masks)
+    engine.STATE.dropout_source = lambda n, c, dev: next(it).reshape(n, c)
+    try:
+        out, act, _ = m1(data, action, labels, 1, 11)
+        flip_op, _, _ = m1(fl, action, labels, 1, 11)
+    finally:
+        engine.STATE.dropout_source = None
+    lab_idx = torch.where(labels == 1)[0]
+    loc = BCEWithLogitsLoss()(out[lab_idx], seg[lab_idx]) + DiceLoss()(out[lab_idx], seg[lab_idx])
+    cls, _ = SpreadLoss(num_class=24, m_min=0.2, m_max=0.9)(act[lab_idx], action[lab_idx])
+    flipped = torch.flip(flip_op, [4])
+    l2 = weighted_mse_loss(flipped, out, torch.ones_like(out))
+    wt_ramp = exp_rampup(100)(1)
+    if bv:
+        v1 = measure_pixelwise_var_v2(out, torch.flip(flipped, [2]), frames_cnt=5)
+        v2 = measure_pixelwise_var_v2(torch.flip(out, [2]), flipped, frames_cnt=5)
+        cons = wt_ramp * (weighted_mse_loss(flipped, out, v1) + weighted_mse_loss(flipped, out, torch.flip(v2, [2]))) + \
+            (1 - wt_ramp) * l2
+    else:
+        cons = weighted_mse_loss(flipped, out, measure_pixelwise_gradient(out))
+    total = loc + cls + 0.1 * cons
+    total.backward()
+    ref_grads = {k: p.grad.clone() for k, p in m1.named_parameters()}
+
+    # ---- fused step (lr = 0 keeps the weights; gradients stay in the flat buffer) ----
+    step = TrainStep(m2, StepArgs(bv=bv, gv=gv, n_frames=5, wt_cons=0.1, lr=0.0))
+    cat832 = torch.cat([masks[0], masks[2]]).reshape(2 * 2, 832)
+    cat128 = torch.cat([masks[1], masks[3]]).reshape(2 * 2, 128)
+    engine.STATE.dropout_source = lambda n, c, dev: (cat832 if c == 832 else cat128)
+    try:
+        res = step(data, fl, action, seg, labels.cpu(), epoch=1)
+    finally:
+        engine.STATE.dropout_source = None
+    e = dict(total=abs(float(res["total"]) - float(total)) / abs(float(total)),
+             loc=abs(float(res["loc"]) - float(loc)) / abs(float(loc)),
+             cls=abs(float(res["cls"]) - float(cls)) / (abs(float(cls)) + 1e-9),
+             cons=abs(float(res["cons"]) - float(cons)) / abs(float(cons)))
+    print("losses fused vs drop-in:", e, "values", float(total), float(loc), float(cls), float(cons))
+    assert max(e.values()) < 2e-3, e
+    assert rel(res["output"], out) < 1e-3 and rel(res["flip_op"], flip_op) < 1e-3
+    errs = {k: rel(p.grad, ref_grads[k]) for k, p in m2.named_parameters()}
+    worst = max(errs, key=errs.get)
+    print(f"grads fused vs drop-in: worst {worst} {errs[worst]:.2e}")
+    assert errs[worst] < 2e-2, (worst, errs[worst])
+    # reported: the same step on the fp64 oracle (chaotic end to end at random init)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        o = restate.train_step_losses({k: v.double() if v.dtype.is_floating_point else v for k, v in sd.items()},
+                                      b["data"].double(), b["fl_data"].double(), b["action"], b["seg"], b["labels"],
+                                      epoch=1, bv=bv, gv=gv, n_frames=5, wt_cons=0.1, drop_masks=[m.double() for m in masks])
+    print("fp64 oracle losses: total %.4f loc %.4f cls %.4f cons %.5f | ours: total %.4f loc %.4f cls %.4f cons %.5f" % (
+        float(o["total"]), float(o["loc"]), float(o["cls"]), float(o["cons"]), float(res["total"]), float(res["loc"]),
+        float(res["cls"]), float(res["cons"])))
+    assert abs(float(res["loc"]) - float(o["loc"])) / float(o["loc"]) < 5e-2
