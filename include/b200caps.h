@@ -247,6 +247,9 @@ int b2c_cons_grad(const float* out, const float* flp, const float* w1, const flo
 int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   int32_t* step_dev, float grad_scale, b2c_stream_t s);
 
+/* tests: 1 = BatchNorm reductions use one block per statistic group (bit-reproducible activations, slow) */
+int b2c_set_deterministic(int32_t on);
+
 /* generic helpers */
 int b2c_fill_f32(float* p, int64_t n, float v, b2c_stream_t s);
 

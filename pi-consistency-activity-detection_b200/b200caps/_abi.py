@@ -77,6 +77,7 @@ _SIGS = {
     "b2c_cons_grad": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, vp],
     "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp],
     "b2c_fill_f32": [vp, i64, f32, vp],
+    "b2c_set_deterministic": [i32],
 }
 
 EXPORTS = sorted(list(_SIGS) + ["b2c_last_error", "b2c_version", "b2c_launch_count"])

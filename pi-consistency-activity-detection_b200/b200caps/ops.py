@@ -218,3 +218,8 @@ def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
 
 def fill_f32(t, v):
     _abi.call("b2c_fill_f32", _p(t), t.numel(), float(v), stream())
+
+
+def set_deterministic(on: bool):
+    """Tests only: bit-reproducible BatchNorm reductions (one block per statistic group)."""
+    _abi.call("b2c_set_deterministic", int(bool(on)))

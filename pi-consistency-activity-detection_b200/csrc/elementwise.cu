@@ -92,20 +92,23 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const bf16* __restrict
       }
     }
   }
-  // block reduce over row lanes through shared memory
-  extern __shared__ float sh[];  // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  // block reduce over row lanes through shared memory in a FIXED order (per-block result is deterministic)
+  extern __shared__ float sh[];  // [rpb][2][C]
   if (m.active) {
+    float* mine = sh + (size_t)m.rlane * 2 * C;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[m.cv * 8 + j], s1[j]);
-      atomicAdd(&sh[C + m.cv * 8 + j], s2[j]);
+      mine[m.cv * 8 + j] = s1[j];
+      mine[C + m.cv * 8 + j] = s2[j];
     }
   }
   __syncthreads();
   float* w = ws + (long long)g * 2 * C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&w[i], sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * C + i];
+    atomicAdd(&w[i], t);
+  }
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ ws_all, int ws_C, int c_off, long long rows_per_group, int C,
@@ -192,19 +195,22 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const bf16* __res
       }
     }
   }
-  extern __shared__ float sh[];
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float sh[];  // [rpb][2][C], fixed-order reduction
   if (m.active) {
+    float* mine = sh + (size_t)m.rlane * 2 * C;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[m.cv * 8 + j], s1[j]);
-      atomicAdd(&sh[C + m.cv * 8 + j], s2[j]);
+      mine[m.cv * 8 + j] = s1[j];
+      mine[C + m.cv * 8 + j] = s2[j];
     }
   }
   __syncthreads();
   float* w = ws + (long long)g * 2 * C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&w[i], sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * C + i];
+    atomicAdd(&w[i], t);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
@@ -584,6 +590,14 @@ inline int grid_for(long long work_items, int per_block = kBlock, int waves = 8)
   if (b < 1) b = 1;
   return (int)b;
 }
+// deterministic mode (tests): cross-block fp32 atomics of the BatchNorm reductions are avoided by using ONE block per
+// statistic group, so two runs -- or two schedules of the same step -- produce bit-identical activations.
+static int g_deterministic = 0;
+inline size_t bn_red_smem(int C) {
+  int rpb = kBlock / (C / 8);
+  if (rpb < 1) rpb = 1;
+  return (size_t)rpb * 2 * C * sizeof(float);
+}
 inline int row_grid(long long rows, int C, int waves = 4) {
   int rpb = kBlock / (C / 8);
   if (rpb < 1) rpb = 1;
@@ -620,8 +634,8 @@ B2C_API int b2c_bn_sums(const void* x, int64_t rows, int32_t C, int64_t row_stri
   CHECK_VIEW("bn_sums", C, row_stride, c_off);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_sums: rows=%lld not divisible by groups=%d", (long long)rows, groups);
   const long long rpg = rows / groups;
-  dim3 grid((unsigned)row_grid(rpg, C, 2), (unsigned)groups);
-  bn_stats_kernel<<<grid, kBlock, 2 * C * sizeof(float), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws);
+  dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
+  bn_stats_kernel<<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_sums");
   return 0;
@@ -663,8 +677,8 @@ B2C_API int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_rs, int32_t dy_co,
   CHECK_VIEW("bn_bwd_reduce(x)", C, x_rs, x_co);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_reduce: rows not divisible by groups");
   const long long rpg = rows / groups;
-  dim3 grid((unsigned)row_grid(rpg, C, 2), (unsigned)groups);
-  bn_bwd_reduce_kernel<<<grid, kBlock, 2 * C * sizeof(float), (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs,
+  dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
+  bn_bwd_reduce_kernel<<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs,
                                                                                  y_co, (const bf16*)x, x_rs, x_co, rpg, C, mean, rstd,
                                                                                  ws, relu);
   b2c_launches_add(1);
@@ -801,5 +815,10 @@ B2C_API int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, in
                                                                                                               (bf16*)out, G);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("im2col_small");
+  return 0;
+}
+
+B2C_API int b2c_set_deterministic(int32_t on) {
+  g_deterministic = on ? 1 : 0;
   return 0;
 }

@@ -34,6 +34,11 @@ def test_fused_step_equals_dropin_composition(mode):
     masks = restate.make_drop_masks(2, seed=3, count=4)       # draw order: enc#1, dec#1, enc#2, dec#2
     data, fl, action, seg, labels = [b[k].cuda() for k in ("data", "fl_data", "action", "seg", "labels")]
     bv, gv = mode == "bv", mode == "gv"
+    # Train-mode BatchNorm at random init is chaotic: two runs of the SAME code differ by 0.29 (relative L2 of the logits)
+    # through nothing but the order of fp32 atomics in the BN sums (tests/gpu_determinism_probe.py).  The comparison is
+    # therefore made in the library's deterministic mode, where both schedules must agree to accumulation noise.
+    from b200caps import ops
+    ops.set_deterministic(True)
 
     # ---- drop-in composition (reference's train_model_interface with our modules + torch autograd).  Both passes go
     # through the modules as ONE 2P batch with per-pass BatchNorm groups, exactly like the fused step, so the two sides
@@ -88,10 +93,10 @@ def test_fused_step_equals_dropin_composition(mode):
     # Both sides are OUR kernels; they differ only in batching (one 2P batch with per-pass BN groups vs two passes) and
     # in the order of fp32 atomics -- differences of 1e-7 that the routing amplifies, hence the
     # percent-level tolerances on quantities downstream of the routing.
-    assert e["loc"] < 1e-3 and max(e.values()) < 2e-2, e
-    assert e_out < 0.1 and e_flp < 0.1
-    assert all(torch.isfinite(p.grad).all() for p in m2.parameters())
-    assert med < 0.1, med
+    ops.set_deterministic(False)
+    assert max(e.values()) < 1e-5, e
+    assert e_out < 1e-5 and e_flp < 1e-5
+    assert errs[worst] < 1e-2, (worst, errs[worst])      # weight gradients: split-K fp32 atomics + bf16 fan-in adds
     # reported: the same step on the fp64 oracle (chaotic end to end at random init)
     torch.set_num_threads(os.cpu_count())
     with torch.no_grad():
