@@ -104,6 +104,18 @@ int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, int32_t 
                      int32_t C_real, int64_t s_r, int64_t s_c, int64_t tap_pitch, int64_t col_off, int32_t r_off,
                      int32_t bn_tile, int32_t nkb, b2c_stream_t stream);
 
+/* The same packing for MANY layers in one launch (the fused step re-packs all 137 operands after every optimiser
+ * step).  jobs_dev: device array; block_start_dev: device int32[njobs+1] prefix of CUDA blocks per job. */
+typedef struct {
+  const void* w;
+  void* packed;
+  const int32_t* wtap;
+  int64_t s_r, s_c, tap_pitch, col_off;
+  int32_t R, ntaps, C, C_real, r_off, bn_tile, nkb, pad_;
+} b2c_pack_job;
+int b2c_pack_weights_batched(const b2c_pack_job* jobs_dev, const int32_t* block_start_dev, int32_t njobs, int32_t nblocks,
+                             b2c_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Bandwidth kernels (channels-last bf16 views: ptr, rows, C, row_stride, c_off)
  * ---------------------------------------------------------------------------------- */

@@ -40,11 +40,18 @@ class WgradDesc(C.Structure):
                 ("ntaps", i32), ("bn_tile", i32), ("nsplit", i32), ("atomic", i32)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", vp), ("packed", vp), ("wtap", vp), ("s_r", i64), ("s_c", i64), ("tap_pitch", i64), ("col_off", i64),
+                ("R", i32), ("ntaps", i32), ("C", i32), ("C_real", i32), ("r_off", i32), ("bn_tile", i32), ("nkb", i32),
+                ("pad_", i32)]
+
+
 # name -> argtypes  (restype is always int unless noted)
 _SIGS = {
     "b2c_conv_fprop": [C.POINTER(ConvDesc), vp],
     "b2c_conv_wgrad": [C.POINTER(WgradDesc), vp],
     "b2c_pack_weights": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, i32, i32, vp],
+    "b2c_pack_weights_batched": [vp, vp, i32, i32, vp],
     "b2c_ncdhw_to_ndhwc": [vp, vp, i32, i32, i64, i32, vp],
     "b2c_ndhwc_to_ncdhw_f32": [vp, i64, i32, vp, i32, i32, i64, vp],
     "b2c_im2col_small": [vp, vp] + [i32] * 19 + [vp],

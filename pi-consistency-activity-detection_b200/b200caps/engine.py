@@ -33,6 +33,23 @@ def bump_weights_epoch():
     STATE.weights_epoch += 1
 
 
+def _packed_key(*weights):
+    """Cache key of derived packed operands.  When the fused step has re-packed every registered operand in one batched
+    launch for the current epoch, the epoch component is dropped so per-layer packing is skipped."""
+    base = tuple((w.data_ptr(), w._version) for w in weights)
+    if ops.PACKS is not None and ops.PACKS.flushed_epoch == STATE.weights_epoch:
+        return base + ("batched",)
+    return base + (STATE.weights_epoch,)
+
+
+def _fresh(old, key) -> bool:
+    """True when the packed operands recorded under `old` are valid for `key` (same tensors and versions, and either
+    the same epoch or re-packed by this epoch's batched flush)."""
+    if old is None or old[:-1] != key[:-1]:
+        return False
+    return old[-1] == key[-1] or key[-1] == "batched"
+
+
 def grad_buf(p: torch.Tensor):
     """Where a parameter gradient is accumulated: the existing .grad (fused step, zeroed once per step) or a
     fresh zero tensor that is handed back to autograd."""
@@ -167,8 +184,8 @@ class StemLayer(ConvLayer):
         col_dims = tuple(int(v) for v in col_dims)
         pl = self.plan(col_dims)
         w = self.weight
-        key = (w.data_ptr(), w._version, STATE.weights_epoch)
-        if self.keys.get(col_dims) != key:
+        key = _packed_key(w)
+        if not _fresh(self.keys.get(col_dims), key):
             from .plans import packed_geometry
             cl = pl.fprop[0]
             bn, _, nkb, elems = packed_geometry(self.cout, self.Kpad)
@@ -178,7 +195,7 @@ class StemLayer(ConvLayer):
             # k = tap*cin + c  <-  w[co][c][tap]
             ops.pack_part(w.detach(), cl.packed, self._wtap, self.cout, self.taps, self.cin, self.cin, self.cin * self.taps,
                           self.taps, self.cin, 0, 0, bn, nkb)
-            self.keys[col_dims] = key
+        self.keys[col_dims] = key
         return pl
 
     def scatter_wgrad(self, scratch: torch.Tensor, dw: torch.Tensor):
@@ -466,8 +483,9 @@ class FusedConvLayer:
 
     def packed(self, in_dims, which: str) -> ConvPlan:
         pl = self.plan(in_dims)
-        key = tuple((w.data_ptr(), w._version) for w in self.weights) + (STATE.weights_epoch,)
-        if self.keys.get((tuple(in_dims), which)) == key:
+        key = _packed_key(*self.weights)
+        if _fresh(self.keys.get((tuple(in_dims), which)), key):
+            self.keys[(tuple(in_dims), which)] = key
             return pl
         spec = pl.spec
         T = spec.k[0] * spec.k[1] * spec.k[2]
@@ -499,7 +517,10 @@ class FusedConvLayer:
         outs = []
         for w, co, off in zip(self.weights, self.couts, self.offs):
             dw, direct = grad_buf(w)
-            ops.conv_wgrad(pl, x, dy, dw, atomic=True, part=(off, co))
+            width = co
+            if co % 64 and self.grad_cpad and off % 64 == 0 and off + (co + 63) // 64 * 64 <= self.grad_cpad:
+                width = (co + 63) // 64 * 64        # zero-padded window: keeps the plain operand on the TMA path
+            ops.conv_wgrad(pl, x, dy, dw, atomic=True, part=(off, width, co))
             outs.append(None if direct else dw)
         return outs
 
@@ -662,14 +683,14 @@ class DecoderFn(torch.autograd.Function):
         db_smooth, ds1 = grad_buf(mod.smooth.bias)
         ops.stencil27_bwd(glog, dP, db_smooth, N, To, Ho, Ho, SmoothLayer.BWD_CPAD)
         sm = L["smooth"]
-        du4 = torch.empty_like(u4)
-        ops.conv_fprop(sm.packed((To, Ho, Ho), "dgrad"), "dgrad", View(dP), View(du4))
+        du4 = torch.empty_like(u4)      # = d(upsample4 pre-dropout output): the Dropout3d scale is applied in the epilogue
+        ops.conv_fprop(sm.packed((To, Ho, Ho), "dgrad"), "dgrad", View(dP), View(du4), scale_nc=ctx.drop)
         dw_smooth, ds0 = grad_buf(mod.smooth.weight)
         ops.conv_wgrad(sm.plan((To, Ho, Ho), "dgrad"), View(u4), View(dP), dw_smooth, atomic=True)
         del dP
         g = {}
         dcat112 = torch.empty_like(cat112)
-        g["upsample4"] = cba_bwd(L["upsample4"], mod.upsample4.bias, View(cat112), None, View(du4), False, ctx.drop, View(dcat112))
+        g["upsample4"] = cba_bwd(L["upsample4"], mod.upsample4.bias, View(cat112), None, View(du4), False, None, View(dcat112))
         del du4
         dc112 = torch.empty_like(c112) if ctx.needs[3] else None
         g["conv112"] = cba_bwd(L["conv112"], mod.conv112.bias, View(c112), View(cat112, 64, 64), View(dcat112, 64, 64), True, None,
@@ -719,8 +740,8 @@ class SmoothLayer:
         dims = tuple(int(v) for v in dims)
         pl = self.plan(dims, which)
         w = self.weight
-        key = (w.data_ptr(), w._version, STATE.weights_epoch)
-        if self.keys.get((dims, which)) != key:
+        key = _packed_key(w)
+        if not _fresh(self.keys.get((dims, which)), key):
             pl.pack(w.detach(), which, ops.stream())
-            self.keys[(dims, which)] = key
+        self.keys[(dims, which)] = key
         return pl

@@ -52,7 +52,51 @@ def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True,
             f"{' T' if plan.spec.transposed else ''}", "b2c_conv_wgrad", d)
 
 
+class PackRegistry:
+    """Every weight-packing job issued so far (pointers are stable: parameters are views of the flat buffer, packed
+    operands are persistent).  Once the fused step has seen all layers, `flush()` re-packs everything in one launch."""
+
+    def __init__(self):
+        self.jobs = {}           # (w_ptr, packed_ptr, r_off, col_off) -> PackJob fields
+        self.table = None        # (jobs_dev, block_start_dev, njobs, nblocks)
+        self.flushed_epoch = -1
+
+    def add(self, key, fields):
+        if key not in self.jobs:
+            self.jobs[key] = fields
+            self.table = None
+
+    def flush(self, epoch: int):
+        if not self.jobs:
+            return False
+        if self.table is None:
+            import numpy as np
+            arr = (_abi.PackJob * len(self.jobs))()
+            starts = [0]
+            for i, f in enumerate(self.jobs.values()):
+                for k, v in f.items():
+                    setattr(arr[i], k, v)
+                total = f["R"] * f["ntaps"] * f["C"]
+                starts.append(starts[-1] + max(1, min(64, (total + 2047) // 2048)))
+            dev = torch.device("cuda", torch.cuda.current_device())
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            bs = torch.tensor(starts, dtype=torch.int32, device=dev)
+            self.table = (raw, bs, len(self.jobs), starts[-1])
+        raw, bs, nj, nb = self.table
+        _abi.call("b2c_pack_weights_batched", _p(raw), _p(bs), nj, nb, stream())
+        self.flushed_epoch = epoch
+        return True
+
+
+PACKS: Optional[PackRegistry] = None     # the registry of the TrainStep that is currently executing (else None)
+
+
 def pack_part(weight, packed, wtap_dev, R, ntaps, C, C_real, s_r, s_c, tap_pitch, col_off, r_off, bn_tile, nkb):
+    if PACKS is not None:
+        key = (weight.data_ptr(), packed.data_ptr(), r_off, col_off)
+        PACKS.add(key, dict(w=weight.data_ptr(), packed=packed.data_ptr(), wtap=wtap_dev.data_ptr(), s_r=s_r, s_c=s_c,
+                            tap_pitch=tap_pitch, col_off=col_off, R=R, ntaps=ntaps, C=C, C_real=C_real, r_off=r_off,
+                            bn_tile=bn_tile, nkb=nkb, pad_=0))
     _abi.call("b2c_pack_weights", _p(weight), _p(packed), _p(wtap_dev), R, ntaps, C, C_real, s_r, s_c, tap_pitch, col_off,
               r_off, bn_tile, nkb, stream())
 

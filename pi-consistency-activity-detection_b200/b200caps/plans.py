@@ -212,8 +212,9 @@ class ConvPlan:
             bn, ntile, nkb, elems = packed_geometry(pk["R_pad"], nt * pk["C"])
             if cl.packed is None:
                 cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=weight.device)
-            _abi.call("b2c_pack_weights", weight.data_ptr(), cl.packed.data_ptr(), cl.wtap_dev.data_ptr(), pk["R"], nt,
-                      pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], pk["C"], 0, 0, bn, nkb, stream_ptr)
+            from . import ops
+            ops.pack_part(weight, cl.packed, cl.wtap_dev, pk["R"], nt, pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], pk["C"], 0, 0,
+                          bn, nkb)
 
 
 @dataclass
@@ -304,7 +305,7 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
         assert geo["g_is_input"], "fused members are plain convolutions"
         dy = View(dy.t, dy.c_off + part[0], part[1])
         geo["Cp"] = part[1]
-        geo["Cp_real"] = part[1]
+        geo["Cp_real"] = part[2] if len(part) > 2 else part[1]
     g, p = (x, dy) if geo["g_is_input"] else (dy, x)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     assert g.C == geo["Cg"] and p.C == geo["Cp"], (g.C, geo["Cg"], p.C, geo["Cp"])

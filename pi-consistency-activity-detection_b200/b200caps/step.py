@@ -100,6 +100,8 @@ class TrainStep:
         ranges = bucket_ranges(self.flat.offsets, {k: p.numel() for k, p in named.items()}, self.flat.n)
         self.buckets = GradBuckets(self.flat.grad, ranges, process_group)
         self.world = self.buckets.world
+        self._steps_seen = 0
+        self.packs = ops.PackRegistry()
         self._split_comm = False     # graph mode on >1 GPU: the NCCL all-reduce runs between two graphs, not inside one
         self.graph = None
         self.graph_opt = None
@@ -195,6 +197,11 @@ class TrainStep:
         wt_ramp = exp_rampup(a.rampup_epochs, epoch)
         model.train()
         flat.zero_grad()
+        # all derived bf16 operand tiles in one launch (after the first step every packing job is registered)
+        ops.PACKS = self.packs
+        if self.packs.flushed_epoch != E.STATE.weights_epoch and self._steps_seen >= 1:
+            self.packs.flush(E.STATE.weights_epoch)
+        self._steps_seen += 1
         E.STATE.direct_grads = True
         E.STATE.bn_groups = 2
         tape = []   # (backward closure) in forward order
@@ -336,6 +343,7 @@ class TrainStep:
             b_stem(g)
         finally:
             E.STATE.direct_grads = False
+            ops.PACKS = None
         if not self._split_comm:
             if self.world > 1:
                 self.buckets.allreduce(0)

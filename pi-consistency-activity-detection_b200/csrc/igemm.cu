@@ -838,6 +838,40 @@ int encode_im2col_map(CUtensorMap* map, const bf16* base, int C, long long row_s
   return 0;
 }
 
+// All weight re-packing of a step in ONE launch: a device table of jobs (stable pointers: flat parameter buffer
+// views -> persistent packed operand buffers); block -> job through a prefix table.
+__global__ void pack_weights_batched_kernel(const b2c_pack_job* __restrict__ jobs, const int* __restrict__ block_start, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {                 // last job whose first block <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (block_start[mid] <= (int)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const b2c_pack_job J = jobs[lo];
+  const int nblk = block_start[lo + 1] - block_start[lo];
+  const int bidx = blockIdx.x - block_start[lo];
+  const float* __restrict__ w = reinterpret_cast<const float*>(J.w);
+  bf16* __restrict__ packed = reinterpret_cast<bf16*>(J.packed);
+  const int32_t* __restrict__ wtap = J.wtap;
+  const long long total = (long long)J.R * J.ntaps * J.C;
+  const long long tile_elems = (long long)J.bn_tile * 64;
+  for (long long i = (long long)bidx * blockDim.x + threadIdx.x; i < total; i += (long long)nblk * blockDim.x) {
+    const int c = (int)(i % J.C);
+    const long long t2 = i / J.C;
+    const int t = (int)(t2 % J.ntaps);
+    const int r = (int)(t2 / J.ntaps);
+    float v = 0.f;
+    if (c < J.C_real) v = w[(long long)r * J.s_r + (long long)c * J.s_c + wtap[t]];
+    const int rg = r + J.r_off;
+    const int tile = rg / J.bn_tile, rr = rg - tile * J.bn_tile;
+    const long long k = (long long)t * J.tap_pitch + J.col_off + c;
+    const int kb = (int)(k >> 6), kk = (int)(k & 63);
+    const long long off = ((long long)tile * J.nkb + kb) * tile_elems + (rr >> 3) * 512 + (rr & 7) * 64 +
+                          (((kk >> 3) ^ (rr & 7)) << 3) + (kk & 7);
+    packed[off] = __float2bfloat16(v);
+  }
+}
+
 int pick_bn_tile(int Cout) {
   if (Cout <= 256) return (Cout + 15) & ~15;
   const int nt = (Cout + 255) / 256;
@@ -1007,5 +1041,14 @@ B2C_API int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, 
                                                                s_r, s_c, tap_pitch, col_off, r_off, bn_tile, nkb);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("pack_weights launch");
+  return 0;
+}
+
+B2C_API int b2c_pack_weights_batched(const b2c_pack_job* jobs_dev, const int32_t* block_start_dev, int32_t njobs, int32_t nblocks,
+                                     b2c_stream_t stream) {
+  B2C_REQUIRE(jobs_dev && block_start_dev && njobs > 0 && nblocks > 0, "pack_weights_batched: bad args");
+  pack_weights_batched_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, block_start_dev, njobs);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("pack_weights_batched launch");
   return 0;
 }
