@@ -140,10 +140,10 @@ class ConvLayer:
         in_dims = tuple(int(v) for v in in_dims)
         pl = self.plan(in_dims)
         w = self.weight
-        key = (w.data_ptr(), w._version, STATE.weights_epoch)
-        if self.keys.get((in_dims, which)) != key:
+        key = _packed_key(w)
+        if not _fresh(self.keys.get((in_dims, which)), key):
             pl.pack(w.detach(), which, ops.stream())
-            self.keys[(in_dims, which)] = key
+        self.keys[(in_dims, which)] = key
         return pl
 
 
