@@ -150,7 +150,8 @@ class TrainStep:
         from . import _abi
         l0 = _abi.launch_count()
         g = torch.cuda.CUDAGraph()
-        if self.world == 1:
+        import os
+        if self.world == 1 and not os.environ.get("B2C_FORCE_SPLIT_GRAPH"):
             with torch.cuda.graph(g):
                 out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
         else:
@@ -175,7 +176,8 @@ class TrainStep:
                 st[k].copy_(v, non_blocking=True)
         self.graph.replay()
         if self.graph_opt is not None:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.buckets.group)
+            if self.world > 1:
+                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.buckets.group)
             self.graph_opt.replay()
         return self.static_out
 
