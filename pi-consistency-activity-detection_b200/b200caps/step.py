@@ -100,6 +100,7 @@ class TrainStep:
         ranges = bucket_ranges(self.flat.offsets, {k: p.numel() for k, p in named.items()}, self.flat.n)
         self.buckets = GradBuckets(self.flat.grad, ranges, process_group)
         self.world = self.buckets.world
+        self.rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
         self._steps_seen = 0
         self.packs = ops.PackRegistry()
         self._split_comm = False     # graph mode on >1 GPU: the NCCL all-reduce runs between two graphs, not inside one
@@ -140,11 +141,20 @@ class TrainStep:
             for k, v in zip(("data", "fl_data", "action", "seg"), init_batch):
                 st[k].copy_(v)
         lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, dev)
+        import os, sys
+        dbg = bool(os.environ.get("B2C_DEBUG"))
+
+        def stage(msg):
+            if dbg:
+                torch.cuda.synchronize()
+                print(f"[b2c r{self.rank}] {msg}", file=sys.stderr, flush=True)
+        stage("capture: buffers ready")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):      # plans, packed-weight buffers, kernel attributes, allocator pools
+            for i in range(warmup):      # plans, packed-weight buffers, kernel attributes, allocator pools
                 self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+                stage(f"capture: warm-up step {i} done")
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _abi
@@ -161,9 +171,11 @@ class TrainStep:
             self._split_comm = True
             with torch.cuda.graph(g):
                 out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+            stage("capture: graph 1 captured")
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt):
                 self._optimizer()
+            stage("capture: graph 2 captured")
         self.launches_per_step = _abi.launch_count() - l0
         self.graph, self.static, self.static_out = g, st, out
         return self
@@ -174,11 +186,19 @@ class TrainStep:
         for k, v in (("data", data), ("fl_data", fl_data), ("action", action), ("seg", seg)):
             if v is not None:
                 st[k].copy_(v, non_blocking=True)
+        import os
+        dbg = bool(os.environ.get("B2C_DEBUG"))
         self.graph.replay()
+        if dbg:
+            torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: graph 1 ok", flush=True)
         if self.graph_opt is not None:
             if self.world > 1:
                 dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.buckets.group)
+                if dbg:
+                    torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: all-reduce ok", flush=True)
             self.graph_opt.replay()
+            if dbg:
+                torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: graph 2 ok", flush=True)
         return self.static_out
 
     # ---- the step ------------------------------------------------------------------------------------------
