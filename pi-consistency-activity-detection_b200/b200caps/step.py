@@ -188,6 +188,8 @@ class TrainStep:
                 st[k].copy_(v, non_blocking=True)
         import os
         dbg = bool(os.environ.get("B2C_DEBUG"))
+        if dbg:
+            torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: input copies ok ({'host' if data is not None and not data.is_cuda else 'device/none'})", flush=True)
         self.graph.replay()
         if dbg:
             torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: graph 1 ok", flush=True)
