@@ -189,7 +189,11 @@ class TrainStep:
         import os
         dbg = bool(os.environ.get("B2C_DEBUG"))
         if dbg:
-            torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: input copies ok ({'host' if data is not None and not data.is_cuda else 'device/none'})", flush=True)
+            torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: input copies ok ({'host' if data is not None and not data.is_cuda else 'device/none'}) "
+                                                    f"action={st['action'].flatten().tolist()} data_sum={float(st['data'].double().sum()):.3f} "
+                                                    f"fl_sum={float(st['fl_data'].double().sum()):.3f} seg_sum={float(st['seg'].sum()):.1f} "
+                                                    f"params_finite={bool(torch.isfinite(self.flat.data).all())} "
+                                                    f"grad_finite={bool(torch.isfinite(self.flat.grad).all())}", flush=True)
         self.graph.replay()
         if dbg:
             torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: graph 1 ok", flush=True)
