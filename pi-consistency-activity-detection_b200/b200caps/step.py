@@ -178,6 +178,9 @@ class TrainStep:
             stage("capture: graph 2 captured")
         self.launches_per_step = _abi.launch_count() - l0
         self.graph, self.static, self.static_out = g, st, out
+        # the graph reads these by address: they were allocated outside the graph's private pool, so they must outlive
+        # this call (dropping them let later allocations reuse the memory -> garbage labeled-clip indices in the graph)
+        self._graph_refs = (lab_idx, labels_dev, side)
         return self
 
     def replay(self, data=None, fl_data=None, action=None, seg=None):
