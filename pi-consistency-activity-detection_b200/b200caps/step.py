@@ -14,6 +14,7 @@ Host logic only; every number is produced by libb200caps.so kernels (torch is th
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -129,7 +130,7 @@ class TrainStep:
 
     # ---- CUDA graph ------------------------------------------------------------------------------------
     def capture(self, P: int, labels_host, epoch: int = 1, T: int = 8, H: int = 224, W: int = 224, warmup: int = 3,
-                init_batch=None):
+                init_batch=None, ddp_graph: Optional[str] = None):
         """Capture the whole step (both passes, losses, backward, all-reduce, Adam, weight re-packing) into one CUDA
         graph with static input buffers.  The labeled/unlabeled pattern and the epoch are baked into the graph.
         NOTE: `warmup` REAL optimisation steps are taken on `init_batch` (data, fl_data, action, seg) before the
@@ -141,45 +142,38 @@ class TrainStep:
             for k, v in zip(("data", "fl_data", "action", "seg"), init_batch):
                 st[k].copy_(v)
         lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, dev)
-        import os, sys
-        dbg = bool(os.environ.get("B2C_DEBUG"))
-
-        def stage(msg):
-            if dbg:
-                torch.cuda.synchronize()
-                print(f"[b2c r{self.rank}] {msg}", file=sys.stderr, flush=True)
-        stage("capture: buffers ready")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for i in range(warmup):      # plans, packed-weight buffers, kernel attributes, allocator pools
+            for _ in range(warmup):      # plans, packed-weight buffers, kernel attributes, allocator pools, NCCL channels
                 self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
-                stage(f"capture: warm-up step {i} done")
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _abi
         l0 = _abi.launch_count()
         g = torch.cuda.CUDAGraph()
-        import os
-        if self.world == 1 and not os.environ.get("B2C_FORCE_SPLIT_GRAPH"):
+        mode = ddp_graph or os.environ.get("B2C_DDP_GRAPH", "single")
+        if self.world == 1 and mode != "split":
             with torch.cuda.graph(g):
                 out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+        elif mode == "single":
+            # data parallel, one graph: the two bucketed NCCL all-reduces are captured on the communication stream
+            # (forked from / joined to the capture stream by events), the first one under the encoder backward
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
         else:
-            # data parallel: graph 1 = forward + backward, then ONE eager NCCL all-reduce of the flat gradient buffer,
-            # graph 2 = Adam + weight re-packing happens at the start of graph 1 of the next step.  (The bucketed
-            # all-reduce that overlaps the encoder backward is the eager path; 192 MB over NVLink is ~0.5 ms.)
+            # "split": graph 1 = forward + backward, ONE eager NCCL all-reduce of the flat gradient buffer,
+            # graph 2 = Adam (weight re-packing happens at the start of graph 1 of the next step)
             self._split_comm = True
             with torch.cuda.graph(g):
                 out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
-            stage("capture: graph 1 captured")
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt):
                 self._optimizer()
-            stage("capture: graph 2 captured")
         self.launches_per_step = _abi.launch_count() - l0
         self.graph, self.static, self.static_out = g, st, out
-        # the graph reads these by address: they were allocated outside the graph's private pool, so they must outlive
-        # this call (dropping them let later allocations reuse the memory -> garbage labeled-clip indices in the graph)
+        # The graph reads these by address and they live OUTSIDE its private pool, so they must outlive this call
+        # (dropping them lets later allocations reuse the memory -> garbage labeled-clip indices inside the graph).
         self._graph_refs = (lab_idx, labels_dev, side)
         return self
 
@@ -189,25 +183,11 @@ class TrainStep:
         for k, v in (("data", data), ("fl_data", fl_data), ("action", action), ("seg", seg)):
             if v is not None:
                 st[k].copy_(v, non_blocking=True)
-        import os
-        dbg = bool(os.environ.get("B2C_DEBUG"))
-        if dbg:
-            torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: input copies ok ({'host' if data is not None and not data.is_cuda else 'device/none'}) "
-                                                    f"action={st['action'].flatten().tolist()} data_sum={float(st['data'].double().sum()):.3f} "
-                                                    f"fl_sum={float(st['fl_data'].double().sum()):.3f} seg_sum={float(st['seg'].sum()):.1f} "
-                                                    f"params_finite={bool(torch.isfinite(self.flat.data).all())} "
-                                                    f"grad_finite={bool(torch.isfinite(self.flat.grad).all())}", flush=True)
         self.graph.replay()
-        if dbg:
-            torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: graph 1 ok", flush=True)
         if self.graph_opt is not None:
             if self.world > 1:
                 dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.buckets.group)
-                if dbg:
-                    torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: all-reduce ok", flush=True)
             self.graph_opt.replay()
-            if dbg:
-                torch.cuda.synchronize(); print(f"[b2c r{self.rank}] replay: graph 2 ok", flush=True)
         return self.static_out
 
     # ---- the step ------------------------------------------------------------------------------------------
