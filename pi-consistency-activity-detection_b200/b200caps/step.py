@@ -152,7 +152,7 @@ class TrainStep:
         from . import _abi
         l0 = _abi.launch_count()
         g = torch.cuda.CUDAGraph()
-        mode = ddp_graph or os.environ.get("B2C_DDP_GRAPH", "single")
+        mode = ddp_graph or os.environ.get("B2C_DDP_GRAPH", "split")   # "single" works but hangs NCCL teardown at exit
         if self.world == 1 and mode != "split":
             with torch.cuda.graph(g):
                 out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
