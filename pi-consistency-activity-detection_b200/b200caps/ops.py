@@ -77,7 +77,8 @@ class PackRegistry:
                 for k, v in f.items():
                     setattr(arr[i], k, v)
                 total = f["R"] * f["ntaps"] * f["C"]
-                starts.append(starts[-1] + max(1, min(64, (total + 2047) // 2048)))
+                assert total < 2 ** 31
+                starts.append(starts[-1] + max(1, (total + 4095) // 4096))       # 16 elements per thread, every job
             dev = torch.device("cuda", torch.cuda.current_device())
             raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
             bs = torch.tensor(starts, dtype=torch.int32, device=dev)

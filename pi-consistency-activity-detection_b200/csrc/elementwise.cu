@@ -538,44 +538,71 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
 struct Im2colGeom {
   int N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad;
 };
-// One warp per output row.  For a fixed (kt, kh) the kw x C block of the im2col row is kw consecutive input pixels
-// (16 bytes each, channels-last with Cs = 8), i.e. one contiguous run: each lane gathers whole (kt,kh) runs with
-// 16-byte loads into a shared row image, then the warp streams the Kpad-wide row out with coalesced 16-byte stores.
-__global__ void __launch_bounds__(kBlock) im2col_small_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Im2colGeom G) {
+// One block per strip of WB consecutive output positions along W at a fixed (n, to, ho).  The strip's input footprint
+// -- kt*kh input rows x ((WB-1)*sw + kw) pixels, real channels only -- is staged in shared memory (zero outside the
+// volume), so that the (kw x C) block of an im2col row for a fixed (kt, kh) is one contiguous run of the staged row.
+// The Kpad-wide rows then stream out as coalesced 16-byte stores, each assembled from 8 staged elements through a
+// per-block column -> staged-offset table (padding columns point at a zero slot).
+constexpr int kIm2colWB = 56;
+__global__ void __launch_bounds__(kBlock) im2col_small_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Im2colGeom G,
+                                                              int strips, int pitch) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  const int warps = kBlock / 32;
-  const int w_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  bf16* srow = reinterpret_cast<bf16*>(s_raw) + (size_t)w_id * G.Kpad;
-  const long long rows = (long long)G.N * G.To * G.Ho * G.Wo;
   const int pairs = G.kt * G.kh;
   const int run = G.kw * G.C;
-  // zero the padding tail once (columns K..Kpad never change)
-  for (int k = G.K + lane; k < G.Kpad; k += 32) srow[k] = __float2bfloat16(0.f);
-  for (long long row = (long long)blockIdx.x * warps + w_id; row < rows; row += (long long)gridDim.x * warps) {
-    long long r = row;
-    const int wo = (int)(r % G.Wo); r /= G.Wo;
+  const int zero_slot = pairs * pitch;
+  unsigned short* tab = reinterpret_cast<unsigned short*>(s_raw);                       // Kpad entries
+  bf16* sin = reinterpret_cast<bf16*>(s_raw + (size_t)G.Kpad * 2);                      // pairs * pitch + 8 elements
+  for (int k = threadIdx.x; k < G.Kpad; k += kBlock) {
+    int off = zero_slot;
+    if (k < G.K) {
+      const int p = k / run;
+      off = p * pitch + (k - p * run);
+    }
+    tab[k] = (unsigned short)off;
+  }
+  if (threadIdx.x < 8) sin[zero_slot + threadIdx.x] = __float2bfloat16(0.f);
+  const int wpix = (kIm2colWB - 1) * G.sw + G.kw;                                       // staged pixels per input row
+  const int vec_per_row = G.Kpad / 8;
+  const long long nblk = (long long)G.N * G.To * G.Ho * strips;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    long long r = blk;
+    const int sidx = (int)(r % strips); r /= strips;
     const int ho = (int)(r % G.Ho); r /= G.Ho;
     const int to = (int)(r % G.To); r /= G.To;
     const int n = (int)r;
-    const int t0 = to * G.st - G.pt, h0 = ho * G.sh - G.ph, w0 = wo * G.sw - G.pw;
-    for (int p = lane; p < pairs; p += 32) {
+    const int wo0 = sidx * kIm2colWB;
+    const int nrow = min(kIm2colWB, G.Wo - wo0);
+    const int t0 = to * G.st - G.pt, h0 = ho * G.sh - G.ph, w0 = wo0 * G.sw - G.pw;
+    __syncthreads();                                                                    // previous strip fully written out
+    for (int i = threadIdx.x; i < pairs * wpix; i += kBlock) {
+      const int p = i / wpix, wl = i - p * wpix;
       const int a = p / G.kh, b = p - a * G.kh;
-      const int t = t0 + a, h = h0 + b;
-      const bool rowok = (unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H;
-      const bf16* src = x + (((long long)n * G.T + t) * G.H + h) * (long long)G.W * G.Cs;
-      bf16* dst = srow + p * run;
-      for (int c = 0; c < G.kw; ++c) {
-        const int w = w0 + c;
-        uint4 px = make_uint4(0, 0, 0, 0);
-        if (rowok && (unsigned)w < (unsigned)G.W) px = ld16(src + (long long)w * G.Cs);   // Cs == 8: one pixel = 16 bytes
-        const bf16* pv = reinterpret_cast<const bf16*>(&px);
-        for (int ch = 0; ch < G.C; ++ch) dst[c * G.C + ch] = pv[ch];
-      }
+      const int t = t0 + a, h = h0 + b, w = w0 + wl;
+      uint4 px = make_uint4(0, 0, 0, 0);
+      if ((unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H && (unsigned)w < (unsigned)G.W)
+        px = ld16(x + ((((long long)n * G.T + t) * G.H + h) * (long long)G.W + w) * G.Cs);   // Cs == 8: one pixel = 16 bytes
+      const bf16* pv = reinterpret_cast<const bf16*>(&px);
+      bf16* dst = sin + p * pitch + wl * G.C;
+      for (int ch = 0; ch < G.C; ++ch) dst[ch] = pv[ch];
     }
-    __syncwarp();
-    bf16* orow = out + row * G.Kpad;
-    for (int v = lane; v < G.Kpad / 8; v += 32) st16(orow + v * 8, *reinterpret_cast<const uint4*>(srow + v * 8));
-    __syncwarp();
+    __syncthreads();
+    bf16* obase = out + ((((long long)n * G.To + to) * G.Ho + ho) * (long long)G.Wo + wo0) * G.Kpad;
+    const unsigned short* sraw = reinterpret_cast<const unsigned short*>(sin);
+    for (int i = threadIdx.x; i < nrow * vec_per_row; i += kBlock) {
+      const int rl = i / vec_per_row, v = i - rl * vec_per_row;
+      const uint4 tv = *reinterpret_cast<const uint4*>(tab + v * 8);
+      const int base = rl * G.sw * G.C;
+      const unsigned tw[4] = {tv.x, tv.y, tv.z, tv.w};
+      unsigned o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o0 = (int)(tw[j] & 0xffffu), o1 = (int)(tw[j] >> 16);
+        const unsigned e0 = sraw[o0 == zero_slot ? o0 : o0 + base];
+        const unsigned e1 = sraw[o1 == zero_slot ? o1 : o1 + base];
+        o[j] = e0 | (e1 << 16);
+      }
+      st16(obase + (long long)rl * G.Kpad + v * 8, make_uint4(o[0], o[1], o[2], o[3]));
+    }
   }
 }
 
@@ -808,11 +835,14 @@ B2C_API int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, in
                              int32_t pt, int32_t ph, int32_t pw, int32_t Kpad, b2c_stream_t s) {
   B2C_REQUIRE(x && out && N > 0 && C > 0 && C <= Cs && C < 256, "im2col_small: bad args");
   const int K = kt * kh * kw * C;
-  B2C_REQUIRE(Kpad % 64 == 0 && Kpad >= K && Cs == 8 && (kBlock / 32) * Kpad * 2 <= 48 * 1024, "im2col_small: bad K / Cs");
+  B2C_REQUIRE(Kpad % 64 == 0 && Kpad >= K && Cs == 8, "im2col_small: bad K / Cs");
   Im2colGeom G{N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad};
-  const long long rows = (long long)N * To * Ho * Wo;
-  im2col_small_kernel<<<grid_for(rows, kBlock / 32, 16), kBlock, (kBlock / 32) * Kpad * 2, (cudaStream_t)s>>>((const bf16*)x,
-                                                                                                              (bf16*)out, G);
+  const int pitch = ((kIm2colWB - 1) * sw + kw) * C;
+  const size_t smem = (size_t)Kpad * 2 + ((size_t)kt * kh * pitch + 8) * 2;
+  B2C_REQUIRE(smem <= 48 * 1024 && (size_t)kt * kh * pitch + 8 < 65536, "im2col_small: footprint too large");
+  const int strips = (Wo + kIm2colWB - 1) / kIm2colWB;
+  const long long nblk = (long long)N * To * Ho * strips;
+  im2col_small_kernel<<<grid_for(nblk, 1, 32), kBlock, smem, (cudaStream_t)s>>>((const bf16*)x, (bf16*)out, G, strips, pitch);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("im2col_small");
   return 0;

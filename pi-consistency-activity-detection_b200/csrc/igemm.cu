@@ -53,12 +53,13 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) {
 //   warps 0-3 : im2col gather producers (one GEMM row per thread, 16-byte cp.async with zero fill);
 //               thread 0 also arms the bulk copy of the pre-swizzled weight tile of each K-block
 //   warp  4   : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 5-8 : epilogue (TMEM -> registers -> bias / scale / ReLU / sigmoid -> global), overlapped with the
-//               next tile's main loop through two TMEM accumulators
+//   warps 5-12: epilogue (TMEM -> registers -> bias / scale / ReLU / sigmoid -> global), two warps per TMEM lane
+//               quarter splitting the columns, overlapped with the next tile's main loop through two TMEM accumulators
 // Each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and its mbarrier phases run
 // continuously across tiles, so there is no pipeline drain / fill between tiles.
 // =====================================================================================
-constexpr int kFpropThreads = 288;
+constexpr int kMaxScaleSmem = 4096;   // floats of dropout scale kept in shared memory
+constexpr int kFpropThreads = 416;   // 4 producer warps + 1 MMA warp + 8 epilogue warps
 
 struct alignas(64) TmaMaps {
   CUtensorMap a[8];   // per class: im2col map of the gathered activation view
@@ -126,6 +127,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   // epilogue staging (bf16 rows, pitch acc_cols*2 + 16 bytes: conflict-free 16-byte shared stores), after the tap tables
   const uint32_t stg_pitch = (uint32_t)(acc_cols * 2 + 16);
   const uint32_t stg_base = (smem_base + (uint32_t)stages * stage_bytes + (uint32_t)sizeof(FpropSmem) + (uint32_t)sum_taps * 4 + 15u) & ~15u;
+  // bias (Cout floats, zeros when the layer has none) and, when it fits, the per-(clip, channel) dropout scale
+  float* s_bias = reinterpret_cast<float*>(smem_al + (stg_base - smem_base) + (size_t)kTileM * stg_pitch);
+  float* s_scale = s_bias + ((d.Cout + 3) & ~3);
+  const bool scale_smem = d.scale_nc != nullptr && d.N * d.Cout <= kMaxScaleSmem;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -142,6 +147,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     for (int c = 0; c < d.nclass; ++c)
       for (int i = tid; i < d.cls[c].ntaps; i += kFpropThreads) s_taps[tap_off[c] + i] = d.cls[c].taps[i];
   }
+  for (int i = tid; i < d.Cout; i += kFpropThreads) s_bias[i] = d.bias ? d.bias[i] : 0.f;
+  if (scale_smem)
+    for (int i = tid; i < d.N * d.Cout; i += kFpropThreads) s_scale[i] = d.scale_nc[i];
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       // gather path: 128 gather threads + the thread that arms the weight bulk copy; TMA path: one producer thread
@@ -150,8 +158,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     }
     mbar_init(&ps->tfull[0], 1);
     mbar_init(&ps->tfull[1], 1);
-    mbar_init(&ps->tempty[0], 128);
-    mbar_init(&ps->tempty[1], 128);
+    mbar_init(&ps->tempty[0], 256);
+    mbar_init(&ps->tempty[1], 256);
     fence_barrier_init();
   }
   const uint32_t tmem_cols = tmem_cols_for(2 * acc_cols);
@@ -330,8 +338,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ------------------------------ epilogue (warps 5..8) ---------------------------
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    // ------------------------------ epilogue (warps 5..12) --------------------------
+    // Warp w may only touch TMEM lanes 32*(w&3)..+31, so two warps share each lane quarter and split the tile's
+    // columns [0,sp) / [sp,bn16) (ncu r01b: with 4 epilogue warps the short-K layers were epilogue-latency bound,
+    // tensor pipe 20 % active).  Bias / dropout scale come from shared memory and are fetched while the TMEM load
+    // is in flight.
+    const int quarter = warp & 3;
+    const int half = (warp - 5) >> 2;
     const bool staged = (d.out_fp32 == 0 && !d.accumulate);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -342,6 +355,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       int bn = d.Cout - n0;
       if (bn > d.bn_tile) bn = d.bn_tile;
       const int bn16 = (bn + 15) & ~15;
+      int sp = ((bn16 + 63) >> 6) << 5;
+      if (sp > bn16) sp = bn16;
+      const int cbeg = half ? sp : 0, cend = half ? bn16 : sp;
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
       const unsigned m = (unsigned)ti.m0 + (unsigned)(quarter * 32 + lane);
       const bool mvalid = m < Mtot;
@@ -356,84 +372,44 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
         opos = (((long long)n_i * d.To + (qt * d.so_t + cc.po_t)) * d.Ho + (qh * d.so_h + cc.po_h)) * d.Wo +
                (qw * d.so_w + cc.po_w);
       }
-      const float* scale_row = d.scale_nc ? d.scale_nc + (long long)n_i * d.Cout : nullptr;
+      const float* scale_row = nullptr;
+      if (d.scale_nc) scale_row = scale_smem ? s_scale + n_i * d.Cout : d.scale_nc + (long long)n_i * d.Cout;
+      const uint32_t srow = stg_base + (uint32_t)(quarter * 32 + lane) * stg_pitch;
+      if (staged) bulk_wait_read0();   // this thread's previous row segment has left shared memory
       mbar_wait(&ps->tfull[acc], acc_phase, 3);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
-      if (staged) {
-        // bf16 row output: registers -> padded smem row -> ONE bulk async store per row (full 128-byte lines instead of
-        // 32 partial sectors per store instruction; ncu r01: 32 sectors/request, epilogue-bound short-K tiles)
-        const uint32_t srow = stg_base + (uint32_t)(quarter * 32 + lane) * stg_pitch;
-        bulk_wait_read0();   // this thread's previous row has left shared memory
-        for (int c0 = 0; c0 < bn16; c0 += 32) {
-          float v[32];
-          const int nh = (bn16 - c0 >= 32) ? 4 : 2;
-          if (nh == 4) tmem_ld32(t_lane + (uint32_t)c0, v);
-          else tmem_ld16(t_lane + (uint32_t)c0, v);
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        uint32_t r[32];
+        const int nh = (cend - c0 >= 32) ? 4 : 2;
+        if (nh == 4) tmem_ld32_issue(t_lane + (uint32_t)c0, r);
+        else tmem_ld16_issue(t_lane + (uint32_t)c0, r);
+        float4 bb[8], ss[8];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            if (h >= nh) break;
-            const int col = n0 + c0 + h * 8;
-            if (col >= d.Cout) break;
-            float* vv = v + h * 8;
-            if (d.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(d.bias + col + 4));
-              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-            }
-            if (scale_row) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_row + col));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale_row + col + 4));
-              vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
-              vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
-            }
-            if (d.relu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
-            }
-            if (d.sigmoid_from >= 0 && col >= d.sigmoid_from) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
-            }
-            st_shared16(srow + (uint32_t)(c0 + h * 8) * 2, pack8(vv));
+        for (int h = 0; h < 4; ++h) {
+          const int col = n0 + c0 + h * 8;
+          const bool on = h < nh && col < d.Cout;
+          bb[2 * h] = on ? *reinterpret_cast<const float4*>(s_bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bb[2 * h + 1] = on ? *reinterpret_cast<const float4*>(s_bias + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (scale_row) {
+            ss[2 * h] = on ? *reinterpret_cast<const float4*>(scale_row + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+            ss[2 * h + 1] = on ? *reinterpret_cast<const float4*>(scale_row + col + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
           }
         }
-        tc_fence_before();
-        mbar_arrive(&ps->tempty[acc]);       // accumulator drained: the MMA warp may start the tile after next
-        fence_proxy_async_smem();
-        if (mvalid) {
-          bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + n0;
-          int ncols = d.Cout - n0;
-          if (ncols > bn) ncols = bn;
-          bulk_s2g(o, srow, (uint32_t)ncols * 2);
-        }
-        bulk_commit();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-        continue;
-      }
-      for (int c0 = 0; c0 < bn16; c0 += 32) {
-        float v[32];
-        const int nh = (bn16 - c0 >= 32) ? 4 : 2;
-        if (nh == 4) tmem_ld32(t_lane + (uint32_t)c0, v);
-        else tmem_ld16(t_lane + (uint32_t)c0, v);
-        if (!mvalid) continue;
+        tmem_ld_fence(r);
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           if (h >= nh) break;
           const int col = n0 + c0 + h * 8;
           if (col >= d.Cout) break;
-          float* vv = v + h * 8;
-          if (d.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(d.bias + col + 4));
-            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-          }
+          float vv[8];
+          const float4 b0 = bb[2 * h], b1 = bb[2 * h + 1];
+          vv[0] = __uint_as_float(r[h * 8 + 0]) + b0.x; vv[1] = __uint_as_float(r[h * 8 + 1]) + b0.y;
+          vv[2] = __uint_as_float(r[h * 8 + 2]) + b0.z; vv[3] = __uint_as_float(r[h * 8 + 3]) + b0.w;
+          vv[4] = __uint_as_float(r[h * 8 + 4]) + b1.x; vv[5] = __uint_as_float(r[h * 8 + 5]) + b1.y;
+          vv[6] = __uint_as_float(r[h * 8 + 6]) + b1.z; vv[7] = __uint_as_float(r[h * 8 + 7]) + b1.w;
           if (scale_row) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_row + col));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale_row + col + 4));
+            const float4 s0 = ss[2 * h], s1 = ss[2 * h + 1];
             vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
             vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
           }
@@ -445,7 +421,12 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
           }
-          if (d.out_fp32 == 2) {
+          if (staged) {
+            // bf16 rows: registers -> padded smem row segment -> ONE bulk async store per (row, column half)
+            st_shared16(srow + (uint32_t)(c0 + h * 8) * 2, pack8(vv));
+          } else if (!mvalid) {
+            // nothing to write for rows past the end of the class
+          } else if (d.out_fp32 == 2) {
             // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
             float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
 #pragma unroll
@@ -477,7 +458,16 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
         }
       }
       tc_fence_before();
-      mbar_arrive(&ps->tempty[acc]);
+      mbar_arrive(&ps->tempty[acc]);       // accumulator drained: the MMA warp may start the tile after next
+      if (staged) {
+        fence_proxy_async_smem();
+        int ce = bn < cend ? bn : cend;    // real columns of this half
+        if (mvalid && ce > cbeg) {
+          bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + n0 + cbeg;
+          bulk_s2g(o, srow + (uint32_t)cbeg * 2, (uint32_t)(ce - cbeg) * 2);
+        }
+        bulk_commit();
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -853,17 +843,17 @@ __global__ void pack_weights_batched_kernel(const b2c_pack_job* __restrict__ job
   const float* __restrict__ w = reinterpret_cast<const float*>(J.w);
   bf16* __restrict__ packed = reinterpret_cast<bf16*>(J.packed);
   const int32_t* __restrict__ wtap = J.wtap;
-  const long long total = (long long)J.R * J.ntaps * J.C;
+  // (host guarantees R * ntaps * C < 2^31: 32-bit index arithmetic)
+  const unsigned total = (unsigned)J.R * (unsigned)J.ntaps * (unsigned)J.C;
+  const unsigned C = (unsigned)J.C, ntaps = (unsigned)J.ntaps, bn = (unsigned)J.bn_tile;
   const long long tile_elems = (long long)J.bn_tile * 64;
-  for (long long i = (long long)bidx * blockDim.x + threadIdx.x; i < total; i += (long long)nblk * blockDim.x) {
-    const int c = (int)(i % J.C);
-    const long long t2 = i / J.C;
-    const int t = (int)(t2 % J.ntaps);
-    const int r = (int)(t2 / J.ntaps);
+  for (unsigned i = (unsigned)bidx * blockDim.x + threadIdx.x; i < total; i += (unsigned)nblk * blockDim.x) {
+    const unsigned t2 = i / C, c = i - t2 * C;
+    const unsigned r = t2 / ntaps, t = t2 - r * ntaps;
     float v = 0.f;
-    if (c < J.C_real) v = w[(long long)r * J.s_r + (long long)c * J.s_c + wtap[t]];
-    const int rg = r + J.r_off;
-    const int tile = rg / J.bn_tile, rr = rg - tile * J.bn_tile;
+    if ((int)c < J.C_real) v = __ldg(w + (long long)r * J.s_r + (long long)c * J.s_c + wtap[t]);
+    const unsigned rg = r + (unsigned)J.r_off;
+    const unsigned tile = rg / bn, rr = rg - tile * bn;
     const long long k = (long long)t * J.tap_pitch + J.col_off + c;
     const int kb = (int)(k >> 6), kk = (int)(k & 63);
     const long long off = ((long long)tile * J.nkb + kb) * tile_elems + (rr >> 3) * 512 + (rr & 7) * 64 +
@@ -917,7 +907,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   const int acc_cols = (d.bn_tile + 15) & ~15;
   const int stage_bytes = kATileBytes + (((acc_cols * 128) + 1023) & ~1023);
   const int staging = kTileM * (acc_cols * 2 + 16) + 16;
-  const int fixed = (int)sizeof(FpropSmem) + sum_taps * 4 + staging + 1024 + 64;
+  const int vecs = (((d.Cout + 3) & ~3) + ((d.scale_nc && d.N * d.Cout <= kMaxScaleSmem) ? d.N * d.Cout : 0)) * 4;
+  const int fixed = (int)sizeof(FpropSmem) + sum_taps * 4 + staging + vecs + 1024 + 64;
   int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B2C_REQUIRE(stages >= 3, "conv_fprop: tile too large for shared memory");
