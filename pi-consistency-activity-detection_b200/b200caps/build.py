@@ -14,7 +14,7 @@ OUT = os.path.join(HERE, "libb200caps.so")
 OBJ = os.path.join(CSRC, "_obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"] + os.environ.get("B2C_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -24,6 +24,21 @@ long long b2c_launches_add(long long n) {
 
 namespace {
 
+// Optional in-kernel phase timing (compile with -DB2C_PROF): CTA 0 prints, per warp role, total cycles and the
+// cycles spent waiting on each mbarrier.
+#ifdef B2C_PROF
+#define B2C_PROF_DECL(x) long long x = 0
+#define B2C_PROF_START(x) x = clock64()
+#define B2C_PROF_ACC(a, t0) a += clock64() - t0
+#define B2C_PROF_PRINT2(name, t0, a, b) \
+  if (blockIdx.x == 0) printf("[prof] %-14s total %lld cyc  waitA %lld  B %lld  tiles/CTA %lld\n", name, clock64() - t0, (long long)(a), (long long)(b), (total_tiles + gridDim.x - 1) / gridDim.x)
+#else
+#define B2C_PROF_DECL(x)
+#define B2C_PROF_START(x)
+#define B2C_PROF_ACC(a, t0)
+#define B2C_PROF_PRINT2(name, t0, a, b)
+#endif
+
 constexpr int kTileM = 128;      // UMMA M
 constexpr int kBlockK = 64;      // bf16 elements per 128-byte swizzle row
 constexpr int kATileBytes = kTileM * 128;
@@ -75,6 +90,31 @@ __device__ __forceinline__ void tma_im2col_5d(uint32_t dst, const CUtensorMap* m
       : "memory");
 }
 
+// Division by a runtime-constant divisor (Granlund-Montgomery): q = n / d for any 32-bit n.  The per-tile index
+// arithmetic (tile -> class -> (clip, t, h, w)) sat on every warp's critical path as hardware-emulated divisions.
+struct FastDiv {
+  uint32_t m, sh1, sh2, d;
+};
+__device__ __forceinline__ FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < (unsigned long long)d) ++l;
+  f.m = (uint32_t)((((1ull << l) - d) << 32) / d + 1ull);
+  f.sh1 = l < 1 ? l : 1;
+  f.sh2 = l > 0 ? l - 1 : 0;
+  f.d = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+// q -> (q / d, q % d)
+__device__ __forceinline__ uint32_t fdivmod(uint32_t n, const FastDiv& f, uint32_t& rem) {
+  const uint32_t q = fdiv(n, f);
+  rem = n - q * f.d;
+  return q;
+}
 struct FpropSmem {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -82,6 +122,7 @@ struct FpropSmem {
   uint64_t tempty[2];
   uint32_t tmem_base;
   uint32_t pad_;
+  FastDiv fd[25];   // [3*c + 0/1/2] = Qw / Qh / Qt of class c; [24] = n_tiles
 };
 
 struct TileInfo {
@@ -92,7 +133,7 @@ struct TileSched {
   unsigned start[9];   // first tile index of each class (prefix sums), start[nclass] = total
 };
 
-__device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass, long long t, int n_tiles) {
+__device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass, long long t, int n_tiles, const FastDiv& fnt) {
   TileInfo ti;
   int c = 0;
 #pragma unroll
@@ -104,8 +145,10 @@ __device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass,
     ti.n_idx = 0;
     ti.m0 = (long long)local * kTileM;
   } else {
-    ti.n_idx = (int)(local % (unsigned)n_tiles);
-    ti.m0 = (long long)(local / (unsigned)n_tiles) * kTileM;
+    uint32_t rem;
+    const uint32_t q = fdivmod(local, fnt, rem);
+    ti.n_idx = (int)rem;
+    ti.m0 = (long long)q * kTileM;
   }
   return ti;
 }
@@ -147,6 +190,16 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     for (int c = 0; c < d.nclass; ++c)
       for (int i = tid; i < d.cls[c].ntaps; i += kFpropThreads) s_taps[tap_off[c] + i] = d.cls[c].taps[i];
   }
+  const FastDiv* s_fd = ps->fd;
+  if (tid < 25) {
+    uint32_t dv = (uint32_t)n_tiles;
+    if (tid < 24) {
+      const int c = tid / 3, k = tid - 3 * c;
+      dv = 1;
+      if (c < d.nclass) dv = (uint32_t)(k == 0 ? d.cls[c].Qw : k == 1 ? d.cls[c].Qh : d.cls[c].Qt);
+    }
+    ps->fd[tid] = make_fastdiv(dv < 1 ? 1u : dv);
+  }
   for (int i = tid; i < d.Cout; i += kFpropThreads) s_bias[i] = d.bias ? d.bias[i] : 0.f;
   if (scale_smem)
     for (int i = tid; i < d.N * d.Cout; i += kFpropThreads) s_scale[i] = d.scale_nc[i];
@@ -176,14 +229,16 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       int stage = 0;
       uint32_t phase = 0;
       const int cblocks = d.Cin / kBlockK;
+      B2C_PROF_DECL(p_wait); B2C_PROF_DECL(p_t0); B2C_PROF_START(p_t0);
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
+        const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
         const b2c_conv_class& cc = d.cls[ti.cls];
         const int32_t* taps = s_taps + tap_off[ti.cls];
-        unsigned q = (unsigned)ti.m0;
-        const int qw = (int)(q % (unsigned)cc.Qw); q /= (unsigned)cc.Qw;
-        const int qh = (int)(q % (unsigned)cc.Qh); q /= (unsigned)cc.Qh;
-        const int qt = (int)(q % (unsigned)cc.Qt); q /= (unsigned)cc.Qt;
+        uint32_t rw, rh, rt;
+        uint32_t q = fdivmod((uint32_t)ti.m0, s_fd[3 * ti.cls], rw);
+        q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
+        q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
+        const int qw = (int)rw, qh = (int)rh, qt = (int)rt;
         const int n_i = (int)q;
         const int bw = qw * d.si_w + cc.lo_w, bh = qh * d.si_h + cc.lo_h, bt = qt * d.si_t + cc.lo_t;
         const int nkb = cc.ntaps * cblocks;
@@ -195,7 +250,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
           const uint16_t ow = (uint16_t)(tap_dw(tv) - cc.lo_w), oh = (uint16_t)(tap_dh(tv) - cc.lo_h),
                          ot = (uint16_t)(tap_dt(tv) - cc.lo_t);
           for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+            B2C_PROF_DECL(w0); B2C_PROF_START(w0);
             mbar_wait(&ps->empty[stage], phase ^ 1, 1);
+            B2C_PROF_ACC(p_wait, w0);
             const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
             mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)(kATileBytes + b_tile_bytes));
             tma_im2col_5d(a_st, map, &ps->full[stage], cb * kBlockK, bw, bh, bt, n_i, ow, oh, ot);
@@ -207,6 +264,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
           }
         }
       }
+      B2C_PROF_PRINT2("producer(tma)", p_t0, p_wait, 0);
     }
   } else if (warp < 4) {
     // ------------------------------ gather producers (Cin not a multiple of 64) --------
@@ -218,7 +276,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     uint32_t phase = 0;
     long long issued = 0;   // K-blocks issued so far by this CTA (all tiles)
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int32_t* taps = s_taps + tap_off[ti.cls];
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
@@ -226,10 +284,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       const bool mvalid = m < Mtot;
       int n_i = 0, qt = 0, qh = 0, qw = 0;
       if (mvalid) {
-        unsigned q = m;
-        qw = (int)(q % (unsigned)cc.Qw); q /= (unsigned)cc.Qw;
-        qh = (int)(q % (unsigned)cc.Qh); q /= (unsigned)cc.Qh;
-        qt = (int)(q % (unsigned)cc.Qt); q /= (unsigned)cc.Qt;
+        uint32_t rw, rh, rt;
+        uint32_t q = fdivmod(m, s_fd[3 * ti.cls], rw);
+        q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
+        q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
+        qw = (int)rw; qh = (int)rh; qt = (int)rt;
         n_i = (int)q;
       }
       const int it0 = qt * d.si_t, ih0 = qh * d.si_h, iw0 = qw * d.si_w;
@@ -300,8 +359,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    B2C_PROF_DECL(m_wfull); B2C_PROF_DECL(m_wtempty); B2C_PROF_DECL(m_t0); B2C_PROF_START(m_t0);
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int n0 = ti.n_idx * d.bn_tile;
       int bn = d.Cout - n0;
@@ -310,10 +370,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       const int nkb = (cc.ntaps * d.Cin + kBlockK - 1) / kBlockK;
       const uint32_t idesc = umma_idesc_bf16(bn16, 0, 0);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+      B2C_PROF_DECL(w1); B2C_PROF_START(w1);
       mbar_wait(&ps->tempty[acc], acc_phase ^ 1, 4);   // epilogue has drained this accumulator
+      B2C_PROF_ACC(m_wtempty, w1);
       tc_fence_after();
       for (int kb = 0; kb < nkb; ++kb) {
+        B2C_PROF_DECL(w2); B2C_PROF_START(w2);
         mbar_wait(&ps->full[stage], phase, 2);
+        B2C_PROF_ACC(m_wfull, w2);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
@@ -337,6 +401,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) { B2C_PROF_PRINT2("mma", m_t0, m_wfull, m_wtempty); }
   } else {
     // ------------------------------ epilogue (warps 5..12) --------------------------
     // Warp w may only touch TMEM lanes 32*(w&3)..+31, so two warps share each lane quarter and split the tile's
@@ -348,8 +413,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     const bool staged = (d.out_fp32 == 0 && !d.accumulate);
     int acc = 0;
     uint32_t acc_phase = 0;
+    B2C_PROF_DECL(e_wait); B2C_PROF_DECL(e_cols); B2C_PROF_DECL(e_t0); B2C_PROF_START(e_t0);
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int n0 = ti.n_idx * d.bn_tile;
       int bn = d.Cout - n0;
@@ -364,10 +430,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       long long opos = 0;
       int n_i = 0;
       if (mvalid) {
-        unsigned q = m;
-        const int qw = (int)(q % (unsigned)cc.Qw); q /= (unsigned)cc.Qw;
-        const int qh = (int)(q % (unsigned)cc.Qh); q /= (unsigned)cc.Qh;
-        const int qt = (int)(q % (unsigned)cc.Qt); q /= (unsigned)cc.Qt;
+        uint32_t rw, rh, rt;
+        uint32_t q = fdivmod(m, s_fd[3 * ti.cls], rw);
+        q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
+        q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
+        const int qw = (int)rw, qh = (int)rh, qt = (int)rt;
         n_i = (int)q;
         opos = (((long long)n_i * d.To + (qt * d.so_t + cc.po_t)) * d.Ho + (qh * d.so_h + cc.po_h)) * d.Wo +
                (qw * d.so_w + cc.po_w);
@@ -375,8 +442,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       const float* scale_row = nullptr;
       if (d.scale_nc) scale_row = scale_smem ? s_scale + n_i * d.Cout : d.scale_nc + (long long)n_i * d.Cout;
       const uint32_t srow = stg_base + (uint32_t)(quarter * 32 + lane) * stg_pitch;
-      if (staged) bulk_wait_read0();   // this thread's previous row segment has left shared memory
+      B2C_PROF_DECL(w3); B2C_PROF_START(w3);
       mbar_wait(&ps->tfull[acc], acc_phase, 3);
+      B2C_PROF_ACC(e_wait, w3);
+      B2C_PROF_DECL(w4); B2C_PROF_START(w4);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
@@ -422,7 +491,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
             for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
           }
           if (staged) {
-            // bf16 rows: registers -> padded smem row segment -> ONE bulk async store per (row, column half)
+            // bf16 rows: registers -> padded smem row segment (conflict-free 16-byte stores), streamed out below
             st_shared16(srow + (uint32_t)(c0 + h * 8) * 2, pack8(vv));
           } else if (!mvalid) {
             // nothing to write for rows past the end of the class
@@ -459,19 +528,37 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       }
       tc_fence_before();
       mbar_arrive(&ps->tempty[acc]);       // accumulator drained: the MMA warp may start the tile after next
+      B2C_PROF_ACC(e_cols, w4);
       if (staged) {
-        fence_proxy_async_smem();
-        int ce = bn < cend ? bn : cend;    // real columns of this half
-        if (mvalid && ce > cbeg) {
-          bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + n0 + cbeg;
-          bulk_s2g(o, srow + (uint32_t)cbeg * 2, (uint32_t)(ce - cbeg) * 2);
+        // The warp stored its 32 rows x [cbeg, cend) columns in shared memory (one row per lane); now it streams them
+        // out with lanes running along the row: full 16-byte vectors, segv lanes per row -> whole 128-byte lines per
+        // request.  (ncu r01b/c: one cp.async.bulk per row serialises lane by lane -- UBLKCP takes uniform operands --
+        // and 256 bulk stores per tile kept the epilogue warps 87 % busy with the tensor pipe at 22 %.)
+        __syncwarp();
+        const int ce = bn < cend ? bn : cend;          // real columns of this half
+        const int segv = ce > cbeg ? (ce - cbeg) >> 3 : 0;
+        const long long obyte = mvalid ? (opos * d.out_row_stride + d.out_c_off + n0 + cbeg) * 2 : -1;
+        const uint32_t sseg = stg_base + (uint32_t)(quarter * 32) * stg_pitch + (uint32_t)cbeg * 2;
+        int lsh = 0;                                   // lanes per row = 2^lsh >= segv (<= 32 vectors per row segment)
+        while ((1 << lsh) < segv) ++lsh;
+        const int vcol = lane & ((1 << lsh) - 1), rsub = lane >> lsh, rstep = 32 >> lsh;
+        const int iters = segv > 0 ? (1 << lsh) : 0;
+        for (int it = 0; it < iters; ++it) {
+          const int rl = it * rstep + rsub;
+          const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(obyte & 0xffffffffll), rl);
+          const int hi = __shfl_sync(0xffffffffu, (int)(obyte >> 32), rl);
+          if (hi >= 0 && vcol < segv) {
+            const uint4 val = ld_shared16(sseg + (uint32_t)rl * stg_pitch + (uint32_t)vcol * 16);
+            uint8_t* o = reinterpret_cast<uint8_t*>(d.out) + (((long long)hi << 32) | (long long)lo) + vcol * 16;
+            *reinterpret_cast<uint4*>(o) = val;
+          }
         }
-        bulk_commit();
+        __syncwarp();
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    bulk_wait0();   // all bulk stores of this thread have completed before the CTA retires
+    if (lane == 0 && (warp == 5 || warp == 9)) { B2C_PROF_PRINT2(warp == 5 ? "epilogue(w5)" : "epilogue(w9)", e_t0, e_wait, e_cols); }
   }
   __syncthreads();
   if (warp == 4) {
