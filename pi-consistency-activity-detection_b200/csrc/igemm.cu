@@ -79,6 +79,23 @@ constexpr int kFpropThreads = 416;   // 4 producer warps + 1 MMA warp + 8 epilog
 struct alignas(64) TmaMaps {
   CUtensorMap a[8];   // per class: im2col map of the gathered activation view
 };
+struct alignas(64) OutMaps {
+  CUtensorMap o[8];   // per class: tiled map of the bf16 output view (TMA-store epilogue)
+};
+constexpr int kStageChunkCols = 64;                 // epilogue staging chunk: 64 bf16 columns = one 128-byte swizzle row
+constexpr int kStagingBytes = 2 * kTileM * 128;     // one 128-row x 128-byte buffer per epilogue half
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c), "r"(row)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c, int w, int h, int t, int n) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c), "r"(w), "r"(h), "r"(t), "r"(n)
+               : "memory");
+}
 
 // im2col TMA: 128 pixels x 64 channels of one filter tap, 128B-swizzled, zero fill outside the tensor
 __device__ __forceinline__ void tma_im2col_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int t,
@@ -153,11 +170,53 @@ __device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass,
   return ti;
 }
 
+__device__ __forceinline__ float fmax_nan(float a, float b) {   // NaN-propagating max: relu(NaN) = NaN, max(x, -inf) = x
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// Branch-free epilogue body for bf16 staged outputs: kCols (32 / 16) accumulator columns of one TMEM lane ->
+// + bias [* dropout scale] -> max(., lo) -> bf16 -> 128B-swizzled staging row.  The bias / scale vectors are fetched
+// from shared memory while the TMEM load is in flight.
+template <bool kScale, int kCols>
+__device__ __forceinline__ void epi_fast(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ scale, float lo,
+                                         uint32_t row_addr, uint32_t swz, uint32_t u0) {
+  uint32_t r[32];
+  if (kCols == 32) tmem_ld32_issue(taddr, r);
+  else tmem_ld16_issue(taddr, r);
+  float4 bb[kCols / 4], ss[kCols / 4];
+#pragma unroll
+  for (int i = 0; i < kCols / 4; ++i) {
+    bb[i] = *reinterpret_cast<const float4*>(bias + 4 * i);
+    if (kScale) ss[i] = *reinterpret_cast<const float4*>(scale + 4 * i);
+  }
+  if (kCols == 32) tmem_ld_fence(r);
+  else tmem_ld_fence16(r);
+#pragma unroll
+  for (int h = 0; h < kCols / 8; ++h) {
+    float vv[8];
+    const float4 b0 = bb[2 * h], b1 = bb[2 * h + 1];
+    vv[0] = __uint_as_float(r[h * 8 + 0]) + b0.x; vv[1] = __uint_as_float(r[h * 8 + 1]) + b0.y;
+    vv[2] = __uint_as_float(r[h * 8 + 2]) + b0.z; vv[3] = __uint_as_float(r[h * 8 + 3]) + b0.w;
+    vv[4] = __uint_as_float(r[h * 8 + 4]) + b1.x; vv[5] = __uint_as_float(r[h * 8 + 5]) + b1.y;
+    vv[6] = __uint_as_float(r[h * 8 + 6]) + b1.z; vv[7] = __uint_as_float(r[h * 8 + 7]) + b1.w;
+    if (kScale) {
+      const float4 s0 = ss[2 * h], s1 = ss[2 * h + 1];
+      vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
+      vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vv[i] = fmax_nan(vv[i], lo);
+    st_shared16(row_addr + (((u0 + (uint32_t)h) ^ swz) << 4), pack8(vv));
+  }
+}
+
 __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d,
                                                                        const __grid_constant__ TmaMaps maps,
+                                                                       const __grid_constant__ OutMaps omaps,
                                                                        const __grid_constant__ TileSched ts, int use_tma,
                                                                        int stages, int lag, long long total_tiles, int n_tiles,
-                                                                       int sum_taps) {
+                                                                       int sum_taps, int store_mode, int piece) {
   const int acc_cols = (d.bn_tile + 15) & ~15;                     // TMEM columns per accumulator
   const int b_tile_bytes = ((acc_cols * 128) + 1023) & ~1023;      // packed weight tile (layer-wide bn_tile)
   const int stage_bytes = kATileBytes + b_tile_bytes;
@@ -165,13 +224,12 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  FpropSmem* ps = reinterpret_cast<FpropSmem*>(smem_al + (size_t)stages * stage_bytes);
+  // [pipeline stages][epilogue staging: 2 halves x (128 rows x 128 B, 128B-swizzled)][barriers][tap tables][bias][scale]
+  const uint32_t stg_base = smem_base + (uint32_t)stages * stage_bytes;                 // 1024-aligned
+  FpropSmem* ps = reinterpret_cast<FpropSmem*>(smem_al + (size_t)stages * stage_bytes + kStagingBytes);
   int32_t* s_taps = reinterpret_cast<int32_t*>(ps + 1);            // all classes back to back
-  // epilogue staging (bf16 rows, pitch acc_cols*2 + 16 bytes: conflict-free 16-byte shared stores), after the tap tables
-  const uint32_t stg_pitch = (uint32_t)(acc_cols * 2 + 16);
-  const uint32_t stg_base = (smem_base + (uint32_t)stages * stage_bytes + (uint32_t)sizeof(FpropSmem) + (uint32_t)sum_taps * 4 + 15u) & ~15u;
   // bias (Cout floats, zeros when the layer has none) and, when it fits, the per-(clip, channel) dropout scale
-  float* s_bias = reinterpret_cast<float*>(smem_al + (stg_base - smem_base) + (size_t)kTileM * stg_pitch);
+  float* s_bias = reinterpret_cast<float*>(smem_al + ((kStagingBytes + (size_t)stages * stage_bytes + sizeof(FpropSmem) + (size_t)sum_taps * 4 + 15) & ~(size_t)15));
   float* s_scale = s_bias + ((d.Cout + 3) & ~3);
   const bool scale_smem = d.scale_nc != nullptr && d.N * d.Cout <= kMaxScaleSmem;
 
@@ -211,8 +269,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     }
     mbar_init(&ps->tfull[0], 1);
     mbar_init(&ps->tfull[1], 1);
-    mbar_init(&ps->tempty[0], 256);
-    mbar_init(&ps->tempty[1], 256);
+    mbar_init(&ps->tempty[0], 4);      // one elected lane of each of the 4 epilogue warps that drain this accumulator
+    mbar_init(&ps->tempty[1], 4);
     fence_barrier_init();
   }
   const uint32_t tmem_cols = tmem_cols_for(2 * acc_cols);
@@ -404,161 +462,230 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     if (lane == 0) { B2C_PROF_PRINT2("mma", m_t0, m_wfull, m_wtempty); }
   } else {
     // ------------------------------ epilogue (warps 5..12) --------------------------
-    // Warp w may only touch TMEM lanes 32*(w&3)..+31, so two warps share each lane quarter and split the tile's
-    // columns [0,sp) / [sp,bn16) (ncu r01b: with 4 epilogue warps the short-K layers were epilogue-latency bound,
-    // tensor pipe 20 % active).  Bias / dropout scale come from shared memory and are fetched while the TMEM load
-    // is in flight.
+    // Warp w may only touch TMEM lanes 32*(w&3)..+31.  The two warp quartets alternate TILES: quartet h drains
+    // accumulator h, so each has two tile periods per tile.  bf16 row outputs go through a 128B-swizzled staging
+    // buffer in 64-column chunks and leave with ONE TMA tensor store per warp and chunk (32 rows x 64 columns) when the
+    // output rows of a tile are addressable by a tensor map (store_mode 1: rows contiguous; 2: strided classes in
+    // `piece`-row pieces), else with coalesced 16-byte stores.  (ncu r01b/c + in-kernel phase timing: with per-lane
+    // index arithmetic and per-row stores the epilogue took ~7000 cycles per 128x128 tile against ~1800 of MMA.)
     const int quarter = warp & 3;
     const int half = (warp - 5) >> 2;
     const bool staged = (d.out_fp32 == 0 && !d.accumulate);
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const bool use_store_tma = staged && store_mode != 0;
+    // a 64-column box that is only partly owned by this N tile (bn_tile % 64 != 0 with several N tiles) must not be
+    // written by TMA (it would spill into the neighbouring tile's columns): such chunks take the coalesced path
+    const bool partial_chunks = n_tiles > 1 && (d.bn_tile & (kStageChunkCols - 1)) != 0;
+    const bool need_pos = !use_store_tma || partial_chunks || d.scale_nc != nullptr;
+    const uint32_t sub = stg_base + (uint32_t)half * (kTileM * 128) + (uint32_t)quarter * 4096;   // this warp's 32 rows
+    const uint32_t my_row = sub + (uint32_t)lane * 128;
+    const uint32_t swz = (uint32_t)(lane & 7);
+    const bool do_relu = d.relu != 0;
+    const float relu_lo = d.relu ? 0.f : __int_as_float(0xff800000);     // -inf: max.NaN(x, -inf) = x
+    // global (not smem-resident) dropout scale rows also work with the fast body: it only dereferences the pointer
+    const bool fast = staged && d.sigmoid_from < 0;
+    const int sig_from = d.sigmoid_from >= 0 ? d.sigmoid_from : 0x7fffffff;
+    const int n_issue = store_mode == 2 ? 32 / piece : 1;
+    const int acc = half;
     B2C_PROF_DECL(e_wait); B2C_PROF_DECL(e_cols); B2C_PROF_DECL(e_t0); B2C_PROF_START(e_t0);
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    B2C_PROF_DECL(e_rd); B2C_PROF_DECL(e_ld); B2C_PROF_DECL(e_st);
+    long long it = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      if ((int)(it & 1) != half) continue;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int n0 = ti.n_idx * d.bn_tile;
       int bn = d.Cout - n0;
       if (bn > d.bn_tile) bn = d.bn_tile;
       const int bn16 = (bn + 15) & ~15;
-      int sp = ((bn16 + 63) >> 6) << 5;
-      if (sp > bn16) sp = bn16;
-      const int cbeg = half ? sp : 0, cend = half ? bn16 : sp;
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
-      const unsigned m = (unsigned)ti.m0 + (unsigned)(quarter * 32 + lane);
+      const unsigned mw = (unsigned)ti.m0 + (unsigned)(quarter * 32);        // first row of this warp
+      const unsigned m = mw + (unsigned)lane;
       const bool mvalid = m < Mtot;
       long long opos = 0;
       int n_i = 0;
-      if (mvalid) {
+      if (need_pos && mvalid) {
         uint32_t rw, rh, rt;
         uint32_t q = fdivmod(m, s_fd[3 * ti.cls], rw);
         q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
         q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
-        const int qw = (int)rw, qh = (int)rh, qt = (int)rt;
         n_i = (int)q;
-        opos = (((long long)n_i * d.To + (qt * d.so_t + cc.po_t)) * d.Ho + (qh * d.so_h + cc.po_h)) * d.Wo +
-               (qw * d.so_w + cc.po_w);
+        opos = (((long long)n_i * d.To + ((int)rt * d.so_t + cc.po_t)) * d.Ho + ((int)rh * d.so_h + cc.po_h)) * d.Wo +
+               ((int)rw * d.so_w + cc.po_w);
       }
       const float* scale_row = nullptr;
       if (d.scale_nc) scale_row = scale_smem ? s_scale + n_i * d.Cout : d.scale_nc + (long long)n_i * d.Cout;
-      const uint32_t srow = stg_base + (uint32_t)(quarter * 32 + lane) * stg_pitch;
       B2C_PROF_DECL(w3); B2C_PROF_START(w3);
       mbar_wait(&ps->tfull[acc], acc_phase, 3);
       B2C_PROF_ACC(e_wait, w3);
       B2C_PROF_DECL(w4); B2C_PROF_START(w4);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        uint32_t r[32];
-        const int nh = (cend - c0 >= 32) ? 4 : 2;
-        if (nh == 4) tmem_ld32_issue(t_lane + (uint32_t)c0, r);
-        else tmem_ld16_issue(t_lane + (uint32_t)c0, r);
-        float4 bb[8], ss[8];
+      for (int ch0 = 0; ch0 < bn16; ch0 += kStageChunkCols) {
+        const int cw = bn16 - ch0 < kStageChunkCols ? bn16 - ch0 : kStageChunkCols;
+        if (staged) {
+          // the previous chunk of this warp has left its staging rows
+          B2C_PROF_DECL(w5); B2C_PROF_START(w5);
+          if (use_store_tma) {
+            if (lane < n_issue) bulk_wait_read0();
+          }
+          __syncwarp();
+          B2C_PROF_ACC(e_rd, w5);
+        }
+        if (fast) {
+          // bf16 staged rows without sigmoid: branch-free body (s_bias / s_scale are padded past Cout; columns >= Cout
+          // are never stored)
+          for (int c0 = ch0; c0 < ch0 + cw; c0 += 32) {
+            const uint32_t ta = t_lane + (uint32_t)c0;
+            const float* bp = s_bias + n0 + c0;
+            const float* sp = scale_row + n0 + c0;
+            const uint32_t u0 = (uint32_t)((c0 - ch0) >> 3);
+            if (ch0 + cw - c0 >= 32) {
+              if (scale_row) epi_fast<true, 32>(ta, bp, sp, relu_lo, my_row, swz, u0);
+              else epi_fast<false, 32>(ta, bp, sp, relu_lo, my_row, swz, u0);
+            } else {
+              if (scale_row) epi_fast<true, 16>(ta, bp, sp, relu_lo, my_row, swz, u0);
+              else epi_fast<false, 16>(ta, bp, sp, relu_lo, my_row, swz, u0);
+            }
+          }
+          if (ch0 + kStageChunkCols >= bn16) {
+            // last TMEM read of this tile is complete: hand the accumulator back before the store phase
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps->tempty[acc]);
+          }
+        } else
+        for (int c0 = ch0; c0 < ch0 + cw; c0 += 32) {
+          uint32_t r[32];
+          const int nh = (ch0 + cw - c0 >= 32) ? 4 : 2;
+          if (nh == 4) tmem_ld32_issue(t_lane + (uint32_t)c0, r);
+          else tmem_ld16_issue(t_lane + (uint32_t)c0, r);
+          float4 bb[8], ss[8];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int col = n0 + c0 + h * 8;
-          const bool on = h < nh && col < d.Cout;
-          bb[2 * h] = on ? *reinterpret_cast<const float4*>(s_bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-          bb[2 * h + 1] = on ? *reinterpret_cast<const float4*>(s_bias + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (scale_row) {
-            ss[2 * h] = on ? *reinterpret_cast<const float4*>(scale_row + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-            ss[2 * h + 1] = on ? *reinterpret_cast<const float4*>(scale_row + col + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+          for (int h = 0; h < 4; ++h) {
+            const int col = n0 + c0 + h * 8;
+            const bool on = h < nh && col < d.Cout;
+            bb[2 * h] = on ? *reinterpret_cast<const float4*>(s_bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bb[2 * h + 1] = on ? *reinterpret_cast<const float4*>(s_bias + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (scale_row) {
+              ss[2 * h] = on ? *reinterpret_cast<const float4*>(scale_row + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+              ss[2 * h + 1] = on ? *reinterpret_cast<const float4*>(scale_row + col + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+          }
+          B2C_PROF_DECL(w6); B2C_PROF_START(w6);
+          tmem_ld_fence(r);
+          B2C_PROF_ACC(e_ld, w6);
+          if (c0 + 32 >= bn16) {
+            // last TMEM read of this tile is complete: hand the accumulator back before the (slow) store phase
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps->tempty[acc]);
+          }
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h >= nh) break;
+            const int col = n0 + c0 + h * 8;
+            float vv[8];
+            const float4 b0 = bb[2 * h], b1 = bb[2 * h + 1];
+            vv[0] = __uint_as_float(r[h * 8 + 0]) + b0.x; vv[1] = __uint_as_float(r[h * 8 + 1]) + b0.y;
+            vv[2] = __uint_as_float(r[h * 8 + 2]) + b0.z; vv[3] = __uint_as_float(r[h * 8 + 3]) + b0.w;
+            vv[4] = __uint_as_float(r[h * 8 + 4]) + b1.x; vv[5] = __uint_as_float(r[h * 8 + 5]) + b1.y;
+            vv[6] = __uint_as_float(r[h * 8 + 6]) + b1.z; vv[7] = __uint_as_float(r[h * 8 + 7]) + b1.w;
+            if (scale_row) {
+              const float4 s0 = ss[2 * h], s1 = ss[2 * h + 1];
+              vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
+              vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
+            }
+            if (do_relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+            }
+            if (col >= sig_from) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
+            }
+            if (staged) {
+              const uint32_t u = (uint32_t)((c0 - ch0) >> 3) + (uint32_t)h;          // 16-byte unit within the 128-byte row
+              st_shared16(my_row + ((u ^ swz) << 4), pack8(vv));
+            } else if (!mvalid || col >= d.Cout) {
+              // nothing to write
+            } else if (d.out_fp32 == 2) {
+              // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
+              float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (d.accumulate) vv[i] += o[(long long)i * d.out_row_stride];
+                o[(long long)i * d.out_row_stride] = vv[i];
+              }
+            } else if (d.out_fp32) {
+              float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+              float4* o4 = reinterpret_cast<float4*>(o);
+              if (d.accumulate) {
+                float4 a = o4[0], b = o4[1];
+                vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
+                vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
+              }
+              o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+              o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+              if (d.accumulate) {
+                float e[8];
+                unpack8(*o4, e);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] += e[i];
+              }
+              *o4 = pack8(vv);
+            }
           }
         }
-        tmem_ld_fence(r);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          if (h >= nh) break;
-          const int col = n0 + c0 + h * 8;
-          if (col >= d.Cout) break;
-          float vv[8];
-          const float4 b0 = bb[2 * h], b1 = bb[2 * h + 1];
-          vv[0] = __uint_as_float(r[h * 8 + 0]) + b0.x; vv[1] = __uint_as_float(r[h * 8 + 1]) + b0.y;
-          vv[2] = __uint_as_float(r[h * 8 + 2]) + b0.z; vv[3] = __uint_as_float(r[h * 8 + 3]) + b0.w;
-          vv[4] = __uint_as_float(r[h * 8 + 4]) + b1.x; vv[5] = __uint_as_float(r[h * 8 + 5]) + b1.y;
-          vv[6] = __uint_as_float(r[h * 8 + 6]) + b1.z; vv[7] = __uint_as_float(r[h * 8 + 7]) + b1.w;
-          if (scale_row) {
-            const float4 s0 = ss[2 * h], s1 = ss[2 * h + 1];
-            vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
-            vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
-          }
-          if (d.relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
-          }
-          if (d.sigmoid_from >= 0 && col >= d.sigmoid_from) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
-          }
-          if (staged) {
-            // bf16 rows: registers -> padded smem row segment (conflict-free 16-byte stores), streamed out below
-            st_shared16(srow + (uint32_t)(c0 + h * 8) * 2, pack8(vv));
-          } else if (!mvalid) {
-            // nothing to write for rows past the end of the class
-          } else if (d.out_fp32 == 2) {
-            // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
-            float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (d.accumulate) vv[i] += o[(long long)i * d.out_row_stride];
-              o[(long long)i * d.out_row_stride] = vv[i];
+        if (!staged) continue;
+        B2C_PROF_DECL(w7); B2C_PROF_START(w7);
+        if (use_store_tma && (cw == kStageChunkCols || n0 + ch0 + kStageChunkCols >= d.Cout)) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (store_mode == 1) {
+            // rows of the tile are consecutive output rows: one 32-row x 64-column box (clipped at Cout / Mtot by the map)
+            if (lane == 0 && mw < Mtot) tma_store_2d(&omaps.o[0], sub, n0 + ch0, (int)mw);
+          } else if (lane < n_issue) {
+            // strided output class: `piece` consecutive positions never leave a W row
+            const unsigned mp = mw + (unsigned)(lane * piece);
+            if (mp < Mtot) {
+              uint32_t rw, rh, rt;
+              uint32_t q = fdivmod(mp, s_fd[3 * ti.cls], rw);
+              q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
+              q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
+              tma_store_5d(&omaps.o[ti.cls], sub + (uint32_t)(lane * piece) * 128, n0 + ch0, (int)rw, (int)rh, (int)rt, (int)q);
             }
-          } else if (d.out_fp32) {
-            float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
-            float4* o4 = reinterpret_cast<float4*>(o);
-            if (d.accumulate) {
-              float4 a = o4[0], b = o4[1];
-              vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
-              vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
-            }
-            o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
-          } else {
-            bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
-            uint4* o4 = reinterpret_cast<uint4*>(o);
-            if (d.accumulate) {
-              float e[8];
-              unpack8(*o4, e);
+          }
+          if (lane < n_issue) bulk_commit();
+        } else {
+          // coalesced fallback: 8 lanes per row (16-byte units), 4 rows per instruction
+          __syncwarp();
+          const int ce = bn - ch0 < cw ? bn - ch0 : cw;            // real columns of this chunk
+          const int segv = ce > 0 ? ce >> 3 : 0;
+          const long long obyte = mvalid ? (opos * d.out_row_stride + d.out_c_off + n0 + ch0) * 2 : -1;
+          const int vcol = lane & 7, rsub = lane >> 3;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] += e[i];
+          for (int itr = 0; itr < 8; ++itr) {
+            const int rl = itr * 4 + rsub;
+            const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(obyte & 0xffffffffll), rl);
+            const int hi = __shfl_sync(0xffffffffu, (int)(obyte >> 32), rl);
+            if (hi >= 0 && vcol < segv) {
+              const uint4 val = ld_shared16(sub + (uint32_t)rl * 128 + (((uint32_t)vcol ^ (uint32_t)(rl & 7)) << 4));
+              uint8_t* o = reinterpret_cast<uint8_t*>(d.out) + (((long long)hi << 32) | (long long)lo) + vcol * 16;
+              *reinterpret_cast<uint4*>(o) = val;
             }
-            *o4 = pack8(vv);
           }
         }
+        B2C_PROF_ACC(e_st, w7);
       }
-      tc_fence_before();
-      mbar_arrive(&ps->tempty[acc]);       // accumulator drained: the MMA warp may start the tile after next
       B2C_PROF_ACC(e_cols, w4);
-      if (staged) {
-        // The warp stored its 32 rows x [cbeg, cend) columns in shared memory (one row per lane); now it streams them
-        // out with lanes running along the row: full 16-byte vectors, segv lanes per row -> whole 128-byte lines per
-        // request.  (ncu r01b/c: one cp.async.bulk per row serialises lane by lane -- UBLKCP takes uniform operands --
-        // and 256 bulk stores per tile kept the epilogue warps 87 % busy with the tensor pipe at 22 %.)
-        __syncwarp();
-        const int ce = bn < cend ? bn : cend;          // real columns of this half
-        const int segv = ce > cbeg ? (ce - cbeg) >> 3 : 0;
-        const long long obyte = mvalid ? (opos * d.out_row_stride + d.out_c_off + n0 + cbeg) * 2 : -1;
-        const uint32_t sseg = stg_base + (uint32_t)(quarter * 32) * stg_pitch + (uint32_t)cbeg * 2;
-        int lsh = 0;                                   // lanes per row = 2^lsh >= segv (<= 32 vectors per row segment)
-        while ((1 << lsh) < segv) ++lsh;
-        const int vcol = lane & ((1 << lsh) - 1), rsub = lane >> lsh, rstep = 32 >> lsh;
-        const int iters = segv > 0 ? (1 << lsh) : 0;
-        for (int it = 0; it < iters; ++it) {
-          const int rl = it * rstep + rsub;
-          const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(obyte & 0xffffffffll), rl);
-          const int hi = __shfl_sync(0xffffffffu, (int)(obyte >> 32), rl);
-          if (hi >= 0 && vcol < segv) {
-            const uint4 val = ld_shared16(sseg + (uint32_t)rl * stg_pitch + (uint32_t)vcol * 16);
-            uint8_t* o = reinterpret_cast<uint8_t*>(d.out) + (((long long)hi << 32) | (long long)lo) + vcol * 16;
-            *reinterpret_cast<uint4*>(o) = val;
-          }
-        }
-        __syncwarp();
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
+    if (use_store_tma && lane < n_issue) bulk_wait0();   // all tensor stores of this thread have completed before the CTA retires
     if (lane == 0 && (warp == 5 || warp == 9)) { B2C_PROF_PRINT2(warp == 5 ? "epilogue(w5)" : "epilogue(w9)", e_t0, e_wait, e_cols); }
+    if (lane == 0 && warp == 5) { B2C_PROF_PRINT2("epi(w5) rd/ld", e_st, e_rd, e_ld); }
   }
   __syncthreads();
   if (warp == 4) {
@@ -915,6 +1042,35 @@ int encode_im2col_map(CUtensorMap* map, const bf16* base, int C, long long row_s
   return 0;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// Tiled map of a bf16 output view for the TMA-store epilogue: dims (C, Qw, Qh, Qt, N) with the class strides
+// (rank 5), or (C, rows) for outputs whose tile rows are consecutive (rank 2).  128B swizzle, 64-channel boxes.
+int encode_out_map(CUtensorMap* map, const bf16* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_tiled();
+  if (!fn) return b2c_fail(-2, "cuTensorMapEncodeTiled entry point not available in this driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<bf16*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return b2c_fail(-3, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
 // All weight re-packing of a step in ONE launch: a device table of jobs (stable pointers: flat parameter buffer
 // views -> persistent packed operand buffers); block -> job through a prefix table.
 __global__ void pack_weights_batched_kernel(const b2c_pack_job* __restrict__ jobs, const int* __restrict__ block_start, int njobs) {
@@ -993,7 +1149,7 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   if (total_tiles == 0) return 0;
   const int acc_cols = (d.bn_tile + 15) & ~15;
   const int stage_bytes = kATileBytes + (((acc_cols * 128) + 1023) & ~1023);
-  const int staging = kTileM * (acc_cols * 2 + 16) + 16;
+  const int staging = kStagingBytes + 16;
   const int vecs = (((d.Cout + 3) & ~3) + ((d.scale_nc && d.N * d.Cout <= kMaxScaleSmem) ? d.N * d.Cout : 0)) * 4;
   const int fixed = (int)sizeof(FpropSmem) + sum_taps * 4 + staging + vecs + 1024 + 64;
   int stages = (224 * 1024 - fixed) / stage_bytes;
@@ -1019,10 +1175,48 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
       if (rc) return rc;
     }
   }
+  // TMA-store epilogue for bf16 row outputs (see the kernel's epilogue comment)
+  OutMaps omaps;
+  memset(&omaps, 0, sizeof(omaps));
+  int store_mode = 0, piece = 32;
+  if (d.out_fp32 == 0 && !d.accumulate && get_encode_tiled() != nullptr) {
+    const bf16* obase = reinterpret_cast<const bf16*>(d.out) + d.out_c_off;
+    const b2c_conv_class& c0 = d.cls[0];
+    const bool contiguous = d.nclass == 1 && d.so_t == 1 && d.so_h == 1 && d.so_w == 1 && c0.po_t == 0 && c0.po_h == 0 &&
+                            c0.po_w == 0 && c0.Qt == d.To && c0.Qh == d.Ho && c0.Qw == d.Wo;
+    if (contiguous) {
+      cuuint64_t dims[2] = {(cuuint64_t)d.Cout, (cuuint64_t)((long long)d.N * d.To * d.Ho * d.Wo)};
+      cuuint64_t strides[1] = {(cuuint64_t)d.out_row_stride * 2};
+      cuuint32_t box[2] = {(cuuint32_t)kStageChunkCols, 32};
+      int rc = encode_out_map(&omaps.o[0], obase, 2, dims, strides, box);
+      if (rc) return rc;
+      store_mode = 1;
+    } else {
+      int g = 32;
+      for (int i = 0; i < d.nclass; ++i)
+        while (d.cls[i].Qw % g) g >>= 1;
+      if (g >= 8) {
+        for (int i = 0; i < d.nclass; ++i) {
+          const b2c_conv_class& c = d.cls[i];
+          const long long rs = d.out_row_stride;
+          cuuint64_t dims[5] = {(cuuint64_t)d.Cout, (cuuint64_t)c.Qw, (cuuint64_t)c.Qh, (cuuint64_t)c.Qt, (cuuint64_t)d.N};
+          cuuint64_t strides[4] = {(cuuint64_t)(d.so_w * rs * 2), (cuuint64_t)((long long)d.so_h * d.Wo * rs * 2),
+                                   (cuuint64_t)((long long)d.so_t * d.Ho * d.Wo * rs * 2),
+                                   (cuuint64_t)((long long)d.To * d.Ho * d.Wo * rs * 2)};
+          cuuint32_t box[5] = {(cuuint32_t)kStageChunkCols, (cuuint32_t)g, 1, 1, 1};
+          const bf16* cb = obase + (((long long)c.po_t * d.Ho + c.po_h) * d.Wo + c.po_w) * rs;
+          int rc = encode_out_map(&omaps.o[i], cb, 5, dims, strides, box);
+          if (rc) return rc;
+        }
+        store_mode = 2;
+        piece = g;
+      }
+    }
+  }
   long long grid = b2c_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, ts, use_tma, stages, lag,
-                                                                                    total_tiles, n_tiles, sum_taps);
+  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, omaps, ts, use_tma, stages, lag,
+                                                                                    total_tiles, n_tiles, sum_taps, store_mode, piece);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_fprop launch");
   return 0;
