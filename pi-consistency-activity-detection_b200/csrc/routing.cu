@@ -223,6 +223,11 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
   float* s_gbu = s_S + 3 * 16 * 32;          // [17][32]  dbeta_u (16) + dbeta_a (1) accumulators (warp 0)
   float* s_caps = s_gbu + 17 * 32;           // [544]
   float* s_dout = s_caps + 544;              // [32*17]
+  // per-iteration routing state of every thread ([t][which][k][thread]: conflict-free) and the per-j scalars.  Keeping
+  // them in shared memory lets the iteration loops stay ROLLED: fully unrolled the kernel was 16 K instructions
+  // (260 KB) and spent 31 % of its issue slots waiting for instruction fetch (ncu r01d, stall_no_inst).
+  float* s_st = s_dout + 32 * 17;            // [3][3][kIPT][kRT]   rp, rn, Z
+  float* s_sc = s_st + 3 * 3 * kIPT * kRT;   // [3][4][32]          R, T, a, inv_s
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool active = lane < C;
   load_W_smem(W, sW, C);
@@ -242,20 +247,25 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
     float V[kIPT][16];
     compute_votes(s_caps, sW, w, lane, V);
 
-    // ---- forward with the per-iteration state kept: scalars in registers, mu/S in shared memory ----
-    float rp_s[3][kIPT], rn_s[3][kIPT], Z_s[3][kIPT];
-    float R_s[3], T_s[3], a_s[3], is_s[3];
+    // ---- forward with the per-iteration state kept in shared memory ----
     {
-      float r[kIPT], mu[16], S[16];
+      float r[kIPT], rn[kIPT], Z[kIPT], mu[16], S[16];
 #pragma unroll
       for (int k = 0; k < kIPT; ++k) r[k] = 1.f / (float)C;
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < 3; ++t) {
+        float* st = s_st + (size_t)t * 3 * kIPT * kRT + threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < kIPT; ++k) rp_s[t][k] = r[k];
-        const MStepOut o = m_step(V, r, s_ain, bu, ba, C, active, w, lane, red, pp, rn_s[t], Z_s[t], mu, S);
-        R_s[t] = o.R; T_s[t] = o.T; a_s[t] = o.a; is_s[t] = o.inv_s;
+        for (int k = 0; k < kIPT; ++k) st[(0 * kIPT + k) * kRT] = r[k];
+        const MStepOut o = m_step(V, r, s_ain, bu, ba, C, active, w, lane, red, pp, rn, Z, mu, S);
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          st[(1 * kIPT + k) * kRT] = rn[k];
+          st[(2 * kIPT + k) * kRT] = Z[k];
+        }
         if (w == 0) {
+          float* sc = s_sc + t * 4 * 32 + lane;
+          sc[0] = o.R; sc[32] = o.T; sc[64] = o.a; sc[96] = o.inv_s;
 #pragma unroll
           for (int h = 0; h < 16; ++h) {
             s_mu[(t * 16 + h) * 32 + lane] = mu[h];
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
         if (t < 2) e_step(V, mu, S, o.a, active, r);
       }
     }
-    __syncthreads();  // s_mu / s_S visible to all warps
+    __syncthreads();  // s_mu / s_S / s_sc visible to all warps
 
     // ---- backward sweep ----
     float gV[kIPT][16];
@@ -283,10 +293,20 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) gr[k] = gain[k] = 0.f;
 
-#pragma unroll
+#pragma unroll 1
     for (int t = 2; t >= 0; --t) {
       const float* mu_t = s_mu + t * 16 * 32 + lane;   // stride 32 per h
       const float* S_t = s_S + t * 16 * 32 + lane;
+      const float* st = s_st + (size_t)t * 3 * kIPT * kRT + threadIdx.x;
+      const float* sc = s_sc + t * 4 * 32 + lane;
+      float rp_t[kIPT], rn_t[kIPT], Z_t[kIPT];
+#pragma unroll
+      for (int k = 0; k < kIPT; ++k) {
+        rp_t[k] = st[(0 * kIPT + k) * kRT];
+        rn_t[k] = st[(1 * kIPT + k) * kRT];
+        Z_t[k] = st[(2 * kIPT + k) * kRT];
+      }
+      const float R_t = sc[0], T_t = sc[32], a_t = sc[64], is_t = sc[96];
       if (t < 2) {
         // E-step backward: r^t = softmax_j(ln p_ij + ln(eps + a_j)) feeds iteration t+1
         float gz[kIPT];
@@ -295,7 +315,7 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
         for (int q = 0; q < 17; ++q) acc[q] = 0.f;
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
-          const float r = rp_s[t + 1][k];
+          const float r = st[(3 * kIPT + k) * kRT];   // rp of iteration t+1 (next [t] block, which = 0)
           const float dot = warp_sum(gr[k] * r);
           gz[k] = r * (gr[k] - dot);
           acc[16] += gz[k];
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
         block_sum<17>(acc, red, pp, w, lane);
 #pragma unroll
         for (int h = 0; h < 16; ++h) gmu[h] = acc[h];
-        ga = acc[16] / (kEps + a_s[t]);
+        ga = acc[16] / (kEps + a_t);
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
           const float m = mu_t[h * 32], invS = 1.f / S_t[h * 32];
@@ -332,16 +352,16 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
         for (int h = 0; h < 16; ++h) gS[h] = acc[h];
       }
       // M-step backward
-      const float R = R_s[t], invR = 1.f / (R + kEps);
-      const float a = a_s[t];
+      const float R = R_t, invR = 1.f / (R + kEps);
+      const float a = a_t;
       const float gu = active ? ga * a * (1.f - a) : 0.f;
-      const float gcost = kLambda * is_s[t] * (gu - warp_sum(gu) / (float)C);
+      const float gcost = kLambda * is_t * (gu - warp_sum(gu) / (float)C);
       if (w == 0 && active) {
         s_gbu[16 * 32 + lane] += kLambda * gu;
 #pragma unroll
         for (int h = 0; h < 16; ++h) s_gbu[h * 32 + lane] += gcost * R;
       }
-      const float gR = gcost * T_s[t];
+      const float gR = gcost * T_t;
       const float one_m_csum = 1.f - R * invR;
       float gc[kIPT];
 #pragma unroll
@@ -356,22 +376,22 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
           const float dv = V[k][h] - m;
           gc[k] = fmaf(gSh, dv * dv, gc[k]);
           gc[k] = fmaf(gmh, V[k][h], gc[k]);
-          const float c = rn_s[t][k] * invR;
+          const float c = rn_t[k] * invR;
           gV[k][h] = fmaf(c, gmh + 2.f * gSh * dv, gV[k][h]);
         }
       }
       float D[1] = {0.f};
 #pragma unroll
-      for (int k = 0; k < kIPT; ++k) D[0] = fmaf(gc[k], rn_s[t][k] * invR, D[0]);
+      for (int k = 0; k < kIPT; ++k) D[0] = fmaf(gc[k], rn_t[k] * invR, D[0]);
       block_sum<1>(D, red, pp, w, lane);
       const float gR_tot = gR - D[0] * invR;
 #pragma unroll
       for (int k = 0; k < kIPT; ++k) {
         const int i = w + kNW * k;
         const float grn = active ? (gc[k] * invR + gR_tot) : 0.f;
-        const float dot2 = warp_sum(grn * rn_s[t][k]);
-        const float grp = active ? (grn - dot2) / Z_s[t][k] : 0.f;
-        gain[k] += warp_sum(grp * rp_s[t][k]);
+        const float dot2 = warp_sum(grn * rn_t[k]);
+        const float grp = active ? (grn - dot2) / Z_t[k] : 0.f;
+        gain[k] += warp_sum(grp * rp_t[k]);
         gr[k] = grp * s_ain[i];
       }
     }
@@ -541,7 +561,8 @@ B2C_API int b2c_em_routing_bwd(const float* caps, const float* W, const float* b
   B2C_REQUIRE(caps && W && beta_u && beta_a && dout && dcaps && dW && dbeta_u && dbeta_a, "em_routing_bwd: null pointer");
   B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_bwd: C=%d must be in [1,32]", C);
   if (b <= 0) return 0;
-  const size_t smem = (size_t)(2 * kB * 16 * 32 + 2 * kNW * 17 * 32 + 2 * 3 * 16 * 32 + 17 * 32 + 544 + 32 * 17) * sizeof(float);
+  const size_t smem = (size_t)(2 * kB * 16 * 32 + 2 * kNW * 17 * 32 + 2 * 3 * 16 * 32 + 17 * 32 + 544 + 32 * 17 + 3 * 3 * kIPT * kRT +
+                               3 * 4 * 32) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
