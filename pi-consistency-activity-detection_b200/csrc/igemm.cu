@@ -32,7 +32,10 @@ namespace {
 #define B2C_PROF_ACC(a, t0) a += clock64() - t0
 #define B2C_PROF_PRINT2(name, t0, a, b) \
   if (blockIdx.x == 0) printf("[prof] %-14s total %lld cyc  waitA %lld  B %lld  tiles/CTA %lld\n", name, clock64() - t0, (long long)(a), (long long)(b), (total_tiles + gridDim.x - 1) / gridDim.x)
+#define B2C_PROF_PRINTW(name, t0, a, n) \
+  if (blockIdx.x == 0) printf("[prof] %-14s total %lld cyc  wait %lld  k-blocks %d\n", name, clock64() - t0, (long long)(a), (int)(n))
 #else
+#define B2C_PROF_PRINTW(name, t0, a, n)
 #define B2C_PROF_DECL(x)
 #define B2C_PROF_START(x)
 #define B2C_PROF_ACC(a, t0)
@@ -704,9 +707,11 @@ struct alignas(64) WgradMaps {
 
 __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_constant__ b2c_wgrad_desc d,
                                                                const __grid_constant__ WgradMaps maps, int use_tma, int lo_t,
-                                                               int lo_h, int lo_w, int stages, int lag, int nsplit) {
+                                                               int lo_h, int lo_w, int stages, int lag, int nsplit, int MT) {
+  // MT 128-column (tap, gc) tiles per CTA share ONE plain-operand tile per K-block (in-kernel timing r01: the MMA warp
+  // waited on TMA data 52 % of the time at ~80 % of the L2 throughput cap; the plain tile is identical for all taps).
   const int K = d.ntaps * d.Cg;            // GEMM-M extent ((tap, gc) columns of the im2col matrix)
-  const int mk0 = blockIdx.x * kTileM;     // first (tap,gc) column of this CTA
+  const int mk0 = blockIdx.x * MT * kTileM;     // first (tap,gc) column of this CTA
   const int n0 = blockIdx.y * d.bn_tile;   // first p-channel
   int bn = d.Cp - n0;
   if (bn > d.bn_tile) bn = d.bn_tile;
@@ -719,7 +724,10 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
   if (nkb <= 0) return;
   const int b_atoms = (bn16 + 63) / 64;
   const int b_tile_bytes = b_atoms * 8 * 1024;
-  const int stage_bytes = kATileBytes + b_tile_bytes;
+  const int a_bytes = MT * kATileBytes;
+  const int stage_bytes = a_bytes + b_tile_bytes;
+  int mt_here = (K - mk0 + kTileM - 1) / kTileM;     // valid tiles of this CTA
+  if (mt_here > MT) mt_here = MT;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -738,7 +746,7 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
     mbar_init(&ps->accum, 1);
     fence_barrier_init();
   }
-  const uint32_t tmem_cols = tmem_cols_for(bn16);
+  const uint32_t tmem_cols = tmem_cols_for(MT * bn16);
   if (warp == 4) tmem_alloc(&ps->tmem_base, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -750,22 +758,25 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
     // two 64-column halves of this CTA's 128 (tap, channel) columns, and bn/64 boxes of the plain operand
     if (tid == 0) {
       const int cblocks = d.Cg / kBlockK;
-      int sub_c[2];
-      uint16_t sub_ow[2], sub_oh[2], sub_ot[2];
-      bool sub_ok[2];
+      constexpr int kMaxSub = 6;                     // MT <= 3 tiles x two 64-column halves
+      int sub_c[kMaxSub];
+      uint16_t sub_ow[kMaxSub], sub_oh[kMaxSub], sub_ot[kMaxSub];
+      bool sub_ok[kMaxSub];
+      int n_ok = 0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int blk = blockIdx.x * 2 + h;          // 64-column block index over (tap, channel block)
-        sub_ok[h] = blk < d.ntaps * cblocks;
+      for (int h = 0; h < kMaxSub; ++h) {
+        const int blk = blockIdx.x * MT * 2 + h;     // 64-column block index over (tap, channel block)
+        sub_ok[h] = h < 2 * MT && blk < d.ntaps * cblocks;
         const int tp = sub_ok[h] ? blk / cblocks : 0;
         sub_c[h] = (blk - tp * cblocks) * kBlockK;
         const int32_t tv = __ldg(d.taps + tp);
         sub_ow[h] = (uint16_t)(tap_dw(tv) - lo_w);
         sub_oh[h] = (uint16_t)(tap_dh(tv) - lo_h);
         sub_ot[h] = (uint16_t)(tap_dt(tv) - lo_t);
+        n_ok += sub_ok[h] ? 1 : 0;
       }
       const int nb = (bn16 + 63) / 64;
-      const uint32_t tx = (uint32_t)(((sub_ok[0] ? 1 : 0) + (sub_ok[1] ? 1 : 0) + nb) * 8192);
+      const uint32_t tx = (uint32_t)((n_ok + nb) * 8192);
       long long pos = kb_lo * kBlockK;
       int n_i, qt, qh, qw;
       {
@@ -777,14 +788,17 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
       }
       int stage = 0;
       uint32_t phase = 0;
+      B2C_PROF_DECL(p_wait); B2C_PROF_DECL(p_t0); B2C_PROF_START(p_t0);
       for (int i = 0; i < nkb; ++i) {
+        B2C_PROF_DECL(w0); B2C_PROF_START(w0);
         mbar_wait(&ps->empty[stage], phase ^ 1, 11);
+        B2C_PROF_ACC(p_wait, w0);
         const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
-        const uint32_t b_st = a_st + kATileBytes;
+        const uint32_t b_st = a_st + (uint32_t)a_bytes;
         mbar_arrive_expect_tx(&ps->full[stage], tx);
         const int gw = qw * d.sg_w + lo_w, gh = qh * d.sg_h + lo_h, gt = qt * d.sg_t + lo_t;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < kMaxSub; ++h)
           if (sub_ok[h])
             tma_im2col_5d(a_st + h * 8192, &maps.g, &ps->full[stage], sub_c[h], gw, gh, gt, n_i, sub_ow[h], sub_oh[h], sub_ot[h]);
         for (int j = 0; j < nb; ++j)
@@ -806,6 +820,7 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
           phase ^= 1;
         }
       }
+      if (blockIdx.y == 0 && blockIdx.z == 0) { B2C_PROF_PRINTW("wgrad producer", p_t0, p_wait, nkb); }
     }
   } else if (warp < 4) {
     // gather producers: thread -> position row r (0..63) and half (0/1) of the chunk columns
@@ -847,7 +862,7 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
     for (int i = 0; i < nkb; ++i) {
       mbar_wait(&ps->empty[stage], phase ^ 1, 11);
       const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
-      const uint32_t b_st = a_st + kATileBytes;
+      const uint32_t b_st = a_st + (uint32_t)a_bytes;      // gather path: MT == 1
       const bool pvalid = (pos0 + (long long)i * kBlockK) < Mtot;
       const int gt0 = qt * d.sg_t, gh0 = qh * d.sg_h, gw0 = qw * d.sg_w;
 #pragma unroll
@@ -909,51 +924,60 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
   if (warp < 4) {
     // epilogue: TMEM lane = (tap,gc) column mk0 + tid ; columns = p channels
     mbar_wait(&ps->accum, 0, 13);
+    B2C_PROF_DECL(e_t0); B2C_PROF_START(e_t0);
     tc_fence_after();
-    const int kcol = mk0 + tid;
-    bool rvalid = kcol < K;
-    long long base = 0;
-    if (rvalid) {
-      const int tp = kcol / d.Cg;
-      const int gc = kcol - tp * d.Cg;
-      rvalid = gc < d.Cg_real;
-      base = (long long)gc * d.s_g + __ldg(d.wtap + tp);
-    }
-    const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < bn16; c0 += 32) {
-      float v[32];
-      const int nc = (bn16 - c0 >= 32) ? 32 : 16;
-      if (nc == 32) tmem_ld32(t_lane + (uint32_t)c0, v);
-      else tmem_ld16(t_lane + (uint32_t)c0, v);
-      if (!rvalid) continue;
+    for (int jt = 0; jt < mt_here; ++jt) {
+      const int kcol = mk0 + jt * kTileM + tid;
+      bool rvalid = kcol < K;
+      long long base = 0;
+      if (rvalid) {
+        const int tp = kcol / d.Cg;
+        const int gc = kcol - tp * d.Cg;
+        rvalid = gc < d.Cg_real;
+        base = (long long)gc * d.s_g + __ldg(d.wtap + tp);
+      }
+      const uint32_t t_lane = tmem_d + (uint32_t)(jt * bn16) + ((uint32_t)(warp * 32) << 16);
+      for (int c0 = 0; c0 < bn16; c0 += 32) {
+        float v[32];
+        const int nc = (bn16 - c0 >= 32) ? 32 : 16;
+        if (nc == 32) tmem_ld32(t_lane + (uint32_t)c0, v);
+        else tmem_ld16(t_lane + (uint32_t)c0, v);
+        if (!rvalid) continue;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i >= nc) break;
-        const int pc = n0 + c0 + i;
-        if (pc < d.Cp_real) {
-          float* dst = d.dw + base + (long long)pc * d.s_p;
-          if (d.atomic) atomicAdd(dst, v[i]);
-          else *dst = v[i];
+        for (int i = 0; i < 32; ++i) {
+          if (i >= nc) break;
+          const int pc = n0 + c0 + i;
+          if (pc < d.Cp_real) {
+            float* dst = d.dw + base + (long long)pc * d.s_p;
+            if (d.atomic) atomicAdd(dst, v[i]);
+            else *dst = v[i];
+          }
         }
       }
     }
     tc_fence_before();
+    if (tid == 0 && blockIdx.y == 0 && blockIdx.z == 0) { B2C_PROF_PRINTW("wgrad epilogue", e_t0, 0, nkb); }
   } else {
     const uint32_t idesc = umma_idesc_bf16(bn16, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
+    B2C_PROF_DECL(m_wait); B2C_PROF_DECL(m_t0); B2C_PROF_START(m_t0);
     for (int i = 0; i < nkb; ++i) {
+      B2C_PROF_DECL(w1); B2C_PROF_START(w1);
       mbar_wait(&ps->full[stage], phase, 12);
+      B2C_PROF_ACC(m_wait, w1);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
-        const uint32_t b_st = a_st + kATileBytes;
+        const uint32_t b_st = a_st + (uint32_t)a_bytes;
+        for (int jt = 0; jt < mt_here; ++jt) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // MN-major SW128: LBO = stride between 64-element MN atoms (8 KB), SBO = stride between 8-position groups
-          const uint64_t ad = umma_desc_sw128(a_st + k * 2048, 8192, 1024);
-          const uint64_t bd = umma_desc_sw128(b_st + k * 2048, 8192, 1024);
-          umma_bf16(tmem_d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // MN-major SW128: LBO = stride between 64-element MN atoms (8 KB), SBO = stride between 8-position groups
+            const uint64_t ad = umma_desc_sw128(a_st + jt * kATileBytes + k * 2048, 8192, 1024);
+            const uint64_t bd = umma_desc_sw128(b_st + k * 2048, 8192, 1024);
+            umma_bf16(tmem_d + (uint32_t)(jt * bn16), ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&ps->empty[stage]);
       }
@@ -965,6 +989,7 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
     }
     if (lane == 0) umma_commit(&ps->accum);
     __syncwarp();
+    if (lane == 0 && blockIdx.y == 0 && blockIdx.z == 0) { B2C_PROF_PRINTW("wgrad mma", m_t0, m_wait, nkb); }
   }
   __syncthreads();
   if (warp == 4) {
@@ -1240,10 +1265,23 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   const int mt = (K + kTileM - 1) / kTileM;
   const int nt = (d.Cp + d.bn_tile - 1) / d.bn_tile;
   const long long nkb = (Mtot + kBlockK - 1) / kBlockK;
+  const int bn16 = (d.bn_tile + 15) & ~15;
+  const int b_tile_bytes = ((bn16 + 63) / 64) * 8 * 1024;
+  const int use_tma = (d.Cg % kBlockK == 0 && d.Cp % kBlockK == 0 && d.taps_host != nullptr) ? 1 : 0;
+  // (tap, gc) tiles per CTA sharing one plain-operand tile: as many as TMEM (512 columns) and >= 3 pipeline stages allow
+  int MT = 1;
+  if (use_tma) {
+    for (int cand = 3; cand >= 2; --cand)
+      if (cand <= mt && cand * bn16 <= 512 && (200 * 1024) / (cand * kATileBytes + b_tile_bytes) >= 3) {
+        MT = cand;
+        break;
+      }
+  }
+  const int mtc = (mt + MT - 1) / MT;      // CTAs along the (tap, gc) dimension
   int nsplit = d.nsplit;
   if (nsplit <= 0) {
     // long position loops with a deep pipeline, one CTA per SM: pick the split so the grid is ~1-2 full waves
-    const long long tiles = (long long)mt * nt;
+    const long long tiles = (long long)mtc * nt;
     const long long sms = b2c_num_sms();
     long long want = (2 * sms + tiles - 1) / tiles;
     if (tiles * want > 2 * sms && want > 1) --want;
@@ -1254,8 +1292,7 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   }
   if (nsplit > nkb) nsplit = (int)nkb;
   B2C_REQUIRE(nsplit == 1 || d.atomic, "conv_wgrad: nsplit>1 requires atomic accumulation");
-  const int bn16 = (d.bn_tile + 15) & ~15;
-  const int stage_bytes = kATileBytes + ((bn16 + 63) / 64) * 8 * 1024;
+  const int stage_bytes = MT * kATileBytes + b_tile_bytes;
   // latency-bound gather: keep as many K-blocks in flight as shared memory allows (ncu r01: 2 stages -> L2 45 %, tensor 11 %)
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1274,7 +1311,6 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   WgradMaps maps;
   memset(&maps, 0, sizeof(maps));
   int lo[3] = {0, 0, 0};
-  const int use_tma = (d.Cg % kBlockK == 0 && d.Cp % kBlockK == 0 && d.taps_host != nullptr) ? 1 : 0;
   if (use_tma) {
     for (int k = 0; k < 3; ++k) lo[k] = 127;
     for (int i = 0; i < d.ntaps; ++i) {
@@ -1290,8 +1326,8 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
                            d.pp_t, d.pp_h, d.pp_w, d.Qt, d.Qh, d.Qw, d.sp_t, d.sp_h, d.sp_w, kBlockK, kBlockK);
     if (rc) return rc;
   }
-  dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)nsplit);
-  igemm_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit);
+  dim3 grid((unsigned)mtc, (unsigned)nt, (unsigned)nsplit);
+  igemm_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit, MT);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_wgrad launch");
   return 0;

@@ -20,6 +20,10 @@ CASES = {
     "c3_64_64": (False, 64, 64, (3, 3, 3), (1, 1, 1), (4, 112, 112), 1, 32, True, True, "fprop"),
     "pc_fprop": (False, 832, 544, (1, 9, 9), (1, 1, 1), (1, 28, 28), 0, 32, False, True, "fprop"),
     "inc_1x1": (False, 480, 192, (1, 1, 1), (1, 1, 1), (4, 28, 28), 0, 32, True, True, "fprop"),
+    "up4_wgrad": (True, 128, 128, (3, 3, 3), (2, 2, 2), (4, 112, 112), 1, 32, False, False, "wgrad"),
+    "c3_64_wgrad": (False, 64, 64, (3, 3, 3), (1, 1, 1), (4, 112, 112), 1, 32, False, False, "wgrad"),
+    "pc_wgrad": (False, 832, 544, (1, 9, 9), (1, 1, 1), (1, 28, 28), 0, 32, False, False, "wgrad"),
+    "inc3_wgrad": (False, 160, 320, (3, 3, 3), (1, 1, 1), (1, 28, 28), 1, 32, False, False, "wgrad"),
 }
 
 
@@ -38,6 +42,18 @@ def run(name):
     plan.pack(w.contiguous(), "fprop", st)
     plan.pack(w.contiguous(), "dgrad", st)
     bias = torch.randn(Cout, device=dev) if use_bias else None
+    if which == "wgrad":
+        x = torch.randn((N,) + tuple(dims) + (spec.Cin_pad,), device=dev).bfloat16()
+        dy = torch.randn((N,) + tuple(plan.out_dims) + (spec.Cout_pad,), device=dev).bfloat16()
+        dw = torch.zeros_like(w)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3):
+            e0.record()
+            ops.conv_wgrad(plan, View(x), View(dy), dw, atomic=True, nsplit=0)
+            e1.record()
+            torch.cuda.synchronize()
+        print(f"== {name}: {e0.elapsed_time(e1):.3f} ms", flush=True)
+        return
     if which == "fprop":
         x = torch.randn((N,) + tuple(dims) + (spec.Cin_pad,), device=dev).bfloat16()
         y = torch.empty((N,) + tuple(plan.out_dims) + (spec.Cout_pad,), device=dev, dtype=torch.bfloat16)
