@@ -24,9 +24,45 @@ class _State:
     dropout_source: Optional[Callable] = None   # tests inject Dropout3d masks: f(n, c, device) -> (n,c) fp32 keep*2
     bn_groups = 1              # >1: the batch holds several independent forward passes (own BN statistics each)
     direct_grads = False       # fused step: kernels accumulate straight into param.grad (flat buffer views)
+    zero_arena = None          # fused step: ZeroArena (all small zero-initialised workspaces of a step, ONE fill launch)
+    defer_bn_counters = False  # fused step: num_batches_tracked of all BatchNorms bumped with one foreach op
 
 
 STATE = _State()
+
+
+class ZeroArena:
+    """Bump allocator over one fp32 buffer that the fused step zeroes with a single fill at step start: replaces the
+    ~90 per-layer torch.zeros launches (BatchNorm sum workspaces) of a step.  The allocation sequence of a step is
+    deterministic, so under CUDA-graph capture every slice keeps its address."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def reset(self):
+        ops.fill_f32(self.buf, 0.0)
+        self.off = 0
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n4 = (n + 3) // 4 * 4
+        if self.off + n4 > self.buf.numel():
+            return None
+        out = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n4
+        return out
+
+
+def zeros_f32(shape, device):
+    """Zero-initialised fp32 workspace: a slice of the step's arena when one is active, else torch.zeros."""
+    if STATE.zero_arena is not None:
+        t = STATE.zero_arena.take(shape)
+        if t is not None:
+            return t
+    return torch.zeros(shape, dtype=torch.float32, device=device)
 
 
 def bump_weights_epoch():
@@ -226,7 +262,7 @@ def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: 
     if training:
         g = groups
         assert N % g == 0
-        ws = torch.zeros((g, 2, Cout), dtype=torch.float32, device=raw.device)
+        ws = zeros_f32((g, 2, Cout), raw.device)
         sv.mean = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
         sv.rstd = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
         ops.bn_sums(rv_, g, ws)
@@ -246,7 +282,7 @@ def unit_bwd(layer: ConvLayer, gamma, beta, sv: UnitSaved, x: View, y: View, gy:
     dev = x.t.device
     Cout = sv.raw.shape[-1]
     raw = View(sv.raw)
-    ws = torch.zeros((sv.groups, 2, Cout), dtype=torch.float32, device=dev)
+    ws = zeros_f32((sv.groups, 2, Cout), dev)
     ops.bn_relu_bwd_reduce(gy, y, raw, sv.groups, sv.mean, sv.rstd, ws, relu=True)
     draw = torch.empty_like(sv.raw)
     dgamma, d1 = grad_buf(gamma)
@@ -319,7 +355,7 @@ class Unit3DFn(torch.autograd.Function):
         training = mod.training
         sv = unit_fwd(layer, gamma, beta, mod.bn.running_mean, mod.bn.running_var, View(x_cl), View(y), training,
                       STATE.bn_groups if training else 1)
-        if training:
+        if training and not STATE.defer_bn_counters:
             mod.bn.num_batches_tracked += 1
         ctx.mod, ctx.sv, ctx.x, ctx.y, ctx.gamma = mod, sv, x_cl, y, gamma
         ctx.training = training
@@ -394,7 +430,7 @@ class InceptionFn(torch.autograd.Function):
         sv["b2b"] = run("b2b", View(mid2), View(out, c0 + c2, c4))
         ops.maxpool_fwd(xv, View(pooled), idx, (3, 3, 3), (1, 1, 1), (1, 1, 1))
         sv["b3b"] = run("b3b", View(pooled), View(out, c0 + c2 + c4, c5))
-        if training:
+        if training and not STATE.defer_bn_counters:
             for m in u.values():
                 m.bn.num_batches_tracked += 1
         ctx.mod, ctx.sv, ctx.oc = mod, sv, oc

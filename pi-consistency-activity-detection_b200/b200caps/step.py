@@ -103,6 +103,8 @@ class TrainStep:
         self.world = self.buckets.world
         self.rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
         self._steps_seen = 0
+        self.arena = None
+        self.bn_counters = None
         self.packs = ops.PackRegistry()
         self._split_comm = False     # graph mode on >1 GPU: the NCCL all-reduce runs between two graphs, not inside one
         self.graph = None
@@ -208,6 +210,12 @@ class TrainStep:
         wt_ramp = exp_rampup(a.rampup_epochs, epoch)
         model.train()
         flat.zero_grad()
+        if self.arena is None:
+            self.arena = E.ZeroArena(1 << 18, dev)       # 1 MB of fp32: BatchNorm sum workspaces of one step (~90 x <= 3 KB)
+            self.bn_counters = [m.num_batches_tracked for m in model.modules() if isinstance(m, torch.nn.BatchNorm3d)]
+        self.arena.reset()
+        E.STATE.zero_arena = self.arena
+        E.STATE.defer_bn_counters = True
         # all derived bf16 operand tiles in one launch (after the first step every packing job is registered)
         ops.PACKS = self.packs
         if self.packs.flushed_epoch != E.STATE.weights_epoch and self._steps_seen >= 1:
@@ -354,7 +362,11 @@ class TrainStep:
             b_stem(g)
         finally:
             E.STATE.direct_grads = False
+            E.STATE.zero_arena = None
+            E.STATE.defer_bn_counters = False
             ops.PACKS = None
+        if self.bn_counters:
+            torch._foreach_add_(self.bn_counters, 1)      # every BatchNorm saw one training forward
         if not self._split_comm:
             if self.world > 1:
                 self.buckets.allreduce(0)

@@ -280,12 +280,14 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restr
     const int oh = (int)(o % G.Ho); o /= G.Ho;
     const int ot = (int)(o % G.To); o /= G.To;
     const int n = (int)o;
-    float best[8];
-    int bi[8];
+    // packed bf16x2 running maximum + packed 16-bit tap indices: per tap and channel pair ONE compare-to-mask and two
+    // bit selects (ncu r01b: the fp32 compare / select version was ALU-bound at 25 % of HBM bandwidth).  Bit selects keep
+    // the reference semantics exactly: strict '>' (first occurrence wins, like ATen), NaN never wins, -0/+0 untouched.
+    uint32_t best2[4], idx2[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      best[j] = -INFINITY;
-      bi[j] = 255;
+    for (int j = 0; j < 4; ++j) {
+      best2[j] = 0xff80ff80u;   // (-inf, -inf)
+      idx2[j] = 0x00ff00ffu;
     }
     int tap = 0;
     for (int a = 0; a < G.kt; ++a) {
@@ -294,28 +296,25 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restr
         const int ih = oh * G.sh - G.ph + b;
         for (int c = 0; c < G.kw; ++c, ++tap) {
           const int iw = ow * G.sw - G.pw + c;
-          float v[8];
           const bool inb = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi && (unsigned)iw < (unsigned)G.Wi;
-          if (inb) {
-            unpack8(ld16(x + ((((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi + iw) * x_rs + x_co + cv * 8), v);
-          } else {
+          uint4 raw = make_uint4(0, 0, 0, 0);     // F.pad zeros are real candidates (pytorch_i3d.py:44)
+          if (inb) raw = ld16(x + ((((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi + iw) * x_rs + x_co + cv * 8);
+          const uint32_t t2 = inb ? ((uint32_t)tap | ((uint32_t)tap << 16)) : 0x00ff00ffu;
+          const uint32_t rv[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;  // F.pad zeros are real candidates (pytorch_i3d.py:44)
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (v[j] > best[j]) {   // strict: first occurrence wins, like ATen
-              best[j] = v[j];
-              bi[j] = inb ? tap : 255;
-            }
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&rv[j]),
+                                           *reinterpret_cast<const __nv_bfloat162*>(&best2[j]));
+            best2[j] = (rv[j] & m) | (best2[j] & ~m);
+            idx2[j] = (t2 & m) | (idx2[j] & ~m);
           }
         }
       }
     }
-    st16(y + orow * y_rs + y_co + cv * 8, pack8(best));
+    st16(y + orow * y_rs + y_co + cv * 8, make_uint4(best2[0], best2[1], best2[2], best2[3]));
     uint2 pk;
-    pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-    pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    pk.x = __byte_perm(idx2[0], idx2[1], 0x6420);
+    pk.y = __byte_perm(idx2[2], idx2[3], 0x6420);
     *reinterpret_cast<uint2*>(idx + orow * G.C + cv * 8) = pk;
   }
 }
@@ -354,6 +353,9 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const bf16* __restr
           const int tap = (a * G.kh + b) * G.kw + c;
           const long long orow = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo + ow;
           const uint2 pk = *reinterpret_cast<const uint2*>(idx + orow * G.C + cv * 8);
+          // ~3/4 of the candidate windows chose another tap in all 8 channels: skip their gradient load
+          const uint32_t t4 = (uint32_t)tap * 0x01010101u;
+          if ((__vcmpeq4(pk.x, t4) | __vcmpeq4(pk.y, t4)) == 0u) continue;
           float d[8];
           unpack8(ld16(dy + orow * dy_rs + dy_co + cv * 8), d);
 #pragma unroll
