@@ -153,7 +153,8 @@ struct TileSched {
   unsigned start[9];   // first tile index of each class (prefix sums), start[nclass] = total
 };
 
-__device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass, long long t, int n_tiles, const FastDiv& fnt) {
+__device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass, long long t, int n_tiles, const FastDiv& fnt,
+                                                int MT) {
   TileInfo ti;
   int c = 0;
 #pragma unroll
@@ -163,12 +164,12 @@ __device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass,
   ti.cls = c;
   if (n_tiles == 1) {
     ti.n_idx = 0;
-    ti.m0 = (long long)local * kTileM;
+    ti.m0 = (long long)local * (kTileM * MT);
   } else {
     uint32_t rem;
     const uint32_t q = fdivmod(local, fnt, rem);
     ti.n_idx = (int)rem;
-    ti.m0 = (long long)q * kTileM;
+    ti.m0 = (long long)q * (kTileM * MT);
   }
   return ti;
 }
@@ -219,10 +220,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
                                                                        const __grid_constant__ OutMaps omaps,
                                                                        const __grid_constant__ TileSched ts, int use_tma,
                                                                        int stages, int lag, long long total_tiles, int n_tiles,
-                                                                       int sum_taps, int store_mode, int piece) {
+                                                                       int sum_taps, int store_mode, int piece, int MT) {
+  // MT (1 or 2) consecutive 128-row M tiles form one scheduling unit and share each K-block's weight tile: half the
+  // weight traffic from L2 per output tile (in-kernel timing r01: the short-N layers wait on operand delivery).
   const int acc_cols = (d.bn_tile + 15) & ~15;                     // TMEM columns per accumulator
   const int b_tile_bytes = ((acc_cols * 128) + 1023) & ~1023;      // packed weight tile (layer-wide bn_tile)
-  const int stage_bytes = kATileBytes + b_tile_bytes;
+  const int a_bytes = MT * kATileBytes;
+  const int stage_bytes = a_bytes + b_tile_bytes;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     mbar_init(&ps->tempty[1], 4);
     fence_barrier_init();
   }
-  const uint32_t tmem_cols = tmem_cols_for(2 * acc_cols);
+  const uint32_t tmem_cols = tmem_cols_for(2 * MT * acc_cols);
   if (warp == 4) tmem_alloc(&ps->tmem_base, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -292,16 +296,28 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       const int cblocks = d.Cin / kBlockK;
       B2C_PROF_DECL(p_wait); B2C_PROF_DECL(p_t0); B2C_PROF_START(p_t0);
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
+        const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24], MT);
         const b2c_conv_class& cc = d.cls[ti.cls];
         const int32_t* taps = s_taps + tap_off[ti.cls];
-        uint32_t rw, rh, rt;
-        uint32_t q = fdivmod((uint32_t)ti.m0, s_fd[3 * ti.cls], rw);
-        q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
-        q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
-        const int qw = (int)rw, qh = (int)rh, qt = (int)rt;
-        const int n_i = (int)q;
-        const int bw = qw * d.si_w + cc.lo_w, bh = qh * d.si_h + cc.lo_h, bt = qt * d.si_t + cc.lo_t;
+        const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
+        int bw[2], bh[2], bt[2], bn_i[2];
+        int nvalid = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const unsigned m0j = (unsigned)ti.m0 + (unsigned)(j * kTileM);
+          bw[j] = bh[j] = bt[j] = bn_i[j] = 0;
+          if (j < MT && m0j < Mtot) {
+            uint32_t rw, rh, rt;
+            uint32_t q = fdivmod(m0j, s_fd[3 * ti.cls], rw);
+            q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
+            q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
+            bw[j] = (int)rw * d.si_w + cc.lo_w;
+            bh[j] = (int)rh * d.si_h + cc.lo_h;
+            bt[j] = (int)rt * d.si_t + cc.lo_t;
+            bn_i[j] = (int)q;
+            nvalid = j + 1;
+          }
+        }
         const int nkb = cc.ntaps * cblocks;
         const uint8_t* wtile = reinterpret_cast<const uint8_t*>(cc.w) + (size_t)ti.n_idx * nkb * (size_t)b_tile_bytes;
         const CUtensorMap* map = &maps.a[ti.cls];
@@ -315,9 +331,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
             mbar_wait(&ps->empty[stage], phase ^ 1, 1);
             B2C_PROF_ACC(p_wait, w0);
             const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
-            mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)(kATileBytes + b_tile_bytes));
-            tma_im2col_5d(a_st, map, &ps->full[stage], cb * kBlockK, bw, bh, bt, n_i, ow, oh, ot);
-            bulk_g2s(a_st + kATileBytes, wtile + (size_t)kb * b_tile_bytes, (uint32_t)b_tile_bytes, &ps->full[stage]);
+            mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)(nvalid * kATileBytes + b_tile_bytes));
+            tma_im2col_5d(a_st, map, &ps->full[stage], cb * kBlockK, bw[0], bh[0], bt[0], bn_i[0], ow, oh, ot);
+            if (nvalid > 1)
+              tma_im2col_5d(a_st + kATileBytes, map, &ps->full[stage], cb * kBlockK, bw[1], bh[1], bt[1], bn_i[1], ow, oh, ot);
+            bulk_g2s(a_st + (uint32_t)a_bytes, wtile + (size_t)kb * b_tile_bytes, (uint32_t)b_tile_bytes, &ps->full[stage]);
             if (++stage == stages) {
               stage = 0;
               phase ^= 1;
@@ -337,7 +355,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     uint32_t phase = 0;
     long long issued = 0;   // K-blocks issued so far by this CTA (all tiles)
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24], MT);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int32_t* taps = s_taps + tap_off[ti.cls];
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
@@ -385,7 +403,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
         }
         if (tid == 0) {
           mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)b_tile_bytes);
-          bulk_g2s(a_st + kATileBytes, wtile + (size_t)kb * b_tile_bytes, (uint32_t)b_tile_bytes, &ps->full[stage]);
+          bulk_g2s(a_st + (uint32_t)a_bytes, wtile + (size_t)kb * b_tile_bytes, (uint32_t)b_tile_bytes, &ps->full[stage]);   // MT == 1
         }
         cp_async_commit();
         ++issued;
@@ -422,7 +440,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     uint32_t acc_phase = 0;
     B2C_PROF_DECL(m_wfull); B2C_PROF_DECL(m_wtempty); B2C_PROF_DECL(m_t0); B2C_PROF_START(m_t0);
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24], MT);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int n0 = ti.n_idx * d.bn_tile;
       int bn = d.Cout - n0;
@@ -430,7 +448,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       const int bn16 = (bn + 15) & ~15;
       const int nkb = (cc.ntaps * d.Cin + kBlockK - 1) / kBlockK;
       const uint32_t idesc = umma_idesc_bf16(bn16, 0, 0);
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MT * acc_cols);
+      const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
+      const int nvalid = (MT > 1 && (unsigned)ti.m0 + (unsigned)kTileM < Mtot) ? 2 : 1;
       B2C_PROF_DECL(w1); B2C_PROF_START(w1);
       mbar_wait(&ps->tempty[acc], acc_phase ^ 1, 4);   // epilogue has drained this accumulator
       B2C_PROF_ACC(m_wtempty, w1);
@@ -441,13 +461,23 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
         B2C_PROF_ACC(m_wfull, w2);
         tc_fence_after();
         if (lane == 0) {
+          // descriptors: only the 14-bit start-address field changes (16-byte units): +2 per 16-element K step,
+          // +1024 per 16 KB A tile -- keep the single-thread issue path short, it paces the long-K layers
           const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
-          const uint32_t b_st = a_st + kATileBytes;
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(a_st + k * 32, 16, 1024);
-            const uint64_t bd = umma_desc_sw128(b_st + k * 32, 16, 1024);
-            umma_bf16(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          const uint64_t ad0 = umma_desc_sw128(a_st, 16, 1024);
+          const uint64_t bd0 = umma_desc_sw128(a_st + (uint32_t)a_bytes, 16, 1024);
+          const uint32_t accf = kb > 0 ? 1u : 0u;
+          umma_bf16(tmem_d, ad0, bd0, idesc, accf);
+          umma_bf16(tmem_d, ad0 + 2, bd0 + 2, idesc, 1u);
+          umma_bf16(tmem_d, ad0 + 4, bd0 + 4, idesc, 1u);
+          umma_bf16(tmem_d, ad0 + 6, bd0 + 6, idesc, 1u);
+          if (nvalid > 1) {
+            const uint64_t ad1 = ad0 + (kATileBytes >> 4);
+            const uint32_t tmem_d1 = tmem_d + (uint32_t)acc_cols;
+            umma_bf16(tmem_d1, ad1, bd0, idesc, accf);
+            umma_bf16(tmem_d1, ad1 + 2, bd0 + 2, idesc, 1u);
+            umma_bf16(tmem_d1, ad1 + 4, bd0 + 4, idesc, 1u);
+            umma_bf16(tmem_d1, ad1 + 6, bd0 + 6, idesc, 1u);
           }
           umma_commit(&ps->empty[stage]);
         }
@@ -495,194 +525,199 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       if ((int)(it & 1) != half) continue;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24]);
+      const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24], MT);
       const b2c_conv_class& cc = d.cls[ti.cls];
       const int n0 = ti.n_idx * d.bn_tile;
       int bn = d.Cout - n0;
       if (bn > d.bn_tile) bn = d.bn_tile;
       const int bn16 = (bn + 15) & ~15;
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
-      const unsigned mw = (unsigned)ti.m0 + (unsigned)(quarter * 32);        // first row of this warp
-      const unsigned m = mw + (unsigned)lane;
-      const bool mvalid = m < Mtot;
-      long long opos = 0;
-      int n_i = 0;
-      if (need_pos && mvalid) {
-        uint32_t rw, rh, rt;
-        uint32_t q = fdivmod(m, s_fd[3 * ti.cls], rw);
-        q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
-        q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
-        n_i = (int)q;
-        opos = (((long long)n_i * d.To + ((int)rt * d.so_t + cc.po_t)) * d.Ho + ((int)rh * d.so_h + cc.po_h)) * d.Wo +
-               ((int)rw * d.so_w + cc.po_w);
-      }
-      const float* scale_row = nullptr;
-      if (d.scale_nc) scale_row = scale_smem ? s_scale + n_i * d.Cout : d.scale_nc + (long long)n_i * d.Cout;
       B2C_PROF_DECL(w3); B2C_PROF_START(w3);
       mbar_wait(&ps->tfull[acc], acc_phase, 3);
       B2C_PROF_ACC(e_wait, w3);
       B2C_PROF_DECL(w4); B2C_PROF_START(w4);
       tc_fence_after();
-      const uint32_t t_lane = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
-      for (int ch0 = 0; ch0 < bn16; ch0 += kStageChunkCols) {
-        const int cw = bn16 - ch0 < kStageChunkCols ? bn16 - ch0 : kStageChunkCols;
-        if (staged) {
-          // the previous chunk of this warp has left its staging rows
-          B2C_PROF_DECL(w5); B2C_PROF_START(w5);
-          if (use_store_tma) {
-            if (lane < n_issue) bulk_wait_read0();
-          }
-          __syncwarp();
-          B2C_PROF_ACC(e_rd, w5);
+      for (int jt = 0; jt < MT; ++jt) {
+        const unsigned m0j = (unsigned)ti.m0 + (unsigned)(jt * kTileM);
+        if (m0j >= Mtot) break;
+        const bool last_j = jt == MT - 1 || m0j + (unsigned)kTileM >= Mtot;   // last 128-row tile of this unit
+        const unsigned mw = m0j + (unsigned)(quarter * 32);        // first row of this warp
+        const unsigned m = mw + (unsigned)lane;
+        const bool mvalid = m < Mtot;
+        long long opos = 0;
+        int n_i = 0;
+        if (need_pos && mvalid) {
+          uint32_t rw, rh, rt;
+          uint32_t q = fdivmod(m, s_fd[3 * ti.cls], rw);
+          q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
+          q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
+          n_i = (int)q;
+          opos = (((long long)n_i * d.To + ((int)rt * d.so_t + cc.po_t)) * d.Ho + ((int)rh * d.so_h + cc.po_h)) * d.Wo +
+                 ((int)rw * d.so_w + cc.po_w);
         }
-        if (fast) {
-          // bf16 staged rows without sigmoid: branch-free body (s_bias / s_scale are padded past Cout; columns >= Cout
-          // are never stored)
+        const float* scale_row = nullptr;
+        if (d.scale_nc) scale_row = scale_smem ? s_scale + n_i * d.Cout : d.scale_nc + (long long)n_i * d.Cout;
+        const uint32_t t_lane = tmem_base + (uint32_t)((acc * MT + jt) * acc_cols) + ((uint32_t)(quarter * 32) << 16);
+        for (int ch0 = 0; ch0 < bn16; ch0 += kStageChunkCols) {
+          const int cw = bn16 - ch0 < kStageChunkCols ? bn16 - ch0 : kStageChunkCols;
+          if (staged) {
+            // the previous chunk of this warp has left its staging rows
+            B2C_PROF_DECL(w5); B2C_PROF_START(w5);
+            if (use_store_tma) {
+              if (lane < n_issue) bulk_wait_read0();
+            }
+            __syncwarp();
+            B2C_PROF_ACC(e_rd, w5);
+          }
+          if (fast) {
+            // bf16 staged rows without sigmoid: branch-free body (s_bias / s_scale are padded past Cout; columns >= Cout
+            // are never stored)
+            for (int c0 = ch0; c0 < ch0 + cw; c0 += 32) {
+              const uint32_t ta = t_lane + (uint32_t)c0;
+              const float* bp = s_bias + n0 + c0;
+              const float* sp = scale_row + n0 + c0;
+              const uint32_t u0 = (uint32_t)((c0 - ch0) >> 3);
+              if (ch0 + cw - c0 >= 32) {
+                if (scale_row) epi_fast<true, 32>(ta, bp, sp, relu_lo, my_row, swz, u0);
+                else epi_fast<false, 32>(ta, bp, sp, relu_lo, my_row, swz, u0);
+              } else {
+                if (scale_row) epi_fast<true, 16>(ta, bp, sp, relu_lo, my_row, swz, u0);
+                else epi_fast<false, 16>(ta, bp, sp, relu_lo, my_row, swz, u0);
+              }
+            }
+            if (last_j && ch0 + kStageChunkCols >= bn16) {
+              // last TMEM read of this tile is complete: hand the accumulator back before the store phase
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ps->tempty[acc]);
+            }
+          } else
           for (int c0 = ch0; c0 < ch0 + cw; c0 += 32) {
-            const uint32_t ta = t_lane + (uint32_t)c0;
-            const float* bp = s_bias + n0 + c0;
-            const float* sp = scale_row + n0 + c0;
-            const uint32_t u0 = (uint32_t)((c0 - ch0) >> 3);
-            if (ch0 + cw - c0 >= 32) {
-              if (scale_row) epi_fast<true, 32>(ta, bp, sp, relu_lo, my_row, swz, u0);
-              else epi_fast<false, 32>(ta, bp, sp, relu_lo, my_row, swz, u0);
-            } else {
-              if (scale_row) epi_fast<true, 16>(ta, bp, sp, relu_lo, my_row, swz, u0);
-              else epi_fast<false, 16>(ta, bp, sp, relu_lo, my_row, swz, u0);
+            uint32_t r[32];
+            const int nh = (ch0 + cw - c0 >= 32) ? 4 : 2;
+            if (nh == 4) tmem_ld32_issue(t_lane + (uint32_t)c0, r);
+            else tmem_ld16_issue(t_lane + (uint32_t)c0, r);
+            float4 bb[8], ss[8];
+  #pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int col = n0 + c0 + h * 8;
+              const bool on = h < nh && col < d.Cout;
+              bb[2 * h] = on ? *reinterpret_cast<const float4*>(s_bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              bb[2 * h + 1] = on ? *reinterpret_cast<const float4*>(s_bias + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (scale_row) {
+                ss[2 * h] = on ? *reinterpret_cast<const float4*>(scale_row + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+                ss[2 * h + 1] = on ? *reinterpret_cast<const float4*>(scale_row + col + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+              }
+            }
+            B2C_PROF_DECL(w6); B2C_PROF_START(w6);
+            tmem_ld_fence(r);
+            B2C_PROF_ACC(e_ld, w6);
+            if (last_j && c0 + 32 >= bn16) {
+              // last TMEM read of this tile is complete: hand the accumulator back before the (slow) store phase
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ps->tempty[acc]);
+            }
+  #pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              if (h >= nh) break;
+              const int col = n0 + c0 + h * 8;
+              float vv[8];
+              const float4 b0 = bb[2 * h], b1 = bb[2 * h + 1];
+              vv[0] = __uint_as_float(r[h * 8 + 0]) + b0.x; vv[1] = __uint_as_float(r[h * 8 + 1]) + b0.y;
+              vv[2] = __uint_as_float(r[h * 8 + 2]) + b0.z; vv[3] = __uint_as_float(r[h * 8 + 3]) + b0.w;
+              vv[4] = __uint_as_float(r[h * 8 + 4]) + b1.x; vv[5] = __uint_as_float(r[h * 8 + 5]) + b1.y;
+              vv[6] = __uint_as_float(r[h * 8 + 6]) + b1.z; vv[7] = __uint_as_float(r[h * 8 + 7]) + b1.w;
+              if (scale_row) {
+                const float4 s0 = ss[2 * h], s1 = ss[2 * h + 1];
+                vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
+                vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
+              }
+              if (do_relu) {
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+              }
+              if (col >= sig_from) {
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
+              }
+              if (staged) {
+                const uint32_t u = (uint32_t)((c0 - ch0) >> 3) + (uint32_t)h;          // 16-byte unit within the 128-byte row
+                st_shared16(my_row + ((u ^ swz) << 4), pack8(vv));
+              } else if (!mvalid || col >= d.Cout) {
+                // nothing to write
+              } else if (d.out_fp32 == 2) {
+                // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
+                float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (d.accumulate) vv[i] += o[(long long)i * d.out_row_stride];
+                  o[(long long)i * d.out_row_stride] = vv[i];
+                }
+              } else if (d.out_fp32) {
+                float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+                float4* o4 = reinterpret_cast<float4*>(o);
+                if (d.accumulate) {
+                  float4 a = o4[0], b = o4[1];
+                  vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
+                  vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
+                }
+                o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+              } else {
+                bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+                uint4* o4 = reinterpret_cast<uint4*>(o);
+                if (d.accumulate) {
+                  float e[8];
+                  unpack8(*o4, e);
+  #pragma unroll
+                  for (int i = 0; i < 8; ++i) vv[i] += e[i];
+                }
+                *o4 = pack8(vv);
+              }
             }
           }
-          if (ch0 + kStageChunkCols >= bn16) {
-            // last TMEM read of this tile is complete: hand the accumulator back before the store phase
-            tc_fence_before();
+          if (!staged) continue;
+          B2C_PROF_DECL(w7); B2C_PROF_START(w7);
+          if (use_store_tma && (cw == kStageChunkCols || n0 + ch0 + kStageChunkCols >= d.Cout)) {
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ps->tempty[acc]);
-          }
-        } else
-        for (int c0 = ch0; c0 < ch0 + cw; c0 += 32) {
-          uint32_t r[32];
-          const int nh = (ch0 + cw - c0 >= 32) ? 4 : 2;
-          if (nh == 4) tmem_ld32_issue(t_lane + (uint32_t)c0, r);
-          else tmem_ld16_issue(t_lane + (uint32_t)c0, r);
-          float4 bb[8], ss[8];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int col = n0 + c0 + h * 8;
-            const bool on = h < nh && col < d.Cout;
-            bb[2 * h] = on ? *reinterpret_cast<const float4*>(s_bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-            bb[2 * h + 1] = on ? *reinterpret_cast<const float4*>(s_bias + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (scale_row) {
-              ss[2 * h] = on ? *reinterpret_cast<const float4*>(scale_row + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-              ss[2 * h + 1] = on ? *reinterpret_cast<const float4*>(scale_row + col + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (store_mode == 1) {
+              // rows of the tile are consecutive output rows: one 32-row x 64-column box (clipped at Cout / Mtot by the map)
+              if (lane == 0 && mw < Mtot) tma_store_2d(&omaps.o[0], sub, n0 + ch0, (int)mw);
+            } else if (lane < n_issue) {
+              // strided output class: `piece` consecutive positions never leave a W row
+              const unsigned mp = mw + (unsigned)(lane * piece);
+              if (mp < Mtot) {
+                uint32_t rw, rh, rt;
+                uint32_t q = fdivmod(mp, s_fd[3 * ti.cls], rw);
+                q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
+                q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
+                tma_store_5d(&omaps.o[ti.cls], sub + (uint32_t)(lane * piece) * 128, n0 + ch0, (int)rw, (int)rh, (int)rt, (int)q);
+              }
             }
-          }
-          B2C_PROF_DECL(w6); B2C_PROF_START(w6);
-          tmem_ld_fence(r);
-          B2C_PROF_ACC(e_ld, w6);
-          if (c0 + 32 >= bn16) {
-            // last TMEM read of this tile is complete: hand the accumulator back before the (slow) store phase
-            tc_fence_before();
+            if (lane < n_issue) bulk_commit();
+          } else {
+            // coalesced fallback: 8 lanes per row (16-byte units), 4 rows per instruction
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ps->tempty[acc]);
-          }
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            if (h >= nh) break;
-            const int col = n0 + c0 + h * 8;
-            float vv[8];
-            const float4 b0 = bb[2 * h], b1 = bb[2 * h + 1];
-            vv[0] = __uint_as_float(r[h * 8 + 0]) + b0.x; vv[1] = __uint_as_float(r[h * 8 + 1]) + b0.y;
-            vv[2] = __uint_as_float(r[h * 8 + 2]) + b0.z; vv[3] = __uint_as_float(r[h * 8 + 3]) + b0.w;
-            vv[4] = __uint_as_float(r[h * 8 + 4]) + b1.x; vv[5] = __uint_as_float(r[h * 8 + 5]) + b1.y;
-            vv[6] = __uint_as_float(r[h * 8 + 6]) + b1.z; vv[7] = __uint_as_float(r[h * 8 + 7]) + b1.w;
-            if (scale_row) {
-              const float4 s0 = ss[2 * h], s1 = ss[2 * h + 1];
-              vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
-              vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
-            }
-            if (do_relu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
-            }
-            if (col >= sig_from) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = sigmoidf_(vv[i]);
-            }
-            if (staged) {
-              const uint32_t u = (uint32_t)((c0 - ch0) >> 3) + (uint32_t)h;          // 16-byte unit within the 128-byte row
-              st_shared16(my_row + ((u ^ swz) << 4), pack8(vv));
-            } else if (!mvalid || col >= d.Cout) {
-              // nothing to write
-            } else if (d.out_fp32 == 2) {
-              // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
-              float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (d.accumulate) vv[i] += o[(long long)i * d.out_row_stride];
-                o[(long long)i * d.out_row_stride] = vv[i];
+            const int ce = bn - ch0 < cw ? bn - ch0 : cw;            // real columns of this chunk
+            const int segv = ce > 0 ? ce >> 3 : 0;
+            const long long obyte = mvalid ? (opos * d.out_row_stride + d.out_c_off + n0 + ch0) * 2 : -1;
+            const int vcol = lane & 7, rsub = lane >> 3;
+  #pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int rl = itr * 4 + rsub;
+              const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(obyte & 0xffffffffll), rl);
+              const int hi = __shfl_sync(0xffffffffu, (int)(obyte >> 32), rl);
+              if (hi >= 0 && vcol < segv) {
+                const uint4 val = ld_shared16(sub + (uint32_t)rl * 128 + (((uint32_t)vcol ^ (uint32_t)(rl & 7)) << 4));
+                uint8_t* o = reinterpret_cast<uint8_t*>(d.out) + (((long long)hi << 32) | (long long)lo) + vcol * 16;
+                *reinterpret_cast<uint4*>(o) = val;
               }
-            } else if (d.out_fp32) {
-              float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
-              float4* o4 = reinterpret_cast<float4*>(o);
-              if (d.accumulate) {
-                float4 a = o4[0], b = o4[1];
-                vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
-                vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
-              }
-              o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-              o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
-            } else {
-              bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
-              uint4* o4 = reinterpret_cast<uint4*>(o);
-              if (d.accumulate) {
-                float e[8];
-                unpack8(*o4, e);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] += e[i];
-              }
-              *o4 = pack8(vv);
             }
           }
+          B2C_PROF_ACC(e_st, w7);
         }
-        if (!staged) continue;
-        B2C_PROF_DECL(w7); B2C_PROF_START(w7);
-        if (use_store_tma && (cw == kStageChunkCols || n0 + ch0 + kStageChunkCols >= d.Cout)) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (store_mode == 1) {
-            // rows of the tile are consecutive output rows: one 32-row x 64-column box (clipped at Cout / Mtot by the map)
-            if (lane == 0 && mw < Mtot) tma_store_2d(&omaps.o[0], sub, n0 + ch0, (int)mw);
-          } else if (lane < n_issue) {
-            // strided output class: `piece` consecutive positions never leave a W row
-            const unsigned mp = mw + (unsigned)(lane * piece);
-            if (mp < Mtot) {
-              uint32_t rw, rh, rt;
-              uint32_t q = fdivmod(mp, s_fd[3 * ti.cls], rw);
-              q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
-              q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
-              tma_store_5d(&omaps.o[ti.cls], sub + (uint32_t)(lane * piece) * 128, n0 + ch0, (int)rw, (int)rh, (int)rt, (int)q);
-            }
-          }
-          if (lane < n_issue) bulk_commit();
-        } else {
-          // coalesced fallback: 8 lanes per row (16-byte units), 4 rows per instruction
-          __syncwarp();
-          const int ce = bn - ch0 < cw ? bn - ch0 : cw;            // real columns of this chunk
-          const int segv = ce > 0 ? ce >> 3 : 0;
-          const long long obyte = mvalid ? (opos * d.out_row_stride + d.out_c_off + n0 + ch0) * 2 : -1;
-          const int vcol = lane & 7, rsub = lane >> 3;
-#pragma unroll
-          for (int itr = 0; itr < 8; ++itr) {
-            const int rl = itr * 4 + rsub;
-            const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(obyte & 0xffffffffll), rl);
-            const int hi = __shfl_sync(0xffffffffu, (int)(obyte >> 32), rl);
-            if (hi >= 0 && vcol < segv) {
-              const uint4 val = ld_shared16(sub + (uint32_t)rl * 128 + (((uint32_t)vcol ^ (uint32_t)(rl & 7)) << 4));
-              uint8_t* o = reinterpret_cast<uint8_t*>(d.out) + (((long long)hi << 32) | (long long)lo) + vcol * 16;
-              *reinterpret_cast<uint4*>(o) = val;
-            }
-          }
-        }
-        B2C_PROF_ACC(e_st, w7);
       }
       B2C_PROF_ACC(e_cols, w4);
     }
@@ -970,14 +1005,18 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
       if (lane == 0) {
         const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t b_st = a_st + (uint32_t)a_bytes;
+        // MN-major SW128: LBO = stride between 64-element MN atoms (8 KB), SBO = stride between 8-position groups.
+        // Only the start-address field (16-byte units) changes: +128 per 16-position K step, +1024 per 16 KB A tile.
+        const uint64_t ad0 = umma_desc_sw128(a_st, 8192, 1024);
+        const uint64_t bd0 = umma_desc_sw128(b_st, 8192, 1024);
+        const uint32_t accf = i > 0 ? 1u : 0u;
         for (int jt = 0; jt < mt_here; ++jt) {
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // MN-major SW128: LBO = stride between 64-element MN atoms (8 KB), SBO = stride between 8-position groups
-            const uint64_t ad = umma_desc_sw128(a_st + jt * kATileBytes + k * 2048, 8192, 1024);
-            const uint64_t bd = umma_desc_sw128(b_st + k * 2048, 8192, 1024);
-            umma_bf16(tmem_d + (uint32_t)(jt * bn16), ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          }
+          const uint64_t ad = ad0 + (uint64_t)(jt * (kATileBytes >> 4));
+          const uint32_t td = tmem_d + (uint32_t)(jt * bn16);
+          umma_bf16(td, ad, bd0, idesc, accf);
+          umma_bf16(td, ad + 128, bd0 + 128, idesc, 1u);
+          umma_bf16(td, ad + 256, bd0 + 256, idesc, 1u);
+          umma_bf16(td, ad + 384, bd0 + 384, idesc, 1u);
         }
         umma_commit(&ps->empty[stage]);
       }
@@ -1154,29 +1193,43 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.out & 15) == 0, "conv_fprop: tensors must be 16B aligned");
   if (d.bn_tile <= 0) d.bn_tile = pick_bn_tile(d.Cout);
   B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_fprop: bn_tile=%d invalid", d.bn_tile);
-  long long total_tiles = 0;
   int sum_taps = 0;
-  TileSched ts;
-  memset(&ts, 0, sizeof(ts));
+  long long tiles128 = 0;
   const int n_tiles = (d.Cout + d.bn_tile - 1) / d.bn_tile;
   for (int i = 0; i < d.nclass; ++i) {
-    ts.start[i] = (unsigned)total_tiles;
     const b2c_conv_class& c = d.cls[i];
     B2C_REQUIRE(c.taps && c.w && c.ntaps > 0, "conv_fprop: class %d incomplete", i);
     B2C_REQUIRE(((uintptr_t)c.w & 15) == 0, "conv_fprop: weights must be 16B aligned");
     const long long m = (long long)d.N * c.Qt * c.Qh * c.Qw;
     B2C_REQUIRE(m < (1LL << 31), "conv_fprop: GEMM-M too large");
-    total_tiles += ((m + kTileM - 1) / kTileM) * n_tiles;
+    tiles128 += ((m + kTileM - 1) / kTileM) * n_tiles;
     sum_taps += c.ntaps;
   }
-  for (int i = d.nclass; i < 9; ++i) ts.start[i] = (unsigned)total_tiles;
-  B2C_REQUIRE(total_tiles < (1LL << 31), "conv_fprop: too many tiles");
-  if (total_tiles == 0) return 0;
+  if (tiles128 == 0) return 0;
+  const int use_tma = (d.Cin % kBlockK == 0) ? 1 : 0;
   const int acc_cols = (d.bn_tile + 15) & ~15;
-  const int stage_bytes = kATileBytes + (((acc_cols * 128) + 1023) & ~1023);
+  const int b_tile_bytes_h = ((acc_cols * 128) + 1023) & ~1023;
   const int staging = kStagingBytes + 16;
   const int vecs = (((d.Cout + 3) & ~3) + ((d.scale_nc && d.N * d.Cout <= kMaxScaleSmem) ? d.N * d.Cout : 0)) * 4;
   const int fixed = (int)sizeof(FpropSmem) + sum_taps * 4 + staging + vecs + 1024 + 64;
+  // two 128-row tiles per scheduling unit (shared weight tile) when TMEM (2 x 2 x acc_cols <= 512 columns), shared
+  // memory (>= 3 stages) and the amount of work (>= 4 units per SM) allow it
+  int MT = 1;
+  if (use_tma && 4 * acc_cols <= 512 && (224 * 1024 - fixed) / (2 * kATileBytes + b_tile_bytes_h) >= 3 &&
+      tiles128 >= 8LL * b2c_num_sms())
+    MT = 2;
+  long long total_tiles = 0;
+  TileSched ts;
+  memset(&ts, 0, sizeof(ts));
+  for (int i = 0; i < d.nclass; ++i) {
+    ts.start[i] = (unsigned)total_tiles;
+    const b2c_conv_class& c = d.cls[i];
+    const long long m = (long long)d.N * c.Qt * c.Qh * c.Qw;
+    total_tiles += ((m + (long long)kTileM * MT - 1) / ((long long)kTileM * MT)) * n_tiles;
+  }
+  for (int i = d.nclass; i < 9; ++i) ts.start[i] = (unsigned)total_tiles;
+  B2C_REQUIRE(total_tiles < (1LL << 31), "conv_fprop: too many tiles");
+  const int stage_bytes = MT * kATileBytes + b_tile_bytes_h;
   int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B2C_REQUIRE(stages >= 3, "conv_fprop: tile too large for shared memory");
@@ -1191,7 +1244,6 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   }
   TmaMaps maps;
   memset(&maps, 0, sizeof(maps));
-  const int use_tma = (d.Cin % kBlockK == 0) ? 1 : 0;
   if (use_tma) {
     for (int i = 0; i < d.nclass; ++i) {
       const b2c_conv_class& c = d.cls[i];
@@ -1241,7 +1293,7 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   long long grid = b2c_num_sms();
   if (grid > total_tiles) grid = total_tiles;
   igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, omaps, ts, use_tma, stages, lag,
-                                                                                    total_tiles, n_tiles, sum_taps, store_mode, piece);
+                                                                                    total_tiles, n_tiles, sum_taps, store_mode, piece, MT);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_fprop launch");
   return 0;

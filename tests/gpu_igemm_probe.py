@@ -31,6 +31,10 @@ CASES = [
     ("convT3d s2 128->64 (1,28,28) N=4", True, 128, 64, (3, 3, 3), (2, 2, 2), (1, 28, 28), 1, 4),
     ("convT3d s2 128->64 (2,56,56) N=2", True, 128, 64, (3, 3, 3), (2, 2, 2), (2, 56, 56), 1, 2),
     ("conv 3x3x3 192->64 p1 (2,56,56)", False, 192, 64, (3, 3, 3), (1, 1, 1), (2, 56, 56), 1, 2),
+    # large-M cases: two 128-row tiles per scheduling unit (odd tile count -> a half-empty last unit)
+    ("1x1 64->128 M=185955 (odd tiles)", False, 64, 128, (1, 1, 1), (1, 1, 1), (7, 161, 165), "same", 1),
+    ("3x3x3 64->64 (8,112,112) N=2", False, 64, 64, (3, 3, 3), (1, 1, 1), (8, 112, 112), "same", 2),
+    ("convT3d s2 128->64 (4,64,64) N=2", True, 128, 64, (3, 3, 3), (2, 2, 2), (4, 64, 64), 1, 2),
 ]
 
 

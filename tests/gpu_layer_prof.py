@@ -19,6 +19,7 @@ CASES = {
     "pw128_32": (False, 128, 32, (1, 1, 1), (1, 1, 1), (8, 224, 224), 0, 32, False, True, "fprop"),
     "c3_64_64": (False, 64, 64, (3, 3, 3), (1, 1, 1), (4, 112, 112), 1, 32, True, True, "fprop"),
     "pc_fprop": (False, 832, 544, (1, 9, 9), (1, 1, 1), (1, 28, 28), 0, 32, False, True, "fprop"),
+    "pc_dgrad": (False, 832, 544, (1, 9, 9), (1, 1, 1), (1, 28, 28), 0, 32, False, False, "dgrad"),
     "inc_1x1": (False, 480, 192, (1, 1, 1), (1, 1, 1), (4, 28, 28), 0, 32, True, True, "fprop"),
     "up4_wgrad": (True, 128, 128, (3, 3, 3), (2, 2, 2), (4, 112, 112), 1, 32, False, False, "wgrad"),
     "c3_64_wgrad": (False, 64, 64, (3, 3, 3), (1, 1, 1), (4, 112, 112), 1, 32, False, False, "wgrad"),
