@@ -266,6 +266,15 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const bf16* __rest
 struct PoolGeom {
   int N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw;
 };
+// v / s and v % s for the (power-of-two in this model) pooling strides without the emulated integer division
+__device__ __forceinline__ bool pool_div(int v, int s, int& q) {
+  if ((s & (s - 1)) == 0) {
+    q = v >> (31 - __clz(s));
+    return (v & (s - 1)) == 0;
+  }
+  q = v / s;
+  return v - q * s == 0;
+}
 
 __global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restrict__ x, long long x_rs, int x_co,
                                                              bf16* __restrict__ y, long long y_rs, int y_co,
@@ -337,25 +346,19 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const bf16* __restr
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int a = 0; a < G.kt; ++a) {
       const int nt = it + G.pt - a;
-      if (nt < 0 || nt % G.st) continue;
-      const int ot = nt / G.st;
-      if (ot >= G.To) continue;
+      int ot;
+      if (nt < 0 || !pool_div(nt, G.st, ot) || ot >= G.To) continue;
       for (int b = 0; b < G.kh; ++b) {
         const int nh = ih + G.ph - b;
-        if (nh < 0 || nh % G.sh) continue;
-        const int oh = nh / G.sh;
-        if (oh >= G.Ho) continue;
+        int oh;
+        if (nh < 0 || !pool_div(nh, G.sh, oh) || oh >= G.Ho) continue;
         for (int c = 0; c < G.kw; ++c) {
           const int nw = iw + G.pw - c;
-          if (nw < 0 || nw % G.sw) continue;
-          const int ow = nw / G.sw;
-          if (ow >= G.Wo) continue;
+          int ow;
+          if (nw < 0 || !pool_div(nw, G.sw, ow) || ow >= G.Wo) continue;
           const int tap = (a * G.kh + b) * G.kw + c;
           const long long orow = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo + ow;
           const uint2 pk = *reinterpret_cast<const uint2*>(idx + orow * G.C + cv * 8);
-          // ~3/4 of the candidate windows chose another tap in all 8 channels: skip their gradient load
-          const uint32_t t4 = (uint32_t)tap * 0x01010101u;
-          if ((__vcmpeq4(pk.x, t4) | __vcmpeq4(pk.y, t4)) == 0u) continue;
           float d[8];
           unpack8(ld16(dy + orow * dy_rs + dy_co + cv * 8), d);
 #pragma unroll
