@@ -36,7 +36,7 @@ FLOP_PER_CLIP = 713.8e9
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bv", choices=["bv", "gv", "bvgv", "none"])
@@ -59,6 +59,8 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -68,6 +70,35 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(0.2)
+
+    def _run_nvml(self) -> bool:
+        """Same fields through NVML (what nvidia-smi reads), sampled every 20 ms so a sub-second timed region still gets
+        tens of samples; returns False when NVML is unavailable (-> nvidia-smi polling)."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        except Exception:
+            return False
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append([str(sm), str(mx), f"{pw:.1f}"] + [("Active" if mask & b else "Not Active") for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.02)
+        return True
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -255,8 +286,22 @@ def run_ours(args):
         recs, ops.TIMING = ops.TIMING, None
         t_ms = sum(a.elapsed_time(b) for _, a, b in recs)
         achieved = FLOP_PER_CLIP * P / (t_ms / 1e3) / 1e12
+        # DRAM traffic of the same launches from the committed ncu pass (profiles/r01_traffic.json, written by
+        # tools/summarize_profiles.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): per launch, like
+        # `achieved` (total over the step's conv launches / number of launches)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if int(tj.get("clips_per_gpu", P)) == P:
+                traffic = float(tj["igemm_dram_bytes_per_step"]) / max(1, len(recs))
+        except Exception:
+            pass
+        top = max(recs, key=lambda r: r[1].elapsed_time(r[2])) if recs else None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (all conv / transposed-conv launches)",
+                    "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, mean over the step's conv launches)",
+                    "algorithmic_flop_per_launch": FLOP_PER_CLIP * P / max(1, len(recs)),
+                    "longest_launch": {"layer": top[0], "ms": top[1].elapsed_time(top[2])} if top else None,
+                    "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (all conv / transposed-conv launches)",
                     "kernel_ms_per_step": t_ms, "kernel_launches_per_step": len(recs),
                     "share_of_step": t_ms / ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",

@@ -91,8 +91,34 @@ def full_summary(tag):
         print("\n".join(out))
 
 
+def traffic_summary(tag):
+    """gpurun_out/dram_<tag>.csv: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:igemm` over the
+    conv launches of ONE step -> profiles/r01_traffic.json (read by bench.py for roofline.traffic)."""
+    import json
+    path = os.path.join(ROOT, "gpurun_out", f"dram_{tag}.csv")
+    if not os.path.isfile(path):
+        return
+    lines = open(path).readlines()
+    start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
+    tot, ids = 0.0, set()
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines[start:]):
+        if row["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v = float(row["Metric Value"].replace(",", ""))
+            b = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row["Metric Unit"], 1)
+            tot += b
+            ids.add(row["ID"])
+            per[row["ID"]] = per.get(row["ID"], 0.0) + b
+    out = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:igemm (one step, {len(ids)} launches), "
+                     f"gpurun_out/dram_{tag}.csv", "clips_per_gpu": 16, "launches": len(ids), "igemm_dram_bytes_per_step": tot,
+           "largest_launches_bytes": sorted(per.values(), reverse=True)[:8]}
+    json.dump(out, open(os.path.join(OUT, "r01_traffic.json"), "w"), indent=1)
+    print(out)
+
+
 if __name__ == "__main__":
     t = sys.argv[1]
     os.makedirs(OUT, exist_ok=True)
     launch_summary(t)
     full_summary(t)
+    traffic_summary(t)
