@@ -280,14 +280,15 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restr
                                                              bf16* __restrict__ y, long long y_rs, int y_co,
                                                              uint8_t* __restrict__ idx, PoolGeom G) {
   const int CV = G.C / 8;
-  const long long total = (long long)G.N * G.To * G.Ho * G.Wo * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    long long o = i / CV;
+  // (host guarantees the element count < 2^31: 32-bit index arithmetic instead of emulated 64-bit divisions)
+  const unsigned total = (unsigned)G.N * G.To * G.Ho * G.Wo * CV;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (unsigned)CV);
+    unsigned o = i / (unsigned)CV;
     const long long orow = o;
-    const int ow = (int)(o % G.Wo); o /= G.Wo;
-    const int oh = (int)(o % G.Ho); o /= G.Ho;
-    const int ot = (int)(o % G.To); o /= G.To;
+    const int ow = (int)(o % (unsigned)G.Wo); o /= (unsigned)G.Wo;
+    const int oh = (int)(o % (unsigned)G.Ho); o /= (unsigned)G.Ho;
+    const int ot = (int)(o % (unsigned)G.To); o /= (unsigned)G.To;
     const int n = (int)o;
     // packed bf16x2 running maximum + packed 16-bit tap indices: per tap and channel pair ONE compare-to-mask and two
     // bit selects (ncu r01b: the fp32 compare / select version was ALU-bound at 25 % of HBM bandwidth).  Bit selects keep
@@ -332,14 +333,14 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const bf16* __restr
                                                              const uint8_t* __restrict__ idx, bf16* __restrict__ dx,
                                                              long long dx_rs, int dx_co, PoolGeom G, int accumulate) {
   const int CV = G.C / 8;
-  const long long total = (long long)G.N * G.Ti * G.Hi * G.Wi * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    long long p = i / CV;
+  const unsigned total = (unsigned)G.N * G.Ti * G.Hi * G.Wi * CV;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (unsigned)CV);
+    unsigned p = i / (unsigned)CV;
     const long long irow = p;
-    const int iw = (int)(p % G.Wi); p /= G.Wi;
-    const int ih = (int)(p % G.Hi); p /= G.Hi;
-    const int it = (int)(p % G.Ti); p /= G.Ti;
+    const int iw = (int)(p % (unsigned)G.Wi); p /= (unsigned)G.Wi;
+    const int ih = (int)(p % (unsigned)G.Hi); p /= (unsigned)G.Hi;
+    const int it = (int)(p % (unsigned)G.Ti); p /= (unsigned)G.Ti;
     const int n = (int)p;
     float acc[8];
 #pragma unroll
@@ -464,11 +465,12 @@ __global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __re
                                                                const float* __restrict__ bias_p, int N, int T, int H, int W) {
   const long long rows = (long long)N * T * H * W;
   const float bias = bias_p ? __ldg(bias_p) : 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
-    long long p = i;
-    const int w = (int)(p % W); p /= W;
-    const int h = (int)(p % H); p /= H;
-    const int t = (int)(p % T);
+  // (host guarantees rows < 2^31: 32-bit index arithmetic, the emulated 64-bit divisions dominated this kernel)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)rows; i += gridDim.x * blockDim.x) {
+    unsigned p = i;
+    const int w = (int)(p % (unsigned)W); p /= (unsigned)W;
+    const int h = (int)(p % (unsigned)H); p /= (unsigned)H;
+    const int t = (int)(p % (unsigned)T);
     float acc = bias;
     int tap = 0;
 #pragma unroll
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __re
         for (int c = 0; c < 3; ++c, ++tap) {
           const int ww = w + 1 - c;
           if ((unsigned)tt < (unsigned)T && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
-            acc += __ldg(P + (long long)tap * rows + i + ((long long)(1 - a) * H + (1 - b)) * W + (1 - c));
+            acc += __ldg(P + (long long)tap * rows + (long long)i + (((1 - a) * H + (1 - b)) * W + (1 - c)));
         }
       }
     }
@@ -493,11 +495,11 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
                                                                float* __restrict__ dbias, int N, int T, int H, int W, int cpad) {
   const long long rows = (long long)N * T * H * W;
   float bsum = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
-    long long p = i;
-    const int w = (int)(p % W); p /= W;
-    const int h = (int)(p % H); p /= H;
-    const int t = (int)(p % T);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)rows; i += gridDim.x * blockDim.x) {
+    unsigned p = i;
+    const int w = (int)(p % (unsigned)W); p /= (unsigned)W;
+    const int h = (int)(p % (unsigned)H); p /= (unsigned)H;
+    const int t = (int)(p % (unsigned)T);
     float v[32];
     int tap = 0;
 #pragma unroll
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
           const int ww = w - 1 + c;
           float g = 0.f;
           if ((unsigned)tt < (unsigned)T && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W)
-            g = __ldg(dout + i + ((long long)(a - 1) * H + (b - 1)) * W + (c - 1));
+            g = __ldg(dout + (long long)i + (((a - 1) * H + (b - 1)) * W + (c - 1)));
           v[tap] = g;
         }
       }
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
 #pragma unroll
     for (int k = 27; k < 32; ++k) v[k] = 0.f;
     bsum += v[13];  // centre tap == dout[i]
-    bf16* dst = dP + i * cpad;
+    bf16* dst = dP + (long long)i * cpad;
 #pragma unroll
     for (int q = 0; q < 4; ++q) st16(dst + q * 8, pack8(v + q * 8));
     for (int q = 4; q < cpad / 8; ++q) st16(dst + q * 8, make_uint4(0, 0, 0, 0));
@@ -745,6 +747,7 @@ B2C_API int b2c_maxpool_fwd(const void* x, int64_t x_rs, int32_t x_co, void* y, 
   B2C_REQUIRE(kt * kh * kw < 255, "maxpool_fwd: window too large");
   PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
   const long long total = (long long)N * To * Ho * Wo * (C / 8);
+  B2C_REQUIRE(total < (1LL << 31) - (1LL << 22) && (long long)N * Ti * Hi * Wi * (C / 8) < (1LL << 31), "maxpool_fwd: tensor too large");
   maxpool_fwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, x_rs, x_co, (bf16*)y, y_rs, y_co, idx, G);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("maxpool_fwd");
@@ -760,6 +763,7 @@ B2C_API int b2c_maxpool_bwd(const void* dy, int64_t dy_rs, int32_t dy_co, const 
   CHECK_VIEW("maxpool_bwd(dx)", C, dx_rs, dx_co);
   PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
   const long long total = (long long)N * Ti * Hi * Wi * (C / 8);
+  B2C_REQUIRE(total < (1LL << 31) - (1LL << 22), "maxpool_bwd: tensor too large");
   maxpool_bwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, idx, (bf16*)dx, dx_rs, dx_co, G,
                                                                       accumulate);
   b2c_launches_add(1);
@@ -810,7 +814,7 @@ B2C_API int b2c_add(const void* a, int64_t a_rs, int32_t a_co, const void* b, in
 
 B2C_API int b2c_stencil27_fwd(const float* P, float* out, const float* bias, int32_t N, int32_t T, int32_t H, int32_t W,
                               b2c_stream_t s) {
-  B2C_REQUIRE(P && out && N > 0, "stencil27_fwd: bad args");
+  B2C_REQUIRE(P && out && N > 0 && (long long)N * T * H * W < (1LL << 31) - (1LL << 22), "stencil27_fwd: bad args");
   stencil27_fwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(P, out, bias, N, T, H, W);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("stencil27_fwd");
@@ -819,7 +823,8 @@ B2C_API int b2c_stencil27_fwd(const float* P, float* out, const float* bias, int
 
 B2C_API int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t N, int32_t T, int32_t H, int32_t W, int32_t cpad,
                               b2c_stream_t s) {
-  B2C_REQUIRE(dout && dP && N > 0 && cpad >= 32 && cpad % 8 == 0, "stencil27_bwd: bad args");
+  B2C_REQUIRE(dout && dP && N > 0 && cpad >= 32 && cpad % 8 == 0 && (long long)N * T * H * W < (1LL << 31) - (1LL << 22),
+              "stencil27_bwd: bad args");
   stencil27_bwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, dbias, N, T, H, W, cpad);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("stencil27_bwd");
