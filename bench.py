@@ -36,8 +36,8 @@ FLOP_PER_CLIP = 713.8e9
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bv", choices=["bv", "gv", "bvgv", "none"])
     ap.add_argument("--clips", type=int, default=8, help="labeled (= unlabeled) clips per GPU")
@@ -308,6 +308,8 @@ def run_ours(args):
                     "longest_launch": {"layer": top[0], "ms": top[1].elapsed_time(top[2])} if top else None,
                     "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (all conv / transposed-conv launches)",
                     "kernel_ms_per_step": t_ms, "kernel_launches_per_step": len(recs),
+                    "peak_burst": float(peaks.get("bf16_tflops", 0.0)) or None,
+                    "frac_of_burst": (achieved / float(peaks["bf16_tflops"])) if peaks.get("bf16_tflops") else None,
                     "share_of_step": t_ms / ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "algorithmic_flop_per_step": FLOP_PER_CLIP * P}

@@ -271,3 +271,38 @@ def test_encoder_modules_fwd_bwd(setup, which):
     model.load_state_dict(sd0)
     assert e_fwd < 2e-2 and e_fwd_ex < 3e-2, (e_fwd, e_fwd_ex)
     assert errs[worst] < 3e-2, (worst, errs[worst])
+
+
+def test_jhmdb_variant_eval_and_step():
+    """Config 4: the 21-class JHMDB CapsNet (ConvCaps(32, 21), upsample1 ConvT2d(336 -> 64),
+    main_jhmdb.py:338,383).  Eval forward (1 clip; the fp64 oracle of one clip takes a few seconds on the host) against
+    the oracle restatement with the same name-keyed weights, then one fused --bv training step (finite losses, gradients
+    reach the 21-class-specific tensors)."""
+    from b200caps.step import StepArgs, TrainStep
+    from models.capsules_jhmdb_semi_sup_pa import CapsNet
+    from oracle import restate
+
+    sd = restate.make_state_dict(21, seed=0)
+    model = CapsNet(pt_path=None)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    b = restate.synthetic_batch(1, 1, seed=47, num_classes=21)
+    with torch.no_grad():
+        out, act, _ = model(b["data"][:1].cuda(), b["action"][:1].cuda(), b["labels"][:1].cuda(), 0, 0)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        o_ref, a_ref, _ = restate.capsnet_forward(sd64, b["data"][:1].double(), b["action"][:1].double(), b["labels"][:1].double(),
+                                                  0, 0, False, None, None, 21)
+    assert act.shape == (1, 21)
+    assert rel(act, a_ref) < 2e-2
+    assert rel(out, o_ref) < 2e-2
+
+    model.train()
+    step = TrainStep(model, StepArgs(bv=True, gv=False, n_frames=5, wt_cons=0.1, lr=1e-4))
+    r = step(b["data"].cuda(), b["fl_data"].cuda(), b["action"].cuda(), b["seg"].cuda(), b["labels"], epoch=1)
+    for k in ("total", "bce", "dice", "cls", "cons"):
+        assert torch.isfinite(r[k]).all(), k
+    assert r["pred_action"].shape == (2, 21)
+    g = dict(model.named_parameters())
+    assert float(step.flat.grad.abs().max()) > 0
+    assert g["upsample1.weight"].shape[0] == 336
