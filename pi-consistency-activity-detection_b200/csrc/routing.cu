@@ -21,7 +21,10 @@ long long b2c_launches_add(long long n);
 namespace {
 
 constexpr int kB = 32;        // input capsule types
-constexpr int kNW = 8;        // warps per CTA
+#ifndef B2C_ROUTING_WARPS
+#define B2C_ROUTING_WARPS 8
+#endif
+constexpr int kNW = B2C_ROUTING_WARPS;   // warps per CTA (8 or 16)
 constexpr int kIPT = kB / kNW;  // i's per thread
 constexpr int kRT = kNW * 32;
 constexpr float kEps = 1e-8f;
@@ -179,13 +182,13 @@ __device__ __forceinline__ void e_step(const float (*V)[16], const float* mu, co
 }
 
 // =====================================================================================
-__global__ void __launch_bounds__(kRT, 2) em_routing_fwd_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+__global__ void __launch_bounds__(kRT, kNW == 8 ? 2 : 1) em_routing_fwd_kernel(const float* __restrict__ caps, const float* __restrict__ W,
                                                                 const float* __restrict__ beta_u, const float* __restrict__ beta_a,
                                                                 float* __restrict__ out, long long b, int C) {
   extern __shared__ float sm[];
   float* sW = sm;                          // [32][16][32]
   float* red = sW + kB * 16 * 32;          // [2][8][17][32]
-  float* s_caps = red + 2 * kNW * 17 * 32; // [544]
+  float* s_caps = red + (kNW + 1) * 17 * 32; // [544]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool active = lane < C;
   load_W_smem(W, sW, C);
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
   float* sW = sm;                            // [32][16][32]
   float* sgW = sW + kB * 16 * 32;            // [32][16][32] per-CTA dW accumulator (owner-thread RMW, no atomics)
   float* red = sgW + kB * 16 * 32;           // [2][8][17][32]
-  float* s_mu = red + 2 * kNW * 17 * 32;     // [3][16][32]
+  float* s_mu = red + (kNW + 1) * 17 * 32;     // [3][16][32]
   float* s_S = s_mu + 3 * 16 * 32;           // [3][16][32]
   float* s_gbu = s_S + 3 * 16 * 32;          // [17][32]  dbeta_u (16) + dbeta_a (1) accumulators (warp 0)
   float* s_caps = s_gbu + 17 * 32;           // [544]
@@ -551,14 +554,14 @@ B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* b
   B2C_REQUIRE(caps && W && beta_u && beta_a && out, "em_routing_fwd: null pointer");
   B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_fwd: C=%d must be in [1,32]", C);
   if (b <= 0) return 0;
-  const size_t smem = (size_t)(kB * 16 * 32 + 2 * kNW * 17 * 32 + 544) * sizeof(float);
+  const size_t smem = (size_t)(kB * 16 * 32 + (kNW + 1) * 17 * 32 + 544) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd attr");
     cfg = true;
   }
-  long long grid = 2LL * b2c_num_sms();
+  long long grid = (kNW == 8 ? 2LL : 1LL) * b2c_num_sms();
   if (grid > b) grid = b;
   em_routing_fwd_kernel<<<(unsigned)grid, kRT, smem, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, b, C);
   b2c_launches_add(1);
@@ -571,7 +574,7 @@ B2C_API int b2c_em_routing_bwd(const float* caps, const float* W, const float* b
   B2C_REQUIRE(caps && W && beta_u && beta_a && dout && dcaps && dW && dbeta_u && dbeta_a, "em_routing_bwd: null pointer");
   B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_bwd: C=%d must be in [1,32]", C);
   if (b <= 0) return 0;
-  const size_t smem = (size_t)(2 * kB * 16 * 32 + 2 * kNW * 17 * 32 + 2 * 3 * 16 * 32 + 17 * 32 + 544 + 32 * 17 + 3 * 3 * kIPT * kRT +
+  const size_t smem = (size_t)(2 * kB * 16 * 32 + (kNW + 1) * 17 * 32 + 2 * 3 * 16 * 32 + 17 * 32 + 544 + 32 * 17 + 3 * 3 * kIPT * kRT +
                                3 * 4 * 32) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {

@@ -35,6 +35,7 @@ CASES = [
     ("1x1 64->128 M=185955 (odd tiles)", False, 64, 128, (1, 1, 1), (1, 1, 1), (7, 161, 165), "same", 1),
     ("3x3x3 64->64 (8,112,112) N=2", False, 64, 64, (3, 3, 3), (1, 1, 1), (8, 112, 112), "same", 2),
     ("convT3d s2 128->64 (4,64,64) N=2", True, 128, 64, (3, 3, 3), (2, 2, 2), (4, 64, 64), 1, 2),
+    ("convT2d 9x9 336->64 (JHMDB upsample1)", True, 336, 64, (1, 9, 9), (1, 1, 1), (1, 20, 20), 0, 1),
 ]
 
 
