@@ -551,15 +551,17 @@ struct Im2colGeom {
 // The Kpad-wide rows then stream out as coalesced 16-byte stores, each assembled from 8 staged elements through a
 // per-block column -> staged-offset table (padding columns point at a zero slot).
 constexpr int kIm2colWB = 56;
-__global__ void __launch_bounds__(kBlock) im2col_small_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Im2colGeom G,
+__global__ void __launch_bounds__(512) im2col_small_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Im2colGeom G,
                                                               int strips, int pitch) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  const int nthr = (int)blockDim.x;      // a multiple of the 16-byte column groups per row (host)
   const int pairs = G.kt * G.kh;
   const int run = G.kw * G.C;
   const int zero_slot = pairs * pitch;
+  const int zero_len = (kIm2colWB - 1) * G.sw * G.C + 8;      // padding columns may be read at zero_slot + row base too
   unsigned short* tab = reinterpret_cast<unsigned short*>(s_raw);                       // Kpad entries
-  bf16* sin = reinterpret_cast<bf16*>(s_raw + (size_t)G.Kpad * 2);                      // pairs * pitch + 8 elements
-  for (int k = threadIdx.x; k < G.Kpad; k += kBlock) {
+  bf16* sin = reinterpret_cast<bf16*>(s_raw + (size_t)G.Kpad * 2);                      // pairs * pitch + zero_len elements
+  for (int k = threadIdx.x; k < G.Kpad; k += nthr) {
     int off = zero_slot;
     if (k < G.K) {
       const int p = k / run;
@@ -567,9 +569,22 @@ __global__ void __launch_bounds__(kBlock) im2col_small_kernel(const bf16* __rest
     }
     tab[k] = (unsigned short)off;
   }
-  if (threadIdx.x < 8) sin[zero_slot + threadIdx.x] = __float2bfloat16(0.f);
+  for (int k = threadIdx.x; k < zero_len; k += nthr) sin[zero_slot + k] = __float2bfloat16(0.f);
+  __syncthreads();
   const int wpix = (kIm2colWB - 1) * G.sw + G.kw;                                       // staged pixels per input row
   const int vec_per_row = G.Kpad / 8;
+  // Each thread owns ONE 16-byte column group of the row (its 8 staged offsets live in registers) and walks the rows
+  // of the strip: per output vector 8 two-byte shared loads + one 16-byte store (ncu r01f: the per-vector table
+  // fetch and zero-slot selects made this kernel issue/L1 bound at 2.4 TB/s of writes).
+  const int lanes = (nthr / vec_per_row) * vec_per_row;                               // threads that own a column group
+  const int rstep = nthr / vec_per_row;                                                 // rows written per sweep
+  const int my_v = threadIdx.x % vec_per_row, my_r0 = threadIdx.x / vec_per_row;
+  unsigned o[8];
+  {
+    const uint4 tv = *reinterpret_cast<const uint4*>(tab + my_v * 8);
+    o[0] = tv.x & 0xffffu; o[1] = tv.x >> 16; o[2] = tv.y & 0xffffu; o[3] = tv.y >> 16;
+    o[4] = tv.z & 0xffffu; o[5] = tv.z >> 16; o[6] = tv.w & 0xffffu; o[7] = tv.w >> 16;
+  }
   const long long nblk = (long long)G.N * G.To * G.Ho * strips;
   for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     long long r = blk;
@@ -581,34 +596,36 @@ __global__ void __launch_bounds__(kBlock) im2col_small_kernel(const bf16* __rest
     const int nrow = min(kIm2colWB, G.Wo - wo0);
     const int t0 = to * G.st - G.pt, h0 = ho * G.sh - G.ph, w0 = wo0 * G.sw - G.pw;
     __syncthreads();                                                                    // previous strip fully written out
-    for (int i = threadIdx.x; i < pairs * wpix; i += kBlock) {
-      const int p = i / wpix, wl = i - p * wpix;
+    // staging: one warp per (kt, kh) input row, lanes along W -- no per-pixel index divisions
+    for (int p = (int)(threadIdx.x >> 5); p < pairs; p += (nthr + 31) >> 5) {
       const int a = p / G.kh, b = p - a * G.kh;
-      const int t = t0 + a, h = h0 + b, w = w0 + wl;
-      uint4 px = make_uint4(0, 0, 0, 0);
-      if ((unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H && (unsigned)w < (unsigned)G.W)
-        px = ld16(x + ((((long long)n * G.T + t) * G.H + h) * (long long)G.W + w) * G.Cs);   // Cs == 8: one pixel = 16 bytes
-      const bf16* pv = reinterpret_cast<const bf16*>(&px);
-      bf16* dst = sin + p * pitch + wl * G.C;
-      for (int ch = 0; ch < G.C; ++ch) dst[ch] = pv[ch];
+      const int t = t0 + a, h = h0 + b;
+      const bool rowok = (unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H;
+      const bf16* src = x + (((long long)n * G.T + t) * G.H + h) * (long long)G.W * G.Cs;
+      bf16* drow = sin + p * pitch;
+      for (int wl = (int)(threadIdx.x & 31); wl < wpix; wl += 32) {
+        const int w = w0 + wl;
+        uint4 px = make_uint4(0, 0, 0, 0);
+        if (rowok && (unsigned)w < (unsigned)G.W) px = ld16(src + (long long)w * G.Cs);   // Cs == 8: one pixel = 16 bytes
+        const bf16* pv = reinterpret_cast<const bf16*>(&px);
+        bf16* dst = drow + wl * G.C;
+        for (int ch = 0; ch < G.C; ++ch) dst[ch] = pv[ch];
+      }
     }
     __syncthreads();
-    bf16* obase = out + ((((long long)n * G.To + to) * G.Ho + ho) * (long long)G.Wo + wo0) * G.Kpad;
-    const unsigned short* sraw = reinterpret_cast<const unsigned short*>(sin);
-    for (int i = threadIdx.x; i < nrow * vec_per_row; i += kBlock) {
-      const int rl = i / vec_per_row, v = i - rl * vec_per_row;
-      const uint4 tv = *reinterpret_cast<const uint4*>(tab + v * 8);
-      const int base = rl * G.sw * G.C;
-      const unsigned tw[4] = {tv.x, tv.y, tv.z, tv.w};
-      unsigned o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o0 = (int)(tw[j] & 0xffffu), o1 = (int)(tw[j] >> 16);
-        const unsigned e0 = sraw[o0 == zero_slot ? o0 : o0 + base];
-        const unsigned e1 = sraw[o1 == zero_slot ? o1 : o1 + base];
-        o[j] = e0 | (e1 << 16);
+    if ((int)threadIdx.x < lanes) {
+      bf16* orow = out + ((((long long)n * G.To + to) * G.Ho + ho) * (long long)G.Wo + wo0) * G.Kpad + my_v * 8;
+      const unsigned short* sraw = reinterpret_cast<const unsigned short*>(sin);
+      const int bstep = G.sw * G.C;
+      for (int rl = my_r0; rl < nrow; rl += rstep) {
+        const unsigned short* sb = sraw + rl * bstep;
+        uint4 v;
+        v.x = (unsigned)sb[o[0]] | ((unsigned)sb[o[1]] << 16);
+        v.y = (unsigned)sb[o[2]] | ((unsigned)sb[o[3]] << 16);
+        v.z = (unsigned)sb[o[4]] | ((unsigned)sb[o[5]] << 16);
+        v.w = (unsigned)sb[o[6]] | ((unsigned)sb[o[7]] << 16);
+        st16(orow + (long long)rl * G.Kpad, v);
       }
-      st16(obase + (long long)rl * G.Kpad + v * 8, make_uint4(o[0], o[1], o[2], o[3]));
     }
   }
 }
@@ -848,11 +865,15 @@ B2C_API int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, in
   B2C_REQUIRE(Kpad % 64 == 0 && Kpad >= K && Cs == 8, "im2col_small: bad K / Cs");
   Im2colGeom G{N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad};
   const int pitch = ((kIm2colWB - 1) * sw + kw) * C;
-  const size_t smem = (size_t)Kpad * 2 + ((size_t)kt * kh * pitch + 8) * 2;
-  B2C_REQUIRE(smem <= 48 * 1024 && (size_t)kt * kh * pitch + 8 < 65536, "im2col_small: footprint too large");
+  const size_t zero_len = (size_t)(kIm2colWB - 1) * sw * C + 8;
+  const size_t smem = (size_t)Kpad * 2 + ((size_t)kt * kh * pitch + zero_len) * 2;
+  B2C_REQUIRE(smem <= 48 * 1024 && (size_t)kt * kh * pitch + zero_len < 65536 && Kpad / 8 <= 512, "im2col_small: footprint too large");
   const int strips = (Wo + kIm2colWB - 1) / kIm2colWB;
   const long long nblk = (long long)N * To * Ho * strips;
-  im2col_small_kernel<<<grid_for(nblk, 1, 32), kBlock, smem, (cudaStream_t)s>>>((const bf16*)x, (bf16*)out, G, strips, pitch);
+  const int vpr = Kpad / 8;
+  const int threads = vpr * (320 / vpr > 0 ? 320 / vpr : 1);      // whole rows per sweep: 272 threads for Kpad = 1088
+  B2C_REQUIRE(threads <= 512, "im2col_small: Kpad too large");
+  im2col_small_kernel<<<grid_for(nblk, 1, 24), threads, smem, (cudaStream_t)s>>>((const bf16*)x, (bf16*)out, G, strips, pitch);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("im2col_small");
   return 0;
