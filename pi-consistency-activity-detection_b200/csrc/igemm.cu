@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "../../include/b200caps.h"
 #include <string.h>
+#include <stdlib.h>
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
 
 static long long g_launches = 0;
@@ -1190,6 +1191,17 @@ constexpr int kCtaSmemTarget = 72 * 1024;    // ~3 CTAs per SM (2 for 256-wide t
 
 }  // namespace
 
+// 128-row tiles per SM above which two tiles are paired into one scheduling unit (B2C_MT_MIN_TILES_PER_SM overrides)
+static int mt_min_tiles_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_MT_MIN_TILES_PER_SM");
+    v = e ? atoi(e) : 8;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(dh != nullptr, "conv_fprop: null descriptor");
   b2c_conv_desc d = *dh;
@@ -1226,7 +1238,7 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   // memory (>= 3 stages) and the amount of work (>= 4 units per SM) allow it
   int MT = 1;
   if (use_tma && 4 * acc_cols <= 512 && (224 * 1024 - fixed) / (2 * kATileBytes + b_tile_bytes_h) >= 3 &&
-      tiles128 >= 8LL * b2c_num_sms())
+      tiles128 >= (long long)mt_min_tiles_per_sm() * b2c_num_sms())
     MT = 2;
   long long total_tiles = 0;
   TileSched ts;
@@ -1317,6 +1329,17 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   return 0;
 }
 
+// grid size of the position split in waves of CTAs (B2C_WGRAD_WAVES overrides)
+static int wgrad_waves() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_WGRAD_WAVES");
+    v = e ? atoi(e) : 1;      // measured on the 8+8 step: 1 wave 36.9 ms, 2 waves 37.4, 3 waves 37.8, 4 waves 38.3
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(dh != nullptr, "conv_wgrad: null descriptor");
   b2c_wgrad_desc d = *dh;
@@ -1350,11 +1373,12 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   const int mtc = (mt + MT - 1) / MT;      // CTAs along the (tap, gc) dimension
   int nsplit = d.nsplit;
   if (nsplit <= 0) {
-    // long position loops with a deep pipeline, one CTA per SM: pick the split so the grid is ~1-2 full waves
+    // long position loops with a deep pipeline, one CTA per SM: pick the split so the grid is at most one full wave
     const long long tiles = (long long)mtc * nt;
     const long long sms = b2c_num_sms();
-    long long want = (2 * sms + tiles - 1) / tiles;
-    if (tiles * want > 2 * sms && want > 1) --want;
+    const long long waves = wgrad_waves();
+    long long want = (waves * sms + tiles - 1) / tiles;
+    if (tiles * want > waves * sms && want > 1) --want;
     long long cap = nkb / 8;
     if (cap < 1) cap = 1;
     nsplit = (int)(want < cap ? want : cap);
