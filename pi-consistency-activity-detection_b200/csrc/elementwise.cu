@@ -597,7 +597,8 @@ __global__ void __launch_bounds__(512) im2col_small_kernel(const bf16* __restric
     const int t0 = to * G.st - G.pt, h0 = ho * G.sh - G.ph, w0 = wo0 * G.sw - G.pw;
     __syncthreads();                                                                    // previous strip fully written out
     // staging: one warp per (kt, kh) input row, lanes along W -- no per-pixel index divisions
-    for (int p = (int)(threadIdx.x >> 5); p < pairs; p += (nthr + 31) >> 5) {
+    // (only FULL warps stage: the block size is a multiple of the row's column groups, not of 32)
+    for (int p = ((int)threadIdx.x >> 5) < (nthr >> 5) ? (int)(threadIdx.x >> 5) : pairs; p < pairs; p += nthr >> 5) {
       const int a = p / G.kh, b = p - a * G.kh;
       const int t = t0 + a, h = h0 + b;
       const bool rowok = (unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H;
