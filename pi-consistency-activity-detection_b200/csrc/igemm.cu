@@ -1,16 +1,16 @@
-// Generalised implicit-GEMM convolution for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM),
-// im2col gather by cp.async into 128B-swizzled UMMA tiles, mbarrier producer/consumer pipeline.
+// Generalised implicit-GEMM convolution for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged
+// by TMA (im2col tensor maps for activations, bulk copies for pre-swizzled weight tiles) into 128B-swizzled UMMA
+// tiles, mbarrier producer/consumer pipelines, TMA tensor stores for the results.
 //
-//   fprop-like kernel : D[M = output positions (128/CTA), N = Cout tile] = A_im2col[M,K] * W[N,K]^T
+//   fprop-like kernel : D[M = output positions (128 or 2x128 per unit), N = Cout tile] = A_im2col[M,K] * W[N,K]^T
 //                       A and W are K-major.  Covers conv fprop, dgrad, transposed-conv fprop
-//                       (by output-parity class) and transposed-conv dgrad.
-//   wgrad kernel      : D[M = (tap,ci) tile of 128, N = Cp tile] = sum_positions Gcol[pos,M] * P[pos,N]
+//                       (by output-parity class) and transposed-conv dgrad.  Persistent, 416 threads:
+//                       warps 0-3 producers (TMA: one thread; cp.async gather: 128 threads), warp 4 TMEM allocator +
+//                       single-thread UMMA issuer, warps 5-12 epilogue (two quartets alternating tiles).
+//   wgrad kernel      : D[M = 1-3 (tap,ci) tiles of 128, N = Cp tile] = sum_positions Gcol[pos,M] * P[pos,N]
 //                       both operands MN-major (positions are the GEMM-K dimension), split over
-//                       position ranges, fp32 red.add into the weight gradient.
-//
-// Warp roles (160 threads): warps 0-3 = producers (one GEMM row / position per thread) and, after the
-// main loop, the TMEM->global epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4 = TMEM allocator +
-// single-thread UMMA issuer.
+//                       position ranges, fp32 red.add into the weight gradient.  160 threads: warps 0-3 producers
+//                       then epilogue (warp w owns TMEM lanes 32w..32w+31), warp 4 allocator + UMMA issuer.
 #include "common.cuh"
 #include "../../include/b200caps.h"
 #include <string.h>
