@@ -78,3 +78,29 @@ def test_transposed_classes_skip_zero_taps():
     assert sorted(len(c.taps) for c in plan.fprop) == [1, 2, 2, 2, 4, 4, 4, 8]
     # algorithmic MACs of upsample4 per clip (22.196 GMAC)
     assert abs(plan.macs_fprop(1) / 1e9 - 22.196) < 0.01
+
+
+def test_fastdiv_formula_matches_integer_division():
+    """Host restatement of csrc/igemm.cu make_fastdiv / fdiv (Granlund-Montgomery multiply-shift division used for the
+    tile -> (clip, t, h, w) arithmetic of every warp role): exact for all 32-bit numerators the kernels can produce."""
+    import random
+
+    def make(d):
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        m = ((((1 << l) - d) << 32) // d + 1) & 0xFFFFFFFF
+        return m, min(l, 1), max(l - 1, 0)
+
+    def fdiv(n, p):
+        m, sh1, sh2 = p
+        t = (m * n) >> 32
+        return ((t + (((n - t) & 0xFFFFFFFF) >> sh1)) & 0xFFFFFFFF) >> sh2
+
+    rng = random.Random(0)
+    divisors = list(range(1, 300)) + [448, 544, 832, 1088, 4096, 50176, 401408, 12845056]
+    for d in divisors:
+        p = make(d)
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 31) - d] + [rng.randrange(0, 1 << 31) for _ in range(200)]
+        for n in ns:
+            assert fdiv(n, p) == n // d, (n, d)
