@@ -331,9 +331,9 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, threads = cpu_reference_step_time(1, 1)
+        sec, threads = cpu_reference_step_time(3, 1)
         cpu_baseline = {"value": 2.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "oracle port of the full --bv step + backward, 1 labeled + 1 unlabeled clip, fp32, 1 warm-up + 1 timed"}
+                        "sample": "oracle port of the full --bv step + backward, 1 labeled + 1 unlabeled clip, fp32, 1 warm-up + 3 timed (mean)"}
 
     if rank == 0:
         line = {
