@@ -54,6 +54,8 @@ typedef struct {
   void* out;             /* bf16 or fp32 */
   const float* bias;     /* [Cout] or NULL */
   const float* scale_nc; /* [N][Cout] per-sample channel scale (Dropout3d mask) or NULL */
+  float* stat_sums;      /* NULL, or fp32 [stat_groups][2][Cout] (zeroed by the caller): the epilogue adds the per-channel sum
+                            and sum of squares of the values it stores (BatchNorm batch statistics fused into the GEMM) */
   int64_t in_row_stride, out_row_stride;
   int32_t in_c_off, out_c_off, Cin, Cout;
   int32_t N, Ti, Hi, Wi, To, Ho, Wo;
@@ -63,6 +65,11 @@ typedef struct {
   int32_t sigmoid_from; /* apply sigmoid to output channels >= this (PrimaryCaps 'a'), <0: none */
   int32_t accumulate;   /* out += result (gradient accumulation) */
   int32_t bn_tile;      /* output-channel tile per CTA: must equal the bn_tile the weights were packed with */
+  int32_t tap_pitch;    /* K elements per tap in the packed weights: 0 = Cin; ceil64(Cin) = zero-padded channel tail, which puts
+                           layers whose Cin is not a multiple of 64 on the TMA path (TMA zero-fills the channels past Cin) */
+  int32_t dtype;        /* 0: bf16 operands (kind::f16), 1: fp32 activations / tf32 operands (kind::tf32; out must be fp32) */
+  int32_t stat_groups;  /* statistic groups of stat_sums: the batch N splits into stat_groups equal runs of clips */
+  int32_t round_out;    /* dtype 1 only: round the stored fp32 result to tf32 (it is the next GEMM's operand) */
   int32_t nclass;
   b2c_conv_class cls[8];
 } b2c_conv_desc;
@@ -90,6 +97,7 @@ typedef struct {
   int32_t bn_tile; /* 0 = auto */
   int32_t nsplit;  /* 0 = auto */
   int32_t atomic;  /* 1: atomicAdd into dw, 0: plain store (only legal when nsplit==1) */
+  int32_t dtype;   /* 0: bf16 operands, 1: fp32 tensors / tf32 operands */
 } b2c_wgrad_desc;
 
 int b2c_conv_wgrad(const b2c_wgrad_desc* desc_host, b2c_stream_t stream);
@@ -246,18 +254,21 @@ int b2c_gv_mask(const float* out, float* m, float* mm, int32_t P, int32_t H, int
  * _grad: dout -= g, dflp(+mirror) += g with g = (a_l2 + a_lv (w1+w2')) 2d/(P THW) + a_lg 2 B d/(THW P^2). */
 int b2c_cons_reduce(const float* out, const float* flp, const float* w1, const float* w2, const float* wg, double* acc,
                     int32_t P, int32_t H, int32_t W, int32_t mirror, int32_t w2_tflip, b2c_stream_t s);
+/* dev_scalars (may be NULL): device float[3] that overrides (wt_ramp, bv_wt, gv_wt) resp. (a_l2, a_lv, a_lg), so the
+ * per-epoch schedule values (main_ucf101.py:181,419) can change between replays of one captured CUDA graph. */
 int b2c_cons_finish(const double* acc, float* loss, int32_t P, int32_t H, int32_t W, int32_t mode, float wt_ramp,
-                    float bv_wt, float gv_wt, b2c_stream_t s);
+                    float bv_wt, float gv_wt, const float* dev_scalars, b2c_stream_t s);
 int b2c_cons_grad(const float* out, const float* flp, const float* w1, const float* w2, const float* wg, float* dout,
                   float* dflp, int32_t P, int32_t H, int32_t W, int32_t mirror, int32_t w2_tflip, float a_l2, float a_lv,
-                  float a_lg, b2c_stream_t s);
+                  float a_lg, const float* dev_scalars, b2c_stream_t s);
 
 /* ------------------------------------------------------------------------------------
  * Optimiser: Adam(lr, betas, eps=1e-6, wd=0) over one flat fp32 buffer (main_ucf101.py:416,184)
  * ---------------------------------------------------------------------------------- */
-/* step_dev: device int32 step counter, incremented by the call (graph replayable bias correction) */
+/* step_dev: device int32 step counter, incremented by the call (graph replayable bias correction);
+ * lr_dev (may be NULL): device float that overrides lr (ReduceLROnPlateau, main_ucf101.py:417,456, between graph replays) */
 int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                  int32_t* step_dev, float grad_scale, b2c_stream_t s);
+                  int32_t* step_dev, float grad_scale, const float* lr_dev, b2c_stream_t s);
 
 /* tests: 1 = BatchNorm reductions use one block per statistic group (bit-reproducible activations, slow) */
 int b2c_set_deterministic(int32_t on);

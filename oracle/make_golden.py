@@ -76,7 +76,10 @@ def build_ref_model(ns, sd64, masks=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--big", type=int, default=0, help="only write the N+N-clip full-step goldens (step_NpN.json)")
     args = ap.parse_args()
+    if args.big:
+        return step_big(args.big)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ns = ref_import.import_reference(double=True)
@@ -260,6 +263,88 @@ def main():
             json.dump(step_gold, f)
 
     with open(os.path.join(GOLD, "pinning_report.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps(report, indent=1))
+
+
+def step_big(n_each: int = 4):
+    """Full-step goldens at n_each labeled + n_each unlabeled clips (fp64): the REFERENCE's train_model_interface +
+    backward for UCF --bv (config 2) and --gv (config 3); the 21-class JHMDB step (config 4) through the restatement,
+    because the reference does not ship that model.  -> tests/golden/step_{n}p{n}.json"""
+    torch.set_num_threads(os.cpu_count())
+    ns = ref_import.import_reference(double=True)
+    _stub_main_deps()
+    saved = list(sys.path)
+    sys.path[:] = [ref_import.REF_ROOT] + [p for p in sys.path if "pi-consistency-activity-detection_b200" not in p]
+    for k in [k for k in sys.modules if k.split(".")[0] in ("models", "utils", "datasets")]:
+        del sys.modules[k]
+    ds = types.ModuleType("datasets.ucf_dataloader")
+    ds.UCF101DataLoader = object
+    pk = types.ModuleType("datasets")
+    pk.ucf_dataloader = ds
+    sys.modules["datasets"] = pk
+    sys.modules["datasets.ucf_dataloader"] = ds
+    import importlib
+    main_mod = importlib.import_module("main_ucf101")
+    sys.path[:] = saved
+    torch.randperm = lambda n, **k: torch.arange(n)   # the shuffle is an input, not part of the step
+    n = n_each
+    gold, report = {}, {}
+    sd64 = restate.make_state_dict(24, seed=0, dtype=torch.float64)
+    batch = restate.synthetic_batch(n, n, seed=47, dtype=torch.float64)
+    masks = restate.make_drop_masks(2 * n, seed=3, count=4, dtype=torch.float64)
+    for cfg_name, flags in (("ucf_bv5", dict(bv=True, gv=False)), ("ucf_gv", dict(bv=False, gv=True))):
+        model = build_ref_model(ns, sd64, masks)
+        model.train()
+        main_mod.model = model
+        main_mod.criterion_cls = main_mod.SpreadLoss(num_class=24, m_min=0.2, m_max=0.9)
+        main_mod.criterion_seg_1 = torch.nn.BCEWithLogitsLoss()
+        main_mod.criterion_seg_2 = main_mod.DiceLoss()
+        a = types.SimpleNamespace(thresh_epoch=11, n_frames=5, predict_maps=False, lower_thresh=None, upper_thresh=None,
+                                  bv_wt=0.5, gv_wt=0.5, wt_loc=1.0, wt_cls=1.0, wt_cons=0.1, **flags)
+        part = lambda lo, hi: dict(data=batch["data"][lo:hi], aug_data=batch["fl_data"][lo:hi], action=batch["action"][lo:hi],
+                                   loc_msk=batch["seg"][lo:hi].double(), label_vid=batch["labels"][lo:hi])
+        t0 = time.time()
+        out = main_mod.train_model_interface(a, part(0, n), part(n, 2 * n), 1, ns.ramp_ups.exp_rampup(100)(1))
+        model.zero_grad()
+        out[4].backward()
+        t_ref = time.time() - t0
+        grads_ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+        new_sd = model.state_dict()
+        gold[cfg_name] = dict(source="reference main_ucf101.train_model_interface + backward (fp64)", total=float(out[4]),
+                              loc=float(out[5]), cls=float(out[6]), cons=float(out[7]), act=out[1].tolist(),
+                              logits=summarize(out[0]), mask_pos=int((out[0] > 0).sum()),
+                              grads={k: summarize(v, 16, 7) for k, v in grads_ref.items()},
+                              bn_running={k: summarize(new_sd[k], 8) for k in ("conv1.Conv3d_1a_7x7.bn.running_mean",
+                                                                                "conv1.Conv3d_1a_7x7.bn.running_var",
+                                                                                "conv1.Mixed_4f.b1b.bn.running_var")},
+                              ref_seconds=t_ref)
+        del model, grads_ref, out
+        # the restatement agrees at this size too
+        sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v)
+               for k, v in sd64.items()}
+        res = restate.train_step_losses(sdg, batch["data"], batch["fl_data"], batch["action"], batch["seg"], batch["labels"],
+                                        epoch=1, thresh_epoch=11, n_frames=5, wt_cons=0.1, drop_masks=masks, **flags)
+        report[cfg_name] = {k: abs(float(res[k]) - gold[cfg_name][k]) for k in ("total", "loc", "cls", "cons")}
+        assert max(report[cfg_name].values()) < 1e-7, report
+        del res, sdg
+        print(cfg_name, gold[cfg_name]["total"], report[cfg_name], f"{t_ref:.0f}s", flush=True)
+    # JHMDB-21 (config 4): restatement only
+    sd21 = restate.make_state_dict(21, seed=0, dtype=torch.float64)
+    b21 = restate.synthetic_batch(n, n, seed=47, num_classes=21, dtype=torch.float64)
+    sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd21.items()}
+    res = restate.train_step_losses(sdg, b21["data"], b21["fl_data"], b21["action"], b21["seg"], b21["labels"], epoch=1,
+                                    thresh_epoch=11, n_frames=5, wt_cons=0.1, drop_masks=masks, bv=True, gv=False, num_classes=21)
+    names = [k for k, v in sdg.items() if v.requires_grad]
+    gr = torch.autograd.grad(res["total"], [sdg[k] for k in names], allow_unused=True)
+    gold["jhmdb_bv5"] = dict(source="oracle/restate.py (the reference does not ship models/capsules_jhmdb_semi_sup_pa.py)",
+                             total=float(res["total"]), loc=float(res["loc"]), cls=float(res["cls"]), cons=float(res["cons"]),
+                             act=res["pred_action"].tolist(), logits=summarize(res["output"]),
+                             mask_pos=int((res["output"] > 0).sum()),
+                             grads={k: summarize(g_, 16, 7) for k, g_ in zip(names, gr)})
+    with open(os.path.join(GOLD, f"step_{n}p{n}.json"), "w") as f:
+        json.dump(gold, f)
+    with open(os.path.join(GOLD, f"pinning_report_{n}p{n}.json"), "w") as f:
         json.dump(report, f, indent=1)
     print(json.dumps(report, indent=1))
 

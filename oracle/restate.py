@@ -310,8 +310,10 @@ def capsules(sd, x: Tensor):
 
 
 def decode(sd, rout: Tensor, cross28: Tensor, cross56: Tensor, cross112: Tensor, classification: Tensor,
-           concat_labels: Tensor, epoch: int, thresh_ep: int, train: bool, drop_mask2: Optional[Tensor]):
-    """Segment 3 (:438-512): class activations, pose masking, localisation decoder."""
+           concat_labels: Tensor, epoch: int, thresh_ep: int, train: bool, drop_mask2: Optional[Tensor],
+           taps: Optional[dict] = None):
+    """Segment 3 (:438-512): class activations, pose masking, localisation decoder.
+    taps: optional dict that receives the intermediate activations (diagnostics: per-layer gradient bisection)."""
     B_ = rout.shape[0]
     C = rout.shape[-1] // 17
     poses = rout[..., :C * 16].reshape(B_, 20, 20, C, 16)
@@ -333,20 +335,26 @@ def decode(sd, rout: Tensor, cross28: Tensor, cross56: Tensor, cross112: Tensor,
     x = _q(poses.reshape(B_, 20, 20, C * 16).permute(0, 3, 1, 2))
     W = {k: _q(sd[k + ".weight"]) for k in ("upsample1", "conv28", "upsample2", "conv56", "upsample3", "conv112",
                                              "upsample4", "smooth")}
-    x = _q(F.relu(F.conv_transpose2d(x, W["upsample1"], sd["upsample1.bias"])))
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+
+    tap("x0", x)
+    x = tap("u1", _q(F.relu(F.conv_transpose2d(x, W["upsample1"], sd["upsample1.bias"]))))
     x = x.view(-1, 64, 1, 28, 28)
     c28 = _q(F.relu(F.conv2d(cross28, W["conv28"], sd["conv28.bias"], padding=1))).view(-1, 64, 1, 28, 28)
-    x = torch.cat((x, c28), dim=1)
-    x = _q(F.relu(F.conv_transpose3d(x, W["upsample2"], sd["upsample2.bias"], stride=2, padding=1, output_padding=1)))
+    x = tap("cat28", torch.cat((x, c28), dim=1))
+    x = tap("u2", _q(F.relu(F.conv_transpose3d(x, W["upsample2"], sd["upsample2.bias"], stride=2, padding=1, output_padding=1))))
     c56 = _q(F.relu(F.conv3d(cross56, W["conv56"], sd["conv56.bias"], padding=1)))
-    x = torch.cat((x, c56), dim=1)
-    x = _q(F.relu(F.conv_transpose3d(x, W["upsample3"], sd["upsample3.bias"], stride=2, padding=1, output_padding=1)))
+    x = tap("cat56", torch.cat((x, c56), dim=1))
+    x = tap("u3", _q(F.relu(F.conv_transpose3d(x, W["upsample3"], sd["upsample3.bias"], stride=2, padding=1, output_padding=1))))
     c112 = _q(F.relu(F.conv3d(cross112, W["conv112"], sd["conv112.bias"], padding=1)))
-    x = torch.cat((x, c112), dim=1)
+    x = tap("cat112", torch.cat((x, c112), dim=1))
     x = F.conv_transpose3d(x, W["upsample4"], sd["upsample4.bias"], stride=2, padding=1, output_padding=1)
     if drop_mask2 is not None:
         x = x * drop_mask2.to(x.dtype)
-    x = _q(x)
+    x = tap("u4", _q(x))
     x = F.conv_transpose3d(x, W["smooth"], sd["smooth.bias"], padding=1)
     return x.view(-1, 1, 8, 224, 224), class_act, feat
 
@@ -470,8 +478,6 @@ def train_step_losses(sd, data: Tensor, fl_data: Tensor, action: Tensor, seg: Te
                       rampup_epochs: int = 100, bn_states: Optional[list] = None):
     """train_model_interface (main_ucf101.py:50-150).  drop_masks: 4 masks in draw order
     (enc#1, dec#1, enc#2, dec#2) or None.  Returns dict of outputs and scalar losses."""
-    if wt_ramp is None:
-        wt_ramp = exp_rampup(rampup_epochs)(epoch)
     dm1 = None if drop_masks is None else drop_masks[0:2]
     dm2 = None if drop_masks is None else drop_masks[2:4]
     bn1, bn2 = BNState(True), BNState(True)
@@ -480,6 +486,20 @@ def train_step_losses(sd, data: Tensor, fl_data: Tensor, action: Tensor, seg: Te
     flip_op, _, _ = capsnet_forward(sd, fl_data, action, labels, epoch, thresh_epoch, True, dm2, bn2, num_classes)
     if bn_states is not None:
         bn_states += [bn1, bn2]
+    res = step_losses(output, flip_op, pred_action, action, seg, labels, epoch=epoch, bv=bv, gv=gv, n_frames=n_frames,
+                      wt_loc=wt_loc, wt_cls=wt_cls, wt_cons=wt_cons, wt_ramp=wt_ramp, bv_wt=bv_wt, gv_wt=gv_wt,
+                      predict_maps=predict_maps, lower=lower, upper=upper, rampup_epochs=rampup_epochs)
+    res.update(output=output, flip_op=flip_op, pred_action=pred_action, feat=feat)
+    return res
+
+
+def step_losses(output: Tensor, flip_op: Tensor, pred_action: Tensor, action: Tensor, seg: Tensor, labels: Tensor,
+                epoch: int = 1, bv: bool = True, gv: bool = False, n_frames: int = 5, wt_loc: float = 1.0,
+                wt_cls: float = 1.0, wt_cons: float = 0.1, wt_ramp: Optional[float] = None, bv_wt: float = 0.5,
+                gv_wt: float = 0.5, predict_maps: bool = False, lower=None, upper=None, rampup_epochs: int = 100):
+    """The loss half of train_model_interface (main_ucf101.py:88-148) given the two forward passes' outputs."""
+    if wt_ramp is None:
+        wt_ramp = exp_rampup(rampup_epochs)(epoch)
     lab_idx = torch.where(labels.view(-1) == 1)[0]
     lab_op = output[lab_idx]
     lab_seg = seg[lab_idx].to(output.dtype)
@@ -508,8 +528,7 @@ def train_step_losses(sd, data: Tensor, fl_data: Tensor, action: Tensor, seg: Te
         cons = l2
     loc = loc1 + loc2
     total = wt_loc * loc + wt_cls * cls_loss + wt_cons * cons
-    return dict(output=output, flip_op=flip_op, pred_action=pred_action, feat=feat, total=total, loc=loc,
-                bce=loc1, dice=loc2, cls=cls_loss, cons=cons, l2=l2)
+    return dict(total=total, loc=loc, bce=loc1, dice=loc2, cls=cls_loss, cons=cons, l2=l2)
 
 
 def synthetic_batch(n_lab: int, n_unl: int, seed: int = 47, num_classes: int = 24, dtype=torch.float32,

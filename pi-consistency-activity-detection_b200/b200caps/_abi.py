@@ -20,12 +20,13 @@ class ConvClass(C.Structure):
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [("inp", vp), ("out", vp), ("bias", vp), ("scale_nc", vp),
+    _fields_ = [("inp", vp), ("out", vp), ("bias", vp), ("scale_nc", vp), ("stat_sums", vp),
                 ("in_row_stride", i64), ("out_row_stride", i64),
                 ("in_c_off", i32), ("out_c_off", i32), ("Cin", i32), ("Cout", i32),
                 ("N", i32), ("Ti", i32), ("Hi", i32), ("Wi", i32), ("To", i32), ("Ho", i32), ("Wo", i32),
                 ("si_t", i32), ("si_h", i32), ("si_w", i32), ("so_t", i32), ("so_h", i32), ("so_w", i32),
                 ("out_fp32", i32), ("relu", i32), ("sigmoid_from", i32), ("accumulate", i32), ("bn_tile", i32),
+                ("tap_pitch", i32), ("dtype", i32), ("stat_groups", i32), ("round_out", i32),
                 ("nclass", i32), ("cls", ConvClass * 8)]
 
 
@@ -37,7 +38,7 @@ class WgradDesc(C.Structure):
                 ("Qt", i32), ("Qh", i32), ("Qw", i32),
                 ("sg_t", i32), ("sg_h", i32), ("sg_w", i32), ("sp_t", i32), ("sp_h", i32), ("sp_w", i32),
                 ("pp_t", i32), ("pp_h", i32), ("pp_w", i32),
-                ("ntaps", i32), ("bn_tile", i32), ("nsplit", i32), ("atomic", i32)]
+                ("ntaps", i32), ("bn_tile", i32), ("nsplit", i32), ("atomic", i32), ("dtype", i32)]
 
 
 class PackJob(C.Structure):
@@ -80,9 +81,9 @@ _SIGS = {
     "b2c_bv_mask": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_gv_mask": [vp, vp, vp, i32, i32, i32, f32, f32, i32, i32, vp],
     "b2c_cons_reduce": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
-    "b2c_cons_finish": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp],
-    "b2c_cons_grad": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, vp],
-    "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp],
+    "b2c_cons_finish": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp],
+    "b2c_cons_grad": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp],
+    "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp, vp],
     "b2c_fill_f32": [vp, i64, f32, vp],
     "b2c_set_deterministic": [i32],
 }

@@ -356,7 +356,7 @@ class Unit3DFn(torch.autograd.Function):
         sv = unit_fwd(layer, gamma, beta, mod.bn.running_mean, mod.bn.running_var, View(x_cl), View(y), training,
                       STATE.bn_groups if training else 1)
         if training and not STATE.defer_bn_counters:
-            mod.bn.num_batches_tracked += 1
+            mod.bn.num_batches_tracked += STATE.bn_groups      # one per forward pass held in the batch
         ctx.mod, ctx.sv, ctx.x, ctx.y, ctx.gamma = mod, sv, x_cl, y, gamma
         ctx.training = training
         return y
@@ -432,7 +432,7 @@ class InceptionFn(torch.autograd.Function):
         sv["b3b"] = run("b3b", View(pooled), View(out, c0 + c2 + c4, c5))
         if training and not STATE.defer_bn_counters:
             for m in u.values():
-                m.bn.num_batches_tracked += 1
+                m.bn.num_batches_tracked += STATE.bn_groups
         ctx.mod, ctx.sv, ctx.oc = mod, sv, oc
         ctx.x, ctx.out, ctx.mid1, ctx.mid2, ctx.pooled, ctx.idx = x_cl, out, mid1, mid2, pooled, idx
         ctx.training = training

@@ -246,19 +246,22 @@ def cons_reduce(out, flp, w1, w2, wg, acc, P, H, W, mirror, w2_tflip):
               stream())
 
 
-def cons_finish(acc, loss, P, H, W, mode, wt_ramp, bv_wt, gv_wt):
-    _abi.call("b2c_cons_finish", _p(acc), _p(loss), P, H, W, mode, float(wt_ramp), float(bv_wt), float(gv_wt), stream())
+def cons_finish(acc, loss, P, H, W, mode, wt_ramp, bv_wt, gv_wt, dev_scalars=None):
+    """dev_scalars: optional device float[3] (wt_ramp, bv_wt, gv_wt) read by the kernel instead of the host values."""
+    _abi.call("b2c_cons_finish", _p(acc), _p(loss), P, H, W, mode, float(wt_ramp), float(bv_wt), float(gv_wt), _p(dev_scalars),
+              stream())
 
 
-def cons_grad(out, flp, w1, w2, wg, dout, dflp, P, H, W, mirror, w2_tflip, a_l2, a_lv, a_lg):
+def cons_grad(out, flp, w1, w2, wg, dout, dflp, P, H, W, mirror, w2_tflip, a_l2, a_lv, a_lg, dev_scalars=None):
     _abi.call("b2c_cons_grad", _p(out), _p(flp), _p(w1), _p(w2), _p(wg), _p(dout), _p(dflp), P, H, W, int(mirror),
-              int(w2_tflip), float(a_l2), float(a_lv), float(a_lg), stream())
+              int(w2_tflip), float(a_l2), float(a_lv), float(a_lg), _p(dev_scalars), stream())
 
 
-def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
-    """step_dev: int32 device tensor holding the number of steps taken so far (incremented by the call)."""
+def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale=1.0, lr_dev=None):
+    """step_dev: int32 device tensor holding the number of steps taken so far (incremented by the call);
+    lr_dev: optional device float that overrides `lr` (graph replays with a scheduler-controlled learning rate)."""
     _abi.call("b2c_adam_step", _p(p), _p(g), _p(m), _p(v), n, float(lr), float(beta1), float(beta2), float(eps), _p(step_dev),
-              float(grad_scale), stream())
+              float(grad_scale), _p(lr_dev), stream())
 
 
 def fill_f32(t, v):

@@ -14,12 +14,24 @@ Pure host logic (unit-tested on CPU); device work happens only in ``ops``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _abi
+
+
+# Zero-padded channel tail: the packed weights give every tap ceil64(C) K-columns, so layers whose input channel count
+# is not a multiple of 64 (Inception 3x3x3 inputs 16..160, the 480 / 528-channel 1x1 inputs, JHMDB's 336) run on the TMA
+# im2col path -- TMA zero-fills the channels past C -- instead of the cp.async gather path.  B2C_TMA_TAIL=0 disables.
+TMA_TAIL = os.environ.get("B2C_TMA_TAIL", "1") != "0"
+
+
+def tap_pitch(C: int) -> int:
+    """K columns per tap of a packed operand over C stored channels."""
+    return (C + 63) // 64 * 64 if (TMA_TAIL and C % 64) else C
 
 
 def pick_bn_tile(cout: int) -> int:
@@ -207,13 +219,14 @@ class ConvPlan:
         assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.is_cuda
         classes = self.fprop if which == "fprop" else self.dgrad
         pk = self.fprop_pack if which == "fprop" else self.dgrad_pack
+        pitch = pk.get("pitch") or tap_pitch(pk["C"])
         for cl in classes:
             nt = len(cl.taps)
-            bn, ntile, nkb, elems = packed_geometry(pk["R_pad"], nt * pk["C"])
+            bn, ntile, nkb, elems = packed_geometry(pk["R_pad"], nt * pitch)
             if cl.packed is None:
                 cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=weight.device)
             from . import ops
-            ops.pack_part(weight, cl.packed, cl.wtap_dev, pk["R"], nt, pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], pk["C"], 0, 0,
+            ops.pack_part(weight, cl.packed, cl.wtap_dev, pk["R"], nt, pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], pitch, 0, 0,
                           bn, nkb)
 
 
@@ -283,6 +296,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
         d.out_fp32 = 2
     assert bn_tile in (0, pick_bn_tile(pk["R_pad"])), "bn_tile is fixed by the packed weight layout"
     d.relu, d.sigmoid_from, d.accumulate, d.bn_tile = int(relu), int(sigmoid_from), int(accumulate), pick_bn_tile(pk["R_pad"])
+    d.tap_pitch = pk.get("pitch") or tap_pitch(pk["C"])
     d.nclass = len(classes)
     assert 1 <= d.nclass <= 8
     for i, cl in enumerate(classes):

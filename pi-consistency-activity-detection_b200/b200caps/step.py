@@ -108,11 +108,40 @@ class TrainStep:
         self._staging = None
         self._staged = False
         self.packs = ops.PackRegistry()
-        self._split_comm = False     # graph mode on >1 GPU: the NCCL all-reduce runs between two graphs, not inside one
         self.graph = None
         self.graph_opt = None
         self.static = None
         self.launches_per_step = None
+        # Schedule scalars the kernels read from DEVICE memory, so one captured graph serves every epoch / learning rate:
+        # [0] lr  [1] wt_ramp [2] bv_wt [3] gv_wt  [4] a_l2 [5] a_lv [6] a_lg (consistency-gradient weights x wt_cons)
+        # [7] 1.0 once epoch >= thresh_epoch (unlabeled clips are pose-masked with their arg-max class, capsules_ucf101.py:466)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._schedule = None
+        self.set_schedule(epoch=1, lr=args.lr)
+
+    def set_schedule(self, epoch: Optional[float] = None, lr: Optional[float] = None):
+        """Per-epoch host scalars of the reference's loop -- wt_ramp = exp_rampup(N_EPOCHS)(epoch) (main_ucf101.py:181,419),
+        the learning rate after ReduceLROnPlateau (:417,456), the epoch >= thresh_epoch switch -- uploaded to the device
+        vector the kernels read.  Cheap (one 32-byte copy); call it whenever either changes, also between graph replays."""
+        a = self.args
+        ep = self._schedule[0] if (epoch is None and self._schedule) else (1 if epoch is None else epoch)
+        lr = self._schedule[1] if (lr is None and self._schedule) else (a.lr if lr is None else lr)
+        if self._schedule == (ep, lr):
+            return
+        wt_ramp = exp_rampup(a.rampup_epochs, ep)
+        mode = (1 if a.bv else 0) | (2 if a.gv else 0)
+        if mode == 3:
+            a_l2, a_lv, a_lg = a.bv_wt * (1 - wt_ramp), a.bv_wt * wt_ramp, a.gv_wt
+        elif mode == 2:
+            a_l2, a_lv, a_lg = 0.0, 0.0, 1.0
+        elif mode == 1:
+            a_l2, a_lv, a_lg = 1 - wt_ramp, wt_ramp, 0.0
+        else:
+            a_l2, a_lv, a_lg = 1.0, 0.0, 0.0
+        vals = [lr, wt_ramp, a.bv_wt, a.gv_wt, a_l2 * a.wt_cons, a_lv * a.wt_cons, a_lg * a.wt_cons,
+                1.0 if ep >= a.thresh_epoch else 0.0]
+        self.hyper.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=False)
+        self._schedule = (ep, lr)
 
     @staticmethod
     def _label_tensors(labels_host, dev):
@@ -125,20 +154,40 @@ class TrainStep:
         list with 1 = labeled.  Returns dict of device scalars (total, loc, cls, cons) and the step's outputs."""
         engine.require_cuda(data, "data")
         lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, data.device)
-        return self._impl(data, fl_data, action, seg, lab_idx, labels_dev, n_lab, epoch)
+        self.set_schedule(epoch=epoch)
+        return self._impl(data, fl_data, action, seg, lab_idx, labels_dev, n_lab)
 
     def _optimizer(self):
         a, flat = self.args, self.flat
-        ops.adam_step(flat.data, flat.grad, flat.m, flat.v, flat.n, a.lr, 0.9, 0.999, 1e-6, self.step_dev, 1.0 / self.world)
+        ops.adam_step(flat.data, flat.grad, flat.m, flat.v, flat.n, a.lr, 0.9, 0.999, 1e-6, self.step_dev, 1.0 / self.world,
+                      lr_dev=self.hyper[0:1])
+        engine.bump_weights_epoch()
+
+    def _snapshot(self):
+        """Everything a training step mutates: weights, Adam moments + step counter, BatchNorm buffers."""
+        bufs = list(self.model.buffers())
+        return dict(data=self.flat.data.clone(), m=self.flat.m.clone(), v=self.flat.v.clone(), step=self.step_dev.clone(),
+                    bufs=[b.clone() for b in bufs])
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            self.flat.data.copy_(snap["data"])
+            self.flat.m.copy_(snap["m"])
+            self.flat.v.copy_(snap["v"])
+            self.step_dev.copy_(snap["step"])
+            for b, saved in zip(self.model.buffers(), snap["bufs"]):
+                b.copy_(saved)
         engine.bump_weights_epoch()
 
     # ---- CUDA graph ------------------------------------------------------------------------------------
     def capture(self, P: int, labels_host, epoch: int = 1, T: int = 8, H: int = 224, W: int = 224, warmup: int = 3,
                 init_batch=None, ddp_graph: Optional[str] = None):
         """Capture the whole step (both passes, losses, backward, all-reduce, Adam, weight re-packing) into one CUDA
-        graph with static input buffers.  The labeled/unlabeled pattern and the epoch are baked into the graph.
-        NOTE: `warmup` REAL optimisation steps are taken on `init_batch` (data, fl_data, action, seg) before the
-        capture (they size the allocator pools and build the kernel plans)."""
+        graph with static input buffers.  Only the labeled/unlabeled PATTERN is baked into the graph; the epoch-dependent
+        scalars and the learning rate are read from device memory (set_schedule), so one capture serves the whole run.
+        `warmup` uncaptured steps run first (they size the allocator pools, build the kernel plans and register the
+        weight-packing jobs); the model weights, Adam state and BatchNorm buffers are snapshotted before and restored
+        after them, so capture() leaves the training state exactly as it found it."""
         dev = self.flat.data.device
         st = dict(data=torch.rand((P, 3, T, H, W), device=dev), fl_data=torch.rand((P, 3, T, H, W), device=dev),
                   action=torch.zeros((P, 1), device=dev), seg=torch.zeros((P, 1, T, H, W), device=dev))
@@ -146,31 +195,36 @@ class TrainStep:
             for k, v in zip(("data", "fl_data", "action", "seg"), init_batch):
                 st[k].copy_(v)
         lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, dev)
+        self.set_schedule(epoch=epoch)
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):      # plans, packed-weight buffers, kernel attributes, allocator pools, NCCL channels
-                self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+                self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._restore(snap)
+        del snap
         from . import _abi
         l0 = _abi.launch_count()
         g = torch.cuda.CUDAGraph()
         mode = ddp_graph or os.environ.get("B2C_DDP_GRAPH", "split")   # "single" works but hangs NCCL teardown at exit
+        self.graph_opt = None
         if self.world == 1 and mode != "split":
             with torch.cuda.graph(g):
-                out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+                out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab)
         elif mode == "single":
             # data parallel, one graph: the two bucketed NCCL all-reduces are captured on the communication stream
             # (forked from / joined to the capture stream by events), the first one under the encoder backward
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+                out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab)
         else:
             # "split": graph 1 = forward + backward, ONE eager NCCL all-reduce of the flat gradient buffer,
-            # graph 2 = Adam (weight re-packing happens at the start of graph 1 of the next step)
-            self._split_comm = True
+            # graph 2 = Adam (weight re-packing happens at the start of graph 1 of the next step).  The split is a
+            # property of THIS capture only: eager calls made later still all-reduce and step the optimiser.
             with torch.cuda.graph(g):
-                out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, epoch)
+                out = self._impl(st["data"], st["fl_data"], st["action"], st["seg"], lab_idx, labels_dev, n_lab, split=True)
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt):
                 self._optimizer()
@@ -198,10 +252,13 @@ class TrainStep:
             self._staging_ready.record(cs)
         self._staged = True
 
-    def replay(self, data=None, fl_data=None, action=None, seg=None):
+    def replay(self, data=None, fl_data=None, action=None, seg=None, epoch=None, lr=None):
         """Copy the (host or device) inputs into the static buffers on the current stream and launch the graph.
-        Without arguments: use the inputs staged by prefetch(), else whatever the static buffers hold."""
+        Without arguments: use the inputs staged by prefetch(), else whatever the static buffers hold.
+        epoch / lr: new schedule point (see set_schedule) -- no re-capture needed."""
         st = self.static
+        if epoch is not None or lr is not None:
+            self.set_schedule(epoch=epoch, lr=lr)
         if data is None and self._staged:
             cur = torch.cuda.current_stream()
             cur.wait_event(self._staging_ready)
@@ -217,24 +274,28 @@ class TrainStep:
             if self.world > 1:
                 dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.buckets.group)
             self.graph_opt.replay()
+        # the graph updated the fp32 weights through raw pointers (tensor._version did not move): packed operands that
+        # the module path (eval / validation forward) caches are stale now
+        engine.bump_weights_epoch()
         return self.static_out
 
     # ---- the step ------------------------------------------------------------------------------------------
-    def _impl(self, data, fl_data, action, seg, lab_idx, labels_dev, n_lab: int, epoch: int):
+    def _impl(self, data, fl_data, action, seg, lab_idx, labels_dev, n_lab: int, split: bool = False):
         """Hand-scheduled forward + backward: the model topology is fixed, so the step walks it explicitly and calls
         the forward / backward halves of the engine functions directly (no autograd engine, no tape threads) -- which
-        also makes the whole step capturable in one CUDA graph."""
+        also makes the whole step capturable in one CUDA graph.  split=True (graph capture on > 1 GPU only): stop after
+        the backward pass; the caller all-reduces and runs the optimiser."""
         with torch.no_grad():
-            return self._impl_nograd(data, fl_data, action, seg, lab_idx, labels_dev, n_lab, epoch)
+            return self._impl_nograd(data, fl_data, action, seg, lab_idx, labels_dev, n_lab, split)
 
-    def _impl_nograd(self, data, fl_data, action, seg, lab_idx, labels_dev, n_lab: int, epoch: int):
+    def _impl_nograd(self, data, fl_data, action, seg, lab_idx, labels_dev, n_lab: int, split: bool):
         a, model, flat = self.args, self.model, self.flat
+        hyper = self.hyper
         E = engine
         P = data.shape[0]
         H, W = data.shape[-2], data.shape[-1]
         dev = data.device
         C = model.NUM_CLASSES
-        wt_ramp = exp_rampup(a.rampup_epochs, epoch)
         model.train()
         flat.zero_grad()
         if self.arena is None:
@@ -305,10 +366,10 @@ class TrainStep:
             cls2 = torch.cat([action, action]).to(dev)
             lab2 = torch.cat([labels_dev, labels_dev])
             lab = torch.nn.functional.one_hot(cls2.long().view(-1), C).float()
-            if epoch < a.thresh_epoch:
-                unl = torch.ones_like(lab)
-            else:
-                unl = torch.nn.functional.one_hot(torch.argmax(act, dim=1), C).float()
+            # unlabeled clips: all-ones before thresh_epoch, arg-max one-hot afterwards (capsules_ucf101.py:462-470);
+            # the switch is the device scalar hyper[7], so the captured graph does not depend on the epoch
+            pseudo = hyper[7]
+            unl = pseudo * torch.nn.functional.one_hot(torch.argmax(act, dim=1), C).float() + (1.0 - pseudo)
             sel = (lab2.view(-1, 1) == 0).float()
             mask = (sel * unl + (1.0 - sel) * lab).contiguous()
             ctx_h = _Ctx((True, False))
@@ -352,17 +413,9 @@ class TrainStep:
         l_cons = torch.empty(4, dtype=torch.float32, device=dev)
         mode = (1 if a.bv else 0) | (2 if a.gv else 0)
         ops.cons_reduce(out, flp, m_clk, m_anti, m_gv, acc, P, H, W, 1, 1)
-        ops.cons_finish(acc, l_cons, P, H, W, mode, wt_ramp, a.bv_wt, a.gv_wt)
-        if mode == 3:
-            a_l2, a_lv, a_lg = a.bv_wt * (1 - wt_ramp), a.bv_wt * wt_ramp, a.gv_wt
-        elif mode == 2:
-            a_l2, a_lv, a_lg = 0.0, 0.0, 1.0
-        elif mode == 1:
-            a_l2, a_lv, a_lg = 1 - wt_ramp, wt_ramp, 0.0
-        else:
-            a_l2, a_lv, a_lg = 1.0, 0.0, 0.0
-        ops.cons_grad(out, flp, m_clk, m_anti, m_gv, dlogits[:P], dlogits[P:], P, H, W, 1, 1, a_l2 * a.wt_cons,
-                      a_lv * a.wt_cons, a_lg * a.wt_cons)
+        ops.cons_finish(acc, l_cons, P, H, W, mode, 0.0, 0.0, 0.0, dev_scalars=hyper[1:4])
+        ops.cons_grad(out, flp, m_clk, m_anti, m_gv, dlogits[:P], dlogits[P:], P, H, W, 1, 1, 0.0, 0.0, 0.0,
+                      dev_scalars=hyper[4:7])
 
         # ---------------- backward (explicit reverse walk) ----------------
         try:
@@ -373,7 +426,7 @@ class TrainStep:
             dcaps = E.EMRoutingFn.backward(ctx_r, drout)[0]
             dxe = E.PrimaryCapsFn.backward(ctx_pc, dcaps.view(caps5.shape))[0]
             ops.add(View(dxe), View(dxe_dec), View(dxe))                      # two consumers of the encoder output
-            if self.world > 1 and not self._split_comm:
+            if self.world > 1 and not split:
                 # everything after the encoder (84 % of the parameters, incl. the 138 MB PrimaryCaps weight) is final now:
                 # all-reduce it on the side stream underneath the encoder backward
                 self.buckets.allreduce(1)
@@ -393,8 +446,8 @@ class TrainStep:
             E.STATE.defer_bn_counters = False
             ops.PACKS = None
         if self.bn_counters:
-            torch._foreach_add_(self.bn_counters, 1)      # every BatchNorm saw one training forward
-        if not self._split_comm:
+            torch._foreach_add_(self.bn_counters, 2)      # every BatchNorm saw two training forwards (main_ucf101.py:85-86)
+        if not split:
             if self.world > 1:
                 self.buckets.allreduce(0)
                 self.buckets.join()

@@ -236,6 +236,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   // weight traffic from L2 per output tile (in-kernel timing r01: the short-N layers wait on operand delivery).
   const int acc_cols = (d.bn_tile + 15) & ~15;                     // TMEM columns per accumulator
   const int b_tile_bytes = ((acc_cols * 128) + 1023) & ~1023;      // packed weight tile (layer-wide bn_tile)
+  // K elements per tap in the packed weights.  TMA path: a multiple of 64 >= Cin -- the im2col box of the last channel
+  // block reaches past Cin, where TMA zero-fills and the packed weights hold zeros.
+  const int k_pitch = d.tap_pitch > 0 ? d.tap_pitch : d.Cin;
   const int a_bytes = MT * kATileBytes;
   const int stage_bytes = a_bytes + b_tile_bytes;
 
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     if (tid == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int cblocks = d.Cin / kBlockK;
+      const int cblocks = k_pitch / kBlockK;
       B2C_PROF_DECL(p_wait); B2C_PROF_DECL(p_t0); B2C_PROF_START(p_t0);
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24], MT);
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       int bn = d.Cout - n0;
       if (bn > d.bn_tile) bn = d.bn_tile;
       const int bn16 = (bn + 15) & ~15;
-      const int nkb = (cc.ntaps * d.Cin + kBlockK - 1) / kBlockK;
+      const int nkb = (cc.ntaps * k_pitch + kBlockK - 1) / kBlockK;
       const uint32_t idesc = umma_idesc_bf16(bn16, 0, 0);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MT * acc_cols);
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
@@ -1228,7 +1231,10 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
     sum_taps += c.ntaps;
   }
   if (tiles128 == 0) return 0;
-  const int use_tma = (d.Cin % kBlockK == 0) ? 1 : 0;
+  const int k_pitch = d.tap_pitch > 0 ? d.tap_pitch : d.Cin;
+  B2C_REQUIRE(k_pitch >= d.Cin && (k_pitch == d.Cin || (k_pitch % kBlockK == 0 && k_pitch - d.Cin < kBlockK)),
+              "conv_fprop: tap_pitch=%d must be Cin=%d or Cin rounded up to a multiple of 64", d.tap_pitch, d.Cin);
+  const int use_tma = (k_pitch % kBlockK == 0) ? 1 : 0;
   const int acc_cols = (d.bn_tile + 15) & ~15;
   const int b_tile_bytes_h = ((acc_cols * 128) + 1023) & ~1023;
   const int staging = kStagingBytes + 16;

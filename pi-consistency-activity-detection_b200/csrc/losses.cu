@@ -319,7 +319,12 @@ __global__ void __launch_bounds__(kBlock) cons_reduce_kernel(const float* __rest
   block_accumulate<4>(part, acc);
 }
 __global__ void cons_finish_kernel(const double* acc, float* loss, int P, long long THW, int mode, float wt_ramp, float bv_wt,
-                                   float gv_wt) {
+                                   float gv_wt, const float* __restrict__ dev) {
+  if (dev) {   // device-resident schedule scalars: one captured graph serves every epoch
+    wt_ramp = dev[0];
+    bv_wt = dev[1];
+    gv_wt = dev[2];
+  }
   const double cnt = (double)P * (double)THW;
   const double l2 = acc[0] / cnt;
   const double lv = (acc[1] + acc[2]) / cnt;
@@ -340,7 +345,12 @@ __global__ void __launch_bounds__(kBlock) cons_grad_kernel(const float* __restri
                                                            const float* __restrict__ w1, const float* __restrict__ w2,
                                                            const float* __restrict__ wg, float* __restrict__ dout,
                                                            float* __restrict__ dflp, int P, int H, int W, int mirror, int w2_tflip,
-                                                           float a_l2, float a_lv, float a_lg) {
+                                                           float a_l2, float a_lv, float a_lg, const float* __restrict__ dev) {
+  if (dev) {
+    a_l2 = dev[0];
+    a_lv = dev[1];
+    a_lg = dev[2];
+  }
   const long long HW = (long long)H * W, THW = kT * HW;
   const float k1 = 2.f / (float)((double)P * (double)THW);
   const float k2 = 2.f / (float)((double)THW * (double)P * (double)P);
@@ -458,9 +468,9 @@ B2C_API int b2c_cons_reduce(const float* out, const float* flp, const float* w1,
 }
 
 B2C_API int b2c_cons_finish(const double* acc, float* loss, int32_t P, int32_t H, int32_t W, int32_t mode, float wt_ramp, float bv_wt,
-                            float gv_wt, b2c_stream_t s) {
+                            float gv_wt, const float* dev_scalars, b2c_stream_t s) {
   B2C_REQUIRE(acc && loss, "cons_finish: null pointer");
-  cons_finish_kernel<<<1, 1, 0, (cudaStream_t)s>>>(acc, loss, P, (long long)kT * H * W, mode, wt_ramp, bv_wt, gv_wt);
+  cons_finish_kernel<<<1, 1, 0, (cudaStream_t)s>>>(acc, loss, P, (long long)kT * H * W, mode, wt_ramp, bv_wt, gv_wt, dev_scalars);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("cons_finish");
   return 0;
@@ -468,10 +478,10 @@ B2C_API int b2c_cons_finish(const double* acc, float* loss, int32_t P, int32_t H
 
 B2C_API int b2c_cons_grad(const float* out, const float* flp, const float* w1, const float* w2, const float* wg, float* dout,
                           float* dflp, int32_t P, int32_t H, int32_t W, int32_t mirror, int32_t w2_tflip, float a_l2, float a_lv,
-                          float a_lg, b2c_stream_t s) {
+                          float a_lg, const float* dev_scalars, b2c_stream_t s) {
   B2C_REQUIRE(out && flp && (dout || dflp) && P > 0, "cons_grad: bad args");
   cons_grad_kernel<<<blocks_for((long long)kT * H * W), kBlock, 0, (cudaStream_t)s>>>(out, flp, w1, w2, wg, dout, dflp, P, H, W,
-                                                                                     mirror, w2_tflip, a_l2, a_lv, a_lg);
+                                                                                     mirror, w2_tflip, a_l2, a_lv, a_lg, dev_scalars);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("cons_grad");
   return 0;
@@ -484,7 +494,8 @@ namespace {
 __global__ void adam_tick_kernel(int* step) { step[0] += 1; }
 __global__ void __launch_bounds__(kBlock) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                       float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                                      const int* __restrict__ step_ptr, float gscale) {
+                                                      const int* __restrict__ step_ptr, float gscale, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = lr_dev[0];   // device-resident learning rate (ReduceLROnPlateau changes it between graph replays)
   const int step = step_ptr[0];
   const float bc1 = 1.f - powf(b1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
@@ -518,12 +529,12 @@ __global__ void __launch_bounds__(kBlock) adam_kernel(float* __restrict__ p, con
 }  // namespace
 
 B2C_API int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                          int32_t* step_dev, float grad_scale, b2c_stream_t s) {
+                          int32_t* step_dev, float grad_scale, const float* lr_dev, b2c_stream_t s) {
   B2C_REQUIRE(p && g && m && v && step_dev && n > 0, "adam_step: bad args");
   B2C_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0,
               "adam_step: buffers must be 16B aligned");
   adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
-  adam_kernel<<<blocks_for(n, 4), kBlock, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale);
+  adam_kernel<<<blocks_for(n, 4), kBlock, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale, lr_dev);
   b2c_launches_add(2);
   B2C_LAUNCH_CHECK("adam_step");
   return 0;

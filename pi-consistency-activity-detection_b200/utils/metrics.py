@@ -1,26 +1,22 @@
-"""The two functions of the reference's utils/metrics.py that the training / validation loops call
-(get_accuracy :7-13, IOU2 :171-193).  The plotting helpers (matplotlib) are outside the hot path."""
+"""``get_accuracy`` and ``IOU2`` -- the two names of the reference's utils/metrics.py that its train / validate loops
+import (main_ucf101.py:27,190,261).  Host-side bookkeeping outside the hot path; the reference's matplotlib plotting
+helpers are not provided."""
 import numpy as np
 import torch
 
 
 def get_accuracy(predicted_actor, actor):
-    maxm, prediction = torch.max(predicted_actor, 1)
-    prediction = prediction.view(-1, 1)
-    actor = actor.view(-1, 1).to(prediction.device)
-    correct = torch.sum(actor == prediction.float()).item()
-    return correct / float(prediction.shape[0])
+    """Fraction of rows whose arg-max class equals the label.  predicted_actor (B, C), actor (B, 1) or (B,)."""
+    pred = predicted_actor.detach().argmax(dim=1).reshape(-1)
+    truth = actor.detach().reshape(-1).to(device=pred.device, dtype=pred.dtype)
+    return float((pred == truth).sum().item()) / float(pred.numel())
 
 
 def IOU2(gt, img):
-    """IoU of two binary numpy masks; NaN when the ground truth is empty."""
-    intersection = gt + img
-    intersection[intersection < 2] = 0
-    intersection[intersection > 0] = 1
-    intersection_sum = intersection.sum()
-    union = gt + img
-    union[union > 1] = 1
-    union_sum = union.sum()
-    if gt.sum() > 0:
-        return intersection_sum / union_sum
-    return float('NaN')
+    """Intersection over union of two {0,1} masks (numpy arrays or tensors); NaN when the ground truth is empty,
+    which is what the validation loop tests for (main_ucf101.py:262)."""
+    g = np.asarray(gt.detach().cpu() if torch.is_tensor(gt) else gt) > 0
+    p = np.asarray(img.detach().cpu() if torch.is_tensor(img) else img) > 0
+    if not g.any():
+        return float("nan")
+    return float(np.logical_and(g, p).sum()) / float(np.logical_or(g, p).sum())

@@ -36,6 +36,12 @@ CASES = [
     ("3x3x3 64->64 (8,112,112) N=2", False, 64, 64, (3, 3, 3), (1, 1, 1), (8, 112, 112), "same", 2),
     ("convT3d s2 128->64 (4,64,64) N=2", True, 128, 64, (3, 3, 3), (2, 2, 2), (4, 64, 64), 1, 2),
     ("convT2d 9x9 336->64 (JHMDB upsample1)", True, 336, 64, (1, 9, 9), (1, 1, 1), (1, 20, 20), 0, 1),
+    # channel counts that are not multiples of 64: TMA path with a zero-filled channel tail (plans.TMA_TAIL)
+    ("1x1 480->192 (Mixed_4b.b0)", False, 480, 192, (1, 1, 1), (1, 1, 1), (1, 28, 28), "same", 4),
+    ("3x3x3 160->320 (Mixed_4f.b1b)", False, 160, 320, (3, 3, 3), (1, 1, 1), (1, 28, 28), "same", 4),
+    ("3x3x3 144->288 (Mixed_4e.b1b)", False, 144, 288, (3, 3, 3), (1, 1, 1), (1, 28, 28), "same", 2),
+    ("3x3x3 32->96 (Mixed_3c.b2b)", False, 32, 96, (3, 3, 3), (1, 1, 1), (2, 28, 28), "same", 2),
+    ("1x1 512->24 (Mixed_4c.b2a)", False, 512, 24, (1, 1, 1), (1, 1, 1), (1, 28, 28), "same", 4),
 ]
 
 

@@ -1,0 +1,235 @@
+"""-m gpu: the FUSED training step (b200caps.step.TrainStep -- what bench.py measures) against numbers produced by
+the REFERENCE's own train_model_interface + loss.backward() (tests/golden/step_1p1.json, step_4p4.json; written by
+oracle/make_golden.py from /root/reference in fp64 on identical name-keyed weights, clips and Dropout3d masks).
+
+Yardstick.  At random init this network amplifies ANY perturbation (BatchNorm + ReLU at initialisation grow a
+perturbation ~1.2x per layer; the EM routing sharpens it): the reference's own mathematics moves by the amounts in
+profiles/r02_conditioning.json when its GEMM operands / stored activations are rounded to bf16 (oracle vs oracle,
+tools/conditioning_probe.py) -- logits 0.54-0.59 (max-abs, normalised) at 1+1, 2+2 AND 4+4 clips, i.e. independent
+of the BatchNorm batch -- while batch-averaged quantities (the losses) converge with the number of clips.  Each
+assertion below is therefore `max(north_star bf16 bar 2e-2, 3 x the oracle's own bf16 deviation)` and prints both."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+COND = os.path.join(os.path.dirname(HERE), "profiles", "r02_conditioning.json")
+BAR = 2e-2          # north_star: bf16 mode, relative
+
+
+def load(name):
+    with open(os.path.join(GOLD, name)) as f:
+        return json.load(f)
+
+
+def oracle_bf16_dev(clips: int):
+    with open(COND) as f:
+        return json.load(f)[f"{clips}+{clips}"]
+
+
+def sampled_dev(t: torch.Tensor, gold: dict) -> float:
+    f = t.detach().double().cpu().reshape(-1)
+    vals = f[torch.tensor(gold["idx"])]
+    return float((vals - torch.tensor(gold["vals"], dtype=torch.float64)).abs().max()) / (gold["maxabs"] + 1e-300)
+
+
+def run_fused_step(n_each: int, num_classes: int, bv: bool, gv: bool):
+    from b200caps import engine
+    from b200caps.step import StepArgs, TrainStep
+    from oracle import restate
+    if num_classes == 24:
+        from models.capsules_ucf101 import CapsNet
+    else:
+        from models.capsules_jhmdb_semi_sup_pa import CapsNet
+    sd = restate.make_state_dict(num_classes, seed=0)
+    model = CapsNet(pt_path=None)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    b = restate.synthetic_batch(n_each, n_each, seed=47, num_classes=num_classes)
+    P = 2 * n_each
+    masks = restate.make_drop_masks(P, seed=3, count=4)          # draw order: enc#1, dec#1, enc#2, dec#2
+    cat832 = torch.cat([masks[0], masks[2]]).reshape(2 * P, 832)
+    cat128 = torch.cat([masks[1], masks[3]]).reshape(2 * P, 128)
+    step = TrainStep(model, StepArgs(bv=bv, gv=gv, n_frames=5, wt_cons=0.1, lr=0.0))      # lr 0: gradients stay inspectable
+    engine.STATE.dropout_source = lambda n, c, dev: (cat832 if c == 832 else cat128)
+    try:
+        res = step(b["data"].cuda(), b["fl_data"].cuda(), b["action"].cuda(), b["seg"].cuda(), b["labels"], epoch=1)
+    finally:
+        engine.STATE.dropout_source = None
+    torch.cuda.synchronize()
+    return model, step, res
+
+
+def check_against_golden(res, model, g, od, tag):
+    """res: TrainStep outputs; g: the reference's golden entry; od: the oracle's own bf16 deviation at this size."""
+    report = {}
+    for k in ("total", "loc", "cls", "cons"):
+        dev = abs(float(res[k]) - g[k]) / abs(g[k])
+        bound = max(BAR, 3 * od["losses_rel_dev"][k])
+        report[k] = (dev, od["losses_rel_dev"][k], bound)
+    act_ref = torch.tensor(g["act"], dtype=torch.float64)
+    act_dev = float((res["pred_action"].double().cpu() - act_ref).abs().max() / act_ref.abs().max())
+    report["act"] = (act_dev, od["act_dev"], max(BAR, 3 * od["act_dev"]))
+    print(f"[{tag}] ours-vs-reference | reference's own bf16 deviation | bound")
+    for k, (d, o, bnd) in report.items():
+        print(f"   {k:6s} {d:.2e} | {o:.2e} | {bnd:.2e}")
+    for k, (d, o, bnd) in report.items():
+        assert d < bnd, (tag, k, d, bnd)
+    # logits: chaotic element-wise at random init (reference's own bf16 deviation 0.5-0.6); reported, bounded loosely, and
+    # the count of positive pixels (the thresholded mask's area) must agree far better than the pixels themselves
+    ldev = sampled_dev(res["output"], g["logits"])
+    pos = int((res["output"] > 0).sum())
+    print(f"   logits (64 samples) {ldev:.2e} | {od['logits_dev']:.2e};  thresholded-mask area {pos} vs reference {g.get('mask_pos')}")
+    assert ldev < 3 * od["logits_dev"] and torch.isfinite(res["output"]).all()
+    if g.get("mask_pos"):
+        assert abs(pos - g["mask_pos"]) / g["mask_pos"] < 0.25
+    # gradients, per parameter tensor (16 sampled entries each, max-abs normalised): medians per group against the
+    # reference's own bf16 deviation
+    grads = dict(model.named_parameters())
+    devs = {k: sampled_dev(grads[k].grad, gs) for k, gs in g["grads"].items()}
+    groups = {"encoder": [v for k, v in devs.items() if k.startswith("conv1.")],
+              "primary_caps": [v for k, v in devs.items() if k.startswith("primary_caps.")],
+              "conv_caps": [v for k, v in devs.items() if k.startswith("conv_caps.")],
+              "decoder": [v for k, v in devs.items() if not k.startswith(("conv1.", "primary_caps.", "conv_caps."))]}
+    for name, v in groups.items():
+        med = sorted(v)[len(v) // 2]
+        o = od["grad_dev"][name]
+        print(f"   grads {name:12s} median {med:.2e} max {max(v):.2e} | reference's own: median {o['median']:.2e} max {o['max']:.2e}")
+        assert all(x == x for x in v), name
+        assert med < max(BAR, 3 * o["median"]), (tag, name, med, o)
+
+
+@pytest.mark.parametrize("cfg", ["bv5", "gv", "bv_gv"])
+def test_fused_step_vs_reference_1p1(cfg):
+    """1 labeled + 1 unlabeled clip: the reference's losses / activations / all parameter gradients."""
+    g = load("step_1p1.json")[cfg]
+    model, step, res = run_fused_step(1, 24, bv=cfg in ("bv5", "bv_gv"), gv=cfg in ("gv", "bv_gv"))
+    od = oracle_bf16_dev(1)
+    check_against_golden(res, model, g, od, f"1+1 {cfg}")
+
+
+@pytest.mark.parametrize("cfg", ["ucf_bv5", "ucf_gv", "jhmdb_bv5"])
+def test_fused_step_vs_reference_4p4(cfg):
+    """4 labeled + 4 unlabeled clips -- BASELINE configs 2 (--bv), 3 (--gv) and 4 (JHMDB-21) at half the batch (the
+    largest size whose fp64 reference step fits the build container's memory).  At this size the batch-averaged losses
+    of the reference itself move by < 3e-3 under bf16 rounding, so they are held to the north_star bar of 2e-2."""
+    g = load("step_4p4.json")[cfg]
+    model, step, res = run_fused_step(4, 21 if cfg.startswith("jhmdb") else 24, bv=cfg.endswith("bv5"), gv=cfg.endswith("gv"))
+    od = oracle_bf16_dev(4)
+    check_against_golden(res, model, g, od, f"4+4 {cfg}")
+    for k in ("total", "loc", "cons"):
+        assert abs(float(res[k]) - g[k]) / abs(g[k]) < BAR, (cfg, k)
+    # the BatchNorm running statistics after the step (two forward passes => two momentum updates per layer)
+    if "bn_running" in g:
+        sd = model.state_dict()
+        for k, gs in g["bn_running"].items():
+            assert sampled_dev(sd[k], gs) < BAR, k
+        assert int(sd["conv1.Conv3d_1a_7x7.bn.num_batches_tracked"]) == 2
+
+
+def _small_step(lr=1e-3):
+    from b200caps.step import StepArgs, TrainStep
+    from models.capsules_ucf101 import CapsNet
+    from oracle import restate
+    torch.manual_seed(0)
+    sd = restate.make_state_dict(24, seed=0)
+    model = CapsNet(pt_path=None)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    b = restate.synthetic_batch(1, 1, seed=47)
+    step = TrainStep(model, StepArgs(bv=True, n_frames=5, wt_cons=0.1, lr=lr))
+    dev_b = [b[k].cuda() for k in ("data", "fl_data", "action", "seg")]
+    return model, step, b, dev_b
+
+
+def test_capture_leaves_training_state_untouched_and_eager_still_trains():
+    """capture()'s warm-up steps must not move weights / Adam state / BatchNorm buffers; an eager call made
+    after a capture must still run the optimiser; a replay must invalidate the packed-operand caches of the module path."""
+    model, step, b, dev_b = _small_step()
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    m0, v0, s0 = step.flat.m.clone(), step.flat.v.clone(), int(step.step_dev)
+    step.capture(2, b["labels"], epoch=1, init_batch=dev_b)
+    torch.cuda.synchronize()
+    after = model.state_dict()
+    for k in before:
+        assert torch.equal(before[k], after[k]), f"capture() changed {k}"
+    assert torch.equal(m0, step.flat.m) and torch.equal(v0, step.flat.v) and int(step.step_dev) == s0
+    # replay trains
+    w = model.upsample4.weight.detach().clone()
+    step.replay(*dev_b)
+    step.replay()
+    torch.cuda.synchronize()
+    assert int(step.step_dev) == s0 + 2 and not torch.equal(w, model.upsample4.weight.detach())
+    assert int(model.conv1.Conv3d_2b_1x1.bn.num_batches_tracked) == 4
+    # the module path after replays must see the NEW weights (packed bf16 operands are derived caches)
+    from b200caps import engine
+    model.eval()
+    with torch.no_grad():
+        o1, a1, _ = model(dev_b[0], dev_b[2], b["labels"].cuda(), 0, 0)
+        engine.bump_weights_epoch()                          # force a full re-pack
+        o2, a2, _ = model(dev_b[0], dev_b[2], b["labels"].cuda(), 0, 0)
+    assert torch.equal(o1, o2) and torch.equal(a1, a2), "eval forward after replay used stale packed weights"
+    # eager call after a capture: still all-reduces (world 1: no-op) and steps the optimiser
+    model.train()
+    w = model.upsample4.weight.detach().clone()
+    s1 = int(step.step_dev)
+    step(*dev_b, b["labels"], epoch=1)
+    torch.cuda.synchronize()
+    assert int(step.step_dev) == s1 + 1 and not torch.equal(w, model.upsample4.weight.detach())
+
+
+def test_one_graph_serves_every_epoch_and_learning_rate():
+    """The per-epoch scalars (wt_ramp, thresh_epoch switch) and the learning rate are device-resident: replay(epoch=..,
+    lr=..) must reproduce the eager step at that schedule point without re-capturing."""
+    from b200caps import engine, ops
+    model, step, b, dev_b = _small_step(lr=0.0)
+    ops.set_deterministic(True)
+    # fixed Dropout3d masks (graph replays advance torch's philox offset, so random draws would differ from eager ones)
+    g = torch.Generator().manual_seed(5)
+    m832 = ((torch.rand((4, 832), generator=g) < 0.5).float() * 2).cuda()
+    m128 = ((torch.rand((4, 128), generator=g) < 0.5).float() * 2).cuda()
+    engine.STATE.dropout_source = lambda n, c, dev: (m832 if c == 832 else m128)
+    try:
+        step.capture(2, b["labels"], epoch=1, init_batch=dev_b)
+        outs = {}
+        for ep in (1, 60, 150):
+            r = step.replay(*dev_b, epoch=ep)
+            outs[ep] = {k: float(r[k]) for k in ("total", "cons", "loc")}
+            e = step(*dev_b, b["labels"], epoch=ep)
+            for k in ("total", "cons", "loc"):
+                assert abs(outs[ep][k] - float(e[k])) <= 1e-5 * abs(float(e[k])), (ep, k, outs[ep][k], float(e[k]))
+        assert outs[1]["cons"] != outs[60]["cons"], "wt_ramp did not reach the captured graph"
+        # learning rate: 0 keeps the weights, > 0 moves them -- through the same graph
+        w = model.smooth.weight.detach().clone()
+        step.replay(*dev_b, lr=0.0)
+        torch.cuda.synchronize()
+        assert torch.equal(w, model.smooth.weight.detach())
+        step.replay(*dev_b, lr=1e-3)
+        torch.cuda.synchronize()
+        assert not torch.equal(w, model.smooth.weight.detach())
+    finally:
+        ops.set_deterministic(False)
+        engine.STATE.dropout_source = None
+
+
+def test_launcher_runs_a_reference_style_script_on_the_kernels(tmp_path):
+    """`python -m b200caps.launch <script>` end to end on the GPU: synthetic loaders -> CapsNet().cuda() -> the two
+    forward passes -> kernel-backed losses / masks -> autograd backward -> torch Adam -> eval forward + IOU2, with the
+    torch-1.7 idioms of the reference scripts.  (The reference's own main_ucf101.py is import-checked under the launcher
+    in the build container, tests/test_dropin_boundary.py; its checkout does not exist on the GPU box.)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    pkg = os.path.join(root, "pi-consistency-activity-detection_b200")
+    env = dict(os.environ, PYTHONPATH=pkg, B200CAPS_SYNTH_LEN="2,2,2")
+    for gv in ([], ["--gv"]):
+        r = subprocess.run([sys.executable, "-m", "b200caps.launch", os.path.join(HERE, "dropin_driver.py"), "--bs", "2"] + gv,
+                           cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("EPOCH DONE")][-1]
+        assert "steps 2" in line and "dummy 1000" in line, line
+        print(line)

@@ -39,61 +39,65 @@ def test_fused_step_equals_dropin_composition(mode):
     # therefore made in the library's deterministic mode, where both schedules must agree to accumulation noise.
     from b200caps import ops
     ops.set_deterministic(True)
-
-    # ---- drop-in composition (reference's train_model_interface with our modules + torch autograd).  Both passes go
-    # through the modules as ONE 2P batch with per-pass BatchNorm groups, exactly like the fused step, so the two sides
-    # launch the same kernels on the same shapes and differ only by the order of fp32 atomics.
-    cat832 = torch.cat([masks[0], masks[2]]).reshape(2 * 2, 832)
-    cat128 = torch.cat([masks[1], masks[3]]).reshape(2 * 2, 128)
-    engine.STATE.dropout_source = lambda n, c, dev: (cat832 if c == 832 else cat128)
-    engine.STATE.bn_groups = 2
     try:
-        both, act2, _ = m1(torch.cat([data, fl]), torch.cat([action, action]), torch.cat([labels, labels]), 1, 11)
+
+        # ---- drop-in composition (reference's train_model_interface with our modules + torch autograd).  Both passes go
+        # through the modules as ONE 2P batch with per-pass BatchNorm groups, exactly like the fused step, so the two sides
+        # launch the same kernels on the same shapes and differ only by the order of fp32 atomics.
+        cat832 = torch.cat([masks[0], masks[2]]).reshape(2 * 2, 832)
+        cat128 = torch.cat([masks[1], masks[3]]).reshape(2 * 2, 128)
+        engine.STATE.dropout_source = lambda n, c, dev: (cat832 if c == 832 else cat128)
+        engine.STATE.bn_groups = 2
+        try:
+            both, act2, _ = m1(torch.cat([data, fl]), torch.cat([action, action]), torch.cat([labels, labels]), 1, 11)
+        finally:
+            engine.STATE.dropout_source = None
+            engine.STATE.bn_groups = 1
+        out, flip_op, act = both[:2], both[2:], act2[:2]
+        lab_idx = torch.where(labels == 1)[0]
+        loc = BCEWithLogitsLoss()(out[lab_idx], seg[lab_idx]) + DiceLoss()(out[lab_idx], seg[lab_idx])
+        cls, _ = SpreadLoss(num_class=24, m_min=0.2, m_max=0.9)(act[lab_idx], action[lab_idx])
+        flipped = torch.flip(flip_op, [4])
+        l2 = weighted_mse_loss(flipped, out, torch.ones_like(out))
+        wt_ramp = exp_rampup(100)(1)
+        if bv:
+            v1 = measure_pixelwise_var_v2(out, torch.flip(flipped, [2]), frames_cnt=5)
+            v2 = measure_pixelwise_var_v2(torch.flip(out, [2]), flipped, frames_cnt=5)
+            cons = wt_ramp * (weighted_mse_loss(flipped, out, v1) + weighted_mse_loss(flipped, out, torch.flip(v2, [2]))) + \
+                (1 - wt_ramp) * l2
+        else:
+            cons = weighted_mse_loss(flipped, out, measure_pixelwise_gradient(out))
+        total = loc + cls + 0.1 * cons
+        total.backward()
+        ref_grads = {k: p.grad.clone() for k, p in m1.named_parameters()}
+
+        # ---- fused step (lr = 0 keeps the weights; gradients stay in the flat buffer) ----
+        step = TrainStep(m2, StepArgs(bv=bv, gv=gv, n_frames=5, wt_cons=0.1, lr=0.0))
+        engine.STATE.dropout_source = lambda n, c, dev: (cat832 if c == 832 else cat128)
+        try:
+            res = step(data, fl, action, seg, labels.cpu(), epoch=1)
+        finally:
+            engine.STATE.dropout_source = None
+        e = dict(total=abs(float(res["total"]) - float(total)) / abs(float(total)),
+                 loc=abs(float(res["loc"]) - float(loc)) / abs(float(loc)),
+                 cls=abs(float(res["cls"]) - float(cls)) / (abs(float(cls)) + 1e-9),
+                 cons=abs(float(res["cons"]) - float(cons)) / abs(float(cons)))
+        print("losses fused vs drop-in:", e, "values", float(total), float(loc), float(cls), float(cons))
+        e_out, e_flp = rel(res["output"], out), rel(res["flip_op"], flip_op)
+        errs = {k: rel(p.grad, ref_grads[k]) for k, p in m2.named_parameters()}
+        worst = max(errs, key=errs.get)
+        med = sorted(errs.values())[len(errs) // 2]
+        dec = {k: v for k, v in errs.items() if not k.startswith(("conv1.", "primary_caps.", "conv_caps."))}
+        l2o = float((res["output"].double() - out.double()).norm() / out.double().norm())
+        print(f"logits fused vs drop-in: max-norm {e_out:.2e} / {e_flp:.2e}, relative L2 {l2o:.2e}; grads: worst {worst} "
+              f"{errs[worst]:.2e}, median {med:.2e}, decoder worst {max(dec.values()):.2e}")
+        # Both sides are OUR kernels; they differ only in batching (one 2P batch with per-pass BN groups vs two passes) and
+        # in the order of fp32 atomics -- differences of 1e-7 that the routing amplifies, hence the
+        # percent-level tolerances on quantities downstream of the routing.
     finally:
+        ops.set_deterministic(False)
         engine.STATE.dropout_source = None
         engine.STATE.bn_groups = 1
-    out, flip_op, act = both[:2], both[2:], act2[:2]
-    lab_idx = torch.where(labels == 1)[0]
-    loc = BCEWithLogitsLoss()(out[lab_idx], seg[lab_idx]) + DiceLoss()(out[lab_idx], seg[lab_idx])
-    cls, _ = SpreadLoss(num_class=24, m_min=0.2, m_max=0.9)(act[lab_idx], action[lab_idx])
-    flipped = torch.flip(flip_op, [4])
-    l2 = weighted_mse_loss(flipped, out, torch.ones_like(out))
-    wt_ramp = exp_rampup(100)(1)
-    if bv:
-        v1 = measure_pixelwise_var_v2(out, torch.flip(flipped, [2]), frames_cnt=5)
-        v2 = measure_pixelwise_var_v2(torch.flip(out, [2]), flipped, frames_cnt=5)
-        cons = wt_ramp * (weighted_mse_loss(flipped, out, v1) + weighted_mse_loss(flipped, out, torch.flip(v2, [2]))) + \
-            (1 - wt_ramp) * l2
-    else:
-        cons = weighted_mse_loss(flipped, out, measure_pixelwise_gradient(out))
-    total = loc + cls + 0.1 * cons
-    total.backward()
-    ref_grads = {k: p.grad.clone() for k, p in m1.named_parameters()}
-
-    # ---- fused step (lr = 0 keeps the weights; gradients stay in the flat buffer) ----
-    step = TrainStep(m2, StepArgs(bv=bv, gv=gv, n_frames=5, wt_cons=0.1, lr=0.0))
-    engine.STATE.dropout_source = lambda n, c, dev: (cat832 if c == 832 else cat128)
-    try:
-        res = step(data, fl, action, seg, labels.cpu(), epoch=1)
-    finally:
-        engine.STATE.dropout_source = None
-    e = dict(total=abs(float(res["total"]) - float(total)) / abs(float(total)),
-             loc=abs(float(res["loc"]) - float(loc)) / abs(float(loc)),
-             cls=abs(float(res["cls"]) - float(cls)) / (abs(float(cls)) + 1e-9),
-             cons=abs(float(res["cons"]) - float(cons)) / abs(float(cons)))
-    print("losses fused vs drop-in:", e, "values", float(total), float(loc), float(cls), float(cons))
-    e_out, e_flp = rel(res["output"], out), rel(res["flip_op"], flip_op)
-    errs = {k: rel(p.grad, ref_grads[k]) for k, p in m2.named_parameters()}
-    worst = max(errs, key=errs.get)
-    med = sorted(errs.values())[len(errs) // 2]
-    dec = {k: v for k, v in errs.items() if not k.startswith(("conv1.", "primary_caps.", "conv_caps."))}
-    l2o = float((res["output"].double() - out.double()).norm() / out.double().norm())
-    print(f"logits fused vs drop-in: max-norm {e_out:.2e} / {e_flp:.2e}, relative L2 {l2o:.2e}; grads: worst {worst} "
-          f"{errs[worst]:.2e}, median {med:.2e}, decoder worst {max(dec.values()):.2e}")
-    # Both sides are OUR kernels; they differ only in batching (one 2P batch with per-pass BN groups vs two passes) and
-    # in the order of fp32 atomics -- differences of 1e-7 that the routing amplifies, hence the
-    # percent-level tolerances on quantities downstream of the routing.
-    ops.set_deterministic(False)
     # forward + losses: identical; decoder / capsule gradients: accumulation noise; encoder gradients additionally pass
     # the (chaotic) train-mode BN backward chain, where the different fp32 fan-in add order of the two schedules shows
     assert max(e.values()) < 1e-5, e
