@@ -119,7 +119,8 @@ typedef struct {
   void* packed;
   const int32_t* wtap;
   int64_t s_r, s_c, tap_pitch, col_off;
-  int32_t R, ntaps, C, C_real, r_off, bn_tile, nkb, pad_;
+  int32_t R, ntaps, C, C_real, r_off, bn_tile, nkb;
+  int32_t dtype; /* 0: bf16 operand, 1: tf32 (fp32 storage, 32 K-elements per 128-byte row) */
 } b2c_pack_job;
 int b2c_pack_weights_batched(const b2c_pack_job* jobs_dev, const int32_t* block_start_dev, int32_t njobs, int32_t nblocks,
                              b2c_stream_t stream);
@@ -272,6 +273,14 @@ int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 
 /* tests: 1 = BatchNorm reductions use one block per statistic group (bit-reproducible activations, slow) */
 int b2c_set_deterministic(int32_t on);
+
+/* Precision mode of the activation tensors, process-wide.  0 (default): bf16 activations, bf16 GEMM operands
+ * (tcgen05.mma kind::f16).  1: fp32 activations and fp32 packed weights read by the tensor core as tf32
+ * (tcgen05.mma kind::tf32, fp32 accumulate) -- the reference computes in fp32 (main_ucf101.py:52-55, cuDNN convs with
+ * allow_tf32 default); this mode is the one its 1e-3 parity bar is asserted in.  Every `void*` activation view of this
+ * header is bf16 in mode 0 and fp32 in mode 1; values that feed a later GEMM are rounded to tf32 when stored. */
+int b2c_set_precision(int32_t mode);
+int b2c_get_precision(void);
 
 /* generic helpers */
 int b2c_fill_f32(float* p, int64_t n, float v, b2c_stream_t s);

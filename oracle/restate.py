@@ -38,23 +38,38 @@ Tensor = torch.Tensor
 # the oracle* separates implementation fidelity from that conditioning.  Straight-through in
 # autograd (rounding has identity gradient), like the CUDA backward.
 # --------------------------------------------------------------------------------------
-_EMULATE_BF16 = False
+_EMULATE = None        # None | "bf16" | "tf32"
 
 
 class emulate_bf16:
+    kind = "bf16"
+
     def __enter__(self):
-        global _EMULATE_BF16
-        self.prev, _EMULATE_BF16 = _EMULATE_BF16, True
+        global _EMULATE
+        self.prev, _EMULATE = _EMULATE, self.kind
 
     def __exit__(self, *a):
-        global _EMULATE_BF16
-        _EMULATE_BF16 = self.prev
+        global _EMULATE
+        _EMULATE = self.prev
+
+
+class emulate_tf32(emulate_bf16):
+    """The CUDA path's tf32 precision mode: the same rounding points, 10 mantissa bits (round to nearest, ties away)."""
+    kind = "tf32"
+
+
+def _round_tf32(x: Tensor) -> Tensor:
+    i = x.to(torch.float32).contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32).to(x.dtype)
 
 
 def _q(x: Tensor) -> Tensor:
-    if not _EMULATE_BF16:
+    if _EMULATE is None:
         return x
-    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+    xd = x.detach()
+    r = xd.to(torch.bfloat16).to(x.dtype) if _EMULATE == "bf16" else _round_tf32(xd)
+    return x + (r - xd)
 
 # --------------------------------------------------------------------------------------
 # architecture tables (models/pytorch_i3d.py:221-281, truncated at Mixed_4f by

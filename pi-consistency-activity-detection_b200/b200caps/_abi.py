@@ -44,7 +44,7 @@ class WgradDesc(C.Structure):
 class PackJob(C.Structure):
     _fields_ = [("w", vp), ("packed", vp), ("wtap", vp), ("s_r", i64), ("s_c", i64), ("tap_pitch", i64), ("col_off", i64),
                 ("R", i32), ("ntaps", i32), ("C", i32), ("C_real", i32), ("r_off", i32), ("bn_tile", i32), ("nkb", i32),
-                ("pad_", i32)]
+                ("dtype", i32)]
 
 
 # name -> argtypes  (restype is always int unless noted)
@@ -86,9 +86,10 @@ _SIGS = {
     "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp, vp],
     "b2c_fill_f32": [vp, i64, f32, vp],
     "b2c_set_deterministic": [i32],
+    "b2c_set_precision": [i32],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["b2c_last_error", "b2c_version", "b2c_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["b2c_last_error", "b2c_version", "b2c_launch_count", "b2c_get_precision"])
 
 _lib = None
 
@@ -112,6 +113,8 @@ def lib():
         L.b2c_last_error.argtypes = []
         L.b2c_version.restype = C.c_int
         L.b2c_launch_count.restype = C.c_longlong
+        L.b2c_get_precision.restype = C.c_int
+        L.b2c_get_precision.argtypes = []
         _lib = L
     return _lib
 

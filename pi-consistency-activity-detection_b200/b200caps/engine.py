@@ -13,7 +13,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from .plans import ConvPlan, ConvSpec, View, same_pad
+from .plans import PREC, ConvPlan, ConvSpec, View, act_dtype, same_pad
 
 BN_EPS = 1e-3       # pytorch_i3d.py:80
 BN_MOMENTUM = 0.01  # pytorch_i3d.py:80
@@ -72,7 +72,7 @@ def bump_weights_epoch():
 def _packed_key(*weights):
     """Cache key of derived packed operands.  When the fused step has re-packed every registered operand in one batched
     launch for the current epoch, the epoch component is dropped so per-layer packing is skipped."""
-    base = tuple((w.data_ptr(), w._version) for w in weights)
+    base = (PREC.mode,) + tuple((w.data_ptr(), w._version) for w in weights)
     if ops.PACKS is not None and ops.PACKS.flushed_epoch == STATE.weights_epoch:
         return base + ("batched",)
     return base + (STATE.weights_epoch,)
@@ -136,7 +136,7 @@ def to_cl(x: torch.Tensor, cpad: Optional[int] = None) -> torch.Tensor:
     assert x.dim() == 5, x.shape
     C = x.shape[1]
     cpad = cpad or (C + 7) // 8 * 8
-    if x.dtype == torch.bfloat16 and cpad == C:
+    if x.dtype == act_dtype() and cpad == C and (x.dtype != torch.float32 or x.permute(0, 2, 3, 4, 1).is_contiguous()):
         v = x.permute(0, 2, 3, 4, 1)
         return v if v.is_contiguous() else v.contiguous()
     return _ToCL.apply(x.float(), cpad)
@@ -148,8 +148,8 @@ def from_cl(x_cl: torch.Tensor) -> torch.Tensor:
 
 def grad_cl(g: torch.Tensor) -> torch.Tensor:
     """Incoming gradient for a CL-shaped output -> contiguous bf16."""
-    if g.dtype != torch.bfloat16:
-        g = g.to(torch.bfloat16)
+    if g.dtype != act_dtype():
+        g = g.to(act_dtype())
     return g if g.is_contiguous() else g.contiguous()
 
 
@@ -202,7 +202,7 @@ class StemLayer(ConvLayer):
 
     def im2col(self, x: View) -> torch.Tensor:
         od, pf = self.geometry(x.dims)
-        col = torch.empty((x.N,) + od + (self.Kpad,), dtype=torch.bfloat16, device=x.t.device)
+        col = torch.empty((x.N,) + od + (self.Kpad,), dtype=act_dtype(), device=x.t.device)
         ops.im2col_small(x, col, self.cin, od, self.k, self.stride, pf, self.Kpad)
         return col
 
@@ -225,8 +225,8 @@ class StemLayer(ConvLayer):
             from .plans import packed_geometry
             cl = pl.fprop[0]
             bn, _, nkb, elems = packed_geometry(self.cout, self.Kpad)
-            if cl.packed is None:
-                cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=w.device)
+            if cl.packed is None or cl.packed.dtype != act_dtype():
+                cl.packed = torch.zeros(elems, dtype=act_dtype(), device=w.device)
                 self._wtap = torch.arange(self.taps, dtype=torch.int32, device=w.device)
             # k = tap*cin + c  <-  w[co][c][tap]
             ops.pack_part(w.detach(), cl.packed, self._wtap, self.cout, self.taps, self.cin, self.cin, self.cin * self.taps,
@@ -254,7 +254,7 @@ def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: 
     pl = layer.packed(x.dims, "fprop")
     N = x.N
     Cout = pl.spec.Cout_pad
-    raw = torch.empty((N,) + tuple(pl.out_dims) + (Cout,), dtype=torch.bfloat16, device=x.t.device)
+    raw = torch.empty((N,) + tuple(pl.out_dims) + (Cout,), dtype=act_dtype(), device=x.t.device)
     ops.conv_fprop(pl, "fprop", x, View(raw))
     sv = UnitSaved()
     sv.raw, sv.dims, sv.col = raw, x.dims, col
@@ -317,7 +317,7 @@ def cba_bwd(layer: ConvLayer, bias, x: View, y: Optional[View], gy: View, relu: 
     C = gy.C
     dbias, d1 = grad_buf(bias)
     if relu or scale_nc is not None:
-        dz_t = torch.empty((gy.N,) + tuple(gy.dims) + (C,), dtype=torch.bfloat16, device=dev)
+        dz_t = torch.empty((gy.N,) + tuple(gy.dims) + (C,), dtype=act_dtype(), device=dev)
         dz = View(dz_t)
         ops.act_bwd(gy, y if relu else None, scale_nc, dz, dbias, relu)
     else:
@@ -351,7 +351,7 @@ class Unit3DFn(torch.autograd.Function):
         else:
             pl = layer.plan(x_cl.shape[1:4])
             od, cpad = tuple(pl.out_dims), pl.spec.Cout_pad
-        y = torch.empty((x_cl.shape[0],) + od + (cpad,), dtype=torch.bfloat16, device=x_cl.device)
+        y = torch.empty((x_cl.shape[0],) + od + (cpad,), dtype=act_dtype(), device=x_cl.device)
         training = mod.training
         sv = unit_fwd(layer, gamma, beta, mod.bn.running_mean, mod.bn.running_var, View(x_cl), View(y), training,
                       STATE.bn_groups if training else 1)
@@ -379,7 +379,7 @@ class MaxPoolFn(torch.autograd.Function):
         N, T, H, W, C = x_cl.shape
         pads = [same_pad(d, kk, ss) for d, kk, ss in zip((T, H, W), k, s)]
         od = tuple((d + p[0] + p[1] - kk) // ss + 1 for d, p, kk, ss in zip((T, H, W), pads, k, s))
-        y = torch.empty((N,) + od + (C,), dtype=torch.bfloat16, device=x_cl.device)
+        y = torch.empty((N,) + od + (C,), dtype=act_dtype(), device=x_cl.device)
         idx = torch.empty((N,) + od + (C,), dtype=torch.uint8, device=x_cl.device)
         pf = tuple(p[0] for p in pads)
         ops.maxpool_fwd(View(x_cl), View(y), idx, k, s, pf)
@@ -391,7 +391,7 @@ class MaxPoolFn(torch.autograd.Function):
     def backward(ctx, gy):
         k, s, pf, xshape = ctx.geo
         gy = grad_cl(gy)
-        dx = torch.empty(xshape, dtype=torch.bfloat16, device=gy.device)
+        dx = torch.empty(xshape, dtype=act_dtype(), device=gy.device)
         ops.maxpool_bwd(View(gy), ctx.idx, View(dx), k, s, pf, accumulate=False)
         return dx, None, None
 
@@ -411,9 +411,9 @@ class InceptionFn(torch.autograd.Function):
         c0, c1, c2, c3, c4, c5 = oc
         training = mod.training
         g = STATE.bn_groups if training else 1
-        out = torch.empty((N, T, H, W, c0 + c2 + c4 + c5), dtype=torch.bfloat16, device=dev)
-        mid1 = torch.empty((N, T, H, W, c1), dtype=torch.bfloat16, device=dev)
-        mid2 = torch.empty((N, T, H, W, c3), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((N, T, H, W, c0 + c2 + c4 + c5), dtype=act_dtype(), device=dev)
+        mid1 = torch.empty((N, T, H, W, c1), dtype=act_dtype(), device=dev)
+        mid2 = torch.empty((N, T, H, W, c3), dtype=act_dtype(), device=dev)
         pooled = torch.empty_like(x_cl)
         idx = torch.empty(x_cl.shape, dtype=torch.uint8, device=dev)
         xv = View(x_cl)
@@ -531,8 +531,8 @@ class FusedConvLayer:
             cl = pl.fprop[0]
             nt = len(cl.taps)
             bn, _, nkb, elems = packed_geometry(spec.Cout_pad, nt * spec.Cin_pad)
-            if cl.packed is None:
-                cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=dev)
+            if cl.packed is None or cl.packed.dtype != act_dtype():
+                cl.packed = torch.zeros(elems, dtype=act_dtype(), device=dev)
             for w, co, off in zip(self.weights, self.couts, self.offs):
                 ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, co, nt, spec.Cin_pad, spec.Cin, spec.Cin * T, T,
                               spec.Cin_pad, 0, off, bn, nkb)
@@ -541,8 +541,8 @@ class FusedConvLayer:
             for cl in pl.dgrad:
                 nt = len(cl.taps)
                 bn, _, nkb, elems = packed_geometry(spec.Cin_pad, nt * cg)
-                if cl.packed is None:
-                    cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=dev)
+                if cl.packed is None or cl.packed.dtype != act_dtype():
+                    cl.packed = torch.zeros(elems, dtype=act_dtype(), device=dev)
                 for w, co, off in zip(self.weights, self.couts, self.offs):
                     ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, spec.Cin, nt, co, co, T, spec.Cin * T, cg, off, 0, bn, nkb)
         self.keys[(tuple(in_dims), which)] = key
@@ -573,7 +573,7 @@ class PrimaryCapsFn(torch.autograd.Function):
         N = x_cl.shape[0]
         bias = torch.cat([bp.detach(), ba.detach()])      # 544 floats (plumbing)
         out = torch.empty((N,) + tuple(pl.out_dims) + (544,), dtype=torch.float32, device=x_cl.device)
-        ops.conv_fprop(pl, "fprop", View(x_cl), View(out), bias=bias, sigmoid_from=512)
+        ops.conv_fprop(pl, "fprop", View(x_cl), View(out), bias=bias, sigmoid_from=512, final=True)
         ctx.mod, ctx.x, ctx.out = mod, x_cl, out
         return out
 
@@ -584,7 +584,7 @@ class PrimaryCapsFn(torch.autograd.Function):
         g = g.contiguous().float()
         rows = out.numel() // 544
         cg = layer.grad_cpad or 544
-        dzb = (torch.zeros if cg != 544 else torch.empty)(out.shape[:-1] + (cg,), dtype=torch.bfloat16, device=out.device)
+        dzb = (torch.zeros if cg != 544 else torch.empty)(out.shape[:-1] + (cg,), dtype=act_dtype(), device=out.device)
         dbias = torch.zeros(544, dtype=torch.float32, device=out.device)
         ops.primarycaps_bwd_prep(g, out, dzb, dbias, rows, cg)
         dims = x.shape[1:4]
@@ -638,7 +638,7 @@ class CapsHeadFn(torch.autograd.Function):
         N, h, w, oc = rout.shape
         C = oc // 17
         L = h * w
-        x0 = torch.empty((N, 1, h, w, C * 16), dtype=torch.bfloat16, device=rout.device)
+        x0 = torch.empty((N, 1, h, w, C * 16), dtype=act_dtype(), device=rout.device)
         ops.pose_mask_fwd(rout, mask, x0, N, L, C)
         ctx.mask, ctx.shape = mask, (N, h, w, C)
         return x0
@@ -681,7 +681,7 @@ class DecoderFn(torch.autograd.Function):
         dev = x0.device
         N = x0.shape[0]
         L = mod._layers
-        bf = torch.bfloat16
+        bf = act_dtype()
         T1 = c56.shape[1]          # 2 for 8-frame clips
         H1 = c28.shape[2]          # 28
         cat28 = torch.empty((N, 1, H1, H1, 128), dtype=bf, device=dev)
@@ -712,7 +712,7 @@ class DecoderFn(torch.autograd.Function):
         L = mod._layers
         x0, c28, c56, c112, cat28, cat56, cat112, u4 = ctx.t
         dev = glog.device
-        bf = torch.bfloat16
+        bf = act_dtype()
         N, To, Ho = u4.shape[0], u4.shape[1], u4.shape[2]
         glog = glog.contiguous().float()
         dP = torch.empty((N, To, Ho, Ho, SmoothLayer.BWD_CPAD), dtype=bf, device=dev)

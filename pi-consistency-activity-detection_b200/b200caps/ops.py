@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _abi
-from .plans import ConvPlan, View, fill_conv_desc, fill_wgrad_desc
+from .plans import PREC, ConvPlan, View, act_dtype, fill_conv_desc, fill_wgrad_desc
 
 
 def stream() -> int:
@@ -39,9 +39,9 @@ def _launch(kind: str, name: str, desc):
 
 
 def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=None, relu=False,
-               sigmoid_from=-1, accumulate=False, bn_tile=0):
+               sigmoid_from=-1, accumulate=False, bn_tile=0, final=False):
     """out: View (bf16 / fp32 rows) or a 2-D fp32 tensor (Cout_pad, rows) for the planar epilogue."""
-    d = fill_conv_desc(plan, which, x, out, bias, scale_nc, relu, sigmoid_from, accumulate, bn_tile)
+    d = fill_conv_desc(plan, which, x, out, bias, scale_nc, relu, sigmoid_from, accumulate, bn_tile, final)
     _launch(f"{which} {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
             f"{' T' if plan.spec.transposed else ''}", "b2c_conv_fprop", d)
 
@@ -97,7 +97,7 @@ def pack_part(weight, packed, wtap_dev, R, ntaps, C, C_real, s_r, s_c, tap_pitch
         key = (weight.data_ptr(), packed.data_ptr(), r_off, col_off)
         PACKS.add(key, dict(w=weight.data_ptr(), packed=packed.data_ptr(), wtap=wtap_dev.data_ptr(), s_r=s_r, s_c=s_c,
                             tap_pitch=tap_pitch, col_off=col_off, R=R, ntaps=ntaps, C=C, C_real=C_real, r_off=r_off,
-                            bn_tile=bn_tile, nkb=nkb, pad_=0))
+                            bn_tile=bn_tile, nkb=nkb, dtype=PREC.mode))
     _abi.call("b2c_pack_weights", _p(weight), _p(packed), _p(wtap_dev), R, ntaps, C, C_real, s_r, s_c, tap_pitch, col_off,
               r_off, bn_tile, nkb, stream())
 
@@ -108,8 +108,8 @@ def ncdhw_to_cl(x: torch.Tensor, cpad: int, out: Optional[torch.Tensor] = None) 
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
     N, Cc, T, H, W = x.shape
     if out is None:
-        out = torch.empty((N, T, H, W, cpad), dtype=torch.bfloat16, device=x.device)
-    assert tuple(out.shape) == (N, T, H, W, cpad) and out.is_contiguous() and out.dtype == torch.bfloat16
+        out = torch.empty((N, T, H, W, cpad), dtype=act_dtype(), device=x.device)
+    assert tuple(out.shape) == (N, T, H, W, cpad) and out.is_contiguous() and out.dtype == act_dtype()
     _abi.call("b2c_ncdhw_to_ndhwc", _p(x), _p(out), N, Cc, T * H * W, cpad, stream())
     return out
 

@@ -29,8 +29,41 @@ from . import _abi
 TMA_TAIL = os.environ.get("B2C_TMA_TAIL", "1") != "0"
 
 
+class _Precision:
+    """Process-wide precision mode of the activation tensors (include/b200caps.h: b2c_set_precision).
+    0 = bf16 activations / bf16 operands; 1 = fp32 activations / tf32 operands (the reference's fp32 arithmetic,
+    main_ucf101.py:52-55, within tensor-core tf32 rounding)."""
+    mode = 0
+
+
+PREC = _Precision()
+
+
+def set_precision(name) -> None:
+    """'bf16' (default) or 'tf32'.  Set it BEFORE building a TrainStep / running a model: packed operands and
+    activation buffers created under one mode are not valid under the other (caches are keyed by the mode)."""
+    mode = {"bf16": 0, "tf32": 1, "fp32": 1, 0: 0, 1: 1}[name]
+    _abi.call("b2c_set_precision", mode)
+    PREC.mode = mode
+
+
+def precision() -> str:
+    return "tf32" if PREC.mode else "bf16"
+
+
+def act_dtype() -> torch.dtype:
+    return torch.float32 if PREC.mode else torch.bfloat16
+
+
+def kblock() -> int:
+    """K elements per 128-byte swizzle row of a GEMM operand."""
+    return 32 if PREC.mode else 64
+
+
 def tap_pitch(C: int) -> int:
     """K columns per tap of a packed operand over C stored channels."""
+    if PREC.mode:
+        return (C + 31) // 32 * 32           # tf32 mode runs on the TMA path only
     return (C + 63) // 64 * 64 if (TMA_TAIL and C % 64) else C
 
 
@@ -46,8 +79,9 @@ def packed_geometry(rows_pad: int, K: int):
     """(bn_tile, n_tiles, nkb, elements) of the pre-swizzled weight operand."""
     bn = pick_bn_tile(rows_pad)
     nt = (rows_pad + bn - 1) // bn
-    nkb = (K + 63) // 64
-    return bn, nt, nkb, nt * nkb * bn * 64
+    kb = kblock()
+    nkb = (K + kb - 1) // kb
+    return bn, nt, nkb, nt * nkb * bn * kb
 
 
 def _tap_word(dt: int, dh: int, dw: int) -> int:
@@ -223,8 +257,8 @@ class ConvPlan:
         for cl in classes:
             nt = len(cl.taps)
             bn, ntile, nkb, elems = packed_geometry(pk["R_pad"], nt * pitch)
-            if cl.packed is None:
-                cl.packed = torch.zeros(elems, dtype=torch.bfloat16, device=weight.device)
+            if cl.packed is None or cl.packed.dtype != act_dtype():
+                cl.packed = torch.zeros(elems, dtype=act_dtype(), device=weight.device)
             from . import ops
             ops.pack_part(weight, cl.packed, cl.wtap_dev, pk["R"], nt, pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], pitch, 0, 0,
                           bn, nkb)
@@ -264,16 +298,18 @@ class View:
 
 
 def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, scale_nc=None, relu=False,
-                   sigmoid_from=-1, accumulate=False, bn_tile=0) -> _abi.ConvDesc:
-    """which = 'fprop' (x = layer input, out = layer output) or 'dgrad' (x = dY, out = dX)."""
+                   sigmoid_from=-1, accumulate=False, bn_tile=0, final=False) -> _abi.ConvDesc:
+    """which = 'fprop' (x = layer input, out = layer output) or 'dgrad' (x = dY, out = dX).
+    final (tf32 mode): the output is not a later GEMM's operand -- keep full fp32 instead of rounding to tf32."""
     classes = plan.fprop if which == "fprop" else plan.dgrad
     si, so = (plan.fprop_si, plan.fprop_so) if which == "fprop" else (plan.dgrad_si, plan.dgrad_so)
     pk = plan.fprop_pack if which == "fprop" else plan.dgrad_pack
     exp_in, exp_out = (plan.in_dims, plan.out_dims) if which == "fprop" else (plan.out_dims, plan.in_dims)
     assert x.dims == tuple(exp_in), (which, x.dims, exp_in)
     assert x.C == pk["C"], (which, x.C, pk["C"])
-    assert x.t.dtype == torch.bfloat16
+    assert x.t.dtype == act_dtype(), (x.t.dtype, precision())
     d = _abi.ConvDesc()
+    d.dtype = PREC.mode
     d.inp = x.ptr
     d.bias = bias.data_ptr() if bias is not None else None
     d.scale_nc = scale_nc.data_ptr() if scale_nc is not None else None
@@ -286,9 +322,10 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
     d.so_t, d.so_h, d.so_w = so
     if isinstance(out, View):
         assert out.dims == tuple(exp_out) and out.C == pk["R_pad"], (which, out.dims, exp_out, out.C, pk["R_pad"])
-        assert out.t.dtype in (torch.bfloat16, torch.float32)
+        assert out.t.dtype in (act_dtype(), torch.float32)
         d.out, d.out_row_stride, d.out_c_off = out.ptr, out.row_stride, out.c_off
         d.out_fp32 = 1 if out.t.dtype == torch.float32 else 0
+        d.round_out = 1 if (PREC.mode and not final) else 0
     else:   # planar fp32 (Cout_pad, rows)
         rows = x.N * exp_out[0] * exp_out[1] * exp_out[2]
         assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (pk["R_pad"], rows)
@@ -323,7 +360,9 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
     g, p = (x, dy) if geo["g_is_input"] else (dy, x)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     assert g.C == geo["Cg"] and p.C == geo["Cp"], (g.C, geo["Cg"], p.C, geo["Cp"])
+    assert g.t.dtype == act_dtype() and p.t.dtype == act_dtype(), (g.t.dtype, p.t.dtype, precision())
     d = _abi.WgradDesc()
+    d.dtype = PREC.mode
     d.Cp_real = geo.get("Cp_real", geo["Cp"])
     d.g, d.p, d.dw = g.ptr, p.ptr, dw.data_ptr()
     d.taps, d.wtap = cl.taps_dev.data_ptr(), cl.wtap_dev.data_ptr()

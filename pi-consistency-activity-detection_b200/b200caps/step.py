@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import engine, ops
-from .plans import View
+from .plans import View, act_dtype
 
 
 @dataclass
@@ -314,7 +314,7 @@ class TrainStep:
         tape = []   # (backward closure) in forward order
         try:
             # ---------------- forward: both passes as one batch [clips ; flipped clips] ----------------
-            x_cl = torch.empty((2 * P, data.shape[2], H, W, 8), dtype=torch.bfloat16, device=dev)
+            x_cl = torch.empty((2 * P, data.shape[2], H, W, 8), dtype=act_dtype(), device=dev)
             ops.ncdhw_to_cl(data.contiguous(), 8, out=x_cl[:P])
             ops.ncdhw_to_cl(fl_data.contiguous(), 8, out=x_cl[P:])
             i3d = model.conv1

@@ -24,6 +24,10 @@ int b2c_cuda_check(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return b2c_cuda_check(e__, what);    \
   } while (0)
 
+// Precision mode of the activation tensors (api.cu: b2c_set_precision): 0 = bf16 activations / bf16 GEMM operands,
+// 1 = fp32 activations / tf32 GEMM operands.  Process-wide; every entry point that takes activation views consults it.
+int b2c_precision();
+
 static inline int b2c_num_sms() {
   static int n = 0;
   if (!n) {
@@ -145,6 +149,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp32 operands read as tf32 (10-bit mantissa; the low 13 bits are ignored), fp32 accumulate; K = 8 per instruction
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool kTF32>
+__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (kTF32) umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 // arrive on an mbarrier when all previously issued UMMAs of this thread retire
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -233,8 +251,19 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n, int a_mn_major, int b
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// the same for kind::tf32: operand format field 2 (TF32) instead of 1 (BF16)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 // ---- small math / packing -----------------------------------------------------------
+// fp32 -> tf32 (10-bit mantissa), round to nearest, ties away from zero; the result is an fp32 bit pattern
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

@@ -32,24 +32,52 @@ __device__ __forceinline__ RowMap row_map(int CV) {
 __device__ __forceinline__ uint4 ld16(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(bf16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// Activations are stored as T = bf16 (default) or T = float (B2C precision mode 1: fp32 activations, tf32 GEMM operands).
+// Every kernel moves 8-channel vectors: 16 bytes of bf16 or 32 bytes of fp32.  `round` (fp32 only): the value is the
+// operand of a later tcgen05 kind::tf32 GEMM and is rounded to tf32 (nearest, ties away) here -- the tensor core would
+// otherwise truncate the low 13 mantissa bits, a systematic -2.4e-4 relative bias per operand.
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void ld8<bf16>(const bf16* p, float* v) { unpack8(ld16(p), v); }
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float* v) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float* v, bool round);
+template <>
+__device__ __forceinline__ void st8<bf16>(bf16* p, const float* v, bool) { st16(p, pack8(v)); }
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float* v, bool round) {
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = round ? tf32_rna(v[j]) : v[j];
+  reinterpret_cast<float4*>(p)[0] = make_float4(r[0], r[1], r[2], r[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+
 // ---------------------------------------------------------------------------------------------
-__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int N, int C, long long THW,
+template <typename T>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, long long THW,
                                       int Cpad) {
   const long long total = (long long)N * THW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / THW, pos = i - n * THW;
     const float* src = in + n * C * THW + pos;
-    bf16* dst = out + i * Cpad;
+    T* dst = out + i * Cpad;
     for (int c0 = 0; c0 < Cpad; c0 += 8) {
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? src[(long long)(c0 + j) * THW] : 0.f;
-      st16(dst + c0, pack8(v));
+      st8(dst + c0, v, true);
     }
   }
 }
 
-__global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ in, long long in_row_stride, int in_c_off, float* __restrict__ out,
+template <typename T>
+__global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ in, long long in_row_stride, int in_c_off, float* __restrict__ out,
                                       int N, int C, long long THW) {
   __shared__ float tile[32][33];
   const long long n = blockIdx.z;
@@ -59,7 +87,7 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ in, long long in_
     const long long p = p0 + j;
     const int c = c0 + threadIdx.x;
     float v = 0.f;
-    if (p < THW && c < C) v = __bfloat162float(in[(n * THW + p) * in_row_stride + in_c_off + c]);
+    if (p < THW && c < C) v = (float)in[(n * THW + p) * in_row_stride + in_c_off + c];
     tile[j][threadIdx.x] = v;
   }
   __syncthreads();
@@ -72,7 +100,8 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16* __restrict__ in, long long in_
 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm statistics: grid (blocks, groups)
-__global__ void __launch_bounds__(kBlock) bn_stats_kernel(const bf16* __restrict__ x, long long rows_per_group, int C,
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T* __restrict__ x, long long rows_per_group, int C,
                                                           long long row_stride, int c_off, float* __restrict__ ws) {
   const int CV = C / 8;
   const RowMap m = row_map(CV);
@@ -81,10 +110,10 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const bf16* __restrict
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (m.active) {
-    const bf16* base = x + (long long)g * rows_per_group * row_stride + c_off + m.cv * 8;
+    const T* base = x + (long long)g * rows_per_group * row_stride + c_off + m.cv * 8;
     for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
       float v[8];
-      unpack8(ld16(base + r * row_stride), v);
+      ld8(base + r * row_stride, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s1[j] += v[j];
@@ -135,10 +164,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ ws_all, int ws_C, i
   if (running_var) running_var[c] = rv;
 }
 
-__global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const bf16* __restrict__ x, long long rows_per_group, int C,
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const T* __restrict__ x, long long rows_per_group, int C,
                                                                long long x_rs, int x_co, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, bf16* __restrict__ y, long long y_rs,
+                                                               const float* __restrict__ beta, T* __restrict__ y, long long y_rs,
                                                                int y_co, int relu) {
   const int CV = C / 8;
   const RowMap m = row_map(CV);
@@ -154,19 +184,20 @@ __global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const bf16* __res
   const long long row0 = (long long)g * rows_per_group;
   for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
     float v[8];
-    unpack8(ld16(x + (row0 + r) * x_rs + x_co + m.cv * 8), v);
+    ld8(x + (row0 + r) * x_rs + x_co + m.cv * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[j] = v[j] * sc[j] + sf[j];
       if (relu) v[j] = fmaxf(v[j], 0.f);
     }
-    st16(y + (row0 + r) * y_rs + y_co + m.cv * 8, pack8(v));
+    st8(y + (row0 + r) * y_rs + y_co + m.cv * 8, v, true);          // next conv's operand
   }
 }
 
-__global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
-                                                               const bf16* __restrict__ y, long long y_rs, int y_co,
-                                                               const bf16* __restrict__ x, long long x_rs, int x_co,
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
+                                                               const T* __restrict__ y, long long y_rs, int y_co,
+                                                               const T* __restrict__ x, long long x_rs, int x_co,
                                                                long long rows_per_group, int C, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, float* __restrict__ ws, int relu) {
   const int CV = C / 8;
@@ -184,9 +215,9 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const bf16* __res
     const long long row0 = (long long)g * rows_per_group;
     for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
       float d[8], yy[8], xx[8];
-      unpack8(ld16(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8), d);
-      unpack8(ld16(x + (row0 + r) * x_rs + x_co + m.cv * 8), xx);
-      if (relu) unpack8(ld16(y + (row0 + r) * y_rs + y_co + m.cv * 8), yy);
+      ld8(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8, d);
+      ld8(x + (row0 + r) * x_rs + x_co + m.cv * 8, xx);
+      if (relu) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
@@ -213,13 +244,14 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const bf16* __res
   }
 }
 
-__global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
-                                                              const bf16* __restrict__ y, long long y_rs, int y_co,
-                                                              const bf16* __restrict__ x, long long x_rs, int x_co,
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
+                                                              const T* __restrict__ y, long long y_rs, int y_co,
+                                                              const T* __restrict__ x, long long x_rs, int x_co,
                                                               long long rows_per_group, int C, int groups,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma, const float* __restrict__ ws,
-                                                              bf16* __restrict__ dx, long long dx_rs, int dx_co, float* dgamma,
+                                                              T* __restrict__ dx, long long dx_rs, int dx_co, float* dgamma,
                                                               float* dbeta, int relu) {
   const int CV = C / 8;
   const RowMap m = row_map(CV);
@@ -250,15 +282,15 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const bf16* __rest
   const long long row0 = (long long)g * rows_per_group;
   for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
     float d[8], yy[8], xx[8], o[8];
-    unpack8(ld16(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8), d);
-    unpack8(ld16(x + (row0 + r) * x_rs + x_co + m.cv * 8), xx);
-    if (relu) unpack8(ld16(y + (row0 + r) * y_rs + y_co + m.cv * 8), yy);
+    ld8(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8, d);
+    ld8(x + (row0 + r) * x_rs + x_co + m.cv * 8, xx);
+    if (relu) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
       o[j] = k0[j] * (dr - a1[j] - (xx[j] - mu[j]) * rs[j] * a2[j]);
     }
-    st16(dx + (row0 + r) * dx_rs + dx_co + m.cv * 8, pack8(o));
+    st8(dx + (row0 + r) * dx_rs + dx_co + m.cv * 8, o, true);       // dgrad / wgrad operand
   }
 }
 
@@ -329,8 +361,61 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restr
   }
 }
 
-__global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
-                                                             const uint8_t* __restrict__ idx, bf16* __restrict__ dx,
+// fp32 activations (precision mode 1): plain compare / select, same semantics (strict '>', first occurrence wins, zero
+// padding candidates are real, NaN never wins).
+__global__ void __launch_bounds__(kBlock) maxpool_fwd_f32_kernel(const float* __restrict__ x, long long x_rs, int x_co,
+                                                                 float* __restrict__ y, long long y_rs, int y_co,
+                                                                 uint8_t* __restrict__ idx, PoolGeom G) {
+  const int CV = G.C / 8;
+  const unsigned total = (unsigned)G.N * G.To * G.Ho * G.Wo * CV;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (unsigned)CV);
+    unsigned o = i / (unsigned)CV;
+    const long long orow = o;
+    const int ow = (int)(o % (unsigned)G.Wo); o /= (unsigned)G.Wo;
+    const int oh = (int)(o % (unsigned)G.Ho); o /= (unsigned)G.Ho;
+    const int ot = (int)(o % (unsigned)G.To); o /= (unsigned)G.To;
+    const int n = (int)o;
+    float best[8];
+    uint32_t bidx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = __int_as_float(0xff800000);
+      bidx[j] = 0xffu;
+    }
+    int tap = 0;
+    for (int a = 0; a < G.kt; ++a) {
+      const int it = ot * G.st - G.pt + a;
+      for (int b = 0; b < G.kh; ++b) {
+        const int ih = oh * G.sh - G.ph + b;
+        for (int c = 0; c < G.kw; ++c, ++tap) {
+          const int iw = ow * G.sw - G.pw + c;
+          const bool inb = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi && (unsigned)iw < (unsigned)G.Wi;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          if (inb) ld8(x + ((((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi + iw) * x_rs + x_co + cv * 8, v);
+          const uint32_t t = inb ? (uint32_t)tap : 0xffu;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > best[j]) {
+              best[j] = v[j];
+              bidx[j] = t;
+            }
+        }
+      }
+    }
+    st8(y + orow * y_rs + y_co + cv * 8, best, false);
+    uint2 pk;
+    pk.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+    pk.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+    *reinterpret_cast<uint2*>(idx + orow * G.C + cv * 8) = pk;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
+                                                             const uint8_t* __restrict__ idx, T* __restrict__ dx,
                                                              long long dx_rs, int dx_co, PoolGeom G, int accumulate) {
   const int CV = G.C / 8;
   const unsigned total = (unsigned)G.N * G.Ti * G.Hi * G.Wi * CV;
@@ -361,7 +446,7 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const bf16* __restr
           const long long orow = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo + ow;
           const uint2 pk = *reinterpret_cast<const uint2*>(idx + orow * G.C + cv * 8);
           float d[8];
-          unpack8(ld16(dy + orow * dy_rs + dy_co + cv * 8), d);
+          ld8(dy + orow * dy_rs + dy_co + cv * 8, d);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t w = j < 4 ? pk.x : pk.y;
@@ -371,20 +456,21 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const bf16* __restr
         }
       }
     }
-    bf16* dst = dx + irow * dx_rs + dx_co + cv * 8;
+    T* dst = dx + irow * dx_rs + dx_co + cv * 8;
     if (accumulate) {
       float e[8];
-      unpack8(ld16(dst), e);
+      ld8(dst, e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += e[j];
     }
-    st16(dst, pack8(acc));
+    st8(dst, acc, false);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) channel_scale_kernel(const bf16* __restrict__ x, long long x_rs, int x_co,
-                                                               const float* __restrict__ scale, bf16* __restrict__ y, long long y_rs,
+template <typename T>
+__global__ void __launch_bounds__(kBlock) channel_scale_kernel(const T* __restrict__ x, long long x_rs, int x_co,
+                                                               const float* __restrict__ scale, T* __restrict__ y, long long y_rs,
                                                                int y_co, int N, long long rows_per_n, int C) {
   const int CV = C / 8;
   const long long total = (long long)N * rows_per_n * CV;
@@ -393,18 +479,19 @@ __global__ void __launch_bounds__(kBlock) channel_scale_kernel(const bf16* __res
     const long long row = i / CV;
     const long long n = row / rows_per_n;
     float v[8];
-    unpack8(ld16(x + row * x_rs + x_co + cv * 8), v);
+    ld8(x + row * x_rs + x_co + cv * 8, v);
     const float* s = scale + n * C + cv * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= s[j];
-    st16(y + row * y_rs + y_co + cv * 8, pack8(v));
+    st8(y + row * y_rs + y_co + cv * 8, v, false);                   // x{0,2}: exact
   }
 }
 
 // grid (blocks, N): per-sample so the scale row is fixed per block
-__global__ void __launch_bounds__(kBlock) act_bwd_kernel(const bf16* __restrict__ dy, long long dy_rs, int dy_co,
-                                                         const bf16* __restrict__ y, long long y_rs, int y_co,
-                                                         const float* __restrict__ scale, bf16* __restrict__ dz, long long dz_rs,
+template <typename T>
+__global__ void __launch_bounds__(kBlock) act_bwd_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
+                                                         const T* __restrict__ y, long long y_rs, int y_co,
+                                                         const float* __restrict__ scale, T* __restrict__ dz, long long dz_rs,
                                                          int dz_co, float* __restrict__ dbias, long long rows_per_n, int C, int relu) {
   const int CV = C / 8;
   const RowMap m = row_map(CV);
@@ -418,8 +505,8 @@ __global__ void __launch_bounds__(kBlock) act_bwd_kernel(const bf16* __restrict_
     const long long row0 = (long long)n * rows_per_n;
     for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_n; r += (long long)gridDim.x * m.rpb) {
       float d[8], yy[8];
-      unpack8(ld16(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8), d);
-      if (relu) unpack8(ld16(y + (row0 + r) * y_rs + y_co + m.cv * 8), yy);
+      ld8(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8, d);
+      if (relu) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float v = d[j] * sc[j];
@@ -427,7 +514,7 @@ __global__ void __launch_bounds__(kBlock) act_bwd_kernel(const bf16* __restrict_
         d[j] = v;
         s1[j] += v;
       }
-      if (dz) st16(dz + (row0 + r) * dz_rs + dz_co + m.cv * 8, pack8(d));
+      if (dz) st8(dz + (row0 + r) * dz_rs + dz_co + m.cv * 8, d, true);   // dgrad / wgrad operand
     }
   }
   if (!dbias) return;
@@ -442,8 +529,9 @@ __global__ void __launch_bounds__(kBlock) act_bwd_kernel(const bf16* __restrict_
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], sh[i]);
 }
 
-__global__ void __launch_bounds__(kBlock) add_kernel(const bf16* __restrict__ a, long long a_rs, int a_co, const bf16* __restrict__ b,
-                                                     long long b_rs, int b_co, bf16* __restrict__ o, long long o_rs, int o_co,
+template <typename T>
+__global__ void __launch_bounds__(kBlock) add_kernel(const T* __restrict__ a, long long a_rs, int a_co, const T* __restrict__ b,
+                                                     long long b_rs, int b_co, T* __restrict__ o, long long o_rs, int o_co,
                                                      long long rows, int C) {
   const int CV = C / 8;
   const long long total = rows * CV;
@@ -451,11 +539,11 @@ __global__ void __launch_bounds__(kBlock) add_kernel(const bf16* __restrict__ a,
     const int cv = (int)(i % CV);
     const long long row = i / CV;
     float x[8], y[8];
-    unpack8(ld16(a + row * a_rs + a_co + cv * 8), x);
-    unpack8(ld16(b + row * b_rs + b_co + cv * 8), y);
+    ld8(a + row * a_rs + a_co + cv * 8, x);
+    ld8(b + row * b_rs + b_co + cv * 8, y);
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] += y[j];
-    st16(o + row * o_rs + o_co + cv * 8, pack8(x));
+    st8(o + row * o_rs + o_co + cv * 8, x, false);
   }
 }
 
@@ -491,7 +579,8 @@ __global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __re
   }
 }
 // adjoint: dP[i][k] = dout[i - 1 + k] (bf16 rows of 32, taps 27..31 zero)
-__global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dP,
+template <typename T_>
+__global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __restrict__ dout, T_* __restrict__ dP,
                                                                float* __restrict__ dbias, int N, int T, int H, int W, int cpad) {
   const long long rows = (long long)N * T * H * W;
   float bsum = 0.f;
@@ -521,10 +610,11 @@ __global__ void __launch_bounds__(kBlock) stencil27_bwd_kernel(const float* __re
 #pragma unroll
     for (int k = 27; k < 32; ++k) v[k] = 0.f;
     bsum += v[13];  // centre tap == dout[i]
-    bf16* dst = dP + (long long)i * cpad;
+    T_* dst = dP + (long long)i * cpad;
+    const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) st16(dst + q * 8, pack8(v + q * 8));
-    for (int q = 4; q < cpad / 8; ++q) st16(dst + q * 8, make_uint4(0, 0, 0, 0));
+    for (int q = 0; q < 4; ++q) st8(dst + q * 8, v + q * 8, true);
+    for (int q = 4; q < cpad / 8; ++q) st8(dst + q * 8, zero8, false);
   }
   if (dbias) {
     __shared__ float sb[kBlock / 32];
@@ -551,8 +641,9 @@ struct Im2colGeom {
 // The Kpad-wide rows then stream out as coalesced 16-byte stores, each assembled from 8 staged elements through a
 // per-block column -> staged-offset table (padding columns point at a zero slot).
 constexpr int kIm2colWB = 56;
-__global__ void __launch_bounds__(512) im2col_small_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Im2colGeom G,
-                                                              int strips, int pitch) {
+template <typename E>   // E = the element's storage word: uint16_t (bf16) or uint32_t (fp32)
+__global__ void __launch_bounds__(512) im2col_small_kernel(const E* __restrict__ x, E* __restrict__ out, Im2colGeom G,
+                                                           int strips, int pitch) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int nthr = (int)blockDim.x;      // a multiple of the 16-byte column groups per row (host)
   const int pairs = G.kt * G.kh;
@@ -560,7 +651,7 @@ __global__ void __launch_bounds__(512) im2col_small_kernel(const bf16* __restric
   const int zero_slot = pairs * pitch;
   const int zero_len = (kIm2colWB - 1) * G.sw * G.C + 8;      // padding columns may be read at zero_slot + row base too
   unsigned short* tab = reinterpret_cast<unsigned short*>(s_raw);                       // Kpad entries
-  bf16* sin = reinterpret_cast<bf16*>(s_raw + (size_t)G.Kpad * 2);                      // pairs * pitch + zero_len elements
+  E* sin = reinterpret_cast<E*>(s_raw + (((size_t)G.Kpad * 2 + 15) & ~(size_t)15));     // pairs * pitch + zero_len elements
   for (int k = threadIdx.x; k < G.Kpad; k += nthr) {
     int off = zero_slot;
     if (k < G.K) {
@@ -569,13 +660,13 @@ __global__ void __launch_bounds__(512) im2col_small_kernel(const bf16* __restric
     }
     tab[k] = (unsigned short)off;
   }
-  for (int k = threadIdx.x; k < zero_len; k += nthr) sin[zero_slot + k] = __float2bfloat16(0.f);
+  for (int k = threadIdx.x; k < zero_len; k += nthr) sin[zero_slot + k] = (E)0;
   __syncthreads();
   const int wpix = (kIm2colWB - 1) * G.sw + G.kw;                                       // staged pixels per input row
   const int vec_per_row = G.Kpad / 8;
-  // Each thread owns ONE 16-byte column group of the row (its 8 staged offsets live in registers) and walks the rows
-  // of the strip: per output vector 8 two-byte shared loads + one 16-byte store (ncu r01f: the per-vector table
-  // fetch and zero-slot selects made this kernel issue/L1 bound at 2.4 TB/s of writes).
+  // Each thread owns ONE 8-element column group of the row (its 8 staged offsets live in registers) and walks the rows
+  // of the strip: per output vector 8 shared loads + one 16-byte (bf16) / two 16-byte (fp32) stores (ncu r01f: the
+  // per-vector table fetch and zero-slot selects made this kernel issue/L1 bound at 2.4 TB/s of writes).
   const int lanes = (nthr / vec_per_row) * vec_per_row;                               // threads that own a column group
   const int rstep = nthr / vec_per_row;                                                 // rows written per sweep
   const int my_v = threadIdx.x % vec_per_row, my_r0 = threadIdx.x / vec_per_row;
@@ -602,30 +693,34 @@ __global__ void __launch_bounds__(512) im2col_small_kernel(const bf16* __restric
       const int a = p / G.kh, b = p - a * G.kh;
       const int t = t0 + a, h = h0 + b;
       const bool rowok = (unsigned)t < (unsigned)G.T && (unsigned)h < (unsigned)G.H;
-      const bf16* src = x + (((long long)n * G.T + t) * G.H + h) * (long long)G.W * G.Cs;
-      bf16* drow = sin + p * pitch;
+      const E* src = x + (((long long)n * G.T + t) * G.H + h) * (long long)G.W * G.Cs;
+      E* drow = sin + p * pitch;
       for (int wl = (int)(threadIdx.x & 31); wl < wpix; wl += 32) {
         const int w = w0 + wl;
-        uint4 px = make_uint4(0, 0, 0, 0);
-        if (rowok && (unsigned)w < (unsigned)G.W) px = ld16(src + (long long)w * G.Cs);   // Cs == 8: one pixel = 16 bytes
-        const bf16* pv = reinterpret_cast<const bf16*>(&px);
-        bf16* dst = drow + wl * G.C;
+        E pv[8];                                                                        // Cs == 8: one pixel = 8 elements
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(E) * 8 / 16); ++q) reinterpret_cast<uint4*>(pv)[q] = make_uint4(0, 0, 0, 0);
+        if (rowok && (unsigned)w < (unsigned)G.W) {
+#pragma unroll
+          for (int q = 0; q < (int)(sizeof(E) * 8 / 16); ++q)
+            reinterpret_cast<uint4*>(pv)[q] = reinterpret_cast<const uint4*>(src + (long long)w * G.Cs)[q];
+        }
+        E* dst = drow + wl * G.C;
         for (int ch = 0; ch < G.C; ++ch) dst[ch] = pv[ch];
       }
     }
     __syncthreads();
     if ((int)threadIdx.x < lanes) {
-      bf16* orow = out + ((((long long)n * G.To + to) * G.Ho + ho) * (long long)G.Wo + wo0) * G.Kpad + my_v * 8;
-      const unsigned short* sraw = reinterpret_cast<const unsigned short*>(sin);
+      E* orow = out + ((((long long)n * G.To + to) * G.Ho + ho) * (long long)G.Wo + wo0) * G.Kpad + my_v * 8;
       const int bstep = G.sw * G.C;
       for (int rl = my_r0; rl < nrow; rl += rstep) {
-        const unsigned short* sb = sraw + rl * bstep;
-        uint4 v;
-        v.x = (unsigned)sb[o[0]] | ((unsigned)sb[o[1]] << 16);
-        v.y = (unsigned)sb[o[2]] | ((unsigned)sb[o[3]] << 16);
-        v.z = (unsigned)sb[o[4]] | ((unsigned)sb[o[5]] << 16);
-        v.w = (unsigned)sb[o[6]] | ((unsigned)sb[o[7]] << 16);
-        st16(orow + (long long)rl * G.Kpad, v);
+        const E* sb = sin + rl * bstep;
+        E v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = sb[o[q]];
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(E) * 8 / 16); ++q)
+          reinterpret_cast<uint4*>(orow + (long long)rl * G.Kpad)[q] = reinterpret_cast<const uint4*>(v)[q];
       }
     }
   }
@@ -656,6 +751,18 @@ inline int row_grid(long long rows, int C, int waves = 4) {
   return grid_for(rows, rpb, waves);
 }
 
+// launch KERNEL<T> with T = the activation storage type of the current precision mode; the argument list may use T
+#define LAUNCH_T(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                                   \
+  do {                                                                                     \
+    if (b2c_precision()) {                                                                 \
+      using T = float;                                                                     \
+      KERNEL<T><<<GRID, BLOCK, SMEM, (cudaStream_t)(STREAM)>>>(__VA_ARGS__);               \
+    } else {                                                                               \
+      using T = bf16;                                                                      \
+      KERNEL<T><<<GRID, BLOCK, SMEM, (cudaStream_t)(STREAM)>>>(__VA_ARGS__);               \
+    }                                                                                      \
+  } while (0)
+
 #define CHECK_VIEW(name, C, rs, co)                                                                         \
   B2C_REQUIRE((C) > 0 && (C) % 8 == 0 && (rs) % 8 == 0 && (co) % 8 == 0 && (C) / 8 <= kBlock, name ": bad view C=%d rs=%lld co=%d", \
               (int)(C), (long long)(rs), (int)(co))
@@ -664,7 +771,10 @@ inline int row_grid(long long rows, int C, int waves = 4) {
 
 B2C_API int b2c_ncdhw_to_ndhwc(const float* in, void* out, int32_t N, int32_t C, int64_t THW, int32_t Cpad, b2c_stream_t s) {
   B2C_REQUIRE(in && out && N > 0 && C > 0 && Cpad % 8 == 0 && Cpad >= C, "ncdhw_to_ndhwc: bad args");
-  ncdhw_to_ndhwc_kernel<<<grid_for((long long)N * THW), kBlock, 0, (cudaStream_t)s>>>(in, (bf16*)out, N, C, THW, Cpad);
+  if (b2c_precision())
+    ncdhw_to_ndhwc_kernel<float><<<grid_for((long long)N * THW), kBlock, 0, (cudaStream_t)s>>>(in, (float*)out, N, C, THW, Cpad);
+  else
+    ncdhw_to_ndhwc_kernel<bf16><<<grid_for((long long)N * THW), kBlock, 0, (cudaStream_t)s>>>(in, (bf16*)out, N, C, THW, Cpad);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("ncdhw_to_ndhwc");
   return 0;
@@ -674,7 +784,10 @@ B2C_API int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_
                                    int64_t THW, b2c_stream_t s) {
   B2C_REQUIRE(in && out && N > 0 && C > 0, "ndhwc_to_ncdhw: bad args");
   dim3 grid((unsigned)((THW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), block(32, 8);
-  ndhwc_to_ncdhw_kernel<<<grid, block, 0, (cudaStream_t)s>>>((const bf16*)in, in_row_stride, in_c_off, out, N, C, THW);
+  if (b2c_precision())
+    ndhwc_to_ncdhw_kernel<float><<<grid, block, 0, (cudaStream_t)s>>>((const float*)in, in_row_stride, in_c_off, out, N, C, THW);
+  else
+    ndhwc_to_ncdhw_kernel<bf16><<<grid, block, 0, (cudaStream_t)s>>>((const bf16*)in, in_row_stride, in_c_off, out, N, C, THW);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("ndhwc_to_ncdhw");
   return 0;
@@ -687,7 +800,10 @@ B2C_API int b2c_bn_sums(const void* x, int64_t rows, int32_t C, int64_t row_stri
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_sums: rows=%lld not divisible by groups=%d", (long long)rows, groups);
   const long long rpg = rows / groups;
   dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
-  bn_stats_kernel<<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws);
+  if (b2c_precision())
+    bn_stats_kernel<float><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const float*)x, rpg, C, row_stride, c_off, ws);
+  else
+    bn_stats_kernel<bf16><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_sums");
   return 0;
@@ -714,8 +830,7 @@ B2C_API int b2c_bn_relu_apply(const void* x, int64_t rows, int32_t C, int64_t x_
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_relu_apply: rows not divisible by groups");
   const long long rpg = rows / groups;
   dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
-  bn_relu_apply_kernel<<<grid, kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, rpg, C, x_rs, x_co, mean, rstd, gamma, beta, (bf16*)y,
-                                                             y_rs, y_co, relu);
+  LAUNCH_T(bn_relu_apply_kernel, grid, kBlock, 0, s, (const T*)x, rpg, C, x_rs, x_co, mean, rstd, gamma, beta, (T*)y, y_rs, y_co, relu);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_relu_apply");
   return 0;
@@ -730,9 +845,7 @@ B2C_API int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_rs, int32_t dy_co,
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_reduce: rows not divisible by groups");
   const long long rpg = rows / groups;
   dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
-  bn_bwd_reduce_kernel<<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs,
-                                                                                 y_co, (const bf16*)x, x_rs, x_co, rpg, C, mean, rstd,
-                                                                                 ws, relu);
+  LAUNCH_T(bn_bwd_reduce_kernel, grid, kBlock, bn_red_smem(C), s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, mean, rstd, ws, relu);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_bwd_reduce");
   return 0;
@@ -748,9 +861,7 @@ B2C_API int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_rs, int32_t dy_co, 
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_apply: rows not divisible by groups");
   const long long rpg = rows / groups;
   dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
-  bn_bwd_apply_kernel<<<grid, kBlock, 0, (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs, y_co, (const bf16*)x,
-                                                            x_rs, x_co, rpg, C, groups, mean, rstd, gamma, ws, (bf16*)dx, dx_rs, dx_co,
-                                                            dgamma, dbeta, relu);
+  LAUNCH_T(bn_bwd_apply_kernel, grid, kBlock, 0, s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, groups, mean, rstd, gamma, ws, (T*)dx, dx_rs, dx_co, dgamma, dbeta, relu);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_bwd_apply");
   return 0;
@@ -766,7 +877,10 @@ B2C_API int b2c_maxpool_fwd(const void* x, int64_t x_rs, int32_t x_co, void* y, 
   PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
   const long long total = (long long)N * To * Ho * Wo * (C / 8);
   B2C_REQUIRE(total < (1LL << 31) - (1LL << 22) && (long long)N * Ti * Hi * Wi * (C / 8) < (1LL << 31), "maxpool_fwd: tensor too large");
-  maxpool_fwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, x_rs, x_co, (bf16*)y, y_rs, y_co, idx, G);
+  if (b2c_precision())
+    maxpool_fwd_f32_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const float*)x, x_rs, x_co, (float*)y, y_rs, y_co, idx, G);
+  else
+    maxpool_fwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, x_rs, x_co, (bf16*)y, y_rs, y_co, idx, G);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("maxpool_fwd");
   return 0;
@@ -782,8 +896,7 @@ B2C_API int b2c_maxpool_bwd(const void* dy, int64_t dy_rs, int32_t dy_co, const 
   PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
   const long long total = (long long)N * Ti * Hi * Wi * (C / 8);
   B2C_REQUIRE(total < (1LL << 31) - (1LL << 22), "maxpool_bwd: tensor too large");
-  maxpool_bwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, idx, (bf16*)dx, dx_rs, dx_co, G,
-                                                                      accumulate);
+  LAUNCH_T(maxpool_bwd_kernel, grid_for(total), kBlock, 0, s, (const T*)dy, dy_rs, dy_co, idx, (T*)dx, dx_rs, dx_co, G, accumulate);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("maxpool_bwd");
   return 0;
@@ -794,8 +907,7 @@ B2C_API int b2c_channel_scale(const void* x, int64_t x_rs, int32_t x_co, const f
   B2C_REQUIRE(x && y && scale_nc, "channel_scale: null pointer");
   CHECK_VIEW("channel_scale(x)", C, x_rs, x_co);
   CHECK_VIEW("channel_scale(y)", C, y_rs, y_co);
-  channel_scale_kernel<<<grid_for((long long)N * rows_per_n * (C / 8)), kBlock, 0, (cudaStream_t)s>>>(
-      (const bf16*)x, x_rs, x_co, scale_nc, (bf16*)y, y_rs, y_co, N, rows_per_n, C);
+  LAUNCH_T(channel_scale_kernel, grid_for((long long)N * rows_per_n * (C / 8)), kBlock, 0, s,  (const T*)x, x_rs, x_co, scale_nc, (T*)y, y_rs, y_co, N, rows_per_n, C);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("channel_scale");
   return 0;
@@ -810,8 +922,7 @@ B2C_API int b2c_act_bwd(const void* dy, int64_t dy_rs, int32_t dy_co, const void
   int gx = row_grid(rows_per_n, C, 2);
   if (gx * N > b2c_num_sms() * 8) gx = (b2c_num_sms() * 8 + N - 1) / N;
   dim3 grid((unsigned)gx, (unsigned)N);
-  act_bwd_kernel<<<grid, kBlock, C * sizeof(float), (cudaStream_t)s>>>((const bf16*)dy, dy_rs, dy_co, (const bf16*)y, y_rs, y_co,
-                                                                       scale_nc, (bf16*)dz, dz_rs, dz_co, dbias, rows_per_n, C, relu);
+  LAUNCH_T(act_bwd_kernel, grid, kBlock, C * sizeof(float), s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, scale_nc, (T*)dz, dz_rs, dz_co, dbias, rows_per_n, C, relu);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("act_bwd");
   return 0;
@@ -823,8 +934,7 @@ B2C_API int b2c_add(const void* a, int64_t a_rs, int32_t a_co, const void* b, in
   CHECK_VIEW("add(a)", C, a_rs, a_co);
   CHECK_VIEW("add(b)", C, b_rs, b_co);
   CHECK_VIEW("add(out)", C, o_rs, o_co);
-  add_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, (cudaStream_t)s>>>((const bf16*)a, a_rs, a_co, (const bf16*)b, b_rs, b_co,
-                                                                      (bf16*)out, o_rs, o_co, rows, C);
+  LAUNCH_T(add_kernel, grid_for(rows * (C / 8)), kBlock, 0, s, (const T*)a, a_rs, a_co, (const T*)b, b_rs, b_co, (T*)out, o_rs, o_co, rows, C);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("add");
   return 0;
@@ -843,7 +953,10 @@ B2C_API int b2c_stencil27_bwd(const float* dout, void* dP, float* dbias, int32_t
                               b2c_stream_t s) {
   B2C_REQUIRE(dout && dP && N > 0 && cpad >= 32 && cpad % 8 == 0 && (long long)N * T * H * W < (1LL << 31) - (1LL << 22),
               "stencil27_bwd: bad args");
-  stencil27_bwd_kernel<<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, dbias, N, T, H, W, cpad);
+  if (b2c_precision())
+    stencil27_bwd_kernel<float><<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (float*)dP, dbias, N, T, H, W, cpad);
+  else
+    stencil27_bwd_kernel<bf16><<<grid_for((long long)N * T * H * W), kBlock, 0, (cudaStream_t)s>>>(dout, (bf16*)dP, dbias, N, T, H, W, cpad);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("stencil27_bwd");
   return 0;
@@ -867,14 +980,26 @@ B2C_API int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, in
   Im2colGeom G{N, Cs, C, T, H, W, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, K, Kpad};
   const int pitch = ((kIm2colWB - 1) * sw + kw) * C;
   const size_t zero_len = (size_t)(kIm2colWB - 1) * sw * C + 8;
-  const size_t smem = (size_t)Kpad * 2 + ((size_t)kt * kh * pitch + zero_len) * 2;
-  B2C_REQUIRE(smem <= 48 * 1024 && (size_t)kt * kh * pitch + zero_len < 65536 && Kpad / 8 <= 512, "im2col_small: footprint too large");
+  const size_t esz = b2c_precision() ? 4 : 2;
+  const size_t smem = (((size_t)Kpad * 2 + 15) & ~(size_t)15) + ((size_t)kt * kh * pitch + zero_len) * esz;
+  B2C_REQUIRE(smem <= 200 * 1024 && (size_t)kt * kh * pitch + zero_len < 65536 && Kpad / 8 <= 512, "im2col_small: footprint too large");
   const int strips = (Wo + kIm2colWB - 1) / kIm2colWB;
   const long long nblk = (long long)N * To * Ho * strips;
   const int vpr = Kpad / 8;
   const int threads = vpr * (320 / vpr > 0 ? 320 / vpr : 1);      // whole rows per sweep: 272 threads for Kpad = 1088
   B2C_REQUIRE(threads <= 512, "im2col_small: Kpad too large");
-  im2col_small_kernel<<<grid_for(nblk, 1, 24), threads, smem, (cudaStream_t)s>>>((const bf16*)x, (bf16*)out, G, strips, pitch);
+  if (b2c_precision()) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(im2col_small_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return b2c_cuda_check(e, "im2col_small: cudaFuncSetAttribute");
+      configured = true;
+    }
+    im2col_small_kernel<uint32_t><<<grid_for(nblk, 1, 8), threads, smem, (cudaStream_t)s>>>((const uint32_t*)x, (uint32_t*)out, G, strips, pitch);
+  } else {
+    B2C_REQUIRE(smem <= 48 * 1024, "im2col_small: footprint too large");
+    im2col_small_kernel<uint16_t><<<grid_for(nblk, 1, 24), threads, smem, (cudaStream_t)s>>>((const uint16_t*)x, (uint16_t*)out, G, strips, pitch);
+  }
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("im2col_small");
   return 0;

@@ -226,6 +226,10 @@ __device__ __forceinline__ void epi_fast(uint32_t taddr, const float* __restrict
   }
 }
 
+// kTF32: fp32 activations / weights read by the tensor core as tf32 (tcgen05.mma kind::tf32): a K-block is 32
+// channels (still 128 bytes per row), everything else -- tile bytes, swizzle, descriptor stepping (32 bytes per MMA
+// K step: 16 bf16 or 8 tf32) -- is identical, so the two precisions share this kernel.
+template <bool kTF32>
 __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __grid_constant__ b2c_conv_desc d,
                                                                        const __grid_constant__ TmaMaps maps,
                                                                        const __grid_constant__ OutMaps omaps,
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
   // K elements per tap in the packed weights.  TMA path: a multiple of 64 >= Cin -- the im2col box of the last channel
   // block reaches past Cin, where TMA zero-fills and the packed weights hold zeros.
   const int k_pitch = d.tap_pitch > 0 ? d.tap_pitch : d.Cin;
+  constexpr int kBK = kTF32 ? 32 : 64;                             // K elements (channels) per 128-byte K-block row
   const int a_bytes = MT * kATileBytes;
   const int stage_bytes = a_bytes + b_tile_bytes;
 
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     if (tid == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int cblocks = k_pitch / kBlockK;
+      const int cblocks = k_pitch / kBK;
       B2C_PROF_DECL(p_wait); B2C_PROF_DECL(p_t0); B2C_PROF_START(p_t0);
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(ts, d.nclass, t, n_tiles, s_fd[24], MT);
@@ -346,9 +351,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
             B2C_PROF_ACC(p_wait, w0);
             const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
             mbar_arrive_expect_tx(&ps->full[stage], (uint32_t)(nvalid * kATileBytes + b_tile_bytes));
-            tma_im2col_5d(a_st, map, &ps->full[stage], cb * kBlockK, bw[0], bh[0], bt[0], bn_i[0], ow, oh, ot);
+            tma_im2col_5d(a_st, map, &ps->full[stage], cb * kBK, bw[0], bh[0], bt[0], bn_i[0], ow, oh, ot);
             if (nvalid > 1)
-              tma_im2col_5d(a_st + kATileBytes, map, &ps->full[stage], cb * kBlockK, bw[1], bh[1], bt[1], bn_i[1], ow, oh, ot);
+              tma_im2col_5d(a_st + kATileBytes, map, &ps->full[stage], cb * kBK, bw[1], bh[1], bt[1], bn_i[1], ow, oh, ot);
             bulk_g2s(a_st + (uint32_t)a_bytes, wtile + (size_t)kb * b_tile_bytes, (uint32_t)b_tile_bytes, &ps->full[stage]);
             if (++stage == stages) {
               stage = 0;
@@ -359,8 +364,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       }
       B2C_PROF_PRINT2("producer(tma)", p_t0, p_wait, 0);
     }
-  } else if (warp < 4) {
-    // ------------------------------ gather producers (Cin not a multiple of 64) --------
+  } else if (warp < 4 && !kTF32) {
+    // ------------------------------ gather producers (Cin not a multiple of 64; bf16 only) --------
     const int r = tid;
     const bf16* in_n = reinterpret_cast<const bf16*>(d.in) + d.in_c_off;
     const uint32_t a_row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
@@ -460,8 +465,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       int bn = d.Cout - n0;
       if (bn > d.bn_tile) bn = d.bn_tile;
       const int bn16 = (bn + 15) & ~15;
-      const int nkb = (cc.ntaps * k_pitch + kBlockK - 1) / kBlockK;
-      const uint32_t idesc = umma_idesc_bf16(bn16, 0, 0);
+      const int nkb = (cc.ntaps * k_pitch + kBK - 1) / kBK;
+      const uint32_t idesc = kTF32 ? umma_idesc_tf32(bn16, 0, 0) : umma_idesc_bf16(bn16, 0, 0);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MT * acc_cols);
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
       const int nvalid = (MT > 1 && (unsigned)ti.m0 + (unsigned)kTileM < Mtot) ? 2 : 1;
@@ -481,17 +486,17 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
           const uint64_t ad0 = umma_desc_sw128(a_st, 16, 1024);
           const uint64_t bd0 = umma_desc_sw128(a_st + (uint32_t)a_bytes, 16, 1024);
           const uint32_t accf = kb > 0 ? 1u : 0u;
-          umma_bf16(tmem_d, ad0, bd0, idesc, accf);
-          umma_bf16(tmem_d, ad0 + 2, bd0 + 2, idesc, 1u);
-          umma_bf16(tmem_d, ad0 + 4, bd0 + 4, idesc, 1u);
-          umma_bf16(tmem_d, ad0 + 6, bd0 + 6, idesc, 1u);
+          umma_any<kTF32>(tmem_d, ad0, bd0, idesc, accf);
+          umma_any<kTF32>(tmem_d, ad0 + 2, bd0 + 2, idesc, 1u);
+          umma_any<kTF32>(tmem_d, ad0 + 4, bd0 + 4, idesc, 1u);
+          umma_any<kTF32>(tmem_d, ad0 + 6, bd0 + 6, idesc, 1u);
           if (nvalid > 1) {
             const uint64_t ad1 = ad0 + (kATileBytes >> 4);
             const uint32_t tmem_d1 = tmem_d + (uint32_t)acc_cols;
-            umma_bf16(tmem_d1, ad1, bd0, idesc, accf);
-            umma_bf16(tmem_d1, ad1 + 2, bd0 + 2, idesc, 1u);
-            umma_bf16(tmem_d1, ad1 + 4, bd0 + 4, idesc, 1u);
-            umma_bf16(tmem_d1, ad1 + 6, bd0 + 6, idesc, 1u);
+            umma_any<kTF32>(tmem_d1, ad1, bd0, idesc, accf);
+            umma_any<kTF32>(tmem_d1, ad1 + 2, bd0 + 2, idesc, 1u);
+            umma_any<kTF32>(tmem_d1, ad1 + 4, bd0 + 4, idesc, 1u);
+            umma_any<kTF32>(tmem_d1, ad1 + 6, bd0 + 6, idesc, 1u);
           }
           umma_commit(&ps->empty[stage]);
         }
@@ -676,6 +681,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
                   vv[0] += a.x; vv[1] += a.y; vv[2] += a.z; vv[3] += a.w;
                   vv[4] += b.x; vv[5] += b.y; vv[6] += b.z; vv[7] += b.w;
                 }
+                if (kTF32 && d.round_out) {   // the stored activation is the next GEMM's tf32 operand: round, do not truncate
+  #pragma unroll
+                  for (int i = 0; i < 8; ++i) vv[i] = tf32_rna(vv[i]);
+                }
                 o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
                 o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
               } else {
@@ -754,25 +763,36 @@ struct alignas(64) WgradMaps {
   CUtensorMap p;   // plain operand (same traversal, no taps)
 };
 
+// kTF32: fp32 tensors read as tf32.  The MN-major swizzle atom is 128 bytes of channels x 8 positions either way, so a
+// TMA box holds 64 channels x 64 positions of bf16 or 32 channels x 32 positions of fp32 (the tf32 K-block is 32
+// positions): stage bytes, LBO/SBO and the 4 MMAs per K-block stay the same, only the box geometry changes.
+template <bool kTF32>
 __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_constant__ b2c_wgrad_desc d,
                                                                const __grid_constant__ WgradMaps maps, int use_tma, int lo_t,
                                                                int lo_h, int lo_w, int stages, int lag, int nsplit, int MT) {
   // MT 128-column (tap, gc) tiles per CTA share ONE plain-operand tile per K-block (in-kernel timing r01: the MMA warp
   // waited on TMA data 52 % of the time at ~80 % of the L2 throughput cap; the plain tile is identical for all taps).
-  const int K = d.ntaps * d.Cg;            // GEMM-M extent ((tap, gc) columns of the im2col matrix)
+  constexpr int kCB = kTF32 ? 32 : 64;          // channels per box (= per 128-byte swizzle row)
+  constexpr int kPK = kTF32 ? 32 : 64;          // positions per K-block
+  constexpr int kBoxBytes = kPK * 128;          // one TMA box
+  constexpr int kSubs = kTileM / kCB;           // boxes per 128-column (tap, channel) tile
+  // TMA path: every tap owns ceil(Cg / kCB) channel blocks; the last one may reach past Cg, where TMA zero-fills
+  // (layers whose channel count is not a multiple of the box width; the epilogue skips those columns)
+  const int g_pitch = use_tma ? (d.Cg + kCB - 1) / kCB * kCB : d.Cg;
+  const int K = d.ntaps * g_pitch;         // GEMM-M extent ((tap, gc) columns of the im2col matrix)
   const int mk0 = blockIdx.x * MT * kTileM;     // first (tap,gc) column of this CTA
   const int n0 = blockIdx.y * d.bn_tile;   // first p-channel
   int bn = d.Cp - n0;
   if (bn > d.bn_tile) bn = d.bn_tile;
   const int bn16 = (bn + 15) & ~15;
   const long long Mtot = (long long)d.N * d.Qt * d.Qh * d.Qw;  // positions = GEMM-K extent
-  const long long nkb_all = (Mtot + kBlockK - 1) / kBlockK;
+  const long long nkb_all = (Mtot + kPK - 1) / kPK;
   const long long kb_lo = nkb_all * blockIdx.z / nsplit;
   const long long kb_hi = nkb_all * (blockIdx.z + 1) / nsplit;
   const int nkb = (int)(kb_hi - kb_lo);
   if (nkb <= 0) return;
-  const int b_atoms = (bn16 + 63) / 64;
-  const int b_tile_bytes = b_atoms * 8 * 1024;
+  const int b_atoms = (bn16 + kCB - 1) / kCB;
+  const int b_tile_bytes = b_atoms * kBoxBytes;
   const int a_bytes = MT * kATileBytes;
   const int stage_bytes = a_bytes + b_tile_bytes;
   int mt_here = (K - mk0 + kTileM - 1) / kTileM;     // valid tiles of this CTA
@@ -806,27 +826,27 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
     // ---- TMA producer: one thread; per stage 2 im2col boxes (64 positions x 64 channels) of the gathered operand for the
     // two 64-column halves of this CTA's 128 (tap, channel) columns, and bn/64 boxes of the plain operand
     if (tid == 0) {
-      const int cblocks = d.Cg / kBlockK;
-      constexpr int kMaxSub = 6;                     // MT <= 3 tiles x two 64-column halves
+      const int cblocks = g_pitch / kCB;
+      constexpr int kMaxSub = 3 * kSubs;             // MT <= 3 tiles x kSubs boxes
       int sub_c[kMaxSub];
       uint16_t sub_ow[kMaxSub], sub_oh[kMaxSub], sub_ot[kMaxSub];
       bool sub_ok[kMaxSub];
       int n_ok = 0;
 #pragma unroll
       for (int h = 0; h < kMaxSub; ++h) {
-        const int blk = blockIdx.x * MT * 2 + h;     // 64-column block index over (tap, channel block)
-        sub_ok[h] = h < 2 * MT && blk < d.ntaps * cblocks;
+        const int blk = blockIdx.x * MT * kSubs + h;     // box index over (tap, channel block)
+        sub_ok[h] = h < kSubs * MT && blk < d.ntaps * cblocks;
         const int tp = sub_ok[h] ? blk / cblocks : 0;
-        sub_c[h] = (blk - tp * cblocks) * kBlockK;
+        sub_c[h] = (blk - tp * cblocks) * kCB;
         const int32_t tv = __ldg(d.taps + tp);
         sub_ow[h] = (uint16_t)(tap_dw(tv) - lo_w);
         sub_oh[h] = (uint16_t)(tap_dh(tv) - lo_h);
         sub_ot[h] = (uint16_t)(tap_dt(tv) - lo_t);
         n_ok += sub_ok[h] ? 1 : 0;
       }
-      const int nb = (bn16 + 63) / 64;
-      const uint32_t tx = (uint32_t)((n_ok + nb) * 8192);
-      long long pos = kb_lo * kBlockK;
+      const int nb = b_atoms;
+      const uint32_t tx = (uint32_t)((n_ok + nb) * kBoxBytes);
+      long long pos = kb_lo * kPK;
       int n_i, qt, qh, qw;
       {
         unsigned q = (unsigned)pos;
@@ -849,11 +869,11 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
 #pragma unroll
         for (int h = 0; h < kMaxSub; ++h)
           if (sub_ok[h])
-            tma_im2col_5d(a_st + h * 8192, &maps.g, &ps->full[stage], sub_c[h], gw, gh, gt, n_i, sub_ow[h], sub_oh[h], sub_ot[h]);
+            tma_im2col_5d(a_st + h * kBoxBytes, &maps.g, &ps->full[stage], sub_c[h], gw, gh, gt, n_i, sub_ow[h], sub_oh[h], sub_ot[h]);
         for (int j = 0; j < nb; ++j)
-          tma_im2col_5d(b_st + j * 8192, &maps.p, &ps->full[stage], n0 + j * 64, qw * d.sp_w + d.pp_w, qh * d.sp_h + d.pp_h,
+          tma_im2col_5d(b_st + j * kBoxBytes, &maps.p, &ps->full[stage], n0 + j * kCB, qw * d.sp_w + d.pp_w, qh * d.sp_h + d.pp_h,
                         qt * d.sp_t + d.pp_t, n_i, 0, 0, 0);
-        qw += kBlockK;
+        qw += kPK;
         while (qw >= d.Qw) {
           qw -= d.Qw;
           if (++qh == d.Qh) {
@@ -871,8 +891,8 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
       }
       if (blockIdx.y == 0 && blockIdx.z == 0) { B2C_PROF_PRINTW("wgrad producer", p_t0, p_wait, nkb); }
     }
-  } else if (warp < 4) {
-    // gather producers: thread -> position row r (0..63) and half (0/1) of the chunk columns
+  } else if (warp < 4 && !kTF32) {
+    // gather producers (bf16 only): thread -> position row r (0..63) and half (0/1) of the chunk columns
     const int r = tid & 63;
     const int half = tid >> 6;
     // fixed (tap, channel) of this thread's 8 A chunks
@@ -980,8 +1000,8 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
       bool rvalid = kcol < K;
       long long base = 0;
       if (rvalid) {
-        const int tp = kcol / d.Cg;
-        const int gc = kcol - tp * d.Cg;
+        const int tp = kcol / g_pitch;
+        const int gc = kcol - tp * g_pitch;
         rvalid = gc < d.Cg_real;
         base = (long long)gc * d.s_g + __ldg(d.wtap + tp);
       }
@@ -1007,7 +1027,9 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
     tc_fence_before();
     if (tid == 0 && blockIdx.y == 0 && blockIdx.z == 0) { B2C_PROF_PRINTW("wgrad epilogue", e_t0, 0, nkb); }
   } else {
-    const uint32_t idesc = umma_idesc_bf16(bn16, 1, 1);
+    const uint32_t idesc = kTF32 ? umma_idesc_tf32(bn16, 1, 1) : umma_idesc_bf16(bn16, 1, 1);
+    // descriptor start-address step per MMA (16-byte units): 16 positions x 128 B (bf16, K = 16) or 8 x 128 B (tf32, K = 8)
+    constexpr uint32_t kStep = kTF32 ? 64u : 128u;
     int stage = 0;
     uint32_t phase = 0;
     B2C_PROF_DECL(m_wait); B2C_PROF_DECL(m_t0); B2C_PROF_START(m_t0);
@@ -1019,18 +1041,18 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
       if (lane == 0) {
         const uint32_t a_st = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t b_st = a_st + (uint32_t)a_bytes;
-        // MN-major SW128: LBO = stride between 64-element MN atoms (8 KB), SBO = stride between 8-position groups.
-        // Only the start-address field (16-byte units) changes: +128 per 16-position K step, +1024 per 16 KB A tile.
-        const uint64_t ad0 = umma_desc_sw128(a_st, 8192, 1024);
-        const uint64_t bd0 = umma_desc_sw128(b_st, 8192, 1024);
+        // MN-major SW128: LBO = stride between MN atoms (= one box), SBO = stride between 8-position groups (1 KB).
+        // Only the start-address field (16-byte units) changes: +kStep per MMA K step, +1024 per 16 KB A tile.
+        const uint64_t ad0 = umma_desc_sw128(a_st, kBoxBytes, 1024);
+        const uint64_t bd0 = umma_desc_sw128(b_st, kBoxBytes, 1024);
         const uint32_t accf = i > 0 ? 1u : 0u;
         for (int jt = 0; jt < mt_here; ++jt) {
           const uint64_t ad = ad0 + (uint64_t)(jt * (kATileBytes >> 4));
           const uint32_t td = tmem_d + (uint32_t)(jt * bn16);
-          umma_bf16(td, ad, bd0, idesc, accf);
-          umma_bf16(td, ad + 128, bd0 + 128, idesc, 1u);
-          umma_bf16(td, ad + 256, bd0 + 256, idesc, 1u);
-          umma_bf16(td, ad + 384, bd0 + 384, idesc, 1u);
+          umma_any<kTF32>(td, ad, bd0, idesc, accf);
+          umma_any<kTF32>(td, ad + kStep, bd0 + kStep, idesc, 1u);
+          umma_any<kTF32>(td, ad + 2 * kStep, bd0 + 2 * kStep, idesc, 1u);
+          umma_any<kTF32>(td, ad + 3 * kStep, bd0 + 3 * kStep, idesc, 1u);
         }
         umma_commit(&ps->empty[stage]);
       }
@@ -1055,11 +1077,28 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
 // fp32 master weights -> bf16 GEMM operand tiles in exactly the shared-memory image the fprop kernel wants:
 // [n-tile][k-block][row (bn_tile)][64 K-elements] with the 128-byte swizzle already applied, so a stage's
 // weight tile is ONE contiguous bulk copy.  k = t*tap_pitch + col_off + c ; global row = r + r_off.
-__global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ packed, const int32_t* __restrict__ wtap,
+// kTF32: fp32 elements rounded to tf32, 32 K-elements per 128-byte row (16-byte swizzle chunk = 4 elements).
+template <bool kTF32>
+__device__ __forceinline__ void pack_store(void* packed, long long tile_base_rows, int rr, long long k, float v, int bn_tile, int nkb,
+                                           int tile) {
+  if (kTF32) {
+    const int kb = (int)(k >> 5), kk = (int)(k & 31);
+    const long long off = ((long long)tile * nkb + kb) * ((long long)bn_tile * 32) + (rr >> 3) * 256 + (rr & 7) * 32 +
+                          (((kk >> 2) ^ (rr & 7)) << 2) + (kk & 3);
+    reinterpret_cast<float*>(packed)[off] = tf32_rna(v);
+  } else {
+    const int kb = (int)(k >> 6), kk = (int)(k & 63);
+    const long long off = ((long long)tile * nkb + kb) * ((long long)bn_tile * 64) + (rr >> 3) * 512 + (rr & 7) * 64 +
+                          (((kk >> 3) ^ (rr & 7)) << 3) + (kk & 7);
+    reinterpret_cast<bf16*>(packed)[off] = __float2bfloat16(v);
+  }
+}
+
+template <bool kTF32>
+__global__ void pack_weights_kernel(const float* __restrict__ w, void* __restrict__ packed, const int32_t* __restrict__ wtap,
                                     int R, int ntaps, int C, int C_real, long long s_r, long long s_c, long long tap_pitch,
                                     long long col_off, int r_off, int bn_tile, int nkb) {
   const long long total = (long long)R * ntaps * C;
-  const long long tile_elems = (long long)bn_tile * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long t2 = i / C;
@@ -1070,10 +1109,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, bf16* __restric
     const int rg = r + r_off;
     const int tile = rg / bn_tile, rr = rg - tile * bn_tile;
     const long long k = (long long)t * tap_pitch + col_off + c;
-    const int kb = (int)(k >> 6), kk = (int)(k & 63);
-    const long long off = ((long long)tile * nkb + kb) * tile_elems + (rr >> 3) * 512 + (rr & 7) * 64 +
-                          (((kk >> 3) ^ (rr & 7)) << 3) + (kk & 7);
-    packed[off] = __float2bfloat16(v);
+    pack_store<kTF32>(packed, 0, rr, k, v, bn_tile, nkb, tile);
   }
 }
 
@@ -1095,27 +1131,27 @@ EncodeIm2colFn get_encode_im2col() {
 // im2col tensor map over a channels-last bf16 view (C, W, H, T, N).  The bounding box of BASE pixels is
 // [lo, lo + (Q-1)*stride] per spatial dim (corner arrays in W,H,D order, like CUTLASS); filter taps are passed as
 // non-negative offsets (d_tap - lo) in the instruction.  Out-of-tensor reads are zero filled (= padding).
-int encode_im2col_map(CUtensorMap* map, const bf16* base, int C, long long row_stride, int N, int T, int H, int W, int lo_t,
-                      int lo_h, int lo_w, int Qt, int Qh, int Qw, int st, int sh, int sw, int channels, int pixels) {
+int encode_im2col_map(CUtensorMap* map, const void* base, int C, long long row_stride, int N, int T, int H, int W, int lo_t,
+                      int lo_h, int lo_w, int Qt, int Qh, int Qw, int st, int sh, int sw, int channels, int pixels, int esz = 2) {
   EncodeIm2colFn fn = get_encode_im2col();
   if (!fn) return b2c_fail(-2, "cuTensorMapEncodeIm2col entry point not available in this driver");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)N};
-  cuuint64_t strides[4] = {(cuuint64_t)row_stride * 2, (cuuint64_t)row_stride * 2 * W, (cuuint64_t)row_stride * 2 * W * H,
-                           (cuuint64_t)row_stride * 2 * W * H * T};
+  const cuuint64_t rsb = (cuuint64_t)row_stride * (cuuint64_t)esz;      // bytes per pixel row
+  cuuint64_t strides[4] = {rsb, rsb * W, rsb * W * H, rsb * W * H * T};
   int lower[3] = {lo_w, lo_h, lo_t};
   int upper[3] = {lo_w + (Qw - 1) * sw - (W - 1), lo_h + (Qh - 1) * sh - (H - 1), lo_t + (Qt - 1) * st - (T - 1)};
   for (int i = 0; i < 3; ++i)
     if (lower[i] < -16 || lower[i] > 15 || upper[i] < -16 || upper[i] > 15)
       return b2c_fail(-1, "im2col corner out of range: lower %d upper %d (dim %d)", lower[i], upper[i], i);
   cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)st, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, lower, upper,
+  CUresult r = fn(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, lower, upper,
                   (cuuint32_t)channels, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return b2c_fail(-3, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
   // CUTLASS (copy_traits_sm90_im2col.hpp) clears this descriptor bit for tensors < 128 KiB on drivers <= 13.1
   static int drv = -1;
   if (drv < 0) cudaDriverGetVersion(&drv);
-  const unsigned long long bytes = (unsigned long long)row_stride * 2ull * W * H * T * N;
+  const unsigned long long bytes = (unsigned long long)rsb * W * H * T * N;
   if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
   return 0;
 }
@@ -1162,12 +1198,11 @@ __global__ void pack_weights_batched_kernel(const b2c_pack_job* __restrict__ job
   const int nblk = block_start[lo + 1] - block_start[lo];
   const int bidx = blockIdx.x - block_start[lo];
   const float* __restrict__ w = reinterpret_cast<const float*>(J.w);
-  bf16* __restrict__ packed = reinterpret_cast<bf16*>(J.packed);
+  void* __restrict__ packed = J.packed;
   const int32_t* __restrict__ wtap = J.wtap;
   // (host guarantees R * ntaps * C < 2^31: 32-bit index arithmetic)
   const unsigned total = (unsigned)J.R * (unsigned)J.ntaps * (unsigned)J.C;
   const unsigned C = (unsigned)J.C, ntaps = (unsigned)J.ntaps, bn = (unsigned)J.bn_tile;
-  const long long tile_elems = (long long)J.bn_tile * 64;
   for (unsigned i = (unsigned)bidx * blockDim.x + threadIdx.x; i < total; i += (unsigned)nblk * blockDim.x) {
     const unsigned t2 = i / C, c = i - t2 * C;
     const unsigned r = t2 / ntaps, t = t2 - r * ntaps;
@@ -1176,10 +1211,8 @@ __global__ void pack_weights_batched_kernel(const b2c_pack_job* __restrict__ job
     const unsigned rg = r + (unsigned)J.r_off;
     const unsigned tile = rg / bn, rr = rg - tile * bn;
     const long long k = (long long)t * J.tap_pitch + J.col_off + c;
-    const int kb = (int)(k >> 6), kk = (int)(k & 63);
-    const long long off = ((long long)tile * J.nkb + kb) * tile_elems + (rr >> 3) * 512 + (rr & 7) * 64 +
-                          (((kk >> 3) ^ (rr & 7)) << 3) + (kk & 7);
-    packed[off] = __float2bfloat16(v);
+    if (J.dtype) pack_store<true>(packed, 0, (int)rr, k, v, J.bn_tile, J.nkb, (int)tile);
+    else pack_store<false>(packed, 0, (int)rr, k, v, J.bn_tile, J.nkb, (int)tile);
   }
 }
 
@@ -1232,9 +1265,14 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   }
   if (tiles128 == 0) return 0;
   const int k_pitch = d.tap_pitch > 0 ? d.tap_pitch : d.Cin;
-  B2C_REQUIRE(k_pitch >= d.Cin && (k_pitch == d.Cin || (k_pitch % kBlockK == 0 && k_pitch - d.Cin < kBlockK)),
-              "conv_fprop: tap_pitch=%d must be Cin=%d or Cin rounded up to a multiple of 64", d.tap_pitch, d.Cin);
-  const int use_tma = (k_pitch % kBlockK == 0) ? 1 : 0;
+  const int tf32 = d.dtype == 1 ? 1 : 0;
+  B2C_REQUIRE(d.dtype == 0 || d.dtype == 1, "conv_fprop: dtype=%d", d.dtype);
+  const int bk = tf32 ? 32 : kBlockK;         // K elements per 128-byte K-block row
+  const int esz = tf32 ? 4 : 2;
+  B2C_REQUIRE(k_pitch >= d.Cin && (k_pitch == d.Cin || (k_pitch % bk == 0 && k_pitch - d.Cin < bk)),
+              "conv_fprop: tap_pitch=%d must be Cin=%d or Cin rounded up to a multiple of %d", d.tap_pitch, d.Cin, bk);
+  const int use_tma = (k_pitch % bk == 0) ? 1 : 0;
+  B2C_REQUIRE(!tf32 || (use_tma && d.out_fp32 != 0), "conv_fprop: tf32 mode needs tap_pitch %% 32 == 0 and an fp32 output");
   const int acc_cols = (d.bn_tile + 15) & ~15;
   const int b_tile_bytes_h = ((acc_cols * 128) + 1023) & ~1023;
   const int staging = kStagingBytes + 16;
@@ -1271,7 +1309,9 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(igemm_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
     if (e != cudaSuccess) return b2c_cuda_check(e, "conv_fprop: cudaFuncSetAttribute");
     configured = true;
   }
@@ -1280,8 +1320,9 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   if (use_tma) {
     for (int i = 0; i < d.nclass; ++i) {
       const b2c_conv_class& c = d.cls[i];
-      int rc = encode_im2col_map(&maps.a[i], reinterpret_cast<const bf16*>(d.in) + d.in_c_off, d.Cin, d.in_row_stride, d.N, d.Ti,
-                                 d.Hi, d.Wi, c.lo_t, c.lo_h, c.lo_w, c.Qt, c.Qh, c.Qw, d.si_t, d.si_h, d.si_w, kBlockK, kTileM);
+      int rc = encode_im2col_map(&maps.a[i], reinterpret_cast<const uint8_t*>(d.in) + (size_t)d.in_c_off * esz, d.Cin,
+                                 d.in_row_stride, d.N, d.Ti, d.Hi, d.Wi, c.lo_t, c.lo_h, c.lo_w, c.Qt, c.Qh, c.Qw, d.si_t, d.si_h,
+                                 d.si_w, bk, kTileM, esz);
       if (rc) return rc;
     }
   }
@@ -1328,8 +1369,12 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   // alternating between two of them (148 % 8 == 4)
   if (ts.interleave && (grid & 1) == 0) --grid;
   if (grid > total_tiles) grid = total_tiles;
-  igemm_fprop_kernel<<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, omaps, ts, use_tma, stages, lag,
-                                                                                    total_tiles, n_tiles, sum_taps, store_mode, piece, MT);
+  if (tf32)
+    igemm_fprop_kernel<true><<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, omaps, ts, use_tma, stages, lag,
+                                                                                            total_tiles, n_tiles, sum_taps, store_mode, piece, MT);
+  else
+    igemm_fprop_kernel<false><<<(unsigned)grid, kFpropThreads, smem, (cudaStream_t)stream>>>(d, maps, omaps, ts, use_tma, stages, lag,
+                                                                                             total_tiles, n_tiles, sum_taps, store_mode, piece, MT);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_fprop launch");
   return 0;
@@ -1360,13 +1405,28 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_wgrad: bn_tile=%d invalid", d.bn_tile);
   const long long Mtot = (long long)d.N * d.Qt * d.Qh * d.Qw;
   if (Mtot == 0) return 0;
-  const int K = d.ntaps * d.Cg;
+  B2C_REQUIRE(d.dtype == 0 || d.dtype == 1, "conv_wgrad: dtype=%d", d.dtype);
+  const int tf32 = d.dtype == 1 ? 1 : 0;
+  const int esz = tf32 ? 4 : 2;
+  const int cb = tf32 ? 32 : 64;           // channels per TMA box (128-byte swizzle row)
+  const int pk = tf32 ? 32 : 64;           // positions per K-block
+  const int box_bytes = pk * 128;
+  // TMA path whenever the host tap table is there: channel counts that are not multiples of the box width are handled by
+  // TMA's zero fill past the tensor extent (B2C_TMA_TAIL=0 restores the cp.async gather path for those layers)
+  static int tail = -1;
+  if (tail < 0) {
+    const char* e = getenv("B2C_TMA_TAIL");
+    tail = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const int use_tma = (d.taps_host != nullptr && (tail || tf32 || (d.Cg % cb == 0 && d.Cp % cb == 0))) ? 1 : 0;
+  B2C_REQUIRE(!tf32 || use_tma, "conv_wgrad: tf32 mode needs the host tap table (TMA path)");
+  const int g_pitch = use_tma ? (d.Cg + cb - 1) / cb * cb : d.Cg;
+  const int K = d.ntaps * g_pitch;
   const int mt = (K + kTileM - 1) / kTileM;
   const int nt = (d.Cp + d.bn_tile - 1) / d.bn_tile;
-  const long long nkb = (Mtot + kBlockK - 1) / kBlockK;
+  const long long nkb = (Mtot + pk - 1) / pk;
   const int bn16 = (d.bn_tile + 15) & ~15;
-  const int b_tile_bytes = ((bn16 + 63) / 64) * 8 * 1024;
-  const int use_tma = (d.Cg % kBlockK == 0 && d.Cp % kBlockK == 0 && d.taps_host != nullptr) ? 1 : 0;
+  const int b_tile_bytes = ((bn16 + cb - 1) / cb) * box_bytes;
   // (tap, gc) tiles per CTA sharing one plain-operand tile: as many as TMEM (512 columns) and >= 3 pipeline stages allow
   int MT = 1;
   if (use_tma) {
@@ -1403,7 +1463,9 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + sizeof(PipeSmem) + 1024 + 64;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(igemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     if (e != cudaSuccess) return b2c_cuda_check(e, "conv_wgrad: cudaFuncSetAttribute");
     configured = true;
   }
@@ -1419,15 +1481,18 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
       for (int k = 0; k < 3; ++k)
         if (v[k] < lo[k]) lo[k] = v[k];
     }
-    int rc = encode_im2col_map(&maps.g, reinterpret_cast<const bf16*>(d.g) + d.g_c_off, d.Cg, d.g_row_stride, d.N, d.Tg, d.Hg, d.Wg,
-                               lo[0], lo[1], lo[2], d.Qt, d.Qh, d.Qw, d.sg_t, d.sg_h, d.sg_w, kBlockK, kBlockK);
+    int rc = encode_im2col_map(&maps.g, reinterpret_cast<const uint8_t*>(d.g) + (size_t)d.g_c_off * esz, d.Cg, d.g_row_stride, d.N,
+                               d.Tg, d.Hg, d.Wg, lo[0], lo[1], lo[2], d.Qt, d.Qh, d.Qw, d.sg_t, d.sg_h, d.sg_w, cb, pk, esz);
     if (rc) return rc;
-    rc = encode_im2col_map(&maps.p, reinterpret_cast<const bf16*>(d.p) + d.p_c_off, d.Cp, d.p_row_stride, d.N, d.Tp, d.Hp, d.Wp,
-                           d.pp_t, d.pp_h, d.pp_w, d.Qt, d.Qh, d.Qw, d.sp_t, d.sp_h, d.sp_w, kBlockK, kBlockK);
+    rc = encode_im2col_map(&maps.p, reinterpret_cast<const uint8_t*>(d.p) + (size_t)d.p_c_off * esz, d.Cp, d.p_row_stride, d.N, d.Tp,
+                           d.Hp, d.Wp, d.pp_t, d.pp_h, d.pp_w, d.Qt, d.Qh, d.Qw, d.sp_t, d.sp_h, d.sp_w, cb, pk, esz);
     if (rc) return rc;
   }
   dim3 grid((unsigned)mtc, (unsigned)nt, (unsigned)nsplit);
-  igemm_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit, MT);
+  if (tf32)
+    igemm_wgrad_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit, MT);
+  else
+    igemm_wgrad_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit, MT);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_wgrad launch");
   return 0;
@@ -1440,13 +1505,19 @@ B2C_API int b2c_pack_weights(const float* w, void* packed, const int32_t* wtap, 
   B2C_REQUIRE(R > 0 && ntaps > 0 && C > 0 && C_real > 0 && C_real <= C, "pack_weights: bad dims");
   B2C_REQUIRE(bn_tile > 0 && bn_tile % 16 == 0 && bn_tile <= 256 && nkb > 0, "pack_weights: bad tiling bn_tile=%d nkb=%d", bn_tile, nkb);
   if (tap_pitch <= 0) tap_pitch = C;
-  B2C_REQUIRE(((int64_t)(ntaps - 1) * tap_pitch + col_off + C + 63) / 64 <= nkb, "pack_weights: K exceeds nkb");
+  const int tf32 = b2c_precision();       // process-wide: the packed operand type follows the activation precision mode
+  const int bk = tf32 ? 32 : 64;
+  B2C_REQUIRE(((int64_t)(ntaps - 1) * tap_pitch + col_off + C + bk - 1) / bk <= nkb, "pack_weights: K exceeds nkb");
   const long long total = (long long)R * ntaps * C;
   int blocks = (int)((total + 255) / 256);
   const int cap = b2c_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<bf16*>(packed), wtap, R, ntaps, C, C_real,
-                                                               s_r, s_c, tap_pitch, col_off, r_off, bn_tile, nkb);
+  if (tf32)
+    pack_weights_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, packed, wtap, R, ntaps, C, C_real, s_r, s_c, tap_pitch,
+                                                                       col_off, r_off, bn_tile, nkb);
+  else
+    pack_weights_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, packed, wtap, R, ntaps, C, C_real, s_r, s_c, tap_pitch,
+                                                                        col_off, r_off, bn_tile, nkb);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("pack_weights launch");
   return 0;

@@ -472,7 +472,19 @@ __global__ void class_mean_kernel(const float* __restrict__ rout, float* __restr
   }
 }
 
-__global__ void pose_mask_kernel(const float* __restrict__ rout, const float* __restrict__ mask, bf16* __restrict__ x, int L, int C,
+// store 8 activation values as the current precision mode's storage type (fp32: rounded to tf32 -- GEMM operand)
+template <typename T>
+__device__ __forceinline__ void store8_act(T* p, const float* v);
+template <>
+__device__ __forceinline__ void store8_act<bf16>(bf16* p, const float* v) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+template <>
+__device__ __forceinline__ void store8_act<float>(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(tf32_rna(v[0]), tf32_rna(v[1]), tf32_rna(v[2]), tf32_rna(v[3]));
+  reinterpret_cast<float4*>(p)[1] = make_float4(tf32_rna(v[4]), tf32_rna(v[5]), tf32_rna(v[6]), tf32_rna(v[7]));
+}
+
+template <typename T>
+__global__ void pose_mask_kernel(const float* __restrict__ rout, const float* __restrict__ mask, T* __restrict__ x, int L, int C,
                                  long long total) {
   const int ocols = C * 17, pc = C * 16;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -484,11 +496,12 @@ __global__ void pose_mask_kernel(const float* __restrict__ rout, const float* __
     float v[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = src[q] * m;
-    *reinterpret_cast<uint4*>(x + row * pc + e * 8) = pack8(v);
+    store8_act(x + row * pc + e * 8, v);
   }
 }
 
-__global__ void caps_head_bwd_kernel(const bf16* __restrict__ dx, const float* __restrict__ mask, const float* __restrict__ dact,
+template <typename T>
+__global__ void caps_head_bwd_kernel(const T* __restrict__ dx, const float* __restrict__ mask, const float* __restrict__ dact,
                                      const float* __restrict__ dfeat, float* __restrict__ drout, int L, int C, long long rows) {
   const int ocols = C * 17, pc = C * 16;
   const long long total = rows * ocols;
@@ -498,7 +511,7 @@ __global__ void caps_head_bwd_kernel(const bf16* __restrict__ dx, const float* _
     const int n = (int)(row / L);
     float v;
     if (col < pc) {
-      v = dx ? __bfloat162float(dx[row * pc + col]) * mask[n * C + col / 16] : 0.f;
+      v = dx ? (float)dx[row * pc + col] * mask[n * C + col / 16] : 0.f;
     } else {
       const int j = col - pc;
       v = (dact ? dact[n * C + j] / (float)L : 0.f) + (dfeat ? dfeat[row * C + j] : 0.f);
@@ -509,8 +522,9 @@ __global__ void caps_head_bwd_kernel(const bf16* __restrict__ dx, const float* _
 
 // PrimaryCaps backward prologue: g fp32 (rows, 544) is the gradient w.r.t. [poses | sigmoid(act)];
 // dz = g * (col >= 512 ? a (1 - a) : 1) as bf16 rows for the dgrad / wgrad GEMMs, dbias[col] += sum_rows dz.
+template <typename T>
 __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* __restrict__ g, const float* __restrict__ out,
-                                                                   bf16* __restrict__ dz, float* __restrict__ dbias, long long rows, int dz_pitch) {
+                                                                   T* __restrict__ dz, float* __restrict__ dbias, long long rows, int dz_pitch) {
   // block = 256 threads: 4 row lanes x 68 column groups of 8 (544 = 68 * 8); threads >= 272 idle
   const int cg = threadIdx.x % 68, rl = threadIdx.x / 68;
   const bool act = rl < 3;
@@ -533,7 +547,7 @@ __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
-      *reinterpret_cast<uint4*>(dz + r * dz_pitch + cg * 8) = pack8(v);
+      store8_act(dz + r * dz_pitch + cg * 8, v);
     }
   }
   __shared__ float sh[544];
@@ -603,7 +617,8 @@ B2C_API int b2c_pose_mask_fwd(const float* rout, const float* mask, void* x, int
   B2C_REQUIRE(rout && mask && x && N > 0 && C > 0, "pose_mask_fwd: bad args");
   const long long total = (long long)N * L * (C * 16 / 8);
   int blocks = (int)((total + 255) / 256);
-  pose_mask_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(rout, mask, (bf16*)x, L, C, total);
+  if (b2c_precision()) pose_mask_kernel<float><<<blocks, 256, 0, (cudaStream_t)s>>>(rout, mask, (float*)x, L, C, total);
+  else pose_mask_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)s>>>(rout, mask, (bf16*)x, L, C, total);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("pose_mask_fwd");
   return 0;
@@ -617,7 +632,10 @@ B2C_API int b2c_caps_head_bwd(const void* dx, const float* mask, const float* da
   int blocks = (int)((total + 255) / 256);
   const int cap = b2c_num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  caps_head_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>((const bf16*)dx, mask, dact, dfeat, drout, L, C, rows);
+  if (b2c_precision())
+    caps_head_bwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)s>>>((const float*)dx, mask, dact, dfeat, drout, L, C, rows);
+  else
+    caps_head_bwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)s>>>((const bf16*)dx, mask, dact, dfeat, drout, L, C, rows);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("caps_head_bwd");
   return 0;
@@ -629,7 +647,10 @@ B2C_API int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz,
   long long blocks = (rows + 2) / 3;
   const long long cap = (long long)b2c_num_sms() * 4;
   if (blocks > cap) blocks = cap;
-  primarycaps_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows, dz_pitch);
+  if (b2c_precision())
+    primarycaps_bwd_prep_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (float*)dz, dbias, rows, dz_pitch);
+  else
+    primarycaps_bwd_prep_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows, dz_pitch);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("primarycaps_bwd_prep");
   return 0;

@@ -30,6 +30,16 @@ def setup():
     return dict(model=model, sd=sd, batch=batch, masks=masks, engine=engine, restate=restate)
 
 
+@pytest.fixture
+def precision(request):
+    """Activation / GEMM-operand precision mode of the CUDA path for one test (restored to bf16 afterwards).
+    tf32 = fp32 activations + tcgen05 kind::tf32: the mode the north_star 1e-3 bar applies to."""
+    from b200caps import plans
+    plans.set_precision(request.param)
+    yield request.param
+    plans.set_precision("bf16")
+
+
 def _inject(engine, masks):
     it = iter(masks)
     engine.STATE.dropout_source = lambda n, c, dev: next(it).reshape(n, c)
@@ -55,8 +65,11 @@ def _cl2ncdhw(t):
     return t.detach().float().permute(0, 4, 1, 2, 3).double().cpu()
 
 
-def test_train_mode_segment_parity(setup):
-    """Train mode (batch-stat BN, injected Dropout3d masks), bf16 mode, against the fp64 oracle.
+@pytest.mark.parametrize("precision", ["bf16", "tf32"], indirect=True)
+def test_train_mode_segment_parity(setup, precision):
+    """Train mode (batch-stat BN, injected Dropout3d masks), both precision modes, against the fp64 oracle.
+    Every bound below is written T(bf16 bound, tf32 bound); the tf32 bounds are the north_star fp32-mode bar (1e-3) for
+    the per-segment forwards and a small multiple of it for gradients (noise-like sums, see below).
 
     The EM routing is chaotically sensitive at random init: bf16 rounding upstream moves the logits by O(1) in the
     REFERENCE ITSELF (oracle with emulated bf16 roundings vs exact: logits 0.59, feat 0.36).  Parity
@@ -64,6 +77,9 @@ def test_train_mode_segment_parity(setup):
     (2e-2 max-abs normalised); the end-to-end deviation is measured and printed next to the oracle's own."""
     s = setup
     model, sd, b, masks, engine, restate = s["model"], s["sd"], s["batch"], s["masks"], s["engine"], s["restate"]
+    tf32 = precision == "tf32"
+    T = lambda bf, tf: tf if tf32 else bf
+    emulate = restate.emulate_tf32 if tf32 else restate.emulate_bf16
     model.train()
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     for p in model.parameters():
@@ -83,7 +99,7 @@ def test_train_mode_segment_parity(setup):
     # activations).  Train-mode BatchNorm over a 2-clip batch amplifies bf16 rounding ~30x by Mixed_4f in the
     # reference itself (exact fp64 vs bf16-rounded reference: x 1.9e-1); that deviation is printed, not asserted.
     bn = restate.BNState(True)
-    with restate.emulate_bf16():
+    with emulate():
         x_ref, c56_ref, c112_ref = restate.encode(sd64, b["data"].double(), m64[0], bn)
     with torch.no_grad():
         x_ex, c56_ex, c112_ex = restate.encode({k: v.detach() for k, v in sd64.items()}, b["data"].double(), m64[0],
@@ -92,21 +108,22 @@ def test_train_mode_segment_parity(setup):
              c112=rel(_cl2ncdhw(c112), c112_ref.detach()))
     e_ex = dict(x=rel(_cl2ncdhw(x_cl)[:, :, 0], x_ex), c56=rel(_cl2ncdhw(c56), c56_ex), c112=rel(_cl2ncdhw(c112), c112_ex))
     o_ex = dict(x=rel(x_ref.detach(), x_ex), c56=rel(c56_ref.detach(), c56_ex), c112=rel(c112_ref.detach(), c112_ex))
-    print("encoder vs oracle(bf16 roundings):", e)
-    print("encoder vs exact fp64 oracle     :", e_ex)
-    print("oracle(bf16 roundings) vs exact  :", o_ex)
+    print(f"[{precision}] encoder vs oracle(same roundings):", e)
+    print(f"[{precision}] encoder vs exact fp64 oracle     :", e_ex)
+    print(f"[{precision}] oracle(same roundings) vs exact  :", o_ex)
     # shallow taps: within the bf16 tolerance of the exact oracle.  The deep tap (17 conv+BN layers) is compared
     # with the rounding-emulated oracle; accumulation-order differences flip bf16 roundings and train-mode BN over a
     # 2-clip batch amplifies them, so its max-norm bound is loose and an L2 bound is added.
-    assert e_ex["c112"] < 2e-2 and e_ex["c56"] < 2e-2 and e["c112"] < 2e-2 and e["c56"] < 2e-2, (e, e_ex)
+    bar = T(2e-2, 1e-3)
+    assert e_ex["c112"] < bar and e_ex["c56"] < bar and e["c112"] < bar and e["c56"] < bar, (e, e_ex)
     xa, xb = _cl2ncdhw(x_cl)[:, :, 0], x_ref.detach()
     l2 = float((xa - xb).norm() / xb.norm())
     print(f"encoder deep tap: max-norm {e['x']:.2e}, relative L2 {l2:.2e} (vs oracle with bf16 roundings)")
-    assert e["x"] < 0.2 and l2 < 0.1, (e, l2)
+    assert e["x"] < T(0.2, 2.5e-2) and l2 < T(0.1, 1.2e-2), (e, l2)
     new_sd = model.state_dict()
     worst = max(max(rel(new_sd[p + ".bn.running_mean"], rm), rel(new_sd[p + ".bn.running_var"], rv))
                 for p, (rm, rv) in bn.updates.items())
-    assert worst < 2e-2, worst
+    assert worst < T(2e-2, 1e-3), worst
     # encoder gradients through a linear probe of the three taps
     g = torch.Generator().manual_seed(9)
     w1 = torch.randn(x_ref.shape, generator=g, dtype=torch.float64)
@@ -134,15 +151,15 @@ def test_train_mode_segment_parity(setup):
     x_in = _cl2ncdhw(x_cl)[:, :, 0].requires_grad_(True)
     caps_ref = restate.primary_caps(x_in, sd64)
     e_caps = rel(caps, caps_ref.detach())
-    print(f"primary caps (same input): {e_caps:.2e}")
-    assert e_caps < 1e-2
+    print(f"[{precision}] primary caps (same input): {e_caps:.2e}")
+    assert e_caps < T(1e-2, 1e-3)
     wc = torch.randn(caps_ref.shape, generator=g, dtype=torch.float64)
     pc_names = [k for k in sd64 if k.startswith("primary_caps.")]
     gref = torch.autograd.grad((caps_ref * wc).sum(), [sd64[k] for k in pc_names] + [x_in])
     (caps * wc.float().cuda()).sum().backward(retain_graph=True)
     for k, gr in zip(pc_names, gref[:-1]):
-        assert rel(gp[k].grad, gr) < 3e-2, (k, rel(gp[k].grad, gr))
-    assert rel(_cl2ncdhw(x_leaf.grad)[:, :, 0], gref[-1]) < 2e-2
+        assert rel(gp[k].grad, gr) < T(3e-2, 3e-3), (k, rel(gp[k].grad, gr))
+    assert rel(_cl2ncdhw(x_leaf.grad)[:, :, 0], gref[-1]) < T(2e-2, 2e-3)
     for p in model.parameters():
         p.grad = None
     caps_d = caps.detach().double().cpu()
@@ -162,13 +179,15 @@ def test_train_mode_segment_parity(setup):
     o_ref, a_ref, f_ref = restate.decode(sd64, rout_in, _cl2ncdhw(x_cl)[:, :, 0], _cl2ncdhw(c56), _cl2ncdhw(c112),
                                          b["action"], b["labels"], 1, 11, True, m64[1])
     e = dict(logits=rel(out, o_ref.detach()), act=rel(act, a_ref.detach()), feat=rel(feat, f_ref.detach()))
-    print("decoder:", e)
-    assert e["logits"] < 2e-2 and e["act"] < 1e-5 and e["feat"] < 1e-6, e
-    tol = 2e-2 * float(o_ref.abs().max())
+    print(f"[{precision}] decoder:", e)
+    assert e["logits"] < T(2e-2, 1e-3) and e["act"] < 1e-5 and e["feat"] < 1e-6, e
+    tol = T(2e-2, 1e-3) * float(o_ref.abs().max())
     safe = o_ref.detach().abs() > tol
     agree = ((out.cpu() > 0) == (o_ref.detach() > 0)) | ~safe
-    print(f"thresholded masks: {int((~safe).sum())} of {safe.numel()} pixels inside the margin (excluded)")
+    print(f"[{precision}] thresholded masks: {int((~safe).sum())} of {safe.numel()} pixels inside the margin (excluded)")
     assert bool(agree.all()), f"{int((~agree).sum())} mask flips outside the margin"
+    if tf32:      # bit-exact masks everywhere but a < 3 % band around zero (bf16 mode: the 2e-2 margin swallows a third)
+        assert int((~safe).sum()) < 0.03 * safe.numel()
     assert act.argmax(1).tolist() == a_ref.argmax(1).tolist()
     w_o = torch.randn(out.shape, generator=g, dtype=torch.float64) / out.numel() ** 0.5
     w_a = torch.randn(act.shape, generator=g, dtype=torch.float64)
@@ -178,7 +197,7 @@ def test_train_mode_segment_parity(setup):
                                      [sd64[k] for k in dec_names] + [rout_in])
     # gradient yardstick = oracle with the same bf16 rounding points: at random init the gradients are noise-like sums,
     # and a fraction f of ReLU masks flipped by bf16 rounding perturbs them by ~sqrt(f) (5-15 %) in the reference itself
-    with restate.emulate_bf16():
+    with emulate():
         o_em, a_em, f_em = restate.decode(sd64, rout_in, _cl2ncdhw(x_cl)[:, :, 0], _cl2ncdhw(c56), _cl2ncdhw(c112),
                                           b["action"], b["labels"], 1, 11, True, m64[1])
     gref = torch.autograd.grad((o_em * w_o).sum() + (a_em * w_a).sum() + (f_em * w_f).sum(),
@@ -187,14 +206,17 @@ def test_train_mode_segment_parity(setup):
     errs = {k: rel(gp[k].grad, gr) for k, gr in zip(dec_names, gref[:-1])}
     errs["rout"] = rel(rout_leaf.grad, gref[-1])
     errs_exact = {k: rel(gp[k].grad, gr) for k, gr in zip(dec_names, gref_exact[:-1])}
-    print("decoder grads vs oracle(bf16 roundings):", {k: f"{v:.1e}" for k, v in errs.items()})
-    print("decoder grads vs exact fp64 oracle      :", {k: f"{v:.1e}" for k, v in errs_exact.items()})
+    print(f"[{precision}] decoder grads vs oracle(same roundings):", {k: f"{v:.1e}" for k, v in errs.items()})
+    print(f"[{precision}] decoder grads vs exact fp64 oracle      :", {k: f"{v:.1e}" for k, v in errs_exact.items()})
     # measured: <= 3e-2 except the two stride-2 ConvTranspose3d(128->64) weights (5e-2 .. 1.4e-1 depending on the run's
     # inputs, which vary with the train-mode encoder's atomics; their wgrad kernel passes at the same shapes in
     # tests/gpu_igemm_probe.py at 1e-6 against torch).  Reported, loosely bounded; open item in DESIGN.md.
     loose = {"upsample2.weight", "upsample3.weight"}
-    assert max(v for k, v in errs.items() if k not in loose) < 4e-2, errs
-    assert max(errs[k] for k in loose) < 0.25, errs
+    if tf32:
+        assert max(errs_exact.values()) < 1e-2, errs_exact
+    else:
+        assert max(v for k, v in errs.items() if k not in loose) < 4e-2, errs
+        assert max(errs[k] for k in loose) < 0.25, errs
 
     # ---- end to end, reported (not asserted at 2e-2: see docstring) -----------------------------------
     model.load_state_dict(sd0)
@@ -207,20 +229,24 @@ def test_train_mode_segment_parity(setup):
     with torch.no_grad():
         sdd = {k: v.detach() for k, v in sd64.items()}
         o_ex, a_ex, f_ex = restate.capsnet_forward(sdd, b["data"].double(), b["action"], b["labels"], 1, 11, True, m64[:2])
-        with restate.emulate_bf16():
+        with emulate():
             o_em, a_em, f_em = restate.capsnet_forward(sdd, b["data"].double(), b["action"], b["labels"], 1, 11, True, m64[:2])
-    print("END-TO-END vs exact fp64 oracle : logits %.2e act %.2e feat %.2e" % (rel(out, o_ex), rel(act, a_ex), rel(feat, f_ex)))
-    print("oracle(bf16 roundings) vs exact : logits %.2e act %.2e feat %.2e" % (rel(o_em, o_ex), rel(a_em, a_ex), rel(f_em, f_ex)))
-    assert rel(act, a_ex) < 5e-2 and torch.isfinite(out).all()
+    print("[%s] END-TO-END vs exact fp64 oracle : logits %.2e act %.2e feat %.2e" % (precision, rel(out, o_ex), rel(act, a_ex), rel(feat, f_ex)))
+    print("[%s] oracle(same roundings) vs exact : logits %.2e act %.2e feat %.2e" % (precision, rel(o_em, o_ex), rel(a_em, a_ex), rel(f_em, f_ex)))
+    assert rel(act, a_ex) < T(5e-2, 1e-2) and torch.isfinite(out).all()
     model.load_state_dict(sd0)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "tf32"], indirect=True)
 @pytest.mark.parametrize("which", ["stem", "conv2b", "conv2c", "Mixed_3b", "Mixed_4f"])
-def test_encoder_modules_fwd_bwd(setup, which):
+def test_encoder_modules_fwd_bwd(setup, which, precision):
     """Module-level parity (level 2): each encoder building block, train mode (batch statistics),
     forward + all parameter / input gradients against the fp64 oracle on the same bf16-representable input."""
     s = setup
     model, sd, restate = s["model"], s["sd"], s["restate"]
+    tf32 = precision == "tf32"
+    T = lambda bf, tf: tf if tf32 else bf
+    emulate = restate.emulate_tf32 if tf32 else restate.emulate_bf16
     model.train()
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(sum(ord(c) for c in which))
@@ -249,7 +275,7 @@ def test_encoder_modules_fwd_bwd(setup, which):
     # yardstick: the oracle with the same bf16 rounding points (GEMM operands, stored conv output / activation);
     # the exact fp64 oracle is printed next to it (ReLU masks flipped by bf16 rounding make noise-like gradients
     # differ by ~sqrt(flipped fraction) in the reference itself)
-    with restate.emulate_bf16():
+    with emulate():
         yr = ref_fn(xr, sd64, restate.BNState(True))
     w = torch.randn(yr.shape, generator=g, dtype=torch.float64)
     names = [k for k, v in sd64.items() if v.requires_grad]
@@ -266,11 +292,13 @@ def test_encoder_modules_fwd_bwd(setup, which):
         errs["input"] = rel(xg.grad.float(), gref[-1])
         errs_ex["input"] = rel(xg.grad.float(), gex[-1])
     worst, worst_ex = max(errs, key=errs.get), max(errs_ex, key=errs_ex.get)
-    print(f"{which}: fwd {e_fwd:.2e} (exact oracle {e_fwd_ex:.2e}); grads worst {worst} {errs[worst]:.2e} "
+    print(f"[{precision}] {which}: fwd {e_fwd:.2e} (exact oracle {e_fwd_ex:.2e}); grads worst {worst} {errs[worst]:.2e} "
           f"(exact oracle: {worst_ex} {errs_ex[worst_ex]:.2e})")
     model.load_state_dict(sd0)
-    assert e_fwd < 2e-2 and e_fwd_ex < 3e-2, (e_fwd, e_fwd_ex)
-    assert errs[worst] < 3e-2, (worst, errs[worst])
+    assert e_fwd < T(2e-2, 1e-3) and e_fwd_ex < T(3e-2, 1e-3), (e_fwd, e_fwd_ex)
+    assert errs[worst] < T(3e-2, 5e-3), (worst, errs[worst])
+    if tf32:
+        assert errs_ex[worst_ex] < 5e-3, (worst_ex, errs_ex[worst_ex])
 
 
 def test_jhmdb_variant_eval_and_step():

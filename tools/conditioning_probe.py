@@ -29,7 +29,7 @@ def rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-300))
 
 
-def run(n_lab, n_unl, mode, grads=True):
+def run(n_lab, n_unl, mode, grads=True, rounding="bf16"):
     sd = restate.make_state_dict(24, seed=0, dtype=torch.float64)
     b = restate.synthetic_batch(n_lab, n_unl, seed=47, dtype=torch.float64)
     masks = restate.make_drop_masks(n_lab + n_unl, seed=3, count=4, dtype=torch.float64)
@@ -37,7 +37,7 @@ def run(n_lab, n_unl, mode, grads=True):
     res = {}
     for tag in ("exact", "bf16"):
         sdg = {k: (v.clone().requires_grad_(grads) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
-        ctx = restate.emulate_bf16() if tag == "bf16" else None
+        ctx = (restate.emulate_tf32() if rounding == "tf32" else restate.emulate_bf16()) if tag == "bf16" else None
         if ctx:
             ctx.__enter__()
         try:
@@ -77,13 +77,14 @@ def main():
     ap.add_argument("--clips", type=int, nargs="+", default=[1, 2, 4])
     ap.add_argument("--mode", default="bv")
     ap.add_argument("--no-grads", action="store_true")
+    ap.add_argument("--round", default="bf16", choices=["bf16", "tf32"], help="rounding emulated at the CUDA path's rounding points")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     results = {}
     for n in a.clips:
         t0 = time.time()
-        r = run(n, n, a.mode, grads=not a.no_grads)
+        r = run(n, n, a.mode, grads=not a.no_grads, rounding=a.round)
         r["seconds"] = time.time() - t0
         results[f"{n}+{n}"] = r
         print(f"{n}+{n}", json.dumps(r), flush=True)
