@@ -71,6 +71,10 @@ typedef struct {
   int32_t stat_groups;  /* statistic groups of stat_sums: the batch N splits into stat_groups equal runs of clips */
   int32_t round_out;    /* dtype 1 only: round the stored fp32 result to tf32 (it is the next GEMM's operand) */
   int32_t nclass;
+  int32_t pad0_;
+  int64_t w_sample_stride; /* bytes between the packed weight sets of consecutive clips (every class pointer `w` is the set of
+                              clip 0); 0 = one set for all clips.  != 0 needs the TMA path and 128-row tiles that do not
+                              straddle clips.  Used by the collapsed decoder tail (per-clip composite weights). */
   b2c_conv_class cls[8];
 } b2c_conv_desc;
 
@@ -98,6 +102,8 @@ typedef struct {
   int32_t nsplit;  /* 0 = auto */
   int32_t atomic;  /* 1: atomicAdd into dw, 0: plain store (only legal when nsplit==1) */
   int32_t dtype;   /* 0: bf16 operands, 1: fp32 tensors / tf32 operands */
+  int64_t dw_sample_stride; /* elements between per-clip gradients dw[n]; 0 = one dw summed over all clips.  != 0: the
+                               position split is a multiple of N so that no CTA straddles clips */
 } b2c_wgrad_desc;
 
 int b2c_conv_wgrad(const b2c_wgrad_desc* desc_host, b2c_stream_t stream);
@@ -274,9 +280,44 @@ int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 /* tests: 1 = BatchNorm reductions use one block per statistic group (bit-reproducible activations, slow) */
 int b2c_set_deterministic(int32_t on);
 
+/* ------------------------------------------------------------------------------------
+ * Collapsed decoder tail: upsample4 (ConvTranspose3d 128->128 k3 s2 p1 op1) -> Dropout3d -> smooth
+ * (ConvTranspose3d 128->1 k3 p1), capsules_ucf101.py:504-509, has no non-linearity in between, so the chain equals ONE
+ * per-clip stride-2 transposed convolution 128 -> 1 with a 5x5x5 composite kernel
+ *     Weff[n][ci][e] = sum_c drop[n][c] sum_{k+m=e} W4[ci][c][k] Ws[c][m]        (per dimension: k, m in 0..2, e in 0..4)
+ * except on the index-0 planes (the reference crops upsample4's position -1 before `smooth` reads it), which use a 6th
+ * per-dimension column e=2' = e=2 without the (k=0, m=2) term.  6^3 = 216 columns, stored 224 wide.
+ *   logits[n][o] = bs + biasfield[n][class(o)] + sum_{i, e: o = 2 i - 2 + e} Y[n][i][col(e, i)],   Y[n][i][:] = x[n][i][:] . Weff[n]
+ * The 128-channel (N,8,224,224) tensor (3.3 GB in bf16 at 16+16 clips) is never formed; the per-clip GEMMs
+ * Y = x Weff (fprop), dx = dY Weff^T (dgrad) and dWeff[n] = x[n]^T dY[n] (wgrad) run on b2c_conv_fprop / b2c_conv_wgrad
+ * with w_sample_stride / dw_sample_stride.  All tensors below are fp32 unless noted.
+ * ---------------------------------------------------------------------------------- */
+/* composite weights in both packed operand images (fprop: rows = 224 columns, K = 128; dgrad: rows = 128, K = 224 padded to
+ * the mode's tap pitch), activation-precision element type, one set per clip `*_stride` ELEMENTS apart (buffers zeroed once by
+ * the caller: padding is never written); biasfield[n][27] (border class (t,h,w), 0 = first plane, 1 = interior, 2 = last). */
+int b2c_tail_weff(const float* w4, const float* b4, const float* ws, const float* drop_nc, void* packed_fprop,
+                  int64_t fprop_stride, void* packed_dgrad, int64_t dgrad_stride, int32_t dgrad_nkb, float* biasfield, int32_t N,
+                  b2c_stream_t s);
+/* logits (N,2It,2Ih,2Iw) from the planar GEMM output Y[224][N*It*Ih*Iw] */
+int b2c_tail_gather_fwd(const float* y_planar, const float* biasfield, const float* bs, float* logits, int32_t N, int32_t It,
+                        int32_t Ih, int32_t Iw, b2c_stream_t s);
+/* dY rows (N*It*Ih*Iw, 224) in the activation precision from dlogits; also sums[n][27] += per-border-class sums of dlogits
+ * (sums zeroed by the caller) */
+int b2c_tail_gather_bwd(const float* dlogits, void* dy, float* class_sums, int32_t N, int32_t It, int32_t Ih, int32_t Iw,
+                        b2c_stream_t s);
+/* chain rule back to the reference's parameters: dweff[n][ci][224] (per-clip wgrad) and class_sums ->
+ * dw4 += , db4 += , dws += , dbs += (accumulated: the buffers are the parameters' .grad) */
+int b2c_tail_chain_bwd(const float* dweff, const float* class_sums, const float* w4, const float* b4, const float* ws,
+                       const float* drop_nc, float* dw4, float* db4, float* dws, float* dbs, int32_t N, b2c_stream_t s);
+
+/* tf32 mode only: fp32 view (rows, C) -> compact bf16 tensors hi = bf16(x), lo = bf16(x - hi).  The mode's weight
+ * gradients are three bf16 GEMMs on these (hi*hi + hi*lo + lo*hi, fp32 accumulate: >= tf32 accuracy). */
+int b2c_split_bf16(const float* x, int64_t x_row_stride, int32_t x_c_off, void* hi, void* lo, int64_t rows, int32_t C,
+                   b2c_stream_t s);
+
 /* Precision mode of the activation tensors, process-wide.  0 (default): bf16 activations, bf16 GEMM operands
  * (tcgen05.mma kind::f16).  1: fp32 activations and fp32 packed weights read by the tensor core as tf32
- * (tcgen05.mma kind::tf32, fp32 accumulate) -- the reference computes in fp32 (main_ucf101.py:52-55, cuDNN convs with
+ * (tcgen05.mma kind::tf32, fp32 accumulate; weight gradients as 3 x bf16 split GEMMs, see b2c_split_bf16) -- the reference computes in fp32 (main_ucf101.py:52-55, cuDNN convs with
  * allow_tf32 default); this mode is the one its 1e-3 parity bar is asserted in.  Every `void*` activation view of this
  * header is bf16 in mode 0 and fp32 in mode 1; values that feed a later GEMM are rounded to tf32 when stored. */
 int b2c_set_precision(int32_t mode);

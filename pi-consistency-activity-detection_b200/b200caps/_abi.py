@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
                 ("si_t", i32), ("si_h", i32), ("si_w", i32), ("so_t", i32), ("so_h", i32), ("so_w", i32),
                 ("out_fp32", i32), ("relu", i32), ("sigmoid_from", i32), ("accumulate", i32), ("bn_tile", i32),
                 ("tap_pitch", i32), ("dtype", i32), ("stat_groups", i32), ("round_out", i32),
-                ("nclass", i32), ("cls", ConvClass * 8)]
+                ("nclass", i32), ("pad0_", i32), ("w_sample_stride", i64), ("cls", ConvClass * 8)]
 
 
 class WgradDesc(C.Structure):
@@ -38,7 +38,8 @@ class WgradDesc(C.Structure):
                 ("Qt", i32), ("Qh", i32), ("Qw", i32),
                 ("sg_t", i32), ("sg_h", i32), ("sg_w", i32), ("sp_t", i32), ("sp_h", i32), ("sp_w", i32),
                 ("pp_t", i32), ("pp_h", i32), ("pp_w", i32),
-                ("ntaps", i32), ("bn_tile", i32), ("nsplit", i32), ("atomic", i32), ("dtype", i32)]
+                ("ntaps", i32), ("bn_tile", i32), ("nsplit", i32), ("atomic", i32), ("dtype", i32),
+                ("dw_sample_stride", i64)]
 
 
 class PackJob(C.Structure):
@@ -87,6 +88,11 @@ _SIGS = {
     "b2c_fill_f32": [vp, i64, f32, vp],
     "b2c_set_deterministic": [i32],
     "b2c_set_precision": [i32],
+    "b2c_split_bf16": [vp, i64, i32, vp, vp, i64, i32, vp],
+    "b2c_tail_weff": [vp, vp, vp, vp, vp, i64, vp, i64, i32, vp, i32, vp],
+    "b2c_tail_gather_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2c_tail_gather_bwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2c_tail_chain_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
 }
 
 EXPORTS = sorted(list(_SIGS) + ["b2c_last_error", "b2c_version", "b2c_launch_count", "b2c_get_precision"])

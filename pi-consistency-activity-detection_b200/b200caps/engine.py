@@ -15,6 +15,12 @@ import torch
 from . import ops
 from .plans import PREC, ConvPlan, ConvSpec, View, act_dtype, same_pad
 
+import os
+
+# Decoder tail: "collapsed" (default) = upsample4 -> Dropout3d -> smooth as one per-clip transposed convolution
+# (CollapsedTail below); B2C_TAIL=explicit keeps the layer-by-layer schedule (3.3 GB intermediate at 16+16 clips).
+TAIL_COLLAPSED = os.environ.get("B2C_TAIL", "collapsed") != "explicit"
+
 BN_EPS = 1e-3       # pytorch_i3d.py:80
 BN_MOMENTUM = 0.01  # pytorch_i3d.py:80
 
@@ -693,6 +699,12 @@ class DecoderFn(torch.autograd.Function):
         cat112 = torch.empty((N, 2 * T1, 4 * H1, 4 * H1, 128), dtype=bf, device=dev)
         cba_fwd(L["upsample3"], mod.upsample3.bias, View(cat56), View(cat112, 0, 64), relu=True)
         cba_fwd(L["conv112"], mod.conv112.bias, View(c112), View(cat112, 64, 64), relu=True)
+        if TAIL_COLLAPSED:
+            logits, tail_saved = L["tail"].forward(View(cat112), drop_scale)
+            ctx.mod, ctx.drop, ctx.tail = mod, drop_scale, tail_saved
+            ctx.t = (x0, c28, c56, c112, cat28, cat56, cat112, None)
+            ctx.needs = ctx.needs_input_grad[:4]
+            return logits
         To, Ho = 4 * T1, 8 * H1
         u4 = torch.empty((N, To, Ho, Ho, 128), dtype=bf, device=dev)
         cba_fwd(L["upsample4"], mod.upsample4.bias, View(cat112), View(u4), relu=False, scale_nc=drop_scale)
@@ -701,7 +713,7 @@ class DecoderFn(torch.autograd.Function):
         ops.conv_fprop(L["smooth"].packed((To, Ho, Ho), "fprop"), "fprop", View(u4), P)
         logits = torch.empty((N, 1, To, Ho, Ho), dtype=torch.float32, device=dev)
         ops.stencil27_fwd(P, logits, mod.smooth.bias.detach(), N, To, Ho, Ho)
-        ctx.mod, ctx.drop = mod, drop_scale
+        ctx.mod, ctx.drop, ctx.tail = mod, drop_scale, None
         ctx.t = (x0, c28, c56, c112, cat28, cat56, cat112, u4)
         ctx.needs = ctx.needs_input_grad[:4]
         return logits
@@ -713,8 +725,13 @@ class DecoderFn(torch.autograd.Function):
         x0, c28, c56, c112, cat28, cat56, cat112, u4 = ctx.t
         dev = glog.device
         bf = act_dtype()
-        N, To, Ho = u4.shape[0], u4.shape[1], u4.shape[2]
         glog = glog.contiguous().float()
+        g = {}
+        dcat112 = torch.empty_like(cat112)
+        if ctx.tail is not None:
+            g["upsample4"], g["smooth"] = L["tail"].backward(ctx.tail, View(cat112), glog, View(dcat112))
+            return DecoderFn._backward_rest(ctx, g, dcat112)
+        N, To, Ho = u4.shape[0], u4.shape[1], u4.shape[2]
         dP = torch.empty((N, To, Ho, Ho, SmoothLayer.BWD_CPAD), dtype=bf, device=dev)
         db_smooth, ds1 = grad_buf(mod.smooth.bias)
         ops.stencil27_bwd(glog, dP, db_smooth, N, To, Ho, Ho, SmoothLayer.BWD_CPAD)
@@ -724,10 +741,16 @@ class DecoderFn(torch.autograd.Function):
         dw_smooth, ds0 = grad_buf(mod.smooth.weight)
         ops.conv_wgrad(sm.plan((To, Ho, Ho), "dgrad"), View(u4), View(dP), dw_smooth, atomic=True)
         del dP
-        g = {}
-        dcat112 = torch.empty_like(cat112)
         g["upsample4"] = cba_bwd(L["upsample4"], mod.upsample4.bias, View(cat112), None, View(du4), False, None, View(dcat112))
         del du4
+        g["smooth"] = (None if ds0 else dw_smooth, None if ds1 else db_smooth)
+        return DecoderFn._backward_rest(ctx, g, dcat112)
+
+    @staticmethod
+    def _backward_rest(ctx, g, dcat112):
+        mod = ctx.mod
+        L = mod._layers
+        x0, c28, c56, c112, cat28, cat56, cat112, _ = ctx.t
         dc112 = torch.empty_like(c112) if ctx.needs[3] else None
         g["conv112"] = cba_bwd(L["conv112"], mod.conv112.bias, View(c112), View(cat112, 64, 64), View(dcat112, 64, 64), True, None,
                                View(dc112) if dc112 is not None else None)
@@ -746,11 +769,96 @@ class DecoderFn(torch.autograd.Function):
         dx0 = torch.empty_like(x0) if ctx.needs[0] else None
         g["upsample1"] = cba_bwd(L["upsample1"], mod.upsample1.bias, View(x0), View(cat28, 0, 64), View(dcat28, 0, 64), True, None,
                                  View(dx0) if dx0 is not None else None)
-        g["smooth"] = (None if ds0 else dw_smooth, None if ds1 else db_smooth)
         flat = []
         for n in DecoderFn.ORDER:
             flat += [g[n][0], g[n][1]]
         return (dx0, dc28, dc56, dc112, None, None) + tuple(flat)
+
+
+class CollapsedTail:
+    """upsample4 -> Dropout3d -> smooth (capsules_ucf101.py:504-509) as ONE per-clip stride-2 transposed convolution
+    128 -> 1 (include/b200caps.h "Collapsed decoder tail"): composite weights per clip (they contain the
+    clip's Dropout3d mask), a 1x1x1 GEMM x -> 216 composite columns, and a stride-2 gather.  The (N,128,8,224,224)
+    tensor is never formed; executed MACs drop from 23.6 G to ~1.4 G per clip-pass."""
+    COLS, COLS_PAD = 216, 224
+
+    def __init__(self, up4: torch.nn.Module, smooth: torch.nn.Module):
+        self.up4, self.smooth = up4, smooth
+        self.plans: Dict = {}
+        self.bufs: Dict = {}
+
+    def plan(self, dims) -> ConvPlan:
+        dims = tuple(int(v) for v in dims)
+        key = (dims, PREC.mode)
+        pl = self.plans.get(key)
+        if pl is None:
+            from .plans import packed_geometry, tap_pitch
+            pl = ConvPlan(ConvSpec(128, self.COLS, (1, 1, 1), Cout_pad=self.COLS_PAD), dims)
+            # per-clip gradient dWeff[n][ci][224]
+            pl.wgrad_geom = dict(pl.wgrad_geom, s_p=1, s_g=self.COLS_PAD)
+            pl.geo_f = packed_geometry(self.COLS_PAD, 128)                       # (bn, nt, nkb, elems)
+            pl.geo_d = packed_geometry(128, tap_pitch(self.COLS_PAD))
+            self.plans[key] = pl
+        return pl.to(self.up4.weight.device)
+
+    def _weights(self, pl: ConvPlan, drop: Optional[torch.Tensor], N: int):
+        """Composite weights (both operand images) + bias field for this step's Dropout3d masks."""
+        dev = self.up4.weight.device
+        nset = N if drop is not None else 1
+        key = (nset, PREC.mode)
+        b = self.bufs.get(key)
+        if b is None:
+            b = dict(f=torch.zeros(nset * pl.geo_f[3], dtype=act_dtype(), device=dev),
+                     d=torch.zeros(nset * pl.geo_d[3], dtype=act_dtype(), device=dev),
+                     bias=torch.zeros((nset, 27), dtype=torch.float32, device=dev),
+                     ones=torch.ones((1, 128), dtype=torch.float32, device=dev))
+            self.bufs[key] = b
+        dr = drop if drop is not None else b["ones"]
+        ops.tail_weff(self.up4.weight.detach(), self.up4.bias.detach(), self.smooth.weight.detach(), dr, b["f"], pl.geo_f[3],
+                      b["d"], pl.geo_d[3], pl.geo_d[2], b["bias"], nset)
+        esz = b["f"].element_size()
+        per_clip = drop is not None
+        pl.fprop[0].packed, pl.dgrad[0].packed = b["f"], b["d"]
+        pl.fprop_pack = dict(pl.fprop_pack, sample_stride_bytes=pl.geo_f[3] * esz if per_clip else 0)
+        pl.dgrad_pack = dict(pl.dgrad_pack, sample_stride_bytes=pl.geo_d[3] * esz if per_clip else 0)
+        return b, dr
+
+    def forward(self, x: View, drop: Optional[torch.Tensor]):
+        """x: cat112 (N,It,Ih,Iw,128) -> fp32 logits (N,1,2It,2Ih,2Iw); returns (logits, saved state)."""
+        N = x.N
+        It, Ih, Iw = x.dims
+        pl = self.plan(x.dims)
+        b, dr = self._weights(pl, drop, N)
+        dev = x.t.device
+        rows = N * It * Ih * Iw
+        Y = torch.empty((self.COLS_PAD, rows), dtype=torch.float32, device=dev)
+        ops.conv_fprop(pl, "fprop", x, Y)
+        logits = torch.empty((N, 1, 2 * It, 2 * Ih, 2 * Iw), dtype=torch.float32, device=dev)
+        bf = b["bias"] if drop is not None else b["bias"].expand(N, 27).contiguous()
+        ops.tail_gather_fwd(Y, bf, self.smooth.bias.detach(), logits, N, It, Ih, Iw)
+        return logits, (pl, dr, drop is not None)
+
+    def backward(self, saved, x: View, glog: torch.Tensor, dx: Optional[View]):
+        """Returns ((dw4, db4), (dws, dbs)) -- None where accumulated straight into .grad; writes dx."""
+        pl, dr, per_clip = saved
+        assert per_clip, "backward through the eval-mode tail (no Dropout3d masks) is not supported"
+        N = x.N
+        It, Ih, Iw = x.dims
+        dev = x.t.device
+        dY = torch.empty((N, It, Ih, Iw, self.COLS_PAD), dtype=act_dtype(), device=dev)
+        sums = zeros_f32((N, 27), dev)
+        ops.tail_gather_bwd(glog, dY, sums, N, It, Ih, Iw)
+        if dx is not None:
+            ops.conv_fprop(pl, "dgrad", View(dY), dx)
+        dweff = torch.zeros((N, 128, self.COLS_PAD), dtype=torch.float32, device=dev)
+        ops.conv_wgrad(pl, x, View(dY), dweff, atomic=True, per_clip=True)
+        dw4, d0 = grad_buf(self.up4.weight)
+        db4, d1 = grad_buf(self.up4.bias)
+        dws, d2 = grad_buf(self.smooth.weight)
+        dbs, d3 = grad_buf(self.smooth.bias)
+        ops.tail_chain_bwd(dweff, sums, self.up4.weight.detach(), self.up4.bias.detach(), self.smooth.weight.detach(), dr,
+                           dw4, db4, dws, dbs, N)
+        return (None if d0 else dw4, None if d1 else db4), (None if d2 else dws, None if d3 else dbs)
 
 
 class SmoothLayer:

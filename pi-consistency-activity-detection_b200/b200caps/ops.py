@@ -46,10 +46,28 @@ def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=Non
             f"{' T' if plan.spec.transposed else ''}", "b2c_conv_fprop", d)
 
 
-def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None):
-    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part)
-    _launch(f"wgrad {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
-            f"{' T' if plan.spec.transposed else ''}", "b2c_conv_wgrad", d)
+def split_bf16(v: View):
+    """tf32 mode: fp32 view -> (hi, lo) compact bf16 Views with hi + lo = x to 2^-17."""
+    shape = tuple(v.t.shape[:-1]) + (v.C,)
+    hi = torch.empty(shape, dtype=torch.bfloat16, device=v.t.device)
+    lo = torch.empty(shape, dtype=torch.bfloat16, device=v.t.device)
+    _abi.call("b2c_split_bf16", v.ptr, v.row_stride, v.c_off, _p(hi), _p(lo), v.rows, v.C, stream())
+    return View(hi), View(lo)
+
+
+def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None, per_clip=False):
+    name = (f"wgrad {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
+            f"{' T' if plan.spec.transposed else ''}")
+    if PREC.mode:
+        # tf32 mode: 3 x bf16 split GEMMs accumulated into dw (see b2c_split_bf16); dw must be zero / an accumulator
+        assert atomic, "tf32-mode wgrad accumulates"
+        xh, xl = split_bf16(x)
+        dh, dl = split_bf16(dy)
+        for a, b in ((xh, dh), (xh, dl), (xl, dh)):
+            _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True))
+        return
+    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part, per_clip)
+    _launch(name, "b2c_conv_wgrad", d)
 
 
 class PackRegistry:
@@ -188,6 +206,25 @@ def stencil27_fwd(P, out, bias, N, T, H, W):
 
 def stencil27_bwd(dout, dP, dbias, N, T, H, W, cpad=32):
     _abi.call("b2c_stencil27_bwd", _p(dout), _p(dP), _p(dbias), N, T, H, W, cpad, stream())
+
+
+# ---- collapsed decoder tail (upsample4 -> Dropout3d -> smooth as one per-clip transposed convolution) --------------
+def tail_weff(w4, b4, ws, drop_nc, packed_f, f_stride, packed_d, d_stride, d_nkb, biasfield, N):
+    _abi.call("b2c_tail_weff", _p(w4), _p(b4), _p(ws), _p(drop_nc), _p(packed_f), f_stride, _p(packed_d), d_stride, d_nkb,
+              _p(biasfield), N, stream())
+
+
+def tail_gather_fwd(y_planar, biasfield, bs, logits, N, It, Ih, Iw):
+    _abi.call("b2c_tail_gather_fwd", _p(y_planar), _p(biasfield), _p(bs), _p(logits), N, It, Ih, Iw, stream())
+
+
+def tail_gather_bwd(dlogits, dy, class_sums, N, It, Ih, Iw):
+    _abi.call("b2c_tail_gather_bwd", _p(dlogits), _p(dy), _p(class_sums), N, It, Ih, Iw, stream())
+
+
+def tail_chain_bwd(dweff, class_sums, w4, b4, ws, drop_nc, dw4, db4, dws, dbs, N):
+    _abi.call("b2c_tail_chain_bwd", _p(dweff), _p(class_sums), _p(w4), _p(b4), _p(ws), _p(drop_nc), _p(dw4), _p(db4), _p(dws),
+              _p(dbs), N, stream())
 
 
 # ---- capsule head ---------------------------------------------------------------------------

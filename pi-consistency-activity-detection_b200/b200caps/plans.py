@@ -334,6 +334,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
     assert bn_tile in (0, pick_bn_tile(pk["R_pad"])), "bn_tile is fixed by the packed weight layout"
     d.relu, d.sigmoid_from, d.accumulate, d.bn_tile = int(relu), int(sigmoid_from), int(accumulate), pick_bn_tile(pk["R_pad"])
     d.tap_pitch = pk.get("pitch") or tap_pitch(pk["C"])
+    d.w_sample_stride = int(pk.get("sample_stride_bytes", 0))     # per-clip weight sets (collapsed decoder tail)
     d.nclass = len(classes)
     assert 1 <= d.nclass <= 8
     for i, cl in enumerate(classes):
@@ -347,7 +348,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
 
 
 def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0,
-                    part=None) -> _abi.WgradDesc:
+                    part=None, per_clip=False, force_bf16=False) -> _abi.WgradDesc:
     """x = layer input, dy = gradient of the layer output, dw = fp32 gradient in torch weight layout.
     part=(c_off, C): restrict a fused layer's wgrad to the output-channel window of one member weight."""
     geo = dict(plan.wgrad_geom)
@@ -360,9 +361,10 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
     g, p = (x, dy) if geo["g_is_input"] else (dy, x)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     assert g.C == geo["Cg"] and p.C == geo["Cp"], (g.C, geo["Cg"], p.C, geo["Cp"])
-    assert g.t.dtype == act_dtype() and p.t.dtype == act_dtype(), (g.t.dtype, p.t.dtype, precision())
+    want = torch.bfloat16 if force_bf16 else act_dtype()
+    assert g.t.dtype == want and p.t.dtype == want, (g.t.dtype, p.t.dtype, precision())
     d = _abi.WgradDesc()
-    d.dtype = PREC.mode
+    d.dtype = 0          # tf32 mode: the caller passes bf16 hi / lo splits (ops.conv_wgrad)
     d.Cp_real = geo.get("Cp_real", geo["Cp"])
     d.g, d.p, d.dw = g.ptr, p.ptr, dw.data_ptr()
     d.taps, d.wtap = cl.taps_dev.data_ptr(), cl.wtap_dev.data_ptr()
@@ -377,4 +379,7 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
     d.sp_t, d.sp_h, d.sp_w = geo["sp"]
     d.pp_t = d.pp_h = d.pp_w = 0
     d.ntaps, d.bn_tile, d.nsplit, d.atomic = len(cl.taps), int(bn_tile), int(nsplit), int(atomic)
+    if per_clip:      # dw is (N, ...): one gradient per clip
+        assert dw.shape[0] == x.N
+        d.dw_sample_stride = dw.numel() // x.N
     return d

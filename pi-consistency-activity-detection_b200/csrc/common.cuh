@@ -305,4 +305,24 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
+// ---- packed GEMM operand image (the fprop kernel's B tiles) ---------------------------------
+// [n-tile][k-block][row (bn_tile)][K elements of one 128-byte row] with the 128-byte swizzle pre-applied.
+// kTF32: fp32 elements rounded to tf32, 32 K-elements per 128-byte row (16-byte swizzle chunk = 4 elements).
+template <bool kTF32>
+__device__ __forceinline__ void pack_store(void* packed, long long tile_base_rows, int rr, long long k, float v, int bn_tile, int nkb,
+                                           int tile) {
+  if (kTF32) {
+    const int kb = (int)(k >> 5), kk = (int)(k & 31);
+    const long long off = ((long long)tile * nkb + kb) * ((long long)bn_tile * 32) + (rr >> 3) * 256 + (rr & 7) * 32 +
+                          (((kk >> 2) ^ (rr & 7)) << 2) + (kk & 3);
+    reinterpret_cast<float*>(packed)[off] = tf32_rna(v);
+  } else {
+    const int kb = (int)(k >> 6), kk = (int)(k & 63);
+    const long long off = ((long long)tile * nkb + kb) * ((long long)bn_tile * 64) + (rr >> 3) * 512 + (rr & 7) * 64 +
+                          (((kk >> 3) ^ (rr & 7)) << 3) + (kk & 7);
+    reinterpret_cast<bf16*>(packed)[off] = __float2bfloat16(v);
+  }
+}
+
+
 #endif  // __CUDACC__

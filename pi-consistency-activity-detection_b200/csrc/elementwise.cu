@@ -547,6 +547,29 @@ __global__ void __launch_bounds__(kBlock) add_kernel(const T* __restrict__ a, lo
   }
 }
 
+// fp32 view -> two compact bf16 tensors hi = bf16(x), lo = bf16(x - hi): x = hi + lo to 2^-17 relative.  The tf32
+// precision mode's weight gradients run as three bf16 GEMMs (hi*hi + hi*lo + lo*hi, fp32 accumulate) on the
+// position-major (MN-major) wgrad kernel: tcgen05 kind::tf32 reads MN-major 32-bit operands only through a dedicated
+// shared-memory layout (128B swizzle, 32-byte base) that the im2col TMA path does not produce.
+__global__ void __launch_bounds__(kBlock) split_bf16_kernel(const float* __restrict__ x, long long x_rs, int x_co, bf16* __restrict__ hi,
+                                                            bf16* __restrict__ lo, long long rows, int C) {
+  const int CV = C / 8;
+  const long long total = rows * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const long long row = i / CV;
+    float v[8], h[8], l[8];
+    ld8(x + row * x_rs + x_co + cv * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16(v[j]));
+      l[j] = v[j] - h[j];
+    }
+    st16(hi + row * C + cv * 8, pack8(h));
+    st16(lo + row * C + cv * 8, pack8(l));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // smooth = ConvTranspose3d(128->1, k3, p1): out[o] = bias + sum_k P_k[o + 1 - k], P planar fp32 [32][rows]
 __global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __restrict__ P, float* __restrict__ out,
@@ -937,6 +960,15 @@ B2C_API int b2c_add(const void* a, int64_t a_rs, int32_t a_co, const void* b, in
   LAUNCH_T(add_kernel, grid_for(rows * (C / 8)), kBlock, 0, s, (const T*)a, a_rs, a_co, (const T*)b, b_rs, b_co, (T*)out, o_rs, o_co, rows, C);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("add");
+  return 0;
+}
+
+B2C_API int b2c_split_bf16(const float* x, int64_t x_rs, int32_t x_co, void* hi, void* lo, int64_t rows, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(x && hi && lo && rows > 0, "split_bf16: bad args");
+  CHECK_VIEW("split_bf16", C, x_rs, x_co);
+  split_bf16_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, (cudaStream_t)s>>>(x, x_rs, x_co, (bf16*)hi, (bf16*)lo, rows, C);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("split_bf16");
   return 0;
 }
 

@@ -338,7 +338,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
           }
         }
         const int nkb = cc.ntaps * cblocks;
-        const uint8_t* wtile = reinterpret_cast<const uint8_t*>(cc.w) + (size_t)ti.n_idx * nkb * (size_t)b_tile_bytes;
+        // per-clip weight sets (collapsed decoder tail): the unit's rows all belong to clip bn_i[0] (host-checked)
+        const uint8_t* wtile = reinterpret_cast<const uint8_t*>(cc.w) + (size_t)ti.n_idx * nkb * (size_t)b_tile_bytes +
+                               (size_t)bn_i[0] * (size_t)d.w_sample_stride;
         const CUtensorMap* map = &maps.a[ti.cls];
         int kb = 0;
         for (int tp = 0; tp < cc.ntaps; ++tp) {
@@ -791,6 +793,8 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
   const long long kb_hi = nkb_all * (blockIdx.z + 1) / nsplit;
   const int nkb = (int)(kb_hi - kb_lo);
   if (nkb <= 0) return;
+  // per-clip gradients: nsplit is a multiple of N (host), so this CTA's positions belong to clip z / (nsplit / N)
+  float* const dw_base = d.dw + (d.dw_sample_stride ? (long long)(blockIdx.z / (nsplit / d.N)) * d.dw_sample_stride : 0ll);
   const int b_atoms = (bn16 + kCB - 1) / kCB;
   const int b_tile_bytes = b_atoms * kBoxBytes;
   const int a_bytes = MT * kATileBytes;
@@ -1017,7 +1021,7 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
           if (i >= nc) break;
           const int pc = n0 + c0 + i;
           if (pc < d.Cp_real) {
-            float* dst = d.dw + base + (long long)pc * d.s_p;
+            float* dst = dw_base + base + (long long)pc * d.s_p;
             if (d.atomic) atomicAdd(dst, v[i]);
             else *dst = v[i];
           }
@@ -1077,23 +1081,6 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
 // fp32 master weights -> bf16 GEMM operand tiles in exactly the shared-memory image the fprop kernel wants:
 // [n-tile][k-block][row (bn_tile)][64 K-elements] with the 128-byte swizzle already applied, so a stage's
 // weight tile is ONE contiguous bulk copy.  k = t*tap_pitch + col_off + c ; global row = r + r_off.
-// kTF32: fp32 elements rounded to tf32, 32 K-elements per 128-byte row (16-byte swizzle chunk = 4 elements).
-template <bool kTF32>
-__device__ __forceinline__ void pack_store(void* packed, long long tile_base_rows, int rr, long long k, float v, int bn_tile, int nkb,
-                                           int tile) {
-  if (kTF32) {
-    const int kb = (int)(k >> 5), kk = (int)(k & 31);
-    const long long off = ((long long)tile * nkb + kb) * ((long long)bn_tile * 32) + (rr >> 3) * 256 + (rr & 7) * 32 +
-                          (((kk >> 2) ^ (rr & 7)) << 2) + (kk & 3);
-    reinterpret_cast<float*>(packed)[off] = tf32_rna(v);
-  } else {
-    const int kb = (int)(k >> 6), kk = (int)(k & 63);
-    const long long off = ((long long)tile * nkb + kb) * ((long long)bn_tile * 64) + (rr >> 3) * 512 + (rr & 7) * 64 +
-                          (((kk >> 3) ^ (rr & 7)) << 3) + (kk & 7);
-    reinterpret_cast<bf16*>(packed)[off] = __float2bfloat16(v);
-  }
-}
-
 template <bool kTF32>
 __global__ void pack_weights_kernel(const float* __restrict__ w, void* __restrict__ packed, const int32_t* __restrict__ wtap,
                                     int R, int ntaps, int C, int C_real, long long s_r, long long s_c, long long tap_pitch,
@@ -1273,6 +1260,12 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
               "conv_fprop: tap_pitch=%d must be Cin=%d or Cin rounded up to a multiple of %d", d.tap_pitch, d.Cin, bk);
   const int use_tma = (k_pitch % bk == 0) ? 1 : 0;
   B2C_REQUIRE(!tf32 || (use_tma && d.out_fp32 != 0), "conv_fprop: tf32 mode needs tap_pitch %% 32 == 0 and an fp32 output");
+  if (d.w_sample_stride != 0) {
+    B2C_REQUIRE(use_tma && d.w_sample_stride > 0 && d.w_sample_stride % 16 == 0, "conv_fprop: per-clip weights need the TMA path and a 16-byte stride");
+    for (int i = 0; i < d.nclass; ++i)
+      B2C_REQUIRE(((long long)d.cls[i].Qt * d.cls[i].Qh * d.cls[i].Qw) % (2 * kTileM) == 0,
+                  "conv_fprop: per-clip weights need positions per clip to be a multiple of 256 (class %d)", i);
+  }
   const int acc_cols = (d.bn_tile + 15) & ~15;
   const int b_tile_bytes_h = ((acc_cols * 128) + 1023) & ~1023;
   const int staging = kStagingBytes + 16;
@@ -1405,8 +1398,11 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(d.bn_tile % 16 == 0 && d.bn_tile <= 256, "conv_wgrad: bn_tile=%d invalid", d.bn_tile);
   const long long Mtot = (long long)d.N * d.Qt * d.Qh * d.Qw;
   if (Mtot == 0) return 0;
-  B2C_REQUIRE(d.dtype == 0 || d.dtype == 1, "conv_wgrad: dtype=%d", d.dtype);
-  const int tf32 = d.dtype == 1 ? 1 : 0;
+  // kind::tf32 reads MN-major (position-major) 32-bit operands only from the 128B-swizzle / 32-byte-base shared-memory
+  // layout, which the im2col TMA path used here does not produce (measured r02: the kTF32 instantiation returned zeros).
+  // The tf32 precision mode therefore computes weight gradients as three bf16 GEMMs on hi / lo splits (b2c_split_bf16).
+  B2C_REQUIRE(d.dtype == 0, "conv_wgrad: dtype=%d -- only bf16 operands; tf32 mode passes bf16 hi/lo splits (b2c_split_bf16)", d.dtype);
+  const int tf32 = 0;
   const int esz = tf32 ? 4 : 2;
   const int cb = tf32 ? 32 : 64;           // channels per TMA box (128-byte swizzle row)
   const int pk = tf32 ? 32 : 64;           // positions per K-block
@@ -1451,6 +1447,15 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
     if (nsplit < 1) nsplit = 1;
   }
   if (nsplit > nkb) nsplit = (int)nkb;
+  if (d.dw_sample_stride != 0) {
+    // per-clip gradients: the position split must not straddle clips
+    const long long per = (long long)d.Qt * d.Qh * d.Qw;
+    B2C_REQUIRE(d.dw_sample_stride > 0 && per % pk == 0, "conv_wgrad: per-clip dw needs positions per clip %% %d == 0", pk);
+    int s = nsplit / d.N;
+    if (s < 1) s = 1;
+    while (s > 1 && (long long)s * 8 > per / pk) --s;
+    nsplit = s * d.N;
+  }
   B2C_REQUIRE(nsplit == 1 || d.atomic, "conv_wgrad: nsplit>1 requires atomic accumulation");
   const int stage_bytes = MT * kATileBytes + b_tile_bytes;
   // latency-bound gather: keep as many K-blocks in flight as shared memory allows (ncu r01: 2 stages -> L2 45 %, tensor 11 %)
@@ -1464,8 +1469,6 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(igemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     if (e != cudaSuccess) return b2c_cuda_check(e, "conv_wgrad: cudaFuncSetAttribute");
     configured = true;
   }
@@ -1489,10 +1492,7 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
     if (rc) return rc;
   }
   dim3 grid((unsigned)mtc, (unsigned)nt, (unsigned)nsplit);
-  if (tf32)
-    igemm_wgrad_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit, MT);
-  else
-    igemm_wgrad_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit, MT);
+  igemm_wgrad_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(d, maps, use_tma, lo[0], lo[1], lo[2], stages, lag, nsplit, MT);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("conv_wgrad launch");
   return 0;

@@ -146,6 +146,7 @@ class CapsNet(nn.Module):
                 "upsample4": engine.ConvLayer(self.upsample4.weight,
                                               lambda d: ConvSpec(128, 128, (3, 3, 3), two, one, z, one, True)),
                 "smooth": engine.SmoothLayer(self.smooth.weight),
+                "tail": engine.CollapsedTail(self.upsample4, self.smooth),
             }
             self.__dict__["_layers_cache"] = lc
         return lc

@@ -231,3 +231,56 @@ def test_adam_matches_torch():
         ops.adam_step(p, g, m, v, n, 1e-3, 0.9, 0.999, 1e-6, step_dev)
     assert int(step_dev) == 3
     assert rel(p, ref.detach()) < 1e-5
+
+
+@pytest.fixture
+def precision(request):
+    from b200caps import plans
+    plans.set_precision(request.param)
+    yield request.param
+    plans.set_precision("bf16")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"], indirect=True)
+@pytest.mark.parametrize("N,dims", [(3, (4, 8, 8)), (2, (1, 16, 16)), (2, (2, 16, 8))])
+def test_collapsed_decoder_tail(N, dims, precision):
+    """upsample4 -> Dropout3d -> smooth (capsules_ucf101.py:504-509) as one per-clip transposed convolution
+    (engine.CollapsedTail) against the layer-by-layer torch chain in fp64: logits, the gradient w.r.t. the 128-channel
+    input and all four parameter gradients -- including the index-0 border planes and the bias field."""
+    from b200caps import engine, plans
+    from b200caps.plans import View
+    torch.manual_seed(N * 100 + dims[0])
+    d = dev()
+    up4 = torch.nn.ConvTranspose3d(128, 128, 3, stride=2, padding=1, output_padding=1).to(d)
+    sm = torch.nn.ConvTranspose3d(128, 1, 3, padding=1).to(d)
+    with torch.no_grad():
+        up4.weight.normal_(0, 0.05)
+        sm.weight.normal_(0, 0.05)
+        up4.bias.normal_(0, 0.3)
+        sm.bias.normal_(0, 0.3)
+    x = torch.relu(torch.randn((N, 128) + dims, device=d)).bfloat16().float()
+    drop = ((torch.rand(N, 128, device=d) < 0.5).float() * 2).contiguous()
+    glog = torch.randn((N, 1) + tuple(2 * v for v in dims), device=d)
+    # reference chain, fp64
+    xd = x.double().requires_grad_(True)
+    P = [p.detach().double().requires_grad_(True) for p in (up4.weight, up4.bias, sm.weight, sm.bias)]
+    u = F.conv_transpose3d(xd, P[0], P[1], stride=2, padding=1, output_padding=1) * drop.double().view(N, 128, 1, 1, 1)
+    ref = F.conv_transpose3d(u, P[2], P[3], padding=1)
+    gref = torch.autograd.grad(ref, [xd] + P, glog.double())
+    # collapsed tail
+    tail = engine.CollapsedTail(up4, sm)
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(plans.act_dtype())
+    logits, saved = tail.forward(View(x_cl), drop)
+    dx = torch.empty_like(x_cl)
+    (dw4, db4), (dws, dbs) = tail.backward(saved, View(x_cl), glog.contiguous(), View(dx))
+    torch.cuda.synchronize()
+    tol = 2e-2 if precision == "bf16" else 1e-3
+    errs = dict(logits=rel(logits, ref.detach()), dx=rel(dx.float().permute(0, 4, 1, 2, 3), gref[0]), dw4=rel(dw4, gref[1]),
+                db4=rel(db4, gref[2]), dws=rel(dws, gref[3]), dbs=rel(dbs, gref[4]))
+    print(precision, N, dims, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < tol, errs
+    # eval mode: no Dropout3d mask, one weight set for all clips
+    logits_e, _ = tail.forward(View(x_cl), None)
+    with torch.no_grad():
+        ref_e = F.conv_transpose3d(F.conv_transpose3d(x.double(), P[0], P[1], stride=2, padding=1, output_padding=1), P[2], P[3], padding=1)
+    assert rel(logits_e, ref_e) < tol

@@ -114,8 +114,12 @@ def test_train_mode_segment_parity(setup, precision):
     # shallow taps: within the bf16 tolerance of the exact oracle.  The deep tap (17 conv+BN layers) is compared
     # with the rounding-emulated oracle; accumulation-order differences flip bf16 roundings and train-mode BN over a
     # 2-clip batch amplifies them, so its max-norm bound is loose and an L2 bound is added.
+    # vs the oracle with the same rounding points: the mode's bar (tf32: 1.5 x, both sides carry rounding noise); vs the
+    # exact oracle: the bar or 1.5 x what the reference's own mathematics moves by under that rounding, whichever is larger
     bar = T(2e-2, 1e-3)
-    assert e_ex["c112"] < bar and e_ex["c56"] < bar and e["c112"] < bar and e["c56"] < bar, (e, e_ex)
+    for k in ("c112", "c56"):
+        assert e[k] < T(2e-2, 1.5e-3), (k, e)
+        assert e_ex[k] < max(bar, 1.5 * o_ex[k]), (k, e_ex, o_ex)
     xa, xb = _cl2ncdhw(x_cl)[:, :, 0], x_ref.detach()
     l2 = float((xa - xb).norm() / xb.norm())
     print(f"encoder deep tap: max-norm {e['x']:.2e}, relative L2 {l2:.2e} (vs oracle with bf16 roundings)")
@@ -295,7 +299,7 @@ def test_encoder_modules_fwd_bwd(setup, which, precision):
     print(f"[{precision}] {which}: fwd {e_fwd:.2e} (exact oracle {e_fwd_ex:.2e}); grads worst {worst} {errs[worst]:.2e} "
           f"(exact oracle: {worst_ex} {errs_ex[worst_ex]:.2e})")
     model.load_state_dict(sd0)
-    assert e_fwd < T(2e-2, 1e-3) and e_fwd_ex < T(3e-2, 1e-3), (e_fwd, e_fwd_ex)
+    assert e_fwd < T(2e-2, 2e-3) and e_fwd_ex < T(3e-2, 1e-3), (e_fwd, e_fwd_ex)
     assert errs[worst] < T(3e-2, 5e-3), (worst, errs[worst])
     if tf32:
         assert errs_ex[worst_ex] < 5e-3, (worst_ex, errs_ex[worst_ex])
