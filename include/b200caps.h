@@ -146,6 +146,20 @@ int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, int32_t C,
                      int32_t Ho, int32_t Wo, int32_t kt, int32_t kh, int32_t kw, int32_t st, int32_t sh, int32_t sw, int32_t pt,
                      int32_t ph, int32_t pw, int32_t Kpad, b2c_stream_t s);
 
+/* Folded stem: the same layer without the im2col matrix.  The time axis is folded into the channel axis
+ * (xs[n][h][w][fp*4 + c] = x[n][fp - pt][h][w][c], fp = padded frame < Tp <= 16, 4 channel slots per frame), which turns the
+ * few-channel 3-D convolution into a 2-D convolution over Tp*4 channels that runs on b2c_conv_fprop / b2c_conv_wgrad's TMA
+ * path with one output class (own weight set W2[t]) per output frame t.
+ *   _fold_input  : x channels-last (N,T,H,W,8) activation precision -> xs (N,H,W,Tp*4)
+ *   _fold_weights: w (Cout,Cin,kt,kh,kw) fp32 -> w2 fp32 [To][Cout][kh*kw][Kf = Tp*4], the kernel shifted to frame t's window
+ *   _unfold_wgrad: dw += the adjoint of _fold_weights applied to dw2 */
+int b2c_stem_fold_input(const void* x, void* xs, int32_t N, int32_t T, int32_t H, int32_t W, int32_t Cs, int32_t pt, int32_t Tp,
+                        b2c_stream_t s);
+int b2c_stem_fold_weights(const float* w, float* w2, int32_t Cout, int32_t Cin, int32_t kt, int32_t khw, int32_t st, int32_t To,
+                          int32_t Kf, b2c_stream_t s);
+int b2c_stem_unfold_wgrad(const float* dw2, float* dw, int32_t Cout, int32_t Cin, int32_t kt, int32_t khw, int32_t st, int32_t To,
+                          int32_t Kf, b2c_stream_t s);
+
 /* BatchNorm3d training statistics (pytorch_i3d.py:80,117).  groups: rows are split evenly into
  * `groups` contiguous segments with independent statistics (two forward passes batched).
  * _sums: ws fp32 [groups][2][C] (zeroed by the caller) += per-channel sum / sum of squares.

@@ -190,8 +190,14 @@ class ConvLayer:
 
 
 class StemLayer(ConvLayer):
-    """Few-input-channel convolution (the RGB 7x7x7 stem) = explicit im2col (bandwidth kernel) + the TMA GEMM path as
-    a 1x1x1 convolution over K = taps*Cin columns (zero padded to a multiple of 64)."""
+    """Few-input-channel convolution (the RGB 7x7x7 stem, pytorch_i3d.py:224).
+
+    "fold" (default): the time axis is folded into the channel axis -- xs[n][h][w][fp*4+c] -- so the layer is a 2-D
+    convolution over 64 channels on the TMA im2col path, one output class (own shifted weight set) per output frame;
+    nothing but the 205 MB folded input is materialised (include/b200caps.h, "Folded stem").
+    "im2col" (B2C_STEM=im2col, or clips the fold does not cover): explicit im2col (bandwidth kernel) + a 1x1x1 GEMM over
+    K = taps*Cin columns -- a 3.5 GB matrix at 16+16 clips, written once and read twice."""
+    KF = 64            # folded channels: 16 padded frames x 4 channel slots
 
     def __init__(self, weight, cin, cout, k, stride):
         self.weight, self.cin, self.cout, self.k, self.stride = weight, cin, cout, tuple(k), tuple(stride)
@@ -200,12 +206,91 @@ class StemLayer(ConvLayer):
         self.Kpad = (self.K + 63) // 64 * 64
         self.plans, self.keys = {}, {}
         self._wtap = None
+        self._w2 = None
+        self.fold_enabled = os.environ.get("B2C_STEM", "fold") != "im2col"
 
     def geometry(self, in_dims):
         pads = [same_pad(d, kk, ss) for d, kk, ss in zip(in_dims, self.k, self.stride)]
         od = tuple((d + p[0] + p[1] - kk) // ss + 1 for d, p, kk, ss in zip(in_dims, pads, self.k, self.stride))
         return od, tuple(p[0] for p in pads)
 
+    # ---- folded path -------------------------------------------------------------------------------------
+    def use_fold(self, in_dims) -> bool:
+        od, pf = self.geometry(in_dims)
+        last = self.stride[0] * (od[0] - 1) + self.k[0]          # padded frames touched
+        return (self.fold_enabled and self.cin <= 4 and od[0] <= 8 and od[0] in (1, 2, 4, 8) and last <= 16
+                and pf[0] + in_dims[0] <= 16)
+
+    def fold_input(self, x: View) -> View:
+        od, pf = self.geometry(x.dims)
+        T, H, W = x.dims
+        xs = torch.empty((x.N, 1, H, W, self.KF), dtype=act_dtype(), device=x.t.device)
+        ops.stem_fold_input(x, xs, pf[0], self.KF // 4)
+        return View(xs)
+
+    def fold_plan(self, in_dims) -> ConvPlan:
+        in_dims = tuple(int(v) for v in in_dims)
+        key = ("fold", in_dims)
+        pl = self.plans.get(key)
+        if pl is None:
+            from .plans import TapClass
+            od, pf = self.geometry(in_dims)
+            T, H, W = in_dims
+            pads = [same_pad(d, kk, ss) for d, kk, ss in zip(in_dims, self.k, self.stride)]
+            spec = ConvSpec(self.KF, self.cout, (1, self.k[1], self.k[2]), (1, self.stride[1], self.stride[2]),
+                            (0, pads[1][0], pads[2][0]), (0, pads[1][1], pads[2][1]))
+            pl = ConvPlan(spec, (1, H, W))
+            b = pl.fprop[0]
+            wt = [i * self.KF for i in range(len(b.taps))]          # tap offset inside W2[t] / dW2[t]: (Cout, khw, KF)
+            pl.fprop = [TapClass(list(b.taps), list(wt), b.Q, (t, 0, 0)) for t in range(od[0])]
+            pl.dgrad = []                                             # the stem input needs no gradient
+            pl.out_dims = tuple(od)
+            khw = self.k[1] * self.k[2]
+            pl.fprop_pack = dict(R=self.cout, R_pad=self.cout, C=self.KF, C_real=self.KF, s_r=khw * self.KF, s_c=1)
+            pl.wgrad_cls = pl.fprop[0]
+            pl.wgrad_geom = dict(pl.wgrad_geom, s_p=khw * self.KF, s_g=1, Q=(1, od[1], od[2]))
+            self.plans[key] = pl
+        return pl.to(self.weight.device)
+
+    def _refresh_w2(self, od0: int):
+        khw = self.k[1] * self.k[2]
+        ops.stem_fold_weights(self.weight.detach(), self._w2, self.cout, self.cin, self.k[0], khw, self.stride[0], od0, self.KF)
+
+    def packed_fold(self, in_dims) -> ConvPlan:
+        in_dims = tuple(int(v) for v in in_dims)
+        pl = self.fold_plan(in_dims)
+        w = self.weight
+        key = _packed_key(w)
+        if not _fresh(self.keys.get(("fold", in_dims)), key):
+            from .plans import packed_geometry
+            To = pl.out_dims[0]
+            khw = self.k[1] * self.k[2]
+            if self._w2 is None or self._w2.shape[0] != To:
+                self._w2 = torch.zeros((To, self.cout, khw, self.KF), dtype=torch.float32, device=w.device)
+            self._refresh_w2(To)
+            if ops.PACKS is not None:
+                ops.PACKS.add_pre(("stem", id(self)), lambda To=To: self._refresh_w2(To))
+            bn, _, nkb, elems = packed_geometry(self.cout, khw * self.KF)
+            for t, cl in enumerate(pl.fprop):
+                if cl.packed is None or cl.packed.dtype != act_dtype():
+                    cl.packed = torch.zeros(elems, dtype=act_dtype(), device=w.device)
+                ops.pack_part(self._w2[t], cl.packed, cl.wtap_dev, self.cout, khw, self.KF, self.KF, khw * self.KF, 1, self.KF,
+                              0, 0, bn, nkb)
+        self.keys[("fold", in_dims)] = key
+        return pl
+
+    def fold_wgrad(self, in_dims, xs: View, dy: View, dw: torch.Tensor):
+        """dw (Cout, Cin, kt, kh, kw) += wgrad: one launch per output frame into dW2[t], then the adjoint of the fold."""
+        pl = self.fold_plan(in_dims)
+        To = pl.out_dims[0]
+        khw = self.k[1] * self.k[2]
+        dw2 = torch.zeros((To, self.cout, khw, self.KF), dtype=torch.float32, device=dw.device)
+        pre = (ops.split_bf16(xs), ops.split_bf16(dy)) if PREC.mode else None
+        for t in range(To):
+            ops.conv_wgrad(pl, xs, dy, dw2[t], atomic=True, pp=(t, 0, 0), presplit=pre)
+        ops.stem_unfold_wgrad(dw2, dw, self.cout, self.cin, self.k[0], khw, self.stride[0], To, self.KF)
+
+    # ---- im2col path -------------------------------------------------------------------------------------
     def im2col(self, x: View) -> torch.Tensor:
         od, pf = self.geometry(x.dims)
         col = torch.empty((x.N,) + od + (self.Kpad,), dtype=act_dtype(), device=x.t.device)
@@ -254,16 +339,23 @@ class UnitSaved:
 def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: bool, groups: int) -> UnitSaved:
     """Unit3D (pytorch_i3d.py:89-120): same-pad conv (tcgen05) -> BatchNorm3d -> ReLU, written into `y`."""
     col = None
-    if isinstance(layer, StemLayer):
-        col = layer.im2col(x)
-        x = View(col)
-    pl = layer.packed(x.dims, "fprop")
+    folded = isinstance(layer, StemLayer) and layer.use_fold(x.dims)
+    orig_dims = x.dims
+    if folded:
+        x = layer.fold_input(x)
+        col = x.t
+        pl = layer.packed_fold(orig_dims)
+    else:
+        if isinstance(layer, StemLayer):
+            col = layer.im2col(x)
+            x = View(col)
+        pl = layer.packed(x.dims, "fprop")
     N = x.N
     Cout = pl.spec.Cout_pad
     raw = torch.empty((N,) + tuple(pl.out_dims) + (Cout,), dtype=act_dtype(), device=x.t.device)
     ops.conv_fprop(pl, "fprop", x, View(raw))
     sv = UnitSaved()
-    sv.raw, sv.dims, sv.col = raw, x.dims, col
+    sv.raw, sv.dims, sv.col = raw, (orig_dims if folded else x.dims), col
     rv_ = View(raw)
     if training:
         g = groups
@@ -297,6 +389,9 @@ def unit_bwd(layer: ConvLayer, gamma, beta, sv: UnitSaved, x: View, y: View, gy:
     dw, d0 = grad_buf(layer.weight)
     if isinstance(layer, StemLayer):
         assert dx is None, "the few-channel stem does not propagate a gradient to its input"
+        if sv.col.shape[-1] == layer.KF and sv.col.shape[1] == 1 and layer.use_fold(sv.dims):
+            layer.fold_wgrad(sv.dims, View(sv.col), View(draw), dw)
+            return (None if d0 else dw), (None if d1 else dgamma), (None if d2 else dbeta)
         scratch = torch.zeros((layer.cout, layer.Kpad), dtype=torch.float32, device=dev)
         ops.conv_wgrad(layer.plan(sv.dims), View(sv.col), View(draw), scratch, atomic=True)
         layer.scatter_wgrad(scratch, dw)

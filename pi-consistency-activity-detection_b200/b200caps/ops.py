@@ -55,18 +55,18 @@ def split_bf16(v: View):
     return View(hi), View(lo)
 
 
-def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None, per_clip=False):
+def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None, per_clip=False,
+               pp=(0, 0, 0), presplit=None):
     name = (f"wgrad {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
             f"{' T' if plan.spec.transposed else ''}")
     if PREC.mode:
         # tf32 mode: 3 x bf16 split GEMMs accumulated into dw (see b2c_split_bf16); dw must be zero / an accumulator
         assert atomic, "tf32-mode wgrad accumulates"
-        xh, xl = split_bf16(x)
-        dh, dl = split_bf16(dy)
+        (xh, xl), (dh, dl) = presplit if presplit is not None else (split_bf16(x), split_bf16(dy))
         for a, b in ((xh, dh), (xh, dl), (xl, dh)):
-            _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True))
+            _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True, pp=pp))
         return
-    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part, per_clip)
+    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part, per_clip, pp=pp)
     _launch(name, "b2c_conv_wgrad", d)
 
 
@@ -78,6 +78,10 @@ class PackRegistry:
         self.jobs = {}           # (w_ptr, packed_ptr, r_off, col_off) -> PackJob fields
         self.table = None        # (jobs_dev, block_start_dev, njobs, nblocks)
         self.flushed_epoch = -1
+        self.pre = {}            # key -> callable launched before the batched pack (derived fp32 sources: folded stem weights)
+
+    def add_pre(self, key, fn):
+        self.pre.setdefault(key, fn)
 
     def add(self, key, fields):
         if key not in self.jobs:
@@ -102,6 +106,8 @@ class PackRegistry:
             bs = torch.tensor(starts, dtype=torch.int32, device=dev)
             self.table = (raw, bs, len(self.jobs), starts[-1])
         raw, bs, nj, nb = self.table
+        for fn in self.pre.values():
+            fn()
         _abi.call("b2c_pack_weights_batched", _p(raw), _p(bs), nj, nb, stream())
         self.flushed_epoch = epoch
         return True
@@ -142,6 +148,19 @@ def cl_to_ncdhw_f32(v: View) -> torch.Tensor:
 
 def im2col_small(x: View, out: torch.Tensor, C, out_dims, k, s, pf, Kpad):
     _abi.call("b2c_im2col_small", x.ptr, _p(out), x.N, x.row_stride, C, *x.dims, *out_dims, *k, *s, *pf, Kpad, stream())
+
+
+def stem_fold_input(x: View, xs: torch.Tensor, pt: int, Tp: int):
+    T, H, W = x.dims
+    _abi.call("b2c_stem_fold_input", x.ptr, _p(xs), x.N, T, H, W, x.row_stride, pt, Tp, stream())
+
+
+def stem_fold_weights(w, w2, cout, cin, kt, khw, st, To, Kf):
+    _abi.call("b2c_stem_fold_weights", _p(w), _p(w2), cout, cin, kt, khw, st, To, Kf, stream())
+
+
+def stem_unfold_wgrad(dw2, dw, cout, cin, kt, khw, st, To, Kf):
+    _abi.call("b2c_stem_unfold_wgrad", _p(dw2), _p(dw), cout, cin, kt, khw, st, To, Kf, stream())
 
 
 # ---- batch norm -----------------------------------------------------------------------------

@@ -348,7 +348,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
 
 
 def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0,
-                    part=None, per_clip=False, force_bf16=False) -> _abi.WgradDesc:
+                    part=None, per_clip=False, force_bf16=False, pp=(0, 0, 0)) -> _abi.WgradDesc:
     """x = layer input, dy = gradient of the layer output, dw = fp32 gradient in torch weight layout.
     part=(c_off, C): restrict a fused layer's wgrad to the output-channel window of one member weight."""
     geo = dict(plan.wgrad_geom)
@@ -377,7 +377,7 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
     d.Qt, d.Qh, d.Qw = geo["Q"]
     d.sg_t, d.sg_h, d.sg_w = geo["sg"]
     d.sp_t, d.sp_h, d.sp_w = geo["sp"]
-    d.pp_t = d.pp_h = d.pp_w = 0
+    d.pp_t, d.pp_h, d.pp_w = pp        # position offset of the plain operand (folded stem: output frame t)
     d.ntaps, d.bn_tile, d.nsplit, d.atomic = len(cl.taps), int(bn_tile), int(nsplit), int(atomic)
     if per_clip:      # dw is (N, ...): one gradient per clip
         assert dw.shape[0] == x.N

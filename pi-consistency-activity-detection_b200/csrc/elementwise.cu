@@ -571,6 +571,74 @@ __global__ void __launch_bounds__(kBlock) split_bf16_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Folded stem (Conv3d_1a_7x7, pytorch_i3d.py:224: 3 -> 64, 7x7x7, stride 2): the time axis is folded into the channel
+// axis so that the few-channel 3-D convolution becomes a 2-D convolution over 64 "channels" on the TMA im2col path,
+// without the (rows x 1088) im2col matrix (3.5 GB written and read twice per step at 16+16 clips).
+//   xs[n][h][w][fp * 4 + c] = x[n][fp - pt][h][w][c]   (fp = padded frame index, zero outside the clip; c < 4)
+// Output frame t reads padded frames st*t .. st*t + kt - 1: one weight set per output frame (an output class of the
+// implicit GEMM) holds the kernel shifted to that window,
+//   W2[t][co][kh*kw_+kw][fp * 4 + c] = w[co][c][fp - st*t][kh][kw]   (zero outside the window / for c >= Cin).
+struct StemFold {
+  int N, T, H, W, Cs, pt, Tp;     // Tp = padded frames held per pixel (Tp * 4 = folded channels, <= 16)
+};
+template <typename T>
+__global__ void __launch_bounds__(kBlock) stem_fold_input_kernel(const T* __restrict__ x, T* __restrict__ xs, StemFold G, long long total) {
+  // one thread per (pixel, pair of padded frames): 8 folded channels = one 16-byte (bf16) / 32-byte (fp32) store
+  const int pairs = G.Tp / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % pairs);
+    long long pix = i / pairs;                       // (n, h, w)
+    const long long hw = (long long)G.H * G.W;
+    const long long n = pix / hw, r = pix - n * hw;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = 2 * q + j - G.pt;
+      float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (f >= 0 && f < G.T) ld8(x + ((n * G.T + f) * hw + r) * G.Cs, t8);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[j * 4 + c] = t8[c];
+    }
+    st8(xs + pix * (G.Tp * 4) + q * 8, v, false);      // values are already operand-rounded
+  }
+}
+
+__global__ void stem_fold_weights_kernel(const float* __restrict__ w, float* __restrict__ w2, int Cout, int Cin, int kt, int khw, int st,
+                                         int To, int Kf) {
+  const long long total = (long long)To * Cout * khw * Kf;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % Kf);
+    long long r = i / Kf;
+    const int tap = (int)(r % khw);
+    r /= khw;
+    const int co = (int)(r % Cout), t = (int)(r / Cout);
+    const int fp = e >> 2, c = e & 3, k = fp - st * t;
+    float v = 0.f;
+    if (c < Cin && k >= 0 && k < kt) v = w[(((long long)co * Cin + c) * kt + k) * khw + tap];
+    w2[i] = v;
+  }
+}
+
+// dw[co][c][k][kh][kw] += sum_t dW2[t][co][tap][(st*t + k) * 4 + c]
+__global__ void stem_unfold_wgrad_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int Cout, int Cin, int kt, int khw, int st,
+                                         int To, int Kf) {
+  const long long total = (long long)Cout * Cin * kt * khw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % khw);
+    long long r = i / khw;
+    const int k = (int)(r % kt);
+    r /= kt;
+    const int c = (int)(r % Cin), co = (int)(r / Cin);
+    float acc = 0.f;
+    for (int t = 0; t < To; ++t) {
+      const int e = (st * t + k) * 4 + c;
+      if (e < Kf) acc += dw2[(((long long)t * Cout + co) * khw + tap) * Kf + e];
+    }
+    dw[i] += acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // smooth = ConvTranspose3d(128->1, k3, p1): out[o] = bias + sum_k P_k[o + 1 - k], P planar fp32 [32][rows]
 __global__ void __launch_bounds__(kBlock) stencil27_fwd_kernel(const float* __restrict__ P, float* __restrict__ out,
                                                                const float* __restrict__ bias_p, int N, int T, int H, int W) {
@@ -960,6 +1028,38 @@ B2C_API int b2c_add(const void* a, int64_t a_rs, int32_t a_co, const void* b, in
   LAUNCH_T(add_kernel, grid_for(rows * (C / 8)), kBlock, 0, s, (const T*)a, a_rs, a_co, (const T*)b, b_rs, b_co, (T*)out, o_rs, o_co, rows, C);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("add");
+  return 0;
+}
+
+B2C_API int b2c_stem_fold_input(const void* x, void* xs, int32_t N, int32_t T, int32_t H, int32_t W, int32_t Cs, int32_t pt,
+                                int32_t Tp, b2c_stream_t s) {
+  B2C_REQUIRE(x && xs && N > 0 && T > 0 && Cs == 8 && Tp > 0 && Tp % 2 == 0 && Tp <= 16 && pt >= 0 && pt + T <= Tp, "stem_fold_input: bad args");
+  StemFold G{N, T, H, W, Cs, pt, Tp};
+  const long long total = (long long)N * H * W * (Tp / 2);
+  if (b2c_precision())
+    stem_fold_input_kernel<float><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const float*)x, (float*)xs, G, total);
+  else
+    stem_fold_input_kernel<bf16><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, (bf16*)xs, G, total);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("stem_fold_input");
+  return 0;
+}
+
+B2C_API int b2c_stem_fold_weights(const float* w, float* w2, int32_t Cout, int32_t Cin, int32_t kt, int32_t khw, int32_t st, int32_t To,
+                                  int32_t Kf, b2c_stream_t s) {
+  B2C_REQUIRE(w && w2 && Cout > 0 && Cin > 0 && Cin <= 4 && kt > 0 && khw > 0 && st > 0 && To > 0 && Kf % 4 == 0, "stem_fold_weights: bad args");
+  stem_fold_weights_kernel<<<grid_for((long long)To * Cout * khw * Kf), kBlock, 0, (cudaStream_t)s>>>(w, w2, Cout, Cin, kt, khw, st, To, Kf);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("stem_fold_weights");
+  return 0;
+}
+
+B2C_API int b2c_stem_unfold_wgrad(const float* dw2, float* dw, int32_t Cout, int32_t Cin, int32_t kt, int32_t khw, int32_t st, int32_t To,
+                                  int32_t Kf, b2c_stream_t s) {
+  B2C_REQUIRE(dw2 && dw && Cout > 0 && Cin > 0 && Cin <= 4 && kt > 0 && khw > 0 && st > 0 && To > 0 && Kf % 4 == 0, "stem_unfold_wgrad: bad args");
+  stem_unfold_wgrad_kernel<<<grid_for((long long)Cout * Cin * kt * khw), kBlock, 0, (cudaStream_t)s>>>(dw2, dw, Cout, Cin, kt, khw, st, To, Kf);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("stem_unfold_wgrad");
   return 0;
 }
 

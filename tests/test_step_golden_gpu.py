@@ -40,7 +40,8 @@ def oracle_dev(clips: int, cfg: str = "bv5", prec: str = "bf16"):
     """The reference's own deviation (oracle vs oracle with the CUDA path's rounding points emulated) for this
     configuration: profiles/r02_conditioning[_tf32][_gv].json, written by tools/conditioning_probe.py."""
     def one(gv):
-        name = "r02_conditioning" + ("_tf32" if prec == "tf32" else "") + ("_gv" if gv else "") + ".json"
+        name = "r02_conditioning" + ("_jhmdb" if cfg.startswith("jhmdb") else "") + ("_tf32" if prec == "tf32" else "") + \
+            ("_gv" if gv else "") + ".json"
         with open(os.path.join(PROF, name)) as f:
             return json.load(f)[f"{clips}+{clips}"]
     if cfg.endswith("bv_gv"):

@@ -29,9 +29,9 @@ def rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-300))
 
 
-def run(n_lab, n_unl, mode, grads=True, rounding="bf16"):
-    sd = restate.make_state_dict(24, seed=0, dtype=torch.float64)
-    b = restate.synthetic_batch(n_lab, n_unl, seed=47, dtype=torch.float64)
+def run(n_lab, n_unl, mode, grads=True, rounding="bf16", classes=24):
+    sd = restate.make_state_dict(classes, seed=0, dtype=torch.float64)
+    b = restate.synthetic_batch(n_lab, n_unl, seed=47, dtype=torch.float64, num_classes=classes)
     masks = restate.make_drop_masks(n_lab + n_unl, seed=3, count=4, dtype=torch.float64)
     out = {}
     res = {}
@@ -78,13 +78,14 @@ def main():
     ap.add_argument("--mode", default="bv")
     ap.add_argument("--no-grads", action="store_true")
     ap.add_argument("--round", default="bf16", choices=["bf16", "tf32"], help="rounding emulated at the CUDA path's rounding points")
+    ap.add_argument("--classes", type=int, default=24, help="24 = UCF101-24, 21 = JHMDB-21")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     results = {}
     for n in a.clips:
         t0 = time.time()
-        r = run(n, n, a.mode, grads=not a.no_grads, rounding=a.round)
+        r = run(n, n, a.mode, grads=not a.no_grads, rounding=a.round, classes=a.classes)
         r["seconds"] = time.time() - t0
         results[f"{n}+{n}"] = r
         print(f"{n}+{n}", json.dumps(r), flush=True)
