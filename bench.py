@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="bf16 (default) or tf32 = fp32 activations / tcgen05 kind::tf32 operands (the reference's arithmetic)")
+    ap.add_argument("--classes", type=int, default=24, choices=[24, 21], help="24 = UCF101-24 (config 2/3), 21 = JHMDB-21 (config 4)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short config 3 (--gv) / config 4 (JHMDB-21) measurements")
     return ap.parse_args()
 
 
@@ -133,7 +137,7 @@ def synthetic_host_batch(n_lab, n_unl, seed, num_classes=24):
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_step_time(steps: int, warmup: int):
     """The reference's training step (oracle port, fp32, torch CPU autograd) on 1 labeled + 1 unlabeled clip,
-    all host threads.  Returns (seconds per step, threads)."""
+    all host threads.  Returns (median seconds per step, threads, min seconds, all times)."""
     import torch
     from oracle import restate
     threads = os.cpu_count() or 1
@@ -152,7 +156,37 @@ def cpu_reference_step_time(steps: int, warmup: int):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return sum(times) / len(times), threads
+    ts = sorted(times)
+    return ts[len(ts) // 2], threads, ts[0], times
+
+
+def cpu_config1_time(steps: int = 5, warmup: int = 1):
+    """CapsNet().train(), batch 2, supervised BCE + Dice + Spread loss, forward + backward
+    (oracle port of the reference classes), all host threads: (median s, min s, threads)."""
+    import torch
+    from oracle import restate
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = restate.make_state_dict(24, seed=0)
+    sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(0)
+    data = torch.rand((2, 3, 8, 224, 224), generator=g)
+    action = torch.randint(0, 24, (2, 1), generator=g).float()
+    seg = (torch.rand((2, 1, 8, 224, 224), generator=g) > 0.7).float()
+    labels = torch.ones(2)
+    names = [k for k, v in sdg.items() if v.requires_grad]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out, act, _ = restate.capsnet_forward(sdg, data, action, labels, 1, 11, True, None, restate.BNState(True))
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(out, seg) + restate.dice_loss(out, seg) + \
+            restate.spread_loss(act, action, 0.2, 0.9)[0]
+        torch.autograd.grad(loss, [sdg[k] for k in names], allow_unused=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ts = sorted(times)
+    return ts[len(ts) // 2], ts[0], threads
 
 
 def run_reference(args):
@@ -160,15 +194,15 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    sec, threads = cpu_reference_step_time(max(1, args.steps), max(0, args.warmup))
+    sec, threads, sec_min, _ = cpu_reference_step_time(max(1, args.steps), max(0, args.warmup))
     value = 2.0 / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic (U[0,1) clips, random-init weights)",
         "config": {"workload": WORKLOAD, "sample": "1 labeled + 1 unlabeled clip per step (bounded sample of the 8+8 workload)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "oracle port of train_model_interface + backward, 1+1 clips, fp32, torch CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "median_s_per_step": sec, "min_s_per_step": sec_min,
+                         "sample": "oracle port of train_model_interface + backward, 1+1 clips, fp32, torch CPU, median over the timed steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -188,16 +222,20 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from b200caps import _abi, ops
+    from b200caps import _abi, ops, plans
     from b200caps.step import StepArgs, TrainStep
-    from models.capsules_ucf101 import CapsNet
+    if args.classes == 21:
+        from models.capsules_jhmdb_semi_sup_pa import CapsNet
+    else:
+        from models.capsules_ucf101 import CapsNet
+    plans.set_precision(args.precision)
 
     torch.manual_seed(47 + rank)
     model = CapsNet(pt_path=None).to(dev)
     sa = StepArgs(bv=args.mode in ("bv", "bvgv"), gv=args.mode in ("gv", "bvgv"), n_frames=5, wt_cons=0.1, lr=1e-4)
     step = TrainStep(model, sa)
     P = 2 * args.clips
-    hb = synthetic_host_batch(args.clips, args.clips, seed=47 + rank)
+    hb = synthetic_host_batch(args.clips, args.clips, seed=47 + rank, num_classes=args.classes)
     db = {k: (v.to(dev) if k != "labels" else v) for k, v in hb.items()}
 
     def barrier():
@@ -276,7 +314,7 @@ def run_ours(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = P * world / (ms_e2e / 1e3)
 
-    # ---- kernel-level timing of the dominant kernel family (tcgen05 implicit GEMM) -------------------------
+    # ---- kernel-level timing: the dominant family (tcgen05 implicit GEMM) and every bandwidth-class kernel ------------
     roofline = None
     if rank == 0 and not args.no_kernel_timing:
         peaks = {}
@@ -284,39 +322,66 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        ops.TIMING = []
+        tf32 = args.precision == "tf32"
+        # tf32 tensor peak = half the bf16 one (B200_PROFILING.md: 1.1 vs 2.25 PFLOP/s nominal)
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) * (0.5 if tf32 else 1.0)
+        burst = (float(peaks["bf16_tflops"]) * (0.5 if tf32 else 1.0)) if peaks.get("bf16_tflops") else None
+        hbm = float(peaks.get("hbm_gbs", 6553.3))
+        ops.TIMING, ops.BW_TIMING = [], []
         step(db["data"], db["fl_data"], db["action"], db["seg"], db["labels"], epoch=1)   # eager, instrumented
         torch.cuda.synchronize()
         recs, ops.TIMING = ops.TIMING, None
-        t_ms = sum(a.elapsed_time(b) for _, a, b in recs)
-        achieved = FLOP_PER_CLIP * P / (t_ms / 1e3) / 1e12
-        # DRAM traffic of the same launches from the committed ncu pass (profiles/r01_traffic.json, written by
+        bw, ops.BW_TIMING = ops.BW_TIMING, None
+        t_ms = sum(a.elapsed_time(b) for _, a, b, _ in recs)
+        flop_alg = FLOP_PER_CLIP * P * (11.40 / 11.42 if args.classes == 21 else 1.0)
+        flop_exec = 2.0 * sum(m for _, _, _, m in recs)
+        achieved = flop_alg / (t_ms / 1e3) / 1e12
+        # DRAM traffic of the same launches from the committed ncu pass (profiles/r0N_traffic.json, written by
         # tools/summarize_profiles.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): per launch, like
         # `achieved` (total over the step's conv launches / number of launches)
         traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if int(tj.get("clips_per_gpu", P)) == P:
-                traffic = float(tj["igemm_dram_bytes_per_step"]) / max(1, len(recs))
-        except Exception:
-            pass
+        for tag in ("r02", "r01"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")))
+                if int(tj.get("clips_per_gpu", P)) == P and args.precision == tj.get("precision", "bf16") and args.classes == 24:
+                    traffic = float(tj["igemm_dram_bytes_per_step"]) / max(1, int(tj.get("launches", len(recs))))
+                    break
+            except Exception:
+                pass
         top = max(recs, key=lambda r: r[1].elapsed_time(r[2])) if recs else None
+        fam = {}
+        for name, a, b, nbytes in bw:
+            f = fam.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+            f["launches"] += 1
+            f["ms"] += a.elapsed_time(b)
+            f["bytes"] += nbytes
+        for f in fam.values():
+            f["GBps"] = f["bytes"] / max(f["ms"], 1e-9) / 1e6
+            f["frac_of_hbm"] = f["GBps"] / hbm
+        bw_ms = sum(f["ms"] for f in fam.values())
+        bw_bytes = sum(f["bytes"] for f in fam.values())
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, mean over the step's conv launches)",
-                    "algorithmic_flop_per_launch": FLOP_PER_CLIP * P / max(1, len(recs)),
+                    "algorithmic_flop_per_launch": flop_alg / max(1, len(recs)),
                     "longest_launch": {"layer": top[0], "ms": top[1].elapsed_time(top[2])} if top else None,
                     "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (all conv / transposed-conv launches)",
                     "kernel_ms_per_step": t_ms, "kernel_launches_per_step": len(recs),
-                    "peak_burst": float(peaks.get("bf16_tflops", 0.0)) or None,
-                    "frac_of_burst": (achieved / float(peaks["bf16_tflops"])) if peaks.get("bf16_tflops") else None,
-                    "share_of_step": t_ms / ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+                    "peak_burst": burst, "frac_of_burst": (achieved / burst) if burst else None,
+                    "share_of_step": t_ms / ms, "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained" + (" x 0.5 (tf32)" if tf32 else ""))
                     if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
-                    "algorithmic_flop_per_step": FLOP_PER_CLIP * P}
+                    "algorithmic_flop_per_step": flop_alg,
+                    # the decoder tail runs as a collapsed per-clip transposed conv and the stem as a folded 2-D conv
+                    # with zero-padded K: `achieved` counts the REFERENCE formulation's FLOPs (the contract's algorithmic
+                    # figure); the FLOPs the tensor cores actually execute and their rate are stated beside it
+                    "executed_flop_per_step": flop_exec, "executed_tflops": flop_exec / (t_ms / 1e3) / 1e12,
+                    "executed_frac": flop_exec / (t_ms / 1e3) / 1e12 / peak,
+                    "bandwidth_kernels": {"hbm_peak_GBps": hbm, "ms_per_step": bw_ms, "bytes_per_step": bw_bytes,
+                                          "GBps": bw_bytes / max(bw_ms, 1e-9) / 1e6, "frac_of_hbm": bw_bytes / max(bw_ms, 1e-9) / 1e6 / hbm,
+                                          "bytes": "algorithmic (every operand element once)", "by_kernel": fam}}
         if world == 1:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             agg, kinds = {}, {}
-            for tag, a, b in recs:
+            for tag, a, b, _ in recs:
                 d = agg.setdefault(tag, [0, 0.0])
                 d[0] += 1
                 d[1] += a.elapsed_time(b)
@@ -325,30 +390,65 @@ def run_ours(args):
                 k[1] += a.elapsed_time(b)
             top = sorted(agg.items(), key=lambda kv: -kv[1][1])
             with open(os.path.join(ROOT, "gpurun_out", "igemm_kernel_times.json"), "w") as f:
-                json.dump({"ms_per_step_total": t_ms, "by_kind": kinds, "by_layer_sorted": top}, f, indent=1)
+                json.dump({"ms_per_step_total": t_ms, "by_kind": kinds, "by_layer_sorted": top, "bandwidth_kernels": fam}, f, indent=1)
     if world > 1:
         dist.barrier()
 
+    # ---- the other single-GPU BASELINE configs, short runs (graph replay, device-resident inputs) ----------------------
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs and use_graph and args.mode == "bv" and args.classes == 24:
+        other = {}
+        del step, model
+        torch.cuda.empty_cache()
+        for tag, mode, classes in (("config3_ucf24_gv", "gv", 24), ("config4_jhmdb21_bv", "bv", 21)):
+            if classes == 21:
+                from models.capsules_jhmdb_semi_sup_pa import CapsNet as Net
+            else:
+                from models.capsules_ucf101 import CapsNet as Net
+            m2 = Net(pt_path=None).to(dev)
+            s2 = TrainStep(m2, StepArgs(bv=mode == "bv", gv=mode == "gv", n_frames=5, wt_cons=0.1, lr=1e-4))
+            hb2 = synthetic_host_batch(args.clips, args.clips, seed=47, num_classes=classes)
+            d2 = [hb2[k].to(dev) for k in ("data", "fl_data", "action", "seg")]
+            s2.capture(P, hb2["labels"], epoch=1, init_batch=d2)
+            s2.replay(*d2)
+            for _ in range(5):
+                s2.replay()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(20):
+                r2 = s2.replay()
+            a1.record()
+            torch.cuda.synchronize()
+            t2 = a0.elapsed_time(a1) / 20
+            other[tag] = {"ms_per_step": t2, "value": P / (t2 / 1e3), "unit": UNIT, "steps": 20, "warmup": 5, "loss_last_step": float(r2["total"])}
+            del s2, m2
+            torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, threads = cpu_reference_step_time(3, 1)
-        cpu_baseline = {"value": 2.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "oracle port of the full --bv step + backward, 1 labeled + 1 unlabeled clip, fp32, 1 warm-up + 3 timed (mean)"}
+        sec, threads, sec_min, _ = cpu_reference_step_time(5, 1)
+        c1_med, c1_min, _ = cpu_config1_time(5, 1)
+        cpu_baseline = {"value": 2.0 / sec, "unit": UNIT, "cores": threads, "kind": "port", "median_s_per_step": sec, "min_s_per_step": sec_min,
+                        "sample": "oracle port of the full --bv step + backward, 1 labeled + 1 unlabeled clip, fp32, 1 warm-up + 5 timed (median)",
+                        "config1": {"value": 2.0 / c1_med, "unit": UNIT, "median_s_per_step": c1_med, "min_s_per_step": c1_min,
+                                    "sample": "BASELINE.md section 4 config 1: supervised BCE + Dice + Spread, batch 2, forward + backward, "
+                                              "1 warm-up + 5 timed (median)"}}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic (U[0,1) 8x224x224 clips, random box masks, random-init weights)",
             "config": {"workload": WORKLOAD if world == 1 else WORKLOAD.replace("1xB200", f"{world}xB200 data-parallel, NCCL all-reduce"),
-                       "clips_per_gpu": P, "mode": args.mode, "n_frames": 5, "cuda_graph": use_graph,
+                       "clips_per_gpu": P, "mode": args.mode, "classes": args.classes, "n_frames": 5, "cuda_graph": use_graph,
                        "l2": "working set per step (>20 GB of activations) >> 126 MB L2; no explicit flush",
                        "e2e_pipeline": "graph mode: the pinned-host -> device copy of step i+1 runs on a copy stream under the compute "
                                        "of step i (TrainStep.prefetch); every step's inputs are copied inside the timed region",
                        "parallelism": f"dp{world}", "loss_last_step": loss_val},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-            "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline, "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

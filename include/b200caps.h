@@ -71,7 +71,8 @@ typedef struct {
   int32_t stat_groups;  /* statistic groups of stat_sums: the batch N splits into stat_groups equal runs of clips */
   int32_t round_out;    /* dtype 1 only: round the stored fp32 result to tf32 (it is the next GEMM's operand) */
   int32_t nclass;
-  int32_t pad0_;
+  int32_t out_fold;     /* 0, or a multiple of 64: output column c is stored in T-plane po_t + c / out_fold at channel c % out_fold
+                           (folded stem: the output frames of a pixel are column blocks of one GEMM row; one class, Qt = 1) */
   int64_t w_sample_stride; /* bytes between the packed weight sets of consecutive clips (every class pointer `w` is the set of
                               clip 0); 0 = one set for all clips.  != 0 needs the TMA path and 128-row tiles that do not
                               straddle clips.  Used by the collapsed decoder tail (per-clip composite weights). */
@@ -101,7 +102,9 @@ typedef struct {
   int32_t bn_tile; /* 0 = auto */
   int32_t nsplit;  /* 0 = auto */
   int32_t atomic;  /* 1: atomicAdd into dw, 0: plain store (only legal when nsplit==1) */
-  int32_t dtype;   /* 0: bf16 operands, 1: fp32 tensors / tf32 operands */
+  int32_t dtype;   /* 0: bf16 operands (the only supported value; tf32 mode passes bf16 hi / lo splits, b2c_split_bf16) */
+  int32_t p_fold;  /* 0, or a multiple of 64: p-channel c is read from T-plane pp_t + c / p_fold at channel c % p_fold (folded stem) */
+  int32_t pad1_;
   int64_t dw_sample_stride; /* elements between per-clip gradients dw[n]; 0 = one dw summed over all clips.  != 0: the
                                position split is a multiple of N so that no CTA straddles clips */
 } b2c_wgrad_desc;

@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
                 ("si_t", i32), ("si_h", i32), ("si_w", i32), ("so_t", i32), ("so_h", i32), ("so_w", i32),
                 ("out_fp32", i32), ("relu", i32), ("sigmoid_from", i32), ("accumulate", i32), ("bn_tile", i32),
                 ("tap_pitch", i32), ("dtype", i32), ("stat_groups", i32), ("round_out", i32),
-                ("nclass", i32), ("pad0_", i32), ("w_sample_stride", i64), ("cls", ConvClass * 8)]
+                ("nclass", i32), ("out_fold", i32), ("w_sample_stride", i64), ("cls", ConvClass * 8)]
 
 
 class WgradDesc(C.Structure):
@@ -39,7 +39,7 @@ class WgradDesc(C.Structure):
                 ("sg_t", i32), ("sg_h", i32), ("sg_w", i32), ("sp_t", i32), ("sp_h", i32), ("sp_w", i32),
                 ("pp_t", i32), ("pp_h", i32), ("pp_w", i32),
                 ("ntaps", i32), ("bn_tile", i32), ("nsplit", i32), ("atomic", i32), ("dtype", i32),
-                ("dw_sample_stride", i64)]
+                ("p_fold", i32), ("pad1_", i32), ("dw_sample_stride", i64)]
 
 
 class PackJob(C.Structure):

@@ -218,8 +218,8 @@ class StemLayer(ConvLayer):
     def use_fold(self, in_dims) -> bool:
         od, pf = self.geometry(in_dims)
         last = self.stride[0] * (od[0] - 1) + self.k[0]          # padded frames touched
-        return (self.fold_enabled and self.cin <= 4 and od[0] <= 8 and od[0] in (1, 2, 4, 8) and last <= 16
-                and pf[0] + in_dims[0] <= 16)
+        return (self.fold_enabled and self.cin <= 4 and od[0] * self.cout <= 256 and self.cout % 64 == 0 and last <= 16
+                and pf[0] + in_dims[0] <= 16 and (od[1] * od[2]) % 64 == 0)
 
     def fold_input(self, x: View) -> View:
         od, pf = self.geometry(x.dims)
@@ -233,22 +233,23 @@ class StemLayer(ConvLayer):
         key = ("fold", in_dims)
         pl = self.plans.get(key)
         if pl is None:
-            from .plans import TapClass
             od, pf = self.geometry(in_dims)
             T, H, W = in_dims
+            To = od[0]
             pads = [same_pad(d, kk, ss) for d, kk, ss in zip(in_dims, self.k, self.stride)]
-            spec = ConvSpec(self.KF, self.cout, (1, self.k[1], self.k[2]), (1, self.stride[1], self.stride[2]),
+            # one GEMM row per output pixel (n, h, w); its To * Cout columns are the output frames (out_fold = Cout)
+            spec = ConvSpec(self.KF, To * self.cout, (1, self.k[1], self.k[2]), (1, self.stride[1], self.stride[2]),
                             (0, pads[1][0], pads[2][0]), (0, pads[1][1], pads[2][1]))
             pl = ConvPlan(spec, (1, H, W))
             b = pl.fprop[0]
-            wt = [i * self.KF for i in range(len(b.taps))]          # tap offset inside W2[t] / dW2[t]: (Cout, khw, KF)
-            pl.fprop = [TapClass(list(b.taps), list(wt), b.Q, (t, 0, 0)) for t in range(od[0])]
+            b.wtap = [i * self.KF for i in range(len(b.taps))]        # tap offset inside W2 / dW2: (To * Cout, khw, KF)
             pl.dgrad = []                                             # the stem input needs no gradient
             pl.out_dims = tuple(od)
             khw = self.k[1] * self.k[2]
-            pl.fprop_pack = dict(R=self.cout, R_pad=self.cout, C=self.KF, C_real=self.KF, s_r=khw * self.KF, s_c=1)
-            pl.wgrad_cls = pl.fprop[0]
-            pl.wgrad_geom = dict(pl.wgrad_geom, s_p=khw * self.KF, s_g=1, Q=(1, od[1], od[2]))
+            pl.fprop_pack = dict(R=To * self.cout, R_pad=To * self.cout, C=self.KF, C_real=self.KF, s_r=khw * self.KF, s_c=1,
+                                 out_fold=self.cout)
+            pl.wgrad_cls = b
+            pl.wgrad_geom = dict(pl.wgrad_geom, s_p=khw * self.KF, s_g=1, Q=(1, od[1], od[2]), p_fold=self.cout)
             self.plans[key] = pl
         return pl.to(self.weight.device)
 
@@ -270,24 +271,23 @@ class StemLayer(ConvLayer):
             self._refresh_w2(To)
             if ops.PACKS is not None:
                 ops.PACKS.add_pre(("stem", id(self)), lambda To=To: self._refresh_w2(To))
-            bn, _, nkb, elems = packed_geometry(self.cout, khw * self.KF)
-            for t, cl in enumerate(pl.fprop):
-                if cl.packed is None or cl.packed.dtype != act_dtype():
-                    cl.packed = torch.zeros(elems, dtype=act_dtype(), device=w.device)
-                ops.pack_part(self._w2[t], cl.packed, cl.wtap_dev, self.cout, khw, self.KF, self.KF, khw * self.KF, 1, self.KF,
-                              0, 0, bn, nkb)
+            bn, _, nkb, elems = packed_geometry(To * self.cout, khw * self.KF)
+            cl = pl.fprop[0]
+            if cl.packed is None or cl.packed.dtype != act_dtype():
+                cl.packed = torch.zeros(elems, dtype=act_dtype(), device=w.device)
+            ops.pack_part(self._w2, cl.packed, cl.wtap_dev, To * self.cout, khw, self.KF, self.KF, khw * self.KF, 1, self.KF,
+                          0, 0, bn, nkb)
         self.keys[("fold", in_dims)] = key
         return pl
 
     def fold_wgrad(self, in_dims, xs: View, dy: View, dw: torch.Tensor):
-        """dw (Cout, Cin, kt, kh, kw) += wgrad: one launch per output frame into dW2[t], then the adjoint of the fold."""
+        """dw (Cout, Cin, kt, kh, kw) += wgrad: ONE launch with N = To * Cout columns (dy's frames are the p-channel blocks)
+        into dW2, then the adjoint of the weight fold."""
         pl = self.fold_plan(in_dims)
         To = pl.out_dims[0]
         khw = self.k[1] * self.k[2]
         dw2 = torch.zeros((To, self.cout, khw, self.KF), dtype=torch.float32, device=dw.device)
-        pre = (ops.split_bf16(xs), ops.split_bf16(dy)) if PREC.mode else None
-        for t in range(To):
-            ops.conv_wgrad(pl, xs, dy, dw2[t], atomic=True, pp=(t, 0, 0), presplit=pre)
+        ops.conv_wgrad(pl, xs, dy, dw2, atomic=True)
         ops.stem_unfold_wgrad(dw2, dw, self.cout, self.cin, self.k[0], khw, self.stride[0], To, self.KF)
 
     # ---- im2col path -------------------------------------------------------------------------------------
@@ -351,7 +351,7 @@ def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: 
             x = View(col)
         pl = layer.packed(x.dims, "fprop")
     N = x.N
-    Cout = pl.spec.Cout_pad
+    Cout = layer.cout if folded else pl.spec.Cout_pad
     raw = torch.empty((N,) + tuple(pl.out_dims) + (Cout,), dtype=act_dtype(), device=x.t.device)
     ops.conv_fprop(pl, "fprop", x, View(raw))
     sv = UnitSaved()

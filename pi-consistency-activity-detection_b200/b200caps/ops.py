@@ -24,10 +24,29 @@ def _p(t: Optional[torch.Tensor]):
 
 
 # ---- tcgen05 implicit GEMM ---------------------------------------------------------------
-TIMING = None   # bench.py: list collecting (kind, start_event, end_event) of every implicit-GEMM launch
+TIMING = None   # bench.py: list collecting (kind, start_event, end_event, executed MACs) of every implicit-GEMM launch
+BW_TIMING = None  # bench.py: list collecting (kernel family, start_event, end_event, algorithmic bytes) of the other kernels
 
 
-def _launch(kind: str, name: str, desc):
+def _bw(name: str, nbytes: int, *args):
+    """Launch a bandwidth-class kernel; when bench.py instruments the step, bracket it with CUDA events and record the
+    ALGORITHMIC bytes it has to move (every operand element once)."""
+    if BW_TIMING is None:
+        _abi.call(name, *args)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _abi.call(name, *args)
+    b.record()
+    BW_TIMING.append((name[4:], a, b, int(nbytes)))
+
+
+def _vb(v) -> int:
+    """bytes of a channel window view"""
+    return v.rows * v.C * v.t.element_size()
+
+
+def _launch(kind: str, name: str, desc, macs: int = 0):
     if TIMING is None:
         _abi.call(name, C.byref(desc), stream())
         return
@@ -35,7 +54,14 @@ def _launch(kind: str, name: str, desc):
     a.record()
     _abi.call(name, C.byref(desc), stream())
     b.record()
-    TIMING.append((kind, a, b))
+    TIMING.append((kind, a, b, macs))
+
+
+def _macs(plan: ConvPlan, which: str, n: int) -> int:
+    """MACs the launch executes (zero-padded channels excluded): positions x taps x Cin x Cout over the classes."""
+    classes = plan.fprop if which in ("fprop", "wgrad") else plan.dgrad
+    pk = plan.fprop_pack if which in ("fprop", "wgrad") else plan.dgrad_pack
+    return n * sum(c.Q[0] * c.Q[1] * c.Q[2] * len(c.taps) for c in classes) * pk["C_real"] * pk["R"]
 
 
 def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=None, relu=False,
@@ -43,7 +69,7 @@ def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=Non
     """out: View (bf16 / fp32 rows) or a 2-D fp32 tensor (Cout_pad, rows) for the planar epilogue."""
     d = fill_conv_desc(plan, which, x, out, bias, scale_nc, relu, sigmoid_from, accumulate, bn_tile, final)
     _launch(f"{which} {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
-            f"{' T' if plan.spec.transposed else ''}", "b2c_conv_fprop", d)
+            f"{' T' if plan.spec.transposed else ''}", "b2c_conv_fprop", d, _macs(plan, which, x.N) if TIMING is not None else 0)
 
 
 def split_bf16(v: View):
@@ -51,7 +77,7 @@ def split_bf16(v: View):
     shape = tuple(v.t.shape[:-1]) + (v.C,)
     hi = torch.empty(shape, dtype=torch.bfloat16, device=v.t.device)
     lo = torch.empty(shape, dtype=torch.bfloat16, device=v.t.device)
-    _abi.call("b2c_split_bf16", v.ptr, v.row_stride, v.c_off, _p(hi), _p(lo), v.rows, v.C, stream())
+    _bw("b2c_split_bf16", _vb(v) * 2, v.ptr, v.row_stride, v.c_off, _p(hi), _p(lo), v.rows, v.C, stream())
     return View(hi), View(lo)
 
 
@@ -59,15 +85,21 @@ def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True,
                pp=(0, 0, 0), presplit=None):
     name = (f"wgrad {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
             f"{' T' if plan.spec.transposed else ''}")
+    wm = 0
+    if TIMING is not None:
+        cl, geo = plan.wgrad_cls, plan.wgrad_geom
+        cp = part[2] if (part is not None and len(part) > 2) else (part[1] if part is not None else geo.get("Cp_real", geo["Cp"]))
+        wm = x.N * geo["Q"][0] * geo["Q"][1] * geo["Q"][2] * len(cl.taps) * geo["Cg_real"] * cp
     if PREC.mode:
         # tf32 mode: 3 x bf16 split GEMMs accumulated into dw (see b2c_split_bf16); dw must be zero / an accumulator
         assert atomic, "tf32-mode wgrad accumulates"
         (xh, xl), (dh, dl) = presplit if presplit is not None else (split_bf16(x), split_bf16(dy))
         for a, b in ((xh, dh), (xh, dl), (xl, dh)):
-            _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True, pp=pp))
+            _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True, pp=pp),
+                    wm)
         return
     d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part, per_clip, pp=pp)
-    _launch(name, "b2c_conv_wgrad", d)
+    _launch(name, "b2c_conv_wgrad", d, wm)
 
 
 class PackRegistry:
@@ -108,7 +140,7 @@ class PackRegistry:
         raw, bs, nj, nb = self.table
         for fn in self.pre.values():
             fn()
-        _abi.call("b2c_pack_weights_batched", _p(raw), _p(bs), nj, nb, stream())
+        _bw("b2c_pack_weights_batched", sum(j['R'] * j['ntaps'] * j['C'] for j in self.jobs.values()) * 6, _p(raw), _p(bs), nj, nb, stream())
         self.flushed_epoch = epoch
         return True
 
@@ -134,7 +166,7 @@ def ncdhw_to_cl(x: torch.Tensor, cpad: int, out: Optional[torch.Tensor] = None) 
     if out is None:
         out = torch.empty((N, T, H, W, cpad), dtype=act_dtype(), device=x.device)
     assert tuple(out.shape) == (N, T, H, W, cpad) and out.is_contiguous() and out.dtype == act_dtype()
-    _abi.call("b2c_ncdhw_to_ndhwc", _p(x), _p(out), N, Cc, T * H * W, cpad, stream())
+    _bw("b2c_ncdhw_to_ndhwc", x.numel() * 4 + out.numel() * out.element_size(), _p(x), _p(out), N, Cc, T * H * W, cpad, stream())
     return out
 
 
@@ -147,12 +179,12 @@ def cl_to_ncdhw_f32(v: View) -> torch.Tensor:
 
 
 def im2col_small(x: View, out: torch.Tensor, C, out_dims, k, s, pf, Kpad):
-    _abi.call("b2c_im2col_small", x.ptr, _p(out), x.N, x.row_stride, C, *x.dims, *out_dims, *k, *s, *pf, Kpad, stream())
+    _bw("b2c_im2col_small", x.rows * C * x.t.element_size() + out.numel() * out.element_size(), x.ptr, _p(out), x.N, x.row_stride, C, *x.dims, *out_dims, *k, *s, *pf, Kpad, stream())
 
 
 def stem_fold_input(x: View, xs: torch.Tensor, pt: int, Tp: int):
     T, H, W = x.dims
-    _abi.call("b2c_stem_fold_input", x.ptr, _p(xs), x.N, T, H, W, x.row_stride, pt, Tp, stream())
+    _bw("b2c_stem_fold_input", _vb(x) // 8 * 3 + xs.numel() * xs.element_size(), x.ptr, _p(xs), x.N, T, H, W, x.row_stride, pt, Tp, stream())
 
 
 def stem_fold_weights(w, w2, cout, cin, kt, khw, st, To, Kf):
@@ -165,7 +197,7 @@ def stem_unfold_wgrad(dw2, dw, cout, cin, kt, khw, st, To, Kf):
 
 # ---- batch norm -----------------------------------------------------------------------------
 def bn_sums(x: View, groups: int, ws: torch.Tensor):
-    _abi.call("b2c_bn_sums", x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(ws), stream())
+    _bw("b2c_bn_sums", _vb(x), x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(ws), stream())
 
 
 def bn_finalize(ws, ws_C, c_off, C, groups, rows_per_group, mean, rstd, rm, rv, momentum, eps):
@@ -174,90 +206,90 @@ def bn_finalize(ws, ws_C, c_off, C, groups, rows_per_group, mean, rstd, rm, rv, 
 
 
 def bn_relu_apply(x: View, groups, mean, rstd, gamma, beta, y: View, relu=True):
-    _abi.call("b2c_bn_relu_apply", x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(mean), _p(rstd), _p(gamma),
+    _bw("b2c_bn_relu_apply", 2 * _vb(x), x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(mean), _p(rstd), _p(gamma),
               _p(beta), y.ptr, y.row_stride, y.c_off, int(relu), stream())
 
 
 def bn_relu_bwd_reduce(dy: View, y: View, x: View, groups, mean, rstd, ws, relu=True):
-    _abi.call("b2c_bn_relu_bwd_reduce", dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
+    _bw("b2c_bn_relu_bwd_reduce", 3 * _vb(x), dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
               x.row_stride, x.c_off, x.rows, x.C, groups, _p(mean), _p(rstd), _p(ws), int(relu), stream())
 
 
 def bn_relu_bwd_apply(dy: View, y: View, x: View, groups, mean, rstd, gamma, ws, dx: View, dgamma, dbeta, relu=True):
-    _abi.call("b2c_bn_relu_bwd_apply", dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
+    _bw("b2c_bn_relu_bwd_apply", 4 * _vb(x), dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
               x.row_stride, x.c_off, x.rows, x.C, groups, _p(mean), _p(rstd), _p(gamma), _p(ws), dx.ptr, dx.row_stride,
               dx.c_off, _p(dgamma), _p(dbeta), int(relu), stream())
 
 
 # ---- pooling / elementwise ------------------------------------------------------------------
 def maxpool_fwd(x: View, y: View, idx, k, s, p):
-    _abi.call("b2c_maxpool_fwd", x.ptr, x.row_stride, x.c_off, y.ptr, y.row_stride, y.c_off, _p(idx), x.N, x.C,
+    _bw("b2c_maxpool_fwd", _vb(x) + _vb(y) + y.rows * y.C, x.ptr, x.row_stride, x.c_off, y.ptr, y.row_stride, y.c_off, _p(idx), x.N, x.C,
               *x.dims, *y.dims, *k, *s, *p, stream())
 
 
 def maxpool_bwd(dy: View, idx, dx: View, k, s, p, accumulate=False):
-    _abi.call("b2c_maxpool_bwd", dy.ptr, dy.row_stride, dy.c_off, _p(idx), dx.ptr, dx.row_stride, dx.c_off, dx.N, dx.C,
+    _bw("b2c_maxpool_bwd", _vb(dy) + dy.rows * dy.C + _vb(dx), dy.ptr, dy.row_stride, dy.c_off, _p(idx), dx.ptr, dx.row_stride, dx.c_off, dx.N, dx.C,
               *dx.dims, *dy.dims, *k, *s, *p, int(accumulate), stream())
 
 
 def channel_scale(x: View, scale_nc, y: View):
     T, H, W = x.dims
-    _abi.call("b2c_channel_scale", x.ptr, x.row_stride, x.c_off, _p(scale_nc), y.ptr, y.row_stride, y.c_off, x.N,
+    _bw("b2c_channel_scale", 2 * _vb(x), x.ptr, x.row_stride, x.c_off, _p(scale_nc), y.ptr, y.row_stride, y.c_off, x.N,
               T * H * W, x.C, stream())
 
 
 def act_bwd(dy: View, y: Optional[View], scale_nc, dz: Optional[View], dbias, relu: bool):
     T, H, W = dy.dims
-    _abi.call("b2c_act_bwd", dy.ptr, dy.row_stride, dy.c_off, y.ptr if y is not None else None,
+    _bw("b2c_act_bwd", _vb(dy) * (1 + (y is not None) + (dz is not None)), dy.ptr, dy.row_stride, dy.c_off, y.ptr if y is not None else None,
               y.row_stride if y is not None else 0, y.c_off if y is not None else 0, _p(scale_nc),
               dz.ptr if dz is not None else None, dz.row_stride if dz is not None else 0,
               dz.c_off if dz is not None else 0, _p(dbias), dy.N, T * H * W, dy.C, int(relu), stream())
 
 
 def add(a: View, b: View, out: View):
-    _abi.call("b2c_add", a.ptr, a.row_stride, a.c_off, b.ptr, b.row_stride, b.c_off, out.ptr, out.row_stride, out.c_off,
+    _bw("b2c_add", 3 * _vb(a), a.ptr, a.row_stride, a.c_off, b.ptr, b.row_stride, b.c_off, out.ptr, out.row_stride, out.c_off,
               a.rows, a.C, stream())
 
 
 def stencil27_fwd(P, out, bias, N, T, H, W):
-    _abi.call("b2c_stencil27_fwd", _p(P), _p(out), _p(bias), N, T, H, W, stream())
+    _bw("b2c_stencil27_fwd", N * T * H * W * 4 * 28, _p(P), _p(out), _p(bias), N, T, H, W, stream())
 
 
 def stencil27_bwd(dout, dP, dbias, N, T, H, W, cpad=32):
-    _abi.call("b2c_stencil27_bwd", _p(dout), _p(dP), _p(dbias), N, T, H, W, cpad, stream())
+    _bw("b2c_stencil27_bwd", N * T * H * W * (4 + cpad * dP.element_size()), _p(dout), _p(dP), _p(dbias), N, T, H, W, cpad, stream())
 
 
 # ---- collapsed decoder tail (upsample4 -> Dropout3d -> smooth as one per-clip transposed convolution) --------------
 def tail_weff(w4, b4, ws, drop_nc, packed_f, f_stride, packed_d, d_stride, d_nkb, biasfield, N):
-    _abi.call("b2c_tail_weff", _p(w4), _p(b4), _p(ws), _p(drop_nc), _p(packed_f), f_stride, _p(packed_d), d_stride, d_nkb,
+    _bw("b2c_tail_weff", 128 * 128 * 27 * 4 + N * (216 * 128 * 2) * packed_f.element_size(), _p(w4), _p(b4), _p(ws), _p(drop_nc), _p(packed_f), f_stride, _p(packed_d), d_stride, d_nkb,
               _p(biasfield), N, stream())
 
 
 def tail_gather_fwd(y_planar, biasfield, bs, logits, N, It, Ih, Iw):
-    _abi.call("b2c_tail_gather_fwd", _p(y_planar), _p(biasfield), _p(bs), _p(logits), N, It, Ih, Iw, stream())
+    _bw("b2c_tail_gather_fwd", N * It * Ih * Iw * (216 * 4 + 8 * 4), _p(y_planar), _p(biasfield), _p(bs), _p(logits), N, It, Ih, Iw, stream())
 
 
 def tail_gather_bwd(dlogits, dy, class_sums, N, It, Ih, Iw):
-    _abi.call("b2c_tail_gather_bwd", _p(dlogits), _p(dy), _p(class_sums), N, It, Ih, Iw, stream())
+    _bw("b2c_tail_gather_bwd", N * It * Ih * Iw * (224 * dy.element_size() + 8 * 4 * 2), _p(dlogits), _p(dy), _p(class_sums), N, It, Ih, Iw, stream())
 
 
 def tail_chain_bwd(dweff, class_sums, w4, b4, ws, drop_nc, dw4, db4, dws, dbs, N):
-    _abi.call("b2c_tail_chain_bwd", _p(dweff), _p(class_sums), _p(w4), _p(b4), _p(ws), _p(drop_nc), _p(dw4), _p(db4), _p(dws),
+    _bw("b2c_tail_chain_bwd", N * 128 * 216 * 4 + 128 * 128 * 27 * 8, _p(dweff), _p(class_sums), _p(w4), _p(b4), _p(ws), _p(drop_nc), _p(dw4), _p(db4), _p(dws),
               _p(dbs), N, stream())
 
 
 # ---- capsule head ---------------------------------------------------------------------------
 def em_routing_fwd(caps, W, beta_u, beta_a, out, b, C):
-    _abi.call("b2c_em_routing_fwd", _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out), b, C, stream())
+    _bw("b2c_em_routing_fwd", b * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out), b, C, stream())
 
 
 def em_routing_bwd(caps, W, beta_u, beta_a, dout, dcaps, dW, dbu, dba, b, C):
-    _abi.call("b2c_em_routing_bwd", _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout), _p(dcaps), _p(dW), _p(dbu),
+    _bw("b2c_em_routing_bwd", b * 2 * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout), _p(dcaps), _p(dW), _p(dbu),
               _p(dba), b, C, stream())
 
 
 def primarycaps_bwd_prep(g, out, dz, dbias, rows, dz_pitch=544):
-    _abi.call("b2c_primarycaps_bwd_prep", _p(g), _p(out), _p(dz), _p(dbias), rows, dz_pitch, stream())
+    _bw("b2c_primarycaps_bwd_prep", rows * (544 * 8 + dz_pitch * dz.element_size()), _p(g), _p(out), _p(dz), _p(dbias), rows, dz_pitch, stream())
 
 
 def class_mean_fwd(rout, act, N, L, C):
@@ -274,11 +306,11 @@ def caps_head_bwd(dx, mask, dact, dfeat, drout, N, L, C):
 
 # ---- losses ---------------------------------------------------------------------------------
 def seg_loss_fwd(logits, targets, lab_idx, n_lab, V, sums, loss):
-    _abi.call("b2c_seg_loss_fwd", _p(logits), _p(targets), _p(lab_idx), n_lab, V, _p(sums), _p(loss), stream())
+    _bw("b2c_seg_loss_fwd", n_lab * V * 8, _p(logits), _p(targets), _p(lab_idx), n_lab, V, _p(sums), _p(loss), stream())
 
 
 def seg_loss_bwd(logits, targets, lab_idx, n_lab, V, sums, w_bce, w_dice, dlogits):
-    _abi.call("b2c_seg_loss_bwd", _p(logits), _p(targets), _p(lab_idx), n_lab, V, _p(sums), float(w_bce), float(w_dice),
+    _bw("b2c_seg_loss_bwd", n_lab * V * 12, _p(logits), _p(targets), _p(lab_idx), n_lab, V, _p(sums), float(w_bce), float(w_dice),
               _p(dlogits), stream())
 
 
@@ -288,17 +320,17 @@ def spread_loss(act, target, lab_idx, n_lab, C, m_min, loss, w, dact):
 
 
 def bv_mask(pred, flip_pred, m, mm, P, H, W, frames_cnt, use_sig, pred_tflip=0, fp_tflip=0, fp_wmirror=0):
-    _abi.call("b2c_bv_mask", _p(pred), _p(flip_pred), _p(m), _p(mm), P, H, W, frames_cnt, int(use_sig), int(pred_tflip),
+    _bw("b2c_bv_mask", P * 8 * H * W * 4 * 3, _p(pred), _p(flip_pred), _p(m), _p(mm), P, H, W, frames_cnt, int(use_sig), int(pred_tflip),
               int(fp_tflip), int(fp_wmirror), stream())
 
 
 def gv_mask(out, m, mm, P, H, W, lower, upper):
-    _abi.call("b2c_gv_mask", _p(out), _p(m), _p(mm), P, H, W, float(lower or 0.0), float(upper or 0.0),
+    _bw("b2c_gv_mask", P * 8 * H * W * 4 * 2, _p(out), _p(m), _p(mm), P, H, W, float(lower or 0.0), float(upper or 0.0),
               int(lower is not None), int(upper is not None), stream())
 
 
 def cons_reduce(out, flp, w1, w2, wg, acc, P, H, W, mirror, w2_tflip):
-    _abi.call("b2c_cons_reduce", _p(out), _p(flp), _p(w1), _p(w2), _p(wg), _p(acc), P, H, W, int(mirror), int(w2_tflip),
+    _bw("b2c_cons_reduce", P * 8 * H * W * 4 * (2 + (w1 is not None) + (w2 is not None) + (wg is not None)), _p(out), _p(flp), _p(w1), _p(w2), _p(wg), _p(acc), P, H, W, int(mirror), int(w2_tflip),
               stream())
 
 
@@ -309,19 +341,19 @@ def cons_finish(acc, loss, P, H, W, mode, wt_ramp, bv_wt, gv_wt, dev_scalars=Non
 
 
 def cons_grad(out, flp, w1, w2, wg, dout, dflp, P, H, W, mirror, w2_tflip, a_l2, a_lv, a_lg, dev_scalars=None):
-    _abi.call("b2c_cons_grad", _p(out), _p(flp), _p(w1), _p(w2), _p(wg), _p(dout), _p(dflp), P, H, W, int(mirror),
+    _bw("b2c_cons_grad", P * 8 * H * W * 4 * (4 + (w1 is not None) + (w2 is not None) + (wg is not None)), _p(out), _p(flp), _p(w1), _p(w2), _p(wg), _p(dout), _p(dflp), P, H, W, int(mirror),
               int(w2_tflip), float(a_l2), float(a_lv), float(a_lg), _p(dev_scalars), stream())
 
 
 def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale=1.0, lr_dev=None):
     """step_dev: int32 device tensor holding the number of steps taken so far (incremented by the call);
     lr_dev: optional device float that overrides `lr` (graph replays with a scheduler-controlled learning rate)."""
-    _abi.call("b2c_adam_step", _p(p), _p(g), _p(m), _p(v), n, float(lr), float(beta1), float(beta2), float(eps), _p(step_dev),
+    _bw("b2c_adam_step", n * 28, _p(p), _p(g), _p(m), _p(v), n, float(lr), float(beta1), float(beta2), float(eps), _p(step_dev),
               float(grad_scale), _p(lr_dev), stream())
 
 
 def fill_f32(t, v):
-    _abi.call("b2c_fill_f32", _p(t), t.numel(), float(v), stream())
+    _bw("b2c_fill_f32", t.numel() * 4, _p(t), t.numel(), float(v), stream())
 
 
 def set_deterministic(on: bool):

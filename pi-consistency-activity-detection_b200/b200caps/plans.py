@@ -321,7 +321,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
     d.si_t, d.si_h, d.si_w = si
     d.so_t, d.so_h, d.so_w = so
     if isinstance(out, View):
-        assert out.dims == tuple(exp_out) and out.C == pk["R_pad"], (which, out.dims, exp_out, out.C, pk["R_pad"])
+        assert out.dims == tuple(exp_out) and out.C == (pk.get("out_fold") or pk["R_pad"]), (which, out.dims, exp_out, out.C, pk["R_pad"])
         assert out.t.dtype in (act_dtype(), torch.float32)
         d.out, d.out_row_stride, d.out_c_off = out.ptr, out.row_stride, out.c_off
         d.out_fp32 = 1 if out.t.dtype == torch.float32 else 0
@@ -335,6 +335,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
     d.relu, d.sigmoid_from, d.accumulate, d.bn_tile = int(relu), int(sigmoid_from), int(accumulate), pick_bn_tile(pk["R_pad"])
     d.tap_pitch = pk.get("pitch") or tap_pitch(pk["C"])
     d.w_sample_stride = int(pk.get("sample_stride_bytes", 0))     # per-clip weight sets (collapsed decoder tail)
+    d.out_fold = int(pk.get("out_fold", 0))                       # folded stem: column blocks -> output frames
     d.nclass = len(classes)
     assert 1 <= d.nclass <= 8
     for i, cl in enumerate(classes):
@@ -360,7 +361,7 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
         geo["Cp_real"] = part[2] if len(part) > 2 else part[1]
     g, p = (x, dy) if geo["g_is_input"] else (dy, x)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
-    assert g.C == geo["Cg"] and p.C == geo["Cp"], (g.C, geo["Cg"], p.C, geo["Cp"])
+    assert g.C == geo["Cg"] and p.C == (geo.get("p_fold") or geo["Cp"]), (g.C, geo["Cg"], p.C, geo["Cp"])
     want = torch.bfloat16 if force_bf16 else act_dtype()
     assert g.t.dtype == want and p.t.dtype == want, (g.t.dtype, p.t.dtype, precision())
     d = _abi.WgradDesc()
@@ -377,7 +378,8 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
     d.Qt, d.Qh, d.Qw = geo["Q"]
     d.sg_t, d.sg_h, d.sg_w = geo["sg"]
     d.sp_t, d.sp_h, d.sp_w = geo["sp"]
-    d.pp_t, d.pp_h, d.pp_w = pp        # position offset of the plain operand (folded stem: output frame t)
+    d.pp_t, d.pp_h, d.pp_w = pp        # position offset of the plain operand
+    d.p_fold = int(geo.get("p_fold", 0))   # folded stem: p-channel blocks are the output frames
     d.ntaps, d.bn_tile, d.nsplit, d.atomic = len(cl.taps), int(bn_tile), int(nsplit), int(atomic)
     if per_clip:      # dw is (N, ...): one gradient per clip
         assert dw.shape[0] == x.N

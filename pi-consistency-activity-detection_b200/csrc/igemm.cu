@@ -581,6 +581,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
         const uint32_t t_lane = tmem_base + (uint32_t)((acc * MT + jt) * acc_cols) + ((uint32_t)(quarter * 32) << 16);
         for (int ch0 = 0; ch0 < bn16; ch0 += kStageChunkCols) {
           const int cw = bn16 - ch0 < kStageChunkCols ? bn16 - ch0 : kStageChunkCols;
+          // out_fold: output column c lives in T-plane (c / out_fold), channel (c % out_fold) (folded stem: all output
+          // frames of a pixel are columns of one GEMM row); a 64-column chunk never straddles planes (out_fold % 64 == 0)
+          const int fold_t = d.out_fold ? (n0 + ch0) / d.out_fold : 0;
+          const int fold_c = d.out_fold ? fold_t * d.out_fold : 0;              // columns to subtract
+          const long long fold_pos = (long long)fold_t * d.Ho * d.Wo;
           if (staged) {
             // the previous chunk of this warp has left its staging rows
             B2C_PROF_DECL(w5); B2C_PROF_START(w5);
@@ -676,7 +681,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
                   o[(long long)i * d.out_row_stride] = vv[i];
                 }
               } else if (d.out_fp32) {
-                float* o = reinterpret_cast<float*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+                float* o = reinterpret_cast<float*>(d.out) + (opos + fold_pos) * d.out_row_stride + d.out_c_off + col - fold_c;
                 float4* o4 = reinterpret_cast<float4*>(o);
                 if (d.accumulate) {
                   float4 a = o4[0], b = o4[1];
@@ -690,7 +695,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
                 o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
                 o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
               } else {
-                bf16* o = reinterpret_cast<bf16*>(d.out) + opos * d.out_row_stride + d.out_c_off + col;
+                bf16* o = reinterpret_cast<bf16*>(d.out) + (opos + fold_pos) * d.out_row_stride + d.out_c_off + col - fold_c;
                 uint4* o4 = reinterpret_cast<uint4*>(o);
                 if (d.accumulate) {
                   float e[8];
@@ -718,7 +723,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
                 uint32_t q = fdivmod(mp, s_fd[3 * ti.cls], rw);
                 q = fdivmod(q, s_fd[3 * ti.cls + 1], rh);
                 q = fdivmod(q, s_fd[3 * ti.cls + 2], rt);
-                tma_store_5d(&omaps.o[ti.cls], sub + (uint32_t)(lane * piece) * 128, n0 + ch0, (int)rw, (int)rh, (int)rt, (int)q);
+                tma_store_5d(&omaps.o[ti.cls], sub + (uint32_t)(lane * piece) * 128, n0 + ch0 - fold_c, (int)rw, (int)rh, (int)rt + fold_t, (int)q);
               }
             }
             if (lane < n_issue) bulk_commit();
@@ -727,7 +732,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
             __syncwarp();
             const int ce = bn - ch0 < cw ? bn - ch0 : cw;            // real columns of this chunk
             const int segv = ce > 0 ? ce >> 3 : 0;
-            const long long obyte = mvalid ? (opos * d.out_row_stride + d.out_c_off + n0 + ch0) * 2 : -1;
+            const long long obyte = mvalid ? ((opos + fold_pos) * d.out_row_stride + d.out_c_off + n0 + ch0 - fold_c) * 2 : -1;
             const int vcol = lane & 7, rsub = lane >> 3;
   #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
@@ -874,9 +879,13 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
         for (int h = 0; h < kMaxSub; ++h)
           if (sub_ok[h])
             tma_im2col_5d(a_st + h * kBoxBytes, &maps.g, &ps->full[stage], sub_c[h], gw, gh, gt, n_i, sub_ow[h], sub_oh[h], sub_ot[h]);
-        for (int j = 0; j < nb; ++j)
-          tma_im2col_5d(b_st + j * kBoxBytes, &maps.p, &ps->full[stage], n0 + j * kCB, qw * d.sp_w + d.pp_w, qh * d.sp_h + d.pp_h,
-                        qt * d.sp_t + d.pp_t, n_i, 0, 0, 0);
+        for (int j = 0; j < nb; ++j) {
+          // p_fold: p-channel block c lives in T-plane (c / p_fold) at channel (c % p_fold) (folded stem)
+          const int pc = n0 + j * kCB;
+          const int ft = d.p_fold ? pc / d.p_fold : 0;
+          tma_im2col_5d(b_st + j * kBoxBytes, &maps.p, &ps->full[stage], pc - ft * d.p_fold, qw * d.sp_w + d.pp_w, qh * d.sp_h + d.pp_h,
+                        qt * d.sp_t + d.pp_t + ft, n_i, 0, 0, 0);
+        }
         qw += kPK;
         while (qw >= d.Qw) {
           qw -= d.Qw;
@@ -1260,6 +1269,11 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
               "conv_fprop: tap_pitch=%d must be Cin=%d or Cin rounded up to a multiple of %d", d.tap_pitch, d.Cin, bk);
   const int use_tma = (k_pitch % bk == 0) ? 1 : 0;
   B2C_REQUIRE(!tf32 || (use_tma && d.out_fp32 != 0), "conv_fprop: tf32 mode needs tap_pitch %% 32 == 0 and an fp32 output");
+  if (d.out_fold != 0) {
+    B2C_REQUIRE(d.out_fold % kStageChunkCols == 0 && d.Cout % d.out_fold == 0 && d.bn_tile % d.out_fold == 0 && d.nclass == 1 &&
+                    d.out_fp32 != 2 && d.cls[0].Qt == 1 && d.so_t == 1 && d.cls[0].po_t + d.Cout / d.out_fold <= d.To && !d.scale_nc,
+                "conv_fprop: out_fold=%d needs 64-column planes, one class with Qt = 1 and Cout / out_fold <= To", d.out_fold);
+  }
   if (d.w_sample_stride != 0) {
     B2C_REQUIRE(use_tma && d.w_sample_stride > 0 && d.w_sample_stride % 16 == 0, "conv_fprop: per-clip weights need the TMA path and a 16-byte stride");
     for (int i = 0; i < d.nclass; ++i)
@@ -1326,7 +1340,7 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   if (d.out_fp32 == 0 && !d.accumulate && get_encode_tiled() != nullptr) {
     const bf16* obase = reinterpret_cast<const bf16*>(d.out) + d.out_c_off;
     const b2c_conv_class& c0 = d.cls[0];
-    const bool contiguous = d.nclass == 1 && d.so_t == 1 && d.so_h == 1 && d.so_w == 1 && c0.po_t == 0 && c0.po_h == 0 &&
+    const bool contiguous = d.out_fold == 0 && d.nclass == 1 && d.so_t == 1 && d.so_h == 1 && d.so_w == 1 && c0.po_t == 0 && c0.po_h == 0 &&
                             c0.po_w == 0 && c0.Qt == d.To && c0.Qh == d.Ho && c0.Qw == d.Wo;
     if (contiguous) {
       cuuint64_t dims[2] = {(cuuint64_t)d.Cout, (cuuint64_t)((long long)d.N * d.To * d.Ho * d.Wo)};
@@ -1343,7 +1357,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
         for (int i = 0; i < d.nclass; ++i) {
           const b2c_conv_class& c = d.cls[i];
           const long long rs = d.out_row_stride;
-          cuuint64_t dims[5] = {(cuuint64_t)d.Cout, (cuuint64_t)c.Qw, (cuuint64_t)c.Qh, (cuuint64_t)c.Qt, (cuuint64_t)d.N};
+          cuuint64_t dims[5] = {(cuuint64_t)(d.out_fold ? d.out_fold : d.Cout), (cuuint64_t)c.Qw, (cuuint64_t)c.Qh,
+                                (cuuint64_t)(d.out_fold ? d.To : c.Qt), (cuuint64_t)d.N};
           cuuint64_t strides[4] = {(cuuint64_t)(d.so_w * rs * 2), (cuuint64_t)((long long)d.so_h * d.Wo * rs * 2),
                                    (cuuint64_t)((long long)d.so_t * d.Ho * d.Wo * rs * 2),
                                    (cuuint64_t)((long long)d.To * d.Ho * d.Wo * rs * 2)};
@@ -1457,6 +1472,10 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
     nsplit = s * d.N;
   }
   B2C_REQUIRE(nsplit == 1 || d.atomic, "conv_wgrad: nsplit>1 requires atomic accumulation");
+  if (d.p_fold != 0)
+    B2C_REQUIRE(use_tma && d.p_fold % cb == 0 && d.Cp % d.p_fold == 0 && d.Qt == 1 && d.sp_t == 1 && d.pp_t + d.Cp / d.p_fold <= d.Tp &&
+                    ((long long)d.Qh * d.Qw) % pk == 0,
+                "conv_wgrad: p_fold=%d needs the TMA path, Qt = 1 and planes of a multiple of %d positions", d.p_fold, pk);
   const int stage_bytes = MT * kATileBytes + b_tile_bytes;
   // latency-bound gather: keep as many K-blocks in flight as shared memory allows (ncu r01: 2 stages -> L2 45 %, tensor 11 %)
   int stages = (200 * 1024) / stage_bytes;
@@ -1487,8 +1506,10 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
     int rc = encode_im2col_map(&maps.g, reinterpret_cast<const uint8_t*>(d.g) + (size_t)d.g_c_off * esz, d.Cg, d.g_row_stride, d.N,
                                d.Tg, d.Hg, d.Wg, lo[0], lo[1], lo[2], d.Qt, d.Qh, d.Qw, d.sg_t, d.sg_h, d.sg_w, cb, pk, esz);
     if (rc) return rc;
-    rc = encode_im2col_map(&maps.p, reinterpret_cast<const uint8_t*>(d.p) + (size_t)d.p_c_off * esz, d.Cp, d.p_row_stride, d.N, d.Tp,
-                           d.Hp, d.Wp, d.pp_t, d.pp_h, d.pp_w, d.Qt, d.Qh, d.Qw, d.sp_t, d.sp_h, d.sp_w, cb, pk, esz);
+    // p_fold: the map covers p_fold channels and every T-plane (the start coordinate selects the plane)
+    rc = encode_im2col_map(&maps.p, reinterpret_cast<const uint8_t*>(d.p) + (size_t)d.p_c_off * esz, d.p_fold ? d.p_fold : d.Cp,
+                           d.p_row_stride, d.N, d.Tp, d.Hp, d.Wp, d.pp_t, d.pp_h, d.pp_w, d.p_fold ? d.Tp - d.pp_t : d.Qt, d.Qh, d.Qw,
+                           d.sp_t, d.sp_h, d.sp_w, cb, pk, esz);
     if (rc) return rc;
   }
   dim3 grid((unsigned)mtc, (unsigned)nt, (unsigned)nsplit);
