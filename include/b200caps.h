@@ -143,6 +143,13 @@ int b2c_ncdhw_to_ndhwc(const float* in, void* out, int32_t N, int32_t C, int64_t
 int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_t in_c_off, float* out, int32_t N, int32_t C,
                            int64_t THW, b2c_stream_t s);
 
+/* Input pipeline on the device (ucf_dataloader.py:162-185, main_ucf101.py:52-55): uint8 clips (P,C,T,H,W) as decoded ->
+ * channels-last activations (2P, T, H, W, 8) of both forward passes: out[n] = u8 / 255, out[P + n] = the clip mirrored in W
+ * (the reference's `aug_data`).  rows = T * H.  The flipped clips and the fp32 copies never cross PCIe. */
+int b2c_u8_clip_to_cl(const uint8_t* in, void* out, int32_t P, int32_t C, int64_t rows, int32_t W, b2c_stream_t s);
+/* out[i] = in[i] * scale (uint8 segmentation masks -> fp32 targets) */
+int b2c_u8_to_f32(const uint8_t* in, float* out, int64_t n, float scale, b2c_stream_t s);
+
 /* Explicit im2col for the few-channel stem (Conv3d_1a_7x7, pytorch_i3d.py:224): x channels-last bf16 (N,T,H,W,Cs) with C
  * real channels -> out (N*To*Ho*Wo, Kpad) bf16, column = tap*C + c, zero padded to Kpad (multiple of 64). */
 int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, int32_t C, int32_t T, int32_t H, int32_t W, int32_t To,

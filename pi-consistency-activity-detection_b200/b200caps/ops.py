@@ -170,6 +170,22 @@ def ncdhw_to_cl(x: torch.Tensor, cpad: int, out: Optional[torch.Tensor] = None) 
     return out
 
 
+def u8_clip_to_cl(u8: torch.Tensor, out: torch.Tensor):
+    """(P,C,T,H,W) uint8 -> out (2P,T,H,W,8): [clips / 255 ; the clips mirrored in W] in the activation precision."""
+    assert u8.dtype == torch.uint8 and u8.is_contiguous() and u8.dim() == 5
+    P, Cc, T, H, W = u8.shape
+    assert tuple(out.shape) == (2 * P, T, H, W, 8) and out.is_contiguous() and out.dtype == act_dtype()
+    _bw("b2c_u8_clip_to_cl", u8.numel() + out.numel() * out.element_size(), _p(u8), _p(out), P, Cc, T * H, W, stream())
+    return out
+
+
+def u8_to_f32(u8: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    assert u8.dtype == torch.uint8 and u8.is_contiguous()
+    out = torch.empty(u8.shape, dtype=torch.float32, device=u8.device)
+    _bw("b2c_u8_to_f32", u8.numel() * 5, _p(u8), _p(out), u8.numel(), float(scale), stream())
+    return out
+
+
 def cl_to_ncdhw_f32(v: View) -> torch.Tensor:
     N = v.N
     T, H, W = v.dims

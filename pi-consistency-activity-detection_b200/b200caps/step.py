@@ -151,7 +151,9 @@ class TrainStep:
 
     def __call__(self, data, fl_data, action, seg, labels_host, epoch: int = 1):
         """data / fl_data (P,3,8,H,W) fp32 CUDA, action (P,1) CUDA, seg (P,1,8,H,W) fp32 CUDA, labels_host: CPU tensor /
-        list with 1 = labeled.  Returns dict of device scalars (total, loc, cls, cons) and the step's outputs."""
+        list with 1 = labeled.  Returns dict of device scalars (total, loc, cls, cons) and the step's outputs.
+        uint8 input pipeline: data (P,3,8,H,W) uint8 as decoded + fl_data=None (+ optionally a uint8 seg): the /255
+        scaling and the mirrored second pass are produced on the device (ucf_dataloader.py:162-185)."""
         engine.require_cuda(data, "data")
         lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, data.device)
         self.set_schedule(epoch=epoch)
@@ -181,7 +183,7 @@ class TrainStep:
 
     # ---- CUDA graph ------------------------------------------------------------------------------------
     def capture(self, P: int, labels_host, epoch: int = 1, T: int = 8, H: int = 224, W: int = 224, warmup: int = 3,
-                init_batch=None, ddp_graph: Optional[str] = None):
+                init_batch=None, ddp_graph: Optional[str] = None, uint8_inputs: bool = False):
         """Capture the whole step (both passes, losses, backward, all-reduce, Adam, weight re-packing) into one CUDA
         graph with static input buffers.  Only the labeled/unlabeled PATTERN is baked into the graph; the epoch-dependent
         scalars and the learning rate are read from device memory (set_schedule), so one capture serves the whole run.
@@ -189,11 +191,17 @@ class TrainStep:
         weight-packing jobs); the model weights, Adam state and BatchNorm buffers are snapshotted before and restored
         after them, so capture() leaves the training state exactly as it found it."""
         dev = self.flat.data.device
-        st = dict(data=torch.rand((P, 3, T, H, W), device=dev), fl_data=torch.rand((P, 3, T, H, W), device=dev),
-                  action=torch.zeros((P, 1), device=dev), seg=torch.zeros((P, 1, T, H, W), device=dev))
+        if uint8_inputs:
+            # static inputs = what the dataloader decodes: uint8 clips and masks; fl_data does not exist on the host side
+            st = dict(data=torch.randint(0, 256, (P, 3, T, H, W), dtype=torch.uint8, device=dev), fl_data=None,
+                      action=torch.zeros((P, 1), device=dev), seg=torch.zeros((P, 1, T, H, W), dtype=torch.uint8, device=dev))
+        else:
+            st = dict(data=torch.rand((P, 3, T, H, W), device=dev), fl_data=torch.rand((P, 3, T, H, W), device=dev),
+                      action=torch.zeros((P, 1), device=dev), seg=torch.zeros((P, 1, T, H, W), device=dev))
         if init_batch is not None:
             for k, v in zip(("data", "fl_data", "action", "seg"), init_batch):
-                st[k].copy_(v)
+                if st[k] is not None:
+                    st[k].copy_(v)
         lab_idx, labels_dev, n_lab = self._label_tensors(labels_host, dev)
         self.set_schedule(epoch=epoch)
         snap = self._snapshot()
@@ -240,7 +248,7 @@ class TrainStep:
         the current step computes.  The next replay() called without inputs moves them into the graph's static buffers
         (device to device, ~0.1 ms) before it launches: the 180 MB/step H2D transfer leaves the critical path."""
         if self._staging is None:
-            self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items() if v is not None}
             self._copy_stream = torch.cuda.Stream()
             self._staging_ready = torch.cuda.Event()
             self._staging_free = torch.cuda.Event()
@@ -248,7 +256,8 @@ class TrainStep:
         cs.wait_event(self._staging_free)          # the previous step has drained the staging set
         with torch.cuda.stream(cs):
             for k, v in (("data", data), ("fl_data", fl_data), ("action", action), ("seg", seg)):
-                self._staging[k].copy_(v, non_blocking=True)
+                if k in self._staging:
+                    self._staging[k].copy_(v, non_blocking=True)
             self._staging_ready.record(cs)
         self._staged = True
 
@@ -262,12 +271,12 @@ class TrainStep:
         if data is None and self._staged:
             cur = torch.cuda.current_stream()
             cur.wait_event(self._staging_ready)
-            for k in ("data", "fl_data", "action", "seg"):
+            for k in self._staging:
                 st[k].copy_(self._staging[k], non_blocking=True)
             self._staging_free.record(cur)
             self._staged = False
         for k, v in (("data", data), ("fl_data", fl_data), ("action", action), ("seg", seg)):
-            if v is not None:
+            if v is not None and st[k] is not None:
                 st[k].copy_(v, non_blocking=True)
         self.graph.replay()
         if self.graph_opt is not None:
@@ -315,8 +324,12 @@ class TrainStep:
         try:
             # ---------------- forward: both passes as one batch [clips ; flipped clips] ----------------
             x_cl = torch.empty((2 * P, data.shape[2], H, W, 8), dtype=act_dtype(), device=dev)
-            ops.ncdhw_to_cl(data.contiguous(), 8, out=x_cl[:P])
-            ops.ncdhw_to_cl(fl_data.contiguous(), 8, out=x_cl[P:])
+            if data.dtype == torch.uint8:
+                assert fl_data is None, "uint8 input pipeline: the mirrored pass is produced on the device"
+                ops.u8_clip_to_cl(data.contiguous(), x_cl)
+            else:
+                ops.ncdhw_to_cl(data.contiguous(), 8, out=x_cl[:P])
+                ops.ncdhw_to_cl(fl_data.contiguous(), 8, out=x_cl[P:])
             i3d = model.conv1
 
             def unit(mod, x, need_dx=True):
@@ -388,7 +401,7 @@ class TrainStep:
         V = out.numel() // P
         dlogits = torch.zeros_like(logits)
         dact = torch.zeros_like(act)
-        seg = seg.contiguous().float()
+        seg = ops.u8_to_f32(seg.contiguous()) if seg.dtype == torch.uint8 else seg.contiguous().float()
         sums = torch.empty(4, dtype=torch.float64, device=dev)
         l_seg = torch.zeros(2, dtype=torch.float32, device=dev)
         l_cls = torch.zeros(2, dtype=torch.float32, device=dev)

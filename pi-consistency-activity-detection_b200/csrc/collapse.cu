@@ -161,10 +161,13 @@ __device__ __forceinline__ void store8_row<float>(float* p, const float* v) {
   reinterpret_cast<float4*>(p)[1] = make_float4(tf32_rna(v[4]), tf32_rna(v[5]), tf32_rna(v[6]), tf32_rna(v[7]));
 }
 
+// One thread per (position, group of 4 (ct, ch) column pairs = 24 columns = three 16-byte bf16 stores): the 6 columns of a
+// pair read 5 consecutive dlogits of one output row, so a thread issues 20 loads for 24 outputs and no per-column index
+// arithmetic (the per-(position, 8 columns) version spent 1.46 ms on integer divisions; r02 bench).
 template <typename T>
 __global__ void __launch_bounds__(256) tail_gather_bwd_kernel(const float* __restrict__ g, T* __restrict__ dy, int N, int It, int Ih,
                                                               int Iw, long long total) {
-  constexpr int kGroups = kTailCols / 8;   // 28
+  constexpr int kGroups = 9;   // 36 (ct, ch) pairs / 4
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int grp = (int)(idx % kGroups);
     long long pos = idx / kGroups;
@@ -174,24 +177,41 @@ __global__ void __launch_bounds__(256) tail_gather_bwd_kernel(const float* __res
     r /= Ih;
     const int it = (int)(r % It);
     const int n = (int)(r / It);
-    float v[8];
+    const int Ot = 2 * It, Oh = 2 * Ih, Ow = 2 * Iw;
+    float v[24];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = grp * 8 + j;
-      float val = 0.f;
-      if (col < 216) {
-        const int ct = col / 36, ch = (col / 6) % 6, cw = col % 6;
-        const int et = ct < 5 ? ct : 2, eh = ch < 5 ? ch : 2, ew = cw < 5 ? cw : 2;
-        const int ot = 2 * it - 2 + et, oh = 2 * ih - 2 + eh, ow = 2 * iw - 2 + ew;
-        // e = 2 belongs to i > 0, its primed twin to i = 0
-        const bool ok = ot >= 0 && ot < 2 * It && oh >= 0 && oh < 2 * Ih && ow >= 0 && ow < 2 * Iw &&
-                        (ct != 5 || it == 0) && (ct != 2 || it != 0) && (ch != 5 || ih == 0) && (ch != 2 || ih != 0) &&
-                        (cw != 5 || iw == 0) && (cw != 2 || iw != 0);
-        if (ok) val = __ldg(g + (((long long)n * 2 * It + ot) * 2 * Ih + oh) * 2 * Iw + ow);
+    for (int j = 0; j < 4; ++j) {
+      const int pair = grp * 4 + j;
+      const int ct = pair / 6, ch = pair - ct * 6;
+      const int et = ct < 5 ? ct : 2, eh = ch < 5 ? ch : 2;
+      const int ot = 2 * it - 2 + et, oh = 2 * ih - 2 + eh;
+      // e = 2 belongs to i > 0, its primed twin (column 5) to i = 0
+      const bool ok = ot >= 0 && ot < Ot && oh >= 0 && oh < Oh && (ct != 5 || it == 0) && (ct != 2 || it != 0) &&
+                      (ch != 5 || ih == 0) && (ch != 2 || ih != 0);
+      float w5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        const float* row = g + (((long long)n * Ot + ot) * Oh + oh) * Ow + (2 * iw - 2);
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+          const int ow = 2 * iw - 2 + e;
+          if (ow >= 0 && ow < Ow) w5[e] = __ldg(row + e);
+        }
       }
-      v[j] = val;
+      v[j * 6 + 0] = w5[0];
+      v[j * 6 + 1] = w5[1];
+      v[j * 6 + 2] = iw != 0 ? w5[2] : 0.f;
+      v[j * 6 + 3] = w5[3];
+      v[j * 6 + 4] = w5[4];
+      v[j * 6 + 5] = iw == 0 ? w5[2] : 0.f;
     }
-    store8_row(dy + pos * kTailCols + grp * 8, v);
+    T* dst = dy + pos * kTailCols + grp * 24;
+    store8_row(dst, v);
+    store8_row(dst + 8, v + 8);
+    store8_row(dst + 16, v + 16);
+    if (grp == kGroups - 1) {
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store8_row(dst + 24, z);     // columns 216..223: padding
+    }
   }
 }
 
@@ -363,7 +383,7 @@ B2C_API int b2c_tail_gather_fwd(const float* y_planar, const float* biasfield, c
 B2C_API int b2c_tail_gather_bwd(const float* dlogits, void* dy, float* class_sums, int32_t N, int32_t It, int32_t Ih, int32_t Iw,
                                 b2c_stream_t s) {
   B2C_REQUIRE(dlogits && dy && class_sums && N > 0 && It > 0 && Ih > 0 && Iw > 0, "tail_gather_bwd: bad args");
-  const long long total = (long long)N * It * Ih * Iw * (kTailCols / 8);
+  const long long total = (long long)N * It * Ih * Iw * 9;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)b2c_num_sms() * 32;
   if (blocks > cap) blocks = cap;

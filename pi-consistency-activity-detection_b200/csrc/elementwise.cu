@@ -76,6 +76,31 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ in, T* __restric
   }
 }
 
+// uint8 clips as the dataloader decodes them (ucf_dataloader.py:162-185: img / 255., aug = the clip mirrored in W) ->
+// channels-last activations of BOTH forward passes: out[n] = u8 / 255, out[P + n] = the same clip mirrored in W.
+// One thread per (n, t*h row, w): 3 byte loads (coalesced across w), two 8-channel vector stores.
+template <typename T>
+__global__ void u8_clip_to_cl_kernel(const uint8_t* __restrict__ in, T* __restrict__ out, int P, int C, long long rows, int W) {
+  const long long total = (long long)P * rows * W;
+  const long long plane = rows * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long r = i / W;                 // n * rows + row
+    const long long n = r / rows, row = r - n * rows;
+    const uint8_t* src = in + n * C * plane + row * W + w;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < C ? (float)src[(long long)j * plane] / 255.f : 0.f;
+    st8(out + i * 8, v, true);
+    st8(out + (((long long)(P + n) * rows + row) * W + (W - 1 - w)) * 8, v, true);
+  }
+}
+
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)in[i] * scale;
+}
+
 template <typename T>
 __global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ in, long long in_row_stride, int in_c_off, float* __restrict__ out,
                                       int N, int C, long long THW) {
@@ -868,6 +893,26 @@ B2C_API int b2c_ncdhw_to_ndhwc(const float* in, void* out, int32_t N, int32_t C,
     ncdhw_to_ndhwc_kernel<bf16><<<grid_for((long long)N * THW), kBlock, 0, (cudaStream_t)s>>>(in, (bf16*)out, N, C, THW, Cpad);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("ncdhw_to_ndhwc");
+  return 0;
+}
+
+B2C_API int b2c_u8_clip_to_cl(const uint8_t* in, void* out, int32_t P, int32_t C, int64_t rows, int32_t W, b2c_stream_t s) {
+  B2C_REQUIRE(in && out && P > 0 && C > 0 && C <= 8 && rows > 0 && W > 0, "u8_clip_to_cl: bad args");
+  const long long total = (long long)P * rows * W;
+  if (b2c_precision())
+    u8_clip_to_cl_kernel<float><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>(in, (float*)out, P, C, rows, W);
+  else
+    u8_clip_to_cl_kernel<bf16><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>(in, (bf16*)out, P, C, rows, W);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("u8_clip_to_cl");
+  return 0;
+}
+
+B2C_API int b2c_u8_to_f32(const uint8_t* in, float* out, int64_t n, float scale, b2c_stream_t s) {
+  B2C_REQUIRE(in && out && n > 0, "u8_to_f32: bad args");
+  u8_to_f32_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)s>>>(in, out, n, scale);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("u8_to_f32");
   return 0;
 }
 

@@ -114,3 +114,51 @@ def test_fused_step_equals_dropin_composition(mode):
         float(o["total"]), float(o["loc"]), float(o["cls"]), float(o["cons"]), float(res["total"]), float(res["loc"]),
         float(res["cls"]), float(res["cons"])))
     assert abs(float(res["loc"]) - float(o["loc"])) / float(o["loc"]) < 5e-2
+
+
+def test_uint8_input_pipeline_matches_fp32_inputs():
+    """n4: uint8 clips / masks as the dataloader decodes them + on-device /255 and mirroring
+    (ucf_dataloader.py:162-185) must give exactly the step that fp32 `data`, `aug_data` and masks give -- eagerly and
+    through a captured graph with staged (prefetch) inputs."""
+    from b200caps import engine, ops
+    from b200caps.step import StepArgs, TrainStep
+    from models.capsules_ucf101 import CapsNet
+    from oracle import restate
+    sd = restate.make_state_dict(24, seed=0)
+    g = torch.Generator().manual_seed(11)
+    P = 2
+    u8 = torch.randint(0, 256, (P, 3, 8, 224, 224), generator=g, dtype=torch.uint8)
+    seg8 = (torch.rand((P, 1, 8, 224, 224), generator=g) > 0.8).to(torch.uint8)
+    action = torch.randint(0, 24, (P, 1), generator=g).float()
+    labels = torch.tensor([1.0, 0.0])
+    data = (u8.double() / 255.0).float()                       # the reference's arithmetic: float64 / 255, then FloatTensor
+    fl = torch.flip(data, [4]).contiguous()
+    m832 = ((torch.rand((4, 832), generator=g) < 0.5).float() * 2).cuda()
+    m128 = ((torch.rand((4, 128), generator=g) < 0.5).float() * 2).cuda()
+    engine.STATE.dropout_source = lambda n, c, dev: (m832 if c == 832 else m128)
+    ops.set_deterministic(True)
+    try:
+        outs = []
+        for kind in ("fp32", "u8", "u8-graph"):
+            model = CapsNet(pt_path=None)
+            model.load_state_dict(sd)
+            model = model.cuda().train()
+            step = TrainStep(model, StepArgs(bv=True, n_frames=5, wt_cons=0.1, lr=0.0))
+            if kind == "fp32":
+                r = step(data.cuda(), fl.cuda(), action.cuda(), seg8.float().cuda(), labels, epoch=1)
+            elif kind == "u8":
+                r = step(u8.cuda(), None, action.cuda(), seg8.cuda(), labels, epoch=1)
+            else:
+                step.capture(P, labels, epoch=1, uint8_inputs=True, init_batch=(u8.cuda(), None, action.cuda(), seg8.cuda()))
+                step.prefetch(u8.pin_memory(), None, action.pin_memory(), seg8.pin_memory())
+                r = step.replay()
+            torch.cuda.synchronize()
+            outs.append(({k: float(r[k]) for k in ("total", "loc", "cls", "cons")}, step.flat.grad.clone()))
+        for (l, gr), kind in zip(outs[1:], ("u8", "u8-graph")):
+            for k in l:
+                assert l[k] == outs[0][0][k], (kind, k, l[k], outs[0][0][k])
+            # the forward is bit-reproducible in deterministic mode; weight gradients are summed with fp32 atomics
+            assert float((gr - outs[0][1]).abs().max()) <= 1e-4 * float(outs[0][1].abs().max()), kind
+    finally:
+        ops.set_deterministic(False)
+        engine.STATE.dropout_source = None
