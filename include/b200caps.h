@@ -334,6 +334,10 @@ int b2c_tail_gather_bwd(const float* dlogits, void* dy, float* class_sums, int32
 int b2c_tail_chain_bwd(const float* dweff, const float* class_sums, const float* w4, const float* b4, const float* ws,
                        const float* drop_nc, float* dw4, float* db4, float* dws, float* dbs, int32_t N, b2c_stream_t s);
 
+/* Evaluation consumer (evaluate_ucf101.py:127,151-168): per frame (HW pixels) pred = sigmoid(logit) >= 0.5 against the
+ * ground-truth mask -> out[f] = {intersection, union, ground-truth pixels} (int32). */
+int b2c_frame_iou_counts(const float* logits, const float* gt, int32_t* out, int64_t frames, int32_t HW, b2c_stream_t s);
+
 /* tf32 mode only: fp32 view (rows, C) -> compact bf16 tensors hi = bf16(x), lo = bf16(x - hi).  The mode's weight
  * gradients are three bf16 GEMMs on these (hi*hi + hi*lo + lo*hi, fp32 accumulate: >= tf32 accuracy). */
 int b2c_split_bf16(const float* x, int64_t x_row_stride, int32_t x_c_off, void* hi, void* lo, int64_t rows, int32_t C,

@@ -93,6 +93,7 @@ _SIGS = {
     "b2c_stem_fold_input": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_stem_fold_weights": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_stem_unfold_wgrad": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "b2c_frame_iou_counts": [vp, vp, vp, i64, i32, vp],
     "b2c_split_bf16": [vp, i64, i32, vp, vp, i64, i32, vp],
     "b2c_tail_weff": [vp, vp, vp, vp, vp, i64, vp, i64, i32, vp, i32, vp],
     "b2c_tail_gather_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],

@@ -20,6 +20,8 @@ import os
 # Decoder tail: "collapsed" (default) = upsample4 -> Dropout3d -> smooth as one per-clip transposed convolution
 # (CollapsedTail below); B2C_TAIL=explicit keeps the layer-by-layer schedule (3.3 GB intermediate at 16+16 clips).
 TAIL_COLLAPSED = os.environ.get("B2C_TAIL", "collapsed") != "explicit"
+# Eval mode: BatchNorm folded into the convolutions (B2C_EVAL_FOLD_BN=0: conv -> running-statistics BatchNorm kernel)
+EVAL_FOLD_BN = os.environ.get("B2C_EVAL_FOLD_BN", "1") != "0"
 
 BN_EPS = 1e-3       # pytorch_i3d.py:80
 BN_MOMENTUM = 0.01  # pytorch_i3d.py:80
@@ -189,6 +191,35 @@ class ConvLayer:
         return pl
 
 
+def _bn_fold(gamma, beta, rm, rv):
+    """Eval-mode BatchNorm as a per-channel affine: y = conv(x) * s + b (pytorch_i3d.py:80,117 with running statistics)."""
+    s = gamma.detach().float() * torch.rsqrt(rv.detach().float() + BN_EPS)
+    return s, (beta.detach().float() - rm.detach().float() * s).contiguous()
+
+
+def _conv_packed_eval(self, in_dims, gamma, beta, rm, rv):
+    """Eval mode: BatchNorm folded into the convolution -- the per-channel scale goes into the packed weights, the shift
+    becomes the epilogue bias, ReLU is applied in the epilogue: one kernel per Unit3D, no pre-activation tensor."""
+    in_dims = tuple(int(v) for v in in_dims)
+    if not hasattr(self, "eval_plans"):
+        self.eval_plans, self.eval_keys, self.eval_bias = {}, {}, {}
+    pl = self.eval_plans.get(in_dims)
+    if pl is None:
+        pl = ConvPlan(self.spec_fn(in_dims), in_dims).to(self.weight.device)
+        self.eval_plans[in_dims] = pl
+    key = _packed_key(self.weight, gamma, beta, rm, rv)
+    if not _fresh(self.eval_keys.get(in_dims), key):
+        s, b = _bn_fold(gamma, beta, rm, rv)
+        wf = (self.weight.detach() * s.view(-1, 1, 1, 1, 1)).contiguous()
+        pl.pack(wf, "fprop", ops.stream())
+        self.eval_bias[in_dims] = b
+    self.eval_keys[in_dims] = key
+    return pl, self.eval_bias[in_dims]
+
+
+ConvLayer.packed_eval = _conv_packed_eval
+
+
 class StemLayer(ConvLayer):
     """Few-input-channel convolution (the RGB 7x7x7 stem, pytorch_i3d.py:224).
 
@@ -280,6 +311,37 @@ class StemLayer(ConvLayer):
         self.keys[("fold", in_dims)] = key
         return pl
 
+    def packed_eval(self, in_dims, gamma, beta, rm, rv):
+        """Eval mode, folded path: BatchNorm scale folded into the (time-folded) weights, shift as the epilogue bias."""
+        in_dims = tuple(int(v) for v in in_dims)
+        if not hasattr(self, "eval_plans"):
+            self.eval_plans, self.eval_keys, self.eval_bias = {}, {}, {}
+        pl = self.eval_plans.get(in_dims)
+        if pl is None:
+            train_plan = self.plans.pop(("fold", in_dims), None)
+            pl = self.fold_plan(in_dims)                     # an independent plan object (own packed operand) for eval
+            self.plans.pop(("fold", in_dims))
+            if train_plan is not None:
+                self.plans[("fold", in_dims)] = train_plan
+            self.eval_plans[in_dims] = pl
+        key = _packed_key(self.weight, gamma, beta, rm, rv)
+        if not _fresh(self.eval_keys.get(in_dims), key):
+            from .plans import packed_geometry
+            s, b = _bn_fold(gamma, beta, rm, rv)
+            To = pl.out_dims[0]
+            khw = self.k[1] * self.k[2]
+            wf = (self.weight.detach() * s.view(-1, 1, 1, 1, 1)).contiguous()
+            w2 = torch.zeros((To, self.cout, khw, self.KF), dtype=torch.float32, device=wf.device)
+            ops.stem_fold_weights(wf, w2, self.cout, self.cin, self.k[0], khw, self.stride[0], To, self.KF)
+            bn, _, nkb, elems = packed_geometry(To * self.cout, khw * self.KF)
+            cl = pl.fprop[0]
+            if cl.packed is None or cl.packed.dtype != act_dtype():
+                cl.packed = torch.zeros(elems, dtype=act_dtype(), device=wf.device)
+            ops.pack_part(w2, cl.packed, cl.wtap_dev, To * self.cout, khw, self.KF, self.KF, khw * self.KF, 1, self.KF, 0, 0, bn, nkb)
+            self.eval_bias[in_dims] = b.repeat(To).contiguous()
+        self.eval_keys[in_dims] = key
+        return pl, self.eval_bias[in_dims]
+
     def fold_wgrad(self, in_dims, xs: View, dy: View, dw: torch.Tensor):
         """dw (Cout, Cin, kt, kh, kw) += wgrad: ONE launch with N = To * Cout columns (dy's frames are the p-channel blocks)
         into dW2, then the adjoint of the weight fold."""
@@ -341,6 +403,15 @@ def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: 
     col = None
     folded = isinstance(layer, StemLayer) and layer.use_fold(x.dims)
     orig_dims = x.dims
+    if not training and EVAL_FOLD_BN and (folded or not isinstance(layer, StemLayer)) and ops.PACKS is None:
+        # inference: conv + folded BatchNorm + ReLU in ONE kernel, written straight into the concat slot
+        pl, bias = layer.packed_eval(orig_dims, gamma, beta, rm, rv)
+        if folded:
+            x = layer.fold_input(x)
+        ops.conv_fprop(pl, "fprop", x, y, bias=bias, relu=True)
+        sv = UnitSaved()
+        sv.raw, sv.dims, sv.col, sv.mean, sv.rstd, sv.groups = None, orig_dims, None, None, None, 1
+        return sv
     if folded:
         x = layer.fold_input(x)
         col = x.t

@@ -361,6 +361,16 @@ def cons_grad(out, flp, w1, w2, wg, dout, dflp, P, H, W, mirror, w2_tflip, a_l2,
               int(w2_tflip), float(a_l2), float(a_lv), float(a_lg), _p(dev_scalars), stream())
 
 
+def frame_iou_counts(logits, gt):
+    """logits, gt: (..., H, W) fp32 CUDA with the same leading shape -> int32 (frames, 3): intersection, union, gt pixels."""
+    assert logits.shape == gt.shape and logits.is_contiguous() and gt.is_contiguous()
+    HW = logits.shape[-1] * logits.shape[-2]
+    frames = logits.numel() // HW
+    out = torch.empty((frames, 3), dtype=torch.int32, device=logits.device)
+    _bw("b2c_frame_iou_counts", logits.numel() * 8, _p(logits), _p(gt), _p(out), frames, HW, stream())
+    return out
+
+
 def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale=1.0, lr_dev=None):
     """step_dev: int32 device tensor holding the number of steps taken so far (incremented by the call);
     lr_dev: optional device float that overrides `lr` (graph replays with a scheduler-controlled learning rate)."""

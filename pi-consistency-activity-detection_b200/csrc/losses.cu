@@ -539,3 +539,49 @@ B2C_API int b2c_adam_step(float* p, const float* g, float* m, float* v, int64_t 
   B2C_LAUNCH_CHECK("adam_step");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Evaluation consumer (evaluate_ucf101.py:127,151-168): per frame, pred = sigmoid(logit) >= 0.5 against the ground-truth
+// mask -> intersection, union and ground-truth pixel counts.  One block per frame; the host only thresholds the ratios.
+namespace {
+__global__ void __launch_bounds__(256) frame_iou_counts_kernel(const float* __restrict__ logits, const float* __restrict__ gt,
+                                                               int32_t* __restrict__ out, int HW) {
+  const long long f = blockIdx.x;
+  const float* l = logits + f * HW;
+  const float* g = gt + f * HW;
+  int inter = 0, uni = 0, ng = 0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const bool p = 1.f / (1.f + expf(-l[i])) >= 0.5f;      // the reference thresholds the fp32 sigmoid, not the logit
+    const bool t = g[i] > 0.f;
+    inter += (p && t) ? 1 : 0;
+    uni += (p || t) ? 1 : 0;
+    ng += t ? 1 : 0;
+  }
+  __shared__ int sh[3][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    inter += __shfl_xor_sync(0xffffffffu, inter, o);
+    uni += __shfl_xor_sync(0xffffffffu, uni, o);
+    ng += __shfl_xor_sync(0xffffffffu, ng, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = inter;
+    sh[1][threadIdx.x >> 5] = uni;
+    sh[2][threadIdx.x >> 5] = ng;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    out[f * 3 + threadIdx.x] = t;
+  }
+}
+}  // namespace
+
+B2C_API int b2c_frame_iou_counts(const float* logits, const float* gt, int32_t* out, int64_t frames, int32_t HW, b2c_stream_t s) {
+  B2C_REQUIRE(logits && gt && out && frames > 0 && HW > 0, "frame_iou_counts: bad args");
+  frame_iou_counts_kernel<<<(unsigned)frames, 256, 0, (cudaStream_t)s>>>(logits, gt, out, HW);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("frame_iou_counts");
+  return 0;
+}
