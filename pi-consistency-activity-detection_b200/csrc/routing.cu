@@ -15,6 +15,7 @@
 // on the fp64 reference (the parity yardstick); its gradient is analytically zero.
 #include "common.cuh"
 #include "../../include/b200caps.h"
+#include <stdlib.h>
 
 long long b2c_launches_add(long long n);
 
@@ -217,6 +218,152 @@ __global__ void __launch_bounds__(kRT, kNW == 8 ? 2 : 1) em_routing_fwd_kernel(c
 #pragma unroll
       for (int h = 0; h < 16; ++h) dst[lane * 16 + h] = mu[h];   // rows are C*17 floats: not 16B aligned for odd C
       dst[C * 16 + lane] = o.a;
+    }
+  }
+}
+
+// =====================================================================================
+// Warp-per-location forward (r02).  The CTA-per-location kernel above spends its time in cross-warp reductions (four
+// __syncthreads per M step) at ~5 % of the fp32 pipe (ncu r02a: 1.31 ms for 12 800 locations).  Here ONE WARP owns a
+// location: lane = output capsule j, the 32 input capsules i are walked sequentially, so every sum over i is a private
+// register accumulation and only the sums over j (the per-i normalisers) are warp shuffles.  Votes are recomputed where
+// they are needed (64 FMAs) instead of being held in 64 registers per thread; the normalised assignments rn_ij of an
+// iteration sit in 4 KB of shared memory per warp.  No block-level barrier inside the location loop.
+//   pass A (per i): V_ij, E step of the previous iteration -> r_ij, rn_ij = r_ij a_i / Z_i, accumulate R_j, sum rn V
+//   pass B (per i): V_ij again, accumulate the variance around the new mean
+// Same formulas and evaluation order per j as m_step / e_step above.
+// =====================================================================================
+constexpr int kWL = 8;   // warps (= locations in flight) per CTA
+
+__device__ __forceinline__ void votes_of(const float* __restrict__ sc, const float* __restrict__ sW, int i, int lane, float* V, int wst) {
+  float M[16], Wr[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 m4 = *reinterpret_cast<const float4*>(sc + i * 16 + q * 4);
+    M[q * 4 + 0] = m4.x; M[q * 4 + 1] = m4.y; M[q * 4 + 2] = m4.z; M[q * 4 + 3] = m4.w;
+  }
+#pragma unroll
+  for (int h = 0; h < 16; ++h) Wr[h] = sW[(i * 16 + h) * wst + lane];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) acc = fmaf(M[r * 4 + kk], Wr[kk * 4 + c], acc);
+      V[r * 4 + c] = acc;
+    }
+}
+
+// shared-memory row pitch of the per-j tables: 24 floats when C <= 24 (two CTAs per SM fit), else 32.  Lanes >= C read
+// their neighbours' (valid) words and are masked out of every result.
+__host__ __device__ __forceinline__ int routing_pitch(int C) { return C <= 24 ? 24 : 32; }
+
+__global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+                                                                         const float* __restrict__ beta_u, const float* __restrict__ beta_a,
+                                                                         float* __restrict__ out, long long b, int C) {
+  extern __shared__ float sm[];
+  const int wst = routing_pitch(C);
+  float* sW = sm;                                   // [32][16][wst] (+ 8 floats of slack for the masked lanes' reads)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* sc = sW + kB * 16 * wst + 8 + w * 544;     // this warp's capsules (poses | activations), 16-byte aligned
+  float* srn = sW + kB * 16 * wst + 8 + kWL * 544 + w * (kB * wst + 8);   // this warp's rn[i][lane]
+  const bool active = lane < C;
+  for (int idx = threadIdx.x; idx < kB * 16 * wst + 8; idx += blockDim.x) sW[idx] = 0.f;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kB * C * 16; idx += blockDim.x) {
+    const int h = idx & 15, j = (idx >> 4) % C, i = (idx >> 4) / C;
+    sW[(i * 16 + h) * wst + j] = W[idx];
+  }
+  __syncthreads();
+  float bu[16];
+  const float ba = active ? beta_a[lane] : 0.f;
+#pragma unroll
+  for (int h = 0; h < 16; ++h) bu[h] = active ? beta_u[lane * 16 + h] : 0.f;
+  const int ocols = C * 17;
+  for (long long loc = (long long)blockIdx.x * kWL + w; loc < b; loc += (long long)gridDim.x * kWL) {
+    __syncwarp();
+    for (int idx = lane; idx < 544 / 4; idx += 32)
+      reinterpret_cast<float4*>(sc)[idx] = reinterpret_cast<const float4*>(caps + loc * 544)[idx];
+    __syncwarp();
+    const float* s_ain = sc + 512;
+    float mu[16], inv2S[16], base = 0.f, a_out = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+      // ---- pass A: assignments of this iteration and the weighted vote sums ----
+      float A1[16], R = 0.f;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) A1[h] = 0.f;
+#pragma unroll 1
+      for (int i = 0; i < kB; ++i) {
+        float V[16];
+        votes_of(sc, sW, i, lane, V, wst);
+        float r;
+        if (t == 0) {
+          r = 1.f / (float)C;
+        } else {
+          float q = 0.f;
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const float dv = V[h] - mu[h];
+            q = fmaf(dv * dv, inv2S[h], q);
+          }
+          const float z = active ? (base - q) : -INFINITY;
+          const float mx = warp_max(z);
+          const float e = active ? expf(z - mx) : 0.f;
+          r = e / warp_sum(e);
+        }
+        const float rp = active ? r * s_ain[i] : 0.f;
+        const float Z = warp_sum(rp) + kEps;
+        const float rn = rp / Z;
+        if (active) srn[i * wst + lane] = rn;
+        R += rn;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) A1[h] = fmaf(rn, V[h], A1[h]);
+      }
+      const float invR = 1.f / (R + kEps);
+#pragma unroll
+      for (int h = 0; h < 16; ++h) mu[h] = A1[h] * invR;
+      // ---- pass B: variance around the new mean ----
+      float S[16];
+#pragma unroll
+      for (int h = 0; h < 16; ++h) S[h] = 0.f;
+#pragma unroll 1
+      for (int i = 0; i < kB; ++i) {
+        float V[16];
+        votes_of(sc, sW, i, lane, V, wst);
+        const float c = srn[i * wst + lane] * invR;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          const float dv = V[h] - mu[h];
+          S[h] = fmaf(c, dv * dv, S[h]);
+        }
+      }
+      float T = 0.f, lnS = 0.f;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) {
+        S[h] += kEps;
+        const float l = logf(S[h]);
+        T += bu[h] + 0.5f * l;
+        lnS += l;
+        inv2S[h] = 0.5f / S[h];
+      }
+      const float cost = T * R;
+      const double cd = active ? (double)cost : 0.0;
+      const double md = warp_sum_d(cd) / (double)C;
+      const double dev = active ? (cd - md) : 0.0;
+      const double sdev = warp_sum_d(dev);
+      const double stdv = sqrt(sdev * sdev / (double)C + (double)kEps);
+      const float inv_s = (float)(1.0 / (stdv + (double)kEps));
+      const float u = kLambda * (ba - ((float)md - cost) * inv_s);
+      a_out = 1.f / (1.f + expf(-u));
+      base = -0.5f * lnS - kHalfLn2Pi16 + logf(kEps + a_out);
+    }
+    if (active) {
+      float* dst = out + loc * ocols;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) dst[lane * 16 + h] = mu[h];
+      dst[C * 16 + lane] = a_out;
     }
   }
 }
@@ -574,6 +721,28 @@ B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* b
     cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd attr");
     cfg = true;
+  }
+  // default: warp-per-location kernel (r02); B2C_ROUTING=cta selects the CTA-per-location kernel of round 1
+  static int use_warp = -1;
+  if (use_warp < 0) {
+    const char* e = getenv("B2C_ROUTING");
+    use_warp = (e && e[0] == 'c') ? 0 : 1;
+  }
+  if (use_warp) {
+    const int wst = routing_pitch(C);
+    const size_t smw = (size_t)(kB * 16 * wst + 8 + kWL * 544 + kWL * (kB * wst + 8)) * sizeof(float);
+    static bool cfgw = false;
+    if (!cfgw) {
+      cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+      if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd(warp) attr");
+      cfgw = true;
+    }
+    long long gridw = 2LL * b2c_num_sms();
+    if (gridw * kWL > b) gridw = (b + kWL - 1) / kWL;
+    em_routing_fwd_warp_kernel<<<(unsigned)gridw, kWL * 32, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, b, C);
+    b2c_launches_add(1);
+    B2C_LAUNCH_CHECK("em_routing_fwd(warp)");
+    return 0;
   }
   long long grid = (kNW == 8 ? 2LL : 1LL) * b2c_num_sms();
   if (grid > b) grid = b;

@@ -214,15 +214,15 @@ def test_train_mode_segment_parity(setup, precision):
     errs_exact = {k: rel(gp[k].grad, gr) for k, gr in zip(dec_names, gref_exact[:-1])}
     print(f"[{precision}] decoder grads vs oracle(same roundings):", {k: f"{v:.1e}" for k, v in errs.items()})
     print(f"[{precision}] decoder grads vs exact fp64 oracle      :", {k: f"{v:.1e}" for k, v in errs_exact.items()})
-    # measured: <= 3e-2 except the two stride-2 ConvTranspose3d(128->64) weights (5e-2 .. 1.4e-1 depending on the run's
-    # inputs, which vary with the train-mode encoder's atomics; their wgrad kernel passes at the same shapes in
-    # tests/gpu_igemm_probe.py at 1e-6 against torch).  Reported, loosely bounded; open item in DESIGN.md.
-    loose = {"upsample2.weight", "upsample3.weight"}
-    if tf32:
-        assert max(errs_exact.values()) < 1e-2, errs_exact
-    else:
-        assert max(v for k, v in errs.items() if k not in loose) < 4e-2, errs
-        assert max(errs[k] for k in loose) < 0.25, errs
+    # Bound per tensor: the mode's bar, or -- where the REFERENCE'S OWN gradient moves by more than that when its GEMM
+    # operands / stored activations are rounded (own[k] = rounded oracle vs exact oracle: ReLU masks flip, and these
+    # gradients are noise-like sums at random init) -- 1.5 x that deviation.  This is the root cause of the round-1
+    # "upsample2/3.weight" finding: tests/gpu_wgrad_bisect.py shows the kernels reproduce torch-fp64 on identical
+    # operands to 5e-7; the incoming gradient itself differs by ~8e-2 once a few hundred ReLU decisions flip.
+    own = {k: rel(gr, ge) for k, gr, ge in zip(dec_names + ["rout"], gref, gref_exact)}
+    print(f"[{precision}] reference's own decoder-gradient deviation under the same rounding:", {k: f"{v:.1e}" for k, v in own.items()})
+    for k, v in errs.items():
+        assert v < max(T(3e-2, 1e-3), 1.5 * own[k]), (k, v, own[k])
 
     # ---- end to end, reported (not asserted at 2e-2: see docstring) -----------------------------------
     model.load_state_dict(sd0)
