@@ -47,6 +47,9 @@ typedef struct {
   int32_t Qt, Qh, Qw;       /* GEMM-M grid of this class */
   int32_t po_t, po_h, po_w; /* output offset of this class */
   int32_t lo_t, lo_h, lo_w; /* per-dimension minimum tap offset (lower corner of the im2col TMA box) */
+  int32_t h_block;          /* 0, or: the taps come in consecutive blocks of h_block taps that share (dt, dh), dt the same for all,
+                               dh monotonic -- lets a tile skip the blocks whose source rows are padding for all its rows */
+  int32_t pad_;
 } b2c_conv_class;
 
 typedef struct {

@@ -16,7 +16,8 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 class ConvClass(C.Structure):
     _fields_ = [("taps", vp), ("w", vp), ("ntaps", i32), ("Qt", i32), ("Qh", i32), ("Qw", i32),
-                ("po_t", i32), ("po_h", i32), ("po_w", i32), ("lo_t", i32), ("lo_h", i32), ("lo_w", i32)]
+                ("po_t", i32), ("po_h", i32), ("po_w", i32), ("lo_t", i32), ("lo_h", i32), ("lo_w", i32),
+                ("h_block", i32), ("pad_", i32)]
 
 
 class ConvDesc(C.Structure):

@@ -568,6 +568,46 @@ class MaxPoolFn(torch.autograd.Function):
         return dx, None, None
 
 
+def bn_fwd_part(raw: View, m, y: View, g: int):
+    """Training-mode BatchNorm3d + ReLU of one channel window of a (possibly fused) convolution output -> y.
+    Returns (mean, rstd) of the window (per statistics group)."""
+    C = raw.C
+    ws = zeros_f32((g, 2, C), raw.t.device)
+    mean = torch.empty((g, C), dtype=torch.float32, device=raw.t.device)
+    rstd = torch.empty((g, C), dtype=torch.float32, device=raw.t.device)
+    ops.bn_sums(raw, g, ws)
+    ops.bn_finalize(ws, C, 0, C, g, raw.rows // g, mean, rstd, m.bn.running_mean, m.bn.running_var, BN_MOMENTUM, BN_EPS)
+    ops.bn_relu_apply(raw, g, mean, rstd, m.bn.weight.detach(), m.bn.bias.detach(), y, relu=True)
+    return mean, rstd
+
+
+def bn_bwd_part(raw: View, y: View, gy: View, draw: View, m, mean, rstd, g: int):
+    """Backward of bn_fwd_part: writes d(raw) into `draw`; returns (dgamma, dbeta) (None where accumulated into .grad)."""
+    ws = zeros_f32((g, 2, raw.C), raw.t.device)
+    ops.bn_relu_bwd_reduce(gy, y, raw, g, mean, rstd, ws, relu=True)
+    dgamma, d1 = grad_buf(m.bn.weight)
+    dbeta, d2 = grad_buf(m.bn.bias)
+    ops.bn_relu_bwd_apply(gy, y, raw, g, mean, rstd, m.bn.weight.detach(), ws, draw, dgamma, dbeta, relu=True)
+    return (None if d1 else dgamma), (None if d2 else dbeta)
+
+
+# Inception blocks: the three 1x1x1 convolutions that read the block input (b0, b1a, b2a) run as ONE implicit GEMM with
+# N = c0 + c1 + c3 output channels (176 .. 448), their three input gradients as ONE dgrad GEMM over the stacked output
+# gradients: 2 launches instead of 6 per block and one read of x instead of three.  B2C_FUSE_SIBLINGS=0 disables.
+FUSE_SIBLINGS = os.environ.get("B2C_FUSE_SIBLINGS", "1") != "0"
+
+
+def _sibling_layer(mod) -> "FusedConvLayer":
+    fl = mod.__dict__.get("_fused_siblings")
+    ws = [mod.b0.conv3d.weight, mod.b1a.conv3d.weight, mod.b2a.conv3d.weight]
+    if fl is None or any(a is not b for a, b in zip(fl.weights, ws)):
+        cin = int(ws[0].shape[1])
+        cout = sum(int(w.shape[0]) for w in ws)
+        fl = FusedConvLayer(ws, lambda d, cin=cin, cout=cout: ConvSpec(cin, cout, (1, 1, 1)))
+        mod.__dict__["_fused_siblings"] = fl
+    return fl
+
+
 class InceptionFn(torch.autograd.Function):
     """InceptionModule (pytorch_i3d.py:124-149) hand-scheduled: six Unit3D + same-pad max-pool, every branch
     writes straight into its channel slot of the concatenated output (no torch.cat), gradients of the four
@@ -595,10 +635,20 @@ class InceptionFn(torch.autograd.Function):
             return unit_fwd(m._layer, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var, xin, yout, training, g)
 
         sv = {}
-        sv["b0"] = run("b0", xv, View(out, 0, c0))
-        sv["b1a"] = run("b1a", xv, View(mid1))
+        fused = training and FUSE_SIBLINGS and c0 % 8 == 0 and c1 % 8 == 0 and c3 % 8 == 0
+        raw3 = None
+        if fused:
+            fl = _sibling_layer(mod)
+            raw3 = torch.empty((N, T, H, W, c0 + c1 + c3), dtype=act_dtype(), device=dev)
+            ops.conv_fprop(fl.packed((T, H, W), "fprop"), "fprop", xv, View(raw3))
+            sv["b0"] = bn_fwd_part(View(raw3, 0, c0), u["b0"], View(out, 0, c0), g)
+            sv["b1a"] = bn_fwd_part(View(raw3, c0, c1), u["b1a"], View(mid1), g)
+            sv["b2a"] = bn_fwd_part(View(raw3, c0 + c1, c3), u["b2a"], View(mid2), g)
+        else:
+            sv["b0"] = run("b0", xv, View(out, 0, c0))
+            sv["b1a"] = run("b1a", xv, View(mid1))
+            sv["b2a"] = run("b2a", xv, View(mid2))
         sv["b1b"] = run("b1b", View(mid1), View(out, c0, c2))
-        sv["b2a"] = run("b2a", xv, View(mid2))
         sv["b2b"] = run("b2b", View(mid2), View(out, c0 + c2, c4))
         ops.maxpool_fwd(xv, View(pooled), idx, (3, 3, 3), (1, 1, 1), (1, 1, 1))
         sv["b3b"] = run("b3b", View(pooled), View(out, c0 + c2 + c4, c5))
@@ -607,7 +657,7 @@ class InceptionFn(torch.autograd.Function):
                 m.bn.num_batches_tracked += STATE.bn_groups
         ctx.mod, ctx.sv, ctx.oc = mod, sv, oc
         ctx.x, ctx.out, ctx.mid1, ctx.mid2, ctx.pooled, ctx.idx = x_cl, out, mid1, mid2, pooled, idx
-        ctx.training = training
+        ctx.training, ctx.raw3, ctx.groups = training, raw3, g
         return out
 
     @staticmethod
@@ -630,11 +680,28 @@ class InceptionFn(torch.autograd.Function):
             m = u[name]
             grads[name] = unit_bwd(m._layer, m.bn.weight, m.bn.bias, sv[name], xin, yv, gyv, dxv, acc)
 
-        run("b0", xv, View(out, 0, c0), View(gout, 0, c0), View(dx), False)
-        run("b1b", View(ctx.mid1), View(out, c0, c2), View(gout, c0, c2), View(dmid1), False)
-        run("b1a", xv, View(ctx.mid1), View(dmid1), View(dx), True)
-        run("b2b", View(ctx.mid2), View(out, c0 + c2, c4), View(gout, c0 + c2, c4), View(dmid2), False)
-        run("b2a", xv, View(ctx.mid2), View(dmid2), View(dx), True)
+        if ctx.raw3 is not None:
+            run("b1b", View(ctx.mid1), View(out, c0, c2), View(gout, c0, c2), View(dmid1), False)
+            run("b2b", View(ctx.mid2), View(out, c0 + c2, c4), View(gout, c0 + c2, c4), View(dmid2), False)
+            raw3, gq = ctx.raw3, ctx.groups
+            draw3 = torch.empty_like(raw3)
+            bn = {}
+            bn["b0"] = bn_bwd_part(View(raw3, 0, c0), View(out, 0, c0), View(gout, 0, c0), View(draw3, 0, c0), u["b0"], *sv["b0"], gq)
+            bn["b1a"] = bn_bwd_part(View(raw3, c0, c1), View(ctx.mid1), View(dmid1), View(draw3, c0, c1), u["b1a"], *sv["b1a"], gq)
+            bn["b2a"] = bn_bwd_part(View(raw3, c0 + c1, c3), View(ctx.mid2), View(dmid2), View(draw3, c0 + c1, c3), u["b2a"],
+                                    *sv["b2a"], gq)
+            fl = _sibling_layer(mod)
+            dims = tuple(x.shape[1:4])
+            ops.conv_fprop(fl.packed(dims, "dgrad"), "dgrad", View(draw3), View(dx))
+            dws = fl.wgrad(dims, xv, View(draw3))
+            for name, dwi in zip(("b0", "b1a", "b2a"), dws):
+                grads[name] = (dwi,) + bn[name]
+        else:
+            run("b0", xv, View(out, 0, c0), View(gout, 0, c0), View(dx), False)
+            run("b1b", View(ctx.mid1), View(out, c0, c2), View(gout, c0, c2), View(dmid1), False)
+            run("b1a", xv, View(ctx.mid1), View(dmid1), View(dx), True)
+            run("b2b", View(ctx.mid2), View(out, c0 + c2, c4), View(gout, c0 + c2, c4), View(dmid2), False)
+            run("b2a", xv, View(ctx.mid2), View(dmid2), View(dx), True)
         run("b3b", View(ctx.pooled), View(out, c0 + c2 + c4, c5), View(gout, c0 + c2 + c4, c5), View(dpool), False)
         ops.maxpool_bwd(View(dpool), ctx.idx, View(dx), (3, 3, 3), (1, 1, 1), (1, 1, 1), accumulate=True)
         flat = []
@@ -699,24 +766,27 @@ class FusedConvLayer:
         T = spec.k[0] * spec.k[1] * spec.k[2]
         dev = self.weights[0].device
         from .plans import packed_geometry
+        from .plans import tap_pitch
         if which == "fprop":
             cl = pl.fprop[0]
             nt = len(cl.taps)
-            bn, _, nkb, elems = packed_geometry(spec.Cout_pad, nt * spec.Cin_pad)
+            pitch = tap_pitch(spec.Cin_pad)
+            bn, _, nkb, elems = packed_geometry(spec.Cout_pad, nt * pitch)
             if cl.packed is None or cl.packed.dtype != act_dtype():
                 cl.packed = torch.zeros(elems, dtype=act_dtype(), device=dev)
             for w, co, off in zip(self.weights, self.couts, self.offs):
                 ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, co, nt, spec.Cin_pad, spec.Cin, spec.Cin * T, T,
-                              spec.Cin_pad, 0, off, bn, nkb)
+                              pitch, 0, off, bn, nkb)
         else:
             cg = self.grad_cpad or spec.Cout_pad
+            pitch = tap_pitch(cg)
             for cl in pl.dgrad:
                 nt = len(cl.taps)
-                bn, _, nkb, elems = packed_geometry(spec.Cin_pad, nt * cg)
+                bn, _, nkb, elems = packed_geometry(spec.Cin_pad, nt * pitch)
                 if cl.packed is None or cl.packed.dtype != act_dtype():
                     cl.packed = torch.zeros(elems, dtype=act_dtype(), device=dev)
                 for w, co, off in zip(self.weights, self.couts, self.offs):
-                    ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, spec.Cin, nt, co, co, T, spec.Cin * T, cg, off, 0, bn, nkb)
+                    ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, spec.Cin, nt, co, co, T, spec.Cin * T, pitch, off, 0, bn, nkb)
         self.keys[(tuple(in_dims), which)] = key
         return pl
 

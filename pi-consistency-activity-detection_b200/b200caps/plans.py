@@ -133,6 +133,27 @@ def _dim_transposed_like(k: int, s: int, p: int, out_size: int):
     return out
 
 
+def _prune_padding_taps(classes, si, in_dims):
+    """Drop the taps that read nothing but padding for EVERY output position of their class (e.g. the dt = +-1 taps of the
+    3x3x3 convolutions of Mixed_4b..4f, whose input has a single frame: 18 of their 27 taps).  Exact: such taps contribute
+    zero to fprop / dgrad and receive a zero weight gradient (which is what the zero-initialised dw already holds)."""
+    for cl in classes:
+        keep = []
+        for idx, tap in enumerate(cl.taps):
+            ok = True
+            for d, s, I, Q in zip(tap, si, in_dims, cl.Q):
+                q_lo = max(0, -(d // s)) if d < 0 else 0          # smallest q with q*s + d >= 0
+                q_hi = min(Q - 1, (I - 1 - d) // s)               # largest q with q*s + d <= I - 1
+                ok = ok and q_lo <= q_hi
+            if ok:
+                keep.append(idx)
+        if not keep:
+            keep = [0]
+        if len(keep) != len(cl.taps):
+            cl.taps = [cl.taps[i] for i in keep]
+            cl.wtap = [cl.wtap[i] for i in keep]
+
+
 def _product_classes(per_dim, kdims):
     """per_dim: for each of 3 dims a list over parity of (taps, Q).  Build the class list."""
     classes = []
@@ -219,6 +240,8 @@ class ConvPlan:
             self.wgrad_cls = self.dgrad[0]
             self.wgrad_geom = dict(g_is_input=False, sg=s, sp=(1, 1, 1), s_p=spec.Cout * T, s_g=T,
                                    Cg=spec.Cout_pad, Cg_real=spec.Cout, Cp=spec.Cin_pad, Cp_real=spec.Cin, Q=self.in_dims)
+        _prune_padding_taps(self.fprop, self.fprop_si, self.in_dims)
+        _prune_padding_taps(self.dgrad, self.dgrad_si, self.out_dims)
         self._device = None
 
     @staticmethod
@@ -262,6 +285,27 @@ class ConvPlan:
             from . import ops
             ops.pack_part(weight, cl.packed, cl.wtap_dev, pk["R"], nt, pk["C"], pk["C_real"], pk["s_r"], pk["s_c"], pitch, 0, 0,
                           bn, nkb)
+
+
+def h_block_of(taps) -> int:
+    """Taps per block of constant (dt, dh) when the tap list is such blocks with one dt overall and strictly monotonic dh
+    (2-D layers in (h, w) product order), else 0.  The kernel then skips blocks that only read padding (b2c_conv_class)."""
+    if len(taps) < 2 or len({t[0] for t in taps}) != 1:
+        return 0
+    nw = 1
+    while nw < len(taps) and taps[nw][1] == taps[0][1]:
+        nw += 1
+    if len(taps) % nw or nw == len(taps):
+        return 0
+    dhs = []
+    for b in range(len(taps) // nw):
+        blk = taps[b * nw:(b + 1) * nw]
+        if len({t[1] for t in blk}) != 1:
+            return 0
+        dhs.append(blk[0][1])
+    inc = all(b > a for a, b in zip(dhs, dhs[1:]))
+    dec = all(b < a for a, b in zip(dhs, dhs[1:]))
+    return nw if (inc or dec) else 0
 
 
 @dataclass
@@ -345,6 +389,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
         c.Qt, c.Qh, c.Qw = cl.Q
         c.po_t, c.po_h, c.po_w = cl.po
         c.lo_t, c.lo_h, c.lo_w = (min(t[i] for t in cl.taps) for i in range(3))
+        c.h_block = h_block_of(cl.taps)
     return d
 
 

@@ -185,6 +185,38 @@ __device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass,
   return ti;
 }
 
+// Taps a unit of rows [m_first, m_last] can skip: when the class marks its taps as blocks of `h_block` taps sharing one
+// H offset (2-D layers: PrimaryCaps' 9x9 dgrad reads a 20x20 gradient from 28x28 positions, upsample1's transposed 9x9
+// likewise) and the unit lies inside one (clip, t) plane, tap blocks whose source rows fall outside [0, Hi) for EVERY row
+// of the unit contribute nothing (TMA would zero-fill them) -- the valid blocks are a contiguous range.  Producer and MMA
+// issuer call this with the same arguments.
+__device__ __forceinline__ void tap_range(const b2c_conv_desc& d, const b2c_conv_class& cc, const int32_t* taps, unsigned m_first,
+                                          unsigned m_last, const FastDiv* fd3, int& lo, int& hi) {
+  lo = 0;
+  hi = cc.ntaps;
+  if (cc.h_block <= 0) return;
+  uint32_t r0, r1, h0, h1;
+  uint32_t q0 = fdivmod(m_first, fd3[0], r0);
+  uint32_t q1 = fdivmod(m_last, fd3[0], r1);
+  q0 = fdivmod(q0, fd3[1], h0);
+  q1 = fdivmod(q1, fd3[1], h1);
+  if (q0 != q1) return;                    // the unit straddles (clip, t) planes
+  const int nb = cc.ntaps / cc.h_block;
+  int first = -1, last = -1;
+  for (int b = 0; b < nb; ++b) {
+    const int dh = tap_dh(taps[b * cc.h_block]);
+    // some row h in [h0, h1] with 0 <= h * si_h + dh < Hi
+    const bool ok = (int)h1 * d.si_h + dh >= 0 && (int)h0 * d.si_h + dh <= d.Hi - 1;
+    if (ok) {
+      if (first < 0) first = b;
+      last = b;
+    }
+  }
+  if (first < 0) first = last = 0;         // nothing valid: keep one (all-zero) block so the accumulator is defined
+  lo = first * cc.h_block;
+  hi = (last + 1) * cc.h_block;
+}
+
 __device__ __forceinline__ float fmax_nan(float a, float b) {   // NaN-propagating max: relu(NaN) = NaN, max(x, -inf) = x
   float r;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -342,8 +374,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
         const uint8_t* wtile = reinterpret_cast<const uint8_t*>(cc.w) + (size_t)ti.n_idx * nkb * (size_t)b_tile_bytes +
                                (size_t)bn_i[0] * (size_t)d.w_sample_stride;
         const CUtensorMap* map = &maps.a[ti.cls];
-        int kb = 0;
-        for (int tp = 0; tp < cc.ntaps; ++tp) {
+        int tp_lo, tp_hi;
+        {
+          unsigned m_last = (unsigned)ti.m0 + (unsigned)(MT * kTileM) - 1u;
+          if (m_last >= Mtot) m_last = Mtot - 1u;
+          tap_range(d, cc, taps, (unsigned)ti.m0, m_last, s_fd + 3 * ti.cls, tp_lo, tp_hi);
+        }
+        int kb = tp_lo * cblocks;
+        for (int tp = tp_lo; tp < tp_hi; ++tp) {
           const int32_t tv = taps[tp];
           const uint16_t ow = (uint16_t)(tap_dw(tv) - cc.lo_w), oh = (uint16_t)(tap_dh(tv) - cc.lo_h),
                          ot = (uint16_t)(tap_dt(tv) - cc.lo_t);
@@ -467,10 +505,17 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       int bn = d.Cout - n0;
       if (bn > d.bn_tile) bn = d.bn_tile;
       const int bn16 = (bn + 15) & ~15;
-      const int nkb = (cc.ntaps * k_pitch + kBK - 1) / kBK;
       const uint32_t idesc = kTF32 ? umma_idesc_tf32(bn16, 0, 0) : umma_idesc_bf16(bn16, 0, 0);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MT * acc_cols);
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
+      int nkb = (cc.ntaps * k_pitch + kBK - 1) / kBK;
+      if (use_tma && cc.h_block > 0) {
+        int tp_lo, tp_hi;
+        unsigned m_last = (unsigned)ti.m0 + (unsigned)(MT * kTileM) - 1u;
+        if (m_last >= Mtot) m_last = Mtot - 1u;
+        tap_range(d, cc, s_taps + tap_off[ti.cls], (unsigned)ti.m0, m_last, s_fd + 3 * ti.cls, tp_lo, tp_hi);
+        nkb = (tp_hi - tp_lo) * (k_pitch / kBK);
+      }
       const int nvalid = (MT > 1 && (unsigned)ti.m0 + (unsigned)kTileM < Mtot) ? 2 : 1;
       B2C_PROF_DECL(w1); B2C_PROF_START(w1);
       mbar_wait(&ps->tempty[acc], acc_phase ^ 1, 4);   // epilogue has drained this accumulator
@@ -1269,6 +1314,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
               "conv_fprop: tap_pitch=%d must be Cin=%d or Cin rounded up to a multiple of %d", d.tap_pitch, d.Cin, bk);
   const int use_tma = (k_pitch % bk == 0) ? 1 : 0;
   B2C_REQUIRE(!tf32 || (use_tma && d.out_fp32 != 0), "conv_fprop: tf32 mode needs tap_pitch %% 32 == 0 and an fp32 output");
+  for (int i = 0; i < d.nclass; ++i)
+    if (d.cls[i].h_block < 0 || !use_tma || (d.cls[i].h_block > 0 && d.cls[i].ntaps % d.cls[i].h_block != 0)) d.cls[i].h_block = 0;
   if (d.out_fold != 0) {
     B2C_REQUIRE(d.out_fold % kStageChunkCols == 0 && d.Cout % d.out_fold == 0 && d.bn_tile % d.out_fold == 0 && d.nclass == 1 &&
                     d.out_fp32 != 2 && d.cls[0].Qt == 1 && d.so_t == 1 && d.cls[0].po_t + d.Cout / d.out_fold <= d.To && !d.scale_nc,

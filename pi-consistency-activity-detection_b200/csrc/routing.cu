@@ -235,6 +235,15 @@ __global__ void __launch_bounds__(kRT, kNW == 8 ? 2 : 1) em_routing_fwd_kernel(c
 // =====================================================================================
 constexpr int kWL = 8;   // warps (= locations in flight) per CTA
 
+// warp maximum in ONE instruction: floats mapped to order-preserving unsigned keys, redux.sync.max.u32
+__device__ __forceinline__ float warp_max_redux(float v) {
+  uint32_t u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  u = __reduce_max_sync(0xffffffffu, u);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
 __device__ __forceinline__ void votes_of(const float* __restrict__ sc, const float* __restrict__ sW, int i, int lane, float* V, int wst) {
   float M[16], Wr[16];
 #pragma unroll
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
             q = fmaf(dv * dv, inv2S[h], q);
           }
           const float z = active ? (base - q) : -INFINITY;
-          const float mx = warp_max(z);
+          const float mx = warp_max_redux(z);
           const float e = active ? expf(z - mx) : 0.f;
           r = e / warp_sum(e);
         }
