@@ -241,6 +241,15 @@ int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, c
  * dW/dbeta_u/dbeta_a are accumulated (atomicAdd) -- zero them first. */
 int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
                        float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s);
+/* Training pair: the forward also saves the per-iteration routing state (assignments, normalisers, means, variances:
+ * b2c_em_routing_state_floats() floats per location) and the backward reads it instead of recomputing the three EM
+ * iterations.  Same results as the pair above. */
+int64_t b2c_em_routing_state_floats(void);
+int b2c_em_routing_fwd_train(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, float* state,
+                             int64_t b, int32_t C, b2c_stream_t s);
+int b2c_em_routing_bwd_state(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
+                             const float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
+                             b2c_stream_t s);
 /* PrimaryCaps backward prologue (capsules_ucf101.py:43-49 adjoint): g, out fp32 (rows,544); dz bf16 (rows,dz_pitch>=544) =
  * g * (col >= 512 ? a(1-a) : 1); dbias[544] += column sums (first 512: pose bias, last 32: a bias). */
 int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, int32_t dz_pitch,

@@ -75,6 +75,8 @@ _SIGS = {
     "b2c_stencil27_bwd": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "b2c_em_routing_fwd": [vp, vp, vp, vp, vp, i64, i32, vp],
     "b2c_em_routing_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
+    "b2c_em_routing_fwd_train": [vp, vp, vp, vp, vp, vp, i64, i32, vp],
+    "b2c_em_routing_bwd_state": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "b2c_primarycaps_bwd_prep": [vp, vp, vp, vp, i64, i32, vp],
     "b2c_class_mean_fwd": [vp, vp, i32, i32, i32, vp],
     "b2c_pose_mask_fwd": [vp, vp, vp, i32, i32, i32, vp],
@@ -102,7 +104,8 @@ _SIGS = {
     "b2c_tail_chain_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["b2c_last_error", "b2c_version", "b2c_launch_count", "b2c_get_precision"])
+EXPORTS = sorted(list(_SIGS) + ["b2c_last_error", "b2c_version", "b2c_launch_count", "b2c_get_precision",
+                                "b2c_em_routing_state_floats"])
 
 _lib = None
 
@@ -128,6 +131,8 @@ def lib():
         L.b2c_launch_count.restype = C.c_longlong
         L.b2c_get_precision.restype = C.c_int
         L.b2c_get_precision.argtypes = []
+        L.b2c_em_routing_state_floats.restype = C.c_int64
+        L.b2c_em_routing_state_floats.argtypes = []
         _lib = L
     return _lib
 

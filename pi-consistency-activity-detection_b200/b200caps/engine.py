@@ -20,6 +20,8 @@ import os
 # Decoder tail: "collapsed" (default) = upsample4 -> Dropout3d -> smooth as one per-clip transposed convolution
 # (CollapsedTail below); B2C_TAIL=explicit keeps the layer-by-layer schedule (3.3 GB intermediate at 16+16 clips).
 TAIL_COLLAPSED = os.environ.get("B2C_TAIL", "collapsed") != "explicit"
+# EM routing: the training forward saves the per-iteration state for the backward kernel (B2C_ROUTING_STATE=0: recompute)
+ROUTING_SAVE_STATE = os.environ.get("B2C_ROUTING_STATE", "1") != "0"
 # Eval mode: BatchNorm folded into the convolutions (B2C_EVAL_FOLD_BN=0: conv -> running-statistics BatchNorm kernel)
 EVAL_FOLD_BN = os.environ.get("B2C_EVAL_FOLD_BN", "1") != "0"
 
@@ -852,7 +854,10 @@ class EMRoutingFn(torch.autograd.Function):
         caps = caps.contiguous()
         out = torch.empty((N, h, w, C * 17), dtype=torch.float32, device=caps.device)
         Wc = W.detach().reshape(32, C, 4, 4).contiguous()
-        ops.em_routing_fwd(caps, Wc, beta_u.detach().contiguous(), beta_a.detach().contiguous(), out, N * h * w, C)
+        # training: the forward saves its per-iteration state for the backward kernel (35 KB per location)
+        need_bwd = ROUTING_SAVE_STATE and any(ctx.needs_input_grad)
+        ctx.state = torch.empty((N * h * w, ops.routing_state_floats()), dtype=torch.float32, device=caps.device) if need_bwd else None
+        ops.em_routing_fwd(caps, Wc, beta_u.detach().contiguous(), beta_a.detach().contiguous(), out, N * h * w, C, state=ctx.state)
         ctx.save_for_backward(caps, W, beta_u, beta_a)
         return out
 
@@ -867,7 +872,7 @@ class EMRoutingFn(torch.autograd.Function):
         dbu, d1 = grad_buf(beta_u)
         dba, d2 = grad_buf(beta_a)
         ops.em_routing_bwd(caps, W.detach().reshape(32, C, 4, 4).contiguous(), beta_u.detach().contiguous(),
-                           beta_a.detach().contiguous(), g, dcaps, dW, dbu, dba, N * h * w, C)
+                           beta_a.detach().contiguous(), g, dcaps, dW, dbu, dba, N * h * w, C, state=getattr(ctx, "state", None))
         return dcaps, (None if d0 else dW), (None if d1 else dbu), (None if d2 else dba)
 
 

@@ -295,13 +295,27 @@ def tail_chain_bwd(dweff, class_sums, w4, b4, ws, drop_nc, dw4, db4, dws, dbs, N
 
 
 # ---- capsule head ---------------------------------------------------------------------------
-def em_routing_fwd(caps, W, beta_u, beta_a, out, b, C):
-    _bw("b2c_em_routing_fwd", b * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out), b, C, stream())
+def em_routing_fwd(caps, W, beta_u, beta_a, out, b, C, state=None):
+    """state: optional fp32 (b, routing_state_floats()) buffer -- the training forward saves the per-iteration routing
+    state there for em_routing_bwd."""
+    if state is None:
+        _bw("b2c_em_routing_fwd", b * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out), b, C, stream())
+    else:
+        _bw("b2c_em_routing_fwd_train", b * (544 + C * 17 + state.shape[1]) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out),
+            _p(state), b, C, stream())
 
 
-def em_routing_bwd(caps, W, beta_u, beta_a, dout, dcaps, dW, dbu, dba, b, C):
-    _bw("b2c_em_routing_bwd", b * 2 * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout), _p(dcaps), _p(dW), _p(dbu),
-              _p(dba), b, C, stream())
+def em_routing_bwd(caps, W, beta_u, beta_a, dout, dcaps, dW, dbu, dba, b, C, state=None):
+    if state is None:
+        _bw("b2c_em_routing_bwd", b * 2 * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout), _p(dcaps), _p(dW),
+            _p(dbu), _p(dba), b, C, stream())
+    else:
+        _bw("b2c_em_routing_bwd_state", b * (2 * (544 + C * 17) + state.shape[1]) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout),
+            _p(state), _p(dcaps), _p(dW), _p(dbu), _p(dba), b, C, stream())
+
+
+def routing_state_floats() -> int:
+    return int(_abi.lib().b2c_em_routing_state_floats())
 
 
 def primarycaps_bwd_prep(g, out, dz, dbias, rows, dz_pitch=544):

@@ -290,7 +290,7 @@ class ConvPlan:
 def h_block_of(taps) -> int:
     """Taps per block of constant (dt, dh) when the tap list is such blocks with one dt overall and strictly monotonic dh
     (2-D layers in (h, w) product order), else 0.  The kernel then skips blocks that only read padding (b2c_conv_class)."""
-    if len(taps) < 2 or len({t[0] for t in taps}) != 1:
+    if len(taps) < 2 or len({t[0] for t in taps}) != 1 or os.environ.get("B2C_TAP_SKIP", "1") == "0":
         return 0
     nw = 1
     while nw < len(taps) and taps[nw][1] == taps[0][1]:

@@ -235,6 +235,17 @@ __global__ void __launch_bounds__(kRT, kNW == 8 ? 2 : 1) em_routing_fwd_kernel(c
 // =====================================================================================
 constexpr int kWL = 8;   // warps (= locations in flight) per CTA
 
+// Routing state saved by the training forward for the backward kernel (floats per location, 32-lane rows):
+//   r_t[i][32] (t = 1, 2: the E-step assignments; t = 0 is the constant 1/C), rn_t[i][32] (t = 0..2), Z_t[i] (t = 0..2),
+//   per-j scalars [t][R, T, a, 1/(stdv + eps)][32], mu_t[h][32], S_t[h][32]
+constexpr int kStR = 0;
+constexpr int kStRN = kStR + 2 * kB * 32;
+constexpr int kStZ = kStRN + 3 * kB * 32;
+constexpr int kStSC = kStZ + 3 * kB;
+constexpr int kStMU = kStSC + 3 * 4 * 32;
+constexpr int kStS = kStMU + 3 * 16 * 32;
+constexpr int kStFloats = kStS + 3 * 16 * 32;     // 8672 floats = 34.7 KB per location
+
 // warp maximum in ONE instruction: floats mapped to order-preserving unsigned keys, redux.sync.max.u32
 __device__ __forceinline__ float warp_max_redux(float v) {
   uint32_t u = __float_as_uint(v);
@@ -270,7 +281,8 @@ __host__ __device__ __forceinline__ int routing_pitch(int C) { return C <= 24 ? 
 
 __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const float* __restrict__ caps, const float* __restrict__ W,
                                                                          const float* __restrict__ beta_u, const float* __restrict__ beta_a,
-                                                                         float* __restrict__ out, long long b, int C) {
+                                                                         float* __restrict__ out, float* __restrict__ state, long long b,
+                                                                         int C) {
   extern __shared__ float sm[];
   const int wst = routing_pitch(C);
   float* sW = sm;                                   // [32][16][wst] (+ 8 floats of slack for the masked lanes' reads)
@@ -296,6 +308,7 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
       reinterpret_cast<float4*>(sc)[idx] = reinterpret_cast<const float4*>(caps + loc * 544)[idx];
     __syncwarp();
     const float* s_ain = sc + 512;
+    float* st = state ? state + loc * kStFloats : nullptr;
     float mu[16], inv2S[16], base = 0.f, a_out = 0.f;
 #pragma unroll 1
     for (int t = 0; t < 3; ++t) {
@@ -326,6 +339,11 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
         const float Z = warp_sum(rp) + kEps;
         const float rn = rp / Z;
         if (active) srn[i * wst + lane] = rn;
+        if (st) {
+          if (t > 0) st[kStR + ((t - 1) * kB + i) * 32 + lane] = r;
+          st[kStRN + (t * kB + i) * 32 + lane] = rn;
+          if (lane == 0) st[kStZ + t * kB + i] = Z;
+        }
         R += rn;
 #pragma unroll
         for (int h = 0; h < 16; ++h) A1[h] = fmaf(rn, V[h], A1[h]);
@@ -367,6 +385,15 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
       const float u = kLambda * (ba - ((float)md - cost) * inv_s);
       a_out = 1.f / (1.f + expf(-u));
       base = -0.5f * lnS - kHalfLn2Pi16 + logf(kEps + a_out);
+      if (st) {
+        float* sc4 = st + kStSC + t * 4 * 32 + lane;
+        sc4[0] = R; sc4[32] = T; sc4[64] = a_out; sc4[96] = inv_s;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          st[kStMU + (t * 16 + h) * 32 + lane] = mu[h];
+          st[kStS + (t * 16 + h) * 32 + lane] = S[h];
+        }
+      }
     }
     if (active) {
       float* dst = out + loc * ocols;
@@ -378,9 +405,13 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
 }
 
 // =====================================================================================
+// kSaved: the per-iteration routing state comes from the training forward (em_routing_fwd_warp_kernel, `state`) instead
+// of being recomputed here -- the recomputation was a third of this kernel (six block-wide reductions per location).
+template <bool kSaved>
 __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __restrict__ caps, const float* __restrict__ W,
                                                                 const float* __restrict__ beta_u, const float* __restrict__ beta_a,
-                                                                const float* __restrict__ dout, float* __restrict__ dcaps,
+                                                                const float* __restrict__ dout, const float* __restrict__ state,
+                                                                float* __restrict__ dcaps,
                                                                 float* __restrict__ dW, float* __restrict__ dbeta_u,
                                                                 float* __restrict__ dbeta_a, long long b, int C) {
   extern __shared__ float sm[];
@@ -416,8 +447,27 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
     float V[kIPT][16];
     compute_votes(s_caps, sW, w, lane, V);
 
-    // ---- forward with the per-iteration state kept in shared memory ----
-    {
+    if (kSaved) {
+      // ---- per-iteration state of this location, saved by the training forward ----
+      const float* stg = state + loc * kStFloats;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        float* st = s_st + (size_t)t * 3 * kIPT * kRT + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+          const int i = w + kNW * k;
+          st[(0 * kIPT + k) * kRT] = t == 0 ? 1.f / (float)C : stg[kStR + ((t - 1) * kB + i) * 32 + lane];
+          st[(1 * kIPT + k) * kRT] = stg[kStRN + (t * kB + i) * 32 + lane];
+          st[(2 * kIPT + k) * kRT] = stg[kStZ + t * kB + i];
+        }
+      }
+      for (int idx = threadIdx.x; idx < 3 * 4 * 32; idx += kRT) s_sc[idx] = stg[kStSC + idx];
+      for (int idx = threadIdx.x; idx < 3 * 16 * 32; idx += kRT) {
+        s_mu[idx] = stg[kStMU + idx];
+        s_S[idx] = stg[kStS + idx];
+      }
+    } else {
+      // ---- forward with the per-iteration state kept in shared memory ----
       float r[kIPT], rn[kIPT], Z[kIPT], mu[16], S[16];
 #pragma unroll
       for (int k = 0; k < kIPT; ++k) r[k] = 1.f / (float)C;
@@ -719,25 +769,18 @@ __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* 
 
 }  // namespace
 
-B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, int64_t b,
-                               int32_t C, b2c_stream_t s) {
+static int routing_fwd_impl(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, float* state,
+                            int64_t b, int32_t C, b2c_stream_t s) {
   B2C_REQUIRE(caps && W && beta_u && beta_a && out, "em_routing_fwd: null pointer");
   B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_fwd: C=%d must be in [1,32]", C);
   if (b <= 0) return 0;
-  const size_t smem = (size_t)(kB * 16 * 32 + (kNW + 1) * 17 * 32 + 544) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd attr");
-    cfg = true;
-  }
   // default: warp-per-location kernel (r02); B2C_ROUTING=cta selects the CTA-per-location kernel of round 1
   static int use_warp = -1;
   if (use_warp < 0) {
     const char* e = getenv("B2C_ROUTING");
     use_warp = (e && e[0] == 'c') ? 0 : 1;
   }
-  if (use_warp) {
+  if (use_warp || state) {
     const int wst = routing_pitch(C);
     const size_t smw = (size_t)(kB * 16 * wst + 8 + kWL * 544 + kWL * (kB * wst + 8)) * sizeof(float);
     static bool cfgw = false;
@@ -748,10 +791,17 @@ B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* b
     }
     long long gridw = 2LL * b2c_num_sms();
     if (gridw * kWL > b) gridw = (b + kWL - 1) / kWL;
-    em_routing_fwd_warp_kernel<<<(unsigned)gridw, kWL * 32, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, b, C);
+    em_routing_fwd_warp_kernel<<<(unsigned)gridw, kWL * 32, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
     b2c_launches_add(1);
     B2C_LAUNCH_CHECK("em_routing_fwd(warp)");
     return 0;
+  }
+  const size_t smem = (size_t)(kB * 16 * 32 + (kNW + 1) * 17 * 32 + 544) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd attr");
+    cfg = true;
   }
   long long grid = (kNW == 8 ? 2LL : 1LL) * b2c_num_sms();
   if (grid > b) grid = b;
@@ -761,8 +811,22 @@ B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* b
   return 0;
 }
 
-B2C_API int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
-                               float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s) {
+B2C_API int b2c_em_routing_fwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, int64_t b,
+                               int32_t C, b2c_stream_t s) {
+  return routing_fwd_impl(caps, W, beta_u, beta_a, out, nullptr, b, C, s);
+}
+
+B2C_API int64_t b2c_em_routing_state_floats(void) { return kStFloats; }
+
+B2C_API int b2c_em_routing_fwd_train(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out,
+                                     float* state, int64_t b, int32_t C, b2c_stream_t s) {
+  B2C_REQUIRE(state, "em_routing_fwd_train: null state buffer");
+  return routing_fwd_impl(caps, W, beta_u, beta_a, out, state, b, C, s);
+}
+
+static int routing_bwd_impl(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
+                            const float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
+                            b2c_stream_t s) {
   B2C_REQUIRE(caps && W && beta_u && beta_a && dout && dcaps && dW && dbeta_u && dbeta_a, "em_routing_bwd: null pointer");
   B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_bwd: C=%d must be in [1,32]", C);
   if (b <= 0) return 0;
@@ -770,17 +834,34 @@ B2C_API int b2c_em_routing_bwd(const float* caps, const float* W, const float* b
                                3 * 4 * 32) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_bwd attr");
     cfg = true;
   }
   long long grid = b2c_num_sms();
   if (grid > b) grid = b;
-  em_routing_bwd_kernel<<<(unsigned)grid, kRT, smem, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, dout, dcaps, dW, dbeta_u, dbeta_a,
-                                                                       b, C);
+  if (state)
+    em_routing_bwd_kernel<true><<<(unsigned)grid, kRT, smem, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, dout, state, dcaps, dW, dbeta_u,
+                                                                               dbeta_a, b, C);
+  else
+    em_routing_bwd_kernel<false><<<(unsigned)grid, kRT, smem, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, dout, nullptr, dcaps, dW,
+                                                                                dbeta_u, dbeta_a, b, C);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("em_routing_bwd");
   return 0;
+}
+
+B2C_API int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
+                               float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s) {
+  return routing_bwd_impl(caps, W, beta_u, beta_a, dout, nullptr, dcaps, dW, dbeta_u, dbeta_a, b, C, s);
+}
+
+B2C_API int b2c_em_routing_bwd_state(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
+                                     const float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
+                                     b2c_stream_t s) {
+  B2C_REQUIRE(state, "em_routing_bwd_state: null state buffer");
+  return routing_bwd_impl(caps, W, beta_u, beta_a, dout, state, dcaps, dW, dbeta_u, dbeta_a, b, C, s);
 }
 
 B2C_API int b2c_class_mean_fwd(const float* rout, float* act, int32_t N, int32_t L, int32_t C, b2c_stream_t s) {

@@ -37,8 +37,10 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(e) / n
 
-    t_f = timeit(lambda: ops.em_routing_fwd(caps, W, bu, ba, out, b, C))
-    t_b = timeit(lambda: ops.em_routing_bwd(caps, W, bu, ba, dout, dcaps, dW, dbu, dba, b, C))
+    use_state = os.environ.get("B2C_ROUTING_STATE", "1") != "0" and os.environ.get("B2C_ROUTING", "warp") != "cta"
+    state = torch.empty((b, ops.routing_state_floats()), device=dev) if use_state else None
+    t_f = timeit(lambda: ops.em_routing_fwd(caps, W, bu, ba, out, b, C, state=state))
+    t_b = timeit(lambda: ops.em_routing_bwd(caps, W, bu, ba, dout, dcaps, dW, dbu, dba, b, C, state=state))
     # parity on 64 locations against the fp64 oracle (forward) and its autograd (backward)
     n = 64
     c64 = caps[:n].double().cpu().requires_grad_(True)
@@ -49,10 +51,13 @@ def main():
     e_f = float((out[:n].double().cpu() - ref.detach()).abs().max() / ref.detach().abs().max())
     gr = torch.autograd.grad(ref, [c64, W64, bu64, ba64], dout[:n].double().cpu())
     dW.zero_(); dbu.zero_(); dba.zero_()
-    ops.em_routing_bwd(caps[:n].contiguous(), W, bu, ba, dout[:n].contiguous(), dcaps[:n], dW, dbu, dba, n, C)
+    st_n = torch.empty((n, ops.routing_state_floats()), device=dev) if use_state else None
+    out_n = torch.empty((n, C * 17), device=dev)
+    ops.em_routing_fwd(caps[:n].contiguous(), W, bu, ba, out_n, n, C, state=st_n)
+    ops.em_routing_bwd(caps[:n].contiguous(), W, bu, ba, dout[:n].contiguous(), dcaps[:n], dW, dbu, dba, n, C, state=st_n)
     torch.cuda.synchronize()
     rel = lambda x, y: float((x.double().cpu() - y).abs().max() / (y.abs().max() + 1e-30))
-    print(f"B2C_ROUTING={os.environ.get('B2C_ROUTING', 'warp')}: fwd {t_f:.3f} ms  bwd {t_b:.3f} ms | parity fwd {e_f:.2e} "
+    print(f"B2C_ROUTING={os.environ.get('B2C_ROUTING', 'warp')} saved-state={use_state}: fwd {t_f:.3f} ms  bwd {t_b:.3f} ms | parity fwd {e_f:.2e} "
           f"dcaps {rel(dcaps[:n], gr[0]):.2e} dW {rel(dW.reshape(gr[1].shape), gr[1]):.2e} dbu {rel(dbu.reshape(gr[2].shape), gr[2]):.2e} "
           f"dba {rel(dba.reshape(gr[3].shape), gr[3]):.2e}")
 
