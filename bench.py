@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
                     help="bf16 (default) or tf32 = fp32 activations / tcgen05 kind::tf32 operands (the reference's arithmetic)")
     ap.add_argument("--classes", type=int, default=24, choices=[24, 21], help="24 = UCF101-24 (config 2/3), 21 = JHMDB-21 (config 4)")
+    ap.add_argument("--u8", action="store_true", help="uint8 input pipeline: the host hands over uint8 clips / masks, /255 and the "
+                    "mirrored pass are produced on the device (26 MB instead of 180 MB per step over PCIe)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short config 3 (--gv) / config 4 (JHMDB-21) measurements")
     return ap.parse_args()
 
@@ -236,7 +238,13 @@ def run_ours(args):
     step = TrainStep(model, sa)
     P = 2 * args.clips
     hb = synthetic_host_batch(args.clips, args.clips, seed=47 + rank, num_classes=args.classes)
-    db = {k: (v.to(dev) if k != "labels" else v) for k, v in hb.items()}
+    if args.u8:
+        # what the dataloader decodes (ucf_dataloader.py:162-185): uint8 frames and masks; aug_data never exists on the host
+        pin = lambda t: t.pin_memory()
+        hb["data"] = pin((hb["data"] * 255.0).round().clamp_(0, 255).to(torch.uint8))
+        hb["seg"] = pin(hb["seg"].to(torch.uint8))
+        hb["fl_data"] = None
+    db = {k: (v.to(dev) if (k != "labels" and v is not None) else v) for k, v in hb.items()}
 
     def barrier():
         if world > 1:
@@ -253,7 +261,7 @@ def run_ours(args):
     # ---- the step as one CUDA graph (removes ~600 launches + the Python tape from the critical path) -------
     use_graph = not args.no_graph
     if use_graph:
-        step.capture(P, hb["labels"], epoch=1, init_batch=(db["data"], db["fl_data"], db["action"], db["seg"]))
+        step.capture(P, hb["labels"], epoch=1, init_batch=(db["data"], db["fl_data"], db["action"], db["seg"]), uint8_inputs=args.u8)
         launches_per_step = step.launches_per_step
 
         def run_resident():
@@ -277,7 +285,7 @@ def run_ours(args):
 
         def run_e2e_loop(k):
             for _ in range(k):
-                d = {kk: hb[kk].to(dev, non_blocking=True) for kk in ("data", "fl_data", "action", "seg")}
+                d = {kk: (hb[kk].to(dev, non_blocking=True) if hb[kk] is not None else None) for kk in ("data", "fl_data", "action", "seg")}
                 r = step(d["data"], d["fl_data"], d["action"], d["seg"], hb["labels"], epoch=1)
                 out_host.copy_(r["total"].detach().reshape(1), non_blocking=True)
     out_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -303,7 +311,7 @@ def run_ours(args):
     loss_val = float(res["total"])
 
     # ---- end-to-end through the public call with HOST buffers ------------------------------------------
-    h2d = sum(hb[k].numel() * hb[k].element_size() for k in ("data", "fl_data", "action", "seg"))
+    h2d = sum(hb[k].numel() * hb[k].element_size() for k in ("data", "fl_data", "action", "seg") if hb[k] is not None)
     run_e2e_loop(max(1, args.warmup))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -442,6 +450,7 @@ def run_ours(args):
             "data": "synthetic (U[0,1) 8x224x224 clips, random box masks, random-init weights)",
             "config": {"workload": WORKLOAD if world == 1 else WORKLOAD.replace("1xB200", f"{world}xB200 data-parallel, NCCL all-reduce"),
                        "clips_per_gpu": P, "mode": args.mode, "classes": args.classes, "n_frames": 5, "cuda_graph": use_graph,
+                       "host_inputs": "uint8 clips + masks (device-side /255 and mirrored pass)" if args.u8 else "fp32 clips, mirrored clips, masks",
                        "l2": "working set per step (>20 GB of activations) >> 126 MB L2; no explicit flush",
                        "e2e_pipeline": "graph mode: the pinned-host -> device copy of step i+1 runs on a copy stream under the compute "
                                        "of step i (TrainStep.prefetch); every step's inputs are copied inside the timed region",

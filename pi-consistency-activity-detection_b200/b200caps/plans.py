@@ -290,7 +290,10 @@ class ConvPlan:
 def h_block_of(taps) -> int:
     """Taps per block of constant (dt, dh) when the tap list is such blocks with one dt overall and strictly monotonic dh
     (2-D layers in (h, w) product order), else 0.  The kernel then skips blocks that only read padding (b2c_conv_class)."""
-    if len(taps) < 2 or len({t[0] for t in taps}) != 1 or os.environ.get("B2C_TAP_SKIP", "1") == "0":
+    # Off by default: measured no gain at the step's shapes (PrimaryCaps dgrad 1.51 -> 1.57 ms, upsample1 0.335 -> 0.336):
+    # with the static round-robin tile order every CTA's tiles sit at the same phase of the 784-row clip period
+    # (37 m-tiles between them = 6.04 periods), so the CTAs that own interior rows skip nothing and set the kernel time.
+    if len(taps) < 2 or len({t[0] for t in taps}) != 1 or os.environ.get("B2C_TAP_SKIP", "0") != "1":
         return 0
     nw = 1
     while nw < len(taps) and taps[nw][1] == taps[0][1]:

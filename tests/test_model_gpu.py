@@ -221,8 +221,16 @@ def test_train_mode_segment_parity(setup, precision):
     # operands to 5e-7; the incoming gradient itself differs by ~8e-2 once a few hundred ReLU decisions flip.
     own = {k: rel(gr, ge) for k, gr, ge in zip(dec_names + ["rout"], gref, gref_exact)}
     print(f"[{precision}] reference's own decoder-gradient deviation under the same rounding:", {k: f"{v:.1e}" for k, v in own.items()})
-    for k, v in errs.items():
-        assert v < max(T(3e-2, 1e-3), 1.5 * own[k]), (k, v, own[k])
+    # The assertion is norm-wise (relative L2 over the tensor): the max-abs figure of a 100 K-element noise-like tensor is
+    # set by its single worst element and swings 6e-2 .. 1.5e-1 between runs of the same build (the train-mode encoder
+    # sums with fp32 atomics, so the decoder's inputs differ in the last bit from run to run); it is printed above.
+    def l2(a, b):
+        a, b = a.double().cpu(), b.double().cpu()
+        return float((a - b).norm() / (b.norm() + 1e-300))
+    ours = [gp[k].grad for k in dec_names] + [rout_leaf.grad]
+    for k, g_ours, gr, ge in zip(dec_names + ["rout"], ours, gref, gref_exact):
+        e_l2, own_l2 = l2(g_ours, gr), l2(gr, ge)
+        assert e_l2 < max(T(3e-2, 1e-3), 1.5 * own_l2), (k, e_l2, own_l2, errs[k], own[k])
 
     # ---- end to end, reported (not asserted at 2e-2: see docstring) -----------------------------------
     model.load_state_dict(sd0)
