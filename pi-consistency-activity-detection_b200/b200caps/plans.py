@@ -60,6 +60,10 @@ def kblock() -> int:
     return 32 if PREC.mode else 64
 
 
+# widest output-channel tile of layers with more than 256 output channels (PrimaryCaps 544, its dgrad 832)
+BN_TILE_MAX = int(os.environ.get("B2C_BN_TILE_MAX", "256"))
+
+
 def tap_pitch(C: int) -> int:
     """K columns per tap of a packed operand over C stored channels."""
     if PREC.mode:
@@ -71,7 +75,7 @@ def pick_bn_tile(cout: int) -> int:
     """Output-channel tile per CTA (UMMA N): the whole Cout when <= 256, else an even split (multiple of 16)."""
     if cout <= 256:
         return (cout + 15) // 16 * 16
-    nt = (cout + 255) // 256
+    nt = (cout + BN_TILE_MAX - 1) // BN_TILE_MAX
     return ((cout + nt - 1) // nt + 15) // 16 * 16
 
 

@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restr
       idx2[j] = 0x00ff00ffu;
     }
     int tap = 0;
+    bool seen_pad = false;
     for (int a = 0; a < G.kt; ++a) {
       const int it = ot * G.st - G.pt + a;
       for (int b = 0; b < G.kh; ++b) {
@@ -364,7 +365,14 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_kernel(const bf16* __restr
         for (int c = 0; c < G.kw; ++c, ++tap) {
           const int iw = ow * G.sw - G.pw + c;
           const bool inb = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi && (unsigned)iw < (unsigned)G.Wi;
-          uint4 raw = make_uint4(0, 0, 0, 0);     // F.pad zeros are real candidates (pytorch_i3d.py:44)
+          // F.pad zeros are real candidates (pytorch_i3d.py:44) -- but only the FIRST padding tap can ever win: once it has
+          // been considered every running maximum is >= 0 and '>' is strict, so later padding zeros are skipped (the 3x3x3
+          // pools of Mixed_4b..4f see one frame: 18 of their 27 taps are padding)
+          if (!inb) {
+            if (seen_pad) continue;
+            seen_pad = true;
+          }
+          uint4 raw = make_uint4(0, 0, 0, 0);
           if (inb) raw = ld16(x + ((((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi + iw) * x_rs + x_co + cv * 8);
           const uint32_t t2 = inb ? ((uint32_t)tap | ((uint32_t)tap << 16)) : 0x00ff00ffu;
           const uint32_t rv[4] = {raw.x, raw.y, raw.z, raw.w};
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_f32_kernel(const float* __
       bidx[j] = 0xffu;
     }
     int tap = 0;
+    bool seen_pad = false;
     for (int a = 0; a < G.kt; ++a) {
       const int it = ot * G.st - G.pt + a;
       for (int b = 0; b < G.kh; ++b) {
@@ -416,6 +425,10 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_f32_kernel(const float* __
         for (int c = 0; c < G.kw; ++c, ++tap) {
           const int iw = ow * G.sw - G.pw + c;
           const bool inb = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi && (unsigned)iw < (unsigned)G.Wi;
+          if (!inb) {                   // only the first padding zero can win (see maxpool_fwd_kernel)
+            if (seen_pad) continue;
+            seen_pad = true;
+          }
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
