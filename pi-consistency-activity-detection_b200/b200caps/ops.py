@@ -282,7 +282,7 @@ def tail_weff(w4, b4, ws, drop_nc, packed_f, f_stride, packed_d, d_stride, d_nkb
 
 
 def tail_gather_fwd(y_planar, biasfield, bs, logits, N, It, Ih, Iw):
-    _bw("b2c_tail_gather_fwd", N * It * Ih * Iw * (216 * 4 + 8 * 4), _p(y_planar), _p(biasfield), _p(bs), _p(logits), N, It, Ih, Iw, stream())
+    _bw("b2c_tail_gather_fwd", N * It * Ih * Iw * (216 * y_planar.element_size() + 8 * 4), _p(y_planar), _p(biasfield), _p(bs), _p(logits), N, It, Ih, Iw, stream())
 
 
 def tail_gather_bwd(dlogits, dy, class_sums, N, It, Ih, Iw):

@@ -717,6 +717,18 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
                 st_shared16(my_row + ((u ^ swz) << 4), pack8(vv));
               } else if (!mvalid || col >= d.Cout) {
                 // nothing to write
+              } else if (d.out_fp32 == 3) {
+                // grouped planar: out[column / 8][position][8] in the activation precision -- one 16 / 32-byte store per
+                // lane and 8 columns, 0.5 / 1 KB contiguous per warp (the collapsed tail's GEMM output; the fp32 planar
+                // mode below wrote 128-byte pieces into 224 planes 6 MB apart and ran at a third of the HBM write rate)
+                const long long g8 = (long long)((d.out_c_off + col) >> 3);
+                if (kTF32) {
+                  float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + (g8 * d.out_row_stride + opos) * 8);
+                  o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                  o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+                } else {
+                  *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d.out) + (g8 * d.out_row_stride + opos) * 8) = pack8(vv);
+                }
               } else if (d.out_fp32 == 2) {
                 // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
                 float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
@@ -1286,7 +1298,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(d.Cin > 0 && d.Cin % 8 == 0, "conv_fprop: Cin=%d must be a positive multiple of 8", d.Cin);
   B2C_REQUIRE(d.Cout > 0 && d.Cout % 8 == 0, "conv_fprop: Cout=%d must be a positive multiple of 8", d.Cout);
   B2C_REQUIRE(d.in_c_off % 8 == 0 && d.out_c_off % 8 == 0, "conv_fprop: channel offsets must be multiples of 8");
-  B2C_REQUIRE(d.in_row_stride % 8 == 0 && (d.out_fp32 == 2 || d.out_row_stride % (d.out_fp32 ? 4 : 8) == 0),
+  B2C_REQUIRE(d.out_fp32 != 3 || (!d.accumulate && d.out_c_off % 8 == 0 && d.out_fold == 0), "conv_fprop: grouped planar output: bad flags");
+  B2C_REQUIRE(d.in_row_stride % 8 == 0 && (d.out_fp32 >= 2 || d.out_row_stride % (d.out_fp32 ? 4 : 8) == 0),
               "conv_fprop: row strides unaligned");
   B2C_REQUIRE(d.nclass >= 1 && d.nclass <= 8, "conv_fprop: nclass=%d out of range", d.nclass);
   B2C_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.out & 15) == 0, "conv_fprop: tensors must be 16B aligned");
