@@ -131,8 +131,9 @@ class PackRegistry:
                 for k, v in f.items():
                     setattr(arr[i], k, v)
                 total = f["R"] * f["ntaps"] * f["C"]
-                assert total < 2 ** 31
-                starts.append(starts[-1] + max(1, (total + 4095) // 4096))       # 16 elements per thread, every job
+                assert total < 2 ** 31 and f["C"] % 8 == 0 and f["col_off"] % 8 == 0 and f["tap_pitch"] % 8 == 0
+                tiles = f["R"] * ((f["C"] + 63) // 64) * ((f["ntaps"] + 31) // 32)     # (row, 64 K-columns, 32 taps) tiles
+                starts.append(starts[-1] + max(1, (tiles + 3) // 4))
             dev = torch.device("cuda", torch.cuda.current_device())
             raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
             bs = torch.tensor(starts, dtype=torch.int32, device=dev)

@@ -106,7 +106,9 @@ def check_against_golden(res, model, g, od, tag, BAR=BARS["bf16"]):
         if k == "cons":
             # the consistency term is a mean of squared differences between the two passes' (chaotic, see above) logits; it
             # enters `total` with weight 0.1.  Measured in tf32 mode: 0.5e-3 .. 1.9e-3 over the six configurations.
-            bound = max(3 * BAR, 5 * od["losses_rel_dev"][k])     # (gv, tf32: 0.8e-3 and 8.6e-3 in two runs of the same build)
+            # one realisation of the rounding (the oracle's emulation) does not bound another: gv, tf32, 1+1 clips measured
+            # 0.8e-3, 8.6e-3 and 1.1e-2 in three runs of the same build (fp32 atomics order) against an emulated 2.2e-3
+            bound = max(3 * BAR, 10 * od["losses_rel_dev"][k])
         report[k] = (dev, od["losses_rel_dev"][k], bound)
     act_ref = torch.tensor(g["act"], dtype=torch.float64)
     act_dev = float((res["pred_action"].double().cpu() - act_ref).abs().max() / act_ref.abs().max())

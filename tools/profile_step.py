@@ -28,7 +28,9 @@ def read_launches(path):
     for row in csv.DictReader(lines[start:]):
         if row["Metric Name"] == "gpu__time_duration.sum":
             v = float(row["Metric Value"].replace(",", ""))
-            rows.append((int(row["ID"]), row["Kernel Name"].split("(")[0], v * {"ns": 1, "us": 1e3, "ms": 1e6}.get(row["Metric Unit"], 1)))
+            # base function name: ncu's -k matches it without template arguments ("igemm_fprop_kernel<0>" -> "igemm_fprop_kernel")
+            name = row["Kernel Name"].split("(")[0].split("<")[0].replace("void ", "").strip()
+            rows.append((int(row["ID"]), name, v * {"ns": 1, "us": 1e3, "ms": 1e6}.get(row["Metric Unit"], 1)))
     return rows
 
 
