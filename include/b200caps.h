@@ -63,8 +63,7 @@ typedef struct {
   int32_t in_c_off, out_c_off, Cin, Cout;
   int32_t N, Ti, Hi, Wi, To, Ho, Wo;
   int32_t si_t, si_h, si_w, so_t, so_h, so_w;
-  int32_t out_fp32;     /* 0: bf16 rows, 1: fp32 rows, 2: fp32 planar out[c][pos] (out_row_stride = plane stride), 3: grouped planar
-                           out[c / 8][pos][8] in the activation precision (out_row_stride = positions per group plane) */
+  int32_t out_fp32;     /* 0: bf16 rows, 1: fp32 rows, 2: fp32 planar out[c][pos] (out_row_stride = plane stride) */
   int32_t relu;         /* apply ReLU */
   int32_t sigmoid_from; /* apply sigmoid to output channels >= this (PrimaryCaps 'a'), <0: none */
   int32_t accumulate;   /* out += result (gradient accumulation) */
@@ -331,15 +330,12 @@ int b2c_set_deterministic(int32_t on);
  * ---------------------------------------------------------------------------------- */
 /* composite weights in both packed operand images (fprop: rows = 224 columns, K = 128; dgrad: rows = 128, K = 224 padded to
  * the mode's tap pitch), activation-precision element type, one set per clip `*_stride` ELEMENTS apart (buffers zeroed once by
- * the caller: padding is never written); biasfield[n][27] (border class (t,h,w), 0 = first plane, 1 = interior, 2 = last).
- * The fprop image has 288 rows in GROUPED order (row = pair * 8 + cw, pair = ct * 6 + ch; two N tiles of 144), the dgrad
- * image 224 K-columns in plain order (column = pair * 6 + cw). */
+ * the caller: padding is never written); biasfield[n][27] (border class (t,h,w), 0 = first plane, 1 = interior, 2 = last). */
 int b2c_tail_weff(const float* w4, const float* b4, const float* ws, const float* drop_nc, void* packed_fprop,
                   int64_t fprop_stride, void* packed_dgrad, int64_t dgrad_stride, int32_t dgrad_nkb, float* biasfield, int32_t N,
                   b2c_stream_t s);
-/* logits (N,2It,2Ih,2Iw) from the GEMM output in grouped planar layout Y[36 (ct,ch) pairs][N*It*Ih*Iw][8] (activation
- * precision; the 6 per-dimension columns cw of a pair in slots 0..5) */
-int b2c_tail_gather_fwd(const void* y_grouped, const float* biasfield, const float* bs, float* logits, int32_t N, int32_t It,
+/* logits (N,2It,2Ih,2Iw) from the planar GEMM output Y[224][N*It*Ih*Iw] */
+int b2c_tail_gather_fwd(const float* y_planar, const float* biasfield, const float* bs, float* logits, int32_t N, int32_t It,
                         int32_t Ih, int32_t Iw, b2c_stream_t s);
 /* dY rows (N*It*Ih*Iw, 224) in the activation precision from dlogits; also sums[n][27] += per-border-class sums of dlogits
  * (sums zeroed by the caller) */

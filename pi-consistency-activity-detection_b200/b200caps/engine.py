@@ -1021,7 +1021,7 @@ class CollapsedTail:
     128 -> 1 (include/b200caps.h "Collapsed decoder tail"): composite weights per clip (they contain the
     clip's Dropout3d mask), a 1x1x1 GEMM x -> 216 composite columns, and a stride-2 gather.  The (N,128,8,224,224)
     tensor is never formed; executed MACs drop from 23.6 G to ~1.4 G per clip-pass."""
-    COLS, COLS_PAD, COLS_F = 216, 224, 288
+    COLS, COLS_PAD = 216, 224
 
     def __init__(self, up4: torch.nn.Module, smooth: torch.nn.Module):
         self.up4, self.smooth = up4, smooth
@@ -1037,11 +1037,8 @@ class CollapsedTail:
             pl = ConvPlan(ConvSpec(128, self.COLS, (1, 1, 1), Cout_pad=self.COLS_PAD), dims)
             # per-clip gradient dWeff[n][ci][224]
             pl.wgrad_geom = dict(pl.wgrad_geom, s_p=1, s_g=self.COLS_PAD)
+            pl.geo_f = packed_geometry(self.COLS_PAD, 128)                       # (bn, nt, nkb, elems)
             pl.geo_d = packed_geometry(128, tap_pitch(self.COLS_PAD))
-            # forward GEMM: 36 (ct, ch) pairs x 8 slots = 288 GROUPED columns, written as Y[pair][position][8]
-            plf = ConvPlan(ConvSpec(128, self.COLS_F, (1, 1, 1), Cout_pad=self.COLS_F), dims)
-            pl.geo_f = packed_geometry(self.COLS_F, 128)                         # (bn, nt, nkb, elems)
-            pl.fwd = plf.to(self.up4.weight.device)
             self.plans[key] = pl
         return pl.to(self.up4.weight.device)
 
@@ -1062,8 +1059,8 @@ class CollapsedTail:
                       b["d"], pl.geo_d[3], pl.geo_d[2], b["bias"], nset)
         esz = b["f"].element_size()
         per_clip = drop is not None
-        pl.fwd.fprop[0].packed, pl.dgrad[0].packed = b["f"], b["d"]
-        pl.fwd.fprop_pack = dict(pl.fwd.fprop_pack, sample_stride_bytes=pl.geo_f[3] * esz if per_clip else 0)
+        pl.fprop[0].packed, pl.dgrad[0].packed = b["f"], b["d"]
+        pl.fprop_pack = dict(pl.fprop_pack, sample_stride_bytes=pl.geo_f[3] * esz if per_clip else 0)
         pl.dgrad_pack = dict(pl.dgrad_pack, sample_stride_bytes=pl.geo_d[3] * esz if per_clip else 0)
         return b, dr
 
@@ -1075,8 +1072,8 @@ class CollapsedTail:
         b, dr = self._weights(pl, drop, N)
         dev = x.t.device
         rows = N * It * Ih * Iw
-        Y = torch.empty((self.COLS_F // 8, rows, 8), dtype=act_dtype(), device=dev)
-        ops.conv_fprop(pl.fwd, "fprop", x, Y)
+        Y = torch.empty((self.COLS_PAD, rows), dtype=torch.float32, device=dev)
+        ops.conv_fprop(pl, "fprop", x, Y)
         logits = torch.empty((N, 1, 2 * It, 2 * Ih, 2 * Iw), dtype=torch.float32, device=dev)
         bf = b["bias"] if drop is not None else b["bias"].expand(N, 27).contiguous()
         ops.tail_gather_fwd(Y, bf, self.smooth.bias.detach(), logits, N, It, Ih, Iw)

@@ -131,9 +131,8 @@ class PackRegistry:
                 for k, v in f.items():
                     setattr(arr[i], k, v)
                 total = f["R"] * f["ntaps"] * f["C"]
-                assert total < 2 ** 31 and f["C"] % 8 == 0 and f["col_off"] % 8 == 0 and f["tap_pitch"] % 8 == 0
-                tiles = f["R"] * ((f["C"] + 63) // 64) * ((f["ntaps"] + 31) // 32)     # (row, 64 K-columns, 32 taps) tiles
-                starts.append(starts[-1] + max(1, (tiles + 3) // 4))
+                assert total < 2 ** 31
+                starts.append(starts[-1] + max(1, (total + 4095) // 4096))       # 16 elements per thread, every job
             dev = torch.device("cuda", torch.cuda.current_device())
             raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
             bs = torch.tensor(starts, dtype=torch.int32, device=dev)
@@ -283,7 +282,7 @@ def tail_weff(w4, b4, ws, drop_nc, packed_f, f_stride, packed_d, d_stride, d_nkb
 
 
 def tail_gather_fwd(y_planar, biasfield, bs, logits, N, It, Ih, Iw):
-    _bw("b2c_tail_gather_fwd", N * It * Ih * Iw * (216 * y_planar.element_size() + 8 * 4), _p(y_planar), _p(biasfield), _p(bs), _p(logits), N, It, Ih, Iw, stream())
+    _bw("b2c_tail_gather_fwd", N * It * Ih * Iw * (216 * 4 + 8 * 4), _p(y_planar), _p(biasfield), _p(bs), _p(logits), N, It, Ih, Iw, stream())
 
 
 def tail_gather_bwd(dlogits, dy, class_sums, N, It, Ih, Iw):

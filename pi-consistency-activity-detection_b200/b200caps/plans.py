@@ -377,11 +377,6 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
         d.out, d.out_row_stride, d.out_c_off = out.ptr, out.row_stride, out.c_off
         d.out_fp32 = 1 if out.t.dtype == torch.float32 else 0
         d.round_out = 1 if (PREC.mode and not final) else 0
-    elif out.dim() == 3:   # grouped planar (Cout_pad / 8, rows, 8) in the activation precision
-        rows = x.N * exp_out[0] * exp_out[1] * exp_out[2]
-        assert out.dtype == act_dtype() and out.is_contiguous() and tuple(out.shape) == (pk["R_pad"] // 8, rows, 8)
-        d.out, d.out_row_stride, d.out_c_off = out.data_ptr(), rows, 0
-        d.out_fp32 = 3
     else:   # planar fp32 (Cout_pad, rows)
         rows = x.N * exp_out[0] * exp_out[1] * exp_out[2]
         assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (pk["R_pad"], rows)

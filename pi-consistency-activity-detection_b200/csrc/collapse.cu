@@ -18,7 +18,6 @@ namespace {
 
 constexpr int kC = 128;          // channels of upsample4's input and output
 constexpr int kTailCols = 224;   // 216 composite columns padded to a multiple of 16 (UMMA N) / 32 (tf32 K-block)
-constexpr int kTailFTile = 144;  // forward GEMM: 36 pairs x 8 slots = 288 grouped columns = two N tiles of 144
 
 // (k, m) pairs of a per-dimension column, encoded k * 3 + m; count in the last slot
 __device__ __constant__ int8_t kPairs[6][4] = {
@@ -76,10 +75,8 @@ __global__ void __launch_bounds__(256) tail_weff_kernel(const float* __restrict_
           acc += T[k * 27 + m];
         }
     using E = typename std::conditional<kTF32, float, bf16>::type;
-    // fprop image: GEMM row = grouped column (pair * 8 + cw), K = ci (two 144-row N tiles, K = 128)
-    const int grow = (tid / 6) * 8 + tid % 6;
-    pack_store<kTF32>(reinterpret_cast<E*>(pf) + (size_t)n * f_stride, 0, grow % kTailFTile, ci, acc, kTailFTile, kC / (kTF32 ? 32 : 64),
-                      grow / kTailFTile);
+    // fprop image: GEMM row = column, K = ci (one 224-row N tile, K = 128)
+    pack_store<kTF32>(reinterpret_cast<E*>(pf) + (size_t)n * f_stride, 0, tid, ci, acc, kTailCols, kC / (kTF32 ? 32 : 64), 0);
     // dgrad image: GEMM row = ci, K = column (one 128-row N tile)
     pack_store<kTF32>(reinterpret_cast<E*>(pd) + (size_t)n * d_stride, 0, ci, tid, acc, kC, d_nkb, 0);
   }
@@ -118,22 +115,10 @@ __device__ __forceinline__ Cand cands(int o, int I) {
 __device__ __forceinline__ int border_class(int o, int O) { return o == 0 ? 0 : (o == O - 1 ? 2 : 1); }
 
 // ------------------------------------------------------------------------------------------------------------------
-// logits[n][ot][oh][2q], [2q+1] from the GEMM output in grouped planar layout Y[pair][position][8] (pair = ct * 6 + ch,
-// slots 0..5 = the per-dimension columns cw).  One thread per (n, ot, oh, q): per (it, ih) candidate three 8-wide vector
-// loads (positions q - 1, q, q + 1 of one pair plane), every element of Y is read once from DRAM.
+// logits[n][ot][oh][2q], [2q+1] from the planar GEMM output.  One thread per (n, ot, oh, q): all loads of a warp are
+// consecutive floats of one plane (coalesced), every element of Y is read exactly once.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void ld8_y(const T* p, float* v);
-template <>
-__device__ __forceinline__ void ld8_y<bf16>(const bf16* p, float* v) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
-template <>
-__device__ __forceinline__ void ld8_y<float>(const float* p, float* v) {
-  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(128) tail_gather_fwd_kernel(const T* __restrict__ y, const float* __restrict__ biasfield,
+__global__ void __launch_bounds__(128) tail_gather_fwd_kernel(const float* __restrict__ y, const float* __restrict__ biasfield,
                                                               const float* __restrict__ bs, float* __restrict__ logits, int N,
                                                               int It, int Ih, int Iw) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,21 +129,15 @@ __global__ void __launch_bounds__(128) tail_gather_fwd_kernel(const T* __restric
   float a0 = 0.f, a1 = 0.f;
   for (int a = 0; a < ct.n; ++a)
     for (int b = 0; b < ch.n; ++b) {
-      const T* p = y + ((long long)(ct.c[a] * 6 + ch.c[b]) * rows + (((long long)n * It + ct.i[a]) * Ih + ch.i[b]) * Iw + q) * 8;
-      float v[8];
+      const float* p = y + (long long)((ct.c[a] * 6 + ch.c[b]) * 6) * rows + (((long long)n * It + ct.i[a]) * Ih + ch.i[b]) * Iw + q;
       // even output 2q: (e=0, i=q+1) (e=2 or 2', i=q) (e=4, i=q-1); odd output 2q+1: (e=1, i=q+1) (e=3, i=q)
-      ld8_y(p, v);
-      a0 += q == 0 ? v[5] : v[2];
-      a1 += v[3];
+      a0 += p[(q == 0 ? 5 : 2) * rows];
+      a1 += p[3 * rows];
       if (q + 1 < Iw) {
-        ld8_y(p + 8, v);
-        a0 += v[0];
-        a1 += v[1];
+        a0 += p[1];
+        a1 += p[rows + 1];
       }
-      if (q > 0) {
-        ld8_y(p - 8, v);
-        a0 += v[4];
-      }
+      if (q > 0) a0 += p[4 * rows - 1];
     }
   const int cb = (border_class(ot, 2 * It) * 3 + border_class(oh, 2 * Ih)) * 3;
   const float b0 = bs[0];
@@ -390,15 +369,12 @@ B2C_API int b2c_tail_weff(const float* w4, const float* b4, const float* ws, con
   return 0;
 }
 
-B2C_API int b2c_tail_gather_fwd(const void* y_grouped, const float* biasfield, const float* bs, float* logits, int32_t N, int32_t It,
+B2C_API int b2c_tail_gather_fwd(const float* y_planar, const float* biasfield, const float* bs, float* logits, int32_t N, int32_t It,
                                 int32_t Ih, int32_t Iw, b2c_stream_t s) {
-  B2C_REQUIRE(y_grouped && biasfield && bs && logits && N > 0 && It > 0 && Ih > 0 && Iw > 0, "tail_gather_fwd: bad args");
-  B2C_REQUIRE(4LL * It * Ih <= 65535 && N <= 65535, "tail_gather_fwd: too large");
+  B2C_REQUIRE(y_planar && biasfield && bs && logits && N > 0 && It > 0 && Ih > 0 && Iw > 0, "tail_gather_fwd: bad args");
+  B2C_REQUIRE((long long)N * It * Ih * Iw * kTailCols < (1LL << 40) && 4LL * It * Ih <= 65535 && N <= 65535, "tail_gather_fwd: too large");
   dim3 grid((unsigned)((Iw + 127) / 128), (unsigned)(4 * It * Ih), (unsigned)N);
-  if (b2c_precision())
-    tail_gather_fwd_kernel<float><<<grid, 128, 0, (cudaStream_t)s>>>((const float*)y_grouped, biasfield, bs, logits, N, It, Ih, Iw);
-  else
-    tail_gather_fwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)s>>>((const bf16*)y_grouped, biasfield, bs, logits, N, It, Ih, Iw);
+  tail_gather_fwd_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(y_planar, biasfield, bs, logits, N, It, Ih, Iw);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("tail_gather_fwd");
   return 0;

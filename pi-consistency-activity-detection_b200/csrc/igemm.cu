@@ -717,18 +717,6 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
                 st_shared16(my_row + ((u ^ swz) << 4), pack8(vv));
               } else if (!mvalid || col >= d.Cout) {
                 // nothing to write
-              } else if (d.out_fp32 == 3) {
-                // grouped planar: out[column / 8][position][8] in the activation precision -- one 16 / 32-byte store per
-                // lane and 8 columns, 0.5 / 1 KB contiguous per warp (the collapsed tail's GEMM output; the fp32 planar
-                // mode below wrote 128-byte pieces into 224 planes 6 MB apart and ran at a third of the HBM write rate)
-                const long long g8 = (long long)((d.out_c_off + col) >> 3);
-                if (kTF32) {
-                  float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + (g8 * d.out_row_stride + opos) * 8);
-                  o4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                  o4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
-                } else {
-                  *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d.out) + (g8 * d.out_row_stride + opos) * 8) = pack8(vv);
-                }
               } else if (d.out_fp32 == 2) {
                 // planar fp32: out[channel][position]; consecutive lanes = consecutive positions -> coalesced
                 float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + col) * d.out_row_stride + opos;
@@ -1240,15 +1228,7 @@ int encode_out_map(CUtensorMap* map, const bf16* base, int rank, const cuuint64_
 
 // All weight re-packing of a step in ONE launch: a device table of jobs (stable pointers: flat parameter buffer
 // views -> persistent packed operand buffers); block -> job through a prefix table.
-// Tiled through shared memory so that BOTH sides are coalesced (r02: the element-per-thread version read the fp32
-// weights with a stride of `taps` floats and wrote single 2-byte elements, 0.43 ms per step at 1.3 TB/s): a tile is one
-// GEMM row r x 64 K-columns c x 32 taps; it is read tap-fastest (w[r][c][t..] is contiguous for conv weights, a 128-byte
-// run per c for the transposed / dgrad views) and written as 16-byte chunks of 8 consecutive c per tap into the swizzled
-// operand image.
-constexpr int kPackC = 64, kPackT = 32;
-__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const b2c_pack_job* __restrict__ jobs, const int* __restrict__ block_start,
-                                                                   int njobs) {
-  __shared__ float tile[kPackT][kPackC + 1];
+__global__ void pack_weights_batched_kernel(const b2c_pack_job* __restrict__ jobs, const int* __restrict__ block_start, int njobs) {
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {                 // last job whose first block <= blockIdx.x
     const int mid = (lo + hi + 1) >> 1;
@@ -1259,47 +1239,21 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const b2c_pac
   const int nblk = block_start[lo + 1] - block_start[lo];
   const int bidx = blockIdx.x - block_start[lo];
   const float* __restrict__ w = reinterpret_cast<const float*>(J.w);
+  void* __restrict__ packed = J.packed;
   const int32_t* __restrict__ wtap = J.wtap;
-  const int CB = (J.C + kPackC - 1) / kPackC, TB = (J.ntaps + kPackT - 1) / kPackT;
-  const long long ntiles = (long long)J.R * CB * TB;
-  const int tid = threadIdx.x;
-  for (long long tl = bidx; tl < ntiles; tl += nblk) {
-    const int tb = (int)(tl % TB);
-    const long long rc = tl / TB;
-    const int cbk = (int)(rc % CB), r = (int)(rc / CB);
-    const int c0 = cbk * kPackC, t0 = tb * kPackT;
-    const int cw = J.C - c0 < kPackC ? J.C - c0 : kPackC;          // multiple of 8
-    const int tw = J.ntaps - t0 < kPackT ? J.ntaps - t0 : kPackT;
-    __syncthreads();
-    for (int e = tid; e < cw * tw; e += 256) {
-      const int cl = e / tw, t = e - cl * tw;
-      float v = 0.f;
-      if (c0 + cl < J.C_real) v = __ldg(w + (long long)r * J.s_r + (long long)(c0 + cl) * J.s_c + wtap[t0 + t]);
-      tile[t][cl] = v;
-    }
-    __syncthreads();
-    const int rg = r + J.r_off;
-    const int tn = rg / J.bn_tile, rr = rg - tn * J.bn_tile;
-    const int chunks = cw >> 3;
-    for (int e = tid; e < tw * chunks; e += 256) {
-      const int t = e / chunks, ch = e - t * chunks;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tile[t][ch * 8 + j];
-      const long long k = (long long)(t0 + t) * J.tap_pitch + J.col_off + c0 + ch * 8;      // multiple of 8
-      if (J.dtype) {
-        float* base = reinterpret_cast<float*>(J.packed) + ((long long)tn * J.nkb + (k >> 5)) * ((long long)J.bn_tile * 32) +
-                      (rr >> 3) * 256 + (rr & 7) * 32;
-        const int kk = (int)(k & 31);
-        *reinterpret_cast<float4*>(base + ((((kk >> 2)) ^ (rr & 7)) << 2)) = make_float4(tf32_rna(v[0]), tf32_rna(v[1]), tf32_rna(v[2]), tf32_rna(v[3]));
-        *reinterpret_cast<float4*>(base + ((((kk >> 2) + 1) ^ (rr & 7)) << 2)) = make_float4(tf32_rna(v[4]), tf32_rna(v[5]), tf32_rna(v[6]), tf32_rna(v[7]));
-      } else {
-        bf16* base = reinterpret_cast<bf16*>(J.packed) + ((long long)tn * J.nkb + (k >> 6)) * ((long long)J.bn_tile * 64) +
-                     (rr >> 3) * 512 + (rr & 7) * 64;
-        const int kk = (int)(k & 63);
-        *reinterpret_cast<uint4*>(base + (((kk >> 3) ^ (rr & 7)) << 3)) = pack8(v);
-      }
-    }
+  // (host guarantees R * ntaps * C < 2^31: 32-bit index arithmetic)
+  const unsigned total = (unsigned)J.R * (unsigned)J.ntaps * (unsigned)J.C;
+  const unsigned C = (unsigned)J.C, ntaps = (unsigned)J.ntaps, bn = (unsigned)J.bn_tile;
+  for (unsigned i = (unsigned)bidx * blockDim.x + threadIdx.x; i < total; i += (unsigned)nblk * blockDim.x) {
+    const unsigned t2 = i / C, c = i - t2 * C;
+    const unsigned r = t2 / ntaps, t = t2 - r * ntaps;
+    float v = 0.f;
+    if ((int)c < J.C_real) v = __ldg(w + (long long)r * J.s_r + (long long)c * J.s_c + wtap[t]);
+    const unsigned rg = r + (unsigned)J.r_off;
+    const unsigned tile = rg / bn, rr = rg - tile * bn;
+    const long long k = (long long)t * J.tap_pitch + J.col_off + c;
+    if (J.dtype) pack_store<true>(packed, 0, (int)rr, k, v, J.bn_tile, J.nkb, (int)tile);
+    else pack_store<false>(packed, 0, (int)rr, k, v, J.bn_tile, J.nkb, (int)tile);
   }
 }
 
@@ -1332,8 +1286,7 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(d.Cin > 0 && d.Cin % 8 == 0, "conv_fprop: Cin=%d must be a positive multiple of 8", d.Cin);
   B2C_REQUIRE(d.Cout > 0 && d.Cout % 8 == 0, "conv_fprop: Cout=%d must be a positive multiple of 8", d.Cout);
   B2C_REQUIRE(d.in_c_off % 8 == 0 && d.out_c_off % 8 == 0, "conv_fprop: channel offsets must be multiples of 8");
-  B2C_REQUIRE(d.out_fp32 != 3 || (!d.accumulate && d.out_c_off % 8 == 0 && d.out_fold == 0), "conv_fprop: grouped planar output: bad flags");
-  B2C_REQUIRE(d.in_row_stride % 8 == 0 && (d.out_fp32 >= 2 || d.out_row_stride % (d.out_fp32 ? 4 : 8) == 0),
+  B2C_REQUIRE(d.in_row_stride % 8 == 0 && (d.out_fp32 == 2 || d.out_row_stride % (d.out_fp32 ? 4 : 8) == 0),
               "conv_fprop: row strides unaligned");
   B2C_REQUIRE(d.nclass >= 1 && d.nclass <= 8, "conv_fprop: nclass=%d out of range", d.nclass);
   B2C_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.out & 15) == 0, "conv_fprop: tensors must be 16B aligned");

@@ -625,7 +625,9 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
         M[h] = s_caps[i * 16 + h];
         Wr[h] = sW[(i * 16 + h) * 32 + lane];
       }
-      float mine = 0.f;
+      // dM_i[r][kk] = sum_j (gV_ij W_ij^T)[r][kk]: 16 sums over the 32 lanes by recursive halving (16 shuffles instead of
+      // 16 x 5): after the five steps lanes 2m and 2m+1 both hold element m
+      float P[16];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -633,10 +635,22 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
           float g = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) g = fmaf(gV[k][r * 4 + c], Wr[kk * 4 + c], g);
-          g = warp_sum(active ? g : 0.f);
-          if (lane == r * 4 + kk) mine = g;
+          P[r * 4 + kk] = active ? g : 0.f;
         }
-      if (lane < 16) dcaps[loc * 544 + i * 16 + lane] = mine;
+#pragma unroll
+      for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool hi = (lane & bit) != 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q < half) {
+            const float send = hi ? P[q] : P[q + half];
+            const float keep = hi ? P[q + half] : P[q];
+            P[q] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+      }
+      P[0] += __shfl_xor_sync(0xffffffffu, P[0], 1);
+      if ((lane & 1) == 0) dcaps[loc * 544 + i * 16 + (lane >> 1)] = P[0];
       if (lane == 0) dcaps[loc * 544 + 512 + i] = gain[k];
       if (active) {
 #pragma unroll
