@@ -29,7 +29,7 @@ def read_launches(path):
         if row["Metric Name"] == "gpu__time_duration.sum":
             v = float(row["Metric Value"].replace(",", ""))
             # base function name: ncu's -k matches it without template arguments ("igemm_fprop_kernel<0>" -> "igemm_fprop_kernel")
-            name = row["Kernel Name"].split("(")[0].split("<")[0].replace("void ", "").strip()
+            name = row["Kernel Name"].split("(")[0].replace("void ", "").replace("<unnamed>::", "").split("<")[0].strip()
             rows.append((int(row["ID"]), name, v * {"ns": 1, "us": 1e3, "ms": 1e6}.get(row["Metric Unit"], 1)))
     return rows
 
