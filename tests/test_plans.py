@@ -104,3 +104,58 @@ def test_fastdiv_formula_matches_integer_division():
         ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 31) - d] + [rng.randrange(0, 1 << 31) for _ in range(200)]
         for n in ns:
             assert fdiv(n, p) == n // d, (n, d)
+
+
+def test_padding_only_taps_are_pruned_exactly():
+    """plans._prune_padding_taps drops exactly the taps that read padding for EVERY output position (brute force)."""
+    from b200caps.plans import ConvPlan, ConvSpec, same_pad
+    cases = [
+        (ConvSpec(160, 320, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1)), (1, 28, 28)),          # Mixed_4f.b1b: one frame
+        (ConvSpec(96, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1)), (2, 28, 28)),           # two frames: nothing to prune
+        (ConvSpec(128, 64, (3, 3, 3), (2, 2, 2), (1, 1, 1), (0, 0, 0), (1, 1, 1), True), (1, 28, 28)),   # upsample2
+        (ConvSpec(832, 544, (1, 9, 9)), (1, 28, 28)),                                            # PrimaryCaps
+    ]
+    for spec, dims in cases:
+        pl = ConvPlan(spec, dims)
+        for classes, si, idims in ((pl.fprop, pl.fprop_si, pl.in_dims), (pl.dgrad, pl.dgrad_si, pl.out_dims)):
+            for cl in classes:
+                for tap in cl.taps:      # every kept tap touches real data somewhere
+                    assert all(any(0 <= q * s + d < I for q in range(Q)) for d, s, I, Q in zip(tap, si, idims, cl.Q)), (spec, tap)
+    one = ConvPlan(cases[0][0], cases[0][1])
+    assert len(one.fprop[0].taps) == 9 and all(t[0] == 0 for t in one.fprop[0].taps)
+    assert len(ConvPlan(cases[1][0], cases[1][1]).fprop[0].taps) == 27
+    up2 = ConvPlan(cases[2][0], cases[2][1])
+    assert [len(c.taps) for c in up2.fprop] == [1, 2, 2, 4, 1, 2, 2, 4] and len(up2.dgrad[0].taps) == 18
+    # the weight-tap offsets stay aligned with the taps
+    for cl in one.fprop:
+        assert len(cl.wtap) == len(cl.taps) and cl.wtap == [9 + i for i in range(9)]
+
+
+def test_h_block_detection():
+    import os
+    from b200caps.plans import ConvPlan, ConvSpec, h_block_of
+    os.environ["B2C_TAP_SKIP"] = "1"
+    try:
+        pc = ConvPlan(ConvSpec(832, 544, (1, 9, 9)), (1, 28, 28))
+        assert h_block_of(pc.dgrad[0].taps) == 9 and h_block_of(pc.fprop[0].taps) == 9
+        c3 = ConvPlan(ConvSpec(96, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1)), (2, 28, 28))
+        assert h_block_of(c3.fprop[0].taps) == 0          # several dt values: no single-frame block structure
+    finally:
+        os.environ.pop("B2C_TAP_SKIP")
+    assert h_block_of(pc.dgrad[0].taps) == 0               # off by default
+
+
+def test_folded_stem_plan_geometry():
+    """engine.StemLayer.fold_plan: 2-D 7x7 stride-2 convolution over 64 folded channels, 4 x 64 output columns."""
+    import torch
+    from b200caps.engine import StemLayer
+    w = torch.nn.Parameter(torch.zeros(64, 3, 7, 7, 7))
+    st = StemLayer(w, 3, 64, (7, 7, 7), (2, 2, 2))
+    assert st.use_fold((8, 224, 224)) and st.use_fold((8, 64, 64))
+    assert not st.use_fold((32, 224, 224))                  # more padded frames than the 16 the fold holds
+    od, pf = st.geometry((8, 224, 224))
+    assert od == (4, 112, 112) and pf == (2, 2, 2)
+    pl = st.fold_plan((8, 224, 224))
+    assert pl.in_dims == (1, 224, 224) and pl.out_dims == (4, 112, 112) and len(pl.fprop) == 1 and len(pl.fprop[0].taps) == 49
+    assert pl.fprop_pack["R"] == 256 and pl.fprop_pack["out_fold"] == 64 and pl.wgrad_geom["p_fold"] == 64
+    assert pl.fprop[0].wtap == [i * 64 for i in range(49)]
