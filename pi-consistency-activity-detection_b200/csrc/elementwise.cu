@@ -468,18 +468,18 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const T* __restrict
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int a = 0; a < G.kt; ++a) {
-      const int nt = it + G.pt - a;
-      int ot;
-      if (nt < 0 || !pool_div(nt, G.st, ot) || ot >= G.To) continue;
-      for (int b = 0; b < G.kh; ++b) {
-        const int nh = ih + G.ph - b;
-        int oh;
-        if (nh < 0 || !pool_div(nh, G.sh, oh) || oh >= G.Ho) continue;
-        for (int c = 0; c < G.kw; ++c) {
-          const int nw = iw + G.pw - c;
-          int ow;
-          if (nw < 0 || !pool_div(nw, G.sw, ow) || ow >= G.Wo) continue;
+    // walk the output windows that contain this input position (per dimension o in [ceil((i + p - k + 1) / s),
+    // floor((i + p) / s)] clipped to the output), not all k^3 taps: a stride-2 3x3 pool has at most 2 x 2 of them, and the
+    // tap-loop version spent its time rejecting the others (ncu r02b: 0.28 ms at 73 % issue-slot utilisation)
+    const int ot_hi = min((it + G.pt) / G.st, G.To - 1), ot_lo = max((it + G.pt - G.kt + G.st) / G.st, 0);
+    const int oh_hi = min((ih + G.ph) / G.sh, G.Ho - 1), oh_lo = max((ih + G.ph - G.kh + G.sh) / G.sh, 0);
+    const int ow_hi = min((iw + G.pw) / G.sw, G.Wo - 1), ow_lo = max((iw + G.pw - G.kw + G.sw) / G.sw, 0);
+    for (int ot = ot_lo; ot <= ot_hi; ++ot) {
+      const int a = it + G.pt - ot * G.st;
+      for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+        const int b = ih + G.ph - oh * G.sh;
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+          const int c = iw + G.pw - ow * G.sw;
           const int tap = (a * G.kh + b) * G.kw + c;
           const long long orow = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo + ow;
           const uint2 pk = *reinterpret_cast<const uint2*>(idx + orow * G.C + cv * 8);

@@ -93,7 +93,7 @@ def full_summary(tag):
 
 def traffic_summary(tag):
     """gpurun_out/dram_<tag>.csv: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:igemm` over the
-    conv launches of ONE step -> profiles/r01_traffic.json (read by bench.py for roofline.traffic)."""
+    conv launches of ONE step -> profiles/<round>_traffic.json (read by bench.py for roofline.traffic)."""
     import json
     path = os.path.join(ROOT, "gpurun_out", f"dram_{tag}.csv")
     if not os.path.isfile(path):
@@ -112,7 +112,7 @@ def traffic_summary(tag):
     out = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:igemm (one step, {len(ids)} launches), "
                      f"gpurun_out/dram_{tag}.csv", "clips_per_gpu": 16, "launches": len(ids), "igemm_dram_bytes_per_step": tot,
            "largest_launches_bytes": sorted(per.values(), reverse=True)[:8]}
-    json.dump(out, open(os.path.join(OUT, "r01_traffic.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(OUT, f"{tag[:3]}_traffic.json"), "w"), indent=1)      # r02b -> r02_traffic.json
     print(out)
 
 
