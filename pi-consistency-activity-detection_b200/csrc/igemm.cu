@@ -582,7 +582,6 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
     const float relu_lo = d.relu ? 0.f : __int_as_float(0xff800000);     // -inf: max.NaN(x, -inf) = x
     // global (not smem-resident) dropout scale rows also work with the fast body: it only dereferences the pointer
     const bool fast = staged && d.sigmoid_from < 0;
-    const bool planar_fast = d.out_fp32 == 2 && !d.bias && !d.scale_nc && !d.relu && d.sigmoid_from < 0 && !d.accumulate;
     const int sig_from = d.sigmoid_from >= 0 ? d.sigmoid_from : 0x7fffffff;
     const int n_issue = store_mode == 2 ? 32 / piece : 1;
     const int acc = half;
@@ -662,30 +661,6 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&ps->tempty[acc]);
-            }
-          } else if (planar_fast) {
-            // fp32 planar output without bias / scale / activation (the collapsed tail's x . Weff): TMEM -> 32 coalesced
-            // column stores, nothing else.  (ncu r02b: through the generic body below this launch executed 14.7 K warp
-            // instructions per 128 x 224 tile -- 3.7 K per epilogue warp -- and ran latency bound at 0.70 ms.)
-            for (int c0 = ch0; c0 < ch0 + cw; c0 += 32) {
-              uint32_t r[32];
-              const bool wide = ch0 + cw - c0 >= 32;
-              if (wide) tmem_ld32_issue(t_lane + (uint32_t)c0, r);
-              else tmem_ld16_issue(t_lane + (uint32_t)c0, r);
-              if (wide) tmem_ld_fence(r);
-              else tmem_ld_fence16(r);
-              if (last_j && c0 + 32 >= bn16) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ps->tempty[acc]);
-              }
-              if (mvalid) {
-                float* o = reinterpret_cast<float*>(d.out) + (long long)(d.out_c_off + n0 + c0) * d.out_row_stride + opos;
-                const int nc = d.Cout - (n0 + c0) < (wide ? 32 : 16) ? d.Cout - (n0 + c0) : (wide ? 32 : 16);
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < nc) o[(long long)i * d.out_row_stride] = __uint_as_float(r[i]);
-              }
             }
           } else
           for (int c0 = ch0; c0 < ch0 + cw; c0 += 32) {
