@@ -340,9 +340,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         recs, ops.TIMING = ops.TIMING, None
         bw, ops.BW_TIMING = ops.BW_TIMING, None
-        t_ms = sum(a.elapsed_time(b) for _, a, b, _ in recs)
+        t_ms = sum(a.elapsed_time(b) for _, a, b, _, _ in recs)
         flop_alg = FLOP_PER_CLIP * P * (11.40 / 11.42 if args.classes == 21 else 1.0)
-        flop_exec = 2.0 * sum(m for _, _, _, m in recs)
+        flop_exec = 2.0 * sum(m for _, _, _, m, _ in recs)
+        bytes_alg = sum(nb for _, _, _, _, nb in recs)
         achieved = flop_alg / (t_ms / 1e3) / 1e12
         # DRAM traffic of the same launches from the committed ncu pass (profiles/r0N_traffic.json, written by
         # tools/summarize_profiles.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`): per launch, like
@@ -371,6 +372,10 @@ def run_ours(args):
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, mean over the step's conv launches)",
                     "algorithmic_flop_per_launch": flop_alg / max(1, len(recs)),
+                    # compulsory bytes of the same launches as they are executed (operands and results once each) next to the
+                    # ncu DRAM traffic above: their ratio is the re-read overhead
+                    "algorithmic_bytes_per_launch": bytes_alg / max(1, len(recs)),
+                    "traffic_over_algorithmic": (traffic / (bytes_alg / max(1, len(recs)))) if traffic else None,
                     "longest_launch": {"layer": top[0], "ms": top[1].elapsed_time(top[2])} if top else None,
                     "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (all conv / transposed-conv launches)",
                     "kernel_ms_per_step": t_ms, "kernel_launches_per_step": len(recs),
@@ -389,7 +394,7 @@ def run_ours(args):
         if world == 1:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             agg, kinds = {}, {}
-            for tag, a, b, _ in recs:
+            for tag, a, b, _, _ in recs:
                 d = agg.setdefault(tag, [0, 0.0])
                 d[0] += 1
                 d[1] += a.elapsed_time(b)

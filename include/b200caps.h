@@ -168,6 +168,10 @@ int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, int32_t C,
  *   _unfold_wgrad: dw += the adjoint of _fold_weights applied to dw2 */
 int b2c_stem_fold_input(const void* x, void* xs, int32_t N, int32_t T, int32_t H, int32_t W, int32_t Cs, int32_t pt, int32_t Tp,
                         b2c_stream_t s);
+/* the fused step's input path: clips (P,C,T,H,W) fp32 (in_u8 = 0) or uint8 (in_u8 = 1: / 255) straight into the folded
+ * layout xs (N',H,W,Tp*4); mirror = 1 also writes the W-mirrored clip (the reference's aug_data) at batch offset P */
+int b2c_clips_to_folded(const void* in, int32_t in_u8, void* xs, int32_t P, int32_t C, int32_t T, int32_t H, int32_t W, int32_t pt,
+                        int32_t Tp, int32_t mirror, b2c_stream_t s);
 int b2c_stem_fold_weights(const float* w, float* w2, int32_t Cout, int32_t Cin, int32_t kt, int32_t khw, int32_t st, int32_t To,
                           int32_t Kf, b2c_stream_t s);
 int b2c_stem_unfold_wgrad(const float* dw2, float* dw, int32_t Cout, int32_t Cin, int32_t kt, int32_t khw, int32_t st, int32_t To,

@@ -94,6 +94,7 @@ _SIGS = {
     "b2c_set_deterministic": [i32],
     "b2c_set_precision": [i32],
     "b2c_stem_fold_input": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "b2c_clips_to_folded": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_stem_fold_weights": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_stem_unfold_wgrad": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_frame_iou_counts": [vp, vp, vp, i64, i32, vp],

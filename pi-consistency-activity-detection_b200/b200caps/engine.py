@@ -400,22 +400,25 @@ class UnitSaved:
     __slots__ = ("raw", "mean", "rstd", "groups", "dims", "col")
 
 
-def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: bool, groups: int) -> UnitSaved:
-    """Unit3D (pytorch_i3d.py:89-120): same-pad conv (tcgen05) -> BatchNorm3d -> ReLU, written into `y`."""
+def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: bool, groups: int,
+             prefolded=None) -> UnitSaved:
+    """Unit3D (pytorch_i3d.py:89-120): same-pad conv (tcgen05) -> BatchNorm3d -> ReLU, written into `y`.
+    prefolded = (T, H, W): x is already the stem's folded input (ops.clips_to_folded) of clips with these dims."""
     col = None
-    folded = isinstance(layer, StemLayer) and layer.use_fold(x.dims)
-    orig_dims = x.dims
+    folded = prefolded is not None or (isinstance(layer, StemLayer) and layer.use_fold(x.dims))
+    orig_dims = tuple(prefolded) if prefolded is not None else x.dims
     if not training and EVAL_FOLD_BN and (folded or not isinstance(layer, StemLayer)) and ops.PACKS is None:
         # inference: conv + folded BatchNorm + ReLU in ONE kernel, written straight into the concat slot
         pl, bias = layer.packed_eval(orig_dims, gamma, beta, rm, rv)
-        if folded:
+        if folded and prefolded is None:
             x = layer.fold_input(x)
         ops.conv_fprop(pl, "fprop", x, y, bias=bias, relu=True)
         sv = UnitSaved()
         sv.raw, sv.dims, sv.col, sv.mean, sv.rstd, sv.groups = None, orig_dims, None, None, None, 1
         return sv
     if folded:
-        x = layer.fold_input(x)
+        if prefolded is None:
+            x = layer.fold_input(x)
         col = x.t
         pl = layer.packed_fold(orig_dims)
     else:
@@ -520,15 +523,16 @@ class Unit3DFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_cl, weight, gamma, beta, mod):
         layer = mod._layer
+        prefolded = getattr(ctx, "prefolded", None)       # fused step: the input is already in the stem's folded layout
         if isinstance(layer, StemLayer):
-            od, cpad = layer.geometry(tuple(x_cl.shape[1:4]))[0], layer.cout
+            od, cpad = layer.geometry(tuple(prefolded or x_cl.shape[1:4]))[0], layer.cout
         else:
             pl = layer.plan(x_cl.shape[1:4])
             od, cpad = tuple(pl.out_dims), pl.spec.Cout_pad
         y = torch.empty((x_cl.shape[0],) + od + (cpad,), dtype=act_dtype(), device=x_cl.device)
         training = mod.training
         sv = unit_fwd(layer, gamma, beta, mod.bn.running_mean, mod.bn.running_var, View(x_cl), View(y), training,
-                      STATE.bn_groups if training else 1)
+                      STATE.bn_groups if training else 1, prefolded=prefolded)
         if training and not STATE.defer_bn_counters:
             mod.bn.num_batches_tracked += STATE.bn_groups      # one per forward pass held in the batch
         ctx.mod, ctx.sv, ctx.x, ctx.y, ctx.gamma = mod, sv, x_cl, y, gamma

@@ -46,7 +46,7 @@ def _vb(v) -> int:
     return v.rows * v.C * v.t.element_size()
 
 
-def _launch(kind: str, name: str, desc, macs: int = 0):
+def _launch(kind: str, name: str, desc, macs: int = 0, nbytes: int = 0):
     if TIMING is None:
         _abi.call(name, C.byref(desc), stream())
         return
@@ -54,7 +54,15 @@ def _launch(kind: str, name: str, desc, macs: int = 0):
     a.record()
     _abi.call(name, C.byref(desc), stream())
     b.record()
-    TIMING.append((kind, a, b, macs))
+    TIMING.append((kind, a, b, macs, nbytes))
+
+
+def _conv_bytes(plan: ConvPlan, which: str, x: View, out) -> int:
+    """Compulsory bytes of a fprop / dgrad launch: the input window, the output, the packed operand -- each once."""
+    classes = plan.fprop if which == "fprop" else plan.dgrad
+    ob = (out.rows * out.C * out.t.element_size()) if isinstance(out, View) else out.numel() * out.element_size()
+    wb = sum(c.packed.numel() * c.packed.element_size() for c in classes if c.packed is not None)
+    return _vb(x) + ob + wb
 
 
 def _macs(plan: ConvPlan, which: str, n: int) -> int:
@@ -69,7 +77,8 @@ def conv_fprop(plan: ConvPlan, which: str, x: View, out, bias=None, scale_nc=Non
     """out: View (bf16 / fp32 rows) or a 2-D fp32 tensor (Cout_pad, rows) for the planar epilogue."""
     d = fill_conv_desc(plan, which, x, out, bias, scale_nc, relu, sigmoid_from, accumulate, bn_tile, final)
     _launch(f"{which} {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
-            f"{' T' if plan.spec.transposed else ''}", "b2c_conv_fprop", d, _macs(plan, which, x.N) if TIMING is not None else 0)
+            f"{' T' if plan.spec.transposed else ''}", "b2c_conv_fprop", d, _macs(plan, which, x.N) if TIMING is not None else 0,
+            _conv_bytes(plan, which, x, out) if TIMING is not None else 0)
 
 
 def split_bf16(v: View):
@@ -85,8 +94,9 @@ def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True,
                pp=(0, 0, 0), presplit=None):
     name = (f"wgrad {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
             f"{' T' if plan.spec.transposed else ''}")
-    wm = 0
+    wm = wb = 0
     if TIMING is not None:
+        wb = _vb(x) + (_vb(dy) if part is None else dy.rows * part[1] * dy.t.element_size()) + dw.numel() * 4
         cl, geo = plan.wgrad_cls, plan.wgrad_geom
         cp = part[2] if (part is not None and len(part) > 2) else (part[1] if part is not None else geo.get("Cp_real", geo["Cp"]))
         wm = x.N * geo["Q"][0] * geo["Q"][1] * geo["Q"][2] * len(cl.taps) * geo["Cg_real"] * cp
@@ -96,10 +106,10 @@ def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True,
         (xh, xl), (dh, dl) = presplit if presplit is not None else (split_bf16(x), split_bf16(dy))
         for a, b in ((xh, dh), (xh, dl), (xl, dh)):
             _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True, pp=pp),
-                    wm)
+                    wm, wb)
         return
     d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part, per_clip, pp=pp)
-    _launch(name, "b2c_conv_wgrad", d, wm)
+    _launch(name, "b2c_conv_wgrad", d, wm, wb)
 
 
 class PackRegistry:
@@ -201,6 +211,15 @@ def im2col_small(x: View, out: torch.Tensor, C, out_dims, k, s, pf, Kpad):
 def stem_fold_input(x: View, xs: torch.Tensor, pt: int, Tp: int):
     T, H, W = x.dims
     _bw("b2c_stem_fold_input", _vb(x) // 8 * 3 + xs.numel() * xs.element_size(), x.ptr, _p(xs), x.N, T, H, W, x.row_stride, pt, Tp, stream())
+
+
+def clips_to_folded(clips: torch.Tensor, xs: torch.Tensor, pt: int, Tp: int, mirror: bool):
+    """clips (P,C,T,H,W) fp32 / uint8 -> folded stem input xs (N',1,H,W,Tp*4) (rows [0,P); with mirror also [P,2P))."""
+    assert clips.is_contiguous() and clips.dim() == 5 and clips.dtype in (torch.float32, torch.uint8)
+    P, Cc, T, H, W = clips.shape
+    assert xs.is_contiguous() and xs.dtype == act_dtype() and tuple(xs.shape[1:]) == (1, H, W, Tp * 4) and xs.shape[0] >= (2 * P if mirror else P)
+    _bw("b2c_clips_to_folded", clips.numel() * clips.element_size() + (2 if mirror else 1) * P * H * W * Tp * 4 * xs.element_size(),
+        _p(clips), int(clips.dtype == torch.uint8), _p(xs), P, Cc, T, H, W, pt, Tp, int(mirror), stream())
 
 
 def stem_fold_weights(w, w2, cout, cin, kt, khw, st, To, Kf):

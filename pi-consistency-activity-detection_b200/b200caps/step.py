@@ -323,17 +323,33 @@ class TrainStep:
         tape = []   # (backward closure) in forward order
         try:
             # ---------------- forward: both passes as one batch [clips ; flipped clips] ----------------
-            x_cl = torch.empty((2 * P, data.shape[2], H, W, 8), dtype=act_dtype(), device=dev)
-            if data.dtype == torch.uint8:
-                assert fl_data is None, "uint8 input pipeline: the mirrored pass is produced on the device"
-                ops.u8_clip_to_cl(data.contiguous(), x_cl)
-            else:
-                ops.ncdhw_to_cl(data.contiguous(), 8, out=x_cl[:P])
-                ops.ncdhw_to_cl(fl_data.contiguous(), 8, out=x_cl[P:])
             i3d = model.conv1
+            Tn = data.shape[2]
+            stem = i3d.Conv3d_1a_7x7._layer
+            prefolded = None
+            if isinstance(stem, E.StemLayer) and stem.use_fold((Tn, H, W)) and data.shape[1] <= 4:
+                # clips go straight into the stem's folded layout (no channels-last copy of the input)
+                pt = stem.geometry((Tn, H, W))[1][0]
+                x_cl = torch.empty((2 * P, 1, H, W, stem.KF), dtype=act_dtype(), device=dev)
+                if data.dtype == torch.uint8:
+                    assert fl_data is None, "uint8 input pipeline: the mirrored pass is produced on the device"
+                    ops.clips_to_folded(data.contiguous(), x_cl, pt, stem.KF // 4, mirror=True)
+                else:
+                    ops.clips_to_folded(data.contiguous(), x_cl, pt, stem.KF // 4, mirror=False)
+                    ops.clips_to_folded(fl_data.contiguous(), x_cl[P:], pt, stem.KF // 4, mirror=False)
+                prefolded = (Tn, H, W)
+            else:
+                x_cl = torch.empty((2 * P, Tn, H, W, 8), dtype=act_dtype(), device=dev)
+                if data.dtype == torch.uint8:
+                    assert fl_data is None, "uint8 input pipeline: the mirrored pass is produced on the device"
+                    ops.u8_clip_to_cl(data.contiguous(), x_cl)
+                else:
+                    ops.ncdhw_to_cl(data.contiguous(), 8, out=x_cl[:P])
+                    ops.ncdhw_to_cl(fl_data.contiguous(), 8, out=x_cl[P:])
 
-            def unit(mod, x, need_dx=True):
+            def unit(mod, x, need_dx=True, prefolded=None):
                 ctx = _Ctx((need_dx, True, True, True, False))
+                ctx.prefolded = prefolded
                 y = E.Unit3DFn.forward(ctx, x, mod.conv3d.weight, mod.bn.weight, mod.bn.bias, mod)
                 return y, (lambda g, ctx=ctx: E.Unit3DFn.backward(ctx, g)[0])
 
@@ -351,7 +367,7 @@ class TrainStep:
                 y = E.InceptionFn.forward(ctx, x, mod, *params)
                 return y, (lambda g, ctx=ctx: E.InceptionFn.backward(ctx, g)[0])
 
-            y1, b_stem = unit(i3d.Conv3d_1a_7x7, x_cl, need_dx=False)          # cross112
+            y1, b_stem = unit(i3d.Conv3d_1a_7x7, x_cl, need_dx=False, prefolded=prefolded)          # cross112
             p1, b_p1 = pool(i3d.MaxPool3d_2a_3x3, y1)
             y2, b_2b = unit(i3d.Conv3d_2b_1x1, p1)
             y3, b_2c = unit(i3d.Conv3d_2c_3x3, y2)                            # cross56

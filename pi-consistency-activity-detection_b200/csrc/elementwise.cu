@@ -641,6 +641,41 @@ __global__ void __launch_bounds__(kBlock) stem_fold_input_kernel(const T* __rest
   }
 }
 
+// Clips straight into the folded stem layout (no intermediate channels-last copy): in = fp32 (P,C,T,H,W) or uint8 (then
+// / 255 and, with `mirror`, also the W-mirrored clip at batch offset P).  One thread per (n, h, pair of padded frames, w)
+// with w fastest: every load is a coalesced run of one (channel, frame) plane.
+template <typename T, typename S>
+__global__ void __launch_bounds__(kBlock) clips_to_folded_kernel(const S* __restrict__ in, T* __restrict__ xs, int P, int C, int Tn, int H,
+                                                                 int W, int pt, int Tp, int mirror, long long total) {
+  const int pairs = Tp / 2;
+  const float scale = sizeof(S) == 1 ? 1.f / 255.f : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int q = (int)(r % pairs);
+    r /= pairs;
+    const int h = (int)(r % H);
+    const long long n = r / H;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = 2 * q + j - pt;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float x = 0.f;
+        if (c < C && f >= 0 && f < Tn) {
+          const S raw = in[(((n * C + c) * Tn + f) * H + h) * W + w];
+          x = sizeof(S) == 1 ? (float)raw / 255.f : (float)raw;
+        }
+        v[j * 4 + c] = x;
+      }
+    }
+    (void)scale;
+    st8(xs + ((n * H + h) * W + w) * (Tp * 4) + q * 8, v, true);
+    if (mirror) st8(xs + (((P + n) * H + h) * W + (W - 1 - w)) * (Tp * 4) + q * 8, v, true);
+  }
+}
+
 __global__ void stem_fold_weights_kernel(const float* __restrict__ w, float* __restrict__ w2, int Cout, int Cin, int kt, int khw, int st,
                                          int To, int Kf) {
   const long long total = (long long)To * Cout * khw * Kf;
@@ -1100,6 +1135,24 @@ B2C_API int b2c_stem_fold_input(const void* x, void* xs, int32_t N, int32_t T, i
     stem_fold_input_kernel<bf16><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, (bf16*)xs, G, total);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("stem_fold_input");
+  return 0;
+}
+
+B2C_API int b2c_clips_to_folded(const void* in, int32_t in_u8, void* xs, int32_t P, int32_t C, int32_t T, int32_t H, int32_t W, int32_t pt,
+                                int32_t Tp, int32_t mirror, b2c_stream_t s) {
+  B2C_REQUIRE(in && xs && P > 0 && C > 0 && C <= 4 && T > 0 && Tp > 0 && Tp % 2 == 0 && Tp <= 16 && pt >= 0 && pt + T <= Tp,
+              "clips_to_folded: bad args");
+  const long long total = (long long)P * H * (Tp / 2) * W;
+  const int tf = b2c_precision();
+  if (in_u8) {
+    if (tf) clips_to_folded_kernel<float, uint8_t><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const uint8_t*)in, (float*)xs, P, C, T, H, W, pt, Tp, mirror, total);
+    else clips_to_folded_kernel<bf16, uint8_t><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const uint8_t*)in, (bf16*)xs, P, C, T, H, W, pt, Tp, mirror, total);
+  } else {
+    if (tf) clips_to_folded_kernel<float, float><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const float*)in, (float*)xs, P, C, T, H, W, pt, Tp, mirror, total);
+    else clips_to_folded_kernel<bf16, float><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const float*)in, (bf16*)xs, P, C, T, H, W, pt, Tp, mirror, total);
+  }
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("clips_to_folded");
   return 0;
 }
 
