@@ -247,12 +247,14 @@ int b2c_em_routing_bwd(const float* caps, const float* W, const float* beta_u, c
                        float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C, b2c_stream_t s);
 /* Training pair: the forward also saves the per-iteration routing state (assignments, normalisers, means, variances:
  * b2c_em_routing_state_floats() floats per location) and the backward reads it instead of recomputing the three EM
- * iterations.  Same results as the pair above. */
+ * iterations.  Same results as the pair above.  The backward CONSUMES the state: its first kernel overwrites the saved
+ * assignments with its per-pair coefficients and fills the rows its second kernel reads, so one forward serves one
+ * backward. */
 int64_t b2c_em_routing_state_floats(void);
 int b2c_em_routing_fwd_train(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, float* state,
                              int64_t b, int32_t C, b2c_stream_t s);
 int b2c_em_routing_bwd_state(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
-                             const float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
+                             float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
                              b2c_stream_t s);
 /* PrimaryCaps backward prologue (capsules_ucf101.py:43-49 adjoint): g, out fp32 (rows,544); dz bf16 (rows,dz_pitch>=544) =
  * g * (col >= 512 ? a(1-a) : 1); dbias[544] += column sums (first 512: pose bias, last 32: a bias). */

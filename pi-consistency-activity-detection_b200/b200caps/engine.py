@@ -877,6 +877,7 @@ class EMRoutingFn(torch.autograd.Function):
         dba, d2 = grad_buf(beta_a)
         ops.em_routing_bwd(caps, W.detach().reshape(32, C, 4, 4).contiguous(), beta_u.detach().contiguous(),
                            beta_a.detach().contiguous(), g, dcaps, dW, dbu, dba, N * h * w, C, state=getattr(ctx, "state", None))
+        ctx.state = None    # the state-based backward consumes the saved state; a second backward recomputes it
         return dcaps, (None if d0 else dW), (None if d1 else dbu), (None if d2 else dba)
 
 

@@ -320,7 +320,8 @@ def em_routing_fwd(caps, W, beta_u, beta_a, out, b, C, state=None):
     if state is None:
         _bw("b2c_em_routing_fwd", b * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out), b, C, stream())
     else:
-        _bw("b2c_em_routing_fwd_train", b * (544 + C * 17 + state.shape[1]) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out),
+        # the forward writes 8672 of the state's floats per location (assignments, normalisers, means, variances)
+        _bw("b2c_em_routing_fwd_train", b * (544 + C * 17 + 8672) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(out),
             _p(state), b, C, stream())
 
 
@@ -329,7 +330,8 @@ def em_routing_bwd(caps, W, beta_u, beta_a, dout, dcaps, dW, dbu, dba, b, C, sta
         _bw("b2c_em_routing_bwd", b * 2 * (544 + C * 17) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout), _p(dcaps), _p(dW),
             _p(dbu), _p(dba), b, C, stream())
     else:
-        _bw("b2c_em_routing_bwd_state", b * (2 * (544 + C * 17) + state.shape[1]) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout),
+        # coefficient kernel: reads what the forward saved, writes 2048 + 4128 floats; final kernel: reads the 11264-float prefix
+        _bw("b2c_em_routing_bwd_state", b * (3 * 544 + 2 * C * 17 + 8672 + 6176 + 11264) * 4, _p(caps), _p(W), _p(beta_u), _p(beta_a), _p(dout),
             _p(state), _p(dcaps), _p(dW), _p(dbu), _p(dba), b, C, stream())
 
 

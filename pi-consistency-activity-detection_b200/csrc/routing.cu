@@ -235,16 +235,24 @@ __global__ void __launch_bounds__(kRT, kNW == 8 ? 2 : 1) em_routing_fwd_kernel(c
 // =====================================================================================
 constexpr int kWL = 8;   // warps (= locations in flight) per CTA
 
-// Routing state saved by the training forward for the backward kernel (floats per location, 32-lane rows):
+// Routing state saved by the training forward for the backward kernels (floats per location, 32-lane rows):
 //   r_t[i][32] (t = 1, 2: the E-step assignments; t = 0 is the constant 1/C), rn_t[i][32] (t = 0..2), Z_t[i] (t = 0..2),
 //   per-j scalars [t][R, T, a, 1/(stdv + eps)][32], mu_t[h][32], S_t[h][32]
+// plus the rows the first backward kernel adds for the second (see em_routing_bwd_coef_kernel): it overwrites r_t with
+// gz_{t-1} and fills X'_t, G'_t (t = 0..2), U_t (t = 0, 1) and one row of per-j scalars.  Everything the second kernel
+// reads is the contiguous prefix [0, kStS).
 constexpr int kStR = 0;
 constexpr int kStRN = kStR + 2 * kB * 32;
 constexpr int kStZ = kStRN + 3 * kB * 32;
 constexpr int kStSC = kStZ + 3 * kB;
 constexpr int kStMU = kStSC + 3 * 4 * 32;
-constexpr int kStS = kStMU + 3 * 16 * 32;
-constexpr int kStFloats = kStS + 3 * 16 * 32;     // 8672 floats = 34.7 KB per location
+constexpr int kStX = kStMU + 3 * 16 * 32;
+constexpr int kStG = kStX + 3 * 16 * 32;
+constexpr int kStU = kStG + 3 * 16 * 32;
+constexpr int kStK = kStU + 2 * 16 * 32;
+constexpr int kStS = kStK + 32;
+constexpr int kStFloats = kStS + 3 * 16 * 32;     // 12800 floats = 51.2 KB per location
+static_assert(kStS == 11264 && kStFloats == 12800, "routing state layout");
 
 // warp maximum in ONE instruction: floats mapped to order-preserving unsigned keys, redux.sync.max.u32
 __device__ __forceinline__ float warp_max_redux(float v) {
@@ -680,6 +688,317 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
 }
 
 // =====================================================================================
+// Two-kernel backward on the saved state (r02d).  The CTA-per-location kernel above is latency bound (8 warps per SM,
+// seven block-wide reductions per location, every warp recomputing the per-j terms: 2.5 ms for 12 800 locations).  The
+// chain rule through the three EM iterations only couples the (i,j) pairs through per-j sums, and the sum
+// D_j = sum_i gc_ij c_ij has a closed form (sum_i c_ij (V_ij - mu_j)^2 = S_j - eps, sum_i c_ij V_ij = mu_j), so:
+//
+//  1. em_routing_bwd_coef_kernel -- ONE WARP per location (lane = output capsule j, the 32 input capsules walked
+//     sequentially with the votes recomputed, like the forward).  Walks t = 2, 1 and produces only scalars per (i,j):
+//         gz^{t-1}_ij = r^t_ij a_i (grp_ij - sum_j grp_ij r^t_ij),   grp_ij = (grn_ij - sum_j grn_ij rn^t_ij) / Z^t_i,
+//         grn_ij = (sum_h gS'_h dv^2 + gmu'_h V_h) / (R+eps) + gR_tot_j
+//     (stored over r^t in the state), the activation gradient of iterations 2 and 1, d beta, and per-j vectors
+//         X'_t = 2 gS'_t / (R_t+eps),  G'_t = gmu'_t / (R_t+eps)  (t = 2, 1, 0),   U_t = 1 / S_t  (t = 1, 0)
+//     where gS', gmu' are the M-step gradients of iteration t (tests/routing_manual.py::backward_split is this
+//     formulation in tensor ops, checked against autograd on the CPU).
+//  2. em_routing_bwd_final_kernel -- thread = one (i,j) pair for all locations of the CTA, so the weight gradient
+//     accumulates in registers.  Assembles the vote gradient of all three iterations in one pass,
+//         gV_ij = sum_t rn^t_ij (G'_t + X'_t (V_ij - mu_t)) - sum_{t<2} gz^t_ij (V_ij - mu_t) U_t,
+//     then dM_i = sum_j gV_ij W_ij^T (recursive-halving warp reduction), dW_ij += M_i^T gV_ij, and iteration 0's
+//     activation-gradient term.  The 45 KB state prefix + capsules of a location arrive by cp.async.bulk into a
+//     double-buffered stage.
+// =====================================================================================
+constexpr int kCoefVecRows = 4 * 16;   // per-warp shared vectors of the coefficient kernel: gS', gmu', mu_t, mu_{t-1}
+
+__global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+                                                                      const float* __restrict__ dout, float* __restrict__ state,
+                                                                      float* __restrict__ dcaps, float* __restrict__ dbeta_u,
+                                                                      float* __restrict__ dbeta_a, long long b, int C) {
+  extern __shared__ __align__(16) float sm[];
+  const int wst = routing_pitch(C);
+  const int nw = blockDim.x >> 5;
+  float* sW = sm;                                               // [32][16][wst] (+8)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* sc = sW + kB * 16 * wst + 8 + w * 544;                 // this warp's capsules
+  float* vec = sW + kB * 16 * wst + 8 + nw * 544 + w * (kCoefVecRows * wst + 8);
+  float* vgS = vec;                // [16][wst]
+  float* vgm = vec + 16 * wst;
+  float* vmu = vec + 32 * wst;
+  float* vmp = vec + 48 * wst;     // mu of iteration t-1
+  float* sred = sW + kB * 16 * wst + 8 + nw * 544 + nw * (kCoefVecRows * wst + 8);   // [nw][2][32]
+  const bool active = lane < C;
+  for (int idx = threadIdx.x; idx < kB * 16 * wst + 8; idx += blockDim.x) sW[idx] = 0.f;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kB * C * 16; idx += blockDim.x) {
+    const int h = idx & 15, j = (idx >> 4) % C, i = (idx >> 4) / C;
+    sW[(i * 16 + h) * wst + j] = W[idx];
+  }
+  __syncthreads();
+  const int ocols = C * 17;
+  const float invC = 1.f / (float)C;
+  float dbu_acc = 0.f, dba_acc = 0.f;
+  for (long long loc = (long long)blockIdx.x * nw + w; loc < b; loc += (long long)gridDim.x * nw) {
+    __syncwarp();
+    for (int idx = lane; idx < 544 / 4; idx += 32)
+      reinterpret_cast<float4*>(sc)[idx] = reinterpret_cast<const float4*>(caps + loc * 544)[idx];
+    __syncwarp();
+    const float* s_ain = sc + 512;
+    float* st = state + loc * kStFloats;
+    float gmu[16], gS[16], ga, gain_acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+      gmu[h] = active ? dout[loc * ocols + lane * 16 + h] : 0.f;
+      gS[h] = 0.f;
+    }
+    ga = active ? dout[loc * ocols + C * 16 + lane] : 0.f;
+#pragma unroll 1
+    for (int t = 2; t >= 0; --t) {
+      // ---- per-j M-step gradient of iteration t ----
+      __syncwarp();
+      const float* sc4 = st + kStSC + t * 4 * 32 + lane;
+      const float R = sc4[0], T = sc4[32], a = sc4[64], is = sc4[96];
+      const float invR = 1.f / (R + kEps);
+      const float gu = active ? ga * a * (1.f - a) : 0.f;
+      const float gcost = kLambda * is * (gu - warp_sum(gu) * invC);
+      dba_acc += kLambda * gu;
+      dbu_acc += active ? gcost * R : 0.f;
+      const float one_m_csum = 1.f - R * invR;
+      float D = 0.f, Kc = 0.f;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) {
+        const float m = st[kStMU + (t * 16 + h) * 32 + lane], Sv = st[kStS + (t * 16 + h) * 32 + lane];
+        const float gSh = gS[h] + gcost * R * 0.5f / Sv;
+        const float gmh = gmu[h] - 2.f * gSh * m * one_m_csum;
+        D = fmaf(gSh, Sv - kEps, D);
+        D = fmaf(gmh, m, D);
+        Kc = fmaf(gmh, m, Kc);
+        st[kStX + (t * 16 + h) * 32 + lane] = active ? 2.f * gSh * invR : 0.f;
+        st[kStG + (t * 16 + h) * 32 + lane] = active ? gmh * invR : 0.f;
+        if (active) {    // rows are wst (24) floats apart: a masked lane would land in the next row
+          vgS[h * wst + lane] = gSh;
+          vgm[h * wst + lane] = gmh;
+          vmu[h * wst + lane] = m;
+        }
+      }
+      const float gR_tot = gcost * T - D * invR;
+      if (t == 0) {
+        st[kStK + lane] = active ? gR_tot : 0.f;
+        break;
+      }
+      // ---- E step of iteration t-1 feeds r^t: per-j vectors of that iteration ----
+#pragma unroll
+      for (int h = 0; h < 16; ++h) {
+        const float iS = 1.f / st[kStS + ((t - 1) * 16 + h) * 32 + lane];
+        st[kStU + ((t - 1) * 16 + h) * 32 + lane] = active ? iS : 0.f;
+        if (active) vmp[h * wst + lane] = st[kStMU + ((t - 1) * 16 + h) * 32 + lane];
+      }
+      __syncwarp();
+      float A[16], Bq[16], gzsum = 0.f;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) A[h] = Bq[h] = 0.f;
+      const float* p_rn = st + kStRN + t * kB * 32 + lane;
+      float* p_r = st + kStR + (t - 1) * kB * 32 + lane;
+      const float* p_Z = st + kStZ + t * kB;
+      float rn_n = p_rn[0], r_n = p_r[0], Z_n = p_Z[0];
+#pragma unroll 1
+      for (int i = 0; i < kB; ++i) {
+        const float rn = rn_n, r = r_n, Z = Z_n;
+        if (i + 1 < kB) {
+          rn_n = p_rn[(i + 1) * 32];
+          r_n = p_r[(i + 1) * 32];
+          Z_n = p_Z[i + 1];
+        }
+        float V[16];
+        votes_of(sc, sW, i, lane, V, wst);
+        float gc = Kc;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          const float dv = V[h] - vmu[h * wst + lane];
+          gc = fmaf(fmaf(vgS[h * wst + lane], dv, vgm[h * wst + lane]), dv, gc);
+        }
+        const float grn = active ? fmaf(gc, invR, gR_tot) : 0.f;
+        const float dot2 = warp_sum(grn * rn);
+        const float grp = active ? (grn - dot2) / Z : 0.f;
+        const float gsum = warp_sum(grp * r);          // d a_in_i of this iteration; sum_j gr r = a_i gsum
+        if (lane == i) gain_acc += gsum;
+        const float gz = r * s_ain[i] * (grp - gsum);
+        p_r[i * 32] = gz;
+        gzsum += gz;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          const float d0 = V[h] - vmp[h * wst + lane];
+          const float u = gz * d0;
+          A[h] += u;
+          Bq[h] = fmaf(u, d0, Bq[h]);
+        }
+      }
+      const float a_prev = st[kStSC + (t - 1) * 4 * 32 + 64 + lane];
+      ga = gzsum / (kEps + a_prev);
+#pragma unroll
+      for (int h = 0; h < 16; ++h) {
+        const float iS = st[kStU + ((t - 1) * 16 + h) * 32 + lane];   // written above by this lane (0 for the masked lanes)
+        gmu[h] = iS * A[h];
+        gS[h] = 0.5f * iS * (iS * Bq[h] - gzsum);
+      }
+    }
+    dcaps[loc * 544 + 512 + lane] = gain_acc;
+  }
+  sred[(w * 2 + 0) * 32 + lane] = dbu_acc;
+  sred[(w * 2 + 1) * 32 + lane] = dba_acc;
+  __syncthreads();
+  if (w == 0 && active) {
+    float su = 0.f, sa = 0.f;
+    for (int ww = 0; ww < nw; ++ww) {
+      su += sred[(ww * 2 + 0) * 32 + lane];
+      sa += sred[(ww * 2 + 1) * 32 + lane];
+    }
+#pragma unroll
+    for (int h = 0; h < 16; ++h) atomicAdd(dbeta_u + lane * 16 + h, su);
+    atomicAdd(dbeta_a + lane, sa);
+  }
+}
+
+constexpr int kFinStage = kStS + 544;      // floats per stage: state prefix + capsules
+constexpr int kFinWarps = 16;              // thread (w, lane) owns the pairs (i = w, j = lane) and (i = w + 16, j = lane)
+
+// one (i, j) pair of the final backward kernel: vote gradient of all three iterations, iteration 0's activation
+// gradient, pose gradient (warp reduction over j) and the weight-gradient accumulation
+__device__ __forceinline__ void final_pair(const float* __restrict__ sv, const float* __restrict__ scap, const float* __restrict__ sW,
+                                        int i, int lane, int wst, bool active, float invC, float gRtot0, float* __restrict__ dcl,
+                                        float (&dWacc)[16]) {
+    float V[16];
+    votes_of(scap, sW, i, lane, V, wst);
+    const float rn0 = sv[kStRN + (0 * kB + i) * 32 + lane], rn1 = sv[kStRN + (1 * kB + i) * 32 + lane],
+                rn2 = sv[kStRN + (2 * kB + i) * 32 + lane];
+    const float gz0 = sv[kStR + (0 * kB + i) * 32 + lane], gz1 = sv[kStR + (1 * kB + i) * 32 + lane];
+    float gc0 = 0.f;
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+      const float d0 = V[h] - sv[kStMU + (0 * 16 + h) * 32 + lane];
+      const float d1 = V[h] - sv[kStMU + (1 * 16 + h) * 32 + lane];
+      const float d2 = V[h] - sv[kStMU + (2 * 16 + h) * 32 + lane];
+      const float X0 = sv[kStX + (0 * 16 + h) * 32 + lane], G0 = sv[kStG + (0 * 16 + h) * 32 + lane];
+      gc0 = fmaf(fmaf(0.5f * X0, d0, G0), d0, gc0);
+      gc0 = fmaf(G0, V[h] - d0, gc0);                       // + G0 mu0
+      float g = rn0 * G0;
+      g = fmaf(rn1, sv[kStG + (1 * 16 + h) * 32 + lane], g);
+      g = fmaf(rn2, sv[kStG + (2 * 16 + h) * 32 + lane], g);
+      g = fmaf(fmaf(rn0, X0, -gz0 * sv[kStU + (0 * 16 + h) * 32 + lane]), d0, g);
+      g = fmaf(fmaf(rn1, sv[kStX + (1 * 16 + h) * 32 + lane], -gz1 * sv[kStU + (1 * 16 + h) * 32 + lane]), d1, g);
+      g = fmaf(rn2 * sv[kStX + (2 * 16 + h) * 32 + lane], d2, g);
+      V[h] = active ? g : 0.f;                              // V now holds gV
+    }
+    // iteration 0's activation gradient: r^0 = 1/C
+    const float grn = active ? gc0 + gRtot0 : 0.f;
+    const float dot2 = warp_sum(grn * rn0);
+    const float grp = active ? (grn - dot2) / sv[kStZ + i] : 0.f;
+    const float gain0 = warp_sum(grp) * invC;
+    if (lane == 0) dcl[512 + i] += gain0;
+    float M[16], Wr[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 m4 = *reinterpret_cast<const float4*>(scap + i * 16 + q * 4);
+      M[q * 4 + 0] = m4.x; M[q * 4 + 1] = m4.y; M[q * 4 + 2] = m4.z; M[q * 4 + 3] = m4.w;
+    }
+#pragma unroll
+    for (int h = 0; h < 16; ++h) Wr[h] = sW[(i * 16 + h) * wst + lane];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float g = dWacc[kk * 4 + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g = fmaf(M[r * 4 + kk], V[r * 4 + c], g);
+        dWacc[kk * 4 + c] = g;
+      }
+    // dM_i[r][kk] = sum_j (gV_ij W_ij^T)[r][kk]: 16 sums over the 32 lanes by recursive halving
+    float P[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float g = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) g = fmaf(V[r * 4 + c], Wr[kk * 4 + c], g);
+        P[r * 4 + kk] = active ? g : 0.f;
+      }
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+      const bool hi = (lane & bit) != 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < half) {
+          const float send = hi ? P[q] : P[q + half];
+          const float keep = hi ? P[q + half] : P[q];
+          P[q] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+      }
+    }
+    P[0] += __shfl_xor_sync(0xffffffffu, P[0], 1);
+    if ((lane & 1) == 0) dcl[i * 16 + (lane >> 1)] = P[0];
+}
+
+__global__ void __launch_bounds__(kFinWarps * 32, 1) em_routing_bwd_final_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+                                                                                 const float* __restrict__ state, float* __restrict__ dcaps,
+                                                                                 float* __restrict__ dW, long long b, int C) {
+  extern __shared__ __align__(128) float sm[];
+  const int wst = routing_pitch(C);
+  float* stage0 = sm;                                   // [2][kFinStage]
+  float* sW = sm + 2 * kFinStage;                       // [32][16][wst] (+8)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sW + kB * 16 * wst + 8);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool active = lane < C;
+  for (int idx = threadIdx.x; idx < kB * 16 * wst + 8; idx += blockDim.x) sW[idx] = 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kB * C * 16; idx += blockDim.x) {
+    const int h = idx & 15, j = (idx >> 4) % C, i = (idx >> 4) / C;
+    sW[(i * 16 + h) * wst + j] = W[idx];
+  }
+  constexpr uint32_t kStBytes = kStS * 4, kCapBytes = 544 * 4;
+  if (threadIdx.x == 0 && (long long)blockIdx.x < b) {
+    mbar_arrive_expect_tx(&full[0], kStBytes + kCapBytes);
+    bulk_g2s(smem_u32(stage0), state + (long long)blockIdx.x * kStFloats, kStBytes, &full[0]);
+    bulk_g2s(smem_u32(stage0 + kStS), caps + (long long)blockIdx.x * 544, kCapBytes, &full[0]);
+  }
+  __syncthreads();
+  float dWacc0[16], dWacc1[16];
+#pragma unroll
+  for (int h = 0; h < 16; ++h) dWacc0[h] = dWacc1[h] = 0.f;
+  const float invC = 1.f / (float)C;
+  int it = 0;
+  for (long long loc = blockIdx.x; loc < b; loc += gridDim.x, ++it) {
+    const int s = it & 1;
+    const long long nxt = loc + gridDim.x;
+    if (threadIdx.x == 0 && nxt < b) {   // stage s^1 was released by the barrier that ended the previous iteration
+      float* dst = stage0 + (s ^ 1) * kFinStage;
+      mbar_arrive_expect_tx(&full[s ^ 1], kStBytes + kCapBytes);
+      bulk_g2s(smem_u32(dst), state + nxt * kStFloats, kStBytes, &full[s ^ 1]);
+      bulk_g2s(smem_u32(dst + kStS), caps + nxt * 544, kCapBytes, &full[s ^ 1]);
+    }
+    mbar_wait(&full[s], (uint32_t)((it >> 1) & 1), 900 + s);
+    const float* sv = stage0 + s * kFinStage;
+    const float* scap = sv + kStS;
+    const float gRtot0 = sv[kStK + lane];
+    final_pair(sv, scap, sW, w, lane, wst, active, invC, gRtot0, dcaps + loc * 544, dWacc0);
+    asm volatile("" ::: "memory");   // keep the two pairs sequential (register pressure)
+    final_pair(sv, scap, sW, w + kFinWarps, lane, wst, active, invC, gRtot0, dcaps + loc * 544, dWacc1);
+    __syncthreads();   // every thread is done with stage s before it is refilled (two iterations ahead)
+  }
+  if (active) {
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+      atomicAdd(dW + ((long long)w * C + lane) * 16 + h, dWacc0[h]);
+      atomicAdd(dW + ((long long)(w + kFinWarps) * C + lane) * 16 + h, dWacc1[h]);
+    }
+  }
+}
+
+// =====================================================================================
 // glue: rout (N, L, C*16 + C) fp32
 __global__ void class_mean_kernel(const float* __restrict__ rout, float* __restrict__ act, int L, int C) {
   const int n = blockIdx.x;
@@ -839,11 +1158,40 @@ B2C_API int b2c_em_routing_fwd_train(const float* caps, const float* W, const fl
 }
 
 static int routing_bwd_impl(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
-                            const float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
+                            float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
                             b2c_stream_t s) {
   B2C_REQUIRE(caps && W && beta_u && beta_a && dout && dcaps && dW && dbeta_u && dbeta_a, "em_routing_bwd: null pointer");
   B2C_REQUIRE(C >= 1 && C <= 32, "em_routing_bwd: C=%d must be in [1,32]", C);
   if (b <= 0) return 0;
+  // saved state: two-kernel backward (r02d); B2C_ROUTING_BWD=cta selects the CTA-per-location kernel on the same state
+  static int split = -1;
+  if (split < 0) {
+    const char* e = getenv("B2C_ROUTING_BWD");
+    split = (e && e[0] == 'c') ? 0 : 1;
+  }
+  if (state && split) {
+    const int wst = routing_pitch(C);
+    const int nw = C <= 24 ? 16 : 8;
+    const size_t sm1 = (size_t)(kB * 16 * wst + 8 + nw * 544 + nw * (kCoefVecRows * wst + 8) + nw * 64) * sizeof(float);
+    const size_t sm2 = (size_t)(2 * kFinStage + kB * 16 * wst + 8) * sizeof(float) + 16;
+    static bool cfg2 = false;
+    if (!cfg2) {
+      cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
+      if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_bwd(split) attr");
+      cfg2 = true;
+    }
+    long long g1 = b2c_num_sms();
+    if (g1 * nw > b) g1 = (b + nw - 1) / nw;
+    em_routing_bwd_coef_kernel<<<(unsigned)g1, nw * 32, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
+    B2C_LAUNCH_CHECK("em_routing_bwd(coef)");
+    long long g2 = b2c_num_sms();
+    if (g2 > b) g2 = b;
+    em_routing_bwd_final_kernel<<<(unsigned)g2, kFinWarps * 32, sm2, (cudaStream_t)s>>>(caps, W, state, dcaps, dW, b, C);
+    b2c_launches_add(2);
+    B2C_LAUNCH_CHECK("em_routing_bwd(final)");
+    return 0;
+  }
   const size_t smem = (size_t)(2 * kB * 16 * 32 + (kNW + 1) * 17 * 32 + 2 * 3 * 16 * 32 + 17 * 32 + 544 + 32 * 17 + 3 * 3 * kIPT * kRT +
                                3 * 4 * 32) * sizeof(float);
   static bool cfg = false;
@@ -872,7 +1220,7 @@ B2C_API int b2c_em_routing_bwd(const float* caps, const float* W, const float* b
 }
 
 B2C_API int b2c_em_routing_bwd_state(const float* caps, const float* W, const float* beta_u, const float* beta_a, const float* dout,
-                                     const float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
+                                     float* state, float* dcaps, float* dW, float* dbeta_u, float* dbeta_a, int64_t b, int32_t C,
                                      b2c_stream_t s) {
   B2C_REQUIRE(state, "em_routing_bwd_state: null state buffer");
   return routing_bwd_impl(caps, W, beta_u, beta_a, dout, state, dcaps, dW, dbeta_u, dbeta_a, b, C, s);

@@ -57,7 +57,7 @@ def main():
     ops.em_routing_bwd(caps[:n].contiguous(), W, bu, ba, dout[:n].contiguous(), dcaps[:n], dW, dbu, dba, n, C, state=st_n)
     torch.cuda.synchronize()
     rel = lambda x, y: float((x.double().cpu() - y).abs().max() / (y.abs().max() + 1e-30))
-    print(f"B2C_ROUTING={os.environ.get('B2C_ROUTING', 'warp')} saved-state={use_state}: fwd {t_f:.3f} ms  bwd {t_b:.3f} ms | parity fwd {e_f:.2e} "
+    print(f"B2C_ROUTING={os.environ.get('B2C_ROUTING', 'warp')} B2C_ROUTING_BWD={os.environ.get('B2C_ROUTING_BWD', 'split')} saved-state={use_state}: fwd {t_f:.3f} ms  bwd {t_b:.3f} ms | parity fwd {e_f:.2e} "
           f"dcaps {rel(dcaps[:n], gr[0]):.2e} dW {rel(dW.reshape(gr[1].shape), gr[1]):.2e} dbu {rel(dbu.reshape(gr[2].shape), gr[2]):.2e} "
           f"dba {rel(dba.reshape(gr[3].shape), gr[3]):.2e}")
 

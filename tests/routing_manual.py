@@ -74,3 +74,72 @@ def backward_manual(poses, a_in, W, beta_u, beta_a, g_mu, g_a, iters=3, eps=1e-8
     g_poses = torch.einsum("nijrc,ijkc->nirk", gV4, W).reshape(b, B, 16)
     g_W = torch.einsum("nirk,nijrc->ijkc", poses.view(b, B, 4, 4), gV4)
     return g_poses, g_ain, g_W, g_beta_u, g_beta_a
+
+
+def backward_split(poses, a_in, W, beta_u, beta_a, g_mu, g_a, iters=3, eps=1e-8, lam=1e-6):
+    """The same backward in the form of the two-kernel split (csrc/routing.cu: em_routing_bwd_coef_kernel +
+    em_routing_bwd_final_kernel).  Phase 1 walks t = 2, 1 and produces only per-(i,j) scalars gz^t and per-j vectors
+    (X' = 2 gS' / (R+eps), G' = gmu' / (R+eps), U = 1/S); the sum D_j = sum_i gc_ij c_ij is closed-form
+    (sum_i c (V-mu)^2 = S - eps, sum_i c V = mu).  Phase 2 assembles every vote gradient in ONE pass:
+        gV_ij = sum_t rn^t (G'_t + X'_t (V - mu_t)) - sum_{t<2} gz^t (V - mu_t) U_t
+    and does iteration 0's activation-gradient term."""
+    assert iters == 3
+    b, B, _ = poses.shape
+    C = W.shape[1]
+    V, saved = forward_saved(poses, a_in, W, beta_u, beta_a, iters, eps, lam)
+    g_beta_u = torch.zeros_like(beta_u)
+    g_beta_a = torch.zeros_like(beta_a)
+    g_ain = torch.zeros_like(a_in)
+    gmu, gS, ga = g_mu.clone(), torch.zeros_like(g_mu), g_a.clone()
+    Xp, Gp, U, gz_saved = {}, {}, {}, {}
+    gR_tot0 = None
+    # ---- phase 1 ----
+    for t in (2, 1, 0):
+        sv = saved[t]
+        mu, S, a, R, rn, Z, T = sv["mu"], sv["S"], sv["a"], sv["R"], sv["rn"], sv["Z"], sv["T"]
+        invR = 1.0 / (R + eps)
+        gu = ga * a * (1 - a)
+        g_beta_a = g_beta_a + lam * gu.sum(0)
+        gcost = lam / (sv["s"] + eps) * (gu - gu.mean(1, keepdim=True))
+        g_beta_u = g_beta_u + (gcost * R).unsqueeze(-1).expand(-1, -1, 16).sum(0)
+        gSh = gS + (gcost * R).unsqueeze(-1) * 0.5 / S
+        gmh = gmu - 2 * gSh * mu * (1 - R * invR).unsqueeze(-1)
+        D = (gSh * (S - eps) + gmh * mu).sum(-1)
+        gR_tot = gcost * T - D * invR
+        Xp[t] = 2 * gSh * invR.unsqueeze(-1)
+        Gp[t] = gmh * invR.unsqueeze(-1)
+        if t == 0:
+            gR_tot0 = gR_tot
+            break
+        dV = V - mu.unsqueeze(1)
+        gc = (gSh.unsqueeze(1) * dV * dV + gmh.unsqueeze(1) * V).sum(-1)
+        grn = gc * invR.unsqueeze(1) + gR_tot.unsqueeze(1)
+        grp = (grn - (grn * rn).sum(2, keepdim=True)) / Z
+        g_ain = g_ain + (grp * sv["r_prev"]).sum(2)
+        gr = grp * a_in.view(b, B, 1)
+        r = sv["r_prev"]
+        gz = r * (gr - (gr * r).sum(2, keepdim=True))
+        gz_saved[t - 1] = gz
+        p = saved[t - 1]
+        iS = 1.0 / p["S"]
+        U[t - 1] = iS
+        d0 = V - p["mu"].unsqueeze(1)
+        dv = d0 * iS.unsqueeze(1)
+        ga = gz.sum(1) / (eps + p["a"])
+        gmu = (gz.unsqueeze(-1) * dv).sum(1)
+        gS = (gz.unsqueeze(-1) * 0.5 * iS.unsqueeze(1) * (dv * d0 - 1)).sum(1)
+    # ---- phase 2 ----
+    d = [V - saved[t]["mu"].unsqueeze(1) for t in range(3)]
+    gV = torch.zeros_like(V)
+    for t in range(3):
+        gV = gV + saved[t]["rn"].unsqueeze(-1) * (Gp[t].unsqueeze(1) + Xp[t].unsqueeze(1) * d[t])
+    for t in range(2):
+        gV = gV - gz_saved[t].unsqueeze(-1) * d[t] * U[t].unsqueeze(1)
+    gc0 = (0.5 * Xp[0].unsqueeze(1) * d[0] * d[0] + Gp[0].unsqueeze(1) * V).sum(-1)
+    grn = gc0 + gR_tot0.unsqueeze(1)
+    grp = (grn - (grn * saved[0]["rn"]).sum(2, keepdim=True)) / saved[0]["Z"]
+    g_ain = g_ain + (grp * saved[0]["r_prev"]).sum(2)
+    gV4 = gV.view(b, B, C, 4, 4)
+    g_poses = torch.einsum("nijrc,ijkc->nirk", gV4, W).reshape(b, B, 16)
+    g_W = torch.einsum("nirk,nijrc->ijkc", poses.view(b, B, 4, 4), gV4)
+    return g_poses, g_ain, g_W, g_beta_u, g_beta_a
