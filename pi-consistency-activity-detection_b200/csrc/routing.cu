@@ -710,13 +710,34 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
 // =====================================================================================
 constexpr int kCoefVecRows = 4 * 16;   // per-warp shared vectors of the coefficient kernel: gS', gmu', mu_t, mu_{t-1}
 
-__global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+// reciprocal without the IEEE-division slow path: MUFU.RCP + one Newton step (<= 1 ulp for the normal-range operands here)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * fmaf(-x, r, 2.f);
+}
+
+// shared-memory load the compiler may not hoist out of a loop (the 16-warp coefficient kernel has 128 registers: hoisting
+// the 64 loop-invariant per-j vector elements makes it spill)
+template <bool kPin>
+__device__ __forceinline__ float lds_vec(const float* p) {
+  if (!kPin) return *p;
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int kNWc>
+__global__ void __launch_bounds__(kNWc * 32, 1) em_routing_bwd_coef_kernel(const float* __restrict__ caps, const float* __restrict__ W,
                                                                       const float* __restrict__ dout, float* __restrict__ state,
                                                                       float* __restrict__ dcaps, float* __restrict__ dbeta_u,
                                                                       float* __restrict__ dbeta_a, long long b, int C) {
   extern __shared__ __align__(16) float sm[];
   const int wst = routing_pitch(C);
-  const int nw = blockDim.x >> 5;
+  constexpr int nw = kNWc;
+  constexpr bool kPin = kNWc > 12;
   float* sW = sm;                                               // [32][16][wst] (+8)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* sc = sW + kB * 16 * wst + 8 + w * 544;                 // this warp's capsules
@@ -744,6 +765,21 @@ __global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float
     __syncwarp();
     const float* s_ain = sc + 512;
     float* st = state + loc * kStFloats;
+    {  // the next location of this warp: pull the rows both loops will read (r, rn of iterations 1 and 2, Z, scalars, mu, S)
+      const long long nl = loc + (long long)gridDim.x * nw;
+      if (nl < b) {
+        const float* sn = state + nl * kStFloats;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) prefetch_l2(sn + kStR + (q * 32 + lane) * 32);
+#pragma unroll
+        for (int q = 1; q < 3; ++q) prefetch_l2(sn + kStRN + (q * 32 + lane) * 32);
+        if (lane < 15) prefetch_l2(sn + kStZ + lane * 32);
+        prefetch_l2(sn + kStMU + lane * 32);
+        if (lane < 16) prefetch_l2(sn + kStMU + (32 + lane) * 32);
+        prefetch_l2(sn + kStS + lane * 32);
+        if (lane < 16) prefetch_l2(sn + kStS + (32 + lane) * 32);
+      }
+    }
     float gmu[16], gS[16], ga, gain_acc = 0.f;
 #pragma unroll
     for (int h = 0; h < 16; ++h) {
@@ -757,7 +793,7 @@ __global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float
       __syncwarp();
       const float* sc4 = st + kStSC + t * 4 * 32 + lane;
       const float R = sc4[0], T = sc4[32], a = sc4[64], is = sc4[96];
-      const float invR = 1.f / (R + kEps);
+      const float invR = fast_rcp(R + kEps);
       const float gu = active ? ga * a * (1.f - a) : 0.f;
       const float gcost = kLambda * is * (gu - warp_sum(gu) * invC);
       dba_acc += kLambda * gu;
@@ -767,7 +803,7 @@ __global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float
 #pragma unroll
       for (int h = 0; h < 16; ++h) {
         const float m = st[kStMU + (t * 16 + h) * 32 + lane], Sv = st[kStS + (t * 16 + h) * 32 + lane];
-        const float gSh = gS[h] + gcost * R * 0.5f / Sv;
+        const float gSh = fmaf(gcost * R * 0.5f, fast_rcp(Sv), gS[h]);
         const float gmh = gmu[h] - 2.f * gSh * m * one_m_csum;
         D = fmaf(gSh, Sv - kEps, D);
         D = fmaf(gmh, m, D);
@@ -788,7 +824,7 @@ __global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float
       // ---- E step of iteration t-1 feeds r^t: per-j vectors of that iteration ----
 #pragma unroll
       for (int h = 0; h < 16; ++h) {
-        const float iS = 1.f / st[kStS + ((t - 1) * 16 + h) * 32 + lane];
+        const float iS = fast_rcp(st[kStS + ((t - 1) * 16 + h) * 32 + lane]);
         st[kStU + ((t - 1) * 16 + h) * 32 + lane] = active ? iS : 0.f;
         if (active) vmp[h * wst + lane] = st[kStMU + ((t - 1) * 16 + h) * 32 + lane];
       }
@@ -813,12 +849,12 @@ __global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float
         float gc = Kc;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
-          const float dv = V[h] - vmu[h * wst + lane];
-          gc = fmaf(fmaf(vgS[h * wst + lane], dv, vgm[h * wst + lane]), dv, gc);
+          const float dv = V[h] - lds_vec<kPin>(vmu + h * wst + lane);
+          gc = fmaf(fmaf(lds_vec<kPin>(vgS + h * wst + lane), dv, lds_vec<kPin>(vgm + h * wst + lane)), dv, gc);
         }
         const float grn = active ? fmaf(gc, invR, gR_tot) : 0.f;
         const float dot2 = warp_sum(grn * rn);
-        const float grp = active ? (grn - dot2) / Z : 0.f;
+        const float grp = active ? (grn - dot2) * fast_rcp(Z) : 0.f;
         const float gsum = warp_sum(grp * r);          // d a_in_i of this iteration; sum_j gr r = a_i gsum
         if (lane == i) gain_acc += gsum;
         const float gz = r * s_ain[i] * (grp - gsum);
@@ -826,14 +862,14 @@ __global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float
         gzsum += gz;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
-          const float d0 = V[h] - vmp[h * wst + lane];
+          const float d0 = V[h] - lds_vec<kPin>(vmp + h * wst + lane);
           const float u = gz * d0;
           A[h] += u;
           Bq[h] = fmaf(u, d0, Bq[h]);
         }
       }
       const float a_prev = st[kStSC + (t - 1) * 4 * 32 + 64 + lane];
-      ga = gzsum / (kEps + a_prev);
+      ga = gzsum * fast_rcp(kEps + a_prev);
 #pragma unroll
       for (int h = 0; h < 16; ++h) {
         const float iS = st[kStU + ((t - 1) * 16 + h) * 32 + lane];   // written above by this lane (0 for the masked lanes)
@@ -861,37 +897,61 @@ __global__ void __launch_bounds__(512, 1) em_routing_bwd_coef_kernel(const float
 constexpr int kFinStage = kStS + 544;      // floats per stage: state prefix + capsules
 constexpr int kFinWarps = 16;              // thread (w, lane) owns the pairs (i = w, j = lane) and (i = w + 16, j = lane)
 
-// one (i, j) pair of the final backward kernel: vote gradient of all three iterations, iteration 0's activation
-// gradient, pose gradient (warp reduction over j) and the weight-gradient accumulation
-__device__ __forceinline__ void final_pair(const float* __restrict__ sv, const float* __restrict__ scap, const float* __restrict__ sW,
-                                        int i, int lane, int wst, bool active, float invC, float gRtot0, float* __restrict__ dcl,
-                                        float (&dWacc)[16]) {
-    float V[16];
-    votes_of(scap, sW, i, lane, V, wst);
-    const float rn0 = sv[kStRN + (0 * kB + i) * 32 + lane], rn1 = sv[kStRN + (1 * kB + i) * 32 + lane],
-                rn2 = sv[kStRN + (2 * kB + i) * 32 + lane];
-    const float gz0 = sv[kStR + (0 * kB + i) * 32 + lane], gz1 = sv[kStR + (1 * kB + i) * 32 + lane];
-    float gc0 = 0.f;
+// the final backward kernel's two (i, j) pairs of a thread.  final_gv: vote gradients of all three iterations for both
+// pairs (the eleven per-j vector elements of every pose component are loaded once and used for both); final_tail:
+// iteration 0's activation gradient, pose gradient (warp reduction over j) and the weight-gradient accumulation of ONE
+// pair
+__device__ __forceinline__ void final_gv(const float* __restrict__ sv, int ia, int ib, int lane, bool active, float (&Va)[16],
+                                         float (&Vb)[16], float& gc0a, float& gc0b, float& rn0a, float& rn0b) {
+  rn0a = sv[kStRN + (0 * kB + ia) * 32 + lane];
+  rn0b = sv[kStRN + (0 * kB + ib) * 32 + lane];
+  const float rn1a = sv[kStRN + (1 * kB + ia) * 32 + lane], rn2a = sv[kStRN + (2 * kB + ia) * 32 + lane];
+  const float rn1b = sv[kStRN + (1 * kB + ib) * 32 + lane], rn2b = sv[kStRN + (2 * kB + ib) * 32 + lane];
+  const float gz0a = sv[kStR + (0 * kB + ia) * 32 + lane], gz1a = sv[kStR + (1 * kB + ia) * 32 + lane];
+  const float gz0b = sv[kStR + (0 * kB + ib) * 32 + lane], gz1b = sv[kStR + (1 * kB + ib) * 32 + lane];
+  gc0a = gc0b = 0.f;
 #pragma unroll
-    for (int h = 0; h < 16; ++h) {
-      const float d0 = V[h] - sv[kStMU + (0 * 16 + h) * 32 + lane];
-      const float d1 = V[h] - sv[kStMU + (1 * 16 + h) * 32 + lane];
-      const float d2 = V[h] - sv[kStMU + (2 * 16 + h) * 32 + lane];
-      const float X0 = sv[kStX + (0 * 16 + h) * 32 + lane], G0 = sv[kStG + (0 * 16 + h) * 32 + lane];
-      gc0 = fmaf(fmaf(0.5f * X0, d0, G0), d0, gc0);
-      gc0 = fmaf(G0, V[h] - d0, gc0);                       // + G0 mu0
-      float g = rn0 * G0;
-      g = fmaf(rn1, sv[kStG + (1 * 16 + h) * 32 + lane], g);
-      g = fmaf(rn2, sv[kStG + (2 * 16 + h) * 32 + lane], g);
-      g = fmaf(fmaf(rn0, X0, -gz0 * sv[kStU + (0 * 16 + h) * 32 + lane]), d0, g);
-      g = fmaf(fmaf(rn1, sv[kStX + (1 * 16 + h) * 32 + lane], -gz1 * sv[kStU + (1 * 16 + h) * 32 + lane]), d1, g);
-      g = fmaf(rn2 * sv[kStX + (2 * 16 + h) * 32 + lane], d2, g);
-      V[h] = active ? g : 0.f;                              // V now holds gV
+  for (int h = 0; h < 16; ++h) {
+    const float mu0 = sv[kStMU + (0 * 16 + h) * 32 + lane], mu1 = sv[kStMU + (1 * 16 + h) * 32 + lane],
+                mu2 = sv[kStMU + (2 * 16 + h) * 32 + lane];
+    const float X0 = sv[kStX + (0 * 16 + h) * 32 + lane], X1 = sv[kStX + (1 * 16 + h) * 32 + lane],
+                X2 = sv[kStX + (2 * 16 + h) * 32 + lane];
+    const float G0 = sv[kStG + (0 * 16 + h) * 32 + lane], G1 = sv[kStG + (1 * 16 + h) * 32 + lane],
+                G2 = sv[kStG + (2 * 16 + h) * 32 + lane];
+    const float U0 = sv[kStU + (0 * 16 + h) * 32 + lane], U1 = sv[kStU + (1 * 16 + h) * 32 + lane];
+    const float hX0 = 0.5f * X0, G0mu = G0 * mu0;
+    {
+      const float d0 = Va[h] - mu0, d1 = Va[h] - mu1, d2 = Va[h] - mu2;
+      gc0a = fmaf(fmaf(hX0, d0, G0), d0, gc0a + G0mu);
+      float g = rn0a * G0;
+      g = fmaf(rn1a, G1, g);
+      g = fmaf(rn2a, G2, g);
+      g = fmaf(fmaf(rn0a, X0, -gz0a * U0), d0, g);
+      g = fmaf(fmaf(rn1a, X1, -gz1a * U1), d1, g);
+      g = fmaf(rn2a * X2, d2, g);
+      Va[h] = active ? g : 0.f;                              // V now holds gV
     }
+    {
+      const float d0 = Vb[h] - mu0, d1 = Vb[h] - mu1, d2 = Vb[h] - mu2;
+      gc0b = fmaf(fmaf(hX0, d0, G0), d0, gc0b + G0mu);
+      float g = rn0b * G0;
+      g = fmaf(rn1b, G1, g);
+      g = fmaf(rn2b, G2, g);
+      g = fmaf(fmaf(rn0b, X0, -gz0b * U0), d0, g);
+      g = fmaf(fmaf(rn1b, X1, -gz1b * U1), d1, g);
+      g = fmaf(rn2b * X2, d2, g);
+      Vb[h] = active ? g : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void final_tail(const float* __restrict__ sv, const float* __restrict__ scap, const float* __restrict__ sW,
+                                           int i, int lane, int wst, bool active, float invC, float gRtot0, float gc0, float rn0,
+                                           const float (&V)[16], float* __restrict__ dcl, float (&dWacc)[16]) {
     // iteration 0's activation gradient: r^0 = 1/C
     const float grn = active ? gc0 + gRtot0 : 0.f;
     const float dot2 = warp_sum(grn * rn0);
-    const float grp = active ? (grn - dot2) / sv[kStZ + i] : 0.f;
+    const float grp = active ? (grn - dot2) * fast_rcp(sv[kStZ + i]) : 0.f;
     const float gain0 = warp_sum(grp) * invC;
     if (lane == 0) dcl[512 + i] += gain0;
     float M[16], Wr[16];
@@ -984,9 +1044,15 @@ __global__ void __launch_bounds__(kFinWarps * 32, 1) em_routing_bwd_final_kernel
     const float* sv = stage0 + s * kFinStage;
     const float* scap = sv + kStS;
     const float gRtot0 = sv[kStK + lane];
-    final_pair(sv, scap, sW, w, lane, wst, active, invC, gRtot0, dcaps + loc * 544, dWacc0);
-    asm volatile("" ::: "memory");   // keep the two pairs sequential (register pressure)
-    final_pair(sv, scap, sW, w + kFinWarps, lane, wst, active, invC, gRtot0, dcaps + loc * 544, dWacc1);
+    {
+      float Va[16], Vb[16], gc0a, gc0b, rn0a, rn0b;
+      votes_of(scap, sW, w, lane, Va, wst);
+      votes_of(scap, sW, w + kFinWarps, lane, Vb, wst);
+      final_gv(sv, w, w + kFinWarps, lane, active, Va, Vb, gc0a, gc0b, rn0a, rn0b);
+      final_tail(sv, scap, sW, w, lane, wst, active, invC, gRtot0, gc0a, rn0a, Va, dcaps + loc * 544, dWacc0);
+      asm volatile("" ::: "memory");   // keep the two tails sequential (register pressure)
+      final_tail(sv, scap, sW, w + kFinWarps, lane, wst, active, invC, gRtot0, gc0b, rn0b, Vb, dcaps + loc * 544, dWacc1);
+    }
     __syncthreads();   // every thread is done with stage s before it is refilled (two iterations ahead)
   }
   if (active) {
@@ -1171,19 +1237,35 @@ static int routing_bwd_impl(const float* caps, const float* W, const float* beta
   }
   if (state && split) {
     const int wst = routing_pitch(C);
-    const int nw = C <= 24 ? 16 : 8;
+    static int nw_env = -1;
+    if (nw_env < 0) {
+      const char* e = getenv("B2C_ROUTING_COEF_WARPS");
+      nw_env = e ? atoi(e) : 0;
+    }
+    // measured (12 800 locations, C = 24): 16 warps / 128 registers 0.68 ms, 12 warps / 168 registers 0.51 ms
+    const int nw = C > 24 ? 8 : (nw_env == 16 || nw_env == 10 || nw_env == 8 ? nw_env : 12);
     const size_t sm1 = (size_t)(kB * 16 * wst + 8 + nw * 544 + nw * (kCoefVecRows * wst + 8) + nw * 64) * sizeof(float);
     const size_t sm2 = (size_t)(2 * kFinStage + kB * 16 * wst + 8) * sizeof(float) + 16;
     static bool cfg2 = false;
     if (!cfg2) {
-      cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
       if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_bwd(split) attr");
       cfg2 = true;
     }
     long long g1 = b2c_num_sms();
     if (g1 * nw > b) g1 = (b + nw - 1) / nw;
-    em_routing_bwd_coef_kernel<<<(unsigned)g1, nw * 32, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
+    if (nw == 16)
+      em_routing_bwd_coef_kernel<16><<<(unsigned)g1, 512, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
+    else if (nw == 12)
+      em_routing_bwd_coef_kernel<12><<<(unsigned)g1, 384, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
+    else if (nw == 10)
+      em_routing_bwd_coef_kernel<10><<<(unsigned)g1, 320, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
+    else
+      em_routing_bwd_coef_kernel<8><<<(unsigned)g1, 256, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
     B2C_LAUNCH_CHECK("em_routing_bwd(coef)");
     long long g2 = b2c_num_sms();
     if (g2 > b) g2 = b;
