@@ -60,6 +60,9 @@ _SIGS = {
     "b2c_u8_clip_to_cl": [vp, vp, i32, i32, i64, i32, vp],
     "b2c_u8_to_f32": [vp, vp, i64, f32, vp],
     "b2c_im2col_small": [vp, vp] + [i32] * 19 + [vp],
+    "b2c_bn_relu_fwd_fused": [vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, i64, i32, i32, vp],
+    "b2c_bn_relu_bwd_fused": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, i64, i32, vp, vp,
+                              i32, vp],
     "b2c_bn_sums": [vp, i64, i32, i64, i32, i32, vp, vp],
     "b2c_bn_finalize": [vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, f32, f32, vp],
     "b2c_bn_relu_apply": [vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, i64, i32, i32, vp],
@@ -92,6 +95,7 @@ _SIGS = {
     "b2c_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp, vp],
     "b2c_fill_f32": [vp, i64, f32, vp],
     "b2c_set_deterministic": [i32],
+    "b2c_set_pool_generic": [i32],
     "b2c_set_precision": [i32],
     "b2c_stem_fold_input": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2c_clips_to_folded": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -439,13 +439,12 @@ def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: 
         ws = zeros_f32((g, 2, Cout), raw.device)
         sv.mean = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
         sv.rstd = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
-        ops.bn_sums(rv_, g, ws)
-        ops.bn_finalize(ws, Cout, 0, Cout, g, rv_.rows // g, sv.mean, sv.rstd, rm, rv, BN_MOMENTUM, BN_EPS)
         sv.groups = g
-    else:
-        sv.mean = rm.detach().float().view(1, -1).contiguous()
-        sv.rstd = torch.rsqrt(rv.detach().float() + BN_EPS).view(1, -1).contiguous()
-        sv.groups = 1
+        ops.bn_relu_fwd_fused(rv_, g, ws, sv.mean, sv.rstd, rm, rv, BN_MOMENTUM, BN_EPS, gamma.detach(), beta.detach(), y, relu=True)
+        return sv
+    sv.mean = rm.detach().float().view(1, -1).contiguous()
+    sv.rstd = torch.rsqrt(rv.detach().float() + BN_EPS).view(1, -1).contiguous()
+    sv.groups = 1
     ops.bn_relu_apply(rv_, sv.groups, sv.mean, sv.rstd, gamma.detach(), beta.detach(), y, relu=True)
     return sv
 
@@ -457,11 +456,10 @@ def unit_bwd(layer: ConvLayer, gamma, beta, sv: UnitSaved, x: View, y: View, gy:
     Cout = sv.raw.shape[-1]
     raw = View(sv.raw)
     ws = zeros_f32((sv.groups, 2, Cout), dev)
-    ops.bn_relu_bwd_reduce(gy, y, raw, sv.groups, sv.mean, sv.rstd, ws, relu=True)
     draw = torch.empty_like(sv.raw)
     dgamma, d1 = grad_buf(gamma)
     dbeta, d2 = grad_buf(beta)
-    ops.bn_relu_bwd_apply(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
+    ops.bn_relu_bwd_fused(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
     dw, d0 = grad_buf(layer.weight)
     if isinstance(layer, StemLayer):
         assert dx is None, "the few-channel stem does not propagate a gradient to its input"
@@ -581,19 +579,17 @@ def bn_fwd_part(raw: View, m, y: View, g: int):
     ws = zeros_f32((g, 2, C), raw.t.device)
     mean = torch.empty((g, C), dtype=torch.float32, device=raw.t.device)
     rstd = torch.empty((g, C), dtype=torch.float32, device=raw.t.device)
-    ops.bn_sums(raw, g, ws)
-    ops.bn_finalize(ws, C, 0, C, g, raw.rows // g, mean, rstd, m.bn.running_mean, m.bn.running_var, BN_MOMENTUM, BN_EPS)
-    ops.bn_relu_apply(raw, g, mean, rstd, m.bn.weight.detach(), m.bn.bias.detach(), y, relu=True)
+    ops.bn_relu_fwd_fused(raw, g, ws, mean, rstd, m.bn.running_mean, m.bn.running_var, BN_MOMENTUM, BN_EPS, m.bn.weight.detach(),
+                          m.bn.bias.detach(), y, relu=True)
     return mean, rstd
 
 
 def bn_bwd_part(raw: View, y: View, gy: View, draw: View, m, mean, rstd, g: int):
     """Backward of bn_fwd_part: writes d(raw) into `draw`; returns (dgamma, dbeta) (None where accumulated into .grad)."""
     ws = zeros_f32((g, 2, raw.C), raw.t.device)
-    ops.bn_relu_bwd_reduce(gy, y, raw, g, mean, rstd, ws, relu=True)
     dgamma, d1 = grad_buf(m.bn.weight)
     dbeta, d2 = grad_buf(m.bn.bias)
-    ops.bn_relu_bwd_apply(gy, y, raw, g, mean, rstd, m.bn.weight.detach(), ws, draw, dgamma, dbeta, relu=True)
+    ops.bn_relu_bwd_fused(gy, y, raw, g, mean, rstd, m.bn.weight.detach(), ws, draw, dgamma, dbeta, relu=True)
     return (None if d1 else dgamma), (None if d2 else dbeta)
 
 

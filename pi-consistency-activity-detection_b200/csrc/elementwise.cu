@@ -4,6 +4,8 @@
 // moves 16-byte (8-channel) vectors; reductions go warp/registers -> shared -> one fp32 atomic per
 // block and channel.
 #include "common.cuh"
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "../../include/b200caps.h"
 
 long long b2c_launches_add(long long n);
@@ -320,6 +322,204 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused train-mode BatchNorm (r02d): statistics -> grid barrier -> finalize -> apply in ONE cooperative launch, and the
+// same for the backward (reduce -> barrier -> apply).  45 layers x (3 + 2) launches of 8..14 us each (latency bound: one
+// or two 16-byte loads per thread, ncu r02b) become 45 x 2; the second pass re-reads the tensor from L2 (all but the
+// three largest layers fit).  Same arithmetic as the separate kernels above (which remain for deterministic mode).
+struct BnFwdArgs {
+  long long rows_per_group, x_rs, y_rs;
+  int C, x_co, y_co, relu, groups;
+  float momentum, eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) bn_fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ ws,
+                                                              float* __restrict__ mean, float* __restrict__ rstd,
+                                                              float* running_mean, float* running_var,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              BnFwdArgs A) {
+  const int C = A.C, CV = C / 8;
+  const RowMap m = row_map(CV);
+  const int g = blockIdx.y;
+  const long long row0 = (long long)g * A.rows_per_group;
+  extern __shared__ float sh[];  // [rpb][2][C]
+  {
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (m.active) {
+      const T* base = x + row0 * A.x_rs + A.x_co + m.cv * 8;
+#pragma unroll 4
+      for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
+        float v[8];
+        ld8(base + r * A.x_rs, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += v[j];
+          s2[j] += v[j] * v[j];
+        }
+      }
+      float* mine = sh + (size_t)m.rlane * 2 * C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mine[m.cv * 8 + j] = s1[j];
+        mine[C + m.cv * 8 + j] = s2[j];
+      }
+    }
+    __syncthreads();
+    float* w = ws + (long long)g * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * C + i];
+      atomicAdd(&w[i], t);
+    }
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  // finalize (same double-precision arithmetic as bn_finalize_kernel); the sums live in L2 (atomics): bypass L1
+  const double M = (double)A.rows_per_group;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && running_mean) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float rm = running_mean[c], rv = running_var[c];
+      for (int gg = 0; gg < A.groups; ++gg) {
+        const double s1 = __ldcg(ws + (long long)gg * 2 * C + c), s2 = __ldcg(ws + (long long)gg * 2 * C + C + c);
+        const double mu = s1 / M;
+        double var = s2 / M - mu * mu;
+        if (var < 0) var = 0;
+        const double unb = A.rows_per_group > 1 ? var * M / (M - 1.0) : var;
+        rm = (1.f - A.momentum) * rm + A.momentum * (float)mu;
+        rv = (1.f - A.momentum) * rv + A.momentum * (float)unb;
+      }
+      running_mean[c] = rm;
+      running_var[c] = rv;
+    }
+  }
+  if (!m.active) return;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = m.cv * 8 + j;
+    const double s1 = __ldcg(ws + (long long)g * 2 * C + c), s2 = __ldcg(ws + (long long)g * 2 * C + C + c);
+    const double mu = s1 / M;
+    double var = s2 / M - mu * mu;
+    if (var < 0) var = 0;
+    const float muf = (float)mu, rsf = (float)(1.0 / sqrt(var + (double)A.eps));
+    if (blockIdx.x == 0 && m.rlane == 0) {
+      mean[g * C + c] = muf;
+      rstd[g * C + c] = rsf;
+    }
+    sc[j] = rsf * gamma[c];
+    sf[j] = beta[c] - muf * sc[j];
+  }
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
+    float v[8];
+    ld8(x + (row0 + r) * A.x_rs + A.x_co + m.cv * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = v[j] * sc[j] + sf[j];
+      if (A.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    st8(y + (row0 + r) * A.y_rs + A.y_co + m.cv * 8, v, true);
+  }
+}
+
+struct BnBwdArgs {
+  long long rows_per_group, dy_rs, y_rs, x_rs, dx_rs;
+  int C, dy_co, y_co, x_co, dx_co, relu, groups;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock, 3) bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
+                                                              T* __restrict__ dx, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                              float* __restrict__ ws, float* dgamma, float* dbeta, BnBwdArgs A) {
+  const int C = A.C, CV = C / 8;
+  const RowMap m = row_map(CV);
+  const int g = blockIdx.y;
+  const long long row0 = (long long)g * A.rows_per_group;
+  const bool relu = A.relu != 0;
+  extern __shared__ float sh[];  // [rpb][2][C]
+  float mu[8], rs[8];
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean[g * C + m.cv * 8 + j];
+      rs[j] = rstd[g * C + m.cv * 8 + j];
+    }
+  }
+  {
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (m.active) {
+#pragma unroll 2
+      for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
+        float d[8], yy[8], xx[8];
+        ld8(dy + (row0 + r) * A.dy_rs + A.dy_co + m.cv * 8, d);
+        ld8(x + (row0 + r) * A.x_rs + A.x_co + m.cv * 8, xx);
+        if (relu) ld8(y + (row0 + r) * A.y_rs + A.y_co + m.cv * 8, yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
+          s1[j] += dr;
+          s2[j] += dr * (xx[j] - mu[j]) * rs[j];
+        }
+      }
+      float* mine = sh + (size_t)m.rlane * 2 * C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mine[m.cv * 8 + j] = s1[j];
+        mine[C + m.cv * 8 + j] = s2[j];
+      }
+    }
+    __syncthreads();
+    float* w = ws + (long long)g * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * C + i];
+      atomicAdd(&w[i], t);
+    }
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f, b = 0.f;
+      for (int gg = 0; gg < A.groups; ++gg) {
+        b += __ldcg(ws + (long long)gg * 2 * C + c);
+        a += __ldcg(ws + (long long)gg * 2 * C + C + c);
+      }
+      dgamma[c] += a;
+      dbeta[c] += b;
+    }
+  }
+  if (!m.active) return;
+  const float invM = 1.f / (float)A.rows_per_group;
+  float k0[8], a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = m.cv * 8 + j;
+    k0[j] = gamma[c] * rs[j];
+    a1[j] = __ldcg(ws + (long long)g * 2 * C + c) * invM;
+    a2[j] = __ldcg(ws + (long long)g * 2 * C + C + c) * invM;
+  }
+#pragma unroll 2
+  for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
+    float d[8], yy[8], xx[8], o[8];
+    ld8(dy + (row0 + r) * A.dy_rs + A.dy_co + m.cv * 8, d);
+    ld8(x + (row0 + r) * A.x_rs + A.x_co + m.cv * 8, xx);
+    if (relu) ld8(y + (row0 + r) * A.y_rs + A.y_co + m.cv * 8, yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
+      o[j] = k0[j] * (dr - a1[j] - (xx[j] - mu[j]) * rs[j] * a2[j]);
+    }
+    st8(dx + (row0 + r) * A.dx_rs + A.dx_co + m.cv * 8, o, true);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct PoolGeom {
   int N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw;
 };
@@ -500,6 +700,181 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_kernel(const T* __restrict
       ld8(dst, e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += e[j];
+    }
+    st8(dst, acc, false);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Specialised max-pool kernels (r02d).  The generic kernels above decode (n, t, h, w, cv) from a flat index and walk
+// runtime window extents: ncu r02b showed them ISSUE bound (73 % issue slots, ~580 instructions per thread, most of them
+// emulated integer divisions) at 1 TB/s.  Here the window (KT,KH,KW) and strides are template parameters, one CTA owns
+// one output row (fwd) / input row (bwd) through a 3-D grid -- no division except one multiply-shift per thread -- and
+// the tap loops unroll.  Same semantics bit for bit (strict '>', first occurrence in (t,h,w) tap order, the first
+// padding zero is a candidate with index 0xff).
+struct PoolRowGeom {
+  int C, CV, Ti, Hi, Wi, To, Ho, Wo, pt, ph, pw;
+  uint32_t cv_magic;   // floor(2^32 / CV) + 1: e / CV = umulhi(e, cv_magic) for e * CV < 2^32
+};
+
+template <typename T, int KT, int KH, int KW, int ST, int SH, int SW>
+__global__ void __launch_bounds__(kBlock) maxpool_fwd_row_kernel(const T* __restrict__ x, long long x_rs, int x_co, T* __restrict__ y,
+                                                                 long long y_rs, int y_co, uint8_t* __restrict__ idx, PoolRowGeom G) {
+  const int oh = blockIdx.x, ot = blockIdx.y, n = blockIdx.z;
+  const long long orow0 = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo;
+  const int total = G.Wo * G.CV;
+  for (int e = threadIdx.x; e < total; e += kBlock) {
+    const int ow = (int)__umulhi((uint32_t)e, G.cv_magic);
+    const int cv = e - ow * G.CV;
+    bool seen_pad = false;
+    if constexpr (sizeof(T) == 2) {
+      uint32_t best2[4], idx2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        best2[j] = 0xff80ff80u;   // (-inf, -inf)
+        idx2[j] = 0x00ff00ffu;
+      }
+#pragma unroll
+      for (int a = 0; a < KT; ++a) {
+        const int it = ot * ST - G.pt + a;
+#pragma unroll
+        for (int b = 0; b < KH; ++b) {
+          const int ih = oh * SH - G.ph + b;
+          const bool row_ok = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi;
+          const bf16* xrow = x + (((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi * x_rs + x_co + cv * 8;
+#pragma unroll
+          for (int c = 0; c < KW; ++c) {
+            constexpr int kDummy = 0;
+            (void)kDummy;
+            const int tap = (a * KH + b) * KW + c;
+            const int iw = ow * SW - G.pw + c;
+            const bool inb = row_ok && (unsigned)iw < (unsigned)G.Wi;
+            if (!inb) {
+              if (seen_pad) continue;
+              seen_pad = true;
+            }
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (inb) raw = ld16(reinterpret_cast<const bf16*>(xrow) + (long long)iw * x_rs);
+            const uint32_t t2 = inb ? ((uint32_t)tap | ((uint32_t)tap << 16)) : 0x00ff00ffu;
+            const uint32_t rv[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&rv[j]),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&best2[j]));
+              best2[j] = (rv[j] & m) | (best2[j] & ~m);
+              idx2[j] = (t2 & m) | (idx2[j] & ~m);
+            }
+          }
+        }
+      }
+      st16(reinterpret_cast<bf16*>(y) + (orow0 + ow) * y_rs + y_co + cv * 8, make_uint4(best2[0], best2[1], best2[2], best2[3]));
+      uint2 pk;
+      pk.x = __byte_perm(idx2[0], idx2[1], 0x6420);
+      pk.y = __byte_perm(idx2[2], idx2[3], 0x6420);
+      *reinterpret_cast<uint2*>(idx + (orow0 + ow) * G.C + cv * 8) = pk;
+    } else {
+      float best[8];
+      uint32_t bidx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        best[j] = __int_as_float(0xff800000);
+        bidx[j] = 0xffu;
+      }
+#pragma unroll
+      for (int a = 0; a < KT; ++a) {
+        const int it = ot * ST - G.pt + a;
+#pragma unroll
+        for (int b = 0; b < KH; ++b) {
+          const int ih = oh * SH - G.ph + b;
+          const bool row_ok = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi;
+          const T* xrow = x + (((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi * x_rs + x_co + cv * 8;
+#pragma unroll
+          for (int c = 0; c < KW; ++c) {
+            const int tap = (a * KH + b) * KW + c;
+            const int iw = ow * SW - G.pw + c;
+            const bool inb = row_ok && (unsigned)iw < (unsigned)G.Wi;
+            if (!inb) {
+              if (seen_pad) continue;
+              seen_pad = true;
+            }
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            if (inb) ld8(xrow + (long long)iw * x_rs, v);
+            const uint32_t t = inb ? (uint32_t)tap : 0xffu;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (v[j] > best[j]) {
+                best[j] = v[j];
+                bidx[j] = t;
+              }
+          }
+        }
+      }
+      st8(y + (orow0 + ow) * y_rs + y_co + cv * 8, best, false);
+      uint2 pk;
+      pk.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+      pk.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+      *reinterpret_cast<uint2*>(idx + (orow0 + ow) * G.C + cv * 8) = pk;
+    }
+  }
+}
+
+// one CTA per input row; a thread visits the (at most ceil(K/S) per dimension) output windows that contain its position
+template <typename T, int KT, int KH, int KW, int ST, int SH, int SW>
+__global__ void __launch_bounds__(kBlock) maxpool_bwd_row_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
+                                                                 const uint8_t* __restrict__ idx, T* __restrict__ dx, long long dx_rs,
+                                                                 int dx_co, PoolRowGeom G, int accumulate) {
+  constexpr int MT = (KT + ST - 1) / ST, MH = (KH + SH - 1) / SH, MW = (KW + SW - 1) / SW;
+  const int ih = blockIdx.x, it = blockIdx.y, n = blockIdx.z;
+  const long long irow0 = (((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi;
+  const int ot_hi = min((it + G.pt) / ST, G.To - 1), ot_lo = max((it + G.pt - KT + ST) / ST, 0);
+  const int oh_hi = min((ih + G.ph) / SH, G.Ho - 1), oh_lo = max((ih + G.ph - KH + SH) / SH, 0);
+  const int total = G.Wi * G.CV;
+  for (int e = threadIdx.x; e < total; e += kBlock) {
+    const int iw = (int)__umulhi((uint32_t)e, G.cv_magic);
+    const int cv = e - iw * G.CV;
+    const int ow_hi = min((iw + G.pw) / SW, G.Wo - 1), ow_lo = max((iw + G.pw - KW + SW) / SW, 0);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int qt = 0; qt < MT; ++qt) {
+      const int ot = ot_lo + qt;
+      if (ot > ot_hi) break;
+      const int a = it + G.pt - ot * ST;
+#pragma unroll
+      for (int qh = 0; qh < MH; ++qh) {
+        const int oh = oh_lo + qh;
+        if (oh > oh_hi) break;
+        const int b = ih + G.ph - oh * SH;
+        const long long orow0 = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo;
+#pragma unroll
+        for (int qw = 0; qw < MW; ++qw) {
+          const int ow = ow_lo + qw;
+          if (ow <= ow_hi) {
+            const int c = iw + G.pw - ow * SW;
+            const uint32_t tap = (uint32_t)((a * KH + b) * KW + c);
+            const long long orow = orow0 + ow;
+            const uint2 pk = *reinterpret_cast<const uint2*>(idx + orow * G.C + cv * 8);
+            float d[8];
+            ld8(dy + orow * dy_rs + dy_co + cv * 8, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t w = j < 4 ? pk.x : pk.y;
+              const uint32_t bi = (w >> ((j & 3) * 8)) & 0xffu;
+              if (bi == tap) acc[j] += d[j];
+            }
+          }
+        }
+      }
+    }
+    T* dst = dx + (irow0 + iw) * dx_rs + dx_co + cv * 8;
+    if (accumulate) {
+      float ev[8];
+      ld8(dst, ev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += ev[j];
     }
     st8(dst, acc, false);
   }
@@ -904,6 +1279,7 @@ inline int grid_for(long long work_items, int per_block = kBlock, int waves = 8)
 // deterministic mode (tests): cross-block fp32 atomics of the BatchNorm reductions are avoided by using ONE block per
 // statistic group, so two runs -- or two schedules of the same step -- produce bit-identical activations.
 static int g_deterministic = 0;
+static int g_pool_generic = -1;   // 1: generic max-pool kernels even where a specialisation exists (tests compare the two)
 inline size_t bn_red_smem(int C) {
   int rpb = kBlock / (C / 8);
   if (rpb < 1) rpb = 1;
@@ -926,6 +1302,24 @@ inline int row_grid(long long rows, int C, int waves = 4) {
       KERNEL<T><<<GRID, BLOCK, SMEM, (cudaStream_t)(STREAM)>>>(__VA_ARGS__);               \
     }                                                                                      \
   } while (0)
+
+// geometry of the specialised (row-per-CTA) pooling kernels; returns 0 when the configuration has no specialisation
+// (B2C_POOL_GENERIC=1 forces the generic kernels), else the index of the instantiated (window, stride) pair
+inline int pool_row_geom(PoolRowGeom& R, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo, int kt, int kh, int kw, int st,
+                         int sh, int sw, int pt, int ph, int pw, int Wthreads) {
+  if (g_pool_generic < 0) {
+    const char* e = getenv("B2C_POOL_GENERIC");
+    g_pool_generic = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int generic = g_pool_generic;
+  const int CV = C / 8;
+  R = PoolRowGeom{C, CV, Ti, Hi, Wi, To, Ho, Wo, pt, ph, pw, (uint32_t)((1ULL << 32) / (unsigned)CV + 1)};
+  if (generic || N > 65535 || Ti > 65535 || To > 65535 || (long long)Wthreads * CV * CV >= (1LL << 31)) return 0;
+  if (kt == 1 && kh == 3 && kw == 3 && st == 1 && sh == 2 && sw == 2) return 1;
+  if (kt == 3 && kh == 3 && kw == 3 && st == 2 && sh == 1 && sw == 1) return 2;
+  if (kt == 3 && kh == 3 && kw == 3 && st == 1 && sh == 1 && sw == 1) return 3;
+  return 0;
+}
 
 #define CHECK_VIEW(name, C, rs, co)                                                                         \
   B2C_REQUIRE((C) > 0 && (C) % 8 == 0 && (rs) % 8 == 0 && (co) % 8 == 0 && (C) / 8 <= kBlock, name ": bad view C=%d rs=%lld co=%d", \
@@ -1051,6 +1445,76 @@ B2C_API int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_rs, int32_t dy_co, 
   return 0;
 }
 
+// cooperative launch of a fused BatchNorm kernel: the grid must be co-resident (grid barrier)
+template <typename K>
+static int bn_coop_launch(K kernel, const char* what, long long rpg, int C, int groups, size_t smem, void** args, b2c_stream_t s) {
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
+  if (e != cudaSuccess) return b2c_cuda_check(e, what);
+  long long cap = (long long)per_sm * b2c_num_sms() / groups;
+  B2C_REQUIRE(cap >= 1, "%s: no co-resident grid for C=%d groups=%d", what, C, groups);
+  long long gx = row_grid(rpg, C, 3);
+  if (gx > cap) gx = cap;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)gx, (unsigned)groups, 1);
+  cfg.blockDim = dim3(kBlock, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
+  if (e != cudaSuccess) return b2c_cuda_check(e, what);
+  b2c_launches_add(1);
+  return 0;
+}
+
+B2C_API int b2c_bn_relu_fwd_fused(const void* x, int64_t rows, int32_t C, int64_t x_rs, int32_t x_co, int32_t groups, float* ws,
+                                  float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
+                                  const float* gamma, const float* beta, void* y, int64_t y_rs, int32_t y_co, int32_t relu,
+                                  b2c_stream_t s) {
+  B2C_REQUIRE(x && y && ws && mean && rstd && gamma && beta, "bn_relu_fwd_fused: null pointer");
+  CHECK_VIEW("bn_relu_fwd_fused", C, x_rs, x_co);
+  CHECK_VIEW("bn_relu_fwd_fused(y)", C, y_rs, y_co);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_relu_fwd_fused: rows not divisible by groups");
+  if (g_deterministic) {   // tests: fixed-order reductions with the separate kernels
+    int rc = b2c_bn_sums(x, rows, C, x_rs, x_co, groups, ws, s);
+    if (rc == 0) rc = b2c_bn_finalize(ws, C, 0, C, groups, rows / groups, mean, rstd, running_mean, running_var, momentum, eps, s);
+    if (rc == 0) rc = b2c_bn_relu_apply(x, rows, C, x_rs, x_co, groups, mean, rstd, gamma, beta, y, y_rs, y_co, relu, s);
+    return rc;
+  }
+  BnFwdArgs A{rows / groups, x_rs, y_rs, C, x_co, y_co, relu, groups, momentum, eps};
+  void* args[] = {(void*)&x, (void*)&y, (void*)&ws, (void*)&mean, (void*)&rstd, (void*)&running_mean, (void*)&running_var,
+                  (void*)&gamma, (void*)&beta, (void*)&A};
+  if (b2c_precision()) return bn_coop_launch(bn_fwd_fused_kernel<float>, "bn_relu_fwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
+  return bn_coop_launch(bn_fwd_fused_kernel<bf16>, "bn_relu_fwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
+}
+
+B2C_API int b2c_bn_relu_bwd_fused(const void* dy, int64_t dy_rs, int32_t dy_co, const void* y, int64_t y_rs, int32_t y_co,
+                                  const void* x, int64_t x_rs, int32_t x_co, int64_t rows, int32_t C, int32_t groups,
+                                  const float* mean, const float* rstd, const float* gamma, float* ws, void* dx, int64_t dx_rs,
+                                  int32_t dx_co, float* dgamma, float* dbeta, int32_t relu, b2c_stream_t s) {
+  B2C_REQUIRE(dy && x && dx && mean && rstd && gamma && ws && (y || !relu), "bn_relu_bwd_fused: null pointer");
+  CHECK_VIEW("bn_relu_bwd_fused(dy)", C, dy_rs, dy_co);
+  CHECK_VIEW("bn_relu_bwd_fused(x)", C, x_rs, x_co);
+  CHECK_VIEW("bn_relu_bwd_fused(dx)", C, dx_rs, dx_co);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_relu_bwd_fused: rows not divisible by groups");
+  if (g_deterministic) {
+    int rc = b2c_bn_relu_bwd_reduce(dy, dy_rs, dy_co, y, y_rs, y_co, x, x_rs, x_co, rows, C, groups, mean, rstd, ws, relu, s);
+    if (rc == 0)
+      rc = b2c_bn_relu_bwd_apply(dy, dy_rs, dy_co, y, y_rs, y_co, x, x_rs, x_co, rows, C, groups, mean, rstd, gamma, ws, dx, dx_rs,
+                                 dx_co, dgamma, dbeta, relu, s);
+    return rc;
+  }
+  BnBwdArgs A{rows / groups, dy_rs, y_rs, x_rs, dx_rs, C, dy_co, y_co, x_co, dx_co, relu, groups};
+  void* args[] = {(void*)&dy, (void*)&y, (void*)&x, (void*)&dx, (void*)&mean, (void*)&rstd, (void*)&gamma, (void*)&ws,
+                  (void*)&dgamma, (void*)&dbeta, (void*)&A};
+  if (b2c_precision()) return bn_coop_launch(bn_bwd_fused_kernel<float>, "bn_relu_bwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
+  return bn_coop_launch(bn_bwd_fused_kernel<bf16>, "bn_relu_bwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
+}
+
 B2C_API int b2c_maxpool_fwd(const void* x, int64_t x_rs, int32_t x_co, void* y, int64_t y_rs, int32_t y_co, uint8_t* idx, int32_t N,
                             int32_t C, int32_t Ti, int32_t Hi, int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, int32_t kt, int32_t kh,
                             int32_t kw, int32_t st, int32_t sh, int32_t sw, int32_t pt, int32_t ph, int32_t pw, b2c_stream_t s) {
@@ -1061,10 +1525,26 @@ B2C_API int b2c_maxpool_fwd(const void* x, int64_t x_rs, int32_t x_co, void* y, 
   PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
   const long long total = (long long)N * To * Ho * Wo * (C / 8);
   B2C_REQUIRE(total < (1LL << 31) - (1LL << 22) && (long long)N * Ti * Hi * Wi * (C / 8) < (1LL << 31), "maxpool_fwd: tensor too large");
-  if (b2c_precision())
+  PoolRowGeom R;
+  const int spec = pool_row_geom(R, N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, Wo);
+  const dim3 rgrid((unsigned)Ho, (unsigned)To, (unsigned)N);
+#define B2C_POOL_FWD(KT_, KH_, KW_, ST_, SH_, SW_)                                                                                  \
+  do {                                                                                                                             \
+    if (b2c_precision())                                                                                                           \
+      maxpool_fwd_row_kernel<float, KT_, KH_, KW_, ST_, SH_, SW_><<<rgrid, kBlock, 0, (cudaStream_t)s>>>((const float*)x, x_rs, x_co, \
+                                                                                                         (float*)y, y_rs, y_co, idx, R); \
+    else                                                                                                                           \
+      maxpool_fwd_row_kernel<bf16, KT_, KH_, KW_, ST_, SH_, SW_><<<rgrid, kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, x_rs, x_co,   \
+                                                                                                        (bf16*)y, y_rs, y_co, idx, R);  \
+  } while (0)
+  if (spec == 1) B2C_POOL_FWD(1, 3, 3, 1, 2, 2);
+  else if (spec == 2) B2C_POOL_FWD(3, 3, 3, 2, 1, 1);
+  else if (spec == 3) B2C_POOL_FWD(3, 3, 3, 1, 1, 1);
+  else if (b2c_precision())
     maxpool_fwd_f32_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const float*)x, x_rs, x_co, (float*)y, y_rs, y_co, idx, G);
   else
     maxpool_fwd_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const bf16*)x, x_rs, x_co, (bf16*)y, y_rs, y_co, idx, G);
+#undef B2C_POOL_FWD
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("maxpool_fwd");
   return 0;
@@ -1080,7 +1560,24 @@ B2C_API int b2c_maxpool_bwd(const void* dy, int64_t dy_rs, int32_t dy_co, const 
   PoolGeom G{N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw};
   const long long total = (long long)N * Ti * Hi * Wi * (C / 8);
   B2C_REQUIRE(total < (1LL << 31) - (1LL << 22), "maxpool_bwd: tensor too large");
-  LAUNCH_T(maxpool_bwd_kernel, grid_for(total), kBlock, 0, s, (const T*)dy, dy_rs, dy_co, idx, (T*)dx, dx_rs, dx_co, G, accumulate);
+  PoolRowGeom R;
+  const int spec = pool_row_geom(R, N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, Wi);
+  const dim3 rgrid((unsigned)Hi, (unsigned)Ti, (unsigned)N);
+#define B2C_POOL_BWD(KT_, KH_, KW_, ST_, SH_, SW_)                                                                       \
+  do {                                                                                                                  \
+    if (b2c_precision())                                                                                                \
+      maxpool_bwd_row_kernel<float, KT_, KH_, KW_, ST_, SH_, SW_><<<rgrid, kBlock, 0, (cudaStream_t)s>>>(                 \
+          (const float*)dy, dy_rs, dy_co, idx, (float*)dx, dx_rs, dx_co, R, accumulate);                                \
+    else                                                                                                                \
+      maxpool_bwd_row_kernel<bf16, KT_, KH_, KW_, ST_, SH_, SW_><<<rgrid, kBlock, 0, (cudaStream_t)s>>>(                  \
+          (const bf16*)dy, dy_rs, dy_co, idx, (bf16*)dx, dx_rs, dx_co, R, accumulate);                                  \
+  } while (0)
+  if (spec == 1) B2C_POOL_BWD(1, 3, 3, 1, 2, 2);
+  else if (spec == 2) B2C_POOL_BWD(3, 3, 3, 2, 1, 1);
+  else if (spec == 3) B2C_POOL_BWD(3, 3, 3, 1, 1, 1);
+  else
+    LAUNCH_T(maxpool_bwd_kernel, grid_for(total), kBlock, 0, s, (const T*)dy, dy_rs, dy_co, idx, (T*)dx, dx_rs, dx_co, G, accumulate);
+#undef B2C_POOL_BWD
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("maxpool_bwd");
   return 0;
@@ -1245,6 +1742,11 @@ B2C_API int b2c_im2col_small(const void* x, void* out, int32_t N, int32_t Cs, in
   }
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("im2col_small");
+  return 0;
+}
+
+B2C_API int b2c_set_pool_generic(int32_t on) {
+  g_pool_generic = on ? 1 : 0;
   return 0;
 }
 

@@ -77,6 +77,19 @@ def test_batchnorm_relu_fwd_bwd(C, groups):
     ops.bn_relu_bwd_apply(View(gy), View(y, C, C), xv, groups, mean, rstd, gamma, ws2, View(dx), dg, db, relu=True)
     # relu mask may differ where y ~ 0 in bf16; compare with a tolerance on the bulk
     assert rel(dx, gx_ref) < 3e-2
+    # the fused cooperative launches (statistics -> grid barrier -> apply) give the same results as the separate kernels
+    rm2, rv2 = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    ws3 = torch.zeros(groups, 2, C, device=dev())
+    mean2, rstd2 = torch.empty_like(mean), torch.empty_like(rstd)
+    y2 = torch.zeros_like(y)
+    ops.bn_relu_fwd_fused(xv, groups, ws3, mean2, rstd2, rm2, rv2, 0.01, 1e-3, gamma, beta, View(y2, C, C), relu=True)
+    assert rel(mean2, mean) < 1e-5 and rel(rstd2, rstd) < 1e-5 and rel(rm2, rm) < 1e-5 and rel(rv2, rv) < 1e-5
+    assert rel(y2[..., C:], y[..., C:]) < 1e-2 and float(y2[..., :C].abs().max()) == 0
+    ws4 = torch.zeros(groups, 2, C, device=dev())
+    dx2 = torch.empty_like(x)
+    dg2, db2 = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    ops.bn_relu_bwd_fused(View(gy), View(y, C, C), xv, groups, mean, rstd, gamma, ws4, View(dx2), dg2, db2, relu=True)
+    assert rel(dx2, dx) < 1e-2 and rel(dg2, dg) < 1e-4 and rel(db2, db) < 1e-4
 
 
 @pytest.mark.parametrize("k,s,dims", [((1, 3, 3), (1, 2, 2), (2, 12, 12)), ((3, 3, 3), (1, 1, 1), (2, 7, 7)),
@@ -97,6 +110,45 @@ def test_maxpool_same(k, s, dims):
     # ties at exactly 0 route gradient differently (irrelevant after the ReLU mask); compare where x > 0
     m = (xr > 0).permute(0, 2, 3, 4, 1)
     assert float(((gx.float().cpu() - gxr.permute(0, 2, 3, 4, 1)) * m).abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("k,s,dims,C", [((1, 3, 3), (1, 2, 2), (3, 23, 30), 72), ((3, 3, 3), (1, 1, 1), (1, 9, 11), 40),
+                                        ((3, 3, 3), (1, 1, 1), (3, 8, 8), 24), ((3, 3, 3), (2, 1, 1), (4, 7, 9), 48),
+                                        ((1, 3, 3), (1, 2, 2), (2, 16, 16), 8)])
+def test_maxpool_row_kernels_equal_generic(k, s, dims, C):
+    """The (window, stride)-specialised row-per-CTA pooling kernels give bit-identical outputs, argmax indices and input
+    gradients (plain and accumulating) to the generic kernels, which are checked against the oracle above; both also
+    against the oracle here (forward bit-exact).  Channel counts with C/8 not a power of two exercise the multiply-shift
+    index split; many exact zeros exercise the first-occurrence / padding-candidate rules."""
+    from b200caps import engine, ops
+    from oracle import restate
+    torch.manual_seed(3)
+    x = torch.relu(torch.randn((3, C) + dims, device=dev())).bfloat16()
+    yr = restate.maxpool_same(x.float().cpu(), k, s)
+    outs = []
+    g = None
+    try:
+        for generic in (True, False):
+            ops.set_pool_generic(generic)
+            xc = engine.to_cl(x).detach().requires_grad_(True)
+            y = engine.MaxPoolFn.apply(xc, k, s)
+            if g is None:
+                g = torch.randn(y.shape, device=dev()).bfloat16()
+            (gx,) = torch.autograd.grad(y, xc, g)
+            # accumulating variant (Inception backward adds the pool branch into the block's input gradient)
+            pads = [engine.same_pad(d, kk, ss) for d, kk, ss in zip(dims, k, s)]
+            yv = torch.empty_like(y.detach())
+            idx = torch.empty(y.shape, dtype=torch.uint8, device=dev())
+            ops.maxpool_fwd(engine.View(xc.detach()), engine.View(yv), idx, k, s, tuple(p[0] for p in pads))
+            acc = torch.full_like(xc.detach(), 0.5)
+            ops.maxpool_bwd(engine.View(g.contiguous()), idx, engine.View(acc), k, s, tuple(p[0] for p in pads), accumulate=True)
+            outs.append((y.detach().clone(), gx.clone(), idx.clone(), acc.clone()))
+    finally:
+        ops.set_pool_generic(False)
+    assert rel(outs[1][0].permute(0, 4, 1, 2, 3), yr) == 0
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
 
 
 def test_em_routing_matches_reference_golden():
