@@ -177,19 +177,6 @@ int b2c_stem_fold_weights(const float* w, float* w2, int32_t Cout, int32_t Cin, 
 int b2c_stem_unfold_wgrad(const float* dw2, float* dw, int32_t Cout, int32_t Cin, int32_t kt, int32_t khw, int32_t st, int32_t To,
                           int32_t Kf, b2c_stream_t s);
 
-/* Fused train-mode BatchNorm3d + ReLU (pytorch_i3d.py:80,117-119) as ONE cooperative launch each way: statistics ->
- * grid barrier -> mean / rstd / running stats -> normalise + ReLU into the view y; and dy -> (dgamma, dbeta sums) ->
- * grid barrier -> dx.  Same arguments and results as the separate kernels below (ws fp32 [groups][2][C] zeroed by the
- * caller; mean / rstd [groups][C] are outputs of the forward and inputs of the backward; dgamma / dbeta accumulate). */
-int b2c_bn_relu_fwd_fused(const void* x, int64_t rows, int32_t C, int64_t x_row_stride, int32_t x_c_off, int32_t groups, float* ws,
-                          float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
-                          const float* gamma, const float* beta, void* y, int64_t y_row_stride, int32_t y_c_off, int32_t relu,
-                          b2c_stream_t s);
-int b2c_bn_relu_bwd_fused(const void* dy, int64_t dy_row_stride, int32_t dy_c_off, const void* y, int64_t y_row_stride,
-                          int32_t y_c_off, const void* x, int64_t x_row_stride, int32_t x_c_off, int64_t rows, int32_t C,
-                          int32_t groups, const float* mean, const float* rstd, const float* gamma, float* ws, void* dx,
-                          int64_t dx_row_stride, int32_t dx_c_off, float* dgamma, float* dbeta, int32_t relu, b2c_stream_t s);
-
 /* BatchNorm3d training statistics (pytorch_i3d.py:80,117).  groups: rows are split evenly into
  * `groups` contiguous segments with independent statistics (two forward passes batched).
  * _sums: ws fp32 [groups][2][C] (zeroed by the caller) += per-channel sum / sum of squares.

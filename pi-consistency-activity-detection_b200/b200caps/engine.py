@@ -440,7 +440,7 @@ def unit_fwd(layer: ConvLayer, gamma, beta, rm, rv, x: View, y: View, training: 
         sv.mean = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
         sv.rstd = torch.empty((g, Cout), dtype=torch.float32, device=raw.device)
         sv.groups = g
-        ops.bn_relu_fwd_fused(rv_, g, ws, sv.mean, sv.rstd, rm, rv, BN_MOMENTUM, BN_EPS, gamma.detach(), beta.detach(), y, relu=True)
+        ops.bn_relu_fwd(rv_, g, ws, sv.mean, sv.rstd, rm, rv, BN_MOMENTUM, BN_EPS, gamma.detach(), beta.detach(), y, relu=True)
         return sv
     sv.mean = rm.detach().float().view(1, -1).contiguous()
     sv.rstd = torch.rsqrt(rv.detach().float() + BN_EPS).view(1, -1).contiguous()
@@ -459,7 +459,7 @@ def unit_bwd(layer: ConvLayer, gamma, beta, sv: UnitSaved, x: View, y: View, gy:
     draw = torch.empty_like(sv.raw)
     dgamma, d1 = grad_buf(gamma)
     dbeta, d2 = grad_buf(beta)
-    ops.bn_relu_bwd_fused(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
+    ops.bn_relu_bwd(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
     dw, d0 = grad_buf(layer.weight)
     if isinstance(layer, StemLayer):
         assert dx is None, "the few-channel stem does not propagate a gradient to its input"
@@ -579,7 +579,7 @@ def bn_fwd_part(raw: View, m, y: View, g: int):
     ws = zeros_f32((g, 2, C), raw.t.device)
     mean = torch.empty((g, C), dtype=torch.float32, device=raw.t.device)
     rstd = torch.empty((g, C), dtype=torch.float32, device=raw.t.device)
-    ops.bn_relu_fwd_fused(raw, g, ws, mean, rstd, m.bn.running_mean, m.bn.running_var, BN_MOMENTUM, BN_EPS, m.bn.weight.detach(),
+    ops.bn_relu_fwd(raw, g, ws, mean, rstd, m.bn.running_mean, m.bn.running_var, BN_MOMENTUM, BN_EPS, m.bn.weight.detach(),
                           m.bn.bias.detach(), y, relu=True)
     return mean, rstd
 
@@ -589,7 +589,7 @@ def bn_bwd_part(raw: View, y: View, gy: View, draw: View, m, mean, rstd, g: int)
     ws = zeros_f32((g, 2, raw.C), raw.t.device)
     dgamma, d1 = grad_buf(m.bn.weight)
     dbeta, d2 = grad_buf(m.bn.bias)
-    ops.bn_relu_bwd_fused(gy, y, raw, g, mean, rstd, m.bn.weight.detach(), ws, draw, dgamma, dbeta, relu=True)
+    ops.bn_relu_bwd(gy, y, raw, g, mean, rstd, m.bn.weight.detach(), ws, draw, dgamma, dbeta, relu=True)
     return (None if d1 else dgamma), (None if d2 else dbeta)
 
 

@@ -232,33 +232,20 @@ def stem_unfold_wgrad(dw2, dw, cout, cin, kt, khw, st, To, Kf):
 
 
 # ---- batch norm -----------------------------------------------------------------------------
-# B2C_BN_FUSED=1: one cooperative launch per direction (statistics -> grid barrier -> apply) instead of the separate
-# statistics / finalize / apply (and reduce / apply) launches.  Off by default: measured SLOWER on the step (graph mode
-# +1.3 ms, eager 1.58 -> 1.99 ms forward, 1.73 -> 2.18 ms backward over the 45 layers) -- a cooperative launch costs more
-# than the two ordinary launches it replaces.
-BN_FUSED = os.environ.get("B2C_BN_FUSED", "0") == "1"
+def bn_relu_fwd(x: View, groups, ws, mean, rstd, rm, rv, momentum, eps, gamma, beta, y: View, relu=True):
+    """Train-mode BatchNorm + ReLU of the view x into the view y: statistics, finalize (mean / rstd (groups, C) for the
+    backward, running stats), apply.  Three launches on purpose: a fused single launch with a grid barrier between the
+    statistics and the apply pass was built and measured slower in the captured step (cooperative launch 22.9 ms, ordinary
+    launch + hand-rolled barrier 22.2 ms, separate launches 21.5 ms per step: the barrier wait exceeds what the next
+    launch's overlap with this one's tail already hides)."""
+    bn_sums(x, groups, ws)
+    bn_finalize(ws, x.C, 0, x.C, groups, x.rows // groups, mean, rstd, rm, rv, momentum, eps)
+    bn_relu_apply(x, groups, mean, rstd, gamma, beta, y, relu)
 
 
-def bn_relu_fwd_fused(x: View, groups, ws, mean, rstd, rm, rv, momentum, eps, gamma, beta, y: View, relu=True):
-    """Train-mode BatchNorm + ReLU of the view x into the view y in one cooperative launch (statistics, running stats,
-    normalisation); mean / rstd (groups, C) are written for the backward."""
-    if not BN_FUSED:
-        bn_sums(x, groups, ws)
-        bn_finalize(ws, x.C, 0, x.C, groups, x.rows // groups, mean, rstd, rm, rv, momentum, eps)
-        bn_relu_apply(x, groups, mean, rstd, gamma, beta, y, relu)
-        return
-    _bw("b2c_bn_relu_fwd_fused", 2 * _vb(x), x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(ws), _p(mean), _p(rstd), _p(rm),
-        _p(rv), float(momentum), float(eps), _p(gamma), _p(beta), y.ptr, y.row_stride, y.c_off, int(relu), stream())
-
-
-def bn_relu_bwd_fused(dy: View, y: View, x: View, groups, mean, rstd, gamma, ws, dx: View, dgamma, dbeta, relu=True):
-    if not BN_FUSED:
-        bn_relu_bwd_reduce(dy, y, x, groups, mean, rstd, ws, relu)
-        bn_relu_bwd_apply(dy, y, x, groups, mean, rstd, gamma, ws, dx, dgamma, dbeta, relu)
-        return
-    _bw("b2c_bn_relu_bwd_fused", 4 * _vb(x), dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr, x.row_stride,
-        x.c_off, x.rows, x.C, groups, _p(mean), _p(rstd), _p(gamma), _p(ws), dx.ptr, dx.row_stride, dx.c_off, _p(dgamma), _p(dbeta),
-        int(relu), stream())
+def bn_relu_bwd(dy: View, y: View, x: View, groups, mean, rstd, gamma, ws, dx: View, dgamma, dbeta, relu=True):
+    bn_relu_bwd_reduce(dy, y, x, groups, mean, rstd, ws, relu)
+    bn_relu_bwd_apply(dy, y, x, groups, mean, rstd, gamma, ws, dx, dgamma, dbeta, relu)
 
 
 def bn_sums(x: View, groups: int, ws: torch.Tensor):

@@ -4,7 +4,6 @@
 // moves 16-byte (8-channel) vectors; reductions go warp/registers -> shared -> one fp32 atomic per
 // block and channel.
 #include "common.cuh"
-#include <cooperative_groups.h>
 #include <stdlib.h>
 #include "../../include/b200caps.h"
 
@@ -322,204 +321,6 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused train-mode BatchNorm (r02d): statistics -> grid barrier -> finalize -> apply in ONE cooperative launch, and the
-// same for the backward (reduce -> barrier -> apply).  45 layers x (3 + 2) launches of 8..14 us each (latency bound: one
-// or two 16-byte loads per thread, ncu r02b) become 45 x 2; the second pass re-reads the tensor from L2 (all but the
-// three largest layers fit).  Same arithmetic as the separate kernels above (which remain for deterministic mode).
-struct BnFwdArgs {
-  long long rows_per_group, x_rs, y_rs;
-  int C, x_co, y_co, relu, groups;
-  float momentum, eps;
-};
-
-template <typename T>
-__global__ void __launch_bounds__(kBlock) bn_fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ ws,
-                                                              float* __restrict__ mean, float* __restrict__ rstd,
-                                                              float* running_mean, float* running_var,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              BnFwdArgs A) {
-  const int C = A.C, CV = C / 8;
-  const RowMap m = row_map(CV);
-  const int g = blockIdx.y;
-  const long long row0 = (long long)g * A.rows_per_group;
-  extern __shared__ float sh[];  // [rpb][2][C]
-  {
-    float s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-    if (m.active) {
-      const T* base = x + row0 * A.x_rs + A.x_co + m.cv * 8;
-#pragma unroll 4
-      for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
-        float v[8];
-        ld8(base + r * A.x_rs, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] += v[j];
-          s2[j] += v[j] * v[j];
-        }
-      }
-      float* mine = sh + (size_t)m.rlane * 2 * C;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        mine[m.cv * 8 + j] = s1[j];
-        mine[C + m.cv * 8 + j] = s2[j];
-      }
-    }
-    __syncthreads();
-    float* w = ws + (long long)g * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-      float t = 0.f;
-      for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * C + i];
-      atomicAdd(&w[i], t);
-    }
-  }
-  __threadfence();
-  cooperative_groups::this_grid().sync();
-  // finalize (same double-precision arithmetic as bn_finalize_kernel); the sums live in L2 (atomics): bypass L1
-  const double M = (double)A.rows_per_group;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && running_mean) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float rm = running_mean[c], rv = running_var[c];
-      for (int gg = 0; gg < A.groups; ++gg) {
-        const double s1 = __ldcg(ws + (long long)gg * 2 * C + c), s2 = __ldcg(ws + (long long)gg * 2 * C + C + c);
-        const double mu = s1 / M;
-        double var = s2 / M - mu * mu;
-        if (var < 0) var = 0;
-        const double unb = A.rows_per_group > 1 ? var * M / (M - 1.0) : var;
-        rm = (1.f - A.momentum) * rm + A.momentum * (float)mu;
-        rv = (1.f - A.momentum) * rv + A.momentum * (float)unb;
-      }
-      running_mean[c] = rm;
-      running_var[c] = rv;
-    }
-  }
-  if (!m.active) return;
-  float sc[8], sf[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = m.cv * 8 + j;
-    const double s1 = __ldcg(ws + (long long)g * 2 * C + c), s2 = __ldcg(ws + (long long)g * 2 * C + C + c);
-    const double mu = s1 / M;
-    double var = s2 / M - mu * mu;
-    if (var < 0) var = 0;
-    const float muf = (float)mu, rsf = (float)(1.0 / sqrt(var + (double)A.eps));
-    if (blockIdx.x == 0 && m.rlane == 0) {
-      mean[g * C + c] = muf;
-      rstd[g * C + c] = rsf;
-    }
-    sc[j] = rsf * gamma[c];
-    sf[j] = beta[c] - muf * sc[j];
-  }
-#pragma unroll 4
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
-    float v[8];
-    ld8(x + (row0 + r) * A.x_rs + A.x_co + m.cv * 8, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = v[j] * sc[j] + sf[j];
-      if (A.relu) v[j] = fmaxf(v[j], 0.f);
-    }
-    st8(y + (row0 + r) * A.y_rs + A.y_co + m.cv * 8, v, true);
-  }
-}
-
-struct BnBwdArgs {
-  long long rows_per_group, dy_rs, y_rs, x_rs, dx_rs;
-  int C, dy_co, y_co, x_co, dx_co, relu, groups;
-};
-
-template <typename T>
-__global__ void __launch_bounds__(kBlock, 3) bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
-                                                              T* __restrict__ dx, const float* __restrict__ mean,
-                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                              float* __restrict__ ws, float* dgamma, float* dbeta, BnBwdArgs A) {
-  const int C = A.C, CV = C / 8;
-  const RowMap m = row_map(CV);
-  const int g = blockIdx.y;
-  const long long row0 = (long long)g * A.rows_per_group;
-  const bool relu = A.relu != 0;
-  extern __shared__ float sh[];  // [rpb][2][C]
-  float mu[8], rs[8];
-  if (m.active) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mu[j] = mean[g * C + m.cv * 8 + j];
-      rs[j] = rstd[g * C + m.cv * 8 + j];
-    }
-  }
-  {
-    float s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-    if (m.active) {
-#pragma unroll 2
-      for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
-        float d[8], yy[8], xx[8];
-        ld8(dy + (row0 + r) * A.dy_rs + A.dy_co + m.cv * 8, d);
-        ld8(x + (row0 + r) * A.x_rs + A.x_co + m.cv * 8, xx);
-        if (relu) ld8(y + (row0 + r) * A.y_rs + A.y_co + m.cv * 8, yy);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
-          s1[j] += dr;
-          s2[j] += dr * (xx[j] - mu[j]) * rs[j];
-        }
-      }
-      float* mine = sh + (size_t)m.rlane * 2 * C;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        mine[m.cv * 8 + j] = s1[j];
-        mine[C + m.cv * 8 + j] = s2[j];
-      }
-    }
-    __syncthreads();
-    float* w = ws + (long long)g * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-      float t = 0.f;
-      for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * C + i];
-      atomicAdd(&w[i], t);
-    }
-  }
-  __threadfence();
-  cooperative_groups::this_grid().sync();
-  if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float a = 0.f, b = 0.f;
-      for (int gg = 0; gg < A.groups; ++gg) {
-        b += __ldcg(ws + (long long)gg * 2 * C + c);
-        a += __ldcg(ws + (long long)gg * 2 * C + C + c);
-      }
-      dgamma[c] += a;
-      dbeta[c] += b;
-    }
-  }
-  if (!m.active) return;
-  const float invM = 1.f / (float)A.rows_per_group;
-  float k0[8], a1[8], a2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = m.cv * 8 + j;
-    k0[j] = gamma[c] * rs[j];
-    a1[j] = __ldcg(ws + (long long)g * 2 * C + c) * invM;
-    a2[j] = __ldcg(ws + (long long)g * 2 * C + C + c) * invM;
-  }
-#pragma unroll 2
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < A.rows_per_group; r += (long long)gridDim.x * m.rpb) {
-    float d[8], yy[8], xx[8], o[8];
-    ld8(dy + (row0 + r) * A.dy_rs + A.dy_co + m.cv * 8, d);
-    ld8(x + (row0 + r) * A.x_rs + A.x_co + m.cv * 8, xx);
-    if (relu) ld8(y + (row0 + r) * A.y_rs + A.y_co + m.cv * 8, yy);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
-      o[j] = k0[j] * (dr - a1[j] - (xx[j] - mu[j]) * rs[j] * a2[j]);
-    }
-    st8(dx + (row0 + r) * A.dx_rs + A.dx_co + m.cv * 8, o, true);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 struct PoolGeom {
   int N, C, Ti, Hi, Wi, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw;
 };
@@ -724,7 +525,7 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_row_kernel(const T* __rest
   const long long orow0 = (((long long)n * G.To + ot) * G.Ho + oh) * G.Wo;
   const int total = G.Wo * G.CV;
   for (int e = threadIdx.x; e < total; e += kBlock) {
-    const int ow = (int)__umulhi((uint32_t)e, G.cv_magic);
+    const int ow = G.CV == 1 ? e : (int)__umulhi((uint32_t)e, G.cv_magic);   // (2^32 / 1 + 1 does not fit the magic word)
     const int cv = e - ow * G.CV;
     bool seen_pad = false;
     if constexpr (sizeof(T) == 2) {
@@ -832,7 +633,7 @@ __global__ void __launch_bounds__(kBlock) maxpool_bwd_row_kernel(const T* __rest
   const int oh_hi = min((ih + G.ph) / SH, G.Ho - 1), oh_lo = max((ih + G.ph - KH + SH) / SH, 0);
   const int total = G.Wi * G.CV;
   for (int e = threadIdx.x; e < total; e += kBlock) {
-    const int iw = (int)__umulhi((uint32_t)e, G.cv_magic);
+    const int iw = G.CV == 1 ? e : (int)__umulhi((uint32_t)e, G.cv_magic);
     const int cv = e - iw * G.CV;
     const int ow_hi = min((iw + G.pw) / SW, G.Wo - 1), ow_lo = max((iw + G.pw - KW + SW) / SW, 0);
     float acc[8];
@@ -1443,76 +1244,6 @@ B2C_API int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_rs, int32_t dy_co, 
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_bwd_apply");
   return 0;
-}
-
-// cooperative launch of a fused BatchNorm kernel: the grid must be co-resident (grid barrier)
-template <typename K>
-static int bn_coop_launch(K kernel, const char* what, long long rpg, int C, int groups, size_t smem, void** args, b2c_stream_t s) {
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
-  if (e != cudaSuccess) return b2c_cuda_check(e, what);
-  long long cap = (long long)per_sm * b2c_num_sms() / groups;
-  B2C_REQUIRE(cap >= 1, "%s: no co-resident grid for C=%d groups=%d", what, C, groups);
-  long long gx = row_grid(rpg, C, 3);
-  if (gx > cap) gx = cap;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)gx, (unsigned)groups, 1);
-  cfg.blockDim = dim3(kBlock, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;
-  at[0].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  e = cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
-  if (e != cudaSuccess) return b2c_cuda_check(e, what);
-  b2c_launches_add(1);
-  return 0;
-}
-
-B2C_API int b2c_bn_relu_fwd_fused(const void* x, int64_t rows, int32_t C, int64_t x_rs, int32_t x_co, int32_t groups, float* ws,
-                                  float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
-                                  const float* gamma, const float* beta, void* y, int64_t y_rs, int32_t y_co, int32_t relu,
-                                  b2c_stream_t s) {
-  B2C_REQUIRE(x && y && ws && mean && rstd && gamma && beta, "bn_relu_fwd_fused: null pointer");
-  CHECK_VIEW("bn_relu_fwd_fused", C, x_rs, x_co);
-  CHECK_VIEW("bn_relu_fwd_fused(y)", C, y_rs, y_co);
-  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_relu_fwd_fused: rows not divisible by groups");
-  if (g_deterministic) {   // tests: fixed-order reductions with the separate kernels
-    int rc = b2c_bn_sums(x, rows, C, x_rs, x_co, groups, ws, s);
-    if (rc == 0) rc = b2c_bn_finalize(ws, C, 0, C, groups, rows / groups, mean, rstd, running_mean, running_var, momentum, eps, s);
-    if (rc == 0) rc = b2c_bn_relu_apply(x, rows, C, x_rs, x_co, groups, mean, rstd, gamma, beta, y, y_rs, y_co, relu, s);
-    return rc;
-  }
-  BnFwdArgs A{rows / groups, x_rs, y_rs, C, x_co, y_co, relu, groups, momentum, eps};
-  void* args[] = {(void*)&x, (void*)&y, (void*)&ws, (void*)&mean, (void*)&rstd, (void*)&running_mean, (void*)&running_var,
-                  (void*)&gamma, (void*)&beta, (void*)&A};
-  if (b2c_precision()) return bn_coop_launch(bn_fwd_fused_kernel<float>, "bn_relu_fwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
-  return bn_coop_launch(bn_fwd_fused_kernel<bf16>, "bn_relu_fwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
-}
-
-B2C_API int b2c_bn_relu_bwd_fused(const void* dy, int64_t dy_rs, int32_t dy_co, const void* y, int64_t y_rs, int32_t y_co,
-                                  const void* x, int64_t x_rs, int32_t x_co, int64_t rows, int32_t C, int32_t groups,
-                                  const float* mean, const float* rstd, const float* gamma, float* ws, void* dx, int64_t dx_rs,
-                                  int32_t dx_co, float* dgamma, float* dbeta, int32_t relu, b2c_stream_t s) {
-  B2C_REQUIRE(dy && x && dx && mean && rstd && gamma && ws && (y || !relu), "bn_relu_bwd_fused: null pointer");
-  CHECK_VIEW("bn_relu_bwd_fused(dy)", C, dy_rs, dy_co);
-  CHECK_VIEW("bn_relu_bwd_fused(x)", C, x_rs, x_co);
-  CHECK_VIEW("bn_relu_bwd_fused(dx)", C, dx_rs, dx_co);
-  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_relu_bwd_fused: rows not divisible by groups");
-  if (g_deterministic) {
-    int rc = b2c_bn_relu_bwd_reduce(dy, dy_rs, dy_co, y, y_rs, y_co, x, x_rs, x_co, rows, C, groups, mean, rstd, ws, relu, s);
-    if (rc == 0)
-      rc = b2c_bn_relu_bwd_apply(dy, dy_rs, dy_co, y, y_rs, y_co, x, x_rs, x_co, rows, C, groups, mean, rstd, gamma, ws, dx, dx_rs,
-                                 dx_co, dgamma, dbeta, relu, s);
-    return rc;
-  }
-  BnBwdArgs A{rows / groups, dy_rs, y_rs, x_rs, dx_rs, C, dy_co, y_co, x_co, dx_co, relu, groups};
-  void* args[] = {(void*)&dy, (void*)&y, (void*)&x, (void*)&dx, (void*)&mean, (void*)&rstd, (void*)&gamma, (void*)&ws,
-                  (void*)&dgamma, (void*)&dbeta, (void*)&A};
-  if (b2c_precision()) return bn_coop_launch(bn_bwd_fused_kernel<float>, "bn_relu_bwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
-  return bn_coop_launch(bn_bwd_fused_kernel<bf16>, "bn_relu_bwd_fused", A.rows_per_group, C, groups, bn_red_smem(C), args, s);
 }
 
 B2C_API int b2c_maxpool_fwd(const void* x, int64_t x_rs, int32_t x_co, void* y, int64_t y_rs, int32_t y_co, uint8_t* idx, int32_t N,
