@@ -110,6 +110,14 @@ typedef struct {
   int32_t pad1_;
   int64_t dw_sample_stride; /* elements between per-clip gradients dw[n]; 0 = one dw summed over all clips.  != 0: the
                                position split is a multiple of N so that no CTA straddles clips */
+  /* Fused layers (several convolutions over one input run as one GEMM, e.g. PrimaryCaps pose | activation, the Inception
+   * sibling 1x1x1 convolutions): p channels [seg_begin[i], seg_begin[i+1]) belong to the weight tensor seg_dw[i] (same
+   * s_p / s_g layout, channel index relative to seg_begin[i]).  nseg = 0: everything goes to dw.  One launch then reads
+   * the gathered operand once instead of once per member. */
+  float* seg_dw[4];
+  int32_t seg_begin[4];
+  int32_t nseg;
+  int32_t pad2_;
 } b2c_wgrad_desc;
 
 int b2c_conv_wgrad(const b2c_wgrad_desc* desc_host, b2c_stream_t stream);

@@ -40,7 +40,8 @@ class WgradDesc(C.Structure):
                 ("sg_t", i32), ("sg_h", i32), ("sg_w", i32), ("sp_t", i32), ("sp_h", i32), ("sp_w", i32),
                 ("pp_t", i32), ("pp_h", i32), ("pp_w", i32),
                 ("ntaps", i32), ("bn_tile", i32), ("nsplit", i32), ("atomic", i32), ("dtype", i32),
-                ("p_fold", i32), ("pad1_", i32), ("dw_sample_stride", i64)]
+                ("p_fold", i32), ("pad1_", i32), ("dw_sample_stride", i64),
+                ("seg_dw", vp * 4), ("seg_begin", i32 * 4), ("nseg", i32), ("pad2_", i32)]
 
 
 class PackJob(C.Structure):

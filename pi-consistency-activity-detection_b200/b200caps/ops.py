@@ -92,12 +92,13 @@ def split_bf16(v: View):
 
 
 def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0, part=None, per_clip=False,
-               pp=(0, 0, 0), presplit=None):
+               pp=(0, 0, 0), presplit=None, segs=None):
     name = (f"wgrad {plan.spec.Cin}->{plan.spec.Cout} k{tuple(plan.spec.k)} s{tuple(plan.spec.stride)} in{plan.in_dims}"
             f"{' T' if plan.spec.transposed else ''}")
     wm = wb = 0
     if TIMING is not None:
-        wb = _vb(x) + (_vb(dy) if part is None else dy.rows * part[1] * dy.t.element_size()) + dw.numel() * 4
+        wb = _vb(x) + (_vb(dy) if part is None else dy.rows * part[1] * dy.t.element_size()) + \
+            (sum(t.numel() for _, t in segs) if segs else dw.numel()) * 4
         cl, geo = plan.wgrad_cls, plan.wgrad_geom
         cp = part[2] if (part is not None and len(part) > 2) else (part[1] if part is not None else geo.get("Cp_real", geo["Cp"]))
         wm = x.N * geo["Q"][0] * geo["Q"][1] * geo["Q"][2] * len(cl.taps) * geo["Cg_real"] * cp
@@ -106,10 +107,10 @@ def conv_wgrad(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True,
         assert atomic, "tf32-mode wgrad accumulates"
         (xh, xl), (dh, dl) = presplit if presplit is not None else (split_bf16(x), split_bf16(dy))
         for a, b in ((xh, dh), (xh, dl), (xl, dh)):
-            _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True, pp=pp),
-                    wm, wb)
+            _launch(name, "b2c_conv_wgrad", fill_wgrad_desc(plan, a, b, dw, True, nsplit, bn_tile, part, per_clip, force_bf16=True, pp=pp,
+                                                             segs=segs), wm, wb)
         return
-    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part, per_clip, pp=pp)
+    d = fill_wgrad_desc(plan, x, dy, dw, atomic, nsplit, bn_tile, part, per_clip, pp=pp, segs=segs)
     _launch(name, "b2c_conv_wgrad", d, wm, wb)
 
 

@@ -401,7 +401,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
 
 
 def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=True, nsplit=0, bn_tile=0,
-                    part=None, per_clip=False, force_bf16=False, pp=(0, 0, 0)) -> _abi.WgradDesc:
+                    part=None, per_clip=False, force_bf16=False, pp=(0, 0, 0), segs=None) -> _abi.WgradDesc:
     """x = layer input, dy = gradient of the layer output, dw = fp32 gradient in torch weight layout.
     part=(c_off, C): restrict a fused layer's wgrad to the output-channel window of one member weight."""
     geo = dict(plan.wgrad_geom)
@@ -436,4 +436,10 @@ def fill_wgrad_desc(plan: ConvPlan, x: View, dy: View, dw: torch.Tensor, atomic=
     if per_clip:      # dw is (N, ...): one gradient per clip
         assert dw.shape[0] == x.N
         d.dw_sample_stride = dw.numel() // x.N
+    if segs:          # fused layer: [(first p channel, member dw), ...] in channel order; dw is the first member's
+        assert part is None and not per_clip and 1 <= len(segs) <= 4 and segs[0][0] == 0 and segs[0][1] is dw
+        d.nseg = len(segs)
+        for i, (begin, t) in enumerate(segs):
+            assert t.dtype == torch.float32 and t.is_contiguous()
+            d.seg_begin[i], d.seg_dw[i] = int(begin), t.data_ptr()
     return d

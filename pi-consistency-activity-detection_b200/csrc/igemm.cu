@@ -1076,6 +1076,13 @@ __global__ void __launch_bounds__(kThreads) igemm_wgrad_kernel(const __grid_cons
           const int pc = n0 + c0 + i;
           if (pc < d.Cp_real) {
             float* dst = dw_base + base + (long long)pc * d.s_p;
+            if (d.nseg > 1) {      // fused layer: this column's member weight tensor
+              int sgm = 0;
+#pragma unroll
+              for (int q = 1; q < 4; ++q)
+                if (q < d.nseg && pc >= d.seg_begin[q]) sgm = q;
+              dst = d.seg_dw[sgm] + base + (long long)(pc - d.seg_begin[sgm]) * d.s_p;
+            }
             if (d.atomic) atomicAdd(dst, v[i]);
             else *dst = v[i];
           }
@@ -1450,6 +1457,10 @@ B2C_API int b2c_conv_wgrad(const b2c_wgrad_desc* dh, b2c_stream_t stream) {
   B2C_REQUIRE(dh != nullptr, "conv_wgrad: null descriptor");
   b2c_wgrad_desc d = *dh;
   B2C_REQUIRE(d.g && d.p && d.dw && d.taps && d.wtap, "conv_wgrad: null pointer");
+  B2C_REQUIRE(d.nseg >= 0 && d.nseg <= 4 && (d.nseg == 0 || d.dw_sample_stride == 0), "conv_wgrad: bad weight-tensor segments");
+  for (int i = 0; i < d.nseg; ++i)
+    B2C_REQUIRE(d.seg_dw[i] && d.seg_begin[i] >= (i ? d.seg_begin[i - 1] : 0) && (i || d.seg_begin[0] == 0),
+                "conv_wgrad: segment %d invalid", i);
   B2C_REQUIRE(d.Cg > 0 && d.Cg % 8 == 0 && d.Cp > 0 && d.Cp % 8 == 0, "conv_wgrad: channels must be multiples of 8");
   B2C_REQUIRE(d.g_c_off % 8 == 0 && d.p_c_off % 8 == 0 && d.g_row_stride % 8 == 0 && d.p_row_stride % 8 == 0,
               "conv_wgrad: unaligned view");

@@ -138,6 +138,37 @@ def test_maxpool_row_kernels_equal_generic(k, s, dims, C):
     assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
 
 
+@pytest.mark.parametrize("couts,k", [((24, 40, 16), (1, 1, 1)), ((64, 8), (1, 3, 3))])
+def test_fused_layer_wgrad_one_launch(couts, k):
+    """FusedConvLayer.wgrad: ONE launch whose output column blocks land in the members' weight gradients
+    (b2c_wgrad_desc.seg_*) == one launch per member == torch."""
+    from b200caps import engine
+    from b200caps.plans import ConvSpec, View
+    torch.manual_seed(5)
+    cin, N, dims = 48, 3, (2, 9, 10)
+    ws = [torch.nn.Parameter(torch.randn((co, cin) + k, device=dev()) * 0.1) for co in couts]
+    pad = tuple(kk // 2 for kk in k)
+    fl = engine.FusedConvLayer(ws, lambda d: ConvSpec(cin, sum(couts), k, (1, 1, 1), pad, pad))
+    x = torch.randn((N,) + dims + (cin,), device=dev()).bfloat16()
+    dy = torch.randn((N,) + dims + (sum(couts),), device=dev()).bfloat16()
+    res = []
+    old = engine.FUSED_WGRAD
+    try:
+        for fused in (True, False):
+            engine.FUSED_WGRAD = fused
+            res.append([t.clone() for t in fl.wgrad(dims, View(x), View(dy))])
+    finally:
+        engine.FUSED_WGRAD = old
+    xr = x.float().permute(0, 4, 1, 2, 3)
+    off = 0
+    for i, (w, co) in enumerate(zip(ws, couts)):
+        g = dy[..., off:off + co].float().permute(0, 4, 1, 2, 3)
+        ref = torch.nn.grad.conv3d_weight(xr, w.shape, g, padding=pad)
+        assert rel(res[0][i], ref) < 2e-5, (i, rel(res[0][i], ref))
+        assert rel(res[0][i], res[1][i]) < 2e-6
+        off += co
+
+
 def test_em_routing_matches_reference_golden():
     """fwd + bwd of the fused routing kernel against the REFERENCE's own outputs / gradients (fp64 golden)."""
     from b200caps import engine
