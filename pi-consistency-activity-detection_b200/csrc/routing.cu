@@ -233,7 +233,6 @@ __global__ void __launch_bounds__(kRT, kNW == 8 ? 2 : 1) em_routing_fwd_kernel(c
 //   pass B (per i): V_ij again, accumulate the variance around the new mean
 // Same formulas and evaluation order per j as m_step / e_step above.
 // =====================================================================================
-constexpr int kWL = 8;   // warps (= locations in flight) per CTA
 
 // Routing state saved by the training forward for the backward kernels (floats per location, 32-lane rows):
 //   r_t[i][32] (t = 1, 2: the E-step assignments; t = 0 is the constant 1/C), rn_t[i][32] (t = 0..2), Z_t[i] (t = 0..2),
@@ -287,16 +286,29 @@ __device__ __forceinline__ void votes_of(const float* __restrict__ sc, const flo
 // their neighbours' (valid) words and are masked out of every result.
 __host__ __device__ __forceinline__ int routing_pitch(int C) { return C <= 24 ? 24 : 32; }
 
-__global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const float* __restrict__ caps, const float* __restrict__ W,
-                                                                         const float* __restrict__ beta_u, const float* __restrict__ beta_a,
-                                                                         float* __restrict__ out, float* __restrict__ state, long long b,
-                                                                         int C) {
+// two independent warp reductions with their shuffles interleaved (the location loops below walk TWO input capsules per
+// iteration: a single capsule's chain  votes -> exponent -> max -> exp -> sum -> normaliser sum  is ~500 cycles of
+// dependent latency, and with 12..16 warps per SM that chain, not the issue rate, set the kernel time)
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+    a += ta;
+    b += tb;
+  }
+}
+
+template <int kW>
+__global__ void __launch_bounds__(kW * 32, 1) em_routing_fwd_warp_kernel(const float* __restrict__ caps, const float* __restrict__ W,
+                                                                        const float* __restrict__ beta_u, const float* __restrict__ beta_a,
+                                                                        float* __restrict__ out, float* __restrict__ state, long long b,
+                                                                        int C) {
   extern __shared__ float sm[];
   const int wst = routing_pitch(C);
   float* sW = sm;                                   // [32][16][wst] (+ 8 floats of slack for the masked lanes' reads)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* sc = sW + kB * 16 * wst + 8 + w * 544;     // this warp's capsules (poses | activations), 16-byte aligned
-  float* srn = sW + kB * 16 * wst + 8 + kWL * 544 + w * (kB * wst + 8);   // this warp's rn[i][lane]
+  float* srn = sW + kB * 16 * wst + 8 + kW * 544 + w * (kB * wst + 8);   // this warp's rn[i][lane]
   const bool active = lane < C;
   for (int idx = threadIdx.x; idx < kB * 16 * wst + 8; idx += blockDim.x) sW[idx] = 0.f;
   __syncthreads();
@@ -305,12 +317,12 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
     sW[(i * 16 + h) * wst + j] = W[idx];
   }
   __syncthreads();
-  float bu[16];
+  float bu_sum = 0.f;
   const float ba = active ? beta_a[lane] : 0.f;
 #pragma unroll
-  for (int h = 0; h < 16; ++h) bu[h] = active ? beta_u[lane * 16 + h] : 0.f;
+  for (int h = 0; h < 16; ++h) bu_sum += active ? beta_u[lane * 16 + h] : 0.f;
   const int ocols = C * 17;
-  for (long long loc = (long long)blockIdx.x * kWL + w; loc < b; loc += (long long)gridDim.x * kWL) {
+  for (long long loc = (long long)blockIdx.x * kW + w; loc < b; loc += (long long)gridDim.x * kW) {
     __syncwarp();
     for (int idx = lane; idx < 544 / 4; idx += 32)
       reinterpret_cast<float4*>(sc)[idx] = reinterpret_cast<const float4*>(caps + loc * 544)[idx];
@@ -325,36 +337,55 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
 #pragma unroll
       for (int h = 0; h < 16; ++h) A1[h] = 0.f;
 #pragma unroll 1
-      for (int i = 0; i < kB; ++i) {
-        float V[16];
-        votes_of(sc, sW, i, lane, V, wst);
-        float r;
+      for (int i = 0; i < kB; i += 2) {
+        float Va[16], Vb[16];
+        votes_of(sc, sW, i, lane, Va, wst);
+        votes_of(sc, sW, i + 1, lane, Vb, wst);
+        float ra, rb;
         if (t == 0) {
-          r = 1.f / (float)C;
+          ra = rb = 1.f / (float)C;
         } else {
-          float q = 0.f;
+          float qa = 0.f, qb = 0.f;
 #pragma unroll
           for (int h = 0; h < 16; ++h) {
-            const float dv = V[h] - mu[h];
-            q = fmaf(dv * dv, inv2S[h], q);
+            const float da = Va[h] - mu[h], db = Vb[h] - mu[h];
+            qa = fmaf(da * da, inv2S[h], qa);
+            qb = fmaf(db * db, inv2S[h], qb);
           }
-          const float z = active ? (base - q) : -INFINITY;
-          const float mx = warp_max_redux(z);
-          const float e = active ? expf(z - mx) : 0.f;
-          r = e / warp_sum(e);
+          const float za = active ? (base - qa) : -INFINITY, zb = active ? (base - qb) : -INFINITY;
+          const float mxa = warp_max_redux(za), mxb = warp_max_redux(zb);
+          const float ea = active ? expf(za - mxa) : 0.f, eb = active ? expf(zb - mxb) : 0.f;
+          float sa = ea, sb = eb;
+          warp_sum2(sa, sb);
+          ra = ea / sa;
+          rb = eb / sb;
         }
-        const float rp = active ? r * s_ain[i] : 0.f;
-        const float Z = warp_sum(rp) + kEps;
-        const float rn = rp / Z;
-        if (active) srn[i * wst + lane] = rn;
+        const float rpa = active ? ra * s_ain[i] : 0.f, rpb = active ? rb * s_ain[i + 1] : 0.f;
+        float Za = rpa, Zb = rpb;
+        warp_sum2(Za, Zb);
+        Za += kEps;
+        Zb += kEps;
+        const float rna = rpa / Za, rnb = rpb / Zb;
+        if (active) {
+          srn[i * wst + lane] = rna;
+          srn[(i + 1) * wst + lane] = rnb;
+        }
         if (st) {
-          if (t > 0) st[kStR + ((t - 1) * kB + i) * 32 + lane] = r;
-          st[kStRN + (t * kB + i) * 32 + lane] = rn;
-          if (lane == 0) st[kStZ + t * kB + i] = Z;
+          if (t > 0) {
+            st[kStR + ((t - 1) * kB + i) * 32 + lane] = ra;
+            st[kStR + ((t - 1) * kB + i + 1) * 32 + lane] = rb;
+          }
+          st[kStRN + (t * kB + i) * 32 + lane] = rna;
+          st[kStRN + (t * kB + i + 1) * 32 + lane] = rnb;
+          if (lane < 2) st[kStZ + t * kB + i + lane] = lane ? Zb : Za;
         }
-        R += rn;
+        R += rna;
+        R += rnb;
 #pragma unroll
-        for (int h = 0; h < 16; ++h) A1[h] = fmaf(rn, V[h], A1[h]);
+        for (int h = 0; h < 16; ++h) {
+          A1[h] = fmaf(rna, Va[h], A1[h]);
+          A1[h] = fmaf(rnb, Vb[h], A1[h]);
+        }
       }
       const float invR = 1.f / (R + kEps);
 #pragma unroll
@@ -364,25 +395,26 @@ __global__ void __launch_bounds__(kWL * 32, 2) em_routing_fwd_warp_kernel(const 
 #pragma unroll
       for (int h = 0; h < 16; ++h) S[h] = 0.f;
 #pragma unroll 1
-      for (int i = 0; i < kB; ++i) {
-        float V[16];
-        votes_of(sc, sW, i, lane, V, wst);
-        const float c = srn[i * wst + lane] * invR;
+      for (int i = 0; i < kB; i += 2) {
+        float Va[16], Vb[16];
+        votes_of(sc, sW, i, lane, Va, wst);
+        votes_of(sc, sW, i + 1, lane, Vb, wst);
+        const float ca = srn[i * wst + lane] * invR, cb = srn[(i + 1) * wst + lane] * invR;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
-          const float dv = V[h] - mu[h];
-          S[h] = fmaf(c, dv * dv, S[h]);
+          const float da = Va[h] - mu[h], db = Vb[h] - mu[h];
+          S[h] = fmaf(ca, da * da, S[h]);
+          S[h] = fmaf(cb, db * db, S[h]);
         }
       }
-      float T = 0.f, lnS = 0.f;
+      float lnS = 0.f;
 #pragma unroll
       for (int h = 0; h < 16; ++h) {
         S[h] += kEps;
-        const float l = logf(S[h]);
-        T += bu[h] + 0.5f * l;
-        lnS += l;
+        lnS += logf(S[h]);
         inv2S[h] = 0.5f / S[h];
       }
+      const float T = bu_sum + 0.5f * lnS;
       const float cost = T * R;
       const double cd = active ? (double)cost : 0.0;
       const double md = warp_sum_d(cd) / (double)C;
@@ -737,7 +769,7 @@ __global__ void __launch_bounds__(kNWc * 32, 1) em_routing_bwd_coef_kernel(const
   extern __shared__ __align__(16) float sm[];
   const int wst = routing_pitch(C);
   constexpr int nw = kNWc;
-  constexpr bool kPin = kNWc > 12;
+  constexpr bool kPin = kNWc >= 12;
   float* sW = sm;                                               // [32][16][wst] (+8)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* sc = sW + kB * 16 * wst + 8 + w * 544;                 // this warp's capsules
@@ -835,37 +867,54 @@ __global__ void __launch_bounds__(kNWc * 32, 1) em_routing_bwd_coef_kernel(const
       const float* p_rn = st + kStRN + t * kB * 32 + lane;
       float* p_r = st + kStR + (t - 1) * kB * 32 + lane;
       const float* p_Z = st + kStZ + t * kB;
-      float rn_n = p_rn[0], r_n = p_r[0], Z_n = p_Z[0];
+      // two input capsules per iteration (independent chains interleaved, see warp_sum2); their state rows are loaded one
+      // iteration ahead
+      float rn_a = p_rn[0], r_a = p_r[0], Z_a = p_Z[0], rn_b = p_rn[32], r_b = p_r[32], Z_b = p_Z[1];
 #pragma unroll 1
-      for (int i = 0; i < kB; ++i) {
-        const float rn = rn_n, r = r_n, Z = Z_n;
-        if (i + 1 < kB) {
-          rn_n = p_rn[(i + 1) * 32];
-          r_n = p_r[(i + 1) * 32];
-          Z_n = p_Z[i + 1];
+      for (int i = 0; i < kB; i += 2) {
+        const float rna = rn_a, ra = r_a, Za = Z_a, rnb = rn_b, rb = r_b, Zb = Z_b;
+        if (i + 2 < kB) {
+          rn_a = p_rn[(i + 2) * 32];
+          r_a = p_r[(i + 2) * 32];
+          Z_a = p_Z[i + 2];
+          rn_b = p_rn[(i + 3) * 32];
+          r_b = p_r[(i + 3) * 32];
+          Z_b = p_Z[i + 3];
         }
-        float V[16];
-        votes_of(sc, sW, i, lane, V, wst);
-        float gc = Kc;
+        float Va[16], Vb[16];
+        votes_of(sc, sW, i, lane, Va, wst);
+        votes_of(sc, sW, i + 1, lane, Vb, wst);
+        float gca = Kc, gcb = Kc;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
-          const float dv = V[h] - lds_vec<kPin>(vmu + h * wst + lane);
-          gc = fmaf(fmaf(lds_vec<kPin>(vgS + h * wst + lane), dv, lds_vec<kPin>(vgm + h * wst + lane)), dv, gc);
+          const float m = lds_vec<kPin>(vmu + h * wst + lane), gs = lds_vec<kPin>(vgS + h * wst + lane),
+                      gm = lds_vec<kPin>(vgm + h * wst + lane);
+          const float da = Va[h] - m, db = Vb[h] - m;
+          gca = fmaf(fmaf(gs, da, gm), da, gca);
+          gcb = fmaf(fmaf(gs, db, gm), db, gcb);
         }
-        const float grn = active ? fmaf(gc, invR, gR_tot) : 0.f;
-        const float dot2 = warp_sum(grn * rn);
-        const float grp = active ? (grn - dot2) * fast_rcp(Z) : 0.f;
-        const float gsum = warp_sum(grp * r);          // d a_in_i of this iteration; sum_j gr r = a_i gsum
-        if (lane == i) gain_acc += gsum;
-        const float gz = r * s_ain[i] * (grp - gsum);
-        p_r[i * 32] = gz;
-        gzsum += gz;
+        const float grna = active ? fmaf(gca, invR, gR_tot) : 0.f, grnb = active ? fmaf(gcb, invR, gR_tot) : 0.f;
+        float d2a = grna * rna, d2b = grnb * rnb;
+        warp_sum2(d2a, d2b);
+        const float grpa = active ? (grna - d2a) * fast_rcp(Za) : 0.f, grpb = active ? (grnb - d2b) * fast_rcp(Zb) : 0.f;
+        float gsa = grpa * ra, gsb = grpb * rb;          // d a_in_i of this iteration; sum_j gr r = a_i gsum
+        warp_sum2(gsa, gsb);
+        if (lane == i) gain_acc += gsa;
+        if (lane == i + 1) gain_acc += gsb;
+        const float gza = ra * s_ain[i] * (grpa - gsa), gzb = rb * s_ain[i + 1] * (grpb - gsb);
+        p_r[i * 32] = gza;
+        p_r[(i + 1) * 32] = gzb;
+        gzsum += gza;
+        gzsum += gzb;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
-          const float d0 = V[h] - lds_vec<kPin>(vmp + h * wst + lane);
-          const float u = gz * d0;
-          A[h] += u;
-          Bq[h] = fmaf(u, d0, Bq[h]);
+          const float mp = lds_vec<kPin>(vmp + h * wst + lane);
+          const float da = Va[h] - mp, db = Vb[h] - mp;
+          const float ua = gza * da, ub = gzb * db;
+          A[h] += ua;
+          Bq[h] = fmaf(ua, da, Bq[h]);
+          A[h] += ub;
+          Bq[h] = fmaf(ub, db, Bq[h]);
         }
       }
       const float a_prev = st[kStSC + (t - 1) * 4 * 32 + 64 + lane];
@@ -1181,16 +1230,29 @@ static int routing_fwd_impl(const float* caps, const float* W, const float* beta
   }
   if (use_warp || state) {
     const int wst = routing_pitch(C);
-    const size_t smw = (size_t)(kB * 16 * wst + 8 + kWL * 544 + kWL * (kB * wst + 8)) * sizeof(float);
+    static int wenv = -1;
+    if (wenv < 0) {
+      const char* e = getenv("B2C_ROUTING_FWD_WARPS");
+      wenv = e ? atoi(e) : 0;
+    }
+    // one CTA per SM; measured at 12 800 locations, C = 24: 8 warps 1.01 ms, 12 warps 0.885 ms, 16 warps 0.80 ms
+    const int kw = C > 24 ? 8 : (wenv == 12 || wenv == 8 || wenv == 10 ? wenv : 16);
+    const size_t smw = (size_t)(kB * 16 * wst + 8 + kw * 544 + kw * (kB * wst + 8)) * sizeof(float);
     static bool cfgw = false;
     if (!cfgw) {
-      cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd(warp) attr");
       cfgw = true;
     }
-    long long gridw = 2LL * b2c_num_sms();
-    if (gridw * kWL > b) gridw = (b + kWL - 1) / kWL;
-    em_routing_fwd_warp_kernel<<<(unsigned)gridw, kWL * 32, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
+    long long gridw = b2c_num_sms();
+    if (gridw * kw > b) gridw = (b + kw - 1) / kw;
+    if (kw == 16) em_routing_fwd_warp_kernel<16><<<(unsigned)gridw, 512, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
+    else if (kw == 12) em_routing_fwd_warp_kernel<12><<<(unsigned)gridw, 384, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
+    else if (kw == 10) em_routing_fwd_warp_kernel<10><<<(unsigned)gridw, 320, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
+    else em_routing_fwd_warp_kernel<8><<<(unsigned)gridw, 256, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
     b2c_launches_add(1);
     B2C_LAUNCH_CHECK("em_routing_fwd(warp)");
     return 0;
