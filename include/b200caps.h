@@ -268,6 +268,10 @@ int b2c_em_routing_bwd_state(const float* caps, const float* W, const float* bet
  * g * (col >= 512 ? a(1-a) : 1); dbias[544] += column sums (first 512: pose bias, last 32: a bias). */
 int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, int32_t dz_pitch,
                              b2c_stream_t s);
+/* PrimaryCaps epilogue for the K-split forward: the GEMM's K dimension (the 81 taps) runs as `nslice` scheduling classes
+ * that write their partial sums to frames 0..nslice-1 of part fp32 (N, nslice, L, 544); out[n][l][c] = sum_s part[n][s][l][c]
+ * + bias[c], sigmoid on the 32 activation columns (capsules_ucf101.py:43-49).  Fixed summation order: bit-reproducible. */
+int b2c_primarycaps_finish(const float* part, int32_t nslice, const float* bias, float* out, int32_t N, int32_t L, b2c_stream_t s);
 /* class activation = mean over the 400 locations (capsules_ucf101.py:450-451); feat is a view of out */
 int b2c_class_mean_fwd(const float* rout, float* act, int32_t N, int32_t L, int32_t C, b2c_stream_t s);
 /* pose masking (capsules_ucf101.py:455-483): x[n,l,j*16+h] = mu[n,l,j,h] * mask[n,j]  -> bf16 (N,L,C*16) */

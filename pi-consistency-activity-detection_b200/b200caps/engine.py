@@ -597,6 +597,8 @@ def bn_bwd_part(raw: View, y: View, gy: View, draw: View, m, mean, rstd, g: int)
 # N = c0 + c1 + c3 output channels (176 .. 448), their three input gradients as ONE dgrad GEMM over the stacked output
 # gradients: 2 launches instead of 6 per block and one read of x instead of three.  B2C_FUSE_SIBLINGS=0 disables.
 FUSE_SIBLINGS = os.environ.get("B2C_FUSE_SIBLINGS", "1") != "0"
+# PrimaryCaps forward: K (the 81 taps) split over this many scheduling classes (B2C_PC_KSPLIT=1: one class, fused epilogue)
+PC_KSPLIT = int(os.environ.get("B2C_PC_KSPLIT", "8"))
 # weight gradients of a fused layer's members in one wgrad launch (B2C_FUSED_WGRAD=0: one launch per member)
 FUSED_WGRAD = os.environ.get("B2C_FUSED_WGRAD", "1") != "0"
 
@@ -737,8 +739,9 @@ class FusedConvLayer:
     GEMM with N = sum(Cout_i): the packed fprop operand stacks the members' rows, the dgrad operand places them
     side by side along K.  Used for PrimaryCaps (pose | a, N = 544)."""
 
-    def __init__(self, weights: Sequence[torch.nn.Parameter], spec_fn, grad_cpad: int = 0):
+    def __init__(self, weights: Sequence[torch.nn.Parameter], spec_fn, grad_cpad: int = 0, fprop_ksplit: int = 1):
         self.weights = list(weights)
+        self.fprop_ksplit = fprop_ksplit   # > 1: the forward GEMM's K (taps) is split over scheduling classes (one output frame each)
         self.grad_cpad = grad_cpad       # channel width of the output-gradient tensor (>= sum Cout, 64-aligned for TMA)
         self.couts = [int(w.shape[0]) for w in self.weights]
         self.offs = [sum(self.couts[:i]) for i in range(len(self.couts))]
@@ -752,6 +755,8 @@ class FusedConvLayer:
         if pl is None:
             pl = ConvPlan(self.spec_fn(in_dims), in_dims)
             assert not pl.spec.transposed and pl.spec.Cout == sum(self.couts)
+            if self.fprop_ksplit > 1:
+                pl.split_fprop_k(self.fprop_ksplit)
             if self.grad_cpad:
                 # the gradient w.r.t. the fused output is stored grad_cpad channels wide (zero tail): dgrad's K and
                 # wgrad's plain operand become 64-channel aligned -> TMA path
@@ -772,15 +777,15 @@ class FusedConvLayer:
         from .plans import packed_geometry
         from .plans import tap_pitch
         if which == "fprop":
-            cl = pl.fprop[0]
-            nt = len(cl.taps)
             pitch = tap_pitch(spec.Cin_pad)
-            bn, _, nkb, elems = packed_geometry(spec.Cout_pad, nt * pitch)
-            if cl.packed is None or cl.packed.dtype != act_dtype():
-                cl.packed = torch.zeros(elems, dtype=act_dtype(), device=dev)
-            for w, co, off in zip(self.weights, self.couts, self.offs):
-                ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, co, nt, spec.Cin_pad, spec.Cin, spec.Cin * T, T,
-                              pitch, 0, off, bn, nkb)
+            for cl in pl.fprop:
+                nt = len(cl.taps)
+                bn, _, nkb, elems = packed_geometry(spec.Cout_pad, nt * pitch)
+                if cl.packed is None or cl.packed.dtype != act_dtype():
+                    cl.packed = torch.zeros(elems, dtype=act_dtype(), device=dev)
+                for w, co, off in zip(self.weights, self.couts, self.offs):
+                    ops.pack_part(w.detach(), cl.packed, cl.wtap_dev, co, nt, spec.Cin_pad, spec.Cin, spec.Cin * T, T,
+                                  pitch, 0, off, bn, nkb)
         else:
             cg = self.grad_cpad or spec.Cout_pad
             pitch = tap_pitch(cg)
@@ -827,8 +832,15 @@ class PrimaryCapsFn(torch.autograd.Function):
         pl = layer.packed(x_cl.shape[1:4], "fprop")
         N = x_cl.shape[0]
         bias = torch.cat([bp.detach(), ba.detach()])      # 544 floats (plumbing)
-        out = torch.empty((N,) + tuple(pl.out_dims) + (544,), dtype=torch.float32, device=x_cl.device)
-        ops.conv_fprop(pl, "fprop", View(x_cl), View(out), bias=bias, sigmoid_from=512, final=True)
+        if len(pl.fprop) > 1:
+            # K split (FusedConvLayer.fprop_ksplit): every slice writes its partial sums to its own frame; sum + bias + sigmoid
+            part = torch.empty((N,) + tuple(pl.fprop_out_dims) + (544,), dtype=torch.float32, device=x_cl.device)
+            out = torch.empty((N,) + tuple(pl.out_dims) + (544,), dtype=torch.float32, device=x_cl.device)
+            ops.conv_fprop(pl, "fprop", View(x_cl), View(part), final=True)
+            ops.primarycaps_finish(part, bias, out)
+        else:
+            out = torch.empty((N,) + tuple(pl.out_dims) + (544,), dtype=torch.float32, device=x_cl.device)
+            ops.conv_fprop(pl, "fprop", View(x_cl), View(out), bias=bias, sigmoid_from=512, final=True)
         ctx.mod, ctx.x, ctx.out = mod, x_cl, out
         return out
 

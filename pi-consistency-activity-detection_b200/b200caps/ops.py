@@ -357,6 +357,13 @@ def routing_state_floats() -> int:
     return int(_abi.lib().b2c_em_routing_state_floats())
 
 
+def primarycaps_finish(part, bias, out):
+    """part (N, S, h, w, 544) fp32 partial sums of the S K-slices -> out (N, 1, h, w, 544) = sum + bias, sigmoid on the last 32"""
+    N, S = part.shape[0], part.shape[1]
+    L = part.shape[2] * part.shape[3]
+    _bw("b2c_primarycaps_finish", (part.numel() + out.numel()) * 4, _p(part), S, _p(bias), _p(out), N, L, stream())
+
+
 def primarycaps_bwd_prep(g, out, dz, dbias, rows, dz_pitch=544):
     _bw("b2c_primarycaps_bwd_prep", rows * (544 * 8 + dz_pitch * dz.element_size()), _p(g), _p(out), _p(dz), _p(dbias), rows, dz_pitch, stream())
 

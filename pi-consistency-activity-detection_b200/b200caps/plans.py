@@ -248,6 +248,22 @@ class ConvPlan:
         _prune_padding_taps(self.dgrad, self.dgrad_si, self.out_dims)
         self._device = None
 
+    def split_fprop_k(self, nsplit: int) -> None:
+        """Turn the single fprop class of a 2-D layer (one output frame) into `nsplit` classes over disjoint tap ranges,
+        class s writing its partial sums to output frame s: the K dimension of the GEMM is split over scheduling units and a
+        small kernel adds the frames (ops.primarycaps_finish) -- fixed order, bit-reproducible.  For a layer whose tile
+        count is a poor multiple of the SM count (PrimaryCaps: 300 tiles on 148 SMs = 3 rounds for 2.03 rounds of work) the
+        finer units fill the last round."""
+        assert len(self.fprop) == 1 and not self.spec.transposed and self._device is None and self.out_dims[0] == 1
+        cl = self.fprop[0]
+        nt = len(cl.taps)
+        nsplit = max(1, min(nsplit, nt, 8))
+        if nsplit == 1:
+            return
+        cuts = [nt * i // nsplit for i in range(nsplit + 1)]
+        self.fprop = [TapClass(cl.taps[a:b], cl.wtap[a:b], cl.Q, (s, 0, 0)) for s, (a, b) in enumerate(zip(cuts, cuts[1:]))]
+        self.fprop_out_dims = (nsplit,) + tuple(self.out_dims[1:])     # the GEMM's output tensor: one frame per K slice
+
     @staticmethod
     def pointwise_from_strides(Cin: int, Cout: int, Cout_pad: int, s_co: int, s_ci: int, dims) -> "ConvPlan":
         """A 1x1x1 convolution whose (Cout, Cin) matrix lives inside another tensor with element strides
@@ -267,7 +283,8 @@ class ConvPlan:
     def to(self, device):
         if self._device == device:
             return self
-        for cl in self.fprop + self.dgrad:
+        extra = [self.wgrad_cls] if not any(self.wgrad_cls is c for c in self.fprop + self.dgrad) else []
+        for cl in self.fprop + self.dgrad + extra:
             words = [_tap_word(*t) for t in cl.taps]
             cl.taps_dev = torch.tensor(words, dtype=torch.int32, device=device)
             cl.taps_host = (C.c_int32 * len(words))(*words)
@@ -355,7 +372,7 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
     classes = plan.fprop if which == "fprop" else plan.dgrad
     si, so = (plan.fprop_si, plan.fprop_so) if which == "fprop" else (plan.dgrad_si, plan.dgrad_so)
     pk = plan.fprop_pack if which == "fprop" else plan.dgrad_pack
-    exp_in, exp_out = (plan.in_dims, plan.out_dims) if which == "fprop" else (plan.out_dims, plan.in_dims)
+    exp_in, exp_out = (plan.in_dims, getattr(plan, "fprop_out_dims", plan.out_dims)) if which == "fprop" else (plan.out_dims, plan.in_dims)
     assert x.dims == tuple(exp_in), (which, x.dims, exp_in)
     assert x.C == pk["C"], (which, x.C, pk["C"])
     assert x.t.dtype == act_dtype(), (x.t.dtype, precision())

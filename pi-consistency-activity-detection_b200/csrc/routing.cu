@@ -1215,7 +1215,45 @@ __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* 
   for (int i = threadIdx.x; i < 544; i += blockDim.x) atomicAdd(&dbias[i], sh[i]);
 }
 
+// PrimaryCaps forward epilogue after a K-split GEMM: sum of the K slices' partial outputs (frames of `part`) + bias, sigmoid on
+// the activation columns (>= 512)
+__global__ void __launch_bounds__(256) primarycaps_finish_kernel(const float* __restrict__ part, int nslice, const float* __restrict__ bias,
+                                                                 float* __restrict__ out, int L, long long total4) {
+  const long long per = (long long)L * 136;     // column quads per (clip, slice): 544 / 4 per location
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / per, r = i - n * per;
+    const int c4 = (int)(r % 136);
+    const float4* src = reinterpret_cast<const float4*>(part) + n * nslice * per + r;
+    float4 v = src[0];
+    for (int sl = 1; sl < nslice; ++sl) {
+      const float4 u = src[(long long)sl * per];
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    const float4 b = reinterpret_cast<const float4*>(bias)[c4];
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if (c4 >= 128) {
+      v.x = sigmoidf_(v.x); v.y = sigmoidf_(v.y); v.z = sigmoidf_(v.z); v.w = sigmoidf_(v.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
 }  // namespace
+
+B2C_API int b2c_primarycaps_finish(const float* part, int32_t nslice, const float* bias, float* out, int32_t N, int32_t L,
+                                   b2c_stream_t s) {
+  B2C_REQUIRE(part && out && bias && nslice >= 1 && N > 0 && L > 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)part & 15) == 0 &&
+                  ((uintptr_t)bias & 15) == 0,
+              "primarycaps_finish: bad args");
+  const long long total4 = (long long)N * L * 136;
+  long long blocks = (total4 + 255) / 256;
+  const long long cap = (long long)b2c_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  primarycaps_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(part, nslice, bias, out, L, total4);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("primarycaps_finish");
+  return 0;
+}
 
 static int routing_fwd_impl(const float* caps, const float* W, const float* beta_u, const float* beta_a, float* out, float* state,
                             int64_t b, int32_t C, b2c_stream_t s) {

@@ -42,7 +42,7 @@ class PrimaryCaps(nn.Module):
             def spec_fn(dims):
                 return ConvSpec(A, n_out, (1, K, K), (1, st, st))
 
-            lc = engine.FusedConvLayer([self.pose.weight, self.a.weight], spec_fn, grad_cpad=576)
+            lc = engine.FusedConvLayer([self.pose.weight, self.a.weight], spec_fn, grad_cpad=576, fprop_ksplit=engine.PC_KSPLIT)
             self.__dict__["_layer_cache"] = lc
         return lc
 

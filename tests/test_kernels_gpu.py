@@ -169,6 +169,30 @@ def test_fused_layer_wgrad_one_launch(couts, k):
         off += co
 
 
+def test_primarycaps_forward_k_split():
+    """PrimaryCaps forward with the GEMM's K dimension split over scheduling classes (partial sums in separate output
+    frames + summing epilogue kernel) == the single-class GEMM with the fused bias / sigmoid epilogue, and bit-reproducible."""
+    from b200caps import engine
+    from models.capsules_ucf101 import PrimaryCaps
+    torch.manual_seed(11)
+    x = torch.randn(2, 832, 1, 28, 28, device=dev()) * 0.5
+    outs = []
+    old = engine.PC_KSPLIT
+    try:
+        for ks in (1, 4, 4, 3):
+            engine.PC_KSPLIT = ks
+            torch.manual_seed(12)
+            pc = PrimaryCaps(A=832, B=32, K=9, P=4, stride=1).to(dev())
+            with torch.no_grad():
+                outs.append(pc(x).clone())
+    finally:
+        engine.PC_KSPLIT = old
+    # K = 67 392 products per output: the tensor core's fp32 accumulation chain is 4x / 3x shorter in the split GEMM, which
+    # moves the result by ~7e-5 of the output range (measured) -- far inside the bf16 operand rounding (1.5e-3 vs the oracle)
+    assert rel(outs[1], outs[0]) < 3e-4 and rel(outs[3], outs[0]) < 3e-4, (rel(outs[1], outs[0]), rel(outs[3], outs[0]))
+    assert torch.equal(outs[1], outs[2])
+
+
 def test_em_routing_matches_reference_golden():
     """fwd + bwd of the fused routing kernel against the REFERENCE's own outputs / gradients (fp64 golden)."""
     from b200caps import engine
