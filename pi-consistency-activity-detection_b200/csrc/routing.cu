@@ -286,6 +286,13 @@ __device__ __forceinline__ void votes_of(const float* __restrict__ sc, const flo
 // their neighbours' (valid) words and are masked out of every result.
 __host__ __device__ __forceinline__ int routing_pitch(int C) { return C <= 24 ? 24 : 32; }
 
+// reciprocal without the IEEE-division slow path: MUFU.RCP + one Newton step (<= 1 ulp for the normal-range operands here)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * fmaf(-x, r, 2.f);
+}
+
 // two independent warp reductions with their shuffles interleaved (the location loops below walk TWO input capsules per
 // iteration: a single capsule's chain  votes -> exponent -> max -> exp -> sum -> normaliser sum  is ~500 cycles of
 // dependent latency, and with 12..16 warps per SM that chain, not the issue rate, set the kernel time)
@@ -298,13 +305,13 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b) {
   }
 }
 
-template <int kW>
+template <int kW, int kPitch>
 __global__ void __launch_bounds__(kW * 32, 1) em_routing_fwd_warp_kernel(const float* __restrict__ caps, const float* __restrict__ W,
                                                                         const float* __restrict__ beta_u, const float* __restrict__ beta_a,
                                                                         float* __restrict__ out, float* __restrict__ state, long long b,
                                                                         int C) {
   extern __shared__ float sm[];
-  const int wst = routing_pitch(C);
+  constexpr int wst = kPitch;                       // compile-time row pitch: shared-memory offsets become immediates
   float* sW = sm;                                   // [32][16][wst] (+ 8 floats of slack for the masked lanes' reads)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* sc = sW + kB * 16 * wst + 8 + w * 544;     // this warp's capsules (poses | activations), 16-byte aligned
@@ -354,18 +361,18 @@ __global__ void __launch_bounds__(kW * 32, 1) em_routing_fwd_warp_kernel(const f
           }
           const float za = active ? (base - qa) : -INFINITY, zb = active ? (base - qb) : -INFINITY;
           const float mxa = warp_max_redux(za), mxb = warp_max_redux(zb);
-          const float ea = active ? expf(za - mxa) : 0.f, eb = active ? expf(zb - mxb) : 0.f;
+          const float ea = active ? __expf(za - mxa) : 0.f, eb = active ? __expf(zb - mxb) : 0.f;
           float sa = ea, sb = eb;
           warp_sum2(sa, sb);
-          ra = ea / sa;
-          rb = eb / sb;
+          ra = ea * fast_rcp(sa);
+          rb = eb * fast_rcp(sb);
         }
         const float rpa = active ? ra * s_ain[i] : 0.f, rpb = active ? rb * s_ain[i + 1] : 0.f;
         float Za = rpa, Zb = rpb;
         warp_sum2(Za, Zb);
         Za += kEps;
         Zb += kEps;
-        const float rna = rpa / Za, rnb = rpb / Zb;
+        const float rna = rpa * fast_rcp(Za), rnb = rpb * fast_rcp(Zb);
         if (active) {
           srn[i * wst + lane] = rna;
           srn[(i + 1) * wst + lane] = rnb;
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(kW * 32, 1) em_routing_fwd_warp_kernel(const f
       for (int h = 0; h < 16; ++h) {
         S[h] += kEps;
         lnS += logf(S[h]);
-        inv2S[h] = 0.5f / S[h];
+        inv2S[h] = 0.5f * fast_rcp(S[h]);
       }
       const float T = bu_sum + 0.5f * lnS;
       const float cost = T * R;
@@ -742,13 +749,6 @@ __global__ void __launch_bounds__(kRT, 1) em_routing_bwd_kernel(const float* __r
 // =====================================================================================
 constexpr int kCoefVecRows = 4 * 16;   // per-warp shared vectors of the coefficient kernel: gS', gmu', mu_t, mu_{t-1}
 
-// reciprocal without the IEEE-division slow path: MUFU.RCP + one Newton step (<= 1 ulp for the normal-range operands here)
-__device__ __forceinline__ float fast_rcp(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r * fmaf(-x, r, 2.f);
-}
-
 // shared-memory load the compiler may not hoist out of a loop (the 16-warp coefficient kernel has 128 registers: hoisting
 // the 64 loop-invariant per-j vector elements makes it spill)
 template <bool kPin>
@@ -761,13 +761,13 @@ __device__ __forceinline__ float lds_vec(const float* p) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int kNWc>
+template <int kNWc, int kPitch>
 __global__ void __launch_bounds__(kNWc * 32, 1) em_routing_bwd_coef_kernel(const float* __restrict__ caps, const float* __restrict__ W,
                                                                       const float* __restrict__ dout, float* __restrict__ state,
                                                                       float* __restrict__ dcaps, float* __restrict__ dbeta_u,
                                                                       float* __restrict__ dbeta_a, long long b, int C) {
   extern __shared__ __align__(16) float sm[];
-  const int wst = routing_pitch(C);
+  constexpr int wst = kPitch;
   constexpr int nw = kNWc;
   constexpr bool kPin = kNWc >= 12;
   float* sW = sm;                                               // [32][16][wst] (+8)
@@ -996,7 +996,7 @@ __device__ __forceinline__ void final_gv(const float* __restrict__ sv, int ia, i
 
 __device__ __forceinline__ void final_tail(const float* __restrict__ sv, const float* __restrict__ scap, const float* __restrict__ sW,
                                            int i, int lane, int wst, bool active, float invC, float gRtot0, float gc0, float rn0,
-                                           const float (&V)[16], float* __restrict__ dcl, float (&dWacc)[16]) {
+                                           const float (&V)[16], float* __restrict__ dcl, float* __restrict__ dWacc) {
     // iteration 0's activation gradient: r^0 = 1/C
     const float grn = active ? gc0 + gRtot0 : 0.f;
     const float dot2 = warp_sum(grn * rn0);
@@ -1015,10 +1015,12 @@ __device__ __forceinline__ void final_tail(const float* __restrict__ sv, const f
     for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float g = dWacc[kk * 4 + c];
+        // owner-thread accumulator in shared memory ([component][thread]: conflict-free); in registers the two pairs'
+        // 32 accumulators pushed the kernel past 128 registers (spills in the location loop)
+        float g = dWacc[(kk * 4 + c) * (kFinWarps * 32)];
 #pragma unroll
         for (int r = 0; r < 4; ++r) g = fmaf(M[r * 4 + kk], V[r * 4 + c], g);
-        dWacc[kk * 4 + c] = g;
+        dWacc[(kk * 4 + c) * (kFinWarps * 32)] = g;
       }
     // dM_i[r][kk] = sum_j (gV_ij W_ij^T)[r][kk]: 16 sums over the 32 lanes by recursive halving
     float P[16];
@@ -1047,17 +1049,20 @@ __device__ __forceinline__ void final_tail(const float* __restrict__ sv, const f
     if ((lane & 1) == 0) dcl[i * 16 + (lane >> 1)] = P[0];
 }
 
+template <int kPitch>
 __global__ void __launch_bounds__(kFinWarps * 32, 1) em_routing_bwd_final_kernel(const float* __restrict__ caps, const float* __restrict__ W,
                                                                                  const float* __restrict__ state, float* __restrict__ dcaps,
                                                                                  float* __restrict__ dW, long long b, int C) {
   extern __shared__ __align__(128) float sm[];
-  const int wst = routing_pitch(C);
+  constexpr int wst = kPitch;
   float* stage0 = sm;                                   // [2][kFinStage]
   float* sW = sm + 2 * kFinStage;                       // [32][16][wst] (+8)
   uint64_t* full = reinterpret_cast<uint64_t*>(sW + kB * 16 * wst + 8);
+  float* sdW = sW + kB * 16 * wst + 8 + 4;              // [2][16][512] weight-gradient accumulators of the threads' two pairs
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool active = lane < C;
   for (int idx = threadIdx.x; idx < kB * 16 * wst + 8; idx += blockDim.x) sW[idx] = 0.f;
+  for (int idx = threadIdx.x; idx < 2 * 16 * kFinWarps * 32; idx += blockDim.x) sdW[idx] = 0.f;
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
@@ -1075,9 +1080,8 @@ __global__ void __launch_bounds__(kFinWarps * 32, 1) em_routing_bwd_final_kernel
     bulk_g2s(smem_u32(stage0 + kStS), caps + (long long)blockIdx.x * 544, kCapBytes, &full[0]);
   }
   __syncthreads();
-  float dWacc0[16], dWacc1[16];
-#pragma unroll
-  for (int h = 0; h < 16; ++h) dWacc0[h] = dWacc1[h] = 0.f;
+  float* dWacc0 = sdW + threadIdx.x;
+  float* dWacc1 = sdW + 16 * kFinWarps * 32 + threadIdx.x;
   const float invC = 1.f / (float)C;
   int it = 0;
   for (long long loc = blockIdx.x; loc < b; loc += gridDim.x, ++it) {
@@ -1107,8 +1111,8 @@ __global__ void __launch_bounds__(kFinWarps * 32, 1) em_routing_bwd_final_kernel
   if (active) {
 #pragma unroll
     for (int h = 0; h < 16; ++h) {
-      atomicAdd(dW + ((long long)w * C + lane) * 16 + h, dWacc0[h]);
-      atomicAdd(dW + ((long long)(w + kFinWarps) * C + lane) * 16 + h, dWacc1[h]);
+      atomicAdd(dW + ((long long)w * C + lane) * 16 + h, dWacc0[h * (kFinWarps * 32)]);
+      atomicAdd(dW + ((long long)(w + kFinWarps) * C + lane) * 16 + h, dWacc1[h * (kFinWarps * 32)]);
     }
   }
 }
@@ -1274,23 +1278,25 @@ static int routing_fwd_impl(const float* caps, const float* W, const float* beta
       wenv = e ? atoi(e) : 0;
     }
     // one CTA per SM; measured at 12 800 locations, C = 24: 8 warps 1.01 ms, 12 warps 0.885 ms, 16 warps 0.80 ms
-    const int kw = C > 24 ? 8 : (wenv == 12 || wenv == 8 || wenv == 10 ? wenv : 16);
+    const int kw = C > 24 ? 8 : (wenv == 12 || wenv == 8 ? wenv : 16);
     const size_t smw = (size_t)(kB * 16 * wst + 8 + kw * 544 + kw * (kB * wst + 8)) * sizeof(float);
-    static bool cfgw = false;
-    if (!cfgw) {
-      cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd(warp) attr");
-      cfgw = true;
-    }
     long long gridw = b2c_num_sms();
     if (gridw * kw > b) gridw = (b + kw - 1) / kw;
-    if (kw == 16) em_routing_fwd_warp_kernel<16><<<(unsigned)gridw, 512, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
-    else if (kw == 12) em_routing_fwd_warp_kernel<12><<<(unsigned)gridw, 384, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
-    else if (kw == 10) em_routing_fwd_warp_kernel<10><<<(unsigned)gridw, 320, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
-    else em_routing_fwd_warp_kernel<8><<<(unsigned)gridw, 256, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C);
+#define B2C_RFWD(KW_, P_)                                                                                                          \
+  do {                                                                                                                             \
+    static bool cfg_ = false;                                                                                                      \
+    if (!cfg_) {                                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(em_routing_fwd_warp_kernel<KW_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_fwd(warp) attr");                                                 \
+      cfg_ = true;                                                                                                                 \
+    }                                                                                                                              \
+    em_routing_fwd_warp_kernel<KW_, P_><<<(unsigned)gridw, KW_ * 32, smw, (cudaStream_t)s>>>(caps, W, beta_u, beta_a, out, state, b, C); \
+  } while (0)
+    if (wst == 32) B2C_RFWD(8, 32);
+    else if (kw == 16) B2C_RFWD(16, 24);
+    else if (kw == 12) B2C_RFWD(12, 24);
+    else B2C_RFWD(8, 24);
+#undef B2C_RFWD
     b2c_launches_add(1);
     B2C_LAUNCH_CHECK("em_routing_fwd(warp)");
     return 0;
@@ -1343,33 +1349,33 @@ static int routing_bwd_impl(const float* caps, const float* W, const float* beta
       nw_env = e ? atoi(e) : 0;
     }
     // measured (12 800 locations, C = 24): 16 warps / 128 registers 0.68 ms, 12 warps / 168 registers 0.51 ms
-    const int nw = C > 24 ? 8 : (nw_env == 16 || nw_env == 10 || nw_env == 8 ? nw_env : 12);
+    const int nw = C > 24 ? 8 : (nw_env == 16 || nw_env == 8 ? nw_env : 12);
     const size_t sm1 = (size_t)(kB * 16 * wst + 8 + nw * 544 + nw * (kCoefVecRows * wst + 8) + nw * 64) * sizeof(float);
-    const size_t sm2 = (size_t)(2 * kFinStage + kB * 16 * wst + 8) * sizeof(float) + 16;
-    static bool cfg2 = false;
-    if (!cfg2) {
-      cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(em_routing_bwd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
-      if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_bwd(split) attr");
-      cfg2 = true;
-    }
+    const size_t sm2 = (size_t)(2 * kFinStage + kB * 16 * wst + 8 + 4 + 2 * 16 * kFinWarps * 32) * sizeof(float);
     long long g1 = b2c_num_sms();
     if (g1 * nw > b) g1 = (b + nw - 1) / nw;
-    if (nw == 16)
-      em_routing_bwd_coef_kernel<16><<<(unsigned)g1, 512, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
-    else if (nw == 12)
-      em_routing_bwd_coef_kernel<12><<<(unsigned)g1, 384, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
-    else if (nw == 10)
-      em_routing_bwd_coef_kernel<10><<<(unsigned)g1, 320, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
-    else
-      em_routing_bwd_coef_kernel<8><<<(unsigned)g1, 256, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u, dbeta_a, b, C);
-    B2C_LAUNCH_CHECK("em_routing_bwd(coef)");
     long long g2 = b2c_num_sms();
     if (g2 > b) g2 = b;
-    em_routing_bwd_final_kernel<<<(unsigned)g2, kFinWarps * 32, sm2, (cudaStream_t)s>>>(caps, W, state, dcaps, dW, b, C);
+#define B2C_RBWD(NW_, P_)                                                                                                          \
+  do {                                                                                                                             \
+    static bool cfg_ = false;                                                                                                      \
+    if (!cfg_) {                                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(em_routing_bwd_coef_kernel<NW_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (e == cudaSuccess)                                                                                                        \
+        e = cudaFuncSetAttribute(em_routing_bwd_final_kernel<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);        \
+      if (e != cudaSuccess) return b2c_cuda_check(e, "em_routing_bwd(split) attr");                                                \
+      cfg_ = true;                                                                                                                 \
+    }                                                                                                                              \
+    em_routing_bwd_coef_kernel<NW_, P_><<<(unsigned)g1, NW_ * 32, sm1, (cudaStream_t)s>>>(caps, W, dout, state, dcaps, dbeta_u,     \
+                                                                                          dbeta_a, b, C);                        \
+    B2C_LAUNCH_CHECK("em_routing_bwd(coef)");                                                                                      \
+    em_routing_bwd_final_kernel<P_><<<(unsigned)g2, kFinWarps * 32, sm2, (cudaStream_t)s>>>(caps, W, state, dcaps, dW, b, C);       \
+  } while (0)
+    if (wst == 32) B2C_RBWD(8, 32);
+    else if (nw == 16) B2C_RBWD(16, 24);
+    else if (nw == 8) B2C_RBWD(8, 24);
+    else B2C_RBWD(12, 24);
+#undef B2C_RBWD
     b2c_launches_add(2);
     B2C_LAUNCH_CHECK("em_routing_bwd(final)");
     return 0;
