@@ -324,6 +324,10 @@ def run_ours(args):
 
     # ---- kernel-level timing: the dominant family (tcgen05 implicit GEMM) and every bandwidth-class kernel ------------
     roofline = None
+    if rank != 0 and not args.no_kernel_timing:
+        # the instrumented eager step below all-reduces its gradients: every rank has to run it (rank 0 alone deadlocks NCCL)
+        step(db["data"], db["fl_data"], db["action"], db["seg"], db["labels"], epoch=1)
+        torch.cuda.synchronize()
     if rank == 0 and not args.no_kernel_timing:
         peaks = {}
         try:

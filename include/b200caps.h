@@ -195,21 +195,27 @@ int b2c_bn_sums(const void* x, int64_t rows, int32_t C, int64_t row_stride, int3
 int b2c_bn_finalize(const float* ws, int32_t ws_C, int32_t c_off, int32_t C, int32_t groups, int64_t rows_per_group,
                     float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
                     b2c_stream_t s);
+/* _sums and _finalize in one launch: the block that publishes its partial sums last computes mean / rstd / running stats */
+int b2c_bn_sums_finalize(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
+                         float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
+                         b2c_stream_t s);
 /* y = relu((x-mean)*rstd*gamma+beta) written into a concat slot */
 int b2c_bn_relu_apply(const void* x, int64_t rows, int32_t C, int64_t x_row_stride, int32_t x_c_off, int32_t groups,
                       const float* mean, const float* rstd, const float* gamma, const float* beta, void* y,
                       int64_t y_row_stride, int32_t y_c_off, int32_t relu, b2c_stream_t s);
-/* backward: pass 1 reduces sum(dyr) and sum(dyr*xhat) (dyr = dy * (y>0)); ws fp32 [groups][2][C] zeroed */
+/* backward: pass 1 reduces sum(dyr) and sum(dyr*xhat) (dyr = dy * (y>0)); ws fp32 [groups][2][C] zeroed.
+ * y == NULL with relu: both passes recompute the mask y > 0 from x with the forward's own arithmetic (gamma, beta needed)
+ * instead of reading y -- a third / a quarter less traffic. */
 int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_row_stride, int32_t dy_c_off, const void* y, int64_t y_row_stride,
                            int32_t y_c_off, const void* x, int64_t x_row_stride, int32_t x_c_off, int64_t rows,
-                           int32_t C, int32_t groups, const float* mean, const float* rstd, float* ws, int32_t relu,
-                           b2c_stream_t s);
+                           int32_t C, int32_t groups, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, float* ws, int32_t relu, b2c_stream_t s);
 /* pass 2: dx = gamma*rstd*(dyr - s1/M - xhat*s2/M); also dgamma += sum_g s2, dbeta += sum_g s1 */
 int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_row_stride, int32_t dy_c_off, const void* y, int64_t y_row_stride,
                           int32_t y_c_off, const void* x, int64_t x_row_stride, int32_t x_c_off, int64_t rows,
                           int32_t C, int32_t groups, const float* mean, const float* rstd, const float* gamma,
-                          const float* ws, void* dx, int64_t dx_row_stride, int32_t dx_c_off, float* dgamma,
-                          float* dbeta, int32_t relu, b2c_stream_t s);
+                          const float* beta, const float* ws, void* dx, int64_t dx_row_stride, int32_t dx_c_off,
+                          float* dgamma, float* dbeta, int32_t relu, b2c_stream_t s);
 
 /* MaxPool3dSamePadding (pytorch_i3d.py:13-45): zero 'same' padding then max; idx = uint8 argmax tap
  * (255 = a padding zero won).  */

@@ -62,10 +62,11 @@ _SIGS = {
     "b2c_u8_to_f32": [vp, vp, i64, f32, vp],
     "b2c_im2col_small": [vp, vp] + [i32] * 19 + [vp],
     "b2c_bn_sums": [vp, i64, i32, i64, i32, i32, vp, vp],
+    "b2c_bn_sums_finalize": [vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp],
     "b2c_bn_finalize": [vp, i32, i32, i32, i32, i64, vp, vp, vp, vp, f32, f32, vp],
     "b2c_bn_relu_apply": [vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, i64, i32, i32, vp],
-    "b2c_bn_relu_bwd_reduce": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, i32, vp, vp, vp, i32, vp],
-    "b2c_bn_relu_bwd_apply": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, i64, i32,
+    "b2c_bn_relu_bwd_reduce": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp],
+    "b2c_bn_relu_bwd_apply": [vp, i64, i32, vp, i64, i32, vp, i64, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32,
                               vp, vp, i32, vp],
     "b2c_maxpool_fwd": [vp, i64, i32, vp, i64, i32, vp] + [i32] * 17 + [vp],
     "b2c_maxpool_bwd": [vp, i64, i32, vp, vp, i64, i32] + [i32] * 18 + [vp],

@@ -459,7 +459,8 @@ def unit_bwd(layer: ConvLayer, gamma, beta, sv: UnitSaved, x: View, y: View, gy:
     draw = torch.empty_like(sv.raw)
     dgamma, d1 = grad_buf(gamma)
     dbeta, d2 = grad_buf(beta)
-    ops.bn_relu_bwd(gy, y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), ws, View(draw), dgamma, dbeta, relu=True)
+    ops.bn_relu_bwd(gy, None if BN_REMASK else y, raw, sv.groups, sv.mean, sv.rstd, gamma.detach(), beta.detach(), ws, View(draw), dgamma,
+                    dbeta, relu=True)
     dw, d0 = grad_buf(layer.weight)
     if isinstance(layer, StemLayer):
         assert dx is None, "the few-channel stem does not propagate a gradient to its input"
@@ -589,7 +590,8 @@ def bn_bwd_part(raw: View, y: View, gy: View, draw: View, m, mean, rstd, g: int)
     ws = zeros_f32((g, 2, raw.C), raw.t.device)
     dgamma, d1 = grad_buf(m.bn.weight)
     dbeta, d2 = grad_buf(m.bn.bias)
-    ops.bn_relu_bwd(gy, y, raw, g, mean, rstd, m.bn.weight.detach(), ws, draw, dgamma, dbeta, relu=True)
+    ops.bn_relu_bwd(gy, None if BN_REMASK else y, raw, g, mean, rstd, m.bn.weight.detach(), m.bn.bias.detach(), ws, draw, dgamma, dbeta,
+                    relu=True)
     return (None if d1 else dgamma), (None if d2 else dbeta)
 
 
@@ -599,6 +601,8 @@ def bn_bwd_part(raw: View, y: View, gy: View, draw: View, m, mean, rstd, g: int)
 FUSE_SIBLINGS = os.environ.get("B2C_FUSE_SIBLINGS", "1") != "0"
 # PrimaryCaps forward: K (the 81 taps) split over this many scheduling classes (B2C_PC_KSPLIT=1: one class, fused epilogue)
 PC_KSPLIT = int(os.environ.get("B2C_PC_KSPLIT", "8"))
+# BatchNorm backward recomputes the ReLU mask from the raw convolution output instead of reading y (B2C_BN_REMASK=0: read y)
+BN_REMASK = os.environ.get("B2C_BN_REMASK", "1") != "0"
 # weight gradients of a fused layer's members in one wgrad launch (B2C_FUSED_WGRAD=0: one launch per member)
 FUSED_WGRAD = os.environ.get("B2C_FUSED_WGRAD", "1") != "0"
 

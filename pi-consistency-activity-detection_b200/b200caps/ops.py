@@ -233,20 +233,29 @@ def stem_unfold_wgrad(dw2, dw, cout, cin, kt, khw, st, To, Kf):
 
 
 # ---- batch norm -----------------------------------------------------------------------------
+BN_FUSE_FINALIZE = os.environ.get("B2C_BN_FUSE_FINALIZE", "1") != "0"
+
+
 def bn_relu_fwd(x: View, groups, ws, mean, rstd, rm, rv, momentum, eps, gamma, beta, y: View, relu=True):
-    """Train-mode BatchNorm + ReLU of the view x into the view y: statistics, finalize (mean / rstd (groups, C) for the
-    backward, running stats), apply.  Three launches on purpose: a fused single launch with a grid barrier between the
+    """Train-mode BatchNorm + ReLU of the view x into the view y: statistics + finalize (mean / rstd (groups, C) for the
+    backward, running stats; done by the statistics launch's last block), apply.  Two launches on purpose: a fused single launch with a grid barrier between the
     statistics and the apply pass was built and measured slower in the captured step (cooperative launch 22.9 ms, ordinary
     launch + hand-rolled barrier 22.2 ms, separate launches 21.5 ms per step: the barrier wait exceeds what the next
     launch's overlap with this one's tail already hides)."""
-    bn_sums(x, groups, ws)
-    bn_finalize(ws, x.C, 0, x.C, groups, x.rows // groups, mean, rstd, rm, rv, momentum, eps)
+    if BN_FUSE_FINALIZE:
+        _bw("b2c_bn_sums_finalize", _vb(x), x.ptr, x.rows, x.C, x.row_stride, x.c_off, groups, _p(ws), _p(mean), _p(rstd), _p(rm), _p(rv),
+            float(momentum), float(eps), stream())
+    else:
+        bn_sums(x, groups, ws)
+        bn_finalize(ws, x.C, 0, x.C, groups, x.rows // groups, mean, rstd, rm, rv, momentum, eps)
     bn_relu_apply(x, groups, mean, rstd, gamma, beta, y, relu)
 
 
-def bn_relu_bwd(dy: View, y: View, x: View, groups, mean, rstd, gamma, ws, dx: View, dgamma, dbeta, relu=True):
-    bn_relu_bwd_reduce(dy, y, x, groups, mean, rstd, ws, relu)
-    bn_relu_bwd_apply(dy, y, x, groups, mean, rstd, gamma, ws, dx, dgamma, dbeta, relu)
+def bn_relu_bwd(dy: View, y, x: View, groups, mean, rstd, gamma, beta, ws, dx: View, dgamma, dbeta, relu=True):
+    """Backward of bn_relu_fwd.  y = None: the kernels recompute the ReLU mask from x (forward's own arithmetic) instead of
+    reading y -- 2 instead of 3 and 3 instead of 4 tensor passes."""
+    bn_relu_bwd_reduce(dy, y, x, groups, mean, rstd, ws, relu, gamma, beta)
+    bn_relu_bwd_apply(dy, y, x, groups, mean, rstd, gamma, ws, dx, dgamma, dbeta, relu, beta)
 
 
 def bn_sums(x: View, groups: int, ws: torch.Tensor):
@@ -263,15 +272,16 @@ def bn_relu_apply(x: View, groups, mean, rstd, gamma, beta, y: View, relu=True):
               _p(beta), y.ptr, y.row_stride, y.c_off, int(relu), stream())
 
 
-def bn_relu_bwd_reduce(dy: View, y: View, x: View, groups, mean, rstd, ws, relu=True):
-    _bw("b2c_bn_relu_bwd_reduce", 3 * _vb(x), dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
-              x.row_stride, x.c_off, x.rows, x.C, groups, _p(mean), _p(rstd), _p(ws), int(relu), stream())
+def bn_relu_bwd_reduce(dy: View, y, x: View, groups, mean, rstd, ws, relu=True, gamma=None, beta=None):
+    _bw("b2c_bn_relu_bwd_reduce", (3 if y is not None else 2) * _vb(x), dy.ptr, dy.row_stride, dy.c_off, y.ptr if y is not None else None,
+        y.row_stride if y is not None else 0, y.c_off if y is not None else 0, x.ptr, x.row_stride, x.c_off, x.rows, x.C, groups,
+        _p(mean), _p(rstd), _p(gamma), _p(beta), _p(ws), int(relu), stream())
 
 
-def bn_relu_bwd_apply(dy: View, y: View, x: View, groups, mean, rstd, gamma, ws, dx: View, dgamma, dbeta, relu=True):
-    _bw("b2c_bn_relu_bwd_apply", 4 * _vb(x), dy.ptr, dy.row_stride, dy.c_off, y.ptr, y.row_stride, y.c_off, x.ptr,
-              x.row_stride, x.c_off, x.rows, x.C, groups, _p(mean), _p(rstd), _p(gamma), _p(ws), dx.ptr, dx.row_stride,
-              dx.c_off, _p(dgamma), _p(dbeta), int(relu), stream())
+def bn_relu_bwd_apply(dy: View, y, x: View, groups, mean, rstd, gamma, ws, dx: View, dgamma, dbeta, relu=True, beta=None):
+    _bw("b2c_bn_relu_bwd_apply", (4 if y is not None else 3) * _vb(x), dy.ptr, dy.row_stride, dy.c_off, y.ptr if y is not None else None,
+        y.row_stride if y is not None else 0, y.c_off if y is not None else 0, x.ptr, x.row_stride, x.c_off, x.rows, x.C, groups,
+        _p(mean), _p(rstd), _p(gamma), _p(beta), _p(ws), dx.ptr, dx.row_stride, dx.c_off, _p(dgamma), _p(dbeta), int(relu), stream())
 
 
 # ---- pooling / elementwise ------------------------------------------------------------------

@@ -126,9 +126,20 @@ __global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ in, long long in_row
 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm statistics: grid (blocks, groups)
+// finalize arguments of bn_stats_kernel (mean == nullptr: statistics only, a bn_finalize launch follows)
+struct BnFinalize {
+  float* mean;
+  float* rstd;
+  float* running_mean;
+  float* running_var;
+  float momentum, eps;
+  int groups;
+};
+__device__ unsigned g_bn_blocks_done = 0;   // blocks of the running bn_stats launch that have published their sums
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T* __restrict__ x, long long rows_per_group, int C,
-                                                          long long row_stride, int c_off, float* __restrict__ ws) {
+                                                          long long row_stride, int c_off, float* __restrict__ ws, BnFinalize F) {
   const int CV = C / 8;
   const RowMap m = row_map(CV);
   const int g = blockIdx.y;
@@ -164,6 +175,37 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T* __restrict__ 
     for (int r = 0; r < m.rpb; ++r) t += sh[(size_t)r * 2 * C + i];
     atomicAdd(&w[i], t);
   }
+  if (F.mean == nullptr) return;
+  // The block that publishes last turns the sums into mean / rstd / running statistics (bn_finalize_kernel's arithmetic):
+  // one launch less per layer.  These launches run one at a time on the step's stream, so one counter serves them all.
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&g_bn_blocks_done, 1u);
+    s_last = done == gridDim.x * gridDim.y - 1;
+    if (s_last) g_bn_blocks_done = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double M = (double)rows_per_group;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float rm = F.running_mean ? F.running_mean[c] : 0.f, rv = F.running_var ? F.running_var[c] : 0.f;
+    for (int gg = 0; gg < F.groups; ++gg) {
+      const double s1 = __ldcg(ws + (long long)gg * 2 * C + c), s2 = __ldcg(ws + (long long)gg * 2 * C + C + c);
+      const double mu = s1 / M;
+      double var = s2 / M - mu * mu;
+      if (var < 0) var = 0;
+      F.mean[gg * C + c] = (float)mu;
+      F.rstd[gg * C + c] = (float)(1.0 / sqrt(var + (double)F.eps));
+      const double unb = rows_per_group > 1 ? var * M / (M - 1.0) : var;
+      rm = (1.f - F.momentum) * rm + F.momentum * (float)mu;
+      rv = (1.f - F.momentum) * rv + F.momentum * (float)unb;
+    }
+    if (F.running_mean) F.running_mean[c] = rm;
+    if (F.running_var) F.running_var[c] = rv;
+  }
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ ws_all, int ws_C, int c_off, long long rows_per_group, int C,
@@ -190,6 +232,13 @@ __global__ void bn_finalize_kernel(const float* __restrict__ ws_all, int ws_C, i
   if (running_var) running_var[c] = rv;
 }
 
+// y = fma(x, sc, sf) with sc = rstd * gamma, sf = fma(-mean, sc, beta): ONE definition, because the backward kernels
+// recompute the ReLU mask (y > 0) from x with it instead of reading y back (a quarter / a third of their traffic)
+__device__ __forceinline__ void bn_scale_shift(float mean, float rstd, float gamma, float beta, float& sc, float& sf) {
+  sc = rstd * gamma;
+  sf = fmaf(-mean, sc, beta);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const T* __restrict__ x, long long rows_per_group, int C,
                                                                long long x_rs, int x_co, const float* __restrict__ mean,
@@ -204,8 +253,7 @@ __global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const T* __restri
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = m.cv * 8 + j;
-    sc[j] = rstd[g * C + c] * gamma[c];
-    sf[j] = beta[c] - mean[g * C + c] * sc[j];
+    bn_scale_shift(mean[g * C + c], rstd[g * C + c], gamma[c], beta[c], sc[j], sf[j]);
   }
   const long long row0 = (long long)g * rows_per_group;
   for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
@@ -213,7 +261,7 @@ __global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const T* __restri
     ld8(x + (row0 + r) * x_rs + x_co + m.cv * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[j] = v[j] * sc[j] + sf[j];
+      v[j] = fmaf(v[j], sc[j], sf[j]);
       if (relu) v[j] = fmaxf(v[j], 0.f);
     }
     st8(y + (row0 + r) * y_rs + y_co + m.cv * 8, v, true);          // next conv's operand
@@ -225,27 +273,31 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const T* __restri
                                                                const T* __restrict__ y, long long y_rs, int y_co,
                                                                const T* __restrict__ x, long long x_rs, int x_co,
                                                                long long rows_per_group, int C, const float* __restrict__ mean,
-                                                               const float* __restrict__ rstd, float* __restrict__ ws, int relu) {
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ ws, int relu) {
   const int CV = C / 8;
   const RowMap m = row_map(CV);
   const int g = blockIdx.y;
-  float s1[8], s2[8], mu[8], rs[8];
+  const bool remask = relu && y == nullptr;     // ReLU mask recomputed from x (see bn_scale_shift)
+  float s1[8], s2[8], mu[8], rs[8], sc[8], sf[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = sc[j] = sf[j] = 0.f;
   if (m.active) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       mu[j] = mean[g * C + m.cv * 8 + j];
       rs[j] = rstd[g * C + m.cv * 8 + j];
+      if (remask) bn_scale_shift(mu[j], rs[j], gamma[m.cv * 8 + j], beta[m.cv * 8 + j], sc[j], sf[j]);
     }
     const long long row0 = (long long)g * rows_per_group;
     for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
       float d[8], yy[8], xx[8];
       ld8(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8, d);
       ld8(x + (row0 + r) * x_rs + x_co + m.cv * 8, xx);
-      if (relu) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
+      if (relu && !remask) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        if (remask) yy[j] = fmaf(xx[j], sc[j], sf[j]);
         const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
         s1[j] += dr;
         s2[j] += dr * (xx[j] - mu[j]) * rs[j];
@@ -276,9 +328,9 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restric
                                                               const T* __restrict__ x, long long x_rs, int x_co,
                                                               long long rows_per_group, int C, int groups,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                              const float* __restrict__ gamma, const float* __restrict__ ws,
-                                                              T* __restrict__ dx, long long dx_rs, int dx_co, float* dgamma,
-                                                              float* dbeta, int relu) {
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ ws, T* __restrict__ dx, long long dx_rs,
+                                                              int dx_co, float* dgamma, float* dbeta, int relu) {
   const int CV = C / 8;
   const RowMap m = row_map(CV);
   const int g = blockIdx.y;
@@ -295,12 +347,15 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restric
   }
   if (!m.active) return;
   const float invM = 1.f / (float)rows_per_group;
-  float mu[8], rs[8], k0[8], a1[8], a2[8];
+  const bool remask = relu && y == nullptr;
+  float mu[8], rs[8], k0[8], a1[8], a2[8], sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = m.cv * 8 + j;
     mu[j] = mean[g * C + c];
     rs[j] = rstd[g * C + c];
+    sc[j] = sf[j] = 0.f;
+    if (remask) bn_scale_shift(mu[j], rs[j], gamma[c], beta[c], sc[j], sf[j]);
     k0[j] = gamma[c] * rs[j];
     a1[j] = ws[(long long)g * 2 * C + c] * invM;
     a2[j] = ws[(long long)g * 2 * C + C + c] * invM;
@@ -310,9 +365,10 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restric
     float d[8], yy[8], xx[8], o[8];
     ld8(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8, d);
     ld8(x + (row0 + r) * x_rs + x_co + m.cv * 8, xx);
-    if (relu) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
+    if (relu && !remask) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      if (remask) yy[j] = fmaf(xx[j], sc[j], sf[j]);
       const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
       o[j] = k0[j] * (dr - a1[j] - (xx[j] - mu[j]) * rs[j] * a2[j]);
     }
@@ -1172,20 +1228,35 @@ B2C_API int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_
   return 0;
 }
 
+static int bn_stats_launch(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
+                           BnFinalize F, b2c_stream_t s) {
+  const long long rpg = rows / groups;
+  dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
+  if (b2c_precision())
+    bn_stats_kernel<float><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const float*)x, rpg, C, row_stride, c_off, ws, F);
+  else
+    bn_stats_kernel<bf16><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws, F);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("bn_sums");
+  return 0;
+}
+
 B2C_API int b2c_bn_sums(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
                         b2c_stream_t s) {
   B2C_REQUIRE(x && ws, "bn_sums: null pointer");
   CHECK_VIEW("bn_sums", C, row_stride, c_off);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_sums: rows=%lld not divisible by groups=%d", (long long)rows, groups);
-  const long long rpg = rows / groups;
-  dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
-  if (b2c_precision())
-    bn_stats_kernel<float><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const float*)x, rpg, C, row_stride, c_off, ws);
-  else
-    bn_stats_kernel<bf16><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const bf16*)x, rpg, C, row_stride, c_off, ws);
-  b2c_launches_add(1);
-  B2C_LAUNCH_CHECK("bn_sums");
-  return 0;
+  return bn_stats_launch(x, rows, C, row_stride, c_off, groups, ws, BnFinalize{nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, groups}, s);
+}
+
+B2C_API int b2c_bn_sums_finalize(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
+                                 float* mean, float* rstd, float* running_mean, float* running_var, float momentum, float eps,
+                                 b2c_stream_t s) {
+  B2C_REQUIRE(x && ws && mean && rstd, "bn_sums_finalize: null pointer");
+  CHECK_VIEW("bn_sums_finalize", C, row_stride, c_off);
+  B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_sums_finalize: rows=%lld not divisible by groups=%d", (long long)rows, groups);
+  return bn_stats_launch(x, rows, C, row_stride, c_off, groups, ws, BnFinalize{mean, rstd, running_mean, running_var, momentum, eps, groups},
+                         s);
 }
 
 B2C_API int b2c_bn_finalize(const float* ws, int32_t ws_C, int32_t c_off, int32_t C, int32_t groups, int64_t rows_per_group,
@@ -1217,14 +1288,15 @@ B2C_API int b2c_bn_relu_apply(const void* x, int64_t rows, int32_t C, int64_t x_
 
 B2C_API int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_rs, int32_t dy_co, const void* y, int64_t y_rs, int32_t y_co,
                                    const void* x, int64_t x_rs, int32_t x_co, int64_t rows, int32_t C, int32_t groups,
-                                   const float* mean, const float* rstd, float* ws, int32_t relu, b2c_stream_t s) {
-  B2C_REQUIRE(dy && x && mean && rstd && ws && (y || !relu), "bn_bwd_reduce: null pointer");
+                                   const float* mean, const float* rstd, const float* gamma, const float* beta, float* ws,
+                                   int32_t relu, b2c_stream_t s) {
+  B2C_REQUIRE(dy && x && mean && rstd && ws && (y || !relu || (gamma && beta)), "bn_bwd_reduce: null pointer");
   CHECK_VIEW("bn_bwd_reduce(dy)", C, dy_rs, dy_co);
   CHECK_VIEW("bn_bwd_reduce(x)", C, x_rs, x_co);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_reduce: rows not divisible by groups");
   const long long rpg = rows / groups;
   dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
-  LAUNCH_T(bn_bwd_reduce_kernel, grid, kBlock, bn_red_smem(C), s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, mean, rstd, ws, relu);
+  LAUNCH_T(bn_bwd_reduce_kernel, grid, kBlock, bn_red_smem(C), s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, mean, rstd, gamma, beta, ws, relu);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_bwd_reduce");
   return 0;
@@ -1232,15 +1304,15 @@ B2C_API int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_rs, int32_t dy_co,
 
 B2C_API int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_rs, int32_t dy_co, const void* y, int64_t y_rs, int32_t y_co,
                                   const void* x, int64_t x_rs, int32_t x_co, int64_t rows, int32_t C, int32_t groups,
-                                  const float* mean, const float* rstd, const float* gamma, const float* ws, void* dx,
-                                  int64_t dx_rs, int32_t dx_co, float* dgamma, float* dbeta, int32_t relu, b2c_stream_t s) {
-  B2C_REQUIRE(dy && x && dx && mean && rstd && gamma && ws && (y || !relu), "bn_bwd_apply: null pointer");
+                                  const float* mean, const float* rstd, const float* gamma, const float* beta, const float* ws,
+                                  void* dx, int64_t dx_rs, int32_t dx_co, float* dgamma, float* dbeta, int32_t relu, b2c_stream_t s) {
+  B2C_REQUIRE(dy && x && dx && mean && rstd && gamma && ws && (y || !relu || beta), "bn_bwd_apply: null pointer");
   CHECK_VIEW("bn_bwd_apply(dy)", C, dy_rs, dy_co);
   CHECK_VIEW("bn_bwd_apply(dx)", C, dx_rs, dx_co);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_apply: rows not divisible by groups");
   const long long rpg = rows / groups;
   dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
-  LAUNCH_T(bn_bwd_apply_kernel, grid, kBlock, 0, s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, groups, mean, rstd, gamma, ws, (T*)dx, dx_rs, dx_co, dgamma, dbeta, relu);
+  LAUNCH_T(bn_bwd_apply_kernel, grid, kBlock, 0, s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, groups, mean, rstd, gamma, beta, ws, (T*)dx, dx_rs, dx_co, dgamma, dbeta, relu);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_bwd_apply");
   return 0;

@@ -78,3 +78,23 @@ def test_allreduced_gradient_is_mean_of_per_rank_gradients():
         print(f"rank {rank}: all-reduced grad / world vs mean of single-GPU grads: rel-L2 {dev_rel:.2e}, max {dev_max:.2e}; same weights {same}")
         # atomics in the weight-gradient kernels make two runs of the same step differ by fp32 rounding only
         assert dev_rel < 1e-3 and dev_max < 1e-2 and same
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_bench_runs_under_torchrun_on_two_gpus():
+    """`bench.py --gpus 2` exactly as the driver launches it (torchrun, one rank per GPU), with every leg enabled: each
+    collective has to be entered by both ranks (the instrumented eager step of the kernel-timing leg all-reduces its
+    gradients; run on rank 0 alone it deadlocked NCCL)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29300 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "3", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["roofline"]["frac"] > 0

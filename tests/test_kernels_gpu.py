@@ -77,6 +77,24 @@ def test_batchnorm_relu_fwd_bwd(C, groups):
     ops.bn_relu_bwd_apply(View(gy), View(y, C, C), xv, groups, mean, rstd, gamma, ws2, View(dx), dg, db, relu=True)
     # relu mask may differ where y ~ 0 in bf16; compare with a tolerance on the bulk
     assert rel(dx, gx_ref) < 3e-2
+    # statistics + finalize in one launch (last block finalizes) == the two launches
+    rm2, rv2 = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    ws5 = torch.zeros(groups, 2, C, device=dev())
+    mean2, rstd2 = torch.empty_like(mean), torch.empty_like(rstd)
+    y2 = torch.zeros_like(y)
+    for _ in range(2):          # twice: the block counter must return to zero
+        rm2.zero_(); rv2.fill_(1.0); ws5.zero_()
+        ops.bn_relu_fwd(xv, groups, ws5, mean2, rstd2, rm2, rv2, 0.01, 1e-3, gamma, beta, View(y2, C, C), relu=True)
+        assert rel(mean2, mean) < 1e-5 and rel(rstd2, rstd) < 1e-5 and rel(rm2, rm) < 1e-5 and rel(rv2, rv) < 1e-5
+        assert rel(y2[..., C:], y[..., C:]) < 1e-2
+    # y = None: the backward recomputes the ReLU mask from x with the forward's arithmetic -- bit-identical results
+    ws3 = torch.zeros(groups, 2, C, device=dev())
+    ops.bn_relu_bwd_reduce(View(gy), None, xv, groups, mean, rstd, ws3, relu=True, gamma=gamma, beta=beta)
+    dx3 = torch.empty_like(x)
+    dg3, db3 = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    ops.bn_relu_bwd_apply(View(gy), None, xv, groups, mean, rstd, gamma, ws3, View(dx3), dg3, db3, relu=True, beta=beta)
+    # (the sums meet in a different atomic order: last-bit differences only)
+    assert rel(dx3, dx) < 1e-3 and rel(dg3, dg) < 1e-5 and rel(db3, db) < 1e-5
 
 
 @pytest.mark.parametrize("k,s,dims", [((1, 3, 3), (1, 2, 2), (2, 12, 12)), ((3, 3, 3), (1, 1, 1), (2, 7, 7)),
