@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const T* __restri
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
+template <typename T, bool kRemask>
+__global__ void __launch_bounds__(kBlock, kRemask ? 3 : 4) bn_bwd_reduce_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
                                                                const T* __restrict__ y, long long y_rs, int y_co,
                                                                const T* __restrict__ x, long long x_rs, int x_co,
                                                                long long rows_per_group, int C, const float* __restrict__ mean,
@@ -278,16 +278,16 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const T* __restri
   const int CV = C / 8;
   const RowMap m = row_map(CV);
   const int g = blockIdx.y;
-  const bool remask = relu && y == nullptr;     // ReLU mask recomputed from x (see bn_scale_shift)
-  float s1[8], s2[8], mu[8], rs[8], sc[8], sf[8];
+  constexpr bool remask = kRemask;              // ReLU mask recomputed from x (see bn_scale_shift); relu is set then
+  float s1[8], s2[8], mu[8], rs[8], sc[kRemask ? 8 : 1], sf[kRemask ? 8 : 1];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = sc[j] = sf[j] = 0.f;
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (m.active) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       mu[j] = mean[g * C + m.cv * 8 + j];
       rs[j] = rstd[g * C + m.cv * 8 + j];
-      if (remask) bn_scale_shift(mu[j], rs[j], gamma[m.cv * 8 + j], beta[m.cv * 8 + j], sc[j], sf[j]);
+      if constexpr (kRemask) bn_scale_shift(mu[j], rs[j], gamma[m.cv * 8 + j], beta[m.cv * 8 + j], sc[j], sf[j]);
     }
     const long long row0 = (long long)g * rows_per_group;
     for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const T* __restri
       if (relu && !remask) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (remask) yy[j] = fmaf(xx[j], sc[j], sf[j]);
+        if constexpr (kRemask) yy[j] = fmaf(xx[j], sc[j], sf[j]);
         const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
         s1[j] += dr;
         s2[j] += dr * (xx[j] - mu[j]) * rs[j];
@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const T* __restri
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
+template <typename T, bool kRemask>
+__global__ void __launch_bounds__(kBlock, 3) bn_bwd_apply_kernel(const T* __restrict__ dy, long long dy_rs, int dy_co,
                                                               const T* __restrict__ y, long long y_rs, int y_co,
                                                               const T* __restrict__ x, long long x_rs, int x_co,
                                                               long long rows_per_group, int C, int groups,
@@ -347,15 +347,14 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restric
   }
   if (!m.active) return;
   const float invM = 1.f / (float)rows_per_group;
-  const bool remask = relu && y == nullptr;
-  float mu[8], rs[8], k0[8], a1[8], a2[8], sc[8], sf[8];
+  constexpr bool remask = kRemask;
+  float mu[8], rs[8], k0[8], a1[8], a2[8], sc[kRemask ? 8 : 1], sf[kRemask ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = m.cv * 8 + j;
     mu[j] = mean[g * C + c];
     rs[j] = rstd[g * C + c];
-    sc[j] = sf[j] = 0.f;
-    if (remask) bn_scale_shift(mu[j], rs[j], gamma[c], beta[c], sc[j], sf[j]);
+    if constexpr (kRemask) bn_scale_shift(mu[j], rs[j], gamma[c], beta[c], sc[j], sf[j]);
     k0[j] = gamma[c] * rs[j];
     a1[j] = ws[(long long)g * 2 * C + c] * invM;
     a2[j] = ws[(long long)g * 2 * C + C + c] * invM;
@@ -368,7 +367,7 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(const T* __restric
     if (relu && !remask) ld8(y + (row0 + r) * y_rs + y_co + m.cv * 8, yy);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (remask) yy[j] = fmaf(xx[j], sc[j], sf[j]);
+      if constexpr (kRemask) yy[j] = fmaf(xx[j], sc[j], sf[j]);
       const float dr = (!relu || yy[j] > 0.f) ? d[j] : 0.f;
       o[j] = k0[j] * (dr - a1[j] - (xx[j] - mu[j]) * rs[j] * a2[j]);
     }
@@ -1296,7 +1295,19 @@ B2C_API int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_rs, int32_t dy_co,
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_reduce: rows not divisible by groups");
   const long long rpg = rows / groups;
   dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
-  LAUNCH_T(bn_bwd_reduce_kernel, grid, kBlock, bn_red_smem(C), s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, mean, rstd, gamma, beta, ws, relu);
+#define B2C_BN_BWD_REDUCE(T, RM)                                                                                              \
+  bn_bwd_reduce_kernel<T, RM><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, \
+                                                                               (const T*)x, x_rs, x_co, rpg, C, mean, rstd, gamma,   \
+                                                                               beta, ws, relu)
+  const bool remask = relu && y == nullptr;
+  if (b2c_precision()) {
+    if (remask) B2C_BN_BWD_REDUCE(float, true);
+    else B2C_BN_BWD_REDUCE(float, false);
+  } else {
+    if (remask) B2C_BN_BWD_REDUCE(bf16, true);
+    else B2C_BN_BWD_REDUCE(bf16, false);
+  }
+#undef B2C_BN_BWD_REDUCE
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_bwd_reduce");
   return 0;
@@ -1312,7 +1323,19 @@ B2C_API int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_rs, int32_t dy_co, 
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_apply: rows not divisible by groups");
   const long long rpg = rows / groups;
   dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
-  LAUNCH_T(bn_bwd_apply_kernel, grid, kBlock, 0, s, (const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, x_rs, x_co, rpg, C, groups, mean, rstd, gamma, beta, ws, (T*)dx, dx_rs, dx_co, dgamma, dbeta, relu);
+#define B2C_BN_BWD_APPLY(T, RM)                                                                                              \
+  bn_bwd_apply_kernel<T, RM><<<grid, kBlock, 0, (cudaStream_t)s>>>((const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, \
+                                                                 x_rs, x_co, rpg, C, groups, mean, rstd, gamma, beta, ws, (T*)dx,    \
+                                                                 dx_rs, dx_co, dgamma, dbeta, relu)
+  const bool remask = relu && y == nullptr;
+  if (b2c_precision()) {
+    if (remask) B2C_BN_BWD_APPLY(float, true);
+    else B2C_BN_BWD_APPLY(float, false);
+  } else {
+    if (remask) B2C_BN_BWD_APPLY(bf16, true);
+    else B2C_BN_BWD_APPLY(bf16, false);
+  }
+#undef B2C_BN_BWD_APPLY
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_bwd_apply");
   return 0;
