@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T* __restrict__ 
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (m.active) {
     const T* base = x + (long long)g * rows_per_group * row_stride + c_off + m.cv * 8;
+#pragma unroll 4
     for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
       float v[8];
       ld8(base + r * row_stride, v);
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(kBlock, kRemask ? 3 : 4) bn_bwd_reduce_kernel(
       if constexpr (kRemask) bn_scale_shift(mu[j], rs[j], gamma[m.cv * 8 + j], beta[m.cv * 8 + j], sc[j], sf[j]);
     }
     const long long row0 = (long long)g * rows_per_group;
+#pragma unroll 2
     for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
       float d[8], yy[8], xx[8];
       ld8(dy + (row0 + r) * dy_rs + dy_co + m.cv * 8, d);
@@ -881,12 +883,17 @@ __global__ void __launch_bounds__(kBlock) clips_to_folded_kernel(const S* __rest
   const int pairs = Tp / 2;
   const float scale = sizeof(S) == 1 ? 1.f / 255.f : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    long long r = i / W;
-    const int q = (int)(r % pairs);
-    r /= pairs;
-    const int h = (int)(r % H);
-    const long long n = r / H;
+    // frame pair fastest: the 8 threads of a pixel write its whole 128-byte row (with w fastest every 16-byte store went to
+    // a different line: in-graph 176 us for 283 MB, r02d_graph_busy.json); the 4-byte reads of 8 planes x 4 pixels per warp
+    // still use full 32-byte sectors across neighbouring warps
+    // (host guarantees total < 2^31: 32-bit divisions -- the emulated 64-bit ones were most of this kernel's instructions)
+    unsigned r = (unsigned)i;
+    const int q = (int)(r % (unsigned)pairs);
+    r /= (unsigned)pairs;
+    const int w = (int)(r % (unsigned)W);
+    r /= (unsigned)W;
+    const int h = (int)(r % (unsigned)H);
+    const long long n = r / (unsigned)H;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -1141,6 +1148,19 @@ inline size_t bn_red_smem(int C) {
   if (rpb < 1) rpb = 1;
   return (size_t)rpb * 2 * C * sizeof(float);
 }
+// grid of the two BatchNorm REDUCTION kernels: every block ends with 2 C fp32 atomics on the same 2 C addresses, which the L2
+// serialises (592 blocks on a 28 x 28 layer: ~6 us of atomics for ~2 us of loads).  At least 8 rows per thread, at most one
+// block per SM and group pair.
+inline int reduce_grid(long long rows, int C, int groups) {
+  int rpb = kBlock / (C / 8);
+  if (rpb < 1) rpb = 1;
+  long long b = (rows + (long long)rpb * 8 - 1) / ((long long)rpb * 8);
+  long long cap = (long long)b2c_num_sms() * 2 / (groups > 0 ? groups : 1);
+  if (cap < 1) cap = 1;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
 inline int row_grid(long long rows, int C, int waves = 4) {
   int rpb = kBlock / (C / 8);
   if (rpb < 1) rpb = 1;
@@ -1230,7 +1250,7 @@ B2C_API int b2c_ndhwc_to_ncdhw_f32(const void* in, int64_t in_row_stride, int32_
 static int bn_stats_launch(const void* x, int64_t rows, int32_t C, int64_t row_stride, int32_t c_off, int32_t groups, float* ws,
                            BnFinalize F, b2c_stream_t s) {
   const long long rpg = rows / groups;
-  dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
+  dim3 grid((unsigned)(g_deterministic ? 1 : reduce_grid(rpg, C, groups)), (unsigned)groups);
   if (b2c_precision())
     bn_stats_kernel<float><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const float*)x, rpg, C, row_stride, c_off, ws, F);
   else
@@ -1294,7 +1314,7 @@ B2C_API int b2c_bn_relu_bwd_reduce(const void* dy, int64_t dy_rs, int32_t dy_co,
   CHECK_VIEW("bn_bwd_reduce(x)", C, x_rs, x_co);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_reduce: rows not divisible by groups");
   const long long rpg = rows / groups;
-  dim3 grid((unsigned)(g_deterministic ? 1 : row_grid(rpg, C, 2)), (unsigned)groups);
+  dim3 grid((unsigned)(g_deterministic ? 1 : reduce_grid(rpg, C, groups)), (unsigned)groups);
 #define B2C_BN_BWD_REDUCE(T, RM)                                                                                              \
   bn_bwd_reduce_kernel<T, RM><<<grid, kBlock, bn_red_smem(C), (cudaStream_t)s>>>((const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, \
                                                                                (const T*)x, x_rs, x_co, rpg, C, mean, rstd, gamma,   \
@@ -1466,6 +1486,7 @@ B2C_API int b2c_clips_to_folded(const void* in, int32_t in_u8, void* xs, int32_t
   B2C_REQUIRE(in && xs && P > 0 && C > 0 && C <= 4 && T > 0 && Tp > 0 && Tp % 2 == 0 && Tp <= 16 && pt >= 0 && pt + T <= Tp,
               "clips_to_folded: bad args");
   const long long total = (long long)P * H * (Tp / 2) * W;
+  B2C_REQUIRE(total < (1LL << 31), "clips_to_folded: too many elements for the 32-bit index split");
   const int tf = b2c_precision();
   if (in_u8) {
     if (tf) clips_to_folded_kernel<float, uint8_t><<<grid_for(total), kBlock, 0, (cudaStream_t)s>>>((const uint8_t*)in, (float*)xs, P, C, T, H, W, pt, Tp, mirror, total);
