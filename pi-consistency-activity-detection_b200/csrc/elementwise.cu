@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kBlock) bn_relu_apply_kernel(const T* __restri
     bn_scale_shift(mean[g * C + c], rstd[g * C + c], gamma[c], beta[c], sc[j], sf[j]);
   }
   const long long row0 = (long long)g * rows_per_group;
+#pragma unroll 4
   for (long long r = (long long)blockIdx.x * m.rpb + m.rlane; r < rows_per_group; r += (long long)gridDim.x * m.rpb) {
     float v[8];
     ld8(x + (row0 + r) * x_rs + x_co + m.cv * 8, v);
@@ -599,14 +600,28 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_row_kernel(const T* __rest
         for (int b = 0; b < KH; ++b) {
           const int ih = oh * SH - G.ph + b;
           const bool row_ok = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi;
+          if (!row_ok) {
+            // CTA-uniform: the whole tap row is padding (18 of the 27 taps of the single-frame 3x3x3 pools).  Only the first
+            // padding tap of the window can win, so the row is at most one zero candidate.
+            if (!seen_pad) {
+              seen_pad = true;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t zero = 0u;
+                const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&zero),
+                                               *reinterpret_cast<const __nv_bfloat162*>(&best2[j]));
+                best2[j] = best2[j] & ~m;
+                idx2[j] = (0x00ff00ffu & m) | (idx2[j] & ~m);
+              }
+            }
+            continue;
+          }
           const bf16* xrow = x + (((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi * x_rs + x_co + cv * 8;
 #pragma unroll
           for (int c = 0; c < KW; ++c) {
-            constexpr int kDummy = 0;
-            (void)kDummy;
             const int tap = (a * KH + b) * KW + c;
             const int iw = ow * SW - G.pw + c;
-            const bool inb = row_ok && (unsigned)iw < (unsigned)G.Wi;
+            const bool inb = (unsigned)iw < (unsigned)G.Wi;
             if (!inb) {
               if (seen_pad) continue;
               seen_pad = true;
@@ -645,12 +660,24 @@ __global__ void __launch_bounds__(kBlock) maxpool_fwd_row_kernel(const T* __rest
         for (int b = 0; b < KH; ++b) {
           const int ih = oh * SH - G.ph + b;
           const bool row_ok = (unsigned)it < (unsigned)G.Ti && (unsigned)ih < (unsigned)G.Hi;
+          if (!row_ok) {          // CTA-uniform padding row: at most one zero candidate (see the bf16 branch)
+            if (!seen_pad) {
+              seen_pad = true;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (0.f > best[j]) {
+                  best[j] = 0.f;
+                  bidx[j] = 0xffu;
+                }
+            }
+            continue;
+          }
           const T* xrow = x + (((long long)n * G.Ti + it) * G.Hi + ih) * G.Wi * x_rs + x_co + cv * 8;
 #pragma unroll
           for (int c = 0; c < KW; ++c) {
             const int tap = (a * KH + b) * KW + c;
             const int iw = ow * SW - G.pw + c;
-            const bool inb = row_ok && (unsigned)iw < (unsigned)G.Wi;
+            const bool inb = (unsigned)iw < (unsigned)G.Wi;
             if (!inb) {
               if (seen_pad) continue;
               seen_pad = true;
@@ -1161,6 +1188,18 @@ inline int reduce_grid(long long rows, int C, int groups) {
   if (b < 1) b = 1;
   return (int)b;
 }
+// grid of the two BatchNorm APPLY kernels: every thread first gathers its 8 channels' statistics / affine parameters (up to 48
+// scalar loads), so give it at least 4 rows to stream; at most 4 blocks per SM over all groups.
+inline int apply_grid(long long rows, int C, int groups) {
+  int rpb = kBlock / (C / 8);
+  if (rpb < 1) rpb = 1;
+  long long b = (rows + (long long)rpb * 4 - 1) / ((long long)rpb * 4);
+  long long cap = (long long)b2c_num_sms() * 4 / (groups > 0 ? groups : 1);
+  if (cap < 1) cap = 1;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
 inline int row_grid(long long rows, int C, int waves = 4) {
   int rpb = kBlock / (C / 8);
   if (rpb < 1) rpb = 1;
@@ -1298,7 +1337,7 @@ B2C_API int b2c_bn_relu_apply(const void* x, int64_t rows, int32_t C, int64_t x_
   CHECK_VIEW("bn_relu_apply(y)", C, y_rs, y_co);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_relu_apply: rows not divisible by groups");
   const long long rpg = rows / groups;
-  dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
+  dim3 grid((unsigned)apply_grid(rpg, C, groups), (unsigned)groups);
   LAUNCH_T(bn_relu_apply_kernel, grid, kBlock, 0, s, (const T*)x, rpg, C, x_rs, x_co, mean, rstd, gamma, beta, (T*)y, y_rs, y_co, relu);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("bn_relu_apply");
@@ -1342,7 +1381,7 @@ B2C_API int b2c_bn_relu_bwd_apply(const void* dy, int64_t dy_rs, int32_t dy_co, 
   CHECK_VIEW("bn_bwd_apply(dx)", C, dx_rs, dx_co);
   B2C_REQUIRE(groups >= 1 && rows % groups == 0, "bn_bwd_apply: rows not divisible by groups");
   const long long rpg = rows / groups;
-  dim3 grid((unsigned)row_grid(rpg, C), (unsigned)groups);
+  dim3 grid((unsigned)apply_grid(rpg, C, groups), (unsigned)groups);
 #define B2C_BN_BWD_APPLY(T, RM)                                                                                              \
   bn_bwd_apply_kernel<T, RM><<<grid, kBlock, 0, (cudaStream_t)s>>>((const T*)dy, dy_rs, dy_co, (const T*)y, y_rs, y_co, (const T*)x, \
                                                                  x_rs, x_co, rpg, C, groups, mean, rstd, gamma, beta, ws, (T*)dx,    \
