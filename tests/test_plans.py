@@ -159,3 +159,24 @@ def test_folded_stem_plan_geometry():
     assert pl.in_dims == (1, 224, 224) and pl.out_dims == (4, 112, 112) and len(pl.fprop) == 1 and len(pl.fprop[0].taps) == 49
     assert pl.fprop_pack["R"] == 256 and pl.fprop_pack["out_fold"] == 64 and pl.wgrad_geom["p_fold"] == 64
     assert pl.fprop[0].wtap == [i * 64 for i in range(49)]
+
+
+def test_split_fprop_k_partitions_the_taps():
+    """ConvPlan.split_fprop_k (PrimaryCaps forward): the K slices hold every tap exactly once in the original order, share
+    the output grid, write to consecutive output frames, and leave the wgrad class (all taps) untouched."""
+    from b200caps.plans import ConvPlan, ConvSpec
+    pl = ConvPlan(ConvSpec(832, 544, (1, 9, 9)), (1, 28, 28))
+    full = pl.fprop[0]
+    taps, wtap = list(full.taps), list(full.wtap)
+    assert len(taps) == 81 and pl.out_dims == (1, 20, 20)
+    pl.split_fprop_k(8)
+    assert len(pl.fprop) == 8 and pl.fprop_out_dims == (8, 20, 20)
+    assert sum((c.taps for c in pl.fprop), []) == taps and sum((c.wtap for c in pl.fprop), []) == wtap
+    assert [c.po for c in pl.fprop] == [(s, 0, 0) for s in range(8)] and all(c.Q == full.Q for c in pl.fprop)
+    assert {len(c.taps) for c in pl.fprop} <= {10, 11}
+    assert pl.wgrad_cls is full and len(pl.wgrad_cls.taps) == 81
+    assert pl.macs_fprop(2) == 2 * 400 * 81 * 832 * 544
+    # one slice = no split
+    p1 = ConvPlan(ConvSpec(832, 544, (1, 9, 9)), (1, 28, 28))
+    p1.split_fprop_k(1)
+    assert len(p1.fprop) == 1 and not hasattr(p1, "fprop_out_dims")
