@@ -169,14 +169,17 @@ __global__ void __launch_bounds__(256) tail_gather_bwd_kernel(const float* __res
                                                               int Iw, long long total) {
   constexpr int kGroups = 9;   // 36 (ct, ch) pairs / 4
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int grp = (int)(idx % kGroups);
-    long long pos = idx / kGroups;
-    const int iw = (int)(pos % Iw);
-    long long r = pos / Iw;
-    const int ih = (int)(r % Ih);
-    r /= Ih;
-    const int it = (int)(r % It);
-    const int n = (int)(r / It);
+    // (host guarantees total < 2^31: 32-bit divisions instead of emulated 64-bit ones)
+    const unsigned u = (unsigned)idx;
+    const int grp = (int)(u % (unsigned)kGroups);
+    const unsigned upos = u / (unsigned)kGroups;
+    const long long pos = upos;
+    const int iw = (int)(upos % (unsigned)Iw);
+    unsigned r = upos / (unsigned)Iw;
+    const int ih = (int)(r % (unsigned)Ih);
+    r /= (unsigned)Ih;
+    const int it = (int)(r % (unsigned)It);
+    const int n = (int)(r / (unsigned)It);
     const int Ot = 2 * It, Oh = 2 * Ih, Ow = 2 * Iw;
     float v[24];
 #pragma unroll
@@ -384,6 +387,7 @@ B2C_API int b2c_tail_gather_bwd(const float* dlogits, void* dy, float* class_sum
                                 b2c_stream_t s) {
   B2C_REQUIRE(dlogits && dy && class_sums && N > 0 && It > 0 && Ih > 0 && Iw > 0, "tail_gather_bwd: bad args");
   const long long total = (long long)N * It * Ih * Iw * 9;
+  B2C_REQUIRE(total < (1LL << 31), "tail_gather_bwd: too many elements for the 32-bit index split");
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)b2c_num_sms() * 32;
   if (blocks > cap) blocks = cap;

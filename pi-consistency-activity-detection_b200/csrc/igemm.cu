@@ -1251,6 +1251,28 @@ __global__ void pack_weights_batched_kernel(const b2c_pack_job* __restrict__ job
   // (host guarantees R * ntaps * C < 2^31: 32-bit index arithmetic)
   const unsigned total = (unsigned)J.R * (unsigned)J.ntaps * (unsigned)J.C;
   const unsigned C = (unsigned)J.C, ntaps = (unsigned)J.ntaps, bn = (unsigned)J.bn_tile;
+  if (J.dtype == 0 && (C & 7u) == 0 && (J.tap_pitch & 7) == 0 && (J.col_off & 7) == 0) {
+    // bf16 operands, 8 consecutive K elements per thread = one 16-byte unit of the swizzled image: one index split and one
+    // store per 8 elements (the element-wise loop below was instruction bound: 0.41 ms for the step's 96 M elements)
+    const unsigned C8 = C >> 3, total8 = (unsigned)J.R * ntaps * C8;
+    bf16* __restrict__ pk = reinterpret_cast<bf16*>(packed);
+    for (unsigned i = (unsigned)bidx * blockDim.x + threadIdx.x; i < total8; i += (unsigned)nblk * blockDim.x) {
+      const unsigned t2 = i / C8, c = (i - t2 * C8) << 3;
+      const unsigned r = t2 / ntaps, t = t2 - r * ntaps;
+      const float* src = w + (long long)r * J.s_r + (long long)c * J.s_c + wtap[t];
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((int)c + j < J.C_real) ? __ldg(src + (long long)j * J.s_c) : 0.f;
+      const unsigned rg = r + (unsigned)J.r_off;
+      const unsigned tile = rg / bn, rr = rg - tile * bn;
+      const long long k = (long long)t * J.tap_pitch + J.col_off + c;
+      const int kb = (int)(k >> 6), kk = (int)(k & 63);
+      const long long off = ((long long)tile * J.nkb + kb) * ((long long)J.bn_tile * 64) + (rr >> 3) * 512 + (rr & 7) * 64 +
+                            (((kk >> 3) ^ (rr & 7)) << 3);
+      *reinterpret_cast<uint4*>(pk + off) = pack8(v);
+    }
+    return;
+  }
   for (unsigned i = (unsigned)bidx * blockDim.x + threadIdx.x; i < total; i += (unsigned)nblk * blockDim.x) {
     const unsigned t2 = i / C, c = i - t2 * C;
     const unsigned r = t2 / ntaps, t = t2 - r * ntaps;
