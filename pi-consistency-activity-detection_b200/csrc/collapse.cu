@@ -218,22 +218,49 @@ __global__ void __launch_bounds__(256) tail_gather_bwd_kernel(const float* __res
   }
 }
 
-// per-clip sums of dlogits over the 27 border classes (gradient of the bias field); one block per (n, ot, oh) row
-__global__ void __launch_bounds__(128) tail_class_sums_kernel(const float* __restrict__ g, float* __restrict__ sums, int Ot, int Oh,
+// per-clip sums of dlogits over the 27 border classes (gradient of the bias field); one block per (n, ot) plane: every thread
+// keeps the 9 (oh class, ow class) sums of the elements it walks, the block reduces them and issues 9 atomics (one block
+// per ROW was 57 344 blocks of 128 threads for 224 floats each: 71 us in the captured step).
+__global__ void __launch_bounds__(256) tail_class_sums_kernel(const float* __restrict__ g, float* __restrict__ sums, int Ot, int Oh,
                                                               int Ow) {
-  const int oh = blockIdx.x % Oh, ot = (blockIdx.x / Oh) % Ot, n = blockIdx.x / (Oh * Ot);
-  const float* row = g + (long long)blockIdx.x * Ow;
-  float acc = 0.f;
-  for (int w = 1 + threadIdx.x; w < Ow - 1; w += blockDim.x) acc += row[w];
-  acc = warp_sum(acc);
-  __shared__ float sh[4];
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  const int ot = blockIdx.x % Ot, n = blockIdx.x / Ot;
+  const float* plane = g + (long long)blockIdx.x * Oh * Ow;
+  float acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.f;
+  // whole rows per warp: lane walks the row with stride 32, so the ow class is known per element and the oh class per row
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int oh = w; oh < Oh; oh += 8) {
+    const int ch = border_class(oh, Oh);
+    const float* row = plane + (long long)oh * Ow;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int x = lane; x < Ow; x += 32) {
+      const float v = row[x];
+      if (x == 0) a0 += v;
+      else if (x == Ow - 1) a2 += v;
+      else a1 += v;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (ch == q) {
+        acc[q * 3 + 0] += a0;
+        acc[q * 3 + 1] += a1;
+        acc[q * 3 + 2] += a2;
+      }
+  }
+  __shared__ float sh[8][9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const float t = warp_sum(acc[q]);
+    if (lane == 0) sh[w][q] = t;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int cb = n * 27 + (border_class(ot, Ot) * 3 + border_class(oh, Oh)) * 3;
-    atomicAdd(sums + cb + 1, sh[0] + sh[1] + sh[2] + sh[3]);
-    atomicAdd(sums + cb + 0, row[0]);
-    atomicAdd(sums + cb + 2, row[Ow - 1]);
+  if (threadIdx.x < 9) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += sh[ww][threadIdx.x];
+    const int cb = n * 27 + border_class(ot, Ot) * 9;
+    atomicAdd(sums + cb + threadIdx.x, t);
   }
 }
 
@@ -246,64 +273,82 @@ __global__ void __launch_bounds__(128) tail_class_sums_kernel(const float* __res
 __global__ void __launch_bounds__(256) tail_chain_kernel(const float* __restrict__ dweff, const float* __restrict__ w4,
                                                          const float* __restrict__ ws, const float* __restrict__ drop,
                                                          float* __restrict__ dw4, float* __restrict__ dws, int N) {
+  // grid (ci, clip groups).  dT rows are padded to 28 floats and read as float4 (all threads read the same row: the
+  // broadcast loads were this kernel's bound -- 729 per thread and clip, 164 us in the captured step).
   __shared__ float dW[216];
-  __shared__ float dT[27 * 27];
+  __shared__ __align__(16) float dT[27 * 28];
   const int ci = blockIdx.x, tid = threadIdx.x;
   const int c = tid & 127;
   const bool second = tid >= 128;
-  float coef[27], acc[27];
+  float coef[28], acc[27];
 #pragma unroll
   for (int j = 0; j < 27; ++j) {
     coef[j] = second ? w4[((size_t)ci * kC + c) * 27 + j] : ws[c * 27 + j];
     acc[j] = 0.f;
   }
-  for (int n = 0; n < N; ++n) {
+  coef[27] = 0.f;
+  const int per = (N + gridDim.y - 1) / gridDim.y;
+  const int n_lo = blockIdx.y * per, n_hi = min(N, n_lo + per);
+  for (int n = n_lo; n < n_hi; ++n) {
     __syncthreads();
     if (tid < 216) dW[tid] = dweff[((size_t)n * kC + ci) * kTailCols + tid];
     __syncthreads();
-    for (int idx = tid; idx < 729; idx += 256) {
-      const int k = idx / 27, m = idx - k * 27;
-      const int kd[3] = {k / 9, (k / 3) % 3, k % 3}, md[3] = {m / 9, (m / 3) % 3, m % 3};
-      int cols[3][2], nc[3];
-#pragma unroll
-      for (int dd = 0; dd < 3; ++dd) {
-        cols[dd][0] = kd[dd] + md[dd];
-        nc[dd] = 1;
-        if (kd[dd] + md[dd] == 2 && kd[dd] >= 1) cols[dd][nc[dd]++] = 5;
-      }
+    for (int idx = tid; idx < 27 * 28; idx += 256) {
+      const int k = idx / 28, m = idx - k * 28;
       float s = 0.f;
-      for (int a = 0; a < nc[0]; ++a)
-        for (int b = 0; b < nc[1]; ++b)
-          for (int e = 0; e < nc[2]; ++e) s += dW[(cols[0][a] * 6 + cols[1][b]) * 6 + cols[2][e]];
+      if (m < 27) {
+        const int kd[3] = {k / 9, (k / 3) % 3, k % 3}, md[3] = {m / 9, (m / 3) % 3, m % 3};
+        int cols[3][2], nc[3];
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) {
+          cols[dd][0] = kd[dd] + md[dd];
+          nc[dd] = 1;
+          if (kd[dd] + md[dd] == 2 && kd[dd] >= 1) cols[dd][nc[dd]++] = 5;
+        }
+        for (int a = 0; a < nc[0]; ++a)
+          for (int b = 0; b < nc[1]; ++b)
+            for (int e = 0; e < nc[2]; ++e) s += dW[(cols[0][a] * 6 + cols[1][b]) * 6 + cols[2][e]];
+      }
       dT[idx] = s;
     }
     __syncthreads();
     const float dr = drop[n * kC + c];
     if (dr != 0.f) {
-      if (!second) {
-        // dW4[ci][c][k] += dr * sum_m Ws[c][m] dT[k][m]
+      float tmp[28];
 #pragma unroll
-        for (int k = 0; k < 27; ++k) {
-          float s = 0.f;
+      for (int m = 0; m < 28; ++m) tmp[m] = 0.f;
 #pragma unroll
-          for (int m = 0; m < 27; ++m) s = fmaf(coef[m], dT[k * 27 + m], s);
-          acc[k] = fmaf(dr, s, acc[k]);
+      for (int k = 0; k < 27; ++k) {
+        float row[28];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(dT + k * 28 + q * 4);
+          row[q * 4 + 0] = v.x; row[q * 4 + 1] = v.y; row[q * 4 + 2] = v.z; row[q * 4 + 3] = v.w;
         }
-      } else {
-        // dWs[c][m] += dr * sum_k W4[ci][c][k] dT[k][m]
+        if (!second) {
+          // dW4[ci][c][k] += dr * sum_m Ws[c][m] dT[k][m]
+          float sk = 0.f;
 #pragma unroll
-        for (int m = 0; m < 27; ++m) {
-          float s = 0.f;
+          for (int m = 0; m < 27; ++m) sk = fmaf(coef[m], row[m], sk);
+          acc[k] = fmaf(dr, sk, acc[k]);
+        } else {
+          // dWs[c][m] += dr * sum_k W4[ci][c][k] dT[k][m]
 #pragma unroll
-          for (int k = 0; k < 27; ++k) s = fmaf(coef[k], dT[k * 27 + m], s);
-          acc[m] = fmaf(dr, s, acc[m]);
+          for (int m = 0; m < 27; ++m) tmp[m] = fmaf(coef[k], row[m], tmp[m]);
         }
+      }
+      if (second) {
+#pragma unroll
+        for (int m = 0; m < 27; ++m) acc[m] = fmaf(dr, tmp[m], acc[m]);
       }
     }
   }
   if (!second) {
 #pragma unroll
-    for (int k = 0; k < 27; ++k) dw4[((size_t)ci * kC + c) * 27 + k] += acc[k];
+    for (int k = 0; k < 27; ++k) {
+      if (gridDim.y == 1) dw4[((size_t)ci * kC + c) * 27 + k] += acc[k];
+      else atomicAdd(dw4 + ((size_t)ci * kC + c) * 27 + k, acc[k]);
+    }
   } else {
 #pragma unroll
     for (int m = 0; m < 27; ++m) atomicAdd(dws + c * 27 + m, acc[m]);
@@ -396,7 +441,7 @@ B2C_API int b2c_tail_gather_bwd(const float* dlogits, void* dy, float* class_sum
   else
     tail_gather_bwd_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(dlogits, (bf16*)dy, N, It, Ih, Iw, total);
   B2C_LAUNCH_CHECK("tail_gather_bwd");
-  tail_class_sums_kernel<<<(unsigned)(N * 4 * It * Ih), 128, 0, (cudaStream_t)s>>>(dlogits, class_sums, 2 * It, 2 * Ih, 2 * Iw);
+  tail_class_sums_kernel<<<(unsigned)(N * 2 * It), 256, 0, (cudaStream_t)s>>>(dlogits, class_sums, 2 * It, 2 * Ih, 2 * Iw);
   b2c_launches_add(2);
   B2C_LAUNCH_CHECK("tail_class_sums");
   return 0;
@@ -406,7 +451,8 @@ B2C_API int b2c_tail_chain_bwd(const float* dweff, const float* class_sums, cons
                                const float* drop_nc, float* dw4, float* db4, float* dws, float* dbs, int32_t N, b2c_stream_t s) {
   B2C_REQUIRE(dweff && class_sums && w4 && b4 && ws && drop_nc && dw4 && db4 && dws && dbs && N > 0 && N * 27 * 4 <= 40000,
               "tail_chain_bwd: bad args");
-  tail_chain_kernel<<<kC, 256, 0, (cudaStream_t)s>>>(dweff, w4, ws, drop_nc, dw4, dws, N);
+  const int groups = N >= 16 ? 4 : (N >= 4 ? 2 : 1);      // clip groups: 128 x 4 CTAs fill the 148 SMs three deep
+  tail_chain_kernel<<<dim3(kC, groups), 256, 0, (cudaStream_t)s>>>(dweff, w4, ws, drop_nc, dw4, dws, N);
   B2C_LAUNCH_CHECK("tail_chain");
   tail_bias_chain_kernel<<<1, 128, (size_t)N * 27 * sizeof(float), (cudaStream_t)s>>>(class_sums, b4, ws, drop_nc, db4, dws, dbs, N);
   b2c_launches_add(2);
