@@ -47,8 +47,9 @@ typedef struct {
   int32_t Qt, Qh, Qw;       /* GEMM-M grid of this class */
   int32_t po_t, po_h, po_w; /* output offset of this class */
   int32_t lo_t, lo_h, lo_w; /* per-dimension minimum tap offset (lower corner of the im2col TMA box) */
-  int32_t h_block;          /* 0, or: the taps come in consecutive blocks of h_block taps that share (dt, dh), dt the same for all,
-                               dh monotonic -- lets a tile skip the blocks whose source rows are padding for all its rows */
+  int32_t h_block;          /* 0, or > 0: the taps come in consecutive blocks of h_block taps that share (dt, dh), dt the same for
+                               all, dh monotonic -- lets a tile skip the blocks whose source rows are padding for all its rows;
+                               < 0: blocks of -h_block taps share dt (dt monotonic): the same along the T axis */
   int32_t pad_;
 } b2c_conv_class;
 
@@ -274,6 +275,13 @@ int b2c_em_routing_bwd_state(const float* caps, const float* W, const float* bet
  * g * (col >= 512 ? a(1-a) : 1); dbias[544] += column sums (first 512: pose bias, last 32: a bias). */
 int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, int32_t dz_pitch,
                              b2c_stream_t s);
+/* the same, also writing dz with image rows outermost: dz_rows[(h * N + n) * Wq + w] = dz[(n * Hq + h) * Wq + w] (operand of the
+ * rows-major PrimaryCaps dgrad, whose tiles then hold one image row of several clips and skip their padding-only tap rows) */
+int b2c_primarycaps_bwd_prep2(const float* g, const float* out, void* dz, void* dz_rows, float* dbias, int32_t N, int32_t Hq,
+                              int32_t Wq, int32_t dz_pitch, b2c_stream_t s);
+/* (H, N, W, C) -> (N, H, W, C) row permutation of an activation tensor (C % 8 == 0): result of the rows-major dgrad back to
+ * clip-major order */
+int b2c_rows_to_clips(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, b2c_stream_t s);
 /* PrimaryCaps epilogue for the K-split forward: the GEMM's K dimension (the 81 taps) runs as `nslice` scheduling classes
  * that write their partial sums to frames 0..nslice-1 of part fp32 (N, nslice, L, 544); out[n][l][c] = sum_s part[n][s][l][c]
  * + bias[c], sigmoid on the 32 activation columns (capsules_ucf101.py:43-49).  Fixed summation order: bit-reproducible. */

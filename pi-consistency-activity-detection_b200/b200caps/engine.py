@@ -601,6 +601,8 @@ def bn_bwd_part(raw: View, y: View, gy: View, draw: View, m, mean, rstd, g: int)
 FUSE_SIBLINGS = os.environ.get("B2C_FUSE_SIBLINGS", "1") != "0"
 # PrimaryCaps forward: K (the 81 taps) split over this many scheduling classes (B2C_PC_KSPLIT=1: one class, fused epilogue)
 PC_KSPLIT = int(os.environ.get("B2C_PC_KSPLIT", "8"))
+# PrimaryCaps dgrad on (row, clip, column) positions with per-tile skipping of padding-only tap rows (B2C_PC_DGRAD_ROWS=0: clip-major)
+PC_DGRAD_ROWS = os.environ.get("B2C_PC_DGRAD_ROWS", "1") != "0"
 # BatchNorm backward recomputes the ReLU mask from the raw convolution output instead of reading y (B2C_BN_REMASK=0: read y)
 BN_REMASK = os.environ.get("B2C_BN_REMASK", "1") != "0"
 # weight gradients of a fused layer's members in one wgrad launch (B2C_FUSED_WGRAD=0: one launch per member)
@@ -803,6 +805,33 @@ class FusedConvLayer:
         self.keys[(tuple(in_dims), which)] = key
         return pl
 
+    def rows_major_dgrad(self, in_dims, N: int) -> ConvPlan:
+        """dgrad plan of a 2-D layer (T = 1) with the image rows on the kernel's T axis and the N clips on its H axis: GEMM
+        positions then run (row, clip, column), every 128-position tile holds ONE image row of several clips, and the
+        tiles skip the tap rows that are padding for that row (b2c_conv_class.h_block < 0).  PrimaryCaps' 9 x 9 'valid'
+        convolution reads a 20 x 20 gradient from 28 x 28 positions: 29 % of its (tap row, position) pairs are such
+        padding.  Same taps in the same order as the clip-major plan, so both share one packed operand."""
+        in_dims = tuple(int(v) for v in in_dims)
+        key = ("rows", in_dims, int(N))
+        pl = self.plans.get(key)
+        base = self.packed(in_dims, "dgrad")
+        if pl is None:
+            sp = base.spec
+            assert in_dims[0] == 1 and sp.k[0] == 1 and not sp.transposed
+            spec = ConvSpec(sp.Cin, sp.Cout, (sp.k[1], 1, sp.k[2]), (sp.stride[1], 1, sp.stride[2]),
+                            (sp.pad_front[1], 0, sp.pad_front[2]), (sp.pad_back[1], 0, sp.pad_back[2]),
+                            Cin_pad=sp.Cin_pad, Cout_pad=sp.Cout_pad)
+            pl = ConvPlan(spec, (in_dims[1], int(N), in_dims[2]))
+            pl.rows_major = True
+            if self.grad_cpad:
+                pl.dgrad_pack = dict(pl.dgrad_pack, C=self.grad_cpad)
+            assert [c.wtap for c in pl.dgrad] == [c.wtap for c in base.dgrad], "rows-major plan must share the packed operand"
+            self.plans[key] = pl
+        pl = pl.to(self.weights[0].device)
+        for a, b in zip(pl.dgrad, base.dgrad):
+            a.packed = b.packed
+        return pl
+
     def wgrad(self, in_dims, x: View, dy: View) -> List[torch.Tensor]:
         pl = self.plan(in_dims)
         outs = []
@@ -855,14 +884,28 @@ class PrimaryCapsFn(torch.autograd.Function):
         g = g.contiguous().float()
         rows = out.numel() // 544
         cg = layer.grad_cpad or 544
-        dzb = (torch.zeros if cg != 544 else torch.empty)(out.shape[:-1] + (cg,), dtype=act_dtype(), device=out.device)
+        alloc = torch.zeros if cg != 544 else torch.empty
+        dzb = alloc(out.shape[:-1] + (cg,), dtype=act_dtype(), device=out.device)
         dbias = torch.zeros(544, dtype=torch.float32, device=out.device)
-        ops.primarycaps_bwd_prep(g, out, dzb, dbias, rows, cg)
-        dims = x.shape[1:4]
+        dims = tuple(x.shape[1:4])
+        N = x.shape[0]
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and PC_DGRAD_ROWS and dims[0] == 1:
+            # rows-major dgrad (FusedConvLayer.rows_major_dgrad): the prologue also writes dz with image rows outermost,
+            # the GEMM runs on (row, clip, column) positions and skips padding-only tap rows, the result is permuted back
+            Hq, Wq = out.shape[2], out.shape[3]
+            dzb_r = alloc((1, Hq, N, Wq, cg), dtype=act_dtype(), device=out.device)
+            ops.primarycaps_bwd_prep2(g, out, dzb, dzb_r, dbias, N, Hq, Wq, cg)
+            plr = layer.rows_major_dgrad(dims, N)
+            dxr = torch.empty((1, dims[1], N, dims[2], x.shape[-1]), dtype=act_dtype(), device=x.device)
+            ops.conv_fprop(plr, "dgrad", View(dzb_r), View(dxr))
             dx = torch.empty_like(x)
-            ops.conv_fprop(layer.packed(dims, "dgrad"), "dgrad", View(dzb), View(dx))
+            ops.rows_to_clips(dxr, dx, N, dims[1], dims[2], x.shape[-1])
+        else:
+            ops.primarycaps_bwd_prep(g, out, dzb, dbias, rows, cg)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                ops.conv_fprop(layer.packed(dims, "dgrad"), "dgrad", View(dzb), View(dx))
         dwp, dwa = layer.wgrad(dims, View(x), View(dzb))
         dbp, dba = dbias[:512], dbias[512:]
         if STATE.direct_grads and mod.pose.bias.grad is not None:

@@ -308,6 +308,27 @@ class ConvPlan:
                           bn, nkb)
 
 
+def t_block_of(taps) -> int:
+    """Taps per block of constant dt when the tap list is such blocks with strictly monotonic dt (a layer whose image rows
+    sit on the T axis, ConvPlan.rows_major), else 0."""
+    if len(taps) < 2:
+        return 0
+    nw = 1
+    while nw < len(taps) and taps[nw][0] == taps[0][0]:
+        nw += 1
+    if len(taps) % nw or nw == len(taps):
+        return 0
+    dts = []
+    for b in range(len(taps) // nw):
+        blk = taps[b * nw:(b + 1) * nw]
+        if len({t[0] for t in blk}) != 1:
+            return 0
+        dts.append(blk[0][0])
+    inc = all(b > a for a, b in zip(dts, dts[1:]))
+    dec = all(b < a for a, b in zip(dts, dts[1:]))
+    return nw if (inc or dec) else 0
+
+
 def h_block_of(taps) -> int:
     """Taps per block of constant (dt, dh) when the tap list is such blocks with one dt overall and strictly monotonic dh
     (2-D layers in (h, w) product order), else 0.  The kernel then skips blocks that only read padding (b2c_conv_class)."""
@@ -413,7 +434,8 @@ def fill_conv_desc(plan: ConvPlan, which: str, x: View, out: View, bias=None, sc
         c.Qt, c.Qh, c.Qw = cl.Q
         c.po_t, c.po_h, c.po_w = cl.po
         c.lo_t, c.lo_h, c.lo_w = (min(t[i] for t in cl.taps) for i in range(3))
-        c.h_block = h_block_of(cl.taps)
+        # rows-major plans (image rows on the T axis, clips on the H axis): skip padding-only tap rows per tile
+        c.h_block = -t_block_of(cl.taps) if getattr(plan, "rows_major", False) else h_block_of(cl.taps)
     return d
 
 

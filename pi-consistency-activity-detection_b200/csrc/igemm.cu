@@ -194,7 +194,34 @@ __device__ __forceinline__ void tap_range(const b2c_conv_desc& d, const b2c_conv
                                           unsigned m_last, const FastDiv* fd3, int& lo, int& hi) {
   lo = 0;
   hi = cc.ntaps;
-  if (cc.h_block <= 0) return;
+  if (cc.h_block == 0) return;
+  if (cc.h_block < 0) {
+    // blocks of |h_block| taps share one T offset (a 2-D layer presented with its image rows on the T axis and the clips
+    // on the H axis, so that every 128-position tile holds ONE image row of several clips: plans.ConvPlan rows-major)
+    const int hb = -cc.h_block;
+    uint32_t r, t0, t1;
+    uint32_t q0 = fdivmod(m_first, fd3[0], r);
+    uint32_t q1 = fdivmod(m_last, fd3[0], r);
+    q0 = fdivmod(q0, fd3[1], r);
+    q1 = fdivmod(q1, fd3[1], r);
+    q0 = fdivmod(q0, fd3[2], t0);
+    q1 = fdivmod(q1, fd3[2], t1);
+    if (q0 != q1) return;                  // the unit straddles samples
+    const int nb = cc.ntaps / hb;
+    int first = -1, last = -1;
+    for (int b = 0; b < nb; ++b) {
+      const int dt = tap_dt(taps[b * hb]);
+      const bool ok = (int)t1 * d.si_t + dt >= 0 && (int)t0 * d.si_t + dt <= d.Ti - 1;
+      if (ok) {
+        if (first < 0) first = b;
+        last = b;
+      }
+    }
+    if (first < 0) first = last = 0;
+    lo = first * hb;
+    hi = (last + 1) * hb;
+    return;
+  }
   uint32_t r0, r1, h0, h1;
   uint32_t q0 = fdivmod(m_first, fd3[0], r0);
   uint32_t q1 = fdivmod(m_last, fd3[0], r1);
@@ -509,7 +536,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MT * acc_cols);
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
       int nkb = (cc.ntaps * k_pitch + kBK - 1) / kBK;
-      if (use_tma && cc.h_block > 0) {
+      if (use_tma && cc.h_block != 0) {
         int tp_lo, tp_hi;
         unsigned m_last = (unsigned)ti.m0 + (unsigned)(MT * kTileM) - 1u;
         if (m_last >= Mtot) m_last = Mtot - 1u;
@@ -1344,7 +1371,8 @@ B2C_API int b2c_conv_fprop(const b2c_conv_desc* dh, b2c_stream_t stream) {
   const int use_tma = (k_pitch % bk == 0) ? 1 : 0;
   B2C_REQUIRE(!tf32 || (use_tma && d.out_fp32 != 0), "conv_fprop: tf32 mode needs tap_pitch %% 32 == 0 and an fp32 output");
   for (int i = 0; i < d.nclass; ++i)
-    if (d.cls[i].h_block < 0 || !use_tma || (d.cls[i].h_block > 0 && d.cls[i].ntaps % d.cls[i].h_block != 0)) d.cls[i].h_block = 0;
+    if (!use_tma || (d.cls[i].h_block != 0 && d.cls[i].ntaps % (d.cls[i].h_block < 0 ? -d.cls[i].h_block : d.cls[i].h_block) != 0))
+      d.cls[i].h_block = 0;
   if (d.out_fold != 0) {
     B2C_REQUIRE(d.out_fold % kStageChunkCols == 0 && d.Cout % d.out_fold == 0 && d.bn_tile % d.out_fold == 0 && d.nclass == 1 &&
                     d.out_fp32 != 2 && d.cls[0].Qt == 1 && d.so_t == 1 && d.cls[0].po_t + d.Cout / d.out_fold <= d.To && !d.scale_nc,

@@ -1191,7 +1191,8 @@ __global__ void caps_head_bwd_kernel(const T* __restrict__ dx, const float* __re
 // dz = g * (col >= 512 ? a (1 - a) : 1) as bf16 rows for the dgrad / wgrad GEMMs, dbias[col] += sum_rows dz.
 template <typename T>
 __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* __restrict__ g, const float* __restrict__ out,
-                                                                   T* __restrict__ dz, float* __restrict__ dbias, long long rows, int dz_pitch) {
+                                                                   T* __restrict__ dz, float* __restrict__ dbias, long long rows, int dz_pitch,
+                                                                   T* __restrict__ dz_rows, int Nc, int Hq, int Wq) {
   // block = 256 threads: 4 row lanes x 68 column groups of 8 (544 = 68 * 8); threads >= 272 idle
   const int cg = threadIdx.x % 68, rl = threadIdx.x / 68;
   const bool act = rl < 3;
@@ -1215,6 +1216,12 @@ __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* 
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
       store8_act(dz + r * dz_pitch + cg * 8, v);
+      if (dz_rows) {       // second copy with image rows outermost (rows-major dgrad)
+        const int L = Hq * Wq;
+        const int n = (int)(r / L), l = (int)(r - (long long)n * L);
+        const int h = l / Wq, w = l - h * Wq;
+        store8_act(dz_rows + ((long long)(h * Nc + n) * Wq + w) * dz_pitch + cg * 8, v);
+      }
     }
   }
   __shared__ float sh[544];
@@ -1467,10 +1474,59 @@ B2C_API int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz,
   const long long cap = (long long)b2c_num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (b2c_precision())
-    primarycaps_bwd_prep_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (float*)dz, dbias, rows, dz_pitch);
+    primarycaps_bwd_prep_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (float*)dz, dbias, rows, dz_pitch, nullptr, 0, 0, 0);
   else
-    primarycaps_bwd_prep_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows, dz_pitch);
+    primarycaps_bwd_prep_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows, dz_pitch, nullptr, 0, 0, 0);
   b2c_launches_add(1);
   B2C_LAUNCH_CHECK("primarycaps_bwd_prep");
+  return 0;
+}
+
+B2C_API int b2c_primarycaps_bwd_prep2(const float* g, const float* out, void* dz, void* dz_rows, float* dbias, int32_t N, int32_t Hq,
+                                      int32_t Wq, int32_t dz_pitch, b2c_stream_t s) {
+  B2C_REQUIRE(g && out && dz && dz_rows && dbias && N > 0 && Hq > 0 && Wq > 0 && dz_pitch >= 544 && dz_pitch % 8 == 0,
+              "primarycaps_bwd_prep2: bad args");
+  const long long rows = (long long)N * Hq * Wq;
+  long long blocks = (rows + 2) / 3;
+  const long long cap = (long long)b2c_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (b2c_precision())
+    primarycaps_bwd_prep_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (float*)dz, dbias, rows, dz_pitch,
+                                                                                      (float*)dz_rows, N, Hq, Wq);
+  else
+    primarycaps_bwd_prep_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(g, out, (bf16*)dz, dbias, rows, dz_pitch,
+                                                                                     (bf16*)dz_rows, N, Hq, Wq);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("primarycaps_bwd_prep2");
+  return 0;
+}
+
+namespace {
+// (H, N, W, C) -> (N, H, W, C): one 16-byte vector per thread
+__global__ void __launch_bounds__(256) rows_to_clips_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W,
+                                                            int CV, unsigned total) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r = i / (unsigned)CV;
+    const unsigned cv = i - r * (unsigned)CV;
+    const unsigned w = r % (unsigned)W;
+    r /= (unsigned)W;
+    const unsigned h = r % (unsigned)H, n = r / (unsigned)H;      // output order (n, h, w)
+    out[i] = in[(((size_t)h * N + n) * W + w) * CV + cv];
+  }
+}
+}  // namespace
+
+B2C_API int b2c_rows_to_clips(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, b2c_stream_t s) {
+  const int esz = b2c_precision() ? 4 : 2;
+  B2C_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && (C * esz) % 16 == 0, "rows_to_clips: bad args");
+  const int CV = C * esz / 16;
+  const long long total = (long long)N * H * W * CV;
+  B2C_REQUIRE(total < (1LL << 31), "rows_to_clips: tensor too large");
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)b2c_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  rows_to_clips_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const uint4*)in, (uint4*)out, N, H, W, CV, (unsigned)total);
+  b2c_launches_add(1);
+  B2C_LAUNCH_CHECK("rows_to_clips");
   return 0;
 }

@@ -211,6 +211,33 @@ def test_primarycaps_forward_k_split():
     assert torch.equal(outs[1], outs[2])
 
 
+def test_primarycaps_dgrad_rows_major_equals_clip_major():
+    """PrimaryCaps backward with the dgrad GEMM on (row, clip, column) positions + per-tile skipping of padding-only tap rows
+    == the clip-major GEMM: same taps in the same order, the skipped ones only ever add zeros -> bit-identical input gradient,
+    identical weight / bias gradients."""
+    from b200caps import engine
+    from models.capsules_ucf101 import PrimaryCaps
+    torch.manual_seed(21)
+    x = (torch.randn(3, 832, 1, 28, 28, device=dev()) * 0.5)
+    gout = torch.randn(3, 20, 20, 544, device=dev())
+    res = []
+    old = engine.PC_DGRAD_ROWS
+    try:
+        for rows in (False, True):
+            engine.PC_DGRAD_ROWS = rows
+            torch.manual_seed(22)
+            pc = PrimaryCaps(A=832, B=32, K=9, P=4, stride=1).to(dev())
+            xi = x.clone().requires_grad_(True)
+            out = pc(xi)
+            out.backward(gout)
+            res.append((xi.grad.clone(), pc.pose.weight.grad.clone(), pc.a.weight.grad.clone(), pc.pose.bias.grad.clone()))
+    finally:
+        engine.PC_DGRAD_ROWS = old
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert rel(a, b) < 1e-5
+
+
 def test_em_routing_matches_reference_golden():
     """fwd + bwd of the fused routing kernel against the REFERENCE's own outputs / gradients (fp64 golden)."""
     from b200caps import engine
