@@ -49,7 +49,8 @@ typedef struct {
   int32_t lo_t, lo_h, lo_w; /* per-dimension minimum tap offset (lower corner of the im2col TMA box) */
   int32_t h_block;          /* 0, or > 0: the taps come in consecutive blocks of h_block taps that share (dt, dh), dt the same for
                                all, dh monotonic -- lets a tile skip the blocks whose source rows are padding for all its rows;
-                               < 0: blocks of -h_block taps share dt (dt monotonic): the same along the T axis */
+                               < 0: blocks of -h_block taps share dt (dt monotonic) and walk the same monotonic dh inside every
+                               block: whole blocks are skipped along the T axis and a sub-range inside them along the H axis */
   int32_t pad_;
 } b2c_conv_class;
 
@@ -275,11 +276,12 @@ int b2c_em_routing_bwd_state(const float* caps, const float* W, const float* bet
  * g * (col >= 512 ? a(1-a) : 1); dbias[544] += column sums (first 512: pose bias, last 32: a bias). */
 int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* dbias, int64_t rows, int32_t dz_pitch,
                              b2c_stream_t s);
-/* the same, also writing dz with image rows outermost: dz_rows[(h * N + n) * Wq + w] = dz[(n * Hq + h) * Wq + w] (operand of the
- * rows-major PrimaryCaps dgrad, whose tiles then hold one image row of several clips and skip their padding-only tap rows) */
+/* the same, also writing dz with the clips innermost: dz_rows[(h * Wq + w) * N + n] = dz[(n * Hq + h) * Wq + w] (operand of the
+ * rows-major PrimaryCaps dgrad, whose tiles then hold a few columns of one image row of all clips and skip the tap rows /
+ * tap columns that are padding for them) */
 int b2c_primarycaps_bwd_prep2(const float* g, const float* out, void* dz, void* dz_rows, float* dbias, int32_t N, int32_t Hq,
                               int32_t Wq, int32_t dz_pitch, b2c_stream_t s);
-/* (H, N, W, C) -> (N, H, W, C) row permutation of an activation tensor (C % 8 == 0): result of the rows-major dgrad back to
+/* (H, W, N, C) -> (N, H, W, C) row permutation of an activation tensor (C % 8 == 0): result of the rows-major dgrad back to
  * clip-major order */
 int b2c_rows_to_clips(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, b2c_stream_t s);
 /* PrimaryCaps epilogue for the K-split forward: the GEMM's K dimension (the 81 taps) runs as `nslice` scheduling classes

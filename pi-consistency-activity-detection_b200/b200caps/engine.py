@@ -806,11 +806,12 @@ class FusedConvLayer:
         return pl
 
     def rows_major_dgrad(self, in_dims, N: int) -> ConvPlan:
-        """dgrad plan of a 2-D layer (T = 1) with the image rows on the kernel's T axis and the N clips on its H axis: GEMM
-        positions then run (row, clip, column), every 128-position tile holds ONE image row of several clips, and the
-        tiles skip the tap rows that are padding for that row (b2c_conv_class.h_block < 0).  PrimaryCaps' 9 x 9 'valid'
-        convolution reads a 20 x 20 gradient from 28 x 28 positions: 29 % of its (tap row, position) pairs are such
-        padding.  Same taps in the same order as the clip-major plan, so both share one packed operand."""
+        """dgrad plan of a 2-D layer (T = 1) with the image rows on the kernel's T axis, the image columns on its H axis and
+        the N clips on its W axis: GEMM positions then run (row, column, clip), a 128-position tile holds 128 / N columns of
+        ONE image row of all clips, and the tiles skip the tap rows and tap columns that are padding for them
+        (b2c_conv_class.h_block < 0).  PrimaryCaps' 9 x 9 'valid' convolution reads a 20 x 20 gradient from 28 x 28
+        positions: 49 % of its (tap, position) pairs are such padding.  Same taps in the same order as the clip-major
+        plan, so both share one packed operand."""
         in_dims = tuple(int(v) for v in in_dims)
         key = ("rows", in_dims, int(N))
         pl = self.plans.get(key)
@@ -818,10 +819,10 @@ class FusedConvLayer:
         if pl is None:
             sp = base.spec
             assert in_dims[0] == 1 and sp.k[0] == 1 and not sp.transposed
-            spec = ConvSpec(sp.Cin, sp.Cout, (sp.k[1], 1, sp.k[2]), (sp.stride[1], 1, sp.stride[2]),
-                            (sp.pad_front[1], 0, sp.pad_front[2]), (sp.pad_back[1], 0, sp.pad_back[2]),
+            spec = ConvSpec(sp.Cin, sp.Cout, (sp.k[1], sp.k[2], 1), (sp.stride[1], sp.stride[2], 1),
+                            (sp.pad_front[1], sp.pad_front[2], 0), (sp.pad_back[1], sp.pad_back[2], 0),
                             Cin_pad=sp.Cin_pad, Cout_pad=sp.Cout_pad)
-            pl = ConvPlan(spec, (in_dims[1], int(N), in_dims[2]))
+            pl = ConvPlan(spec, (in_dims[1], in_dims[2], int(N)))
             pl.rows_major = True
             if self.grad_cpad:
                 pl.dgrad_pack = dict(pl.dgrad_pack, C=self.grad_cpad)
@@ -891,13 +892,13 @@ class PrimaryCapsFn(torch.autograd.Function):
         N = x.shape[0]
         dx = None
         if ctx.needs_input_grad[0] and PC_DGRAD_ROWS and dims[0] == 1:
-            # rows-major dgrad (FusedConvLayer.rows_major_dgrad): the prologue also writes dz with image rows outermost,
-            # the GEMM runs on (row, clip, column) positions and skips padding-only tap rows, the result is permuted back
+            # rows-major dgrad (FusedConvLayer.rows_major_dgrad): the prologue also writes dz with the clips innermost, the
+            # GEMM runs on (row, column, clip) positions and skips padding-only tap rows / columns, the result is permuted back
             Hq, Wq = out.shape[2], out.shape[3]
-            dzb_r = alloc((1, Hq, N, Wq, cg), dtype=act_dtype(), device=out.device)
+            dzb_r = alloc((1, Hq, Wq, N, cg), dtype=act_dtype(), device=out.device)
             ops.primarycaps_bwd_prep2(g, out, dzb, dzb_r, dbias, N, Hq, Wq, cg)
             plr = layer.rows_major_dgrad(dims, N)
-            dxr = torch.empty((1, dims[1], N, dims[2], x.shape[-1]), dtype=act_dtype(), device=x.device)
+            dxr = torch.empty((1, dims[1], dims[2], N, x.shape[-1]), dtype=act_dtype(), device=x.device)
             ops.conv_fprop(plr, "dgrad", View(dzb_r), View(dxr))
             dx = torch.empty_like(x)
             ops.rows_to_clips(dxr, dx, N, dims[1], dims[2], x.shape[-1])

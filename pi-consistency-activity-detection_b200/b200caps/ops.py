@@ -375,13 +375,13 @@ def primarycaps_finish(part, bias, out):
 
 
 def primarycaps_bwd_prep2(g, out, dz, dz_rows, dbias, N, Hq, Wq, dz_pitch=544):
-    """primarycaps_bwd_prep that also writes dz with image rows outermost (h, n, w) for the rows-major dgrad"""
+    """primarycaps_bwd_prep that also writes dz in (h, w, n) order for the rows-major dgrad"""
     _bw("b2c_primarycaps_bwd_prep2", N * Hq * Wq * (544 * 8 + 2 * dz_pitch * dz.element_size()), _p(g), _p(out), _p(dz), _p(dz_rows),
         _p(dbias), N, Hq, Wq, dz_pitch, stream())
 
 
 def rows_to_clips(src, dst, N, H, W, C):
-    """(H, N, W, C) -> (N, H, W, C)"""
+    """(H, W, N, C) -> (N, H, W, C)"""
     _bw("b2c_rows_to_clips", 2 * N * H * W * C * src.element_size(), _p(src), _p(dst), N, H, W, C, stream())
 
 

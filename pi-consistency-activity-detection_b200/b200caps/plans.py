@@ -309,8 +309,9 @@ class ConvPlan:
 
 
 def t_block_of(taps) -> int:
-    """Taps per block of constant dt when the tap list is such blocks with strictly monotonic dt (a layer whose image rows
-    sit on the T axis, ConvPlan.rows_major), else 0."""
+    """Taps per block of constant dt when the tap list is such blocks with strictly monotonic dt, every block walking the
+    same strictly monotonic dh at one dw (a 2-D layer with its image rows on the T axis and its columns on the H axis,
+    ConvPlan.rows_major), else 0."""
     if len(taps) < 2:
         return 0
     nw = 1
@@ -319,14 +320,14 @@ def t_block_of(taps) -> int:
     if len(taps) % nw or nw == len(taps):
         return 0
     dts = []
+    inner = [t[1] for t in taps[:nw]]
     for b in range(len(taps) // nw):
         blk = taps[b * nw:(b + 1) * nw]
-        if len({t[0] for t in blk}) != 1:
+        if len({t[0] for t in blk}) != 1 or [t[1] for t in blk] != inner or len({t[2] for t in blk}) != 1:
             return 0
         dts.append(blk[0][0])
-    inc = all(b > a for a, b in zip(dts, dts[1:]))
-    dec = all(b < a for a, b in zip(dts, dts[1:]))
-    return nw if (inc or dec) else 0
+    mono = lambda v: all(b > a for a, b in zip(v, v[1:])) or all(b < a for a, b in zip(v, v[1:])) or len(v) == 1
+    return nw if (mono(dts) and mono(inner)) else 0
 
 
 def h_block_of(taps) -> int:

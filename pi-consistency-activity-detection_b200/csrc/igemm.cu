@@ -191,19 +191,23 @@ __device__ __forceinline__ TileInfo decode_tile(const TileSched& ts, int nclass,
 // of the unit contribute nothing (TMA would zero-fill them) -- the valid blocks are a contiguous range.  Producer and MMA
 // issuer call this with the same arguments.
 __device__ __forceinline__ void tap_range(const b2c_conv_desc& d, const b2c_conv_class& cc, const int32_t* taps, unsigned m_first,
-                                          unsigned m_last, const FastDiv* fd3, int& lo, int& hi) {
+                                          unsigned m_last, const FastDiv* fd3, int& lo, int& hi, int& jlo, int& jhi) {
   lo = 0;
   hi = cc.ntaps;
+  jlo = 0;
+  jhi = 0x7fffffff;                        // [jlo, jhi): taps kept INSIDE every block (h_block < 0 mode only)
   if (cc.h_block == 0) return;
   if (cc.h_block < 0) {
-    // blocks of |h_block| taps share one T offset (a 2-D layer presented with its image rows on the T axis and the clips
-    // on the H axis, so that every 128-position tile holds ONE image row of several clips: plans.ConvPlan rows-major)
+    // Blocks of |h_block| taps share one T offset, the taps inside a block walk the H offsets: a 2-D layer presented with
+    // its image rows on the T axis, its image columns on the H axis and the clips on the W axis, so that a 128-position
+    // tile holds a few columns of ONE image row of all clips (plans.ConvPlan rows-major).  Tap rows that are padding for
+    // that image row are skipped as whole blocks, tap columns that are padding for all of the tile's columns inside them.
     const int hb = -cc.h_block;
-    uint32_t r, t0, t1;
+    uint32_t r, h0, h1, t0, t1;
     uint32_t q0 = fdivmod(m_first, fd3[0], r);
     uint32_t q1 = fdivmod(m_last, fd3[0], r);
-    q0 = fdivmod(q0, fd3[1], r);
-    q1 = fdivmod(q1, fd3[1], r);
+    q0 = fdivmod(q0, fd3[1], h0);
+    q1 = fdivmod(q1, fd3[1], h1);
     q0 = fdivmod(q0, fd3[2], t0);
     q1 = fdivmod(q1, fd3[2], t1);
     if (q0 != q1) return;                  // the unit straddles samples
@@ -220,6 +224,20 @@ __device__ __forceinline__ void tap_range(const b2c_conv_desc& d, const b2c_conv
     if (first < 0) first = last = 0;
     lo = first * hb;
     hi = (last + 1) * hb;
+    if (t0 == t1) {                        // one image row: its columns h0..h1 bound the useful H offsets
+      int f2 = -1, l2 = -1;
+      for (int j = 0; j < hb; ++j) {
+        const int dh = tap_dh(taps[j]);    // (every block walks the same H offsets: host-checked product order)
+        const bool ok = (int)h1 * d.si_h + dh >= 0 && (int)h0 * d.si_h + dh <= d.Hi - 1;
+        if (ok) {
+          if (f2 < 0) f2 = j;
+          l2 = j;
+        }
+      }
+      if (f2 < 0) f2 = l2 = 0;
+      jlo = f2;
+      jhi = l2 + 1;
+    }
     return;
   }
   uint32_t r0, r1, h0, h1;
@@ -401,14 +419,19 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
         const uint8_t* wtile = reinterpret_cast<const uint8_t*>(cc.w) + (size_t)ti.n_idx * nkb * (size_t)b_tile_bytes +
                                (size_t)bn_i[0] * (size_t)d.w_sample_stride;
         const CUtensorMap* map = &maps.a[ti.cls];
-        int tp_lo, tp_hi;
+        int tp_lo, tp_hi, tj_lo, tj_hi;
         {
           unsigned m_last = (unsigned)ti.m0 + (unsigned)(MT * kTileM) - 1u;
           if (m_last >= Mtot) m_last = Mtot - 1u;
-          tap_range(d, cc, taps, (unsigned)ti.m0, m_last, s_fd + 3 * ti.cls, tp_lo, tp_hi);
+          tap_range(d, cc, taps, (unsigned)ti.m0, m_last, s_fd + 3 * ti.cls, tp_lo, tp_hi, tj_lo, tj_hi);
         }
-        int kb = tp_lo * cblocks;
+        const int hbk = cc.h_block < 0 ? -cc.h_block : 0;
         for (int tp = tp_lo; tp < tp_hi; ++tp) {
+          if (hbk) {                       // inside-block sub-range (tap columns that are padding for the whole tile)
+            const int j = tp % hbk;
+            if (j < tj_lo || j >= tj_hi) continue;
+          }
+          int kb = tp * cblocks;
           const int32_t tv = taps[tp];
           const uint16_t ow = (uint16_t)(tap_dw(tv) - cc.lo_w), oh = (uint16_t)(tap_dh(tv) - cc.lo_h),
                          ot = (uint16_t)(tap_dt(tv) - cc.lo_t);
@@ -537,11 +560,17 @@ __global__ void __launch_bounds__(kFpropThreads, 1) igemm_fprop_kernel(const __g
       const unsigned Mtot = (unsigned)((long long)d.N * cc.Qt * cc.Qh * cc.Qw);
       int nkb = (cc.ntaps * k_pitch + kBK - 1) / kBK;
       if (use_tma && cc.h_block != 0) {
-        int tp_lo, tp_hi;
+        int tp_lo, tp_hi, tj_lo, tj_hi;
         unsigned m_last = (unsigned)ti.m0 + (unsigned)(MT * kTileM) - 1u;
         if (m_last >= Mtot) m_last = Mtot - 1u;
-        tap_range(d, cc, s_taps + tap_off[ti.cls], (unsigned)ti.m0, m_last, s_fd + 3 * ti.cls, tp_lo, tp_hi);
-        nkb = (tp_hi - tp_lo) * (k_pitch / kBK);
+        tap_range(d, cc, s_taps + tap_off[ti.cls], (unsigned)ti.m0, m_last, s_fd + 3 * ti.cls, tp_lo, tp_hi, tj_lo, tj_hi);
+        int ntp = tp_hi - tp_lo;
+        if (cc.h_block < 0) {
+          const int hbk = -cc.h_block;
+          const int jh = tj_hi < hbk ? tj_hi : hbk;
+          ntp = (ntp / hbk) * (jh - tj_lo);
+        }
+        nkb = ntp * (k_pitch / kBK);
       }
       const int nvalid = (MT > 1 && (unsigned)ti.m0 + (unsigned)kTileM < Mtot) ? 2 : 1;
       B2C_PROF_DECL(w1); B2C_PROF_START(w1);

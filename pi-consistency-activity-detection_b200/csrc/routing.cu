@@ -1220,7 +1220,7 @@ __global__ void __launch_bounds__(256) primarycaps_bwd_prep_kernel(const float* 
         const int L = Hq * Wq;
         const int n = (int)(r / L), l = (int)(r - (long long)n * L);
         const int h = l / Wq, w = l - h * Wq;
-        store8_act(dz_rows + ((long long)(h * Nc + n) * Wq + w) * dz_pitch + cg * 8, v);
+        store8_act(dz_rows + ((long long)(h * Wq + w) * Nc + n) * dz_pitch + cg * 8, v);
       }
     }
   }
@@ -1502,7 +1502,7 @@ B2C_API int b2c_primarycaps_bwd_prep2(const float* g, const float* out, void* dz
 }
 
 namespace {
-// (H, N, W, C) -> (N, H, W, C): one 16-byte vector per thread
+// (H, W, N, C) -> (N, H, W, C): one 16-byte vector per thread
 __global__ void __launch_bounds__(256) rows_to_clips_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W,
                                                             int CV, unsigned total) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -1511,7 +1511,7 @@ __global__ void __launch_bounds__(256) rows_to_clips_kernel(const uint4* __restr
     const unsigned w = r % (unsigned)W;
     r /= (unsigned)W;
     const unsigned h = r % (unsigned)H, n = r / (unsigned)H;      // output order (n, h, w)
-    out[i] = in[(((size_t)h * N + n) * W + w) * CV + cv];
+    out[i] = in[(((size_t)h * W + w) * N + n) * CV + cv];
   }
 }
 }  // namespace
