@@ -180,3 +180,23 @@ def test_split_fprop_k_partitions_the_taps():
     p1 = ConvPlan(ConvSpec(832, 544, (1, 9, 9)), (1, 28, 28))
     p1.split_fprop_k(1)
     assert len(p1.fprop) == 1 and not hasattr(p1, "fprop_out_dims")
+
+
+def test_rows_major_plan_shares_the_packed_operand_and_marks_tap_blocks():
+    """FusedConvLayer.rows_major_dgrad's geometry (PrimaryCaps dgrad): the layer with its image rows on T, columns on H, clips
+    on W has the same taps in the same order as the clip-major plan (so both read one packed operand), its tap list is
+    blocks of constant dt walking one monotonic dh sequence (what b2c_conv_class.h_block < 0 promises the kernel), and the
+    fraction of (tap, position) pairs a perfect skipper would keep is 51 %."""
+    from b200caps.plans import ConvPlan, ConvSpec, t_block_of, h_block_of
+    base = ConvPlan(ConvSpec(832, 544, (1, 9, 9)), (1, 28, 28))
+    rows = ConvPlan(ConvSpec(832, 544, (9, 9, 1)), (28, 28, 32))
+    assert rows.out_dims == (20, 20, 32) and len(rows.dgrad) == len(base.dgrad) == 1
+    assert rows.dgrad[0].wtap == base.dgrad[0].wtap
+    assert [(t[0], t[1]) for t in rows.dgrad[0].taps] == [(t[1], t[2]) for t in base.dgrad[0].taps]
+    assert t_block_of(rows.dgrad[0].taps) == 9 and rows.dgrad[0].Q == (28, 28, 32)
+    # the clip-major tap list is no T-block list (one dt), and arbitrary lists are rejected
+    assert t_block_of(base.dgrad[0].taps) == 0
+    assert t_block_of([(0, 0, 0), (0, -1, 0), (-1, 0, 0), (-1, -2, 0)]) == 0
+    # useful (tap, position) pairs of the 'valid' 9x9 gradient: per axis sum_x #{k: 0 <= x - k <= 19} = 180 of 28 * 9
+    per_axis = sum(sum(1 for k in range(9) if 0 <= x - k <= 19) for x in range(28))
+    assert per_axis == 180 and abs((per_axis / 252.0) ** 2 - 0.51) < 0.005
