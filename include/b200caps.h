@@ -281,9 +281,12 @@ int b2c_primarycaps_bwd_prep(const float* g, const float* out, void* dz, float* 
  * tap columns that are padding for them) */
 int b2c_primarycaps_bwd_prep2(const float* g, const float* out, void* dz, void* dz_rows, float* dbias, int32_t N, int32_t Hq,
                               int32_t Wq, int32_t dz_pitch, b2c_stream_t s);
-/* (H, W, N, C) -> (N, H, W, C) row permutation of an activation tensor (C % 8 == 0): result of the rows-major dgrad back to
- * clip-major order */
-int b2c_rows_to_clips(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, b2c_stream_t s);
+/* Row permutations between the clip-major activation layout (a channel window [c_off, c_off + C) of a (N, H, W, Ctot) tensor
+ * with row stride Ctot) and the compact (H, W, N, C) order the rows-major GEMMs work in (C % 8 == 0). */
+int b2c_rows_to_clips(const void* in, void* out, int64_t out_row_stride, int32_t out_c_off, int32_t N, int32_t H, int32_t W, int32_t C,
+                      b2c_stream_t s);
+int b2c_clips_to_rows(const void* in, int64_t in_row_stride, int32_t in_c_off, void* out, int32_t N, int32_t H, int32_t W, int32_t C,
+                      b2c_stream_t s);
 /* PrimaryCaps epilogue for the K-split forward: the GEMM's K dimension (the 81 taps) runs as `nslice` scheduling classes
  * that write their partial sums to frames 0..nslice-1 of part fp32 (N, nslice, L, 544); out[n][l][c] = sum_s part[n][s][l][c]
  * + bias[c], sigmoid on the 32 activation columns (capsules_ucf101.py:43-49).  Fixed summation order: bit-reproducible. */

@@ -81,7 +81,8 @@ _SIGS = {
     "b2c_em_routing_bwd_state": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "b2c_primarycaps_finish": [vp, i32, vp, vp, i32, i32, vp],
     "b2c_primarycaps_bwd_prep2": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
-    "b2c_rows_to_clips": [vp, vp, i32, i32, i32, i32, vp],
+    "b2c_rows_to_clips": [vp, vp, i64, i32, i32, i32, i32, i32, vp],
+    "b2c_clips_to_rows": [vp, i64, i32, vp, i32, i32, i32, i32, vp],
     "b2c_primarycaps_bwd_prep": [vp, vp, vp, vp, i64, i32, vp],
     "b2c_class_mean_fwd": [vp, vp, i32, i32, i32, vp],
     "b2c_pose_mask_fwd": [vp, vp, vp, i32, i32, i32, vp],

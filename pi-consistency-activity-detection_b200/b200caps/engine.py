@@ -193,6 +193,37 @@ class ConvLayer:
         return pl
 
 
+def _rows_major_spec(sp: ConvSpec) -> ConvSpec:
+    """The 2-D layer `sp` (kt = 1) with its image rows on the T axis, its columns on the H axis and nothing along W."""
+    assert sp.k[0] == 1
+    return ConvSpec(sp.Cin, sp.Cout, (sp.k[1], sp.k[2], 1), (sp.stride[1], sp.stride[2], 1), (sp.pad_front[1], sp.pad_front[2], 0),
+                    (sp.pad_back[1], sp.pad_back[2], 0), (sp.out_pad[1], sp.out_pad[2], 0), sp.transposed, Cin_pad=sp.Cin_pad,
+                    Cout_pad=sp.Cout_pad)
+
+
+def _conv_rows_major_fprop(self, in_dims, N: int) -> ConvPlan:
+    """fprop plan of a 2-D layer on (row, column, clip) positions (see FusedConvLayer.rows_major_dgrad): for the transposed
+    9 x 9 convolution `upsample1` (20 x 20 -> 28 x 28) half of the (tap, position) pairs are padding, which the tiles of
+    this order skip.  Shares the packed operand of the clip-major plan."""
+    in_dims = tuple(int(v) for v in in_dims)
+    base = self.packed(in_dims, "fprop")
+    key = ("rows", in_dims, int(N))
+    pl = self.plans.get(key)
+    if pl is None:
+        assert in_dims[0] == 1
+        pl = ConvPlan(_rows_major_spec(base.spec), (in_dims[1], in_dims[2], int(N)))
+        pl.rows_major = True
+        assert [c.wtap for c in pl.fprop] == [c.wtap for c in base.fprop], "rows-major plan must share the packed operand"
+        self.plans[key] = pl
+    pl = pl.to(self.weight.device)
+    for a, b in zip(pl.fprop, base.fprop):
+        a.packed = b.packed
+    return pl
+
+
+ConvLayer.rows_major_fprop = _conv_rows_major_fprop
+
+
 def _bn_fold(gamma, beta, rm, rv):
     """Eval-mode BatchNorm as a per-channel affine: y = conv(x) * s + b (pytorch_i3d.py:80,117 with running statistics)."""
     s = gamma.detach().float() * torch.rsqrt(rv.detach().float() + BN_EPS)
@@ -603,6 +634,10 @@ FUSE_SIBLINGS = os.environ.get("B2C_FUSE_SIBLINGS", "1") != "0"
 PC_KSPLIT = int(os.environ.get("B2C_PC_KSPLIT", "8"))
 # PrimaryCaps dgrad on (row, clip, column) positions with per-tile skipping of padding-only tap rows (B2C_PC_DGRAD_ROWS=0: clip-major)
 PC_DGRAD_ROWS = os.environ.get("B2C_PC_DGRAD_ROWS", "1") != "0"
+# upsample1 forward on (row, column, clip) positions with padding-tap skipping.  Off by default: bit-identical and measured
+# neutral on the step (19.73 vs 19.74 ms) -- the layer's N = 64 tiles are bound by the tensor core's own shared-memory reads,
+# and the two row permutations cost what the skipped taps save.  B2C_UP1_ROWS=1 enables it.
+UP1_ROWS = os.environ.get("B2C_UP1_ROWS", "0") == "1"
 # BatchNorm backward recomputes the ReLU mask from the raw convolution output instead of reading y (B2C_BN_REMASK=0: read y)
 BN_REMASK = os.environ.get("B2C_BN_REMASK", "1") != "0"
 # weight gradients of a fused layer's members in one wgrad launch (B2C_FUSED_WGRAD=0: one launch per member)
@@ -819,10 +854,7 @@ class FusedConvLayer:
         if pl is None:
             sp = base.spec
             assert in_dims[0] == 1 and sp.k[0] == 1 and not sp.transposed
-            spec = ConvSpec(sp.Cin, sp.Cout, (sp.k[1], sp.k[2], 1), (sp.stride[1], sp.stride[2], 1),
-                            (sp.pad_front[1], sp.pad_front[2], 0), (sp.pad_back[1], sp.pad_back[2], 0),
-                            Cin_pad=sp.Cin_pad, Cout_pad=sp.Cout_pad)
-            pl = ConvPlan(spec, (in_dims[1], in_dims[2], int(N)))
+            pl = ConvPlan(_rows_major_spec(sp), (in_dims[1], in_dims[2], int(N)))
             pl.rows_major = True
             if self.grad_cpad:
                 pl.dgrad_pack = dict(pl.dgrad_pack, C=self.grad_cpad)
@@ -901,7 +933,7 @@ class PrimaryCapsFn(torch.autograd.Function):
             dxr = torch.empty((1, dims[1], dims[2], N, x.shape[-1]), dtype=act_dtype(), device=x.device)
             ops.conv_fprop(plr, "dgrad", View(dzb_r), View(dxr))
             dx = torch.empty_like(x)
-            ops.rows_to_clips(dxr, dx, N, dims[1], dims[2], x.shape[-1])
+            ops.rows_to_clips(dxr, View(dx))
         else:
             ops.primarycaps_bwd_prep(g, out, dzb, dbias, rows, cg)
             if ctx.needs_input_grad[0]:
@@ -1004,7 +1036,16 @@ class DecoderFn(torch.autograd.Function):
         T1 = c56.shape[1]          # 2 for 8-frame clips
         H1 = c28.shape[2]          # 28
         cat28 = torch.empty((N, 1, H1, H1, 128), dtype=bf, device=dev)
-        cba_fwd(L["upsample1"], mod.upsample1.bias, View(x0), View(cat28, 0, 64), relu=True)
+        if UP1_ROWS and x0.shape[1] == 1 and L["upsample1"].plan(x0.shape[1:4]).spec.k[0] == 1:
+            # upsample1 (transposed 9 x 9, 20 x 20 -> 28 x 28) on (row, column, clip) positions: tiles skip padding-only taps
+            x0r = torch.empty((1, x0.shape[2], x0.shape[3], N, x0.shape[4]), dtype=bf, device=dev)
+            ops.clips_to_rows(View(x0), x0r)
+            plr = L["upsample1"].rows_major_fprop(x0.shape[1:4], N)
+            y1r = torch.empty((1, H1, H1, N, 64), dtype=bf, device=dev)
+            ops.conv_fprop(plr, "fprop", View(x0r), View(y1r), bias=mod.upsample1.bias.detach(), relu=True)
+            ops.rows_to_clips(y1r, View(cat28, 0, 64))
+        else:
+            cba_fwd(L["upsample1"], mod.upsample1.bias, View(x0), View(cat28, 0, 64), relu=True)
         cba_fwd(L["conv28"], mod.conv28.bias, View(c28), View(cat28, 64, 64), relu=True)
         cat56 = torch.empty((N, T1, 2 * H1, 2 * H1, 128), dtype=bf, device=dev)
         cba_fwd(L["upsample2"], mod.upsample2.bias, View(cat28), View(cat56, 0, 64), relu=True)

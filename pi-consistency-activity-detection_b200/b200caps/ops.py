@@ -380,9 +380,18 @@ def primarycaps_bwd_prep2(g, out, dz, dz_rows, dbias, N, Hq, Wq, dz_pitch=544):
         _p(dbias), N, Hq, Wq, dz_pitch, stream())
 
 
-def rows_to_clips(src, dst, N, H, W, C):
-    """(H, W, N, C) -> (N, H, W, C)"""
-    _bw("b2c_rows_to_clips", 2 * N * H * W * C * src.element_size(), _p(src), _p(dst), N, H, W, C, stream())
+def rows_to_clips(src, dst: View):
+    """compact (1, H, W, N, C) -> the channel window `dst` of a clip-major (N, 1, H, W, Ctot) tensor"""
+    _, H, W, N, C = src.shape
+    assert dst.N == N and dst.dims == (1, H, W) and dst.C == C
+    _bw("b2c_rows_to_clips", 2 * N * H * W * C * src.element_size(), _p(src), dst.ptr, dst.row_stride, dst.c_off, N, H, W, C, stream())
+
+
+def clips_to_rows(src: View, dst):
+    """channel window of a clip-major (N, 1, H, W, Ctot) tensor -> compact (1, H, W, N, C)"""
+    _, H, W, N, C = dst.shape
+    assert src.N == N and src.dims == (1, H, W) and src.C == C
+    _bw("b2c_clips_to_rows", 2 * N * H * W * C * dst.element_size(), src.ptr, src.row_stride, src.c_off, _p(dst), N, H, W, C, stream())
 
 
 def primarycaps_bwd_prep(g, out, dz, dbias, rows, dz_pitch=544):

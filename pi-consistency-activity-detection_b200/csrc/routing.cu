@@ -1502,31 +1502,53 @@ B2C_API int b2c_primarycaps_bwd_prep2(const float* g, const float* out, void* dz
 }
 
 namespace {
-// (H, W, N, C) -> (N, H, W, C): one 16-byte vector per thread
-__global__ void __launch_bounds__(256) rows_to_clips_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W,
-                                                            int CV, unsigned total) {
+// (H, W, N, C) -> (N, H, W, C) channel window of a wider tensor (kToRows: the opposite direction): one 16-byte vector per thread
+template <bool kToRows>
+__global__ void __launch_bounds__(256) rows_clips_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W, int CV,
+                                                         long long clip_rs16, int clip_co16, unsigned total) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     unsigned r = i / (unsigned)CV;
     const unsigned cv = i - r * (unsigned)CV;
     const unsigned w = r % (unsigned)W;
     r /= (unsigned)W;
-    const unsigned h = r % (unsigned)H, n = r / (unsigned)H;      // output order (n, h, w)
-    out[i] = in[(((size_t)h * W + w) * N + n) * CV + cv];
+    const unsigned h = r % (unsigned)H, n = r / (unsigned)H;      // clip-major order (n, h, w)
+    const size_t rows_idx = (((size_t)h * W + w) * N + n) * CV + cv;                              // compact (H, W, N, C)
+    const size_t clip_idx = (((size_t)n * H + h) * W + w) * (size_t)clip_rs16 + clip_co16 + cv;   // view of (N, H, W, Ctot)
+    if (kToRows) out[rows_idx] = in[clip_idx];
+    else out[clip_idx] = in[rows_idx];
   }
 }
-}  // namespace
 
-B2C_API int b2c_rows_to_clips(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, b2c_stream_t s) {
+int rows_clips_launch(bool to_rows, const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int64_t clip_rs, int32_t clip_co,
+                      b2c_stream_t s, const char* what) {
   const int esz = b2c_precision() ? 4 : 2;
-  B2C_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && (C * esz) % 16 == 0, "rows_to_clips: bad args");
+  B2C_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && (C * esz) % 16 == 0 && (clip_rs * esz) % 16 == 0 && (clip_co * esz) % 16 == 0 &&
+                  clip_rs >= clip_co + C,
+              "%s: bad args", what);
   const int CV = C * esz / 16;
   const long long total = (long long)N * H * W * CV;
-  B2C_REQUIRE(total < (1LL << 31), "rows_to_clips: tensor too large");
+  B2C_REQUIRE(total < (1LL << 31), "%s: tensor too large", what);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)b2c_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  rows_to_clips_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const uint4*)in, (uint4*)out, N, H, W, CV, (unsigned)total);
+  const long long rs16 = clip_rs * esz / 16;
+  const int co16 = (int)(clip_co * esz / 16);
+  if (to_rows)
+    rows_clips_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const uint4*)in, (uint4*)out, N, H, W, CV, rs16, co16, (unsigned)total);
+  else
+    rows_clips_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const uint4*)in, (uint4*)out, N, H, W, CV, rs16, co16, (unsigned)total);
   b2c_launches_add(1);
-  B2C_LAUNCH_CHECK("rows_to_clips");
+  B2C_LAUNCH_CHECK(what);
   return 0;
+}
+}  // namespace
+
+B2C_API int b2c_rows_to_clips(const void* in, void* out, int64_t out_row_stride, int32_t out_c_off, int32_t N, int32_t H, int32_t W,
+                              int32_t C, b2c_stream_t s) {
+  return rows_clips_launch(false, in, out, N, H, W, C, out_row_stride, out_c_off, s, "rows_to_clips");
+}
+
+B2C_API int b2c_clips_to_rows(const void* in, int64_t in_row_stride, int32_t in_c_off, void* out, int32_t N, int32_t H, int32_t W,
+                              int32_t C, b2c_stream_t s) {
+  return rows_clips_launch(true, in, out, N, H, W, C, in_row_stride, in_c_off, s, "clips_to_rows");
 }

@@ -238,6 +238,31 @@ def test_primarycaps_dgrad_rows_major_equals_clip_major():
         assert rel(a, b) < 1e-5
 
 
+@pytest.mark.parametrize("N,C16", [(5, 384), (32, 336)])
+def test_upsample1_rows_major_equals_clip_major(N, C16):
+    """upsample1 (transposed 9 x 9, 20 x 20 -> 28 x 28) on (row, column, clip) positions with per-tile padding-tap skipping ==
+    the clip-major GEMM, bit for bit, written into the same concat slot (C16 = 384: UCF101-24, 336: JHMDB-21)."""
+    from b200caps import engine, ops
+    from b200caps.plans import ConvSpec, View
+    torch.manual_seed(31)
+    one, z = (1, 1, 1), (0, 0, 0)
+    w = torch.nn.Parameter(torch.randn(C16, 64, 1, 9, 9, device=dev()) * 0.02)
+    bias = torch.randn(64, device=dev()) * 0.1
+    layer = engine.ConvLayer(w, lambda d: ConvSpec(C16, 64, (1, 9, 9), one, z, z, z, True))
+    x0 = torch.randn(N, 1, 20, 20, C16, device=dev()).bfloat16()
+    cat_a = torch.zeros(N, 1, 28, 28, 128, device=dev(), dtype=torch.bfloat16)
+    engine.cba_fwd(layer, bias, View(x0), View(cat_a, 0, 64), relu=True)
+    cat_b = torch.zeros_like(cat_a)
+    x0r = torch.empty((1, 20, 20, N, C16), dtype=torch.bfloat16, device=dev())
+    ops.clips_to_rows(View(x0), x0r)
+    assert torch.equal(x0r[0], x0[:, 0].permute(1, 2, 0, 3))
+    plr = layer.rows_major_fprop((1, 20, 20), N)
+    y1r = torch.empty((1, 28, 28, N, 64), dtype=torch.bfloat16, device=dev())
+    ops.conv_fprop(plr, "fprop", View(x0r), View(y1r), bias=bias, relu=True)
+    ops.rows_to_clips(y1r, View(cat_b, 0, 64))
+    assert float(cat_a[..., :64].abs().max()) > 0 and torch.equal(cat_a, cat_b)
+
+
 def test_em_routing_matches_reference_golden():
     """fwd + bwd of the fused routing kernel against the REFERENCE's own outputs / gradients (fp64 golden)."""
     from b200caps import engine
